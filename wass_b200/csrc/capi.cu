@@ -1,0 +1,321 @@
+// C ABI of libwassgpu.so (declared in include/wassgpu.h).  Thin: argument checks, a grow-only
+// device arena per handle, kernel launches on the handle's stream.  No CPU fallback anywhere.
+#include "../../include/wassgpu.h"
+#include "sgbm.cuh"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace wsg;
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+};
+
+struct wsg_handle {
+    int device = 0;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    // SGBM arena
+    DevBuf pre1, pre2, C, S, raw, img1, img2, disp, scalars;
+    SgbmPlan plan{};
+    bool have_plan = false;
+    wsg_sgbm_stats stats{};
+    // profiling
+    bool prof = false;
+    float stage_ms[WSG_NUM_STAGES] = {0};
+    int stage_launches[WSG_NUM_STAGES] = {0};
+    std::vector<std::pair<int, std::pair<cudaEvent_t, cudaEvent_t>>> pending;
+    std::vector<cudaEvent_t> ev_pool;
+};
+
+#define CK(h, call)                                                                           \
+    do {                                                                                      \
+        cudaError_t e__ = (call);                                                             \
+        if (e__ != cudaSuccess) {                                                             \
+            (h)->err = std::string(#call) + ": " + cudaGetErrorString(e__);                   \
+            return WSG_ERR_CUDA;                                                              \
+        }                                                                                     \
+    } while (0)
+
+static int ensure(wsg_handle* h, DevBuf& b, size_t bytes)
+{
+    if (bytes <= b.cap) return WSG_OK;
+    if (b.p) { cudaFree(b.p); b.p = nullptr; b.cap = 0; }
+    cudaError_t e = cudaMalloc(&b.p, bytes);
+    if (e != cudaSuccess) {
+        h->err = std::string("cudaMalloc(") + std::to_string(bytes) + "): " + cudaGetErrorString(e);
+        cudaGetLastError();
+        return e == cudaErrorMemoryAllocation ? WSG_ERR_NOMEM : WSG_ERR_CUDA;
+    }
+    b.cap = bytes;
+    return WSG_OK;
+}
+
+struct StageTimer {
+    wsg_handle* h; int stage; cudaEvent_t a = nullptr, b = nullptr;
+    static cudaEvent_t get(wsg_handle* h)
+    {
+        if (!h->ev_pool.empty()) { cudaEvent_t e = h->ev_pool.back(); h->ev_pool.pop_back(); return e; }
+        cudaEvent_t e; cudaEventCreate(&e); return e;
+    }
+    StageTimer(wsg_handle* h_, int s, int launches) : h(h_), stage(s)
+    {
+        h->stage_launches[s] += launches;
+        if (h->prof) { a = get(h); b = get(h); cudaEventRecord(a, h->stream); }
+    }
+    ~StageTimer()
+    {
+        if (h->prof) { cudaEventRecord(b, h->stream); h->pending.push_back({stage, {a, b}}); }
+    }
+};
+
+static void drain_profile(wsg_handle* h)
+{
+    for (auto& pe : h->pending) {
+        cudaEventSynchronize(pe.second.second);
+        float ms = 0;
+        cudaEventElapsedTime(&ms, pe.second.first, pe.second.second);
+        h->stage_ms[pe.first] += ms;
+        h->ev_pool.push_back(pe.second.first);
+        h->ev_pool.push_back(pe.second.second);
+    }
+    h->pending.clear();
+}
+
+extern "C" {
+
+const char* wsg_version(void) { return "wassgpu 0.1.0 (sm_100a)"; }
+
+int wsg_create(int device, wsg_handle** out)
+{
+    if (!out) return WSG_ERR_INVALID_ARG;
+    *out = nullptr;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || device < 0 || device >= n) { cudaGetLastError(); return WSG_ERR_CUDA; }
+    if (cudaSetDevice(device) != cudaSuccess) return WSG_ERR_CUDA;
+    wsg_handle* h = new wsg_handle();
+    h->device = device;
+    if (cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking) != cudaSuccess) { delete h; return WSG_ERR_CUDA; }
+    h->stream = h->own_stream;
+    *out = h;
+    return WSG_OK;
+}
+
+void wsg_destroy(wsg_handle* h)
+{
+    if (!h) return;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    drain_profile(h);
+    for (DevBuf* b : {&h->pre1, &h->pre2, &h->C, &h->S, &h->raw, &h->img1, &h->img2, &h->disp, &h->scalars})
+        if (b->p) cudaFree(b->p);
+    for (auto e : h->ev_pool) cudaEventDestroy(e);
+    cudaStreamDestroy(h->own_stream);
+    delete h;
+}
+
+int wsg_set_stream(wsg_handle* h, void* cuda_stream)
+{
+    if (!h) return WSG_ERR_INVALID_ARG;
+    h->stream = cuda_stream ? (cudaStream_t)cuda_stream : h->own_stream;
+    return WSG_OK;
+}
+
+int wsg_synchronize(wsg_handle* h)
+{
+    if (!h) return WSG_ERR_INVALID_ARG;
+    CK(h, cudaStreamSynchronize(h->stream));
+    return WSG_OK;
+}
+
+const char* wsg_last_error(const wsg_handle* h) { return h ? h->err.c_str() : "null handle"; }
+
+static int make_plan(wsg_handle* h, int rows, int cols, const wsg_sgbm_params* p, SgbmPlan& pl)
+{
+    if (!p || rows <= 0 || cols <= 0) { h->err = "bad image size or null params"; return WSG_ERR_INVALID_ARG; }
+    if (p->numDisparities <= 0 || p->numDisparities % 16 || p->numDisparities > 1280) {
+        h->err = "numDisparities must be a positive multiple of 16, <= 1280"; return WSG_ERR_INVALID_ARG;
+    }
+    if (p->blockSize > 25 || (p->blockSize > 0 && p->blockSize % 2 == 0)) {
+        h->err = "blockSize must be odd and <= 25"; return WSG_ERR_INVALID_ARG;
+    }
+    if (p->mode != WSG_MODE_SGBM && p->mode != WSG_MODE_HH) { h->err = "mode must be 0 (SGBM) or 1 (HH)"; return WSG_ERR_INVALID_ARG; }
+    if (p->speckleWindowSize > 0) { h->err = "speckleWindowSize > 0 is not supported yet (off at WASS defaults)"; return WSG_ERR_INVALID_ARG; }
+    pl.H = rows; pl.W = cols;
+    pl.minD = p->minDisparity; pl.D = p->numDisparities; pl.maxD = pl.minD + pl.D;
+    pl.SW2 = pl.SH2 = p->blockSize > 0 ? p->blockSize / 2 : 1;
+    pl.ftzero = std::max(p->preFilterCap, 15) | 1;
+    pl.P1 = p->P1 > 0 ? p->P1 : 2;
+    pl.P2 = std::max(p->P2 > 0 ? p->P2 : 5, pl.P1 + 1);
+    if (pl.P2 > 32767 || pl.ftzero > 127) { h->err = "P2 must be <= 32767 and preFilterCap <= 127"; return WSG_ERR_INVALID_ARG; }
+    pl.uniq = p->uniquenessRatio >= 0 ? p->uniquenessRatio : 10;
+    pl.d12 = p->disp12MaxDiff > 0 ? p->disp12MaxDiff : 1;
+    pl.minX1 = std::max(pl.maxD, 0);
+    pl.maxX1 = cols + std::min(pl.minD, 0);
+    pl.W1 = pl.maxX1 - pl.minX1;
+    pl.INVALID = (pl.minD - 1) * 16;
+    pl.mode = p->mode;
+    // cv2 raises for images this narrow (stereosgbm.cpp:511); mirror it as an error code
+    if (cols - (pl.minD + pl.D) <= pl.SW2 || pl.W1 <= 0) { h->err = "image too narrow for minDisparity+numDisparities and blockSize"; return WSG_ERR_TOO_SMALL; }
+    const int NV = pl.D / 8;
+    if (NV <= 8) { pl.NL = 8; pl.K = 1; }
+    else if (NV <= 16) { pl.NL = 16; pl.K = 1; }
+    else { pl.NL = 32; pl.K = (NV + 31) / 32; }
+    pl.Dp = pl.NL * pl.K * 8;
+    return WSG_OK;
+}
+
+static int run_sgbm(wsg_handle* h, const uint8_t* d_img1, const uint8_t* d_img2, size_t stride, int16_t* d_disp)
+{
+    const SgbmPlan& pl = h->plan;
+    const size_t npix = (size_t)pl.H * pl.W;
+    const size_t vol = (size_t)pl.H * pl.W1 * pl.Dp * sizeof(int16_t);
+    int rc;
+    if ((rc = ensure(h, h->pre1, npix * sizeof(uint2)))) return rc;
+    if ((rc = ensure(h, h->pre2, npix * sizeof(uint2)))) return rc;
+    if ((rc = ensure(h, h->C, vol))) return rc;
+    if ((rc = ensure(h, h->S, vol))) return rc;
+    if ((rc = ensure(h, h->raw, npix * sizeof(int16_t)))) return rc;
+    if ((rc = ensure(h, h->scalars, 64))) return rc;
+    int launches = 0;
+    CK(h, cudaMemsetAsync(h->scalars.p, 0, 64, h->stream));
+    {
+        StageTimer t(h, WSG_STAGE_PREFILTER, 2);
+        launch_prefilter(d_img1, stride, (uint2*)h->pre1.p, pl, h->stream);
+        launch_prefilter(d_img2, stride, (uint2*)h->pre2.p, pl, h->stream);
+        launches += 2;
+    }
+    {
+        StageTimer t(h, WSG_STAGE_COST, 1);
+        launch_cost((const uint2*)h->pre1.p, (const uint2*)h->pre2.p, (int16_t*)h->C.p, (int*)h->scalars.p, pl, h->stream, &launches);
+    }
+    {
+        const int ndirs = pl.mode == WSG_MODE_HH ? 8 : 5;
+        StageTimer t(h, WSG_STAGE_AGGREGATE, ndirs);
+        for (int r = 0; r < ndirs; ++r)
+            launch_aggregate_dir((const int16_t*)h->C.p, (int16_t*)h->S.p, r, r == 0, pl, h->stream);
+        launches += ndirs;
+    }
+    {
+        StageTimer t(h, WSG_STAGE_WTA, 1);
+        launch_wta((const int16_t*)h->S.p, (int16_t*)h->raw.p, pl, h->stream);
+        launches += 1;
+    }
+    {
+        StageTimer t(h, WSG_STAGE_MEDIAN, 1);
+        launch_median3((const int16_t*)h->raw.p, d_disp, pl.H, pl.W, h->stream);
+        launches += 1;
+    }
+    CK(h, cudaGetLastError());
+    h->stats.kernel_launches = launches;
+    h->stats.width1 = pl.W1;
+    h->stats.d_padded = pl.Dp;
+    h->stats.volume_bytes = (long long)vol;
+    h->have_plan = true;
+    return WSG_OK;
+}
+
+int wsg_sgbm_compute_device(wsg_handle* h, const uint8_t* d_img1, const uint8_t* d_img2, int rows, int cols,
+                            size_t stride, const wsg_sgbm_params* p, int16_t* d_disp16)
+{
+    if (!h) return WSG_ERR_INVALID_ARG;
+    if (!d_img1 || !d_img2 || !d_disp16 || stride < (size_t)std::max(cols, 0)) { h->err = "null pointer or stride < cols"; return WSG_ERR_INVALID_ARG; }
+    CK(h, cudaSetDevice(h->device));
+    SgbmPlan pl{};
+    int rc = make_plan(h, rows, cols, p, pl);
+    if (rc) return rc;
+    h->plan = pl;
+    h->stats.out_of_domain = 0; h->stats.max_cost = 0;
+    return run_sgbm(h, d_img1, d_img2, stride, d_disp16);
+}
+
+int wsg_sgbm_compute(wsg_handle* h, const uint8_t* img1, const uint8_t* img2, int rows, int cols, size_t stride,
+                     const wsg_sgbm_params* p, int16_t* disp16)
+{
+    if (!h) return WSG_ERR_INVALID_ARG;
+    if (!img1 || !img2 || !disp16 || stride < (size_t)std::max(cols, 0)) { h->err = "null pointer or stride < cols"; return WSG_ERR_INVALID_ARG; }
+    CK(h, cudaSetDevice(h->device));
+    SgbmPlan pl{};
+    int rc = make_plan(h, rows, cols, p, pl);
+    if (rc) return rc;
+    h->plan = pl;
+    const size_t npix = (size_t)rows * cols;
+    if ((rc = ensure(h, h->img1, npix))) return rc;
+    if ((rc = ensure(h, h->img2, npix))) return rc;
+    if ((rc = ensure(h, h->disp, npix * sizeof(int16_t)))) return rc;
+    CK(h, cudaMemcpy2DAsync(h->img1.p, cols, img1, stride, cols, rows, cudaMemcpyHostToDevice, h->stream));
+    CK(h, cudaMemcpy2DAsync(h->img2.p, cols, img2, stride, cols, rows, cudaMemcpyHostToDevice, h->stream));
+    rc = run_sgbm(h, (const uint8_t*)h->img1.p, (const uint8_t*)h->img2.p, cols, (int16_t*)h->disp.p);
+    if (rc) return rc;
+    CK(h, cudaMemcpyAsync(disp16, h->disp.p, npix * sizeof(int16_t), cudaMemcpyDeviceToHost, h->stream));
+    CK(h, cudaStreamSynchronize(h->stream));
+    return WSG_OK;
+}
+
+int wsg_sgbm_get_stats(wsg_handle* h, wsg_sgbm_stats* out)
+{
+    if (!h || !out) return WSG_ERR_INVALID_ARG;
+    if (!h->have_plan) { h->err = "no compute yet"; return WSG_ERR_STATE; }
+    int maxc = 0;
+    CK(h, cudaMemcpyAsync(&maxc, h->scalars.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CK(h, cudaStreamSynchronize(h->stream));
+    h->stats.max_cost = maxc;
+    h->stats.out_of_domain = (maxc + h->plan.P2 > 32767) ? 1 : 0;
+    *out = h->stats;
+    return WSG_OK;
+}
+
+int wsg_sgbm_debug_volumes(wsg_handle* h, int16_t* C_host, int16_t* S_host)
+{
+    if (!h) return WSG_ERR_INVALID_ARG;
+    if (!h->have_plan) { h->err = "no compute yet"; return WSG_ERR_STATE; }
+    const SgbmPlan& pl = h->plan;
+    const size_t npx = (size_t)pl.H * pl.W1;
+    std::vector<int16_t> tmp(npx * pl.Dp);
+    for (int which = 0; which < 2; ++which) {
+        int16_t* dst = which ? S_host : C_host;
+        if (!dst) continue;
+        CK(h, cudaMemcpyAsync(tmp.data(), which ? h->S.p : h->C.p, tmp.size() * 2, cudaMemcpyDeviceToHost, h->stream));
+        CK(h, cudaStreamSynchronize(h->stream));
+        for (size_t px = 0; px < npx; ++px)
+            for (int j = 0; j < pl.D / 8; ++j)
+                memcpy(dst + px * pl.D + (size_t)j * 8, tmp.data() + px * pl.Dp + (size_t)vec_slot(j, pl.NL, pl.K) * 8, 16);
+    }
+    return WSG_OK;
+}
+
+int wsg_profile_enable(wsg_handle* h, int enable)
+{
+    if (!h) return WSG_ERR_INVALID_ARG;
+    h->prof = enable != 0;
+    return WSG_OK;
+}
+
+int wsg_profile_reset(wsg_handle* h)
+{
+    if (!h) return WSG_ERR_INVALID_ARG;
+    cudaStreamSynchronize(h->stream);
+    drain_profile(h);
+    for (int i = 0; i < WSG_NUM_STAGES; ++i) { h->stage_ms[i] = 0; h->stage_launches[i] = 0; }
+    return WSG_OK;
+}
+
+int wsg_profile_get(wsg_handle* h, float* ms, int* launches, int n)
+{
+    if (!h || n < 0) return WSG_ERR_INVALID_ARG;
+    CK(h, cudaStreamSynchronize(h->stream));
+    drain_profile(h);
+    for (int i = 0; i < n && i < WSG_NUM_STAGES; ++i) {
+        if (ms) ms[i] = h->stage_ms[i];
+        if (launches) launches[i] = h->stage_launches[i];
+    }
+    return WSG_OK;
+}
+
+}  // extern "C"

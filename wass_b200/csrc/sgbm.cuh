@@ -1,0 +1,37 @@
+// Internal declarations shared by the SGBM kernels and the C ABI (not installed).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace wsg {
+
+// Derived matcher parameters + HBM layout of the C / S volumes.
+struct SgbmPlan {
+    int H, W;                 // image rows / cols (cols = padded width Wp in wass_stereo)
+    int minD, D, maxD;
+    int SW2, SH2;
+    int ftzero;
+    int P1, P2;
+    int uniq, d12;
+    int minX1, maxX1, W1;     // matched column range in image space, W1 = maxX1-minX1
+    int INVALID;              // (minD-1)*16
+    int mode;                 // 0 = 5 paths, 1 = 8 paths
+    // volume layout: int16 [H][W1][Dp]; a pixel's Dp slots are NL*K vectors of 8 disparities.
+    // memory vector slot s = k*NL + l holds logical vector j = l*K + k (disparities 8j..8j+7), so
+    // that lane l of a pixel group owns K*8 consecutive disparities and each of its K loads is
+    // one fully coalesced 16-byte access across the group.
+    int NL, K, Dp;
+};
+
+__host__ __device__ inline int vec_slot(int j, int NL, int K) { return (j % K) * NL + (j / K); }
+
+// kernels (sgbm_kernels.cu)
+void launch_prefilter(const uint8_t* img, size_t stride, uint2* pre, const SgbmPlan& p, cudaStream_t st);
+void launch_cost(const uint2* pre1, const uint2* pre2, int16_t* C, int* maxC, const SgbmPlan& p, cudaStream_t st, int* launches);
+// dir: 0..7 = predecessor offsets (-1,0) (-1,-1) (0,-1) (1,-1) (1,0) (-1,1) (0,1) (1,1)
+void launch_aggregate_dir(const int16_t* C, int16_t* S, int dir, bool first, const SgbmPlan& p, cudaStream_t st);
+void launch_wta(const int16_t* S, int16_t* raw, const SgbmPlan& p, cudaStream_t st);
+void launch_median3(const int16_t* src, int16_t* dst, int rows, int cols, cudaStream_t st);
+int cost_smem_bytes(const SgbmPlan& p);
+
+}  // namespace wsg
