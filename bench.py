@@ -181,7 +181,9 @@ def run_ours(args, rank, world):
     img1, img2 = make_frame(rank)            # frame index = rank (frames shard one per GPU)
     H, Wp = img1.shape
     h = capi.Handle(local)
-    stream = torch.cuda.current_stream()
+    # a dedicated (non-default) torch stream: the library launches on it, torch events time it
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
     h.set_stream(stream.cuda_stream)
 
     d1 = torch.from_numpy(img1).cuda()
