@@ -1,0 +1,411 @@
+"""CPU restatement of the wass_stereo stages around the matcher -- TEST INFRASTRUCTURE ONLY.
+
+Each function cites the reference lines it follows (paths relative to the reference root).  numpy for the
+array arithmetic, explicit Python loops only where the reference's loop order matters (small inputs).
+OpenCV calls of the reference are restated in numpy (cv::solve 3x3, cv::SVD) and pinned against cv2
+in tests/test_oracle_pipeline.py.  Parity of this file is pinned by fixtures generated with
+tests/golden/make_golden.py (cv2 where the reference calls OpenCV) and by analytic ground truth of the
+synthetic generator; the reference executable itself cannot be built here (no OpenCV C++/Boost).
+"""
+import ctypes
+import struct
+import numpy as np
+
+F32 = np.float32
+
+
+# ----------------------------------------------------------------------------------------------
+# disparity clean-up  (src/wass_stereo/wass_stereo.cpp:617-733, 853-928)
+# ----------------------------------------------------------------------------------------------
+def clean_and_convert_disparity(disp16, mindisp, num_disp, disp_offset, scale):
+    """wass_stereo.cpp:714-733"""
+    d = disp16.astype(F32) / F32(16.0)
+    keep = ~((d <= F32(mindisp)) | (d > F32(num_disp)))
+    v = (d + F32(disp_offset)).astype(F32)
+    out = np.zeros(disp16.shape, F32)
+    out[keep] = (v.astype(np.float64) * np.float64(scale)).astype(F32)[keep]
+    return out
+
+
+def matrix_dilate_zero(src):
+    """wass_stereo.cpp:617-662, including the one-column shift of the output pointer."""
+    out = src.copy()
+    H, W = src.shape
+    if H < 3 or W < 3:
+        return out
+    i0, i1 = 1, H - 1          # rows 1..H-2
+    k = np.arange(0, W - 2)    # written column k, neighbourhood centred on k+1
+    T = src[i0 - 1:i1 - 1]
+    B = src[i0 + 1:i1 + 1]
+    Cc = src[i0:i1]
+    # accumulation order of the reference: tm1, tp1, t, bm1, bp1, b, cm1, cp1
+    terms = [T[:, k], T[:, k + 2], T[:, k + 1], B[:, k], B[:, k + 2], B[:, k + 1], Cc[:, k], Cc[:, k + 2]]
+    avg = np.zeros((i1 - i0, k.size), F32)
+    num = np.zeros((i1 - i0, k.size), np.int32)
+    for t in terms:
+        pos = t > 0
+        avg = np.where(pos, (avg + t).astype(F32), avg)
+        num += pos
+    centre_zero = out[i0:i1][:, k] == 0
+    wr = centre_zero & (num > 1)
+    res = (avg / np.maximum(num, 1).astype(F32)).astype(F32)
+    blk = out[i0:i1, 0:W - 2]
+    blk[wr] = res[wr]
+    return out
+
+
+def matrix_erode_zero(src):
+    """wass_stereo.cpp:665-711"""
+    out = src.copy()
+    H, W = src.shape
+    if H >= 3 and W >= 3:
+        z = src == 0
+        zt, zb, zc = z[0:H - 2], z[2:H], z[1:H - 1]
+        anyz = (zt[:, 1:W - 1] | zt[:, 0:W - 2] | zt[:, 2:W] | zb[:, 1:W - 1] | zb[:, 0:W - 2] | zb[:, 2:W] |
+                zc[:, 0:W - 2] | zc[:, 2:W])
+        inner = out[1:H - 1, 1:W - 1]
+        inner[anyz] = 0
+    if H >= 3:
+        out[1:H - 1, 0] = 0
+        out[1:H - 1, W - 1] = 0
+    out[0, :] = 0
+    out[H - 1, :] = 0
+    return out
+
+
+def postprocess_disparity(disp16_roi, mindisp, num_disp, disparity_offset=0, dense_scale=1.0,
+                          dilate_steps=1, erosion_steps=2):
+    """wass_stereo.cpp:853-928 at DENSE_SCALE==1 (both cv::resize calls are exact copies then)."""
+    assert dense_scale == 1.0
+    off = max(disparity_offset, 0)
+    d = clean_and_convert_disparity(disp16_roi, mindisp, num_disp, off, 1.0 / dense_scale)
+    for _ in range(max(dilate_steps, 0)):
+        d = matrix_dilate_zero(d)
+    for _ in range(max(erosion_steps, 0)):
+        d = matrix_erode_zero(d)
+    nn = matrix_erode_zero(d)
+    out = d.copy()
+    out[nn == 0] = 0
+    return out
+
+
+# ----------------------------------------------------------------------------------------------
+# triangulation  (wass_stereo.cpp:299-324, 1039-1386; src/wass_lib/triangulate.hpp:26-72)
+# ----------------------------------------------------------------------------------------------
+def solve3_lu(A, b):
+    """cv::solve(A,b,x,DECOMP_LU) for 3x3: OpenCV's closed-form (Cramer) fast path, in double."""
+    det = (A[0, 0] * (A[1, 1] * A[2, 2] - A[1, 2] * A[2, 1]) - A[0, 1] * (A[1, 0] * A[2, 2] - A[1, 2] * A[2, 0]) +
+           A[0, 2] * (A[1, 0] * A[2, 1] - A[1, 1] * A[2, 0]))
+    if det == 0.0:
+        return np.zeros(3)
+    d = 1.0 / det
+    t0 = d * (b[0] * (A[1, 1] * A[2, 2] - A[1, 2] * A[2, 1]) - A[0, 1] * (b[1] * A[2, 2] - A[1, 2] * b[2]) +
+              A[0, 2] * (b[1] * A[2, 1] - A[1, 1] * b[2]))
+    t1 = d * (A[0, 0] * (b[1] * A[2, 2] - A[1, 2] * b[2]) - b[0] * (A[1, 0] * A[2, 2] - A[1, 2] * A[2, 0]) +
+              A[0, 2] * (A[1, 0] * b[2] - b[1] * A[2, 0]))
+    t2 = d * (A[0, 0] * (A[1, 1] * b[2] - b[1] * A[2, 1]) - A[0, 1] * (A[1, 0] * b[2] - b[1] * A[2, 0]) +
+              b[0] * (A[1, 0] * A[2, 1] - A[1, 1] * A[2, 0]))
+    return np.array([t0, t1, t2])
+
+
+def triangulate_point(p, q, R, T):
+    """src/wass_lib/triangulate.hpp:26-72 (normal equations of the 4x3 system, same summation order)."""
+    Af = np.array([-1.0, 0.0, p[0],
+                   0.0, -1.0, p[1],
+                   q[0] * R[2, 0] - R[0, 0], q[0] * R[2, 1] - R[0, 1], q[0] * R[2, 2] - R[0, 2],
+                   q[1] * R[2, 0] - R[1, 0], q[1] * R[2, 1] - R[1, 1], q[1] * R[2, 2] - R[1, 2]])
+    Bf = np.array([0.0, 0.0, T[0] - T[2] * q[0], T[1] - T[2] * q[1]])
+    A = np.empty(9)
+    A[0] = Af[0] * Af[0] + Af[3] * Af[3] + Af[6] * Af[6] + Af[9] * Af[9]
+    A[1] = Af[0] * Af[1] + Af[3] * Af[4] + Af[10] * Af[9] + Af[6] * Af[7]
+    A[2] = Af[0] * Af[2] + Af[3] * Af[5] + Af[11] * Af[9] + Af[6] * Af[8]
+    A[3] = A[1]
+    A[4] = Af[1] * Af[1] + Af[10] * Af[10] + Af[4] * Af[4] + Af[7] * Af[7]
+    A[5] = Af[10] * Af[11] + Af[1] * Af[2] + Af[4] * Af[5] + Af[7] * Af[8]
+    A[6] = A[2]
+    A[7] = A[5]
+    A[8] = Af[11] * Af[11] + Af[2] * Af[2] + Af[5] * Af[5] + Af[8] * Af[8]
+    b = np.empty(3)
+    b[0] = Af[0] * Bf[0] + Af[3] * Bf[1] + Af[6] * Bf[2] + Af[9] * Bf[3]
+    b[1] = Af[1] * Bf[0] + Af[10] * Bf[3] + Af[4] * Bf[1] + Af[7] * Bf[2]
+    b[2] = Af[2] * Bf[0] + Af[11] * Bf[3] + Af[5] * Bf[1] + Af[8] * Bf[2]
+    return solve3_lu(A.reshape(3, 3), b)
+
+
+def unrectify(uv, Kold, Rrect, Pnew):
+    """wass_stereo.cpp:299-324 (cv::stereoRectify branch)."""
+    x = (uv[0] - Pnew[0, 2]) / Pnew[0, 0]
+    y = (uv[1] - Pnew[1, 2]) / Pnew[1, 1]
+    Rt = Rrect.T
+    v0 = Rt[0, 0] * x + Rt[0, 1] * y + Rt[0, 2] * 1.0
+    v1 = Rt[1, 0] * x + Rt[1, 1] * y + Rt[1, 2] * 1.0
+    v2 = Rt[2, 0] * x + Rt[2, 1] * y + Rt[2, 2] * 1.0
+    v0 /= v2
+    v1 /= v2
+    return np.array([v0 * Kold[0, 0] + Kold[0, 2], v1 * Kold[1, 1] + Kold[1, 2]])
+
+
+def triangulate(disparity, calib, left, right, left_mask=None, right_mask=None, min_angle=20.0,
+                bbox=None, discard_burned=True, disparity_compensation=0, dense_scale=1.0, cam_distance=1.0):
+    """wass_stereo.cpp:1039-1386.  disparity: float32, full rectified size.  calib: dict with
+    K0,K1 (left/right intrinsics after any swap), R,T, R1,R2,P1,P2 (cv::stereoRectify outputs) and
+    roi_left, roi_right = (x,y,w,h).  left/right: original (unrectified) uint8 images.
+    Returns dict(valid bool [h][w], p3d float64 [h][w][3], color uint8 [h][w], n)."""
+    K0, K1, R, T = calib["K0"], calib["K1"], calib["R"], np.asarray(calib["T"], np.float64).reshape(3)
+    R1, R2, P1, P2 = calib["R1"], calib["R2"], calib["P1"], calib["P2"]
+    rlx, rly, rlw, rlh = calib["roi_left"]
+    rrx, rry, rrw, rrh = calib["roi_right"]
+    Hl, Wl = left.shape
+    Hr, Wr = right.shape
+    rect_cols = disparity.shape[1]
+    lm = np.ones(left.shape, np.uint8) if left_mask is None else (left_mask > 0).astype(np.uint8)
+    rm = np.ones(right.shape, np.uint8) if right_mask is None else (right_mask > 0).astype(np.uint8)
+    if discard_burned:
+        lm = lm * (1 - (left > 254).astype(np.uint8))
+        rm = rm * (1 - (right > 254).astype(np.uint8))
+    if bbox is None:
+        tl, br = (0.0, 0.0), (float(Wl), float(Hl))
+    else:
+        tl, br = (bbox[0], bbox[1]), (bbox[2], bbox[3])
+    valid = np.zeros((rrh, rrw), bool)
+    p3d = np.zeros((rrh, rrw, 3), np.float64)
+    color = np.zeros((rrh, rrw), np.uint8)
+    n = 0
+    for yr in range(rry, rry + rrh):
+        for xr in range(rrx, rrx + rrw):
+            dv = disparity[yr, xr]
+            if not dv > 1:
+                continue
+            xl = F32(F32(xr - rrx + rlx) - dv)
+            xl = F32(np.float64(xl) + disparity_compensation / dense_scale)
+            yl = F32(yr)
+            if xl < 0 or xl >= rect_cols:
+                continue
+            pi = unrectify((np.float64(xl), np.float64(yl)), K0, R1, P1)
+            qi = unrectify((np.float64(xr), np.float64(yr)), K1, R2, P2)
+            skip = False
+            if (pi[0] < 1 or pi[0] >= Wl - 1 or pi[1] < 1 or pi[1] >= Hl - 1 or
+                    qi[0] < 1 or qi[0] >= Wr - 1 or qi[1] < 1 or qi[1] >= Hr - 1):
+                continue  # reference sets skip and later indexes masks; out-of-range there is UB -> we stop here
+            p = np.array([(pi[0] - K0[0, 2]) / K0[0, 0], (pi[1] - K0[1, 2]) / K0[1, 1]])
+            q = np.array([(qi[0] - K1[0, 2]) / K1[0, 0], (qi[1] - K1[1, 2]) / K1[1, 1]])
+            if pi[0] <= tl[0] or pi[1] <= tl[1] or pi[0] >= br[0] or pi[1] >= br[1]:
+                skip = True
+            if lm[int(pi[1]), int(pi[0])] == 0:
+                skip = True
+            if rm[int(qi[1]), int(qi[0])] == 0:
+                skip = True
+            if min_angle > 0:
+                a = np.array([p[0], p[1], 1.0])
+                n1 = np.sqrt(a[0] * a[0] + a[1] * a[1] + a[2] * a[2])
+                d1 = a * (1.0 / n1 if n1 else 0.0)
+                b0 = R[0, 0] * q[0] + R[0, 1] * q[1] + R[0, 2] * 1.0 + T[0]
+                b1 = R[1, 0] * q[0] + R[1, 1] * q[1] + R[1, 2] * 1.0 + T[1]
+                b2 = R[2, 0] * q[0] + R[2, 1] * q[1] + R[2, 2] * 1.0 + T[2]
+                n2 = np.sqrt(b0 * b0 + b1 * b1 + b2 * b2)
+                s = 1.0 / n2 if n2 else 0.0
+                d2 = np.array([b0 * s, b1 * s, b2 * s])
+                dot = d1[0] * d2[0] + d1[1] * d2[1] + d1[2] * d2[2]
+                ang = abs(np.arccos(min(max(dot, -1.0), 1.0)) * 57.29577951) if abs(dot) <= 1 else float("nan")
+                if ang < min_angle:
+                    skip = True
+            if skip:
+                continue
+            X = triangulate_point(p, q, R, T)
+            dist = np.sqrt(X[0] * X[0] + X[1] * X[1] + X[2] * X[2])
+            if dist < cam_distance / 10.0 or X[2] < 1.0:
+                continue
+            if dist > cam_distance * 200.0 or X[2] > 1e30:
+                continue
+            u, v = xr - rrx, yr - rry
+            valid[v, u] = True
+            p3d[v, u] = X
+            color[v, u] = right[int(qi[1]), int(qi[0])]
+            n += 1
+    return dict(valid=valid, p3d=p3d, color=color, n=n)
+
+
+# ----------------------------------------------------------------------------------------------
+# PovMesh  (src/wass_stereo/PovMesh.cpp)
+# ----------------------------------------------------------------------------------------------
+def zgap_percentile(valid, z, percentile=99.0):
+    """PovMesh.cpp:888-926"""
+    H, W = valid.shape
+    c = valid[1:H, 1:W - 1]
+    z0 = z[1:H, 1:W - 1]
+    gaps = []
+    for dx in (-1, 0, 1):
+        nb = valid[0:H - 1, 1 + dx:W - 1 + dx]
+        zn = z[0:H - 1, 1 + dx:W - 1 + dx]
+        m = c & nb
+        gaps.append(np.abs(z0[m] - zn[m]))
+    g = np.sort(np.concatenate(gaps))
+    if g.size == 0:
+        return float("nan")
+    idx = int(np.floor(percentile / 100.0 * g.size))
+    return float(g[min(idx, g.size - 1)]) if idx < g.size else float("nan")
+
+
+def biggest_component(valid, z, zgap):
+    """PovMesh.cpp:929-987 (+147-203): 4-connected, edge iff |dz| < zgap; biggest wins, ties go to the
+    component found first by the column-major rescan.  Returns the new valid mask."""
+    from scipy import ndimage  # labels only; equivalence classes via union-find below
+    H, W = valid.shape
+    parent = np.arange(H * W)
+
+    def find(a):
+        while parent[a] != a:
+            parent[a] = parent[parent[a]]
+            a = parent[a]
+        return a
+
+    idx = np.arange(H * W).reshape(H, W)
+    eh = valid[:, :-1] & valid[:, 1:] & (np.abs(z[:, :-1] - z[:, 1:]) < zgap)
+    ev = valid[:-1, :] & valid[1:, :] & (np.abs(z[:-1, :] - z[1:, :]) < zgap)
+    for a, b in list(zip(idx[:, :-1][eh], idx[:, 1:][eh])) + list(zip(idx[:-1, :][ev], idx[1:, :][ev])):
+        ra, rb = find(a), find(b)
+        if ra != rb:
+            parent[max(ra, rb)] = min(ra, rb)
+    roots = np.array([find(a) if valid.flat[a] else -1 for a in range(H * W)])
+    if not valid.any():
+        return valid.copy()
+    labs, counts = np.unique(roots[roots >= 0], return_counts=True)
+    best = counts.max()
+    cand = labs[counts == best]
+    # first found in column-major scan = smallest (u*H + v) over the members of each candidate
+    vv, uu = np.divmod(np.arange(H * W), W)
+    colmajor = uu * H + vv
+    firsts = [colmajor[roots == c].min() for c in cand]
+    win = cand[int(np.argmin(firsts))]
+    return (roots == win).reshape(H, W)
+
+
+class LibcRand:
+    """glibc srand/rand, as the reference uses for RANSAC (wass_stereo.cpp:1864-1872, PovMesh.cpp:680-682)."""
+
+    def __init__(self, seed):
+        self.libc = ctypes.CDLL("libc.so.6")
+        self.libc.srand(ctypes.c_uint(seed))
+
+    def rand(self):
+        return self.libc.rand()
+
+
+def ransac_draw_triples(rng, W, H, rounds):
+    """The draw loop of PovMesh.cpp:678-692 with a DEFINED order (u then v, p1,p2,p3 left to right);
+    the reference's order inside constructor arguments is unspecified by C++.
+    Returns int32 [rounds][6] pixel coordinates (u1,v1,u2,v2,u3,v3) of the rounds that pass the
+    minimum-distance test (each consumes one round)."""
+    out = np.zeros((rounds, 6), np.int32)
+    mind = H * 0.01
+    r = 0
+    while r < rounds:
+        c = [rng.rand() % W, rng.rand() % H, rng.rand() % W, rng.rand() % H, rng.rand() % W, rng.rand() % H]
+        d12 = np.hypot(c[0] - c[2], c[1] - c[3])
+        d23 = np.hypot(c[2] - c[4], c[3] - c[5])
+        d13 = np.hypot(c[0] - c[4], c[1] - c[5])
+        if d12 < mind or d23 < mind or d13 < mind:
+            continue
+        out[r] = c
+        r += 1
+    return out
+
+
+def ransac_find_plane(valid, p3d, triples, threshold):
+    """PovMesh.cpp:665-777 given the drawn triples.  Returns (ok, plane[4], best_inliers)."""
+    H, W = valid.shape
+    P = p3d[valid]
+    best, best_n, best_d = 0, np.zeros(3), 0.0
+    for t in triples:
+        u1, v1, u2, v2, u3, v3 = [int(a) for a in t]
+        if not (valid[v1, u1] and valid[v2, u2] and valid[v3, u3]):
+            continue
+        p1, p2, p3 = p3d[v1, u1], p3d[v2, u2], p3d[v3, u3]
+        n = np.cross(p2 - p1, p3 - p1)
+        n = n / np.sqrt(n[0] * n[0] + n[1] * n[1] + n[2] * n[2])
+        if n[2] < 0:
+            n = n * -1.0
+        d = -(n[0] * p1[0] + n[1] * p1[1] + n[2] * p1[2])
+        dist = np.abs(P[:, 0] * n[0] + P[:, 1] * n[1] + P[:, 2] * n[2] + d)
+        k = int((dist < threshold).sum())
+        if k > best:
+            best, best_n, best_d = k, n, d
+    ok = not (best < (H * W) // 10)
+    return ok, np.array([best_n[0], best_n[1], best_n[2], best_d]), best
+
+
+def crop_plane(valid, p3d, plane, threshold):
+    """PovMesh.cpp:780-815"""
+    d = np.abs(p3d[..., 0] * plane[0] + p3d[..., 1] * plane[1] + p3d[..., 2] * plane[2] + plane[3])
+    return valid & (d < threshold)
+
+
+def refine_plane(valid, p3d, xmin=-9999.0, xmax=9999.0, ymin=-9999.0, ymax=9999.0, max_distance=70.0,
+                 weight_by_distance=True, central_third=False):
+    """PovMesh.cpp:581-660.  Returns (plane[4], n_inliers)."""
+    H, W = valid.shape
+    umin, umax = (W // 4, W * 3 // 4) if central_third else (0, W - 1)
+    vmin, vmax = (H // 4, H * 2 // 3) if central_third else (0, H - 1)
+    sel = np.zeros_like(valid)
+    sel[vmin:vmax + 1, umin:umax + 1] = True
+    P = p3d
+    dist = np.sqrt(P[..., 0] * P[..., 0] + P[..., 1] * P[..., 1] + P[..., 2] * P[..., 2])
+    m = valid & sel & (P[..., 0] > xmin) & (P[..., 0] < xmax) & (P[..., 1] > ymin) & (P[..., 1] < ymax) & (dist < max_distance)
+    pts = P[m]
+    w = dist[m] if weight_by_distance else np.ones(pts.shape[0])
+    wsum = w.sum()
+    c = (pts * w[:, None]).sum(axis=0) / wsum
+    q = pts - c
+    A = (q[:, :, None] * q[:, None, :] * w[:, None, None]).sum(axis=0)
+    _, _, vt = np.linalg.svd(A)
+    n = vt[2]
+    n = n / np.sqrt((n * n).sum())
+    if n[2] < 0:
+        n = -n
+    d = -(n[0] * c[0] + n[1] * c[1] + n[2] * c[2])
+    return np.array([n[0], n[1], n[2], d]), int(m.sum())
+
+
+def rt_from_plane(a, b, c, d):
+    """PovMesh.cpp:1044-1074"""
+    q = (1 - c) / (a * a + b * b)
+    R = np.array([[1 - a * a * q, -a * b * q, -a], [-a * b * q, 1 - b * b * q, -b], [a, b, c]])
+    T = np.array([0.0, 0.0, d])
+    Rinv = R.T.copy()
+    Tinv = Rinv @ (-T)
+    return R, T, Rinv, Tinv
+
+
+def xyz_compressed_bytes(valid, p3d, plane):
+    """PovMesh.cpp:377-460: the bytes of mesh_cam.xyzC."""
+    R, T, Rinv, Tinv = rt_from_plane(*plane)
+    P = p3d[valid]
+    n = P.shape[0]
+    Q = np.stack([R[i, 0] * P[:, 0] + R[i, 1] * P[:, 1] + R[i, 2] * P[:, 2] + T[i] for i in range(3)], axis=1)
+    mn, mx = Q.min(axis=0), Q.max(axis=0)
+    scale = 65535.0 / (mx - mn)
+    q16 = ((Q - mn) * scale).astype(np.uint16)  # C cast: truncation
+    hdr = struct.pack("<I", n) + struct.pack("<3d", *scale) + struct.pack("<3d", *mn)
+    hdr += struct.pack("<9d", *Rinv.reshape(-1)) + struct.pack("<3d", *Tinv)
+    return hdr + q16.astype("<u2").tobytes()
+
+
+def xyz_compressed_decode(buf):
+    """The reader of gridding/wassgridsurface/wass_utils.py:22-35 (second format pin: matlab/load_camera_mesh.m:15-28)."""
+    n = struct.unpack_from("<I", buf, 0)[0]
+    scale = np.array(struct.unpack_from("<3d", buf, 4))
+    mn = np.array(struct.unpack_from("<3d", buf, 28))
+    Rinv = np.array(struct.unpack_from("<9d", buf, 52)).reshape(3, 3)
+    Tinv = np.array(struct.unpack_from("<3d", buf, 124))
+    q = np.frombuffer(buf, "<u2", count=3 * n, offset=148).reshape(n, 3).astype(np.float64)
+    p_plane = q / scale + mn
+    return (Rinv @ p_plane.T).T + Tinv
+
+
+def rectified_calibration_identity(K, T, W, H):
+    """Calibration of the synthetic rig of SURVEY.md §8d (already rectified: R=I, K0=K1, T along +x):
+    what cv::stereoRectify returns there -- R1=R2=I, P1=[K|0], P2=[K|(f*Tx,0,0)], full-image ROIs."""
+    P1 = np.hstack([K, np.zeros((3, 1))])
+    P2 = np.hstack([K, np.array([[K[0, 0] * T[0]], [0.0], [0.0]])])
+    return dict(K0=K.copy(), K1=K.copy(), R=np.eye(3), T=np.asarray(T, np.float64), R1=np.eye(3), R2=np.eye(3),
+                P1=P1, P2=P2, roi_left=(0, 0, W, H), roi_right=(0, 0, W, H))

@@ -5,6 +5,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -167,6 +168,11 @@ static int make_plan(wsg_handle* h, int rows, int cols, const wsg_sgbm_params* p
     if (NV <= 8) { pl.NL = 8; pl.K = 1; }
     else if (NV <= 16) { pl.NL = 16; pl.K = 1; }
     else { pl.NL = 32; pl.K = (NV + 31) / 32; }
+    // tuning override (same results, different lane mapping): WSG_AGG_LANES=8|16 for D=256
+    if (const char* e = getenv("WSG_AGG_LANES")) {
+        const int nl = atoi(e);
+        if (NV == 32 && (nl == 8 || nl == 16)) { pl.NL = nl; pl.K = 32 / nl; }
+    }
     pl.Dp = pl.NL * pl.K * 8;
     return WSG_OK;
 }

@@ -228,25 +228,24 @@ struct AggArgs {
     int H, W1, Dp, D;
     int sx, sy;        // successor step
     int nchains, len;
-    int first;         // 1: S = L (no read)
     unsigned P1p, P2mP1p;
 };
 
-__device__ __forceinline__ uint4 ldg_stream(const int16_t* p)
+__device__ __forceinline__ uint4 ldg_stream(const uint4* p)
 {
     uint4 r;
     asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
                  : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
     return r;
 }
-__device__ __forceinline__ uint4 ldg_rw(const int16_t* p)
+__device__ __forceinline__ uint4 ldg_rw(const uint4* p)
 {
     uint4 r;
     asm volatile("ld.global.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
                  : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
     return r;
 }
-__device__ __forceinline__ void stg_stream(int16_t* p, const uint4& v)
+__device__ __forceinline__ void stg_stream(uint4* p, const uint4& v)
 {
     asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
                  : "memory");
@@ -264,8 +263,40 @@ __device__ __forceinline__ unsigned group_min_u32(unsigned v)
     }
 }
 
-template <int NL, int K, int PF>
-__global__ void __launch_bounds__(128) aggregate_kernel(const int16_t* __restrict__ C, int16_t* __restrict__ S, AggArgs a)
+// One step of the recurrence for one direction.  R: normalised state of the predecessor (in/out),
+// Cw: cost of this pixel, v: L of this pixel (out).  NR packed registers, 2 disparities each.
+template <int NL, int NR, bool HASPAD>
+__device__ __forceinline__ void agg_step(unsigned (&R)[NR], const unsigned (&Cw)[NR], unsigned (&v)[NR], int l,
+                                         unsigned P1p, unsigned P2mP1p, const unsigned* padm)
+{
+    unsigned up = __shfl_up_sync(FULL, R[NR - 1], 1, NL);
+    unsigned dn = __shfl_down_sync(FULL, R[0], 1, NL);
+    if (l == 0) up = SAT2;
+    if (l == NL - 1) dn = SAT2;
+    unsigned q[NR + 1];
+    q[0] = __byte_perm(up, R[0], 0x5432);
+#pragma unroll
+    for (int j = 1; j < NR; ++j) q[j] = __byte_perm(R[j - 1], R[j], 0x5432);
+    q[NR] = __byte_perm(R[NR - 1], dn, 0x5432);
+#pragma unroll
+    for (int j = 0; j < NR; ++j) {
+        unsigned t = __vimin3_s16x2(q[j], q[j + 1], P2mP1p);
+        t = __viaddmin_s16x2(t, P1p, R[j]);
+        v[j] = __viaddmin_u16x2(t, Cw[j], SAT2);
+        if (HASPAD) v[j] |= padm[j / 4];
+    }
+    unsigned m = v[0];
+#pragma unroll
+    for (int j = 1; j < NR; ++j) m = __vmins2(m, v[j]);
+    unsigned mm = min(m & 0xFFFFu, m >> 16);
+    mm = group_min_u32<NL>(mm);
+    const unsigned mpk = mm * 0x10001u;
+#pragma unroll
+    for (int j = 0; j < NR; ++j) R[j] = v[j] - mpk;  // both halves >= mm: no borrow between them
+}
+
+template <int NL, int K, int PF, bool FIRST, bool DIAG, bool HASPAD>
+__global__ void __launch_bounds__(128) aggregate_kernel(const uint4* __restrict__ C, uint4* __restrict__ S, AggArgs a)
 {
     constexpr int NR = 4 * K;  // packed registers of state per lane
     const int gid = (blockIdx.x * blockDim.x + threadIdx.x) / NL;
@@ -277,121 +308,102 @@ __global__ void __launch_bounds__(128) aggregate_kernel(const int16_t* __restric
     unsigned padm[K];
 #pragma unroll
     for (int k = 0; k < K; ++k) padm[k] = ((l * K + k) * 8 >= a.D) ? SAT2 : 0u;
-    const bool has_pad = a.Dp != a.D;
 
-    // chain geometry
-    int px, py;  // prefetch cursor
-    if (a.sy == 0) { py = chain; px = a.sx > 0 ? 0 : a.W1 - 1; }
-    else           { px = chain; py = a.sy > 0 ? 0 : a.H - 1; }
-    int cx = px, cy = py;  // compute cursor
-    const size_t lane_off = (size_t)l * 8;
-
-    auto advance = [&](int& x, int& y) {
-        x += a.sx; y += a.sy;
-        if (a.sy != 0) { if (x >= a.W1) x = 0; else if (x < 0) x = a.W1 - 1; }
+    // cursors in units of 16-byte vectors: idx(x,y) = (y*W1+x)*Dp/8 + lane slot
+    const int Dp8 = a.Dp >> 3;
+    const int dstep = (a.sx + a.sy * a.W1) * Dp8;
+    const int wrapfix = a.W1 * Dp8;
+    int x0, y0;
+    if (a.sy == 0) { y0 = chain; x0 = a.sx > 0 ? 0 : a.W1 - 1; }
+    else           { x0 = chain; y0 = a.sy > 0 ? 0 : a.H - 1; }
+    int xp = x0, ip = (y0 * a.W1 + x0) * Dp8 + l;   // prefetch cursor
+    int xc = xp, ic = ip;                           // compute cursor
+    auto advance = [&](int& x, int& idx) {
+        idx += dstep;
+        if (DIAG) {
+            x += a.sx;
+            if (x >= a.W1) { x = 0; idx -= wrapfix; }
+            else if (x < 0) { x = a.W1 - 1; idx += wrapfix; }
+        }
     };
-    auto offset = [&](int x, int y) -> size_t { return ((size_t)y * a.W1 + x) * a.Dp + lane_off; };
 
     uint4 cb[PF][K], sb[PF][K];
+    int spf = 0;
 #pragma unroll
     for (int u = 0; u < PF; ++u) {
-        if (u < a.len) {
-            const size_t o = offset(px, py);
 #pragma unroll
-            for (int k = 0; k < K; ++k) {
-                cb[u][k] = ldg_stream(C + o + (size_t)k * NL * 8);
-                if (!a.first) sb[u][k] = ldg_rw(S + o + (size_t)k * NL * 8);
-            }
-            advance(px, py);
+        for (int k = 0; k < K; ++k) {
+            cb[u][k] = ldg_stream(C + ip + k * NL);
+            if (!FIRST) sb[u][k] = ldg_rw(S + ip + k * NL);
         }
+        if (spf + 1 < a.len) advance(xp, ip);
+        ++spf;
     }
 
     unsigned R[NR];
 #pragma unroll
     for (int j = 0; j < NR; ++j) R[j] = 0;
 
-    for (int i = 0; i < a.len; i += PF) {
+    for (int base = 0; base < a.len; base += PF) {
 #pragma unroll
         for (int u = 0; u < PF; ++u) {
-            const int step = i + u;
-            if (step < a.len) {
-                unsigned Cw[NR], Sw[NR];
+            const int step = base + u;
+            unsigned Cw[NR], v[NR];
 #pragma unroll
-                for (int k = 0; k < K; ++k) {
-                    Cw[4 * k] = cb[u][k].x; Cw[4 * k + 1] = cb[u][k].y; Cw[4 * k + 2] = cb[u][k].z; Cw[4 * k + 3] = cb[u][k].w;
-                    Sw[4 * k] = sb[u][k].x; Sw[4 * k + 1] = sb[u][k].y; Sw[4 * k + 2] = sb[u][k].z; Sw[4 * k + 3] = sb[u][k].w;
-                }
-                if (step + PF < a.len) {
-                    const size_t o = offset(px, py);
-#pragma unroll
-                    for (int k = 0; k < K; ++k) {
-                        cb[u][k] = ldg_stream(C + o + (size_t)k * NL * 8);
-                        if (!a.first) sb[u][k] = ldg_rw(S + o + (size_t)k * NL * 8);
-                    }
-                    advance(px, py);
-                }
-                // chain restart: first step, or a diagonal chain that just wrapped around the edge
-                const bool restart = (step == 0) || (a.sy != 0 && ((a.sx > 0 && cx == 0) || (a.sx < 0 && cx == a.W1 - 1)));
-                if (restart) {
-#pragma unroll
-                    for (int j = 0; j < NR; ++j) R[j] = 0;
-                }
-                unsigned up = __shfl_up_sync(FULL, R[NR - 1], 1, NL);
-                unsigned dn = __shfl_down_sync(FULL, R[0], 1, NL);
-                if (l == 0) up = SAT2;
-                if (l == NL - 1) dn = SAT2;
-                unsigned q[NR + 1];
-                q[0] = __byte_perm(up, R[0], 0x5432);
-#pragma unroll
-                for (int j = 1; j < NR; ++j) q[j] = __byte_perm(R[j - 1], R[j], 0x5432);
-                q[NR] = __byte_perm(R[NR - 1], dn, 0x5432);
-                unsigned v[NR];
-#pragma unroll
-                for (int j = 0; j < NR; ++j) {
-                    unsigned t = __vimin3_s16x2(q[j], q[j + 1], a.P2mP1p);
-                    t = __viaddmin_s16x2(t, a.P1p, R[j]);
-                    v[j] = __viaddmin_u16x2(t, Cw[j], SAT2);
-                }
-                if (has_pad) {
-#pragma unroll
-                    for (int j = 0; j < NR; ++j) v[j] |= padm[j / 4];
-                }
-                unsigned m = v[0];
-#pragma unroll
-                for (int j = 1; j < NR; ++j) m = __vmins2(m, v[j]);
-                unsigned mm = min(m & 0xFFFFu, m >> 16);
-                mm = group_min_u32<NL>(mm);
-                const unsigned negp = ((0u - mm) & 0xFFFFu) * 0x10001u;
-                const size_t o = offset(cx, cy);
-#pragma unroll
-                for (int k = 0; k < K; ++k) {
-                    uint4 out;
-                    if (a.first) {
-                        out = make_uint4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
-                    } else {
-                        out.x = __viaddmin_u16x2(Sw[4 * k], v[4 * k], SAT2);
-                        out.y = __viaddmin_u16x2(Sw[4 * k + 1], v[4 * k + 1], SAT2);
-                        out.z = __viaddmin_u16x2(Sw[4 * k + 2], v[4 * k + 2], SAT2);
-                        out.w = __viaddmin_u16x2(Sw[4 * k + 3], v[4 * k + 3], SAT2);
-                    }
-                    if (active) stg_stream(S + o + (size_t)k * NL * 8, out);
-                }
-#pragma unroll
-                for (int j = 0; j < NR; ++j) R[j] = __vadd2(v[j], negp);
-                advance(cx, cy);
+            for (int k = 0; k < K; ++k) {
+                Cw[4 * k] = cb[u][k].x; Cw[4 * k + 1] = cb[u][k].y; Cw[4 * k + 2] = cb[u][k].z; Cw[4 * k + 3] = cb[u][k].w;
             }
+            if (DIAG) {
+                // a diagonal chain that just wrapped around the image edge restarts (out-of-image predecessor)
+                const bool restart = (a.sx > 0 && xc == 0) || (a.sx < 0 && xc == a.W1 - 1);
+#pragma unroll
+                for (int j = 0; j < NR; ++j) R[j] = restart ? 0u : R[j];
+            }
+            agg_step<NL, NR, HASPAD>(R, Cw, v, l, a.P1p, a.P2mP1p, padm);
+            const bool st = active && step < a.len;
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                uint4 out;
+                if (FIRST) {
+                    out = make_uint4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+                } else {
+                    out.x = __viaddmin_u16x2(sb[u][k].x, v[4 * k], SAT2);
+                    out.y = __viaddmin_u16x2(sb[u][k].y, v[4 * k + 1], SAT2);
+                    out.z = __viaddmin_u16x2(sb[u][k].z, v[4 * k + 2], SAT2);
+                    out.w = __viaddmin_u16x2(sb[u][k].w, v[4 * k + 3], SAT2);
+                }
+                if (st) stg_stream(S + ic + k * NL, out);
+            }
+            advance(xc, ic);
+            // refill this stage for step + PF (cursor frozen at the last pixel once the chain is exhausted)
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                cb[u][k] = ldg_stream(C + ip + k * NL);
+                if (!FIRST) sb[u][k] = ldg_rw(S + ip + k * NL);
+            }
+            if (spf + 1 < a.len) advance(xp, ip);
+            ++spf;
         }
     }
 }
 
-template <int NL, int K>
-static void launch_agg_t(const int16_t* C, int16_t* S, const AggArgs& a, cudaStream_t st)
+template <int NL, int K, bool HASPAD>
+static void launch_agg_t(const int16_t* C, int16_t* S, const AggArgs& a, bool first, cudaStream_t st)
 {
     constexpr int PF = K == 1 ? 6 : (K == 2 ? 3 : 2);
     const int threads = 128;
     const long long total = (long long)a.nchains * NL;
     const int blocks = (int)((total + threads - 1) / threads);
-    aggregate_kernel<NL, K, PF><<<blocks, threads, 0, st>>>(C, S, a);
+    const uint4* c = reinterpret_cast<const uint4*>(C);
+    uint4* s = reinterpret_cast<uint4*>(S);
+    const bool diag = a.sx != 0 && a.sy != 0;
+    if (first) {
+        if (diag) aggregate_kernel<NL, K, PF, true, true, HASPAD><<<blocks, threads, 0, st>>>(c, s, a);
+        else      aggregate_kernel<NL, K, PF, true, false, HASPAD><<<blocks, threads, 0, st>>>(c, s, a);
+    } else {
+        if (diag) aggregate_kernel<NL, K, PF, false, true, HASPAD><<<blocks, threads, 0, st>>>(c, s, a);
+        else      aggregate_kernel<NL, K, PF, false, false, HASPAD><<<blocks, threads, 0, st>>>(c, s, a);
+    }
 }
 
 void launch_aggregate_dir(const int16_t* C, int16_t* S, int dir, bool first, const SgbmPlan& p, cudaStream_t st)
@@ -402,12 +414,17 @@ void launch_aggregate_dir(const int16_t* C, int16_t* S, int dir, bool first, con
     a.sx = -pred[dir][0]; a.sy = -pred[dir][1];
     a.nchains = a.sy == 0 ? p.H : p.W1;
     a.len = a.sy == 0 ? p.W1 : p.H;
-    a.first = first ? 1 : 0;
     a.P1p = ((unsigned)p.P1 & 0xFFFFu) * 0x10001u;
     a.P2mP1p = ((unsigned)(p.P2 - p.P1) & 0xFFFFu) * 0x10001u;
-#define WSG_AGG_CASE(nl, k) if (p.NL == nl && p.K == k) { launch_agg_t<nl, k>(C, S, a, st); return; }
+    const bool pad = p.Dp != p.D;
+#define WSG_AGG_CASE(nl, k)                                                    \
+    if (p.NL == nl && p.K == k) {                                              \
+        if (pad) launch_agg_t<nl, k, true>(C, S, a, first, st);               \
+        else     launch_agg_t<nl, k, false>(C, S, a, first, st);              \
+        return;                                                                \
+    }
     WSG_AGG_CASE(8, 1) WSG_AGG_CASE(16, 1) WSG_AGG_CASE(32, 1) WSG_AGG_CASE(32, 2)
-    WSG_AGG_CASE(32, 3) WSG_AGG_CASE(32, 4) WSG_AGG_CASE(32, 5)
+    WSG_AGG_CASE(32, 3) WSG_AGG_CASE(32, 4) WSG_AGG_CASE(32, 5) WSG_AGG_CASE(8, 4) WSG_AGG_CASE(16, 2)
 #undef WSG_AGG_CASE
 }
 
@@ -511,7 +528,7 @@ void launch_wta(const int16_t* S, int16_t* raw, const SgbmPlan& p, cudaStream_t 
         return;                                                                                          \
     }
     WSG_WTA_CASE(8, 1) WSG_WTA_CASE(16, 1) WSG_WTA_CASE(32, 1) WSG_WTA_CASE(32, 2)
-    WSG_WTA_CASE(32, 3) WSG_WTA_CASE(32, 4) WSG_WTA_CASE(32, 5)
+    WSG_WTA_CASE(32, 3) WSG_WTA_CASE(32, 4) WSG_WTA_CASE(32, 5) WSG_WTA_CASE(8, 4) WSG_WTA_CASE(16, 2)
 #undef WSG_WTA_CASE
 }
 
