@@ -88,6 +88,129 @@ int wsg_sgbm_get_stats(wsg_handle* h, wsg_sgbm_stats* out);
  * in logical layout [rows][W1][numDisparities] int16.  Either pointer may be NULL. */
 int wsg_sgbm_debug_volumes(wsg_handle* h, int16_t* C_host, int16_t* S_host);
 
+/* ---- dense stereo stage as a whole ------------------------------------------------------------ */
+/* Replaces sgbm_dense_stereo(env), wass_stereo.cpp:764-1020, between the two rectified crops and the
+ * float disparity of the ROI: P1/P2 from WINSIZE, zero padding by numDisparities(+offset) columns,
+ * compute(right,left), crop, clean_and_convert_disparity, DISP_DILATE_STEPS x matrix_dilate_zero,
+ * DISP_EROSION_STEPS x matrix_erode_zero, nearest-neighbour mask (one more erosion).
+ * Field names are the reference's configuration keys (wass_stereo.cpp:742-761). */
+typedef struct wsg_dense_params {
+    int MIN_DISPARITY;
+    int MAX_DISPARITY;            /* = numberOfDisparities (wass_stereo.cpp:768) */
+    int WINSIZE;
+    double DENSE_SCALE;           /* only 1.0 is supported */
+    int DISPARITY_OFFSET;
+    int DISP_DILATE_STEPS;
+    int DISP_EROSION_STEPS;
+    int DENSE_P1_MULT;
+    int DENSE_P2_MULT;
+    int DENSE_UNIQUENESS_RATIO;
+    int DENSE_DISP12MAXDIFF;
+    int DENSE_PREFILTER_CAP;
+    int DENSE_SPECKLE_RANGE;
+    int DENSE_SPECKLE_WINDOW_SIZE;
+    int mode;                     /* WSG_MODE_SGBM (reference default) or WSG_MODE_HH */
+} wsg_dense_params;
+void wsg_dense_params_default(wsg_dense_params* p);
+
+/* left_crop/right_crop: rows x cols uint8 HOST images (the rectified ROI crops, wass_stereo.cpp:607-608).
+ * disp_roi: rows x cols float32 HOST, 0 = invalid.  disp16_roi (optional, may be NULL): the raw
+ * matcher output cropped to the ROI, int16 x16. */
+int wsg_dense_stereo(wsg_handle* h, const uint8_t* left_crop, const uint8_t* right_crop, int rows, int cols,
+                     size_t stride, const wsg_dense_params* p, float* disp_roi, int16_t* disp16_roi);
+
+/* Replaces wass_stereo.cpp:853-928 alone: int16 x16 ROI disparity -> cleaned float32 disparity. HOST pointers. */
+int wsg_disparity_postprocess(wsg_handle* h, const int16_t* disp16_roi, int rows, int cols, int minDisparity,
+                              int numDisparities, int disparityOffset, double denseScale, int dilateSteps,
+                              int erosionSteps, float* disp_roi);
+
+/* ---- triangulation + PovMesh ---------------------------------------------------------------------- */
+/* Calibration after load_data()+rectify() (wass_stereo.cpp:337-613), all row-major doubles.
+ * K0/K1: intrinsics of the LEFT/RIGHT camera after any left-right swap; R,T: pose of right w.r.t. left
+ * (|T| already rescaled to cam_distance); R1,R2,P1,P2: outputs of cv::stereoRectify. */
+typedef struct wsg_calib {
+    double K0[9], K1[9], R[9], T[3];
+    double R1[9], R2[9], P1[12], P2[12];
+    int roi_left[4], roi_right[4];        /* x,y,width,height = roi_comb_left / roi_comb_right */
+    int left_cols, left_rows, right_cols, right_rows;   /* original (undistorted) images */
+    int rect_cols, rect_rows;             /* rectified images */
+} wsg_calib;
+
+typedef struct wsg_tri_params {
+    double TRIANG_MIN_ANGLE;              /* degrees; <= 0 disables */
+    double TRIANG_BBOX_TOP, TRIANG_BBOX_LEFT, TRIANG_BBOX_RIGHT, TRIANG_BBOX_BOTTOM;  /* all >= 0 to enable */
+    int DISCARD_BURNED_AREAS;
+    int disparity_compensation;           /* max(-DISPARITY_OFFSET,0) */
+    double DENSE_SCALE;
+    double cam_distance;                  /* 1.0 in wass_stereo (wass_stereo.cpp:1878) */
+} wsg_tri_params;
+void wsg_tri_params_default(wsg_tri_params* p);
+
+/* Replaces triangulate(env), wass_stereo.cpp:1039-1386.  disparity: rect_rows x rect_cols float32 (HOST);
+ * left/right: the original 8-bit images (HOST); left_mask/right_mask: optional 0/1 masks of the same
+ * sizes (NULL = none).  Creates the handle's device-resident mesh (roi_right.width x roi_right.height
+ * point grid, the PovMesh of the reference) and returns the number of triangulated points. */
+int wsg_triangulate(wsg_handle* h, const float* disparity, const uint8_t* left, const uint8_t* right,
+                    const uint8_t* left_mask, const uint8_t* right_mask, const wsg_calib* calib,
+                    const wsg_tri_params* p, unsigned long long* n_points);
+
+/* Same, but takes the ROI disparity still on the device from the last wsg_dense_stereo call
+ * (paste into the full rectified frame, wass_stereo.cpp:990-991, happens on the device). */
+int wsg_triangulate_from_dense(wsg_handle* h, const uint8_t* left, const uint8_t* right, const uint8_t* left_mask,
+                               const uint8_t* right_mask, const wsg_calib* calib, const wsg_tri_params* p,
+                               unsigned long long* n_points);
+
+/* Test / tooling access to the mesh (PovMesh grid): upload replaces the handle's mesh. xyz: h*w*3 doubles. */
+int wsg_mesh_upload(wsg_handle* h, int width, int height, const uint8_t* valid, const double* xyz, const uint8_t* grey);
+int wsg_mesh_download(wsg_handle* h, uint8_t* valid, double* xyz, uint8_t* grey);
+int wsg_mesh_size(wsg_handle* h, int* width, int* height, unsigned long long* n_valid);
+
+/* PovMesh::compute_zgap_percentile, PovMesh.cpp:888-926 */
+int wsg_mesh_zgap_percentile(wsg_handle* h, double percentile, double* zgap);
+/* PovMesh::cluster_biggest_connected_component, PovMesh.cpp:929-987 */
+int wsg_mesh_biggest_component(wsg_handle* h, double zgap, unsigned long long* n_left);
+/* PovMesh::ransac_find_plane, PovMesh.cpp:665-777.  triples: n x 6 int32 pixel coordinates
+ * (u1,v1,u2,v2,u3,v3) drawn by the caller with libc rand() (see wsg_ransac_draw); *ok = 0 when the
+ * best hypothesis has fewer than width*height/10 inliers. */
+int wsg_mesh_ransac_plane(wsg_handle* h, const int32_t* triples, int n, double threshold, double plane[4], int* ok,
+                          unsigned long long* best_inliers);
+/* The draw loop of PovMesh.cpp:678-692 with a defined argument order (u before v, points 1,2,3 in order):
+ * consumes libc rand(); rounds whose points are closer than 0.01*height are redrawn. Host only. */
+int wsg_ransac_draw(int width, int height, int rounds, int32_t* triples);
+/* PovMesh::crop_plane, PovMesh.cpp:780-815 */
+int wsg_mesh_crop_plane(wsg_handle* h, const double plane[4], double threshold, unsigned long long* n_left);
+/* PovMesh::refine_plane, PovMesh.cpp:581-660 */
+typedef struct wsg_refine_params {
+    double PLANE_REFINE_XMIN, PLANE_REFINE_XMAX, PLANE_REFINE_YMIN, PLANE_REFINE_YMAX;
+    double PLANE_REFINEMENT_MAX_DISTANCE;
+    int PLANE_WEIGHT_PROPORTIONAL_TO_DISTANCE;
+    int PLANE_USE_CENTRAL_THIRD_ONLY;
+} wsg_refine_params;
+void wsg_refine_params_default(wsg_refine_params* p);
+int wsg_mesh_refine_plane(wsg_handle* h, const wsg_refine_params* p, double plane[4], unsigned long long* n_inliers);
+/* PovMesh::RT_from_plane, PovMesh.cpp:1044-1074 (host arithmetic) */
+void wsg_rt_from_plane(const double plane[4], double R[9], double T[3], double Rinv[9], double Tinv[3]);
+/* PovMesh::save_as_xyz_compressed, PovMesh.cpp:377-460: the exact bytes of mesh_cam.xyzC into dst. */
+int wsg_mesh_export_xyzc(wsg_handle* h, const double plane[4], void* dst, size_t capacity, size_t* nbytes);
+/* PovMesh::save_as_xyz_binary, PovMesh.cpp:346-375: the exact bytes of mesh_cam.xyzbin. */
+int wsg_mesh_export_xyzbin(wsg_handle* h, void* dst, size_t capacity, size_t* nbytes);
+
+/* ---- rectification (the step before the hot path) ---------------------- */
+/* cv::stereoRectify(K0, 0, K1, 0, size, R, T, R1, R2, P1, P2, Q, flags=0, alpha=1.0, size, &roi1, &roi2)
+ * exactly as wass_stereo.cpp:541 calls it (zero distortion).  Host arithmetic only. */
+int wsg_stereo_rectify(const double K0[9], const double K1[9], const double R[9], const double T[3], int width, int height,
+                       double R1[9], double R2[9], double P1[12], double P2[12], int roi1[4], int roi2[4]);
+/* cv::initUndistortRectifyMap(K, 0, Rrect, P, size, CV_32FC1) + cv::remap(img, INTER_CUBIC), wass_stereo.cpp:600-604.
+ * img/out: rows x cols uint8 HOST buffers (out is dense). */
+int wsg_rectify_image(wsg_handle* h, const uint8_t* img, int rows, int cols, size_t stride, const double K[9],
+                      const double Rrect[9], const double P[12], uint8_t* out);
+
+/* NaN-aware accumulation of per-frame planes for the sequence mean (what wassgridsurface does with
+ * planes.txt: np.nanmean, gridding/wassgridsurface/wassgridsurface.py:672-678).  acc[5] = sums of a,b,c,d
+ * and the count; all-reduce acc (sum) across ranks, then wsg_plane_mean_finish. Host only. */
+void wsg_plane_mean_accumulate(double acc[5], const double plane[4]);
+void wsg_plane_mean_finish(const double acc[5], double mean[4]);
+
 /* Per-stage device timing (CUDA events on the handle's stream).  enable!=0 turns recording on.
  * Stage ids: see WSG_STAGE_*.  ms[i] receives the accumulated milliseconds of stage i and
  * launches[i] the number of kernel launches since the last wsg_profile_reset. */

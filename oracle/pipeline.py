@@ -404,8 +404,9 @@ def xyz_compressed_decode(buf):
 
 def rectified_calibration_identity(K, T, W, H):
     """Calibration of the synthetic rig of SURVEY.md §8d (already rectified: R=I, K0=K1, T along +x):
-    what cv::stereoRectify returns there -- R1=R2=I, P1=[K|0], P2=[K|(f*Tx,0,0)], full-image ROIs."""
+    what cv::stereoRectify(alpha=1) returns there -- R1=R2=I, P1=[K|0], P2=[K|(f*Tx,0,0)], ROIs (0,0,W-1,H-1)
+    (pinned against cv2 in tests/test_oracle_pipeline.py)."""
     P1 = np.hstack([K, np.zeros((3, 1))])
     P2 = np.hstack([K, np.array([[K[0, 0] * T[0]], [0.0], [0.0]])])
     return dict(K0=K.copy(), K1=K.copy(), R=np.eye(3), T=np.asarray(T, np.float64), R1=np.eye(3), R2=np.eye(3),
-                P1=P1, P2=P2, roi_left=(0, 0, W, H), roi_right=(0, 0, W, H))
+                P1=P1, P2=P2, roi_left=(0, 0, W - 1, H - 1), roi_right=(0, 0, W - 1, H - 1))

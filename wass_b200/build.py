@@ -17,7 +17,9 @@ LIB = os.path.join(HERE, "libwassgpu.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 CXX = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
-FLAGS = ["-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "-ccbin", CXX, "--use_fast_math"]
+FLAGS = ["-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "-ccbin", CXX]
+# fp32/fp64 parity kernels: reproduce the reference's operation order literally (no FMA contraction)
+PER_FILE = {"geom_kernels.cu": ["-fmad=false"], "capi_geom.cu": ["-fmad=false"], "rectify.cu": ["-fmad=false"]}
 
 
 def _newer(srcs, out):
@@ -38,7 +40,7 @@ def build(force=False, verbose=False):
         o = os.path.join(objdir, os.path.basename(s)[:-3] + ".o")
         objs.append(o)
         if force or _newer([s] + [d for d in deps if not d.endswith(".cu")], o):
-            cmd = [NVCC] + ARCH + FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o]
+            cmd = [NVCC] + ARCH + FLAGS + PER_FILE.get(os.path.basename(s), []) + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o]
             procs.append((cmd, subprocess.Popen(cmd)))
     for cmd, p in procs:
         if p.wait() != 0:

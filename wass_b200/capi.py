@@ -35,6 +35,52 @@ class SgbmStats(ctypes.Structure):
                 ("width1", ctypes.c_int), ("d_padded", ctypes.c_int), ("volume_bytes", ctypes.c_longlong)]
 
 
+class DenseParams(ctypes.Structure):
+    _fields_ = [("MIN_DISPARITY", ctypes.c_int), ("MAX_DISPARITY", ctypes.c_int), ("WINSIZE", ctypes.c_int),
+                ("DENSE_SCALE", ctypes.c_double), ("DISPARITY_OFFSET", ctypes.c_int), ("DISP_DILATE_STEPS", ctypes.c_int),
+                ("DISP_EROSION_STEPS", ctypes.c_int), ("DENSE_P1_MULT", ctypes.c_int), ("DENSE_P2_MULT", ctypes.c_int),
+                ("DENSE_UNIQUENESS_RATIO", ctypes.c_int), ("DENSE_DISP12MAXDIFF", ctypes.c_int),
+                ("DENSE_PREFILTER_CAP", ctypes.c_int), ("DENSE_SPECKLE_RANGE", ctypes.c_int),
+                ("DENSE_SPECKLE_WINDOW_SIZE", ctypes.c_int), ("mode", ctypes.c_int)]
+
+
+class Calib(ctypes.Structure):
+    _fields_ = [("K0", ctypes.c_double * 9), ("K1", ctypes.c_double * 9), ("R", ctypes.c_double * 9), ("T", ctypes.c_double * 3),
+                ("R1", ctypes.c_double * 9), ("R2", ctypes.c_double * 9), ("P1", ctypes.c_double * 12), ("P2", ctypes.c_double * 12),
+                ("roi_left", ctypes.c_int * 4), ("roi_right", ctypes.c_int * 4),
+                ("left_cols", ctypes.c_int), ("left_rows", ctypes.c_int), ("right_cols", ctypes.c_int), ("right_rows", ctypes.c_int),
+                ("rect_cols", ctypes.c_int), ("rect_rows", ctypes.c_int)]
+
+
+class TriParams(ctypes.Structure):
+    _fields_ = [("TRIANG_MIN_ANGLE", ctypes.c_double), ("TRIANG_BBOX_TOP", ctypes.c_double), ("TRIANG_BBOX_LEFT", ctypes.c_double),
+                ("TRIANG_BBOX_RIGHT", ctypes.c_double), ("TRIANG_BBOX_BOTTOM", ctypes.c_double),
+                ("DISCARD_BURNED_AREAS", ctypes.c_int), ("disparity_compensation", ctypes.c_int),
+                ("DENSE_SCALE", ctypes.c_double), ("cam_distance", ctypes.c_double)]
+
+
+class RefineParams(ctypes.Structure):
+    _fields_ = [("PLANE_REFINE_XMIN", ctypes.c_double), ("PLANE_REFINE_XMAX", ctypes.c_double),
+                ("PLANE_REFINE_YMIN", ctypes.c_double), ("PLANE_REFINE_YMAX", ctypes.c_double),
+                ("PLANE_REFINEMENT_MAX_DISTANCE", ctypes.c_double), ("PLANE_WEIGHT_PROPORTIONAL_TO_DISTANCE", ctypes.c_int),
+                ("PLANE_USE_CENTRAL_THIRD_ONLY", ctypes.c_int)]
+
+
+def make_calib(c, left_shape, right_shape, rect_shape):
+    """dict(K0,K1,R,T,R1,R2,P1,P2,roi_left,roi_right) -> Calib"""
+    k = Calib()
+    for name, n in (("K0", 9), ("K1", 9), ("R", 9), ("T", 3), ("R1", 9), ("R2", 9), ("P1", 12), ("P2", 12)):
+        arr = np.asarray(c[name], np.float64).reshape(-1)
+        assert arr.size == n, name
+        getattr(k, name)[:] = list(arr)
+    k.roi_left[:] = [int(v) for v in c["roi_left"]]
+    k.roi_right[:] = [int(v) for v in c["roi_right"]]
+    k.left_rows, k.left_cols = left_shape
+    k.right_rows, k.right_cols = right_shape
+    k.rect_rows, k.rect_cols = rect_shape
+    return k
+
+
 _lib = None
 
 
@@ -63,8 +109,110 @@ def load():
     lib.wsg_profile_enable.argtypes = [vp, ci]
     lib.wsg_profile_reset.argtypes = [vp]
     lib.wsg_profile_get.argtypes = [vp, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ci), ci]
+    u64p = ctypes.POINTER(ctypes.c_ulonglong)
+    dp = ctypes.POINTER(ctypes.c_double)
+    lib.wsg_dense_params_default.argtypes = [ctypes.POINTER(DenseParams)]
+    lib.wsg_dense_params_default.restype = None
+    lib.wsg_tri_params_default.argtypes = [ctypes.POINTER(TriParams)]
+    lib.wsg_tri_params_default.restype = None
+    lib.wsg_refine_params_default.argtypes = [ctypes.POINTER(RefineParams)]
+    lib.wsg_refine_params_default.restype = None
+    lib.wsg_dense_stereo.argtypes = [vp, vp, vp, ci, ci, sz, ctypes.POINTER(DenseParams), vp, vp]
+    lib.wsg_disparity_postprocess.argtypes = [vp, vp, ci, ci, ci, ci, ci, ctypes.c_double, ci, ci, vp]
+    lib.wsg_triangulate.argtypes = [vp, vp, vp, vp, vp, vp, ctypes.POINTER(Calib), ctypes.POINTER(TriParams), u64p]
+    lib.wsg_triangulate_from_dense.argtypes = [vp, vp, vp, vp, vp, ctypes.POINTER(Calib), ctypes.POINTER(TriParams), u64p]
+    lib.wsg_mesh_upload.argtypes = [vp, ci, ci, vp, vp, vp]
+    lib.wsg_mesh_download.argtypes = [vp, vp, vp, vp]
+    lib.wsg_mesh_size.argtypes = [vp, ctypes.POINTER(ci), ctypes.POINTER(ci), u64p]
+    lib.wsg_mesh_zgap_percentile.argtypes = [vp, ctypes.c_double, dp]
+    lib.wsg_mesh_biggest_component.argtypes = [vp, ctypes.c_double, u64p]
+    lib.wsg_mesh_ransac_plane.argtypes = [vp, vp, ci, ctypes.c_double, dp, ctypes.POINTER(ci), u64p]
+    lib.wsg_ransac_draw.argtypes = [ci, ci, ci, vp]
+    lib.wsg_mesh_crop_plane.argtypes = [vp, dp, ctypes.c_double, u64p]
+    lib.wsg_mesh_refine_plane.argtypes = [vp, ctypes.POINTER(RefineParams), dp, u64p]
+    lib.wsg_rt_from_plane.argtypes = [dp, dp, dp, dp, dp]
+    lib.wsg_rt_from_plane.restype = None
+    lib.wsg_mesh_export_xyzc.argtypes = [vp, dp, vp, sz, ctypes.POINTER(sz)]
+    lib.wsg_mesh_export_xyzbin.argtypes = [vp, vp, sz, ctypes.POINTER(sz)]
+    ip = ctypes.POINTER(ci)
+    lib.wsg_stereo_rectify.argtypes = [dp, dp, dp, dp, ci, ci, dp, dp, dp, dp, ip, ip]
+    lib.wsg_rectify_image.argtypes = [vp, vp, ci, ci, sz, dp, dp, dp, vp]
+    lib.wsg_plane_mean_accumulate.argtypes = [dp, dp]
+    lib.wsg_plane_mean_accumulate.restype = None
+    lib.wsg_plane_mean_finish.argtypes = [dp, dp]
+    lib.wsg_plane_mean_finish.restype = None
     _lib = lib
     return lib
+
+
+def dense_params(**kw):
+    p = DenseParams()
+    load().wsg_dense_params_default(ctypes.byref(p))
+    for k, v in kw.items():
+        setattr(p, k, v)
+    return p
+
+
+def tri_params(**kw):
+    p = TriParams()
+    load().wsg_tri_params_default(ctypes.byref(p))
+    for k, v in kw.items():
+        setattr(p, k, v)
+    return p
+
+
+def refine_params(**kw):
+    p = RefineParams()
+    load().wsg_refine_params_default(ctypes.byref(p))
+    for k, v in kw.items():
+        setattr(p, k, v)
+    return p
+
+
+def ransac_draw(width, height, rounds):
+    """libc rand()-driven triple draw (PovMesh.cpp:678-692); seed with libc srand first."""
+    t = np.zeros((rounds, 6), np.int32)
+    rc = load().wsg_ransac_draw(width, height, rounds, t.ctypes.data)
+    if rc:
+        raise WsgError(rc, "wsg_ransac_draw")
+    return t
+
+
+def _darr(a, n):
+    a = np.asarray(a, np.float64).reshape(-1)
+    assert a.size == n
+    return (ctypes.c_double * n)(*a)
+
+
+def stereo_rectify(K0, K1, R, T, width, height):
+    """cv::stereoRectify as wass_stereo calls it (flags=0, alpha=1, zero distortion). Host only."""
+    R1, R2 = (ctypes.c_double * 9)(), (ctypes.c_double * 9)()
+    P1, P2 = (ctypes.c_double * 12)(), (ctypes.c_double * 12)()
+    r1, r2 = (ctypes.c_int * 4)(), (ctypes.c_int * 4)()
+    rc = load().wsg_stereo_rectify(_darr(K0, 9), _darr(K1, 9), _darr(R, 9), _darr(T, 3), width, height, R1, R2, P1, P2, r1, r2)
+    if rc:
+        raise WsgError(rc, "wsg_stereo_rectify")
+    return dict(R1=np.array(list(R1)).reshape(3, 3), R2=np.array(list(R2)).reshape(3, 3), P1=np.array(list(P1)).reshape(3, 4),
+                P2=np.array(list(P2)).reshape(3, 4), roi1=tuple(r1), roi2=tuple(r2))
+
+
+def rt_from_plane(plane):
+    R, T, Ri, Ti = (ctypes.c_double * 9)(), (ctypes.c_double * 3)(), (ctypes.c_double * 9)(), (ctypes.c_double * 3)()
+    load().wsg_rt_from_plane(_d4(plane), R, T, Ri, Ti)
+    return (np.array(list(R)).reshape(3, 3), np.array(list(T)), np.array(list(Ri)).reshape(3, 3), np.array(list(Ti)))
+
+
+def plane_mean(planes):
+    acc = (ctypes.c_double * 5)(0, 0, 0, 0, 0)
+    for p in planes:
+        load().wsg_plane_mean_accumulate(acc, _d4(p))
+    mean = (ctypes.c_double * 4)()
+    load().wsg_plane_mean_finish(acc, mean)
+    return np.array(list(mean)), np.array(list(acc))
+
+
+def _d4(a):
+    return (ctypes.c_double * 4)(*[float(v) for v in a])
 
 
 class Handle:
@@ -130,6 +278,121 @@ class Handle:
         S = np.empty((rows, w1, D), np.int16)
         self._ck(self.lib.wsg_sgbm_debug_volumes(self.h, C.ctypes.data, S.ctypes.data))
         return C, S
+
+    # ---- dense stage ----
+    def dense_stereo(self, left_crop, right_crop, params, want_disp16=False):
+        """Mirrors sgbm_dense_stereo (wass_stereo.cpp:764-1020): crops in, float ROI disparity out."""
+        left_crop = np.ascontiguousarray(left_crop, np.uint8)
+        right_crop = np.ascontiguousarray(right_crop, np.uint8)
+        H, W = left_crop.shape
+        out = np.empty((H, W), np.float32)
+        d16 = np.empty((H, W), np.int16) if want_disp16 else None
+        self._ck(self.lib.wsg_dense_stereo(self.h, left_crop.ctypes.data, right_crop.ctypes.data, H, W, W, ctypes.byref(params),
+                                           out.ctypes.data, d16.ctypes.data if want_disp16 else None))
+        return (out, d16) if want_disp16 else out
+
+    def disparity_postprocess(self, disp16_roi, min_disp, num_disp, disparity_offset=0, dense_scale=1.0, dilate=1, erode=2):
+        d = np.ascontiguousarray(disp16_roi, np.int16)
+        H, W = d.shape
+        out = np.empty((H, W), np.float32)
+        self._ck(self.lib.wsg_disparity_postprocess(self.h, d.ctypes.data, H, W, min_disp, num_disp, disparity_offset,
+                                                    dense_scale, dilate, erode, out.ctypes.data))
+        return out
+
+    # ---- triangulation + mesh ----
+    def triangulate(self, disparity, left, right, calib, params=None, left_mask=None, right_mask=None):
+        disparity = np.ascontiguousarray(disparity, np.float32)
+        left = np.ascontiguousarray(left, np.uint8)
+        right = np.ascontiguousarray(right, np.uint8)
+        c = make_calib(calib, left.shape, right.shape, disparity.shape) if isinstance(calib, dict) else calib
+        p = params or tri_params()
+        n = ctypes.c_ulonglong()
+        lm = np.ascontiguousarray(left_mask, np.uint8) if left_mask is not None else None
+        rm = np.ascontiguousarray(right_mask, np.uint8) if right_mask is not None else None
+        self._ck(self.lib.wsg_triangulate(self.h, disparity.ctypes.data, left.ctypes.data, right.ctypes.data,
+                                          lm.ctypes.data if lm is not None else None, rm.ctypes.data if rm is not None else None,
+                                          ctypes.byref(c), ctypes.byref(p), ctypes.byref(n)))
+        return n.value
+
+    def triangulate_from_dense(self, left, right, calib, rect_shape, params=None):
+        left = np.ascontiguousarray(left, np.uint8)
+        right = np.ascontiguousarray(right, np.uint8)
+        c = make_calib(calib, left.shape, right.shape, rect_shape) if isinstance(calib, dict) else calib
+        p = params or tri_params()
+        n = ctypes.c_ulonglong()
+        self._ck(self.lib.wsg_triangulate_from_dense(self.h, left.ctypes.data, right.ctypes.data, None, None,
+                                                     ctypes.byref(c), ctypes.byref(p), ctypes.byref(n)))
+        return n.value
+
+    def mesh_upload(self, valid, p3d, grey=None):
+        valid = np.ascontiguousarray(valid, np.uint8)
+        p3d = np.ascontiguousarray(p3d, np.float64)
+        H, W = valid.shape
+        g = np.ascontiguousarray(grey, np.uint8) if grey is not None else None
+        self._ck(self.lib.wsg_mesh_upload(self.h, W, H, valid.ctypes.data, p3d.ctypes.data, g.ctypes.data if g is not None else None))
+
+    def mesh_size(self):
+        w, hh, n = ctypes.c_int(), ctypes.c_int(), ctypes.c_ulonglong()
+        self._ck(self.lib.wsg_mesh_size(self.h, ctypes.byref(w), ctypes.byref(hh), ctypes.byref(n)))
+        return w.value, hh.value, n.value
+
+    def mesh_download(self):
+        W, H, _ = self.mesh_size()
+        valid = np.empty((H, W), np.uint8)
+        p3d = np.empty((H, W, 3), np.float64)
+        grey = np.empty((H, W), np.uint8)
+        self._ck(self.lib.wsg_mesh_download(self.h, valid.ctypes.data, p3d.ctypes.data, grey.ctypes.data))
+        return valid.astype(bool), p3d, grey
+
+    def mesh_zgap_percentile(self, percentile=99.0):
+        z = ctypes.c_double()
+        self._ck(self.lib.wsg_mesh_zgap_percentile(self.h, percentile, ctypes.byref(z)))
+        return z.value
+
+    def mesh_biggest_component(self, zgap):
+        n = ctypes.c_ulonglong()
+        self._ck(self.lib.wsg_mesh_biggest_component(self.h, zgap, ctypes.byref(n)))
+        return n.value
+
+    def mesh_ransac_plane(self, triples, threshold):
+        t = np.ascontiguousarray(triples, np.int32)
+        plane = (ctypes.c_double * 4)()
+        ok, best = ctypes.c_int(), ctypes.c_ulonglong()
+        self._ck(self.lib.wsg_mesh_ransac_plane(self.h, t.ctypes.data, t.shape[0], threshold, plane, ctypes.byref(ok), ctypes.byref(best)))
+        return bool(ok.value), np.array(list(plane)), best.value
+
+    def mesh_crop_plane(self, plane, threshold):
+        n = ctypes.c_ulonglong()
+        self._ck(self.lib.wsg_mesh_crop_plane(self.h, _d4(plane), threshold, ctypes.byref(n)))
+        return n.value
+
+    def mesh_refine_plane(self, params=None):
+        p = params or refine_params()
+        plane = (ctypes.c_double * 4)()
+        n = ctypes.c_ulonglong()
+        self._ck(self.lib.wsg_mesh_refine_plane(self.h, ctypes.byref(p), plane, ctypes.byref(n)))
+        return np.array(list(plane)), n.value
+
+    def mesh_export_xyzc(self, plane):
+        W, H, _ = self.mesh_size()
+        buf = np.empty(148 + W * H * 6, np.uint8)
+        nb = ctypes.c_size_t()
+        self._ck(self.lib.wsg_mesh_export_xyzc(self.h, _d4(plane), buf.ctypes.data, buf.size, ctypes.byref(nb)))
+        return buf[:nb.value].tobytes()
+
+    def mesh_export_xyzbin(self):
+        W, H, _ = self.mesh_size()
+        buf = np.empty(4 + W * H * 12, np.uint8)
+        nb = ctypes.c_size_t()
+        self._ck(self.lib.wsg_mesh_export_xyzbin(self.h, buf.ctypes.data, buf.size, ctypes.byref(nb)))
+        return buf[:nb.value].tobytes()
+
+    def rectify_image(self, img, K, Rrect, P):
+        img = np.ascontiguousarray(img, np.uint8)
+        H, W = img.shape
+        out = np.empty((H, W), np.uint8)
+        self._ck(self.lib.wsg_rectify_image(self.h, img.ctypes.data, H, W, W, _darr(K, 9), _darr(Rrect, 9), _darr(P, 12), out.ctypes.data))
+        return out
 
     # ---- profiling ----
     def profile_enable(self, on=True):

@@ -1,93 +1,6 @@
 // C ABI of libwassgpu.so (declared in include/wassgpu.h).  Thin: argument checks, a grow-only
 // device arena per handle, kernel launches on the handle's stream.  No CPU fallback anywhere.
-#include "../../include/wassgpu.h"
-#include "sgbm.cuh"
-
-#include <algorithm>
-#include <cstdio>
-#include <cstdlib>
-#include <cstring>
-#include <string>
-#include <vector>
-
-using namespace wsg;
-
-struct DevBuf {
-    void* p = nullptr;
-    size_t cap = 0;
-};
-
-struct wsg_handle {
-    int device = 0;
-    cudaStream_t own_stream = nullptr;
-    cudaStream_t stream = nullptr;
-    std::string err;
-    // SGBM arena
-    DevBuf pre1, pre2, C, S, raw, img1, img2, disp, scalars;
-    SgbmPlan plan{};
-    bool have_plan = false;
-    wsg_sgbm_stats stats{};
-    // profiling
-    bool prof = false;
-    float stage_ms[WSG_NUM_STAGES] = {0};
-    int stage_launches[WSG_NUM_STAGES] = {0};
-    std::vector<std::pair<int, std::pair<cudaEvent_t, cudaEvent_t>>> pending;
-    std::vector<cudaEvent_t> ev_pool;
-};
-
-#define CK(h, call)                                                                           \
-    do {                                                                                      \
-        cudaError_t e__ = (call);                                                             \
-        if (e__ != cudaSuccess) {                                                             \
-            (h)->err = std::string(#call) + ": " + cudaGetErrorString(e__);                   \
-            return WSG_ERR_CUDA;                                                              \
-        }                                                                                     \
-    } while (0)
-
-static int ensure(wsg_handle* h, DevBuf& b, size_t bytes)
-{
-    if (bytes <= b.cap) return WSG_OK;
-    if (b.p) { cudaFree(b.p); b.p = nullptr; b.cap = 0; }
-    cudaError_t e = cudaMalloc(&b.p, bytes);
-    if (e != cudaSuccess) {
-        h->err = std::string("cudaMalloc(") + std::to_string(bytes) + "): " + cudaGetErrorString(e);
-        cudaGetLastError();
-        return e == cudaErrorMemoryAllocation ? WSG_ERR_NOMEM : WSG_ERR_CUDA;
-    }
-    b.cap = bytes;
-    return WSG_OK;
-}
-
-struct StageTimer {
-    wsg_handle* h; int stage; cudaEvent_t a = nullptr, b = nullptr;
-    static cudaEvent_t get(wsg_handle* h)
-    {
-        if (!h->ev_pool.empty()) { cudaEvent_t e = h->ev_pool.back(); h->ev_pool.pop_back(); return e; }
-        cudaEvent_t e; cudaEventCreate(&e); return e;
-    }
-    StageTimer(wsg_handle* h_, int s, int launches) : h(h_), stage(s)
-    {
-        h->stage_launches[s] += launches;
-        if (h->prof) { a = get(h); b = get(h); cudaEventRecord(a, h->stream); }
-    }
-    ~StageTimer()
-    {
-        if (h->prof) { cudaEventRecord(b, h->stream); h->pending.push_back({stage, {a, b}}); }
-    }
-};
-
-static void drain_profile(wsg_handle* h)
-{
-    for (auto& pe : h->pending) {
-        cudaEventSynchronize(pe.second.second);
-        float ms = 0;
-        cudaEventElapsedTime(&ms, pe.second.first, pe.second.second);
-        h->stage_ms[pe.first] += ms;
-        h->ev_pool.push_back(pe.second.first);
-        h->ev_pool.push_back(pe.second.second);
-    }
-    h->pending.clear();
-}
+#include "handle.cuh"
 
 extern "C" {
 
@@ -114,7 +27,9 @@ void wsg_destroy(wsg_handle* h)
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
     drain_profile(h);
-    for (DevBuf* b : {&h->pre1, &h->pre2, &h->C, &h->S, &h->raw, &h->img1, &h->img2, &h->disp, &h->scalars})
+    for (DevBuf* b : {&h->pre1, &h->pre2, &h->C, &h->S, &h->raw, &h->img1, &h->img2, &h->disp, &h->scalars, &h->crop_l, &h->crop_r,
+                      &h->fa, &h->fb, &h->dispfull, &h->im_left, &h->im_right, &h->mask_l, &h->mask_r, &h->m_valid, &h->m_X, &h->m_Y,
+                      &h->m_Z, &h->m_color, &h->m_labels, &h->m_scratch, &h->m_small, &h->m_out})
         if (b->p) cudaFree(b->p);
     for (auto e : h->ev_pool) cudaEventDestroy(e);
     cudaStreamDestroy(h->own_stream);
@@ -137,7 +52,7 @@ int wsg_synchronize(wsg_handle* h)
 
 const char* wsg_last_error(const wsg_handle* h) { return h ? h->err.c_str() : "null handle"; }
 
-static int make_plan(wsg_handle* h, int rows, int cols, const wsg_sgbm_params* p, SgbmPlan& pl)
+int wsg_make_plan(wsg_handle* h, int rows, int cols, const wsg_sgbm_params* p, SgbmPlan& pl)
 {
     if (!p || rows <= 0 || cols <= 0) { h->err = "bad image size or null params"; return WSG_ERR_INVALID_ARG; }
     if (p->numDisparities <= 0 || p->numDisparities % 16 || p->numDisparities > 1280) {
@@ -177,7 +92,7 @@ static int make_plan(wsg_handle* h, int rows, int cols, const wsg_sgbm_params* p
     return WSG_OK;
 }
 
-static int run_sgbm(wsg_handle* h, const uint8_t* d_img1, const uint8_t* d_img2, size_t stride, int16_t* d_disp)
+int wsg_run_sgbm(wsg_handle* h, const uint8_t* d_img1, const uint8_t* d_img2, size_t stride, int16_t* d_disp)
 {
     const SgbmPlan& pl = h->plan;
     const size_t npix = (size_t)pl.H * pl.W;
@@ -234,11 +149,11 @@ int wsg_sgbm_compute_device(wsg_handle* h, const uint8_t* d_img1, const uint8_t*
     if (!d_img1 || !d_img2 || !d_disp16 || stride < (size_t)std::max(cols, 0)) { h->err = "null pointer or stride < cols"; return WSG_ERR_INVALID_ARG; }
     CK(h, cudaSetDevice(h->device));
     SgbmPlan pl{};
-    int rc = make_plan(h, rows, cols, p, pl);
+    int rc = wsg_make_plan(h, rows, cols, p, pl);
     if (rc) return rc;
     h->plan = pl;
     h->stats.out_of_domain = 0; h->stats.max_cost = 0;
-    return run_sgbm(h, d_img1, d_img2, stride, d_disp16);
+    return wsg_run_sgbm(h, d_img1, d_img2, stride, d_disp16);
 }
 
 int wsg_sgbm_compute(wsg_handle* h, const uint8_t* img1, const uint8_t* img2, int rows, int cols, size_t stride,
@@ -248,7 +163,7 @@ int wsg_sgbm_compute(wsg_handle* h, const uint8_t* img1, const uint8_t* img2, in
     if (!img1 || !img2 || !disp16 || stride < (size_t)std::max(cols, 0)) { h->err = "null pointer or stride < cols"; return WSG_ERR_INVALID_ARG; }
     CK(h, cudaSetDevice(h->device));
     SgbmPlan pl{};
-    int rc = make_plan(h, rows, cols, p, pl);
+    int rc = wsg_make_plan(h, rows, cols, p, pl);
     if (rc) return rc;
     h->plan = pl;
     const size_t npix = (size_t)rows * cols;
@@ -257,7 +172,7 @@ int wsg_sgbm_compute(wsg_handle* h, const uint8_t* img1, const uint8_t* img2, in
     if ((rc = ensure(h, h->disp, npix * sizeof(int16_t)))) return rc;
     CK(h, cudaMemcpy2DAsync(h->img1.p, cols, img1, stride, cols, rows, cudaMemcpyHostToDevice, h->stream));
     CK(h, cudaMemcpy2DAsync(h->img2.p, cols, img2, stride, cols, rows, cudaMemcpyHostToDevice, h->stream));
-    rc = run_sgbm(h, (const uint8_t*)h->img1.p, (const uint8_t*)h->img2.p, cols, (int16_t*)h->disp.p);
+    rc = wsg_run_sgbm(h, (const uint8_t*)h->img1.p, (const uint8_t*)h->img2.p, cols, (int16_t*)h->disp.p);
     if (rc) return rc;
     CK(h, cudaMemcpyAsync(disp16, h->disp.p, npix * sizeof(int16_t), cudaMemcpyDeviceToHost, h->stream));
     CK(h, cudaStreamSynchronize(h->stream));

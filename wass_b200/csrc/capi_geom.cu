@@ -1,0 +1,567 @@
+// C ABI, part 2: the dense-stereo stage as a whole, triangulation and the PovMesh operations.
+#include "handle.cuh"
+
+#include <cmath>
+
+namespace {
+
+MeshView mesh_view(wsg_handle* h)
+{
+    MeshView m;
+    m.w = h->mesh_w; m.h = h->mesh_h;
+    m.valid = (uint8_t*)h->m_valid.p; m.X = (double*)h->m_X.p; m.Y = (double*)h->m_Y.p; m.Z = (double*)h->m_Z.p;
+    m.color = (uint8_t*)h->m_color.p;
+    return m;
+}
+
+int alloc_mesh(wsg_handle* h, int w, int hh)
+{
+    const size_t n = (size_t)w * hh;
+    int rc;
+    if ((rc = ensure(h, h->m_valid, n))) return rc;
+    if ((rc = ensure(h, h->m_color, n))) return rc;
+    if ((rc = ensure(h, h->m_X, n * 8))) return rc;
+    if ((rc = ensure(h, h->m_Y, n * 8))) return rc;
+    if ((rc = ensure(h, h->m_Z, n * 8))) return rc;
+    if ((rc = ensure(h, h->m_small, 1 << 16))) return rc;
+    h->mesh_w = w; h->mesh_h = hh;
+    return WSG_OK;
+}
+
+int need_mesh(wsg_handle* h)
+{
+    if (!h) return WSG_ERR_INVALID_ARG;
+    if (!h->have_mesh) { h->err = "no mesh: call wsg_triangulate or wsg_mesh_upload first"; return WSG_ERR_STATE; }
+    if (cudaSetDevice(h->device) != cudaSuccess) return WSG_ERR_CUDA;
+    return WSG_OK;
+}
+
+// device part of wass_stereo.cpp:853-928 on the ROI disparity (int16 x16, `cols_full` per row, ROI starting at x0)
+int postprocess_device(wsg_handle* h, const int16_t* d_disp16, int rows, int cols_full, int x0, int width, int mindisp,
+                       int ndisp, int disp_offset, double dense_scale, int dilate, int erode)
+{
+    const size_t n = (size_t)rows * width;
+    int rc;
+    if ((rc = ensure(h, h->fa, n * 4))) return rc;
+    if ((rc = ensure(h, h->fb, n * 4))) return rc;
+    float* a = (float*)h->fa.p;
+    float* b = (float*)h->fb.p;
+    StageTimer t(h, WSG_STAGE_POSTFILTER, 2 + std::max(dilate, 0) + std::max(erode, 0));
+    launch_clean_convert(d_disp16, rows, cols_full, x0, width, mindisp, ndisp, disp_offset, 1.0 / dense_scale, a, h->stream);
+    for (int s = 0; s < dilate; ++s) { launch_dilate_zero(a, b, rows, width, h->stream); std::swap(a, b); }
+    for (int s = 0; s < erode; ++s) { launch_erode_zero(a, b, rows, width, h->stream); std::swap(a, b); }
+    launch_mask_by_eroded(a, b, rows, width, h->stream);
+    std::swap(a, b);
+    if (a != (float*)h->fa.p) std::swap(h->fa, h->fb);   // result always ends up in h->fa
+    CK(h, cudaGetLastError());
+    h->dense_rows = rows; h->dense_cols = width; h->have_dense = true;
+    return WSG_OK;
+}
+
+void jacobi_eigen3(double A[3][3], double V[3][3], double w[3])
+{
+    for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) V[i][j] = i == j;
+    for (int sweep = 0; sweep < 64; ++sweep) {
+        double off = fabs(A[0][1]) + fabs(A[0][2]) + fabs(A[1][2]);
+        if (off < 1e-300) break;
+        for (int p = 0; p < 2; ++p)
+            for (int q = p + 1; q < 3; ++q) {
+                if (fabs(A[p][q]) < 1e-300) continue;
+                const double theta = (A[q][q] - A[p][p]) / (2.0 * A[p][q]);
+                const double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+                const double c = 1.0 / sqrt(t * t + 1.0), s = t * c;
+                for (int k = 0; k < 3; ++k) { const double akp = A[k][p], akq = A[k][q]; A[k][p] = c * akp - s * akq; A[k][q] = s * akp + c * akq; }
+                for (int k = 0; k < 3; ++k) { const double apk = A[p][k], aqk = A[q][k]; A[p][k] = c * apk - s * aqk; A[q][k] = s * apk + c * aqk; }
+                for (int k = 0; k < 3; ++k) { const double vkp = V[k][p], vkq = V[k][q]; V[k][p] = c * vkp - s * vkq; V[k][q] = s * vkp + c * vkq; }
+            }
+    }
+    for (int i = 0; i < 3; ++i) w[i] = A[i][i];
+}
+
+}  // namespace
+
+extern "C" {
+
+void wsg_dense_params_default(wsg_dense_params* p)
+{
+    if (!p) return;
+    // defaults of wass_stereo.cpp:742-761
+    p->MIN_DISPARITY = 1; p->MAX_DISPARITY = 640; p->WINSIZE = 13; p->DENSE_SCALE = 1.0; p->DISPARITY_OFFSET = 0;
+    p->DISP_DILATE_STEPS = 1; p->DISP_EROSION_STEPS = 2; p->DENSE_P1_MULT = 2; p->DENSE_P2_MULT = 64;
+    p->DENSE_UNIQUENESS_RATIO = 1; p->DENSE_DISP12MAXDIFF = -1; p->DENSE_PREFILTER_CAP = 60; p->DENSE_SPECKLE_RANGE = 16;
+    p->DENSE_SPECKLE_WINDOW_SIZE = -70; p->mode = WSG_MODE_SGBM;
+}
+
+void wsg_tri_params_default(wsg_tri_params* p)
+{
+    if (!p) return;
+    // defaults of wass_stereo.cpp:1030-1037
+    p->TRIANG_MIN_ANGLE = 20.0; p->TRIANG_BBOX_TOP = p->TRIANG_BBOX_LEFT = p->TRIANG_BBOX_RIGHT = p->TRIANG_BBOX_BOTTOM = -1.0;
+    p->DISCARD_BURNED_AREAS = 1; p->disparity_compensation = 0; p->DENSE_SCALE = 1.0; p->cam_distance = 1.0;
+}
+
+void wsg_refine_params_default(wsg_refine_params* p)
+{
+    if (!p) return;
+    // defaults of wass_stereo.cpp:62-66 and PovMesh.cpp:577-579
+    p->PLANE_REFINE_XMIN = -9999; p->PLANE_REFINE_XMAX = 9999; p->PLANE_REFINE_YMIN = -9999; p->PLANE_REFINE_YMAX = 9999;
+    p->PLANE_REFINEMENT_MAX_DISTANCE = 70.0; p->PLANE_WEIGHT_PROPORTIONAL_TO_DISTANCE = 1; p->PLANE_USE_CENTRAL_THIRD_ONLY = 0;
+}
+
+int wsg_dense_stereo(wsg_handle* h, const uint8_t* left_crop, const uint8_t* right_crop, int rows, int cols, size_t stride,
+                     const wsg_dense_params* p, float* disp_roi, int16_t* disp16_roi)
+{
+    if (!h) return WSG_ERR_INVALID_ARG;
+    if (!left_crop || !right_crop || !p || !disp_roi || rows <= 0 || cols <= 0 || stride < (size_t)cols) { h->err = "bad argument"; return WSG_ERR_INVALID_ARG; }
+    if (p->DENSE_SCALE != 1.0) { h->err = "DENSE_SCALE != 1 is not supported (cv::resize INTER_CUBIC parity not implemented)"; return WSG_ERR_INVALID_ARG; }
+    CK(h, cudaSetDevice(h->device));
+    const int N = p->MAX_DISPARITY;
+    const int off = std::max(p->DISPARITY_OFFSET, 0), comp = std::max(-p->DISPARITY_OFFSET, 0);
+    if (comp > N + off) { h->err = "DISPARITY_OFFSET too negative"; return WSG_ERR_INVALID_ARG; }
+    const int wp = cols + N + off;
+    wsg_sgbm_params sp;
+    sp.minDisparity = p->MIN_DISPARITY; sp.numDisparities = N; sp.blockSize = p->WINSIZE;
+    sp.P1 = p->DENSE_P1_MULT * p->WINSIZE * p->WINSIZE; sp.P2 = p->DENSE_P2_MULT * p->WINSIZE * p->WINSIZE;
+    sp.disp12MaxDiff = p->DENSE_DISP12MAXDIFF; sp.preFilterCap = p->DENSE_PREFILTER_CAP; sp.uniquenessRatio = p->DENSE_UNIQUENESS_RATIO;
+    sp.speckleWindowSize = p->DENSE_SPECKLE_WINDOW_SIZE; sp.speckleRange = p->DENSE_SPECKLE_RANGE; sp.mode = p->mode;
+    SgbmPlan pl{};
+    int rc = wsg_make_plan(h, rows, wp, &sp, pl);
+    if (rc) return rc;
+    h->plan = pl;
+    const size_t ncrop = (size_t)rows * cols, npad = (size_t)rows * wp;
+    if ((rc = ensure(h, h->crop_l, ncrop))) return rc;
+    if ((rc = ensure(h, h->crop_r, ncrop))) return rc;
+    if ((rc = ensure(h, h->img1, npad))) return rc;
+    if ((rc = ensure(h, h->img2, npad))) return rc;
+    if ((rc = ensure(h, h->disp, npad * 2))) return rc;
+    CK(h, cudaMemcpy2DAsync(h->crop_l.p, cols, left_crop, stride, cols, rows, cudaMemcpyHostToDevice, h->stream));
+    CK(h, cudaMemcpy2DAsync(h->crop_r.p, cols, right_crop, stride, cols, rows, cudaMemcpyHostToDevice, h->stream));
+    launch_pad_images((const uint8_t*)h->crop_l.p, (const uint8_t*)h->crop_r.p, cols, rows, cols, N, off, comp,
+                      (uint8_t*)h->img1.p, (uint8_t*)h->img2.p, wp, h->stream);
+    rc = wsg_run_sgbm(h, (const uint8_t*)h->img1.p, (const uint8_t*)h->img2.p, wp, (int16_t*)h->disp.p);
+    if (rc) return rc;
+    rc = postprocess_device(h, (const int16_t*)h->disp.p, rows, wp, N, cols, p->MIN_DISPARITY, N, off, p->DENSE_SCALE,
+                            p->DISP_DILATE_STEPS, p->DISP_EROSION_STEPS);
+    if (rc) return rc;
+    CK(h, cudaMemcpyAsync(disp_roi, h->fa.p, ncrop * 4, cudaMemcpyDeviceToHost, h->stream));
+    if (disp16_roi)
+        CK(h, cudaMemcpy2DAsync(disp16_roi, (size_t)cols * 2, (const int16_t*)h->disp.p + N, (size_t)wp * 2, (size_t)cols * 2, rows,
+                                cudaMemcpyDeviceToHost, h->stream));
+    CK(h, cudaStreamSynchronize(h->stream));
+    return WSG_OK;
+}
+
+int wsg_disparity_postprocess(wsg_handle* h, const int16_t* disp16_roi, int rows, int cols, int minDisparity, int numDisparities,
+                              int disparityOffset, double denseScale, int dilateSteps, int erosionSteps, float* disp_roi)
+{
+    if (!h) return WSG_ERR_INVALID_ARG;
+    if (!disp16_roi || !disp_roi || rows <= 0 || cols <= 0) { h->err = "bad argument"; return WSG_ERR_INVALID_ARG; }
+    if (denseScale != 1.0) { h->err = "DENSE_SCALE != 1 is not supported"; return WSG_ERR_INVALID_ARG; }
+    CK(h, cudaSetDevice(h->device));
+    const size_t n = (size_t)rows * cols;
+    int rc;
+    if ((rc = ensure(h, h->disp, n * 2))) return rc;
+    CK(h, cudaMemcpyAsync(h->disp.p, disp16_roi, n * 2, cudaMemcpyHostToDevice, h->stream));
+    rc = postprocess_device(h, (const int16_t*)h->disp.p, rows, cols, 0, cols, minDisparity, numDisparities,
+                            std::max(disparityOffset, 0), denseScale, dilateSteps, erosionSteps);
+    if (rc) return rc;
+    CK(h, cudaMemcpyAsync(disp_roi, h->fa.p, n * 4, cudaMemcpyDeviceToHost, h->stream));
+    CK(h, cudaStreamSynchronize(h->stream));
+    return WSG_OK;
+}
+
+static int triangulate_common(wsg_handle* h, const float* d_disp_full, const uint8_t* left, const uint8_t* right,
+                              const uint8_t* left_mask, const uint8_t* right_mask, const wsg_calib* c, const wsg_tri_params* p,
+                              unsigned long long* n_points)
+{
+    CalibDev cd;
+    memcpy(cd.K0, c->K0, 72); memcpy(cd.K1, c->K1, 72); memcpy(cd.R, c->R, 72); memcpy(cd.T, c->T, 24);
+    memcpy(cd.R1, c->R1, 72); memcpy(cd.R2, c->R2, 72);
+    cd.P1fx = c->P1[0]; cd.P1fy = c->P1[5]; cd.P1cx = c->P1[2]; cd.P1cy = c->P1[6];
+    cd.P2fx = c->P2[0]; cd.P2fy = c->P2[5]; cd.P2cx = c->P2[2]; cd.P2cy = c->P2[6];
+    cd.rlx = c->roi_left[0]; cd.rly = c->roi_left[1]; cd.rlw = c->roi_left[2]; cd.rlh = c->roi_left[3];
+    cd.rrx = c->roi_right[0]; cd.rry = c->roi_right[1]; cd.rrw = c->roi_right[2]; cd.rrh = c->roi_right[3];
+    cd.left_cols = c->left_cols; cd.left_rows = c->left_rows; cd.right_cols = c->right_cols; cd.right_rows = c->right_rows;
+    cd.rect_cols = c->rect_cols; cd.rect_rows = c->rect_rows;
+    cd.min_angle = p->TRIANG_MIN_ANGLE;
+    if (p->TRIANG_BBOX_TOP >= 0 && p->TRIANG_BBOX_LEFT >= 0 && p->TRIANG_BBOX_BOTTOM >= 0 && p->TRIANG_BBOX_RIGHT >= 0) {
+        cd.bbox_l = p->TRIANG_BBOX_LEFT; cd.bbox_t = p->TRIANG_BBOX_TOP; cd.bbox_r = p->TRIANG_BBOX_RIGHT; cd.bbox_b = p->TRIANG_BBOX_BOTTOM;
+    } else {
+        cd.bbox_l = 0; cd.bbox_t = 0; cd.bbox_r = c->left_cols; cd.bbox_b = c->left_rows;
+    }
+    cd.discard_burned = p->DISCARD_BURNED_AREAS; cd.has_lmask = left_mask != nullptr; cd.has_rmask = right_mask != nullptr;
+    cd.comp_over_scale = (double)p->disparity_compensation / p->DENSE_SCALE;
+    cd.cam_distance = p->cam_distance;
+    if (cd.rrx < 0 || cd.rry < 0 || cd.rrw <= 0 || cd.rrh <= 0 || cd.rrx + cd.rrw > cd.rect_cols || cd.rry + cd.rrh > cd.rect_rows) {
+        h->err = "roi_right outside the rectified image"; return WSG_ERR_INVALID_ARG;
+    }
+    const size_t nl = (size_t)c->left_cols * c->left_rows, nr = (size_t)c->right_cols * c->right_rows;
+    int rc;
+    if ((rc = ensure(h, h->im_left, nl))) return rc;
+    if ((rc = ensure(h, h->im_right, nr))) return rc;
+    CK(h, cudaMemcpyAsync(h->im_left.p, left, nl, cudaMemcpyHostToDevice, h->stream));
+    CK(h, cudaMemcpyAsync(h->im_right.p, right, nr, cudaMemcpyHostToDevice, h->stream));
+    if (left_mask) { if ((rc = ensure(h, h->mask_l, nl))) return rc; CK(h, cudaMemcpyAsync(h->mask_l.p, left_mask, nl, cudaMemcpyHostToDevice, h->stream)); }
+    if (right_mask) { if ((rc = ensure(h, h->mask_r, nr))) return rc; CK(h, cudaMemcpyAsync(h->mask_r.p, right_mask, nr, cudaMemcpyHostToDevice, h->stream)); }
+    if ((rc = alloc_mesh(h, cd.rrw, cd.rrh))) return rc;
+    const size_t n = (size_t)cd.rrw * cd.rrh;
+    MeshView m = mesh_view(h);
+    CK(h, cudaMemsetAsync(m.valid, 0, n, h->stream));
+    CK(h, cudaMemsetAsync(m.color, 0, n, h->stream));
+    CK(h, cudaMemsetAsync(m.X, 0, n * 8, h->stream));
+    CK(h, cudaMemsetAsync(m.Y, 0, n * 8, h->stream));
+    CK(h, cudaMemsetAsync(m.Z, 0, n * 8, h->stream));
+    unsigned long long* counter = (unsigned long long*)h->m_small.p;
+    CK(h, cudaMemsetAsync(counter, 0, 8, h->stream));
+    {
+        StageTimer t(h, WSG_STAGE_TRIANGULATE, 1);
+        launch_triangulate(d_disp_full, (const uint8_t*)h->im_left.p, (const uint8_t*)h->im_right.p,
+                           left_mask ? (const uint8_t*)h->mask_l.p : nullptr, right_mask ? (const uint8_t*)h->mask_r.p : nullptr,
+                           cd, m, counter, h->stream);
+    }
+    unsigned long long cnt = 0;
+    CK(h, cudaMemcpyAsync(&cnt, counter, 8, cudaMemcpyDeviceToHost, h->stream));
+    CK(h, cudaStreamSynchronize(h->stream));
+    CK(h, cudaGetLastError());
+    h->have_mesh = true;
+    if (n_points) *n_points = cnt;
+    return WSG_OK;
+}
+
+int wsg_triangulate(wsg_handle* h, const float* disparity, const uint8_t* left, const uint8_t* right, const uint8_t* left_mask,
+                    const uint8_t* right_mask, const wsg_calib* calib, const wsg_tri_params* p, unsigned long long* n_points)
+{
+    if (!h) return WSG_ERR_INVALID_ARG;
+    if (!disparity || !left || !right || !calib || !p) { h->err = "null argument"; return WSG_ERR_INVALID_ARG; }
+    CK(h, cudaSetDevice(h->device));
+    const size_t n = (size_t)calib->rect_cols * calib->rect_rows;
+    int rc;
+    if ((rc = ensure(h, h->dispfull, n * 4))) return rc;
+    CK(h, cudaMemcpyAsync(h->dispfull.p, disparity, n * 4, cudaMemcpyHostToDevice, h->stream));
+    return triangulate_common(h, (const float*)h->dispfull.p, left, right, left_mask, right_mask, calib, p, n_points);
+}
+
+int wsg_triangulate_from_dense(wsg_handle* h, const uint8_t* left, const uint8_t* right, const uint8_t* left_mask,
+                               const uint8_t* right_mask, const wsg_calib* calib, const wsg_tri_params* p, unsigned long long* n_points)
+{
+    if (!h) return WSG_ERR_INVALID_ARG;
+    if (!left || !right || !calib || !p) { h->err = "null argument"; return WSG_ERR_INVALID_ARG; }
+    if (!h->have_dense) { h->err = "no dense disparity on the device: call wsg_dense_stereo first"; return WSG_ERR_STATE; }
+    if (h->dense_cols != calib->roi_right[2] || h->dense_rows != calib->roi_right[3]) {
+        h->err = "dense disparity size does not match roi_right"; return WSG_ERR_INVALID_ARG;
+    }
+    CK(h, cudaSetDevice(h->device));
+    const size_t n = (size_t)calib->rect_cols * calib->rect_rows;
+    int rc;
+    if ((rc = ensure(h, h->dispfull, n * 4))) return rc;
+    // env.disparity = zeros(full); copy ROI (wass_stereo.cpp:990-991)
+    launch_paste_roi((const float*)h->fa.p, h->dense_rows, h->dense_cols, (float*)h->dispfull.p, calib->rect_rows, calib->rect_cols,
+                     calib->roi_right[0], calib->roi_right[1], h->stream);
+    return triangulate_common(h, (const float*)h->dispfull.p, left, right, left_mask, right_mask, calib, p, n_points);
+}
+
+int wsg_mesh_upload(wsg_handle* h, int width, int height, const uint8_t* valid, const double* xyz, const uint8_t* grey)
+{
+    if (!h) return WSG_ERR_INVALID_ARG;
+    if (width <= 0 || height <= 0 || !valid || !xyz) { h->err = "bad argument"; return WSG_ERR_INVALID_ARG; }
+    CK(h, cudaSetDevice(h->device));
+    int rc = alloc_mesh(h, width, height);
+    if (rc) return rc;
+    const size_t n = (size_t)width * height;
+    std::vector<double> plane(n);
+    MeshView m = mesh_view(h);
+    double* dst[3] = {m.X, m.Y, m.Z};
+    for (int k = 0; k < 3; ++k) {
+        for (size_t i = 0; i < n; ++i) plane[i] = xyz[3 * i + k];
+        CK(h, cudaMemcpyAsync(dst[k], plane.data(), n * 8, cudaMemcpyHostToDevice, h->stream));
+        CK(h, cudaStreamSynchronize(h->stream));
+    }
+    CK(h, cudaMemcpyAsync(m.valid, valid, n, cudaMemcpyHostToDevice, h->stream));
+    if (grey) CK(h, cudaMemcpyAsync(m.color, grey, n, cudaMemcpyHostToDevice, h->stream));
+    else CK(h, cudaMemsetAsync(m.color, 0, n, h->stream));
+    CK(h, cudaStreamSynchronize(h->stream));
+    h->have_mesh = true;
+    return WSG_OK;
+}
+
+int wsg_mesh_download(wsg_handle* h, uint8_t* valid, double* xyz, uint8_t* grey)
+{
+    int rc = need_mesh(h);
+    if (rc) return rc;
+    const size_t n = (size_t)h->mesh_w * h->mesh_h;
+    MeshView m = mesh_view(h);
+    if (valid) CK(h, cudaMemcpyAsync(valid, m.valid, n, cudaMemcpyDeviceToHost, h->stream));
+    if (grey) CK(h, cudaMemcpyAsync(grey, m.color, n, cudaMemcpyDeviceToHost, h->stream));
+    if (xyz) {
+        std::vector<double> plane(n);
+        const double* src[3] = {m.X, m.Y, m.Z};
+        for (int k = 0; k < 3; ++k) {
+            CK(h, cudaMemcpyAsync(plane.data(), src[k], n * 8, cudaMemcpyDeviceToHost, h->stream));
+            CK(h, cudaStreamSynchronize(h->stream));
+            for (size_t i = 0; i < n; ++i) xyz[3 * i + k] = plane[i];
+        }
+    }
+    CK(h, cudaStreamSynchronize(h->stream));
+    return WSG_OK;
+}
+
+int wsg_mesh_size(wsg_handle* h, int* width, int* height, unsigned long long* n_valid)
+{
+    int rc = need_mesh(h);
+    if (rc) return rc;
+    if (width) *width = h->mesh_w;
+    if (height) *height = h->mesh_h;
+    if (n_valid) {
+        unsigned long long* counter = (unsigned long long*)h->m_small.p;
+        CK(h, cudaMemsetAsync(counter, 0, 8, h->stream));
+        launch_count_valid(mesh_view(h), counter, h->stream);
+        CK(h, cudaMemcpyAsync(n_valid, counter, 8, cudaMemcpyDeviceToHost, h->stream));
+        CK(h, cudaStreamSynchronize(h->stream));
+    }
+    return WSG_OK;
+}
+
+int wsg_mesh_zgap_percentile(wsg_handle* h, double percentile, double* zgap)
+{
+    int rc = need_mesh(h);
+    if (rc) return rc;
+    if (!zgap) return WSG_ERR_INVALID_ARG;
+    const size_t bytes = zgap_scratch_bytes(h->mesh_w, h->mesh_h);
+    if ((rc = ensure(h, h->m_scratch, bytes))) return rc;
+    StageTimer t(h, WSG_STAGE_MESH, 2);
+    if (mesh_zgap_percentile(mesh_view(h), percentile, h->m_scratch.p, bytes, zgap, h->stream)) { h->err = "zgap percentile failed"; return WSG_ERR_CUDA; }
+    CK(h, cudaGetLastError());
+    return WSG_OK;
+}
+
+int wsg_mesh_biggest_component(wsg_handle* h, double zgap, unsigned long long* n_left)
+{
+    int rc = need_mesh(h);
+    if (rc) return rc;
+    const size_t n = (size_t)h->mesh_w * h->mesh_h;
+    if ((rc = ensure(h, h->m_labels, n * 4))) return rc;
+    if ((rc = ensure(h, h->m_scratch, 64 + n * 4))) return rc;
+    unsigned long long left = 0;
+    StageTimer t(h, WSG_STAGE_MESH, 5);
+    if (mesh_biggest_component(mesh_view(h), zgap, (int*)h->m_labels.p, (unsigned long long*)h->m_scratch.p, &left, h->stream)) {
+        h->err = "connected components failed"; return WSG_ERR_CUDA;
+    }
+    CK(h, cudaGetLastError());
+    if (n_left) *n_left = left;
+    return WSG_OK;
+}
+
+int wsg_ransac_draw(int width, int height, int rounds, int32_t* triples)
+{
+    if (width <= 0 || height <= 0 || rounds < 0 || !triples) return WSG_ERR_INVALID_ARG;
+    const double mindist = height * 0.01;
+    for (int r = 0; r < rounds;) {
+        int c[6];
+        for (int k = 0; k < 6; ++k) c[k] = rand() % ((k & 1) ? height : width);
+        auto dist = [&](int a, int b) { const double dx = c[2 * a] - c[2 * b], dy = c[2 * a + 1] - c[2 * b + 1]; return sqrt(dx * dx + dy * dy); };
+        if (dist(0, 1) < mindist || dist(1, 2) < mindist || dist(0, 2) < mindist) continue;   // "round--; continue" of the reference
+        for (int k = 0; k < 6; ++k) triples[6 * r + k] = c[k];
+        ++r;
+    }
+    return WSG_OK;
+}
+
+int wsg_mesh_ransac_plane(wsg_handle* h, const int32_t* triples, int n, double threshold, double plane[4], int* ok,
+                          unsigned long long* best_inliers)
+{
+    int rc = need_mesh(h);
+    if (rc) return rc;
+    if (!triples || n <= 0 || !plane || !ok) { h->err = "bad argument"; return WSG_ERR_INVALID_ARG; }
+    for (int i = 0; i < n; ++i)
+        for (int k = 0; k < 6; ++k) {
+            const int v = triples[6 * i + k];
+            if (v < 0 || v >= ((k & 1) ? h->mesh_h : h->mesh_w)) { h->err = "triple outside the mesh"; return WSG_ERR_INVALID_ARG; }
+        }
+    const size_t bytes = (size_t)n * (6 * 4 + 4 * 8 + 4 + 8) + 256;
+    if ((rc = ensure(h, h->m_scratch, bytes))) return rc;
+    char* base = (char*)h->m_scratch.p;
+    double* planes = (double*)base;
+    unsigned long long* counts = (unsigned long long*)(base + (size_t)n * 32);
+    int* d_tr = (int*)(base + (size_t)n * 40);
+    int* d_ok = (int*)(base + (size_t)n * 64);
+    CK(h, cudaMemcpyAsync(d_tr, triples, (size_t)n * 24, cudaMemcpyHostToDevice, h->stream));
+    {
+        StageTimer t(h, WSG_STAGE_MESH, 2);
+        launch_ransac_planes(mesh_view(h), d_tr, n, planes, d_ok, h->stream);
+        launch_ransac_count(mesh_view(h), planes, d_ok, n, threshold, counts, h->stream);
+    }
+    std::vector<double> hp((size_t)n * 4);
+    std::vector<unsigned long long> hc(n);
+    std::vector<int> hok(n);
+    CK(h, cudaMemcpyAsync(hp.data(), planes, (size_t)n * 32, cudaMemcpyDeviceToHost, h->stream));
+    CK(h, cudaMemcpyAsync(hc.data(), counts, (size_t)n * 8, cudaMemcpyDeviceToHost, h->stream));
+    CK(h, cudaMemcpyAsync(hok.data(), d_ok, (size_t)n * 4, cudaMemcpyDeviceToHost, h->stream));
+    CK(h, cudaStreamSynchronize(h->stream));
+    CK(h, cudaGetLastError());
+    unsigned long long best = 0;
+    plane[0] = plane[1] = plane[2] = plane[3] = 0;
+    for (int i = 0; i < n; ++i)
+        if (hok[i] && hc[i] > best) { best = hc[i]; memcpy(plane, &hp[4 * (size_t)i], 32); }   // strict >: first best wins
+    *ok = !(best < (unsigned long long)((size_t)h->mesh_w * h->mesh_h / 10));
+    if (best_inliers) *best_inliers = best;
+    return WSG_OK;
+}
+
+int wsg_mesh_crop_plane(wsg_handle* h, const double plane[4], double threshold, unsigned long long* n_left)
+{
+    int rc = need_mesh(h);
+    if (rc) return rc;
+    if (!plane) return WSG_ERR_INVALID_ARG;
+    unsigned long long* counter = (unsigned long long*)h->m_small.p;
+    {
+        StageTimer t(h, WSG_STAGE_MESH, 1);
+        launch_crop_plane(mesh_view(h), plane[0], plane[1], plane[2], plane[3], threshold, counter, h->stream);
+    }
+    unsigned long long k = 0;
+    CK(h, cudaMemcpyAsync(&k, counter, 8, cudaMemcpyDeviceToHost, h->stream));
+    CK(h, cudaStreamSynchronize(h->stream));
+    CK(h, cudaGetLastError());
+    if (n_left) *n_left = k;
+    return WSG_OK;
+}
+
+int wsg_mesh_refine_plane(wsg_handle* h, const wsg_refine_params* p, double plane[4], unsigned long long* n_inliers)
+{
+    int rc = need_mesh(h);
+    if (rc) return rc;
+    if (!p || !plane) return WSG_ERR_INVALID_ARG;
+    const int W = h->mesh_w, H = h->mesh_h;
+    RefineArgs a;
+    a.xmin = p->PLANE_REFINE_XMIN; a.xmax = p->PLANE_REFINE_XMAX; a.ymin = p->PLANE_REFINE_YMIN; a.ymax = p->PLANE_REFINE_YMAX;
+    a.maxdist = p->PLANE_REFINEMENT_MAX_DISTANCE; a.weight_by_distance = p->PLANE_WEIGHT_PROPORTIONAL_TO_DISTANCE;
+    const bool ct = p->PLANE_USE_CENTRAL_THIRD_ONLY != 0;
+    a.umin = ct ? W / 4 : 0; a.umax = ct ? W * 3 / 4 : W - 1; a.vmin = ct ? H / 4 : 0; a.vmax = ct ? H * 2 / 3 : H - 1;
+    MeshView m = mesh_view(h);
+    const int nb = refine_blocks(m);
+    if ((rc = ensure(h, h->m_scratch, (size_t)nb * 6 * 8))) return rc;
+    double* part = (double*)h->m_scratch.p;
+    std::vector<double> hp((size_t)nb * 6);
+    StageTimer t(h, WSG_STAGE_MESH, 2);
+    launch_refine_pass1(m, a, part, h->stream);
+    CK(h, cudaMemcpyAsync(hp.data(), part, (size_t)nb * 5 * 8, cudaMemcpyDeviceToHost, h->stream));
+    CK(h, cudaStreamSynchronize(h->stream));
+    double s[5] = {0, 0, 0, 0, 0};
+    for (int b = 0; b < nb; ++b) for (int k = 0; k < 5; ++k) s[k] += hp[(size_t)b * 5 + k];
+    if (n_inliers) *n_inliers = (unsigned long long)s[4];
+    const double cx = s[1] / s[0], cy = s[2] / s[0], cz = s[3] / s[0];
+    launch_refine_pass2(m, a, cx, cy, cz, part, h->stream);
+    CK(h, cudaMemcpyAsync(hp.data(), part, (size_t)nb * 6 * 8, cudaMemcpyDeviceToHost, h->stream));
+    CK(h, cudaStreamSynchronize(h->stream));
+    CK(h, cudaGetLastError());
+    double q[6] = {0, 0, 0, 0, 0, 0};
+    for (int b = 0; b < nb; ++b) for (int k = 0; k < 6; ++k) q[k] += hp[(size_t)b * 6 + k];
+    double A[3][3] = {{q[0], q[1], q[2]}, {q[1], q[3], q[4]}, {q[2], q[4], q[5]}}, V[3][3], w[3];
+    jacobi_eigen3(A, V, w);
+    int mi = 0;   // smallest eigenvalue == last singular vector of the symmetric PSD scatter matrix (cv::SVD vt row 2)
+    for (int i = 1; i < 3; ++i) if (w[i] < w[mi]) mi = i;
+    double n0 = V[0][mi], n1 = V[1][mi], n2 = V[2][mi];
+    const double nn = sqrt(n0 * n0 + n1 * n1 + n2 * n2);
+    n0 /= nn; n1 /= nn; n2 /= nn;
+    if (n2 < 0) { n0 = -n0; n1 = -n1; n2 = -n2; }
+    plane[0] = n0; plane[1] = n1; plane[2] = n2; plane[3] = -(n0 * cx + n1 * cy + n2 * cz);
+    return WSG_OK;
+}
+
+void wsg_rt_from_plane(const double pl[4], double R[9], double T[3], double Rinv[9], double Tinv[3])
+{
+    const double a = pl[0], b = pl[1], c = pl[2], d = pl[3];
+    const double q = (1 - c) / (a * a + b * b);
+    R[0] = 1 - a * a * q; R[1] = -a * b * q; R[2] = -a;
+    R[3] = -a * b * q; R[4] = 1 - b * b * q; R[5] = -b;
+    R[6] = a; R[7] = b; R[8] = c;
+    for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) Rinv[3 * i + j] = R[3 * j + i];
+    T[0] = 0; T[1] = 0; T[2] = d;
+    for (int i = 0; i < 3; ++i) Tinv[i] = Rinv[3 * i] * (-T[0]) + Rinv[3 * i + 1] * (-T[1]) + Rinv[3 * i + 2] * (-T[2]);
+}
+
+int wsg_mesh_export_xyzc(wsg_handle* h, const double plane[4], void* dst, size_t capacity, size_t* nbytes)
+{
+    int rc = need_mesh(h);
+    if (rc) return rc;
+    if (!plane || !dst || !nbytes) return WSG_ERR_INVALID_ARG;
+    const int n = h->mesh_w * h->mesh_h;
+    double RT[12], Rinv[9], Tinv[3];
+    wsg_rt_from_plane(plane, RT, RT + 9, Rinv, Tinv);
+    const size_t cub_bytes = compact_cub_bytes(n);
+    if ((rc = ensure(h, h->m_scratch, (size_t)n * 8 + cub_bytes + 512))) return rc;
+    if ((rc = ensure(h, h->m_out, (size_t)n * 6 + 16))) return rc;
+    char* base = (char*)h->m_scratch.p;
+    double* d_RT = (double*)base;                 // 12 doubles
+    double* d_mm = (double*)(base + 128);         // 6 doubles (min xyz, max xyz)
+    double* d_ms = (double*)(base + 192);         // 3 mins + 3 scales
+    unsigned* scan_tmp = (unsigned*)(base + 256);
+    void* cub_tmp = base + 256 + (size_t)n * 8;
+    MeshView m = mesh_view(h);
+    StageTimer t(h, WSG_STAGE_MESH, 5);
+    CK(h, cudaMemcpyAsync(d_RT, RT, 96, cudaMemcpyHostToDevice, h->stream));
+    launch_plane_minmax(m, d_RT, nullptr, d_mm, h->stream);
+    double mm[6];
+    CK(h, cudaMemcpyAsync(mm, d_mm, 48, cudaMemcpyDeviceToHost, h->stream));
+    CK(h, cudaStreamSynchronize(h->stream));
+    const double MV = 65535.0;
+    double ms[6] = {mm[0], mm[1], mm[2], MV / (mm[3] - mm[0]), MV / (mm[4] - mm[1]), MV / (mm[5] - mm[2])};
+    CK(h, cudaMemcpyAsync(d_ms, ms, 48, cudaMemcpyHostToDevice, h->stream));
+    unsigned long long np = 0;
+    if (mesh_compact_quantise(m, d_RT, nullptr, d_ms, d_ms + 3, (uint16_t*)h->m_out.p, scan_tmp, cub_tmp, cub_bytes, &np, h->stream)) {
+        h->err = "compaction failed"; return WSG_ERR_CUDA;
+    }
+    const size_t total = 148 + (size_t)np * 6;
+    *nbytes = total;
+    if (capacity < total) { h->err = "destination too small"; return WSG_ERR_INVALID_ARG; }
+    char* o = (char*)dst;
+    const uint32_t n32 = (uint32_t)np;
+    memcpy(o, &n32, 4);
+    memcpy(o + 4, ms + 3, 24);      // xscale, yscale, zscale
+    memcpy(o + 28, ms, 24);         // minx, miny, minz
+    memcpy(o + 52, Rinv, 72);
+    memcpy(o + 124, Tinv, 24);
+    CK(h, cudaMemcpyAsync(o + 148, h->m_out.p, (size_t)np * 6, cudaMemcpyDeviceToHost, h->stream));
+    CK(h, cudaStreamSynchronize(h->stream));
+    CK(h, cudaGetLastError());
+    return WSG_OK;
+}
+
+int wsg_mesh_export_xyzbin(wsg_handle* h, void* dst, size_t capacity, size_t* nbytes)
+{
+    int rc = need_mesh(h);
+    if (rc) return rc;
+    if (!dst || !nbytes) return WSG_ERR_INVALID_ARG;
+    const int n = h->mesh_w * h->mesh_h;
+    const size_t cub_bytes = compact_cub_bytes(n);
+    if ((rc = ensure(h, h->m_scratch, (size_t)n * 8 + cub_bytes + 512))) return rc;
+    if ((rc = ensure(h, h->m_out, (size_t)n * 12 + 16))) return rc;
+    char* base = (char*)h->m_scratch.p;
+    unsigned long long np = 0;
+    StageTimer t(h, WSG_STAGE_MESH, 3);
+    if (mesh_compact_xyz(mesh_view(h), (float*)h->m_out.p, (unsigned*)(base + 256), base + 256 + (size_t)n * 8, cub_bytes, &np, h->stream)) {
+        h->err = "compaction failed"; return WSG_ERR_CUDA;
+    }
+    const size_t total = 4 + (size_t)np * 12;
+    *nbytes = total;
+    if (capacity < total) { h->err = "destination too small"; return WSG_ERR_INVALID_ARG; }
+    const uint32_t n32 = (uint32_t)np;
+    memcpy(dst, &n32, 4);
+    CK(h, cudaMemcpyAsync((char*)dst + 4, h->m_out.p, (size_t)np * 12, cudaMemcpyDeviceToHost, h->stream));
+    CK(h, cudaStreamSynchronize(h->stream));
+    CK(h, cudaGetLastError());
+    return WSG_OK;
+}
+
+void wsg_plane_mean_accumulate(double acc[5], const double plane[4])
+{
+    if (std::isnan(plane[0]) || std::isnan(plane[1]) || std::isnan(plane[2]) || std::isnan(plane[3])) return;
+    for (int k = 0; k < 4; ++k) acc[k] += plane[k];
+    acc[4] += 1.0;
+}
+
+void wsg_plane_mean_finish(const double acc[5], double mean[4])
+{
+    for (int k = 0; k < 4; ++k) mean[k] = acc[4] > 0 ? acc[k] / acc[4] : std::nan("");
+}
+
+}  // extern "C"

@@ -1,0 +1,637 @@
+// Stages of wass_stereo after the matcher, as sm_100a kernels (compiled with -fmad=false so that the
+// fp32/fp64 operation order of the reference is reproduced literally):
+//   disparity clean-up      src/wass_stereo/wass_stereo.cpp:617-733, 853-928
+//   triangulation           src/wass_stereo/wass_stereo.cpp:299-324, 1039-1386; src/wass_lib/triangulate.hpp:26-72
+//   PovMesh                 src/wass_stereo/PovMesh.cpp (zgap percentile, biggest component, RANSAC, crop, refine, export)
+#include "geom.cuh"
+
+#include <cub/cub.cuh>
+#include <cfloat>
+#include <climits>
+
+namespace wsg {
+
+// ------------------------------------------------------------------------------------------------
+// zero padding of the two crops (wass_stereo.cpp:820-831): img1 = padded RIGHT, img2 = padded LEFT
+// ------------------------------------------------------------------------------------------------
+__global__ void pad_kernel(const uint8_t* __restrict__ left, const uint8_t* __restrict__ right, size_t stride, int rows,
+                           int cols, int ndisp, int off, int comp, uint8_t* __restrict__ img1, uint8_t* __restrict__ img2, int wp)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= wp) return;
+    const int xr = x - ndisp;
+    const int xl = x - (ndisp + off - comp);
+    img1[(size_t)y * wp + x] = (xr >= 0 && xr < cols) ? right[(size_t)y * stride + xr] : 0;
+    img2[(size_t)y * wp + x] = (xl >= 0 && xl < cols) ? left[(size_t)y * stride + xl] : 0;
+}
+void launch_pad_images(const uint8_t* left, const uint8_t* right, size_t stride, int rows, int cols, int ndisp,
+                       int off, int comp, uint8_t* img1, uint8_t* img2, int wp, cudaStream_t st)
+{
+    dim3 b(256), g((wp + 255) / 256, rows);
+    pad_kernel<<<g, b, 0, st>>>(left, right, stride, rows, cols, ndisp, off, comp, img1, img2, wp);
+}
+
+// ------------------------------------------------------------------------------------------------
+// clean_and_convert_disparity (wass_stereo.cpp:714-733) on the column range [x0, x0+width)
+// ------------------------------------------------------------------------------------------------
+__global__ void clean_convert_kernel(const int16_t* __restrict__ disp16, int rows, int cols_full, int x0, int width,
+                                     int mindisp, int ndisp, int disp_offset, double scale, float* __restrict__ out)
+{
+    const int j = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y;
+    if (j >= width) return;
+    float dval = __fdiv_rn((float)disp16[(size_t)i * cols_full + x0 + j], 16.0f);
+    float r = 0.f;
+    if (!(dval <= (float)mindisp || dval > (float)ndisp)) {
+        dval = __fadd_rn(dval, (float)disp_offset);
+        r = (float)__dmul_rn((double)dval, scale);
+    }
+    out[(size_t)i * width + j] = r;
+}
+void launch_clean_convert(const int16_t* disp16, int rows, int cols_full, int x0, int width, int mindisp, int ndisp,
+                          int disp_offset, double scale, float* out, cudaStream_t st)
+{
+    dim3 b(256), g((width + 255) / 256, rows);
+    clean_convert_kernel<<<g, b, 0, st>>>(disp16, rows, cols_full, x0, width, mindisp, ndisp, disp_offset, scale, out);
+}
+
+// matrix_dilate_zero<float> (wass_stereo.cpp:617-662) with its one-column output shift
+__global__ void dilate_zero_kernel(const float* __restrict__ src, float* __restrict__ dst, int rows, int cols)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y;
+    if (k >= cols) return;
+    const size_t o = (size_t)i * cols + k;
+    float v = src[o];
+    if (i >= 1 && i <= rows - 2 && k <= cols - 3 && v == 0.f) {
+        const float* t = src + (size_t)(i - 1) * cols;
+        const float* b = src + (size_t)(i + 1) * cols;
+        const float* c = src + (size_t)i * cols;
+        // reference order: tm1, tp1, t, bm1, bp1, b, cm1, cp1 (columns relative to the centre k+1)
+        const float nb[8] = {t[k], t[k + 2], t[k + 1], b[k], b[k + 2], b[k + 1], c[k], c[k + 2]};
+        float avg = 0.f; int num = 0;
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+            if (nb[q] > 0.f) { avg = __fadd_rn(avg, nb[q]); ++num; }
+        if (num > 1) v = __fdiv_rn(avg, (float)num);
+    }
+    dst[o] = v;
+}
+void launch_dilate_zero(const float* src, float* dst, int rows, int cols, cudaStream_t st)
+{
+    dim3 b(256), g((cols + 255) / 256, rows);
+    dilate_zero_kernel<<<g, b, 0, st>>>(src, dst, rows, cols);
+}
+
+// matrix_erode_zero<float> (wass_stereo.cpp:665-711)
+__global__ void erode_zero_kernel(const float* __restrict__ src, float* __restrict__ dst, int rows, int cols)
+{
+    const int j = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y;
+    if (j >= cols) return;
+    const size_t o = (size_t)i * cols + j;
+    float v = src[o];
+    if (i == 0 || i == rows - 1 || j == 0 || j == cols - 1) {
+        v = 0.f;
+    } else {
+        const float* t = src + (size_t)(i - 1) * cols + j;
+        const float* b = src + (size_t)(i + 1) * cols + j;
+        const float* c = src + (size_t)i * cols + j;
+        if (t[0] == 0.f || t[-1] == 0.f || t[1] == 0.f || b[0] == 0.f || b[-1] == 0.f || b[1] == 0.f || c[-1] == 0.f || c[1] == 0.f)
+            v = 0.f;
+    }
+    dst[o] = v;
+}
+void launch_erode_zero(const float* src, float* dst, int rows, int cols, cudaStream_t st)
+{
+    dim3 b(256), g((cols + 255) / 256, rows);
+    erode_zero_kernel<<<g, b, 0, st>>>(src, dst, rows, cols);
+}
+// wass_stereo.cpp:903-928 at DENSE_SCALE==1: zero the pixels that one more erosion would zero == one more erosion
+void launch_mask_by_eroded(const float* src, float* dst, int rows, int cols, cudaStream_t st)
+{
+    launch_erode_zero(src, dst, rows, cols, st);
+}
+
+__global__ void paste_kernel(const float* __restrict__ roi, int rh, int rw, float* __restrict__ full, int rows, int cols, int x0, int y0)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= cols) return;
+    const int u = x - x0, v = y - y0;
+    full[(size_t)y * cols + x] = (u >= 0 && u < rw && v >= 0 && v < rh) ? roi[(size_t)v * rw + u] : 0.f;
+}
+void launch_paste_roi(const float* roi, int rh, int rw, float* full, int rows, int cols, int x0, int y0, cudaStream_t st)
+{
+    dim3 b(256), g((cols + 255) / 256, rows);
+    paste_kernel<<<g, b, 0, st>>>(roi, rh, rw, full, rows, cols, x0, y0);
+}
+
+// ------------------------------------------------------------------------------------------------
+// triangulation: one thread per ROI pixel
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void unrectify_dev(double u, double v, const double* K, const double* Rr, double fx, double fy,
+                                              double cx, double cy, double& ox, double& oy)
+{
+    // wass_stereo.cpp:313-322 : xyw = Rrect^T * ((u-cx)/fx, (v-cy)/fy, 1); project with the original intrinsics
+    const double x = (u - cx) / fx, y = (v - cy) / fy;
+    double a = Rr[0] * x + Rr[3] * y + Rr[6] * 1.0;
+    double b = Rr[1] * x + Rr[4] * y + Rr[7] * 1.0;
+    const double c = Rr[2] * x + Rr[5] * y + Rr[8] * 1.0;
+    a /= c; b /= c;
+    ox = a * K[0] + K[2];
+    oy = b * K[4] + K[5];
+}
+
+__global__ void triangulate_kernel(const float* __restrict__ disparity, const uint8_t* __restrict__ left,
+                                   const uint8_t* __restrict__ right, const uint8_t* __restrict__ lmask,
+                                   const uint8_t* __restrict__ rmask, CalibDev c, MeshView m, unsigned long long* counter)
+{
+    const int u = blockIdx.x * blockDim.x + threadIdx.x, v = blockIdx.y;
+    if (u >= m.w) return;
+    const int xr = c.rrx + u, yr = c.rry + v;
+    const float dv = disparity[(size_t)yr * c.rect_cols + xr];
+    if (!(dv > 1.0f)) return;
+    // wass_stereo.cpp:1180-1181 : int - float in float, then + double, then cast to float
+    float xl = (float)((double)((float)(xr - c.rrx + c.rlx) - dv) + c.comp_over_scale);
+    const float yl = (float)yr;
+    if (xl < 0.f || xl >= (float)c.rect_cols) return;
+    double pix, piy, qix, qiy;
+    unrectify_dev((double)xl, (double)yl, c.K0, c.R1, c.P1fx, c.P1fy, c.P1cx, c.P1cy, pix, piy);
+    unrectify_dev((double)xr, (double)yr, c.K1, c.R2, c.P2fx, c.P2fy, c.P2cx, c.P2cy, qix, qiy);
+    if (pix < 1 || pix >= c.left_cols - 1 || piy < 1 || piy >= c.left_rows - 1 || qix < 1 || qix >= c.right_cols - 1 ||
+        qiy < 1 || qiy >= c.right_rows - 1)
+        return;
+    const double px = (pix - c.K0[2]) / c.K0[0], py = (piy - c.K0[5]) / c.K0[4];
+    const double qx = (qix - c.K1[2]) / c.K1[0], qy = (qiy - c.K1[5]) / c.K1[4];
+    if (pix <= c.bbox_l || piy <= c.bbox_t || pix >= c.bbox_r || piy >= c.bbox_b) return;
+    {
+        const size_t li = (size_t)(int)piy * c.left_cols + (int)pix;
+        const size_t ri = (size_t)(int)qiy * c.right_cols + (int)qix;
+        if (c.has_lmask && lmask[li] == 0) return;
+        if (c.has_rmask && rmask[ri] == 0) return;
+        if (c.discard_burned && (left[li] > 254 || right[ri] > 254)) return;
+    }
+    if (c.min_angle > 0) {
+        const double n1 = sqrt(px * px + py * py + 1.0 * 1.0);
+        const double s1 = n1 != 0 ? 1.0 / n1 : 0.0;
+        const double b0 = c.R[0] * qx + c.R[1] * qy + c.R[2] * 1.0 + c.T[0];
+        const double b1 = c.R[3] * qx + c.R[4] * qy + c.R[5] * 1.0 + c.T[1];
+        const double b2 = c.R[6] * qx + c.R[7] * qy + c.R[8] * 1.0 + c.T[2];
+        const double n2 = sqrt(b0 * b0 + b1 * b1 + b2 * b2);
+        const double s2 = n2 != 0 ? 1.0 / n2 : 0.0;
+        const double dot = (px * s1) * (b0 * s2) + (py * s1) * (b1 * s2) + (1.0 * s1) * (b2 * s2);
+        const double ang = fabs(acos(dot) * 57.29577951);
+        if (ang < c.min_angle) return;
+    }
+    // triangulate.hpp:26-72
+    const double* R = c.R;
+    double Af[12], Bf[4];
+    Af[0] = -1.0; Af[1] = 0.0; Af[2] = px;
+    Af[3] = 0.0; Af[4] = -1.0; Af[5] = py;
+    Af[6] = qx * R[6] - R[0]; Af[7] = qx * R[7] - R[1]; Af[8] = qx * R[8] - R[2];
+    Af[9] = qy * R[6] - R[3]; Af[10] = qy * R[7] - R[4]; Af[11] = qy * R[8] - R[5];
+    Bf[0] = 0.0; Bf[1] = 0.0; Bf[2] = c.T[0] - c.T[2] * qx; Bf[3] = c.T[1] - c.T[2] * qy;
+    double A[9], b[3];
+    A[0] = Af[0] * Af[0] + Af[3] * Af[3] + Af[6] * Af[6] + Af[9] * Af[9];
+    A[1] = Af[0] * Af[1] + Af[3] * Af[4] + Af[10] * Af[9] + Af[6] * Af[7];
+    A[2] = Af[0] * Af[2] + Af[3] * Af[5] + Af[11] * Af[9] + Af[6] * Af[8];
+    A[3] = A[1];
+    A[4] = Af[1] * Af[1] + Af[10] * Af[10] + Af[4] * Af[4] + Af[7] * Af[7];
+    A[5] = Af[10] * Af[11] + Af[1] * Af[2] + Af[4] * Af[5] + Af[7] * Af[8];
+    A[6] = A[2]; A[7] = A[5];
+    A[8] = Af[11] * Af[11] + Af[2] * Af[2] + Af[5] * Af[5] + Af[8] * Af[8];
+    b[0] = Af[0] * Bf[0] + Af[3] * Bf[1] + Af[6] * Bf[2] + Af[9] * Bf[3];
+    b[1] = Af[1] * Bf[0] + Af[10] * Bf[3] + Af[4] * Bf[1] + Af[7] * Bf[2];
+    b[2] = Af[2] * Bf[0] + Af[11] * Bf[3] + Af[5] * Bf[1] + Af[8] * Bf[2];
+    // cv::solve(DECOMP_LU) on 3x3 == closed form with the determinant (OpenCV fast path)
+    const double det = A[0] * (A[4] * A[8] - A[5] * A[7]) - A[1] * (A[3] * A[8] - A[5] * A[6]) + A[2] * (A[3] * A[7] - A[4] * A[6]);
+    double X0 = 0, X1 = 0, X2 = 0;
+    if (det != 0.0) {
+        const double d = 1.0 / det;
+        X0 = d * (b[0] * (A[4] * A[8] - A[5] * A[7]) - A[1] * (b[1] * A[8] - A[5] * b[2]) + A[2] * (b[1] * A[7] - A[4] * b[2]));
+        X1 = d * (A[0] * (b[1] * A[8] - A[5] * b[2]) - b[0] * (A[3] * A[8] - A[5] * A[6]) + A[2] * (A[3] * b[2] - b[1] * A[6]));
+        X2 = d * (A[0] * (A[4] * b[2] - b[1] * A[7]) - A[1] * (A[3] * b[2] - b[1] * A[6]) + b[0] * (A[3] * A[7] - A[4] * A[6]));
+    }
+    const double dist = sqrt(X0 * X0 + X1 * X1 + X2 * X2);
+    if (dist < c.cam_distance / 10.0 || X2 < 1.0) return;
+    if (dist > c.cam_distance * 200.0 || X2 > 1e30) return;
+    const size_t o = (size_t)v * m.w + u;
+    m.valid[o] = 1; m.X[o] = X0; m.Y[o] = X1; m.Z[o] = X2;
+    m.color[o] = right[(size_t)(int)qiy * c.right_cols + (int)qix];
+    atomicAdd(counter, 1ull);
+}
+void launch_triangulate(const float* disparity, const uint8_t* left, const uint8_t* right, const uint8_t* lmask,
+                        const uint8_t* rmask, const CalibDev& c, MeshView m, unsigned long long* counter, cudaStream_t st)
+{
+    dim3 b(128), g((m.w + 127) / 128, m.h);
+    triangulate_kernel<<<g, b, 0, st>>>(disparity, left, right, lmask, rmask, c, m, counter);
+}
+
+__global__ void count_valid_kernel(MeshView m, unsigned long long* counter)
+{
+    const size_t n = (size_t)m.w * m.h;
+    unsigned long long loc = 0;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) loc += m.valid[i];
+    for (int o = 16; o > 0; o >>= 1) loc += __shfl_xor_sync(0xffffffffu, loc, o);
+    if ((threadIdx.x & 31) == 0 && loc) atomicAdd(counter, loc);
+}
+void launch_count_valid(const MeshView& m, unsigned long long* counter, cudaStream_t st)
+{
+    count_valid_kernel<<<296, 256, 0, st>>>(m, counter);
+}
+
+// ------------------------------------------------------------------------------------------------
+// compute_zgap_percentile (PovMesh.cpp:888-926): exact order statistic by sorting all gaps
+// ------------------------------------------------------------------------------------------------
+__global__ void zgap_kernel(MeshView m, double* gaps, unsigned long long* count)
+{
+    const int j = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y;
+    if (j >= m.w) return;
+    const size_t o = (size_t)i * m.w + j;
+    double g0 = DBL_MAX, g1 = DBL_MAX, g2 = DBL_MAX;
+    int n = 0;
+    if (i >= 1 && j >= 1 && j <= m.w - 2 && m.valid[o]) {
+        const double z = m.Z[o];
+        const size_t up = o - m.w;
+        if (m.valid[up - 1]) { g0 = fabs(z - m.Z[up - 1]); ++n; }
+        if (m.valid[up]) { g1 = fabs(z - m.Z[up]); ++n; }
+        if (m.valid[up + 1]) { g2 = fabs(z - m.Z[up + 1]); ++n; }
+    }
+    gaps[3 * o] = g0; gaps[3 * o + 1] = g1; gaps[3 * o + 2] = g2;
+    if (n) atomicAdd(count, (unsigned long long)n);
+}
+size_t zgap_scratch_bytes(int w, int h)
+{
+    const size_t n = (size_t)3 * w * h;
+    size_t tmp = 0;
+    cub::DeviceRadixSort::SortKeys(nullptr, tmp, (const double*)nullptr, (double*)nullptr, (int)n);
+    return 2 * n * sizeof(double) + tmp + 256;
+}
+int mesh_zgap_percentile(const MeshView& m, double percentile, void* scratch, size_t scratch_bytes, double* out_host, cudaStream_t st)
+{
+    const size_t n = (size_t)3 * m.w * m.h;
+    double* a = (double*)scratch;
+    double* b = a + n;
+    unsigned long long* cnt = (unsigned long long*)(b + n);
+    void* tmp = (void*)(cnt + 16);
+    size_t tmp_bytes = scratch_bytes - (2 * n * sizeof(double) + 128);
+    cudaMemsetAsync(cnt, 0, 8, st);
+    dim3 blk(256), g((m.w + 255) / 256, m.h);
+    zgap_kernel<<<g, blk, 0, st>>>(m, a, cnt);
+    cub::DeviceRadixSort::SortKeys(tmp, tmp_bytes, a, b, (int)n, 0, 64, st);
+    unsigned long long k = 0;
+    cudaMemcpyAsync(&k, cnt, 8, cudaMemcpyDeviceToHost, st);
+    if (cudaStreamSynchronize(st) != cudaSuccess) return -1;
+    if (k == 0) { *out_host = nan(""); return 0; }
+    size_t idx = (size_t)floor(percentile / 100.0 * (double)k);
+    if (idx >= k) { *out_host = nan(""); return 0; }   // the reference reads past the end here (percentile >= 100)
+    cudaMemcpyAsync(out_host, b + idx, 8, cudaMemcpyDeviceToHost, st);
+    return cudaStreamSynchronize(st) == cudaSuccess ? 0 : -1;
+}
+
+// ------------------------------------------------------------------------------------------------
+// cluster_biggest_connected_component (PovMesh.cpp:929-987): union-find on 4-connected edges with
+// |dz| < zgap; label = smallest column-major index of the component, so ties between equally big
+// components resolve to the one the reference's column-major rescan finds first.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int uf_find(int* L, int x)
+{
+    int p = L[x];
+    while (p != x) { x = p; p = L[x]; }
+    return x;
+}
+__device__ __forceinline__ void uf_union(int* L, int a, int b)
+{
+    while (true) {
+        a = uf_find(L, a); b = uf_find(L, b);
+        if (a == b) return;
+        if (a > b) { const int t = a; a = b; b = t; }
+        const int old = atomicMin(&L[b], a);
+        if (old == b) return;
+        b = old;
+    }
+}
+__global__ void ccl_init_kernel(MeshView m, int* L)
+{
+    const int u = blockIdx.x * blockDim.x + threadIdx.x, v = blockIdx.y;
+    if (u >= m.w) return;
+    const int id = u * m.h + v;
+    L[id] = m.valid[(size_t)v * m.w + u] ? id : INT_MAX;
+}
+__global__ void ccl_merge_kernel(MeshView m, int* L, double zgap)
+{
+    const int u = blockIdx.x * blockDim.x + threadIdx.x, v = blockIdx.y;
+    if (u >= m.w) return;
+    const size_t o = (size_t)v * m.w + u;
+    if (!m.valid[o]) return;
+    const double z = m.Z[o];
+    const int id = u * m.h + v;
+    if (u + 1 < m.w && m.valid[o + 1] && fabs(z - m.Z[o + 1]) < zgap) uf_union(L, id, id + m.h);
+    if (v + 1 < m.h && m.valid[o + m.w] && fabs(z - m.Z[o + m.w]) < zgap) uf_union(L, id, id + 1);
+}
+__global__ void ccl_flatten_count_kernel(MeshView m, int* L, unsigned* cnt)
+{
+    const int u = blockIdx.x * blockDim.x + threadIdx.x, v = blockIdx.y;
+    if (u >= m.w) return;
+    const int id = u * m.h + v;
+    if (L[id] == INT_MAX) return;
+    const int r = uf_find(L, id);
+    L[id] = r;
+    atomicAdd(&cnt[r], 1u);
+}
+__global__ void ccl_best_kernel(const unsigned* cnt, int n, unsigned long long* best)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n || cnt[i] == 0) return;
+    atomicMax(best, ((unsigned long long)cnt[i] << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)i));
+}
+__global__ void ccl_extract_kernel(MeshView m, const int* L, const unsigned long long* best)
+{
+    const int u = blockIdx.x * blockDim.x + threadIdx.x, v = blockIdx.y;
+    if (u >= m.w) return;
+    const int lab = (int)(0xFFFFFFFFu - (unsigned)(*best & 0xFFFFFFFFull));
+    const size_t o = (size_t)v * m.w + u;
+    if (m.valid[o] && L[u * m.h + v] != lab) m.valid[o] = 0;
+}
+int mesh_biggest_component(MeshView m, double zgap, int* labels, unsigned long long* scratch, unsigned long long* n_left_host, cudaStream_t st)
+{
+    const int n = m.w * m.h;
+    unsigned* cnt = (unsigned*)(scratch + 2);
+    cudaMemsetAsync(scratch, 0, 16 + (size_t)n * sizeof(unsigned), st);
+    dim3 b(128), g((m.w + 127) / 128, m.h);
+    ccl_init_kernel<<<g, b, 0, st>>>(m, labels);
+    ccl_merge_kernel<<<g, b, 0, st>>>(m, labels, zgap);
+    ccl_flatten_count_kernel<<<g, b, 0, st>>>(m, labels, cnt);
+    ccl_best_kernel<<<(n + 255) / 256, 256, 0, st>>>(cnt, n, scratch);
+    ccl_extract_kernel<<<g, b, 0, st>>>(m, labels, scratch);
+    unsigned long long best = 0;
+    cudaMemcpyAsync(&best, scratch, 8, cudaMemcpyDeviceToHost, st);
+    if (cudaStreamSynchronize(st) != cudaSuccess) return -1;
+    *n_left_host = best >> 32;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// ransac_find_plane (PovMesh.cpp:665-777): host draws the pixel triples with libc rand(); the device
+// builds all hypotheses and scores every one against every point in a single pass over the mesh.
+// ------------------------------------------------------------------------------------------------
+__global__ void ransac_planes_kernel(MeshView m, const int* __restrict__ triples, int n, double* planes, int* ok)
+{
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    const int* t = triples + 6 * r;
+    const size_t i1 = (size_t)t[1] * m.w + t[0], i2 = (size_t)t[3] * m.w + t[2], i3 = (size_t)t[5] * m.w + t[4];
+    if (!m.valid[i1] || !m.valid[i2] || !m.valid[i3]) { ok[r] = 0; return; }
+    const double ax = m.X[i2] - m.X[i1], ay = m.Y[i2] - m.Y[i1], az = m.Z[i2] - m.Z[i1];
+    const double bx = m.X[i3] - m.X[i1], by = m.Y[i3] - m.Y[i1], bz = m.Z[i3] - m.Z[i1];
+    double nx = ay * bz - az * by, ny = az * bx - ax * bz, nz = ax * by - ay * bx;
+    const double s = 1.0 / sqrt(nx * nx + ny * ny + nz * nz);   // cv::Vec / double multiplies by the reciprocal
+    nx *= s; ny *= s; nz *= s;
+    if (nz < 0) { nx *= -1.0; ny *= -1.0; nz *= -1.0; }
+    planes[4 * r] = nx; planes[4 * r + 1] = ny; planes[4 * r + 2] = nz;
+    planes[4 * r + 3] = -(nx * m.X[i1] + ny * m.Y[i1] + nz * m.Z[i1]);
+    ok[r] = 1;
+}
+void launch_ransac_planes(const MeshView& m, const int* triples, int n, double* planes, int* ok, cudaStream_t st)
+{
+    ransac_planes_kernel<<<(n + 127) / 128, 128, 0, st>>>(m, triples, n, planes, ok);
+}
+
+static constexpr int RH = 64;   // hypotheses scored per pass over a point
+__global__ void __launch_bounds__(256) ransac_count_kernel(MeshView m, const double* __restrict__ planes, const int* __restrict__ ok,
+                                                           int n, double thr, unsigned long long* counts)
+{
+    __shared__ double sp[RH * 4];
+    __shared__ unsigned sc[RH];
+    const size_t npts = (size_t)m.w * m.h;
+    for (int h0 = 0; h0 < n; h0 += RH) {
+        const int nh = min(RH, n - h0);
+        __syncthreads();
+        for (int i = threadIdx.x; i < nh * 4; i += blockDim.x) sp[i] = planes[4 * h0 + i];
+        for (int i = threadIdx.x; i < RH; i += blockDim.x) sc[i] = 0;
+        __syncthreads();
+        for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < ((npts + 31) / 32) * 32; i += (size_t)gridDim.x * blockDim.x) {
+            const bool v = i < npts && m.valid[i];
+            const double x = v ? m.X[i] : 0, y = v ? m.Y[i] : 0, z = v ? m.Z[i] : 0;
+            if (__any_sync(0xffffffffu, v)) {
+                for (int hh = 0; hh < nh; ++hh) {
+                    const double d = fabs(sp[4 * hh] * x + sp[4 * hh + 1] * y + sp[4 * hh + 2] * z + sp[4 * hh + 3]);
+                    const unsigned bal = __ballot_sync(0xffffffffu, v && d < thr);
+                    if ((threadIdx.x & 31) == 0 && bal) atomicAdd(&sc[hh], __popc(bal));
+                }
+            }
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < nh; i += blockDim.x)
+            if (sc[i] && ok[h0 + i]) atomicAdd(&counts[h0 + i], (unsigned long long)sc[i]);
+    }
+}
+void launch_ransac_count(const MeshView& m, const double* planes, const int* ok, int n, double thr, unsigned long long* counts, cudaStream_t st)
+{
+    cudaMemsetAsync(counts, 0, (size_t)n * 8, st);
+    ransac_count_kernel<<<148 * 4, 256, 0, st>>>(m, planes, ok, n, thr, counts);
+}
+
+// crop_plane (PovMesh.cpp:780-815)
+__global__ void crop_plane_kernel(MeshView m, double a, double b, double c, double d, double thr, unsigned long long* counter)
+{
+    const size_t n = (size_t)m.w * m.h;
+    unsigned long long loc = 0;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        if (m.valid[i]) {
+            const double dist = fabs(a * m.X[i] + b * m.Y[i] + c * m.Z[i] + d);
+            if (dist < thr) ++loc; else m.valid[i] = 0;
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) loc += __shfl_xor_sync(0xffffffffu, loc, o);
+    if ((threadIdx.x & 31) == 0 && loc) atomicAdd(counter, loc);
+}
+void launch_crop_plane(MeshView m, double a, double b, double c, double d, double thr, unsigned long long* counter, cudaStream_t st)
+{
+    cudaMemsetAsync(counter, 0, 8, st);
+    crop_plane_kernel<<<296, 256, 0, st>>>(m, a, b, c, d, thr, counter);
+}
+
+// ------------------------------------------------------------------------------------------------
+// refine_plane (PovMesh.cpp:581-660): weighted centroid, then weighted scatter matrix; per-block
+// partial sums in a fixed order, summed on the host (deterministic).
+// ------------------------------------------------------------------------------------------------
+static constexpr int RBLK = 296;
+int refine_blocks(const MeshView&) { return RBLK; }
+
+__device__ __forceinline__ bool refine_inlier(const MeshView& m, const RefineArgs& a, size_t i, double& x, double& y, double& z, double& w)
+{
+    if (!m.valid[i]) return false;
+    const int v = (int)(i / m.w), u = (int)(i % m.w);
+    if (u < a.umin || u > a.umax || v < a.vmin || v > a.vmax) return false;
+    x = m.X[i]; y = m.Y[i]; z = m.Z[i];
+    const double dist = sqrt(x * x + y * y + z * z);
+    if (!(x > a.xmin && x < a.xmax && y > a.ymin && y < a.ymax && dist < a.maxdist)) return false;
+    w = a.weight_by_distance ? dist : 1.0;
+    return true;
+}
+template <int NV>
+__device__ __forceinline__ void block_sum_store(double (&acc)[NV], double* out)
+{
+    __shared__ double sh[NV][8];
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+        double v = acc[k];
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if ((threadIdx.x & 31) == 0) sh[k][threadIdx.x >> 5] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < NV) {
+        double s = 0;
+        for (int wv = 0; wv < 8; ++wv) s += sh[threadIdx.x][wv];
+        out[blockIdx.x * NV + threadIdx.x] = s;
+    }
+}
+__global__ void __launch_bounds__(256) refine1_kernel(MeshView m, RefineArgs a, double* partial)
+{
+    double acc[5] = {0, 0, 0, 0, 0};   // wsum, sum w*x, w*y, w*z, count
+    const size_t n = (size_t)m.w * m.h;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        double x, y, z, w;
+        if (refine_inlier(m, a, i, x, y, z, w)) { acc[0] += w; acc[1] += x * w; acc[2] += y * w; acc[3] += z * w; acc[4] += 1.0; }
+    }
+    block_sum_store<5>(acc, partial);
+}
+__global__ void __launch_bounds__(256) refine2_kernel(MeshView m, RefineArgs a, double cx, double cy, double cz, double* partial)
+{
+    double acc[6] = {0, 0, 0, 0, 0, 0};   // xx xy xz yy yz zz
+    const size_t n = (size_t)m.w * m.h;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        double x, y, z, w;
+        if (refine_inlier(m, a, i, x, y, z, w)) {
+            x -= cx; y -= cy; z -= cz;
+            acc[0] += w * x * x; acc[1] += w * x * y; acc[2] += w * x * z; acc[3] += w * y * y; acc[4] += w * y * z; acc[5] += w * z * z;
+        }
+    }
+    block_sum_store<6>(acc, partial);
+}
+void launch_refine_pass1(const MeshView& m, const RefineArgs& a, double* partial, cudaStream_t st)
+{
+    refine1_kernel<<<RBLK, 256, 0, st>>>(m, a, partial);
+}
+void launch_refine_pass2(const MeshView& m, const RefineArgs& a, double cx, double cy, double cz, double* partial, cudaStream_t st)
+{
+    refine2_kernel<<<RBLK, 256, 0, st>>>(m, a, cx, cy, cz, partial);
+}
+
+// ------------------------------------------------------------------------------------------------
+// save_as_xyz_compressed (PovMesh.cpp:377-460): limits in the plane frame, then quantise + compact
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void to_plane(const double* R, const double* T, double x, double y, double z, double& a, double& b, double& c)
+{
+    a = R[0] * x + R[1] * y + R[2] * z + T[0];
+    b = R[3] * x + R[4] * y + R[5] * z + T[1];
+    c = R[6] * x + R[7] * y + R[8] * z + T[2];
+}
+__device__ __forceinline__ unsigned long long dkey(double v)
+{   // order-preserving map double -> u64
+    unsigned long long u = (unsigned long long)__double_as_longlong(v);
+    return (u & 0x8000000000000000ull) ? ~u : (u | 0x8000000000000000ull);
+}
+__device__ __forceinline__ double dunkey(unsigned long long k)
+{
+    const unsigned long long u = (k & 0x8000000000000000ull) ? (k & 0x7FFFFFFFFFFFFFFFull) : ~k;
+    return __longlong_as_double((long long)u);
+}
+__global__ void plane_minmax_kernel(MeshView m, const double* __restrict__ RT, unsigned long long* mm)
+{
+    double R[9], T[3];
+    for (int i = 0; i < 9; ++i) R[i] = RT[i];
+    for (int i = 0; i < 3; ++i) T[i] = RT[9 + i];
+    unsigned long long lo[3] = {~0ull, ~0ull, ~0ull}, hi[3] = {0, 0, 0};
+    const size_t n = (size_t)m.w * m.h;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        if (!m.valid[i]) continue;
+        double p[3];
+        to_plane(R, T, m.X[i], m.Y[i], m.Z[i], p[0], p[1], p[2]);
+        for (int k = 0; k < 3; ++k) { const unsigned long long key = dkey(p[k]); lo[k] = min(lo[k], key); hi[k] = max(hi[k], key); }
+    }
+    for (int k = 0; k < 3; ++k) {
+        for (int o = 16; o > 0; o >>= 1) {
+            lo[k] = min(lo[k], __shfl_xor_sync(0xffffffffu, lo[k], o));
+            hi[k] = max(hi[k], __shfl_xor_sync(0xffffffffu, hi[k], o));
+        }
+        if ((threadIdx.x & 31) == 0) { atomicMin(&mm[k], lo[k]); atomicMax(&mm[3 + k], hi[k]); }
+    }
+}
+__global__ void minmax_decode_kernel(const unsigned long long* mm, double* out)
+{
+    if (threadIdx.x < 6) out[threadIdx.x] = dunkey(mm[threadIdx.x]);
+}
+void launch_plane_minmax(const MeshView& m, const double* RT12_dev_and_out, const double* /*unused*/, double* minmax6, cudaStream_t st)
+{
+    // minmax6 doubles as scratch: first 6 x u64 keys, decoded in place afterwards
+    unsigned long long* mm = (unsigned long long*)minmax6;
+    const unsigned long long init[6] = {~0ull, ~0ull, ~0ull, 0, 0, 0};
+    cudaMemcpyAsync(mm, init, sizeof(init), cudaMemcpyHostToDevice, st);
+    plane_minmax_kernel<<<296, 256, 0, st>>>(m, RT12_dev_and_out, mm);
+    minmax_decode_kernel<<<1, 32, 0, st>>>(mm, minmax6);
+}
+
+__global__ void flags_kernel(MeshView m, unsigned* flags)
+{
+    const size_t n = (size_t)m.w * m.h;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) flags[i] = m.valid[i] ? 1u : 0u;
+}
+__global__ void quantise_scatter_kernel(MeshView m, const double* __restrict__ RT, const double* __restrict__ mins, const double* __restrict__ scl,
+                                        const unsigned* __restrict__ pos, uint16_t* __restrict__ out)
+{
+    double R[9], T[3];
+    for (int i = 0; i < 9; ++i) R[i] = RT[i];
+    for (int i = 0; i < 3; ++i) T[i] = RT[9 + i];
+    const size_t n = (size_t)m.w * m.h;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        if (!m.valid[i]) continue;
+        double p[3];
+        to_plane(R, T, m.X[i], m.Y[i], m.Z[i], p[0], p[1], p[2]);
+        uint16_t* o = out + (size_t)pos[i] * 3;
+        for (int k = 0; k < 3; ++k) o[k] = (uint16_t)(unsigned)__double2uint_rz((p[k] - mins[k]) * scl[k]);
+    }
+}
+__global__ void xyz_scatter_kernel(MeshView m, const unsigned* __restrict__ pos, float* __restrict__ out)
+{
+    const size_t n = (size_t)m.w * m.h;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        if (!m.valid[i]) continue;
+        float* o = out + (size_t)pos[i] * 3;
+        o[0] = (float)m.X[i]; o[1] = (float)m.Y[i]; o[2] = (float)m.Z[i];
+    }
+}
+size_t compact_cub_bytes(int n)
+{
+    size_t tmp = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, tmp, (const unsigned*)nullptr, (unsigned*)nullptr, n);
+    return tmp;
+}
+static int scan_positions(const MeshView& m, unsigned* scan_tmp, void* cub_tmp, size_t cub_bytes, unsigned long long* n_host, cudaStream_t st)
+{
+    const int n = m.w * m.h;
+    unsigned* flags = scan_tmp;
+    unsigned* pos = scan_tmp + n;
+    flags_kernel<<<296, 256, 0, st>>>(m, flags);
+    cub::DeviceScan::ExclusiveSum(cub_tmp, cub_bytes, flags, pos, n, st);
+    unsigned lastp = 0, lastf = 0;
+    cudaMemcpyAsync(&lastp, pos + n - 1, 4, cudaMemcpyDeviceToHost, st);
+    cudaMemcpyAsync(&lastf, flags + n - 1, 4, cudaMemcpyDeviceToHost, st);
+    if (cudaStreamSynchronize(st) != cudaSuccess) return -1;
+    *n_host = (unsigned long long)lastp + lastf;
+    return 0;
+}
+int mesh_compact_quantise(const MeshView& m, const double* RT, const double* /*T3*/, const double* min3, const double* scale3,
+                          uint16_t* out, unsigned* scan_tmp, void* cub_tmp, size_t cub_bytes, unsigned long long* n_host, cudaStream_t st)
+{
+    if (scan_positions(m, scan_tmp, cub_tmp, cub_bytes, n_host, st)) return -1;
+    quantise_scatter_kernel<<<296, 256, 0, st>>>(m, RT, min3, scale3, scan_tmp + (size_t)m.w * m.h, out);
+    return 0;
+}
+int mesh_compact_xyz(const MeshView& m, float* out, unsigned* scan_tmp, void* cub_tmp, size_t cub_bytes,
+                     unsigned long long* n_host, cudaStream_t st)
+{
+    if (scan_positions(m, scan_tmp, cub_tmp, cub_bytes, n_host, st)) return -1;
+    xyz_scatter_kernel<<<296, 256, 0, st>>>(m, scan_tmp + (size_t)m.w * m.h, out);
+    return 0;
+}
+
+}  // namespace wsg

@@ -1,0 +1,103 @@
+// Internal: the handle object shared by the C ABI translation units.
+#pragma once
+#include "../../include/wassgpu.h"
+#include "sgbm.cuh"
+#include "geom.cuh"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace wsg;
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+};
+
+struct wsg_handle {
+    int device = 0;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    // SGBM arena
+    DevBuf pre1, pre2, C, S, raw, img1, img2, disp, scalars;
+    SgbmPlan plan{};
+    bool have_plan = false;
+    wsg_sgbm_stats stats{};
+    // dense stage / geometry arena
+    DevBuf crop_l, crop_r, fa, fb, dispfull, im_left, im_right, mask_l, mask_r;
+    int dense_rows = 0, dense_cols = 0;     // size of the ROI disparity held in `fa` after wsg_dense_stereo
+    bool have_dense = false;
+    DevBuf m_valid, m_X, m_Y, m_Z, m_color, m_labels, m_scratch, m_small, m_out;
+    int mesh_w = 0, mesh_h = 0;
+    bool have_mesh = false;
+    // profiling
+    bool prof = false;
+    float stage_ms[WSG_NUM_STAGES] = {0};
+    int stage_launches[WSG_NUM_STAGES] = {0};
+    std::vector<std::pair<int, std::pair<cudaEvent_t, cudaEvent_t>>> pending;
+    std::vector<cudaEvent_t> ev_pool;
+};
+
+#define CK(h, call)                                                                           \
+    do {                                                                                      \
+        cudaError_t e__ = (call);                                                             \
+        if (e__ != cudaSuccess) {                                                             \
+            (h)->err = std::string(#call) + ": " + cudaGetErrorString(e__);                   \
+            return WSG_ERR_CUDA;                                                              \
+        }                                                                                     \
+    } while (0)
+
+inline int ensure(wsg_handle* h, DevBuf& b, size_t bytes)
+{
+    if (bytes <= b.cap) return WSG_OK;
+    if (b.p) { cudaFree(b.p); b.p = nullptr; b.cap = 0; }
+    cudaError_t e = cudaMalloc(&b.p, bytes);
+    if (e != cudaSuccess) {
+        h->err = std::string("cudaMalloc(") + std::to_string(bytes) + "): " + cudaGetErrorString(e);
+        cudaGetLastError();
+        return e == cudaErrorMemoryAllocation ? WSG_ERR_NOMEM : WSG_ERR_CUDA;
+    }
+    b.cap = bytes;
+    return WSG_OK;
+}
+
+struct StageTimer {
+    wsg_handle* h; int stage; cudaEvent_t a = nullptr, b = nullptr;
+    static cudaEvent_t get(wsg_handle* h)
+    {
+        if (!h->ev_pool.empty()) { cudaEvent_t e = h->ev_pool.back(); h->ev_pool.pop_back(); return e; }
+        cudaEvent_t e; cudaEventCreate(&e); return e;
+    }
+    StageTimer(wsg_handle* h_, int s, int launches) : h(h_), stage(s)
+    {
+        h->stage_launches[s] += launches;
+        if (h->prof) { a = get(h); b = get(h); cudaEventRecord(a, h->stream); }
+    }
+    ~StageTimer()
+    {
+        if (h->prof) { cudaEventRecord(b, h->stream); h->pending.push_back({stage, {a, b}}); }
+    }
+};
+
+inline void drain_profile(wsg_handle* h)
+{
+    for (auto& pe : h->pending) {
+        cudaEventSynchronize(pe.second.second);
+        float ms = 0;
+        cudaEventElapsedTime(&ms, pe.second.first, pe.second.second);
+        h->stage_ms[pe.first] += ms;
+        h->ev_pool.push_back(pe.second.first);
+        h->ev_pool.push_back(pe.second.second);
+    }
+    h->pending.clear();
+}
+
+
+// internal helpers implemented in capi.cu (C linkage only because they live inside its extern "C" block)
+extern "C" int wsg_make_plan(wsg_handle* h, int rows, int cols, const wsg_sgbm_params* p, SgbmPlan& pl);
+extern "C" int wsg_run_sgbm(wsg_handle* h, const uint8_t* d_img1, const uint8_t* d_img2, size_t stride, int16_t* d_disp);

@@ -1,0 +1,203 @@
+#include "io.hpp"
+
+#include <zlib.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <sstream>
+
+namespace wasshost {
+
+static bool slurp(const std::string& path, std::string& out)
+{
+    std::ifstream f(path.c_str(), std::ios::binary);
+    if (!f.is_open()) return false;
+    std::stringstream ss;
+    ss << f.rdbuf();
+    out = ss.str();
+    return true;
+}
+
+bool write_file(const std::string& path, const void* data, size_t n)
+{
+    FILE* f = fopen(path.c_str(), "wb");
+    if (!f) return false;
+    const bool ok = fwrite(data, 1, n, f) == n;
+    return fclose(f) == 0 && ok;
+}
+
+// ---- OpenCV FileStorage XML: <opencv_storage><name type_id="opencv-matrix"><rows>..<cols>..<dt>d</dt><data>..</data>
+static bool tag_text(const std::string& s, size_t from, const char* tag, std::string& text, size_t* end)
+{
+    const std::string open = std::string("<") + tag + ">", close = std::string("</") + tag + ">";
+    const size_t a = s.find(open, from);
+    if (a == std::string::npos) return false;
+    const size_t b = s.find(close, a);
+    if (b == std::string::npos) return false;
+    text = s.substr(a + open.size(), b - a - open.size());
+    if (end) *end = b + close.size();
+    return true;
+}
+
+bool load_matrix_xml(const std::string& path, Mat& out, std::string* err)
+{
+    std::string s;
+    if (!slurp(path, s)) { if (err) *err = "Unable to load " + path; return false; }
+    const size_t root = s.find("<opencv_storage>");
+    if (root == std::string::npos) { if (err) *err = path + ": not an OpenCV XML storage"; return false; }
+    const size_t node = s.find("type_id=\"opencv-matrix\"", root);
+    if (node == std::string::npos) { if (err) *err = path + ": first node is not a matrix"; return false; }
+    std::string rows, cols, dt, data;
+    size_t pos = node;
+    if (!tag_text(s, pos, "rows", rows, nullptr) || !tag_text(s, pos, "cols", cols, nullptr) || !tag_text(s, pos, "dt", dt, nullptr) ||
+        !tag_text(s, pos, "data", data, nullptr)) {
+        if (err) *err = path + ": malformed matrix node";
+        return false;
+    }
+    out.rows = atoi(rows.c_str());
+    out.cols = atoi(cols.c_str());
+    if (out.rows <= 0 || out.cols <= 0) { if (err) *err = path + ": bad matrix size"; return false; }
+    out.v.clear();
+    std::stringstream ds(data);
+    std::string tok;
+    while (ds >> tok) {
+        // OpenCV writes ".Inf" / "-.Inf" / ".Nan" for non-finite values
+        if (tok == ".Inf") out.v.push_back(INFINITY);
+        else if (tok == "-.Inf") out.v.push_back(-INFINITY);
+        else if (tok == ".Nan") out.v.push_back(NAN);
+        else out.v.push_back(strtod(tok.c_str(), nullptr));
+    }
+    if ((int)out.v.size() != out.rows * out.cols) { if (err) *err = path + ": element count does not match rows*cols"; return false; }
+    return true;
+}
+
+bool save_matrix_txt(const std::string& path, const Mat& m)
+{
+    std::ofstream ofs(path.c_str());
+    if (ofs.fail()) return false;
+    ofs.precision(16);
+    ofs << std::scientific;
+    for (int i = 0; i < m.rows; ++i) {
+        for (int j = 0; j < m.cols; ++j) {
+            ofs << m.at(i, j);
+            if (j != m.cols - 1) ofs << " ";
+        }
+        if (i != m.rows - 1) ofs << std::endl;
+    }
+    ofs.close();
+    return true;
+}
+
+// ---- PNG ------------------------------------------------------------------------------------------
+static uint32_t be32(const unsigned char* p) { return ((uint32_t)p[0] << 24) | ((uint32_t)p[1] << 16) | ((uint32_t)p[2] << 8) | p[3]; }
+
+bool read_png_gray(const std::string& path, Image8& out, std::string* err)
+{
+    std::string s;
+    if (!slurp(path, s)) { if (err) *err = "unable to open " + path; return false; }
+    const unsigned char* d = (const unsigned char*)s.data();
+    static const unsigned char sig[8] = {137, 80, 78, 71, 13, 10, 26, 10};
+    if (s.size() < 33 || memcmp(d, sig, 8)) { if (err) *err = path + ": not a PNG file"; return false; }
+    size_t pos = 8;
+    int w = 0, h = 0, depth = 0, ctype = 0, interlace = 0;
+    std::vector<unsigned char> idat, plte;
+    while (pos + 12 <= s.size()) {
+        const uint32_t len = be32(d + pos);
+        const std::string type((const char*)d + pos + 4, 4);
+        const unsigned char* body = d + pos + 8;
+        if (pos + 12 + len > s.size()) break;
+        if (type == "IHDR") { w = (int)be32(body); h = (int)be32(body + 4); depth = body[8]; ctype = body[9]; interlace = body[12]; }
+        else if (type == "PLTE") plte.assign(body, body + len);
+        else if (type == "IDAT") idat.insert(idat.end(), body, body + len);
+        else if (type == "IEND") break;
+        pos += 12 + len;
+    }
+    if (w <= 0 || h <= 0 || interlace != 0 || (depth != 8 && depth != 16) ) {
+        if (err) *err = path + ": unsupported PNG (need non-interlaced 8/16-bit)";
+        return false;
+    }
+    int ch = ctype == 0 ? 1 : ctype == 2 ? 3 : ctype == 3 ? 1 : ctype == 4 ? 2 : ctype == 6 ? 4 : 0;
+    if (!ch || (ctype == 3 && depth != 8)) { if (err) *err = path + ": unsupported PNG colour type"; return false; }
+    const int bpp = ch * depth / 8;
+    const size_t stride = (size_t)w * bpp;
+    std::vector<unsigned char> raw((stride + 1) * h);
+    uLongf rawlen = raw.size();
+    if (uncompress(raw.data(), &rawlen, idat.data(), idat.size()) != Z_OK || rawlen != raw.size()) {
+        if (err) *err = path + ": zlib inflate failed";
+        return false;
+    }
+    std::vector<unsigned char> img(stride * h);
+    for (int y = 0; y < h; ++y) {
+        const unsigned char* in = raw.data() + (stride + 1) * y;
+        unsigned char* cur = img.data() + stride * y;
+        const unsigned char* up = y ? cur - stride : nullptr;
+        const int ft = in[0];
+        for (size_t x = 0; x < stride; ++x) {
+            const int a = x >= (size_t)bpp ? cur[x - bpp] : 0, b = up ? up[x] : 0, c = (up && x >= (size_t)bpp) ? up[x - bpp] : 0;
+            int v = in[1 + x];
+            switch (ft) {
+                case 1: v += a; break;
+                case 2: v += b; break;
+                case 3: v += (a + b) / 2; break;
+                case 4: { const int p = a + b - c, pa = abs(p - a), pb = abs(p - b), pc = abs(p - c); v += (pa <= pb && pa <= pc) ? a : (pb <= pc ? b : c); break; }
+                default: break;
+            }
+            cur[x] = (unsigned char)v;
+        }
+    }
+    out.rows = h; out.cols = w; out.px.resize((size_t)w * h);
+    const int step = depth / 8;     // 16-bit: keep the high byte (cv::imread 8-bit conversion scales by 1/256)
+    for (size_t i = 0; i < (size_t)w * h; ++i) {
+        const unsigned char* p = img.data() + i * bpp;
+        if (ctype == 0 || ctype == 4) out.px[i] = p[0];
+        else if (ctype == 3) {
+            const int k = p[0] * 3;
+            const int r = k + 2 < (int)plte.size() ? plte[k] : 0, g = k + 2 < (int)plte.size() ? plte[k + 1] : 0, b = k + 2 < (int)plte.size() ? plte[k + 2] : 0;
+            out.px[i] = (uint8_t)((r * 4899 + g * 9617 + b * 1868 + 8192) >> 14);
+        } else {
+            // OpenCV BGR2GRAY fixed point: (R*4899 + G*9617 + B*1868 + 2^13) >> 14
+            const int r = p[0], g = p[step], b = p[2 * step];
+            out.px[i] = (uint8_t)((r * 4899 + g * 9617 + b * 1868 + 8192) >> 14);
+        }
+    }
+    return true;
+}
+
+static void put_chunk(std::vector<unsigned char>& o, const char* type, const unsigned char* data, size_t n)
+{
+    const uint32_t len = (uint32_t)n;
+    unsigned char hdr[8] = {(unsigned char)(len >> 24), (unsigned char)(len >> 16), (unsigned char)(len >> 8), (unsigned char)len,
+                            (unsigned char)type[0], (unsigned char)type[1], (unsigned char)type[2], (unsigned char)type[3]};
+    o.insert(o.end(), hdr, hdr + 8);
+    if (n) o.insert(o.end(), data, data + n);
+    uLong crc = crc32(0L, hdr + 4, 4);
+    if (n) crc = crc32(crc, data, (uInt)n);
+    const unsigned char c[4] = {(unsigned char)(crc >> 24), (unsigned char)(crc >> 16), (unsigned char)(crc >> 8), (unsigned char)crc};
+    o.insert(o.end(), c, c + 4);
+}
+
+bool write_png_gray(const std::string& path, const Image8& img)
+{
+    if (img.empty()) return false;
+    std::vector<unsigned char> raw((size_t)(img.cols + 1) * img.rows);
+    for (int y = 0; y < img.rows; ++y) {
+        raw[(size_t)(img.cols + 1) * y] = 0;
+        memcpy(&raw[(size_t)(img.cols + 1) * y + 1], &img.px[(size_t)img.cols * y], img.cols);
+    }
+    uLongf clen = compressBound(raw.size());
+    std::vector<unsigned char> comp(clen);
+    if (compress2(comp.data(), &clen, raw.data(), raw.size(), 3) != Z_OK) return false;
+    std::vector<unsigned char> o = {137, 80, 78, 71, 13, 10, 26, 10};
+    unsigned char ihdr[13] = {(unsigned char)(img.cols >> 24), (unsigned char)(img.cols >> 16), (unsigned char)(img.cols >> 8), (unsigned char)img.cols,
+                              (unsigned char)(img.rows >> 24), (unsigned char)(img.rows >> 16), (unsigned char)(img.rows >> 8), (unsigned char)img.rows,
+                              8, 0, 0, 0, 0};
+    put_chunk(o, "IHDR", ihdr, 13);
+    put_chunk(o, "IDAT", comp.data(), clen);
+    put_chunk(o, "IEND", nullptr, 0);
+    return write_file(path, o.data(), o.size());
+}
+
+}  // namespace wasshost

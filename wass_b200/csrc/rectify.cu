@@ -1,0 +1,287 @@
+// Rectification stage of wass_stereo (src/wass_stereo/wass_stereo.cpp:447-613, cv::stereoRectify branch):
+//   wsg_stereo_rectify   host arithmetic of cv::stereoRectify(K0,0,K1,0,size,R,T,...,flags=0,alpha=1,size)
+//   wsg_rectify_image    cv::initUndistortRectifyMap(K,0,Rrect,P,size,CV_32FC1) + cv::remap(INTER_CUBIC)
+// The published OpenCV algorithm (Bouguet's method, fixed-point bicubic remap with 1/32-pixel
+// phases) is restated here; tests/test_rectify.py pins both functions against cv2.
+#include "handle.cuh"
+
+#include <cfloat>
+#include <cmath>
+
+namespace {
+
+void mat3_mul(const double* A, const double* B, double* C)
+{
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) C[3 * i + j] = A[3 * i] * B[j] + A[3 * i + 1] * B[3 + j] + A[3 * i + 2] * B[6 + j];
+}
+void mat3_t(const double* A, double* T) { for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) T[3 * i + j] = A[3 * j + i]; }
+void mat3_vec(const double* A, const double* v, double* o) { for (int i = 0; i < 3; ++i) o[i] = A[3 * i] * v[0] + A[3 * i + 1] * v[1] + A[3 * i + 2] * v[2]; }
+
+void rodrigues_v2m(const double* om, double* R)
+{
+    const double theta = sqrt(om[0] * om[0] + om[1] * om[1] + om[2] * om[2]);
+    if (theta < DBL_EPSILON) { for (int i = 0; i < 9; ++i) R[i] = (i % 4 == 0); return; }
+    const double c = cos(theta), s = sin(theta), c1 = 1. - c, it = 1. / theta;
+    const double x = om[0] * it, y = om[1] * it, z = om[2] * it;
+    R[0] = c + c1 * x * x; R[1] = c1 * x * y - s * z; R[2] = c1 * x * z + s * y;
+    R[3] = c1 * x * y + s * z; R[4] = c + c1 * y * y; R[5] = c1 * y * z - s * x;
+    R[6] = c1 * x * z - s * y; R[7] = c1 * y * z + s * x; R[8] = c + c1 * z * z;
+}
+void rodrigues_m2v(const double* R, double* om)
+{
+    double rx = R[7] - R[5], ry = R[2] - R[6], rz = R[3] - R[1];
+    const double s = sqrt((rx * rx + ry * ry + rz * rz) * 0.25);
+    double c = (R[0] + R[4] + R[8] - 1) * 0.5;
+    c = c > 1. ? 1. : c < -1. ? -1. : c;
+    const double theta = acos(c);
+    if (s < 1e-5) {
+        if (c > 0) { om[0] = om[1] = om[2] = 0; return; }
+        double t;
+        t = (R[0] + 1) * 0.5; rx = sqrt(t > 0 ? t : 0);
+        t = (R[4] + 1) * 0.5; ry = sqrt(t > 0 ? t : 0) * (R[1] < 0 ? -1. : 1.);
+        t = (R[8] + 1) * 0.5; rz = sqrt(t > 0 ? t : 0) * (R[2] < 0 ? -1. : 1.);
+        if (fabs(rx) < fabs(ry) && fabs(rx) < fabs(rz) && (R[5] > 0) != (ry * rz > 0)) rz = -rz;
+        const double k = theta / sqrt(rx * rx + ry * ry + rz * rz);
+        om[0] = rx * k; om[1] = ry * k; om[2] = rz * k;
+        return;
+    }
+    const double vth = 1 / (2 * s) * theta;
+    om[0] = rx * vth; om[1] = ry * vth; om[2] = rz * vth;
+}
+
+struct RectF { float x, y, w, h; };
+
+// icvGetRectangles with zero distortion: 9x9 grid -> normalise with K, rotate with R, project with P
+void get_rectangles(const double* K, const double* R, const double* P /*3x4*/, int W, int H, RectF& inner, RectF& outer)
+{
+    const int N = 9;
+    float iX0 = -FLT_MAX, iX1 = FLT_MAX, iY0 = -FLT_MAX, iY1 = FLT_MAX, oX0 = FLT_MAX, oX1 = -FLT_MAX, oY0 = FLT_MAX, oY1 = -FLT_MAX;
+    for (int y = 0; y < N; ++y)
+        for (int x = 0; x < N; ++x) {
+            const float px = (float)x * (W - 1) / (N - 1), py = (float)y * (H - 1) / (N - 1);
+            const double xn = ((double)px - K[2]) / K[0], yn = ((double)py - K[5]) / K[4];
+            const double X = R[0] * xn + R[1] * yn + R[2], Y = R[3] * xn + R[4] * yn + R[5], Wz = R[6] * xn + R[7] * yn + R[8];
+            const double xr = X / Wz, yr = Y / Wz;
+            const float qx = (float)(xr * P[0] + P[2]), qy = (float)(yr * P[5] + P[6]);
+            oX0 = fminf(oX0, qx); oX1 = fmaxf(oX1, qx); oY0 = fminf(oY0, qy); oY1 = fmaxf(oY1, qy);
+            if (x == 0) iX0 = fmaxf(iX0, qx);
+            if (x == N - 1) iX1 = fminf(iX1, qx);
+            if (y == 0) iY0 = fmaxf(iY0, qy);
+            if (y == N - 1) iY1 = fminf(iY1, qy);
+        }
+    inner = {iX0, iY0, iX1 - iX0, iY1 - iY0};
+    outer = {oX0, oY0, oX1 - oX0, oY1 - oY0};
+}
+
+// ---- bicubic fixed-point tables of cv::remap (INTER_BITS = 5, coefficient scale 2^15) -----------------
+const int TABSZ = 32, COEF_BITS = 15, COEF_SCALE = 1 << COEF_BITS;
+
+inline short sat_short_round(float v)
+{
+    const long r = lrintf(v);     // round half to even, like cvRound
+    return (short)(r > 32767 ? 32767 : r < -32768 ? -32768 : r);
+}
+
+void build_cubic_table(short* itab /*[32*32][16]*/)
+{
+    float tab1[TABSZ * 4];
+    const float A = -0.75f;
+    for (int i = 0; i < TABSZ; ++i) {
+        const float x = i * (1.f / TABSZ);
+        float* c = tab1 + 4 * i;
+        c[0] = ((A * (x + 1) - 5 * A) * (x + 1) + 8 * A) * (x + 1) - 4 * A;
+        c[1] = ((A + 2) * x - (A + 3)) * x * x + 1;
+        c[2] = ((A + 2) * (1 - x) - (A + 3)) * (1 - x) * (1 - x) + 1;
+        c[3] = 1.f - c[0] - c[1] - c[2];
+    }
+    for (int i = 0; i < TABSZ; ++i)
+        for (int j = 0; j < TABSZ; ++j) {
+            short* t = itab + (i * TABSZ + j) * 16;
+            int isum = 0;
+            for (int k1 = 0; k1 < 4; ++k1) {
+                const float vy = tab1[i * 4 + k1];
+                for (int k2 = 0; k2 < 4; ++k2) {
+                    const float v = vy * tab1[j * 4 + k2];
+                    isum += t[k1 * 4 + k2] = sat_short_round(v * COEF_SCALE);
+                }
+            }
+            if (isum != COEF_SCALE) {
+                const int diff = isum - COEF_SCALE;
+                int Mk1 = 2, Mk2 = 2, mk1 = 2, mk2 = 2;
+                for (int k1 = 2; k1 < 4; ++k1)
+                    for (int k2 = 2; k2 < 4; ++k2) {
+                        if (t[k1 * 4 + k2] < t[mk1 * 4 + mk2]) { mk1 = k1; mk2 = k2; }
+                        else if (t[k1 * 4 + k2] > t[Mk1 * 4 + Mk2]) { Mk1 = k1; Mk2 = k2; }
+                    }
+                if (diff < 0) t[Mk1 * 4 + Mk2] = (short)(t[Mk1 * 4 + Mk2] - diff);
+                else t[mk1 * 4 + mk2] = (short)(t[mk1 * 4 + mk2] - diff);
+            }
+        }
+}
+
+__global__ void rectify_remap_kernel(const uint8_t* __restrict__ src, int rows, int cols, size_t stride, const double* __restrict__ ir /*9*/,
+                                     double fx, double fy, double cx, double cy, const short* __restrict__ wtab, uint8_t* __restrict__ dst)
+{
+    const int u = blockIdx.x * blockDim.x + threadIdx.x, v = blockIdx.y;
+    if (u >= cols) return;
+    // initUndistortRectifyMap, zero distortion: [x y w] = (P_3x3 * R)^-1 [u v 1]
+    const double X = ir[0] * u + ir[1] * v + ir[2], Y = ir[3] * u + ir[4] * v + ir[5], Wz = ir[6] * u + ir[7] * v + ir[8];
+    const double w = 1. / Wz, x = X * w, y = Y * w;
+    const float mx = (float)(x * fx + cx), my = (float)(y * fy + cy);
+    // cv::remap: maps -> 1/32-pixel fixed point
+    const int sxf = __float2int_rn(mx * TABSZ), syf = __float2int_rn(my * TABSZ);
+    int sx = sxf >> 5, sy = syf >> 5;
+    sx = min(max(sx, -32768), 32767); sy = min(max(sy, -32768), 32767);
+    const short* wt = wtab + ((syf & 31) * TABSZ + (sxf & 31)) * 16;
+    sx -= 1; sy -= 1;
+    int out = 0;
+    if (!(sx >= cols || sx + 4 <= 0 || sy >= rows || sy + 4 <= 0)) {
+        int sum = 0;
+#pragma unroll
+        for (int k1 = 0; k1 < 4; ++k1) {
+            const int yy = sy + k1;
+            if (yy < 0 || yy >= rows) continue;
+#pragma unroll
+            for (int k2 = 0; k2 < 4; ++k2) {
+                const int xx = sx + k2;
+                if (xx < 0 || xx >= cols) continue;
+                sum += (int)src[(size_t)yy * stride + xx] * wt[k1 * 4 + k2];
+            }
+        }
+        out = (sum + (1 << (COEF_BITS - 1))) >> COEF_BITS;
+        out = min(max(out, 0), 255);
+    }
+    dst[(size_t)v * cols + u] = (uint8_t)out;
+}
+
+bool inv3(const double* m, double* o)
+{
+    const double det = m[0] * (m[4] * m[8] - m[5] * m[7]) - m[1] * (m[3] * m[8] - m[5] * m[6]) + m[2] * (m[3] * m[7] - m[4] * m[6]);
+    if (det == 0) return false;
+    const double d = 1. / det;
+    o[0] = (m[4] * m[8] - m[5] * m[7]) * d; o[1] = (m[2] * m[7] - m[1] * m[8]) * d; o[2] = (m[1] * m[5] - m[2] * m[4]) * d;
+    o[3] = (m[5] * m[6] - m[3] * m[8]) * d; o[4] = (m[0] * m[8] - m[2] * m[6]) * d; o[5] = (m[2] * m[3] - m[0] * m[5]) * d;
+    o[6] = (m[3] * m[7] - m[4] * m[6]) * d; o[7] = (m[1] * m[6] - m[0] * m[7]) * d; o[8] = (m[0] * m[4] - m[1] * m[3]) * d;
+    return true;
+}
+
+}  // namespace
+
+extern "C" {
+
+int wsg_stereo_rectify(const double K0[9], const double K1[9], const double R[9], const double T[3], int width, int height,
+                       double R1[9], double R2[9], double P1[12], double P2[12], int roi1[4], int roi2[4])
+{
+    if (!K0 || !K1 || !R || !T || !R1 || !R2 || !P1 || !P2 || width <= 0 || height <= 0) return WSG_ERR_INVALID_ARG;
+    double om[3], r_r[9], t[3], uu[3] = {0, 0, 0}, ww[3], wR[9], tmp[9];
+    rodrigues_m2v(R, om);
+    for (int i = 0; i < 3; ++i) om[i] *= -0.5;          // each camera rotates half way
+    rodrigues_v2m(om, r_r);
+    mat3_vec(r_r, T, t);
+    const int idx = fabs(t[0]) > fabs(t[1]) ? 0 : 1;
+    const double c = t[idx], nt = sqrt(t[0] * t[0] + t[1] * t[1] + t[2] * t[2]);
+    uu[idx] = c > 0 ? 1 : -1;
+    ww[0] = t[1] * uu[2] - t[2] * uu[1]; ww[1] = t[2] * uu[0] - t[0] * uu[2]; ww[2] = t[0] * uu[1] - t[1] * uu[0];
+    const double nw = sqrt(ww[0] * ww[0] + ww[1] * ww[1] + ww[2] * ww[2]);
+    if (nw > 0.0) { const double k = acos(fabs(c) / nt) / nw; for (int i = 0; i < 3; ++i) ww[i] *= k; }
+    rodrigues_v2m(ww, wR);
+    mat3_t(r_r, tmp);
+    mat3_mul(wR, tmp, R1);          // R1 = wR * r_r^T
+    mat3_mul(wR, r_r, R2);          // R2 = wR * r_r
+    mat3_vec(R2, T, t);
+    // new focal length: mean of the two focal lengths on the axis perpendicular to the baseline
+    // (what cv2 4.13 does with zero distortion; pinned in tests/test_rectify.py)
+    const double fc_new0 = (K0[idx == 0 ? 4 : 0] + K1[idx == 0 ? 4 : 0]) * 0.5;
+    double fc_new = fc_new0;
+    double ccn[2][2];
+    for (int k = 0; k < 2; ++k) {
+        const double* A = k == 0 ? K0 : K1;
+        const double* Rk = k == 0 ? R1 : R2;
+        double ax = 0, ay = 0;
+        for (int i = 0; i < 4; ++i) {
+            const float px = (float)((i % 2) * (width - 1)), py = (float)((i < 2 ? 0 : 1) * (height - 1));
+            const float xn = (float)(((double)px - A[2]) / A[0]), yn = (float)(((double)py - A[5]) / A[4]);
+            const double X = Rk[0] * xn + Rk[1] * yn + Rk[2], Y = Rk[3] * xn + Rk[4] * yn + Rk[5], Z = Rk[6] * xn + Rk[7] * yn + Rk[8];
+            const double z = Z ? 1. / Z : 1.;
+            ax += (float)(X * z * fc_new); ay += (float)(Y * z * fc_new);
+        }
+        ccn[k][0] = (width - 1) / 2. - ax / 4;
+        ccn[k][1] = (height - 1) / 2. - ay / 4;
+    }
+    // flags = 0 (no CALIB_ZERO_DISPARITY): only the coordinate perpendicular to the baseline is shared
+    if (idx == 0) ccn[0][1] = ccn[1][1] = (ccn[0][1] + ccn[1][1]) * 0.5;
+    else ccn[0][0] = ccn[1][0] = (ccn[0][0] + ccn[1][0]) * 0.5;
+    auto fillP = [&](double* P, int k, double f) {
+        for (int i = 0; i < 12; ++i) P[i] = 0;
+        P[0] = f; P[5] = f; P[2] = ccn[k][0]; P[6] = ccn[k][1]; P[10] = 1;
+    };
+    fillP(P1, 0, fc_new); fillP(P2, 1, fc_new);
+    P2[idx * 4 + 3] = t[idx] * fc_new;
+    // alpha = 1 : scale so that all source pixels are retained
+    RectF in1, out1, in2, out2;
+    get_rectangles(K0, R1, P1, width, height, in1, out1);
+    get_rectangles(K1, R2, P2, width, height, in2, out2);
+    const double cx1_0 = ccn[0][0], cy1_0 = ccn[0][1], cx2_0 = ccn[1][0], cy2_0 = ccn[1][1];
+    const double cx1 = cx1_0, cy1 = cy1_0, cx2 = cx2_0, cy2 = cy2_0;     // newImgSize == imageSize
+    const double alpha = 1.0;
+    double s0 = fmax(fmax(fmax(cx1 / (cx1_0 - in1.x), cy1 / (cy1_0 - in1.y)), (width - 1 - cx1) / (in1.x + in1.w - cx1_0)),
+                     (height - 1 - cy1) / (in1.y + in1.h - cy1_0));
+    s0 = fmax(fmax(fmax(fmax(cx2 / (cx2_0 - in2.x), cy2 / (cy2_0 - in2.y)), (width - 1 - cx2) / (in2.x + in2.w - cx2_0)),
+                   (height - 1 - cy2) / (in2.y + in2.h - cy2_0)), s0);
+    double s1 = fmin(fmin(fmin(cx1 / (cx1_0 - out1.x), cy1 / (cy1_0 - out1.y)), (width - 1 - cx1) / (out1.x + out1.w - cx1_0)),
+                     (height - 1 - cy1) / (out1.y + out1.h - cy1_0));
+    s1 = fmin(fmin(fmin(fmin(cx2 / (cx2_0 - out2.x), cy2 / (cy2_0 - out2.y)), (width - 1 - cx2) / (out2.x + out2.w - cx2_0)),
+                   (height - 1 - cy2) / (out2.y + out2.h - cy2_0)), s1);
+    const double s = s0 * (1 - alpha) + s1 * alpha;
+    fc_new *= s;
+    fillP(P1, 0, fc_new); fillP(P2, 1, fc_new);
+    P2[idx * 4 + 3] = t[idx] * fc_new0 * s;
+    auto roi = [&](const RectF& in, double cx0, double cy0, double cx, double cy, int* r) {
+        int x = (int)ceil((in.x - cx0) * s + cx), y = (int)ceil((in.y - cy0) * s + cy);
+        int w = (int)floor(in.w * s), h = (int)floor(in.h * s);
+        // intersect with the image rectangle
+        const int x0 = x > 0 ? x : 0, y0 = y > 0 ? y : 0;
+        const int x1 = x + w < width ? x + w : width, y1 = y + h < height ? y + h : height;
+        if (x1 <= x0 || y1 <= y0) { r[0] = r[1] = r[2] = r[3] = 0; return; }
+        r[0] = x0; r[1] = y0; r[2] = x1 - x0; r[3] = y1 - y0;
+    };
+    if (roi1) roi(in1, cx1_0, cy1_0, cx1, cy1, roi1);
+    if (roi2) roi(in2, cx2_0, cy2_0, cx2, cy2, roi2);
+    return WSG_OK;
+}
+
+int wsg_rectify_image(wsg_handle* h, const uint8_t* img, int rows, int cols, size_t stride, const double K[9], const double Rrect[9],
+                      const double P[12], uint8_t* out)
+{
+    if (!h) return WSG_ERR_INVALID_ARG;
+    if (!img || !K || !Rrect || !P || !out || rows <= 0 || cols <= 0 || stride < (size_t)cols) { h->err = "bad argument"; return WSG_ERR_INVALID_ARG; }
+    CK(h, cudaSetDevice(h->device));
+    double A[9] = {P[0], P[1], P[2], P[4], P[5], P[6], P[8], P[9], P[10]}, AR[9], iR[9];
+    mat3_mul(A, Rrect, AR);
+    if (!inv3(AR, iR)) { h->err = "singular rectification"; return WSG_ERR_INVALID_ARG; }
+    const size_t n = (size_t)rows * cols;
+    int rc;
+    if ((rc = ensure(h, h->im_left, n))) return rc;
+    if ((rc = ensure(h, h->im_right, n))) return rc;
+    if ((rc = ensure(h, h->m_small, 1 << 16))) return rc;
+    static short itab[TABSZ * TABSZ * 16];
+    static bool have = false;
+    if (!have) { build_cubic_table(itab); have = true; }
+    char* small = (char*)h->m_small.p;
+    double* d_ir = (double*)(small + 1024);
+    short* d_tab = (short*)(small + 2048);
+    static_assert(2048 + sizeof(itab) <= (1 << 16), "table fits the scratch buffer");
+    CK(h, cudaMemcpyAsync(d_ir, iR, 72, cudaMemcpyHostToDevice, h->stream));
+    CK(h, cudaMemcpyAsync(d_tab, itab, sizeof(itab), cudaMemcpyHostToDevice, h->stream));
+    CK(h, cudaMemcpy2DAsync(h->im_left.p, cols, img, stride, cols, rows, cudaMemcpyHostToDevice, h->stream));
+    dim3 b(128), g((cols + 127) / 128, rows);
+    rectify_remap_kernel<<<g, b, 0, h->stream>>>((const uint8_t*)h->im_left.p, rows, cols, cols, d_ir, K[0], K[4], K[2], K[5], d_tab,
+                                                 (uint8_t*)h->im_right.p);
+    CK(h, cudaMemcpyAsync(out, h->im_right.p, n, cudaMemcpyDeviceToHost, h->stream));
+    CK(h, cudaStreamSynchronize(h->stream));
+    CK(h, cudaGetLastError());
+    return WSG_OK;
+}
+
+}  // extern "C"

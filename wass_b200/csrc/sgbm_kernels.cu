@@ -61,6 +61,7 @@ static constexpr int DT = 64;     // disparities per CTA
 static constexpr int CT = 256;    // threads: 32 columns x 8 groups of 8 disparities
 static constexpr int RB = 128;    // rows per band
 static constexpr int VT = 120;    // entries of the reversed img2 tables (>= XT+2*12+DT-1 .. rounded)
+static constexpr int RVPAD = 4;   // s16 elements between table copy A and copy B (shared-memory bank skew)
 
 struct CostSmem {
     // offsets into dynamic shared memory (bytes)
@@ -72,8 +73,8 @@ __host__ __device__ inline CostSmem cost_smem_layout(int SW2, int SH2)
     const int ncol = XT + 2 * SW2;
     s.pd = 0;                                  // u16 [ncol][DT]
     s.uu = s.pd + ncol * DT * 2;               // u32 [ncol][8]
-    s.rv = s.uu + ncol * 8 * 4;                // s16 [2][8][VT]
-    s.ring = (s.rv + 2 * 8 * VT * 2 + 15) & ~15;  // u16 [2*SH2+1][XT][DT]
+    s.rv = s.uu + ncol * 8 * 4;                // s16 [2][8][VT] (+4 between the two copies: bank skew)
+    s.ring = (s.rv + (2 * 8 * VT + RVPAD) * 2 + 15) & ~15;  // u16 [2*SH2+1][XT][DT]
     s.total = s.ring + (2 * SH2 + 1) * XT * DT * 2;
     return s;
 }
@@ -102,9 +103,9 @@ __global__ void __launch_bounds__(CT) cost_kernel(const uint2* __restrict__ pre1
     const int dlo = p.minD + d0;
     const int vtop = xb - dlo;               // largest img2 column touched; table index i <-> x' = vtop - i
 
-    const int c = tid >> 3, g = tid & 7;     // phase-2 role: column c, disparities d0+8g..+7
+    const int c4 = (tid >> 3) & 7, g = tid & 7;   // phase-2 role (tid<64): columns 4*c4..+3, disparities d0+8g..+7
     const bool real_vec = (d0 + 8 * g) < p.D;
-    unsigned acc[4] = {0, 0, 0, 0};
+    unsigned acc[4][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}, {0, 0, 0, 0}, {0, 0, 0, 0}};
     int vmax = 0;
 
     const int nsteps = (y1 - y0) + 2 * p.SH2;
@@ -131,8 +132,8 @@ __global__ void __launch_bounds__(CT) cost_kernel(const uint2* __restrict__ pre1
                                     (int16_t)v1, (int16_t)-v1, (int16_t)l1, (int16_t)-h1};
 #pragma unroll
             for (int qn = 0; qn < 8; ++qn) {
-                rv[(0 * 8 + qn) * VT + tid] = val[qn];                   // copy A: rv[i]
-                if (tid > 0) rv[(1 * 8 + qn) * VT + tid - 1] = val[qn];  // copy B: rv[i+1]
+                rv[(0 * 8 + qn) * VT + tid] = val[qn];                           // copy A: rv[i]
+                if (tid > 0) rv[RVPAD + (1 * 8 + qn) * VT + tid - 1] = val[qn];  // copy B: rv[i+1]
             }
         }
         __syncthreads();
@@ -144,7 +145,7 @@ __global__ void __launch_bounds__(CT) cost_kernel(const uint2* __restrict__ pre1
                 const int xx = p.minX1 + min(max(x0 - p.SW2 + cc, 0), p.W1 - 1);
                 const int i0 = (xb - xx) + 8 * gg;
                 const int par = i0 & 1;
-                const unsigned* rvw = reinterpret_cast<const unsigned*>(rv + (par * 8) * VT) + ((i0 - par) >> 1);
+                const unsigned* rvw = reinterpret_cast<const unsigned*>(rv + par * (8 * VT + RVPAD)) + ((i0 - par) >> 1);
                 const uint4 ua = *reinterpret_cast<const uint4*>(uu + cc * 8);
                 const uint4 ub = *reinterpret_cast<const uint4*>(uu + cc * 8 + 4);
                 unsigned res[4];
@@ -168,33 +169,56 @@ __global__ void __launch_bounds__(CT) cost_kernel(const uint2* __restrict__ pre1
             *reinterpret_cast<uint4*>(pdrow + cc * DT + gg * 8) = out;
         }
         __syncthreads();
-        // ---- phase 2: horizontal box sum, ring update, vertical sliding sum, store
-        {
+        // ---- phase 2: horizontal box sum (sliding over 4 adjacent columns per thread), ring update,
+        //      vertical sliding sum, store.  64 threads: 8 column groups x 8 disparity groups.
+        if (tid < 64) {
+            const int win = 2 * p.SW2 + 1;
             unsigned hs[4] = {0, 0, 0, 0};
-            for (int i = 0; i <= 2 * p.SW2; ++i) {
-                const uint4 v = *reinterpret_cast<const uint4*>(pdrow + (c + i) * DT + g * 8);
+            uint4 head[3];
+            const uint16_t* prow = pdrow + (c4 * 4) * DT + g * 8;
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {   // the three columns that leave the window while sliding
+                head[i] = *reinterpret_cast<const uint4*>(prow + i * DT);
+                if (i < win) {
+                    hs[0] = __vadd2(hs[0], head[i].x); hs[1] = __vadd2(hs[1], head[i].y);
+                    hs[2] = __vadd2(hs[2], head[i].z); hs[3] = __vadd2(hs[3], head[i].w);
+                }
+            }
+            for (int i = 3; i < win; ++i) {
+                const uint4 v = *reinterpret_cast<const uint4*>(prow + i * DT);
                 hs[0] = __vadd2(hs[0], v.x); hs[1] = __vadd2(hs[1], v.y);
                 hs[2] = __vadd2(hs[2], v.z); hs[3] = __vadd2(hs[3], v.w);
             }
-            uint4* slot = reinterpret_cast<uint4*>(ring + ((idx % NR) * XT + c) * DT + g * 8);
-            if (idx >= NR) {
-                const uint4 o = *slot;
-                acc[0] = __vsub2(acc[0], o.x); acc[1] = __vsub2(acc[1], o.y);
-                acc[2] = __vsub2(acc[2], o.z); acc[3] = __vsub2(acc[3], o.w);
-            }
-            *slot = make_uint4(hs[0], hs[1], hs[2], hs[3]);
-            acc[0] = __vadd2(acc[0], hs[0]); acc[1] = __vadd2(acc[1], hs[1]);
-            acc[2] = __vadd2(acc[2], hs[2]); acc[3] = __vadd2(acc[3], hs[3]);
-            if (idx >= 2 * p.SH2 && x0 + c < p.W1) {
-                const int y = r - p.SH2;
-                const int j = (d0 >> 3) + g;
-                int16_t* dst = C + ((size_t)y * p.W1 + (x0 + c)) * p.Dp + vec_slot(j, p.NL, p.K) * 8;
-                if (real_vec) {
-                    *reinterpret_cast<uint4*>(dst) = make_uint4(acc[0], acc[1], acc[2], acc[3]);
-                    unsigned m = __vmaxs2(__vmaxs2(acc[0], acc[1]), __vmaxs2(acc[2], acc[3]));
-                    vmax = max(vmax, max((int)(short)(m & 0xFFFF), (int)(short)(m >> 16)));
-                } else {
-                    *reinterpret_cast<uint4*>(dst) = make_uint4(0, 0, 0, 0);
+#pragma unroll
+            for (int cc = 0; cc < 4; ++cc) {
+                const int col = c4 * 4 + cc;
+                if (cc > 0) {
+                    const uint4 vn = *reinterpret_cast<const uint4*>(prow + (win - 1 + cc) * DT);
+                    const uint4 vo = head[cc - 1];
+                    hs[0] = __vsub2(__vadd2(hs[0], vn.x), vo.x); hs[1] = __vsub2(__vadd2(hs[1], vn.y), vo.y);
+                    hs[2] = __vsub2(__vadd2(hs[2], vn.z), vo.z); hs[3] = __vsub2(__vadd2(hs[3], vn.w), vo.w);
+                }
+                uint4* slot = reinterpret_cast<uint4*>(ring + ((idx % NR) * XT + col) * DT + g * 8);
+                unsigned* ac = acc[cc];
+                if (idx >= NR) {
+                    const uint4 o = *slot;
+                    ac[0] = __vsub2(ac[0], o.x); ac[1] = __vsub2(ac[1], o.y);
+                    ac[2] = __vsub2(ac[2], o.z); ac[3] = __vsub2(ac[3], o.w);
+                }
+                *slot = make_uint4(hs[0], hs[1], hs[2], hs[3]);
+                ac[0] = __vadd2(ac[0], hs[0]); ac[1] = __vadd2(ac[1], hs[1]);
+                ac[2] = __vadd2(ac[2], hs[2]); ac[3] = __vadd2(ac[3], hs[3]);
+                if (idx >= 2 * p.SH2 && x0 + col < p.W1) {
+                    const int y = r - p.SH2;
+                    const int j = (d0 >> 3) + g;
+                    int16_t* dst = C + ((size_t)y * p.W1 + (x0 + col)) * p.Dp + vec_slot(j, p.NL, p.K) * 8;
+                    if (real_vec) {
+                        *reinterpret_cast<uint4*>(dst) = make_uint4(ac[0], ac[1], ac[2], ac[3]);
+                        unsigned m = __vmaxs2(__vmaxs2(ac[0], ac[1]), __vmaxs2(ac[2], ac[3]));
+                        vmax = max(vmax, max((int)(short)(m & 0xFFFF), (int)(short)(m >> 16)));
+                    } else {
+                        *reinterpret_cast<uint4*>(dst) = make_uint4(0, 0, 0, 0);
+                    }
                 }
             }
         }
@@ -445,39 +469,61 @@ __global__ void __launch_bounds__(256) wta_kernel(const int16_t* __restrict__ S,
     __syncthreads();
 
     constexpr int G = 256 / NL;
+    constexpr int NV8 = K * 8;               // disparities held by one lane
     const int grp = tid / NL, l = tid % NL;
     const int iters = (p.W1 + G - 1) / G;
+    const int dlane = l * NV8;               // first logical disparity of this lane
+    // uniqueness test  S(d)*(100-uniq) < minS*100  <=>  S(d) <= Tm,  Tm = floor((minS*100-1)/(100-uniq))  (0<=uniq<100)
+    const int udiv = 100 - p.uniq;
+    const float urcp = udiv > 0 ? 1.0f / (float)udiv : 0.f;
     for (int it = 0; it < iters; ++it) {
         const int xh_raw = p.W1 - 1 - (it * G + grp);
         const bool act = xh_raw >= 0;
         const int xh = act ? xh_raw : 0;
         const int16_t* Sp = S + ((size_t)y * p.W1 + xh) * p.Dp;
-        unsigned key = 0xFFFFFFFFu;
-        int sv[K * 8];
+        // 32-bit keys (S << 16 | d): their minimum is the FIRST disparity with minimal S
+        unsigned key[NV8];
 #pragma unroll
         for (int k = 0; k < K; ++k) {
             const uint4 v = *reinterpret_cast<const uint4*>(Sp + ((size_t)k * NL + l) * 8);
             const unsigned w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-            for (int e = 0; e < 8; ++e) {
-                const int s = (int)((w[e >> 1] >> ((e & 1) * 16)) & 0xFFFFu);
-                sv[k * 8 + e] = s;
-                const int d = (l * K + k) * 8 + e;
-                if (d < p.D) key = min(key, ((unsigned)s << 16) | (unsigned)d);
+            for (int e = 0; e < 4; ++e) {
+                key[k * 8 + 2 * e] = (w[e] << 16) + (unsigned)(dlane + k * 8 + 2 * e);
+                key[k * 8 + 2 * e + 1] = (w[e] & 0xFFFF0000u) + (unsigned)(dlane + k * 8 + 2 * e + 1);
             }
         }
-        key = group_min_u32<NL>(key);
-        const int minS = (int)(key >> 16), best = (int)(key & 0xFFFFu);
+        unsigned kmin = 0xFFFFFFFFu;
+#pragma unroll
+        for (int e = 0; e < NV8; ++e)
+            if (dlane + e < p.D) kmin = min(kmin, key[e]);
+        kmin = group_min_u32<NL>(kmin);
+        const int minS = (int)(kmin >> 16), best = (int)(kmin & 0xFFFFu);
         int bad = 0;
+        if (udiv > 0) {
+            const int n = minS * 100 - 1;                    // < 3.3e6: exact in float
+            int Tm = n < 0 ? -1 : (int)((float)n * urcp);
+            if (n >= 0) { if ((Tm + 1) * udiv <= n) ++Tm; else if (Tm * udiv > n) --Tm; }
+            const unsigned Tkey = Tm < 0 ? 0u : (((unsigned)Tm << 16) | 0xFFFFu);
+            const int rel = best - dlane;                   // position of best inside this lane (may be outside)
 #pragma unroll
-        for (int k = 0; k < K; ++k)
-#pragma unroll
-            for (int e = 0; e < 8; ++e) {
-                const int d = (l * K + k) * 8 + e;
-                if (d < p.D && sv[k * 8 + e] * (100 - p.uniq) < minS * 100 && abs(best - d) > 1) bad = 1;
+            for (int e = 0; e < NV8; ++e) {
+                const bool near = (unsigned)(e - rel + 1) <= 2u;
+                if (Tm >= 0 && key[e] <= Tkey && !near && dlane + e < p.D) bad = 1;
             }
+        } else {
+            // uniquenessRatio >= 100: S*(100-uniq) < minS*100 evaluated literally
 #pragma unroll
-        for (int o = NL / 2; o > 0; o >>= 1) bad |= __shfl_xor_sync(FULL, bad, o, NL);
+            for (int e = 0; e < NV8; ++e) {
+                const int sv = (int)(key[e] >> 16), d = dlane + e;
+                if (d < p.D && sv * udiv < minS * 100 && abs(best - d) > 1) bad = 1;
+            }
+        }
+        bad = __any_sync(FULL, bad && true) ? (NL == 32 ? 1 : bad) : 0;
+        if (NL < 32) {
+#pragma unroll
+            for (int o = NL / 2; o > 0; o >>= 1) bad |= __shfl_xor_sync(FULL, bad, o, NL);
+        }
         if (act && l == 0 && !bad) {
             const int x = xh + p.minX1;
             const int x2 = x - best - p.minD;

@@ -43,8 +43,9 @@ def make_pair(W, H, D, seed=0, d0=4.0, noise=2.0, lo=80, hi=176):
     tex = np.clip(_bicubic_upsample(coarse, H, Wt), 0, 254).astype(np.float32)
     d = disparity_field(W, H, D, d0)
     y, x = np.mgrid[0:H, 0:W].astype(np.float32)
-    right = tex[:, D:D + W]
-    left = _remap_linear(tex, x + D + d, y)
+    # the disparity field is defined on the RIGHT (reference) view: right(x) = left(x - d(x,y))
+    left = tex[:, D:D + W]
+    right = _remap_linear(tex, x + D - d, y)
     right = np.clip(right + rng.normal(0, noise, right.shape), 0, 254).astype(np.uint8)
     left = np.clip(left + rng.normal(0, noise, left.shape), 0, 254).astype(np.uint8)
     return right, left, d
