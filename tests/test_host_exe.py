@@ -1,0 +1,117 @@
+"""The drop-in `wass_stereo` executable: CLI contract on CPU (usage, --genconfig, config errors, exit codes;
+SURVEY.md §8b) and a full workdir run on the GPU."""
+import os
+import subprocess
+import numpy as np
+import pytest
+from helpers import ROOT
+
+EXE = os.path.join(ROOT, "wass_b200", "bin", "wass_stereo")
+
+
+def run(args, cwd=None, env=None):
+    return subprocess.run([EXE] + args, capture_output=True, text=True, cwd=cwd, env=env)
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _built():
+    if not os.path.exists(EXE):
+        from wass_b200 import build
+        build.build()
+
+
+def test_no_arguments_is_usage_and_exit_0():
+    r = run([])
+    assert r.returncode == 0          # drivers use this as a liveness probe (cli/wasscli/wasscli.py:66-71)
+    assert "wass_stereo  v." in r.stdout and "Usage:" in r.stdout
+    assert "wass_stereo [--genconfig] <config_file> <workdir> [--measure] [--rectify-only]" in r.stdout
+
+
+def test_genconfig_format(tmp_path):
+    r = run(["--genconfig"], cwd=tmp_path)
+    assert r.returncode == 0
+    txt = (tmp_path / "stereo_config.txt").read_text()
+    # incfg.hpp:436-450: "# desc\n# \n[#]KEY=value\n\n", keys sorted, defaults commented out
+    assert "# Stereo match window size\n# \n#WINSIZE=13\n\n" in txt
+    assert '#LEFT_MASK_IMAGE="none"\n' in txt and "#SAVE_COMPRESSED=true\n" in txt and "#ZGAP_PERCENTILE=99\n" in txt
+    assert "#SAVE_INPUT_SCALE=0.3\n" in txt and "#PLANE_REFINE_XMIN=-9999\n" in txt and "#MAX_DISPARITY=640\n" in txt
+    keys = [l.lstrip("#").split("=")[0] for l in txt.splitlines() if "=" in l and not l.startswith("# ")]
+    assert keys == sorted(keys) and len(keys) >= 47
+    for k in ("RANDOM_SEED", "MIN_TRIANGULATED_POINTS", "DISABLE_AUTO_LEFT_RIGHT", "PLANE_RANSAC_ROUNDS", "DENSE_P2_MULT",
+              "TRIANG_MIN_ANGLE", "PLANE_WEIGHT_PROPORTIONAL_TO_DISTANCE", "DISCARD_BURNED_AREAS", "DISPARITY_OFFSET"):
+        assert k in keys
+
+
+def test_bad_invocations(tmp_path):
+    assert run(["a"]).returncode == 255                          # -1
+    assert run(["cfg.txt", str(tmp_path / "missing_wd")]).returncode == 255
+    wd = tmp_path / "wd"; wd.mkdir()
+    assert run([str(tmp_path / "nocfg.txt"), str(wd)]).returncode == 255
+    cfg = tmp_path / "cfg.txt"
+    cfg.write_text("NOT_A_KEY=3\n")
+    r = run([str(cfg), str(wd)])
+    assert r.returncode == 255 and "Unexpected key: NOT_A_KEY" in r.stdout
+    cfg.write_text("SAVE_AS_PLY=yes\n")
+    r = run([str(cfg), str(wd)])
+    assert r.returncode == 255 and 'Unable to parse yes to "true" or "false"' in r.stdout
+    assert (wd / "wass_stereo_log.txt").exists()
+
+
+def test_config_parsing_rules(tmp_path):
+    # spaces stripped outside quotes, '#' comments, CRLF, non-default keys un-commented in the saved copy
+    wd = tmp_path / "wd"; wd.mkdir()
+    cfg = tmp_path / "cfg.txt"
+    cfg.write_text("# comment\r\n  WINSIZE = 11 \r\nLEFT_MASK_IMAGE = \"my mask.png\"\r\n\r\nSAVE_AS_PLY=true\n")
+    r = run([str(cfg), str(wd)])
+    assert r.returncode == 255                # no input data in the workdir (or no GPU) -> fails after the config stage
+    saved = (wd / "stereo_config.txt").read_text()
+    assert "\nWINSIZE=11\n" in saved and '\nLEFT_MASK_IMAGE="my mask.png"\n' in saved and "\nSAVE_AS_PLY=true\n" in saved
+    assert "#MAX_DISPARITY=640\n" in saved
+
+
+@pytest.mark.gpu
+def test_full_workdir_run(tmp_path):
+    from wass_b200 import synth, workdir, capi
+    from oracle import pipeline as op
+    W, H, D = 640, 480, 64
+    right, left, dtrue = synth.make_pair(W, H, D, seed=1, d0=8.0)
+    c = synth.make_calibration(W, H)
+    wd = tmp_path / "000000_wd"
+    # cam0 = left, cam1 = right, X1 = X0 + T with T.x > 0 (no auto-swap)
+    workdir.write_workdir(str(wd), left, right, c["K0"], c["K1"], c["R"], c["T"])
+    cfg = tmp_path / "stereo_config.txt"
+    workdir.write_config(str(cfg), MAX_DISPARITY=D, RANDOM_SEED=7, SAVE_AS_PLY=True, PLANE_RANSAC_ROUNDS=60)
+    r = run([str(cfg), str(wd)])
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+    for tok in ("[P|10|100]", "[P|20|100]", "[P|40|100]", "[P|60|100]", "[P|80|100]", "[P|90|100]", "[P|100|100]", "All done."):
+        assert tok in r.stdout
+    for f in ("mesh_cam.xyzC", "plane.txt", "P0cam.txt", "P1cam.txt", "Cam0_poseR.txt", "Cam0_poseT.txt", "Cam1_poseR.txt",
+              "Cam1_poseT.txt", "wass_stereo_log.txt", "stereo_config.txt", "mesh.ply", "plane_refinement_inliers.xyz",
+              "00000000_s.png", "K0_small.txt", "scale.txt"):
+        assert (wd / f).exists(), f
+    P1 = workdir.load_matrix_txt(str(wd / "P1cam.txt"))
+    assert np.allclose(P1, c["K1"] @ np.hstack([c["R"], c["T"].reshape(3, 1)]))
+    assert (wd / "P0cam.txt").read_text().count("\n") == 2 and "e+" in (wd / "P0cam.txt").read_text()
+    plane = np.array([float(x) for x in (wd / "plane.txt").read_text().split()])
+    assert plane.shape == (4,) and abs(np.linalg.norm(plane[:3]) - 1) < 1e-9 and plane[2] > 0
+    pts = workdir.load_camera_mesh(str(wd / "mesh_cam.xyzC"))
+    assert pts.shape[0] > 0.5 * W * H
+    dist = np.abs(pts @ plane[:3] + plane[3])
+    assert dist.max() < 1.5 + 1e-2                               # PLANE_MAX_DISTANCE crop
+    # same frame through the library in-process: same point count and plane
+    h = capi.Handle(0)
+    cal = capi.stereo_rectify(c["K0"], c["K1"], c["R"], c["T"], W, H)
+    lr = h.rectify_image(left, c["K0"], cal["R1"], cal["P1"])
+    rr = h.rectify_image(right, c["K1"], cal["R2"], cal["P2"])
+    ymin = max(cal["roi1"][1], cal["roi2"][1]); ymax = min(cal["roi1"][1] + cal["roi1"][3], cal["roi2"][1] + cal["roi2"][3])
+    wroi = min(cal["roi1"][2], cal["roi2"][2])
+    rl = (cal["roi1"][0], ymin, wroi, ymax - ymin); rrr = (cal["roi2"][0], ymin, wroi, ymax - ymin)
+    h.dense_stereo(lr[rl[1]:rl[1] + rl[3], rl[0]:rl[0] + rl[2]].copy(), rr[rrr[1]:rrr[1] + rrr[3], rrr[0]:rrr[0] + rrr[2]].copy(),
+                   capi.dense_params(MAX_DISPARITY=D))
+    calib = dict(K0=c["K0"], K1=c["K1"], R=c["R"], T=c["T"], R1=cal["R1"], R2=cal["R2"], P1=cal["P1"], P2=cal["P2"], roi_left=rl, roi_right=rrr)
+    n = h.triangulate_from_dense(left, right, calib, (H, W))
+    assert ("%d valid points found" % n) in r.stdout
+    h.close()
+    # depth against the generator's ground truth
+    z_true = W / dtrue
+    assert abs(np.median(pts[:, 2]) - np.median(z_true)) / np.median(z_true) < 0.1

@@ -48,7 +48,21 @@ def build(force=False, verbose=False):
     if force or procs or _newer(objs, LIB):
         cmd = [NVCC] + ARCH + ["-shared", "-ccbin", CXX, "-o", LIB] + objs + ["-lcudart_static", "-lpthread", "-ldl", "-lrt"]
         subprocess.check_call(cmd)
+    build_host(force or bool(procs))
     return LIB
+
+
+def build_host(force=False):
+    """The drop-in `wass_stereo` executable (C++ host over the C ABI): wass_b200/bin/wass_stereo."""
+    host = os.path.join(CSRC, "host")
+    srcs = sorted(glob.glob(os.path.join(host, "*.cpp")))
+    exe = os.path.join(HERE, "bin", "wass_stereo")
+    os.makedirs(os.path.dirname(exe), exist_ok=True)
+    deps = srcs + glob.glob(os.path.join(host, "*.hpp")) + glob.glob(os.path.join(ROOT, "include", "*.h")) + [LIB]
+    if force or _newer(deps, exe):
+        cmd = [CXX, "-O2", "-std=c++17", "-Wall", "-o", exe] + srcs + ["-L" + HERE, "-lwassgpu", "-lz", "-Wl,-rpath,$ORIGIN/.."]
+        subprocess.check_call(cmd)
+    return exe
 
 
 if __name__ == "__main__":

@@ -1,0 +1,535 @@
+// wass_stereo -- drop-in replacement of the reference's stage-4 executable
+// (src/wass_stereo/wass_stereo.cpp:1799-2149): same argv, exit codes, progress protocol, configuration
+// surface and workdir files; all per-pixel work runs on the GPU through the C ABI of libwassgpu.so.
+#include "../../../include/wassgpu.h"
+#include "config.hpp"
+#include "io.hpp"
+
+#include <sys/stat.h>
+#include <sys/time.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <ctime>
+#include <fstream>
+#include <iomanip>
+#include <iostream>
+#include <sstream>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+using namespace wasshost;
+
+namespace {
+
+// ---- logging: the NaiveLogger of src/include/log.hpp:78-168 (stdout + log file, "<scope> [sev  ] " prefix)
+std::string g_scope;
+std::ofstream* g_logfile = nullptr;
+struct Log {
+    explicit Log(const char* sev) { put(g_scope + " [" + sev + "] "); }
+    ~Log() { std::cout << std::endl; if (g_logfile) (*g_logfile) << std::endl; }
+    template <typename T> Log& operator<<(const T& v) { std::cout << v; if (g_logfile) (*g_logfile) << v; return *this; }
+    static void put(const std::string& s) { std::cout << s; if (g_logfile) (*g_logfile) << s; }
+};
+#define LOGI Log("info ")
+#define LOGE Log("error")
+#define LOG_SCOPE(n) (g_scope = (n))
+
+struct Timer {   // cvlab::HiresTimer (src/wass_lib/hires_timer.cpp): cumulative seconds + named events
+    double t0 = 0, tstop = -1;
+    std::vector<std::pair<double, std::string>> evts;
+    static double now() { timeval tv; gettimeofday(&tv, nullptr); return tv.tv_sec + tv.tv_usec * 1e-6; }
+    void start() { t0 = now(); }
+    void stop() { tstop = now(); }
+    double elapsed() const { return (tstop >= 0 ? tstop : now()) - t0; }
+    void mark(const char* name) { evts.push_back({elapsed(), name}); }
+};
+
+bool exists(const std::string& p) { struct stat st; return stat(p.c_str(), &st) == 0; }
+
+Mat eye3() { Mat m; m.rows = m.cols = 3; m.v = {1, 0, 0, 0, 1, 0, 0, 0, 1}; return m; }
+Mat zeros(int r, int c) { Mat m; m.rows = r; m.cols = c; m.v.assign((size_t)r * c, 0.0); return m; }
+Mat mul(const Mat& a, const Mat& b)
+{
+    Mat o = zeros(a.rows, b.cols);
+    for (int i = 0; i < a.rows; ++i) for (int j = 0; j < b.cols; ++j) { double s = 0; for (int k = 0; k < a.cols; ++k) s += a.at(i, k) * b.at(k, j); o.at(i, j) = s; }
+    return o;
+}
+Mat transpose(const Mat& a) { Mat o = zeros(a.cols, a.rows); for (int i = 0; i < a.rows; ++i) for (int j = 0; j < a.cols; ++j) o.at(j, i) = a.at(i, j); return o; }
+Mat stack_matrices(const Mat& R, const Mat& T)   // wass_stereo.cpp:181-194
+{
+    Mat o = zeros(3, 4);
+    for (int i = 0; i < 3; ++i) { for (int j = 0; j < 3; ++j) o.at(i, j) = R.at(i, j); o.at(i, 3) = T.at(i, 0); }
+    return o;
+}
+void invert_RT(Mat& R, Mat& T)   // wass_stereo.cpp:197-201
+{
+    R = transpose(R);
+    Mat t = mul(R, T);
+    for (auto& x : t.v) x = -x;
+    T = t;
+}
+
+struct Env {
+    Timer timer;
+    std::string workdir;
+    Mat K0, K1, intr_left, intr_right, R, T, Rinv, Tinv, P0, P1, Rpose0, Tpose0, Rpose1, Tpose1;
+    Image8 left, right, left_rect, right_rect, left_crop, right_crop;
+    int left_index = 0, right_index = 1;
+    double cam_distance = 1.0;
+    double R1[9], R2[9], P1r[12], P2r[12];
+    int roi_left[4], roi_right[4];
+    int disparity_compensation = 0;
+    void computeP() { P0 = mul(K0, stack_matrices(Rpose0, Tpose0)); P1 = mul(K1, stack_matrices(Rpose1, Tpose1)); }
+    void swapLeftRight()   // wass_stereo.cpp:262-297
+    {
+        std::swap(left_index, right_index);
+        std::swap(left, right);
+        std::swap(intr_left, intr_right);
+        std::swap(R, Rinv);
+        std::swap(T, Tinv);
+        std::swap(Rpose0, Rpose1);
+        std::swap(Tpose0, Tpose1);
+        invert_RT(Rpose0, Tpose0);
+        invert_RT(Rpose1, Tpose1);
+        computeP();
+    }
+};
+
+std::string path(const Env& e, const char* f) { return e.workdir + "/" + f; }
+
+int save_configuration(const Config& cfg, const std::string& filename)   // wass_stereo.cpp:1776-1795
+{
+    LOG_SCOPE("wass_stereo");
+    LOGI << "Writing " << filename;
+    std::ofstream ofs(filename.c_str());
+    if (!ofs.is_open()) { LOGE << "Unable to open " << filename << " for write"; return -1; }
+    ofs << cfg.to_config_string();
+    ofs.close();
+    LOGI << "Done!";
+    return 0;
+}
+
+// bicubic (A=-0.75) resize for the *_s.png previews (wass_stereo.cpp:401-418); content is informative only
+Image8 resize_cubic(const Image8& src, int nw, int nh)
+{
+    Image8 o; o.rows = nh; o.cols = nw; o.px.resize((size_t)nw * nh);
+    auto wgt = [](float x, float* c) {
+        const float A = -0.75f;
+        c[0] = ((A * (x + 1) - 5 * A) * (x + 1) + 8 * A) * (x + 1) - 4 * A;
+        c[1] = ((A + 2) * x - (A + 3)) * x * x + 1;
+        c[2] = ((A + 2) * (1 - x) - (A + 3)) * (1 - x) * (1 - x) + 1;
+        c[3] = 1.f - c[0] - c[1] - c[2];
+    };
+    const double sx = (double)src.cols / nw, sy = (double)src.rows / nh;
+    for (int y = 0; y < nh; ++y) {
+        const double fy = (y + 0.5) * sy - 0.5; const int iy = (int)floor(fy); float cy[4]; wgt((float)(fy - iy), cy);
+        for (int x = 0; x < nw; ++x) {
+            const double fx = (x + 0.5) * sx - 0.5; const int ix = (int)floor(fx); float cx[4]; wgt((float)(fx - ix), cx);
+            float s = 0;
+            for (int a = 0; a < 4; ++a) {
+                const int yy = std::min(std::max(iy - 1 + a, 0), src.rows - 1);
+                for (int b = 0; b < 4; ++b) { const int xx = std::min(std::max(ix - 1 + b, 0), src.cols - 1); s += cy[a] * cx[b] * src.px[(size_t)yy * src.cols + xx]; }
+            }
+            o.px[(size_t)y * nw + x] = (uint8_t)std::min(std::max((int)lrintf(s), 0), 255);
+        }
+    }
+    return o;
+}
+
+bool load_data(Env& env, const Config& cfg)   // wass_stereo.cpp:337-442
+{
+    LOG_SCOPE("load_data");
+    std::string err;
+    if (!load_matrix_xml(path(env, "ext_R.xml"), env.R, &err)) LOGE << err;
+    if (env.R.rows != 3 || env.R.cols != 3) { LOGE << "invalid extrinsic rotation matrix (ext_R.xml)"; return false; }
+    if (!load_matrix_xml(path(env, "ext_T.xml"), env.T, &err)) LOGE << err;
+    if (env.T.cols != 1 || env.T.rows != 3) { LOGE << "invalid extrinsic translation vector (ext_T.xml)"; return false; }
+    env.Rinv = env.R; env.Tinv = env.T;
+    invert_RT(env.Rinv, env.Tinv);
+    const double cur = sqrt(env.T.at(0, 0) * env.T.at(0, 0) + env.T.at(1, 0) * env.T.at(1, 0) + env.T.at(2, 0) * env.T.at(2, 0));
+    for (int i = 0; i < 3; ++i) {
+        env.T.at(i, 0) = env.T.at(i, 0) / cur * env.cam_distance;
+        env.Tinv.at(i, 0) = env.Tinv.at(i, 0) / cur * env.cam_distance;
+    }
+    env.Rpose0 = eye3(); env.Tpose0 = zeros(3, 1); env.Rpose1 = env.R; env.Tpose1 = env.T;
+    if (!load_matrix_xml(path(env, "intrinsics_00000000.xml"), env.K0, &err)) { LOGE << err; return false; }
+    if (!load_matrix_xml(path(env, "intrinsics_00000001.xml"), env.K1, &err)) { LOGE << err; return false; }
+    if (env.K0.rows != 3 || env.K0.cols != 3 || env.K1.rows != 3 || env.K1.cols != 3) { LOGE << "invalid intrinsics"; return false; }
+    env.intr_left = env.K0; env.intr_right = env.K1;
+    env.computeP();
+    if (!read_png_gray(path(env, "undistorted/00000000.png"), env.left, &err)) { LOGE << "unable to load input images"; LOGE << err; return false; }
+    env.left_index = 0;
+    LOGI << "image 0 loaded, Size: " << env.left.cols << "x" << env.left.rows;
+    if (!read_png_gray(path(env, "undistorted/00000001.png"), env.right, &err)) { LOGE << "unable to load input images"; LOGE << err; return false; }
+    env.right_index = 1;
+    LOGI << "image 1 loaded, Size: " << env.right.cols << "x" << env.right.rows;
+    if (env.left.cols != env.right.cols || env.left.rows != env.right.rows) { LOGE << "left and right images differ in size"; return false; }
+    const double sis = cfg.getd("SAVE_INPUT_SCALE");
+    if (sis < 1.0) {
+        const size_t nw = (size_t)(env.left.cols * sis), nh = (size_t)(env.left.rows * sis);
+        const double scale = (double)nw / (double)env.left.cols;
+        LOGI << "original size: " << env.left.cols << "x" << env.left.rows;
+        LOGI << "  scaled size: " << nw << "x" << nh;
+        LOGI << "        scale: " << scale;
+        if (nw > 0 && nh > 0) {
+            write_png_gray(path(env, "00000000_s.png"), resize_cubic(env.left, (int)nw, (int)nh));
+            write_png_gray(path(env, "00000001_s.png"), resize_cubic(env.right, (int)nw, (int)nh));
+        }
+        Mat k0 = env.intr_left, k1 = env.intr_right;
+        for (auto& x : k0.v) x *= scale;
+        for (auto& x : k1.v) x *= scale;
+        k0.at(2, 2) = 1; k1.at(2, 2) = 1;
+        save_matrix_txt(path(env, "K0_small.txt"), k0);
+        save_matrix_txt(path(env, "K1_small.txt"), k1);
+        std::ofstream ofs(path(env, "scale.txt").c_str());
+        ofs.precision(16); ofs << std::scientific << scale; ofs.close();
+    }
+    return true;
+}
+
+bool rectify(Env& env, const Config& cfg, wsg_handle* h)   // wass_stereo.cpp:447-613
+{
+    LOG_SCOPE("rectify");
+    LOGI << "rectifying...";
+    bool auto_swap = true, do_swap = false;
+    if (fabs(env.T.at(1, 0)) > fabs(env.T.at(0, 0))) { LOGE << "Vertical stereo not supported"; return false; }
+    LOGI << "Detected stereo setup:";
+    if (env.T.at(0, 0) > 0) LOGI << "CAM1 (L) ---------  CAM0 (R)"; else LOGI << "CAM0 (L) ---------  CAM1 (R)";
+    if (cfg.getb("DISABLE_AUTO_LEFT_RIGHT")) {
+        auto_swap = false;
+        do_swap = cfg.getb("SWAP_LEFT_RIGHT");
+        LOGI << "auto left-right detection disabled. Swap left-right? " << (do_swap ? "YES" : "NO");
+        if (do_swap) { LOGI << "swapping left-right images as requested"; env.swapLeftRight(); }
+    } else if (env.T.at(0, 0) < 0) {
+        LOGI << "auto-swapping left-right images" << "\n";
+        env.swapLeftRight();
+    }
+    if (cfg.getb("USE_CUSTOM_STEREORECTIFY")) {
+        LOGE << "USE_CUSTOM_STEREORECTIFY=true is not supported by this build (see DESIGN.md)";
+        return false;
+    }
+    LOGI << "Rectifying via cv::stereoRectify";
+    const int W = env.left.cols, H = env.left.rows;
+    int roi_l[4], roi_r[4];
+    bool ok = false;
+    int guard = 0;
+    do {
+        if (wsg_stereo_rectify(env.intr_left.v.data(), env.intr_right.v.data(), env.R.v.data(), env.T.v.data(), W, H, env.R1, env.R2,
+                               env.P1r, env.P2r, roi_l, roi_r) != WSG_OK) { LOGE << "stereoRectify failed"; return false; }
+        if (fabs(env.P2r[3]) < fabs(env.P2r[7])) { LOGE << "vertical stereo not supported"; return false; }
+        if (roi_l[2] == 0 || roi_r[2] == 0 || roi_l[3] == 0 || roi_r[3] == 0) { LOGE << "the epipole lies inside the image plane"; return false; }
+        if (auto_swap) {
+            if (env.P2r[3] < 0) { LOGI << "auto-swapping left-right images" << "\n"; env.swapLeftRight(); }
+            else ok = true;
+        } else if (do_swap) {
+            LOGI << "swapping left-right images as requested"; env.swapLeftRight(); do_swap = false;
+        } else ok = true;
+    } while (!ok && ++guard < 4);
+    if (!ok) { LOGE << "rectification did not converge"; return false; }
+    const int ymin = std::max(roi_l[1], roi_r[1]);
+    const int ymax = std::min(roi_l[1] + roi_l[3], roi_r[1] + roi_r[3]);
+    env.roi_left[0] = roi_l[0]; env.roi_left[1] = ymin; env.roi_left[2] = roi_l[2]; env.roi_left[3] = ymax - ymin;
+    env.roi_right[0] = roi_r[0]; env.roi_right[1] = ymin; env.roi_right[2] = roi_r[2]; env.roi_right[3] = ymax - ymin;
+    if (env.roi_left[2] > env.roi_right[2]) env.roi_left[2] = env.roi_right[2]; else env.roi_right[2] = env.roi_left[2];
+    if (env.roi_left[3] <= 0 || env.roi_left[2] <= 0) { LOGE << "empty rectification ROI"; return false; }
+    env.left_rect.rows = env.right_rect.rows = H; env.left_rect.cols = env.right_rect.cols = W;
+    env.left_rect.px.resize((size_t)W * H); env.right_rect.px.resize((size_t)W * H);
+    if (wsg_rectify_image(h, env.left.px.data(), H, W, W, env.intr_left.v.data(), env.R1, env.P1r, env.left_rect.px.data()) != WSG_OK ||
+        wsg_rectify_image(h, env.right.px.data(), H, W, W, env.intr_right.v.data(), env.R2, env.P2r, env.right_rect.px.data()) != WSG_OK) {
+        LOGE << "remap failed: " << wsg_last_error(h); return false;
+    }
+    auto crop = [&](const Image8& src, const int* r, Image8& dst) {
+        dst.rows = r[3]; dst.cols = r[2]; dst.px.resize((size_t)r[2] * r[3]);
+        for (int y = 0; y < r[3]; ++y) memcpy(&dst.px[(size_t)y * r[2]], &src.px[(size_t)(r[1] + y) * src.cols + r[0]], r[2]);
+    };
+    crop(env.left_rect, env.roi_left, env.left_crop);
+    crop(env.right_rect, env.roi_right, env.right_crop);
+    LOGI << "rectification map generated. Size: " << env.left_crop.cols << "x" << env.left_crop.rows;
+    return true;
+}
+
+void save_poses(const Env& env)   // wass_stereo.cpp:1888-1894, 1902-1908
+{
+    save_matrix_txt(path(env, "P0cam.txt"), env.P0);
+    save_matrix_txt(path(env, "P1cam.txt"), env.P1);
+    save_matrix_txt(path(env, "Cam0_poseR.txt"), env.Rpose0);
+    save_matrix_txt(path(env, "Cam0_poseT.txt"), env.Tpose0);
+    save_matrix_txt(path(env, "Cam1_poseR.txt"), env.Rpose1);
+    save_matrix_txt(path(env, "Cam1_poseT.txt"), env.Tpose1);
+}
+
+bool save_ply(wsg_handle* h, const std::string& filename)   // PovMesh::save_as_ply_points, PovMesh.cpp:463-517
+{
+    int w = 0, hh = 0; unsigned long long n = 0;
+    if (wsg_mesh_size(h, &w, &hh, &n) != WSG_OK) return false;
+    const size_t np = (size_t)w * hh;
+    std::vector<uint8_t> valid(np), grey(np);
+    std::vector<double> xyz(np * 3);
+    if (wsg_mesh_download(h, valid.data(), xyz.data(), grey.data()) != WSG_OK) return false;
+    std::ofstream ofs(filename.c_str(), std::ios::binary);
+    if (ofs.fail()) return false;
+    ofs << "ply\nformat binary_little_endian 1.0\nelement vertex " << n << "\nproperty float x\nproperty float y\nproperty float z\n"
+        << "property uchar red\nproperty uchar green\nproperty uchar blue\nend_header\n";
+    std::vector<char> buf(n * 15);
+    char* p = buf.data();
+    for (size_t i = 0; i < np; ++i)
+        if (valid[i]) {
+            for (int k = 0; k < 3; ++k) { const float f = (float)xyz[3 * i + k]; memcpy(p, &f, 4); p += 4; }
+            p[0] = p[1] = p[2] = (char)grey[i]; p += 3;
+        }
+    ofs.write(buf.data(), (std::streamsize)buf.size());
+    return !ofs.fail();
+}
+
+void show_time_stats(const Timer& t)   // src/wass_stereo/render.hpp:175-191
+{
+    LOGI << "+----------------------------+-------------------+";
+    LOGI << "|   Task                     |   Time (seconds)  |";
+    LOGI << "+----------------------------+-------------------+";
+    double last = 0;
+    for (const auto& e : t.evts) {
+        std::stringstream ss; ss << "| " << std::setw(25) << e.second << "  |" << std::setw(18) << (e.first - last) << " |";
+        LOGI << ss.str();
+        last = e.first;
+    }
+    LOGI << "+----------------------------+-------------------+";
+    std::stringstream ss; ss << "| " << std::setw(25) << "TOTAL" << "  |" << std::setw(18) << t.elapsed() << " |";
+    LOGI << ss.str();
+    LOGI << "+----------------------------+-------------------+";
+}
+
+#define WSG_CHECK(call) do { if ((call) != WSG_OK) throw std::runtime_error(std::string(#call) + ": " + wsg_last_error(h)); } while (0)
+
+}  // namespace
+
+int main(int argc, char* argv[])
+{
+    std::cout << "wass_stereo  v. " << "1.7_b200-0.1" << std::endl;
+    std::cout << "----------------------------------------------" << std::endl;
+    std::cout << " [Release] " << wsg_version() << ", OpenCV none" << std::endl << std::endl;
+    Config cfg;
+    if (argc == 1) {
+        std::cout << "Usage:" << std::endl;
+        std::cout << "wass_stereo [--genconfig] <config_file> <workdir> [--measure] [--rectify-only]" << std::endl << std::endl;
+        std::cout << "Not enough arguments, aborting." << std::endl;
+        return 0;
+    }
+    if (argc > 1 && std::string("--genconfig") == argv[1]) return save_configuration(cfg, "stereo_config.txt");
+    if (argc != 3 && argc != 4) { std::cerr << "Invalid arguments" << std::endl; return -1; }
+    Env env;
+    env.workdir = argv[2];
+    if (!exists(env.workdir)) { std::cerr << "\"" << env.workdir << "\" does not exists, aborting." << std::endl; return -1; }
+    g_logfile = new std::ofstream(path(env, "wass_stereo_log.txt").c_str());
+    LOG_SCOPE("wass_stereo");
+    {
+        LOGI << "Loading configuration file " << argv[1];
+        std::ifstream ifs(argv[1]);
+        if (!ifs.is_open()) { LOGE << "Unable to load " << argv[1]; return -1; }
+        try { cfg.load(ifs); } catch (std::runtime_error& er) { LOGE << er.what(); return -1; }
+        if (save_configuration(cfg, path(env, "stereo_config.txt")) != 0) LOGE << "Unable to save stereo configuration file";
+    }
+    if (cfg.geti("RANDOM_SEED") == -1) srand((unsigned)time(0));
+    else { srand(cfg.geti("RANDOM_SEED")); LOGI << "random seed set to: " << cfg.geti("RANDOM_SEED"); }
+
+    wsg_handle* h = nullptr;
+    int device = 0;
+    if (const char* e = getenv("WASS_GPU_DEVICE")) device = atoi(e);
+    if (wsg_create(device, &h) != WSG_OK) { LOGE << "no usable CUDA device " << device << " (this build has no CPU path)"; return -1; }
+    try {
+        LOGI << "Reconstructing \"" << env.workdir << "\"";
+        env.timer.start();
+        env.cam_distance = 1.0;
+        if (!load_data(env, cfg)) return -1;
+        env.timer.mark("Data load");
+        std::cout << "[P|10|100]" << std::endl;
+        save_poses(env);
+        if (!rectify(env, cfg, h)) return -1;   // the reference ignores this return value and runs on undefined state
+        env.timer.mark("Rectification");
+        std::cout << "[P|20|100]" << std::endl;
+        LOG_SCOPE("wass_stereo");
+        save_poses(env);
+        if (argc == 4 && std::string("--rectify-only") == argv[3]) { LOGI << "All done."; return 0; }
+        if (argc == 4 && std::string("--measure") == argv[3]) { LOGE << "--measure needs the interactive HighGUI point picker; not available in this build"; return -1; }
+
+        // ---- dense stereo (wass_stereo.cpp:764-1020)
+        LOG_SCOPE("sgbm_dense_stereo");
+        if (cfg.geti("MEDIAN_FILTER_WSIZE") >= 3 || cfg.geti("DENSE_DISPARITY_BIGGEST_COMPONENT_THRESHOLD") > 0)
+            throw std::runtime_error("MEDIAN_FILTER_WSIZE / DENSE_DISPARITY_BIGGEST_COMPONENT_THRESHOLD are not supported by this build");
+        wsg_dense_params dp;
+        wsg_dense_params_default(&dp);
+        dp.MIN_DISPARITY = cfg.geti("MIN_DISPARITY"); dp.MAX_DISPARITY = cfg.geti("MAX_DISPARITY"); dp.WINSIZE = cfg.geti("WINSIZE");
+        dp.DENSE_SCALE = cfg.getd("DENSE_SCALE"); dp.DISPARITY_OFFSET = cfg.geti("DISPARITY_OFFSET");
+        dp.DISP_DILATE_STEPS = cfg.geti("DISP_DILATE_STEPS"); dp.DISP_EROSION_STEPS = cfg.geti("DISP_EROSION_STEPS");
+        dp.DENSE_P1_MULT = cfg.geti("DENSE_P1_MULT"); dp.DENSE_P2_MULT = cfg.geti("DENSE_P2_MULT");
+        dp.DENSE_UNIQUENESS_RATIO = cfg.geti("DENSE_UNIQUENESS_RATIO"); dp.DENSE_DISP12MAXDIFF = cfg.geti("DENSE_DISP12MAXDIFF");
+        dp.DENSE_PREFILTER_CAP = cfg.geti("DENSE_PREFILTER_CAP"); dp.DENSE_SPECKLE_RANGE = cfg.geti("DENSE_SPECKLE_RANGE");
+        dp.DENSE_SPECKLE_WINDOW_SIZE = cfg.geti("DENSE_SPECKLE_WINDOW_SIZE");
+        dp.mode = cfg.getb("SGM_FULL_8PATH") ? WSG_MODE_HH : WSG_MODE_SGBM;
+        LOGI << "Disparity offset: " << dp.DISPARITY_OFFSET << " px";
+        env.disparity_compensation = dp.DISPARITY_OFFSET > 0 ? 0 : -dp.DISPARITY_OFFSET;
+        LOGI << "computing dense disparity map... (may take a while)";
+        std::vector<float> disp_roi((size_t)env.right_crop.rows * env.right_crop.cols);
+        WSG_CHECK(wsg_dense_stereo(h, env.left_crop.px.data(), env.right_crop.px.data(), env.right_crop.rows, env.right_crop.cols,
+                                   env.right_crop.cols, &dp, disp_roi.data(), nullptr));
+        wsg_sgbm_stats st;
+        if (wsg_sgbm_get_stats(h, &st) == WSG_OK && st.out_of_domain)
+            LOGE << "matching cost range exceeds int16 headroom (max cost " << st.max_cost << "): results may deviate from OpenCV";
+        LOGI << "dense stereo completed successfully";
+        env.timer.mark("Dense Stereo");
+        std::cout << "[P|40|100]" << std::endl;
+
+        // ---- triangulation (wass_stereo.cpp:1039-1386)
+        LOG_SCOPE("triangulate");
+        wsg_calib cal;
+        memcpy(cal.K0, env.intr_left.v.data(), 72); memcpy(cal.K1, env.intr_right.v.data(), 72);
+        memcpy(cal.R, env.R.v.data(), 72); memcpy(cal.T, env.T.v.data(), 24);
+        memcpy(cal.R1, env.R1, 72); memcpy(cal.R2, env.R2, 72); memcpy(cal.P1, env.P1r, 96); memcpy(cal.P2, env.P2r, 96);
+        memcpy(cal.roi_left, env.roi_left, 16); memcpy(cal.roi_right, env.roi_right, 16);
+        cal.left_cols = env.left.cols; cal.left_rows = env.left.rows; cal.right_cols = env.right.cols; cal.right_rows = env.right.rows;
+        cal.rect_cols = env.right_rect.cols; cal.rect_rows = env.right_rect.rows;
+        wsg_tri_params tp;
+        wsg_tri_params_default(&tp);
+        tp.TRIANG_MIN_ANGLE = cfg.getd("TRIANG_MIN_ANGLE");
+        tp.TRIANG_BBOX_TOP = cfg.getd("TRIANG_BBOX_TOP"); tp.TRIANG_BBOX_LEFT = cfg.getd("TRIANG_BBOX_LEFT");
+        tp.TRIANG_BBOX_RIGHT = cfg.getd("TRIANG_BBOX_RIGHT"); tp.TRIANG_BBOX_BOTTOM = cfg.getd("TRIANG_BBOX_BOTTOM");
+        tp.DISCARD_BURNED_AREAS = cfg.getb("DISCARD_BURNED_AREAS"); tp.disparity_compensation = env.disparity_compensation;
+        tp.DENSE_SCALE = dp.DENSE_SCALE; tp.cam_distance = env.cam_distance;
+        auto load_mask = [&](const char* key, const Image8& ref, std::vector<uint8_t>& m) -> const uint8_t* {
+            if (cfg.gets(key) == "none") return nullptr;
+            const std::string fn = env.workdir + "/" + cfg.gets(key);
+            LOGI << "Loading " << fn << " as " << (std::string(key) == "LEFT_MASK_IMAGE" ? "left" : "right") << " camera mask";
+            Image8 im; std::string err;
+            if (!read_png_gray(fn, im, &err) || im.cols != ref.cols || im.rows != ref.rows) { LOGE << "not found or invalid image."; return nullptr; }
+            m.resize(im.px.size());
+            for (size_t i = 0; i < m.size(); ++i) m[i] = im.px[i] > 0 ? 1 : 0;   // cv::threshold(aux, mask, 0.5, 1, THRESH_BINARY)
+            return m.data();
+        };
+        std::vector<uint8_t> lm, rm;
+        const uint8_t* lmp = load_mask("LEFT_MASK_IMAGE", env.left, lm);
+        const uint8_t* rmp = load_mask("RIGHT_MASK_IMAGE", env.right, rm);
+        LOGI << "triangulating disparity map";
+        unsigned long long n_pts = 0;
+        WSG_CHECK(wsg_triangulate_from_dense(h, env.left.px.data(), env.right.px.data(), lmp, rmp, &cal, &tp, &n_pts));
+        LOGI << "... 100%";
+        LOGI << n_pts << " valid points found";
+        env.timer.mark("Triangulation");
+        std::cout << "[P|60|100]" << std::endl;
+        LOG_SCOPE("wass_stereo");
+        if ((long long)n_pts < cfg.geti("MIN_TRIANGULATED_POINTS")) { LOGE << "Too few points triangulated, aborting"; return -1; }
+
+        // ---- outlier removal (wass_stereo.cpp:2046-2060)
+        double zgap = 0;
+        WSG_CHECK(wsg_mesh_zgap_percentile(h, cfg.getd("ZGAP_PERCENTILE"), &zgap));
+        env.timer.mark("Z-gap stats");
+        unsigned long long nleft = 0;
+        LOG_SCOPE("cluster");
+        LOGI << "extracting connected-components";
+        WSG_CHECK(wsg_mesh_biggest_component(h, zgap, &nleft));
+        LOGI << "biggest component size: " << nleft << " (px)";
+        env.timer.mark("Outlier removal");
+        std::cout << "[P|80|100]" << std::endl;
+        LOG_SCOPE("wass_stereo");
+        if (cfg.getb("SAVE_FULL_MESH") && !save_ply(h, path(env, "mesh_full.ply"))) { LOGE << "unable to save mesh data."; return -1; }
+
+        // ---- plane (wass_stereo.cpp:2062-2107)
+        LOGI << "estimating best fitting plane...";
+        const int rounds = cfg.geti("PLANE_RANSAC_ROUNDS");
+        std::vector<int32_t> triples((size_t)std::max(rounds, 1) * 6);
+        int mw = 0, mh = 0;
+        WSG_CHECK(wsg_mesh_size(h, &mw, &mh, nullptr));
+        wsg_ransac_draw(mw, mh, rounds, triples.data());
+        double plane[4] = {0, 0, 0, 0};
+        int ok = 0; unsigned long long best = 0;
+        if (rounds > 0) WSG_CHECK(wsg_mesh_ransac_plane(h, triples.data(), rounds, cfg.getd("PLANE_RANSAC_THRESHOLD"), plane, &ok, &best));
+        LOG_SCOPE("ransac_find_plane");
+        LOGI << rounds << " ransac rounds, " << best << " best inliers";
+        LOGI << "ransac plane coeffs: " << plane[0] << " " << plane[1] << " " << plane[2] << " " << plane[3];
+        LOG_SCOPE("wass_stereo");
+        if (ok) {
+            env.timer.mark("Plane fitting");
+            std::cout << "[P|90|100]" << std::endl;
+            LOGI << "refining plane";
+            unsigned long long k = 0;
+            WSG_CHECK(wsg_mesh_crop_plane(h, plane, cfg.getd("PLANE_RANSAC_THRESHOLD"), &k));
+            LOGI << "number of points after plane cropping: " << k;
+            wsg_refine_params rp;
+            wsg_refine_params_default(&rp);
+            rp.PLANE_REFINE_XMIN = cfg.getd("PLANE_REFINE_XMIN"); rp.PLANE_REFINE_XMAX = cfg.getd("PLANE_REFINE_XMAX");
+            rp.PLANE_REFINE_YMIN = cfg.getd("PLANE_REFINE_YMIN"); rp.PLANE_REFINE_YMAX = cfg.getd("PLANE_REFINE_YMAX");
+            rp.PLANE_REFINEMENT_MAX_DISTANCE = cfg.getd("PLANE_REFINEMENT_MAX_DISTANCE");
+            rp.PLANE_WEIGHT_PROPORTIONAL_TO_DISTANCE = cfg.getb("PLANE_WEIGHT_PROPORTIONAL_TO_DISTANCE");
+            rp.PLANE_USE_CENTRAL_THIRD_ONLY = cfg.getb("PLANE_USE_CENTRAL_THIRD_ONLY");
+            {   // plane_refinement_inliers.xyz: every 10th refinement inlier, in grid scan order (wass_stereo.cpp:2077-2085)
+                const size_t np = (size_t)mw * mh;
+                std::vector<uint8_t> valid(np);
+                std::vector<double> xyz(np * 3);
+                WSG_CHECK(wsg_mesh_download(h, valid.data(), xyz.data(), nullptr));
+                const bool ct = rp.PLANE_USE_CENTRAL_THIRD_ONLY != 0;
+                const int umin = ct ? mw / 4 : 0, umax = ct ? mw * 3 / 4 : mw - 1, vmin = ct ? mh / 4 : 0, vmax = ct ? mh * 2 / 3 : mh - 1;
+                std::ofstream ofs(path(env, "plane_refinement_inliers.xyz").c_str());
+                size_t idx = 0;
+                for (int v = vmin; v <= vmax; ++v)
+                    for (int u = umin; u <= umax; ++u) {
+                        const size_t i = (size_t)v * mw + u;
+                        if (!valid[i]) continue;
+                        const double x = xyz[3 * i], y = xyz[3 * i + 1], z = xyz[3 * i + 2];
+                        if (x > rp.PLANE_REFINE_XMIN && x < rp.PLANE_REFINE_XMAX && y > rp.PLANE_REFINE_YMIN && y < rp.PLANE_REFINE_YMAX &&
+                            sqrt(x * x + y * y + z * z) < rp.PLANE_REFINEMENT_MAX_DISTANCE) {
+                            if (idx % 10 == 0) ofs << x << " " << y << " " << z << std::endl;
+                            ++idx;
+                        }
+                    }
+            }
+            unsigned long long nin = 0;
+            WSG_CHECK(wsg_mesh_refine_plane(h, &rp, plane, &nin));
+            LOG_SCOPE("refine_plane");
+            LOGI << "refinement inliers (after cropping): " << nin;
+            LOGI << "estimated plane coeffs: " << plane[0] << " " << plane[1] << " " << plane[2] << " " << plane[3];
+            LOG_SCOPE("wass_stereo");
+            WSG_CHECK(wsg_mesh_crop_plane(h, plane, cfg.getd("PLANE_MAX_DISTANCE"), &k));
+            LOGI << "number of points after plane cropping: " << k;
+            env.timer.mark("Plane refinement");
+            std::ofstream ofs(path(env, "plane.txt").c_str());
+            ofs << std::setprecision(20);
+            for (int i = 0; i < 4; ++i) ofs << plane[i] << std::endl;
+        } else {
+            LOGE << "ransac failed. I'll continue anyway but plane data won't be available!";
+            std::ofstream ofs(path(env, "plane.txt").c_str());
+            ofs << "nan nan nan nan" << std::endl;
+        }
+
+        // ---- export (wass_stereo.cpp:2110-2135)
+        LOGI << "Exporting point cloud data";
+        if (cfg.getb("SAVE_AS_PLY") && !save_ply(h, path(env, "mesh.ply"))) { LOGE << "unable to save mesh data."; return -1; }
+        {
+            int w2 = 0, h2 = 0; unsigned long long nv = 0;
+            WSG_CHECK(wsg_mesh_size(h, &w2, &h2, &nv));
+            std::vector<char> buf(256 + (size_t)nv * 12);
+            size_t nb = 0;
+            if (cfg.getb("SAVE_COMPRESSED")) {
+                LOG_SCOPE("save_as_xyz_compressed");
+                LOGI << "saving mesh as compressed xyz file...";
+                WSG_CHECK(wsg_mesh_export_xyzc(h, plane, buf.data(), buf.size(), &nb));
+                if (!write_file(path(env, "mesh_cam.xyzC"), buf.data(), nb)) { LOGE << "unable to save mesh data"; return -1; }
+                LOGI << "total data size: " << (double)nb / 1e6 << " MB";
+            } else {
+                WSG_CHECK(wsg_mesh_export_xyzbin(h, buf.data(), buf.size(), &nb));
+                if (!write_file(path(env, "mesh_cam.xyzbin"), buf.data(), nb)) { LOGE << "unable to save mesh data"; return -1; }
+            }
+        }
+        LOG_SCOPE("wass_stereo");
+        env.timer.stop();
+        std::cout << "[P|100|100]" << std::endl;
+        show_time_stats(env.timer);
+        LOGI << "All done.";
+    } catch (std::runtime_error& e) {
+        LOGE << e.what();
+        return -1;
+    }
+    wsg_destroy(h);
+    return 0;
+}
