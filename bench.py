@@ -181,6 +181,7 @@ def run_ours(args, rank, world):
     img1, img2 = make_frame(rank)            # frame index = rank (frames shard one per GPU)
     H, Wp = img1.shape
     h = capi.Handle(local)
+    h.sgbm_set_impl(args.agg_impl)
     # a dedicated (non-default) torch stream: the library launches on it, torch events time it
     stream = torch.cuda.Stream()
     torch.cuda.set_stream(stream)
@@ -249,7 +250,14 @@ def run_ours(args, rank, world):
         peak, peak_src = measured_peak_gbs()
         alg_bytes = 4.0 * V                       # aggregation sweeps alone = 4*V per frame
         achieved = alg_bytes / (agg_ms_per_frame * 1e-3) / 1e9
-        phys_bytes = (2 + 3 * 7) * V              # this build: 8 single-direction launches (first 2V, others 3V)
+        impl = stats["agg_impl"]
+        wta_ms = prof["wta"][0] / args.steps
+        if impl == 0:      # 8 single-direction launches (first 2V, others 3V); separate WTA reads V
+            phys_bytes, kname = (2 + 3 * 7) * V, "aggregate_kernel (8 launches/frame)"
+        elif impl == 1:    # sweep 1: read C, write S; sweep 2: read C, read S, write S; separate WTA reads V
+            phys_bytes, kname = 5 * V, "sweep_kernel (2 launches/frame), S written, separate WTA"
+        else:              # sweep 1: read C, write S; sweep 2: read C, read S, WTA inside
+            phys_bytes, kname = 4 * V, "sweep_kernel (2 launches/frame), WTA fused into the second"
         line = {
             "metric": "Mdisparities/s", "value": value, "unit": "Mdisp/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -258,7 +266,7 @@ def run_ours(args, rank, world):
                        "l2": "inputs larger than L2 (C and S volumes %.2f GB each)" % (V / 1e9),
                        "parallelism": "frame-per-GPU x%d" % world, "device_vs_e2e_bit_exact": same,
                        "max_cost": stats["max_cost"], "out_of_domain": stats["out_of_domain"]},
-            "roofline": {"bound": "hbm", "kernel": "aggregate_kernel (8 launches/frame)", "achieved": achieved, "peak": peak,
+            "roofline": {"bound": "hbm", "kernel": kname, "agg_impl": impl, "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                          "algorithmic_bytes_per_frame": alg_bytes, "ms_per_frame": agg_ms_per_frame,
                          "launches_per_frame": agg_launches / args.steps,
@@ -285,6 +293,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--agg-impl", type=int, default=2, choices=[0, 1, 2],
+                    help="0 per-direction launches, 1 fused sweeps, 2 fused sweeps + fused WTA (default)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))

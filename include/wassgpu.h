@@ -80,6 +80,7 @@ typedef struct wsg_sgbm_stats {
     int kernel_launches;     /* CUDA kernels launched by the call */
     int width1;              /* W1: matched columns */
     int d_padded;            /* disparity slots per pixel in the HBM volumes */
+    int agg_impl;            /* WSG_AGG_* actually used by the call */
     long long volume_bytes;  /* bytes of one int16 volume (C or S) */
 } wsg_sgbm_stats;
 int wsg_sgbm_get_stats(wsg_handle* h, wsg_sgbm_stats* out);
@@ -87,6 +88,17 @@ int wsg_sgbm_get_stats(wsg_handle* h, wsg_sgbm_stats* out);
 /* Test hook: copies the cost volume C and the aggregated volume S of the last compute to host,
  * in logical layout [rows][W1][numDisparities] int16.  Either pointer may be NULL. */
 int wsg_sgbm_debug_volumes(wsg_handle* h, int16_t* C_host, int16_t* S_host);
+
+/* Which device implementation of the path aggregation (A.4) + winner-take-all (A.5) the next computes use.
+ * All three produce identical results; the choice only moves HBM traffic:
+ *   WSG_AGG_PER_DIRECTION  one launch per path direction (8 or 5), separate WTA kernel          (23V moved)
+ *   WSG_AGG_SWEEPS         fused 4-direction wavefront sweeps, S written out, separate WTA      ( 6V moved)
+ *   WSG_AGG_SWEEPS_WTA     fused sweeps, WTA inside the last sweep, S never written (default)   ( 4V moved)
+ * The fused forms need numDisparities <= 512; above that the per-direction form is used regardless. */
+#define WSG_AGG_PER_DIRECTION 0
+#define WSG_AGG_SWEEPS 1
+#define WSG_AGG_SWEEPS_WTA 2
+int wsg_sgbm_set_impl(wsg_handle* h, int impl);
 
 /* ---- dense stereo stage as a whole ------------------------------------------------------------ */
 /* Replaces sgbm_dense_stereo(env), wass_stereo.cpp:764-1020, between the two rectified crops and the

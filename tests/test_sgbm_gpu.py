@@ -21,24 +21,41 @@ def _supported(p):
     return p["speckleWindowSize"] <= 0
 
 
+IMPLS = [0, 1, 2]   # capi.AGG_PER_DIRECTION, AGG_SWEEPS, AGG_SWEEPS_WTA: three device decompositions, one result
+
+
+@pytest.fixture(params=IMPLS, ids=["per_direction", "sweeps", "sweeps_wta"])
+def impl(request, handle):
+    handle.sgbm_set_impl(request.param)
+    yield request.param
+    handle.sgbm_set_impl(2)
+
+
 @pytest.mark.parametrize("idx", range(len(CASES)))
-def test_gpu_matches_cv2_golden(handle, idx):
+def test_gpu_matches_cv2_golden(handle, impl, idx):
     img1, img2, p, disp = CASES[idx]
     if not _supported(p):
         pytest.skip("speckle filter not implemented on GPU yet")
     out = handle.sgbm_compute(img1, img2, p)
     nbad = int((out != disp).sum())
     assert nbad == 0, "%d / %d pixels differ from cv2" % (nbad, disp.size)
+    want = impl if p["numDisparities"] <= 512 else 0
+    assert handle.sgbm_stats()["agg_impl"] == want
 
 
 @pytest.mark.parametrize("idx", [0, 3, 9, 12])
-def test_gpu_volumes_match_oracle(handle, idx):
+@pytest.mark.parametrize("which", [0, 1], ids=["per_direction", "sweeps"])
+def test_gpu_volumes_match_oracle(handle, which, idx):
     from oracle import sgbm
     img1, img2, p, _ = CASES[idx]
     ref = sgbm.compute(img1, img2, p, want_volumes=True)
-    handle.sgbm_compute(img1, img2, p)
-    H, W1, D = ref["C"].shape
-    C, S = handle.sgbm_debug_volumes(H, W1, D)
+    handle.sgbm_set_impl(which)
+    try:
+        handle.sgbm_compute(img1, img2, p)
+        H, W1, D = ref["C"].shape
+        C, S = handle.sgbm_debug_volumes(H, W1, D)
+    finally:
+        handle.sgbm_set_impl(2)
     assert np.array_equal(C, ref["C"]), "cost volume differs"
     assert np.array_equal(S, ref["S"]), "aggregated volume differs"
     st = handle.sgbm_stats()
@@ -48,7 +65,7 @@ def test_gpu_volumes_match_oracle(handle, idx):
 
 @pytest.mark.parametrize("W,H,D,mode", [(640, 480, 64, 0), (640, 480, 64, 1), (500, 120, 256, 1),
                                         (300, 64, 512, 1), (260, 48, 640, 0), (333, 77, 80, 1)])
-def test_gpu_matches_oracle_wass_defaults(handle, W, H, D, mode):
+def test_gpu_matches_oracle_wass_defaults(handle, impl, W, H, D, mode):
     from oracle import sgbm
     from wass_b200 import synth
     r, l, _ = synth.make_pair(W, H, D, seed=W + D)
@@ -58,6 +75,35 @@ def test_gpu_matches_oracle_wass_defaults(handle, W, H, D, mode):
     out = handle.sgbm_compute(i1, i2, p)
     assert ref["maxC"] + p["P2"] <= 32767
     assert np.array_equal(out, ref["disp"])
+
+
+def test_fused_wta_does_not_expose_S(handle):
+    """AGG_SWEEPS_WTA consumes S inside the last sweep; asking for it is a state error, not stale data."""
+    from wass_b200 import capi
+    img1, img2, p, _ = CASES[0]
+    handle.sgbm_set_impl(capi.AGG_SWEEPS_WTA)
+    handle.sgbm_compute(img1, img2, p)
+    H, W = img1.shape
+    with pytest.raises(capi.WsgError) as e:
+        handle.sgbm_debug_volumes(H, 8, p["numDisparities"])
+    assert e.value.code == -5
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+def test_sweeps_many_bands_and_reuse(handle, mode):
+    """Tall image (many 8-row bands, H not a multiple of 8), then a different geometry on the same handle:
+    the band hand-off buffer and its epoch tags must survive reuse."""
+    from oracle import sgbm
+    from wass_b200 import capi, synth
+    handle.sgbm_set_impl(capi.AGG_SWEEPS_WTA)
+    for (W, H, D) in [(96, 331, 64), (96, 331, 64), (200, 75, 160), (96, 331, 64)]:
+        r, l, _ = synth.make_pair(W, H, D, seed=H + D)
+        i1, i2 = synth.pad_for_sgbm(r, l, D)
+        p = sgbm.wass_params(D, mode=mode)
+        ref = sgbm.compute(i1, i2, p)
+        for _ in range(2):
+            out = handle.sgbm_compute(i1, i2, p)
+            assert np.array_equal(out, ref["disp"])
 
 
 def test_too_narrow_image_is_an_error(handle):

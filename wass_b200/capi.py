@@ -32,7 +32,8 @@ class SgbmParams(ctypes.Structure):
 
 class SgbmStats(ctypes.Structure):
     _fields_ = [("max_cost", ctypes.c_int), ("out_of_domain", ctypes.c_int), ("kernel_launches", ctypes.c_int),
-                ("width1", ctypes.c_int), ("d_padded", ctypes.c_int), ("volume_bytes", ctypes.c_longlong)]
+                ("width1", ctypes.c_int), ("d_padded", ctypes.c_int), ("agg_impl", ctypes.c_int),
+                ("volume_bytes", ctypes.c_longlong)]
 
 
 class DenseParams(ctypes.Structure):
@@ -81,6 +82,8 @@ def make_calib(c, left_shape, right_shape, rect_shape):
     return k
 
 
+AGG_PER_DIRECTION, AGG_SWEEPS, AGG_SWEEPS_WTA = 0, 1, 2
+
 _lib = None
 
 
@@ -106,6 +109,7 @@ def load():
     lib.wsg_sgbm_compute_device.argtypes = [vp, vp, vp, ci, ci, sz, ctypes.POINTER(SgbmParams), vp]
     lib.wsg_sgbm_get_stats.argtypes = [vp, ctypes.POINTER(SgbmStats)]
     lib.wsg_sgbm_debug_volumes.argtypes = [vp, vp, vp]
+    lib.wsg_sgbm_set_impl.argtypes = [vp, ci]
     lib.wsg_profile_enable.argtypes = [vp, ci]
     lib.wsg_profile_reset.argtypes = [vp]
     lib.wsg_profile_get.argtypes = [vp, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ci), ci]
@@ -273,11 +277,15 @@ class Handle:
         self._ck(self.lib.wsg_sgbm_get_stats(self.h, ctypes.byref(s)))
         return {f[0]: getattr(s, f[0]) for f in SgbmStats._fields_}
 
-    def sgbm_debug_volumes(self, rows, w1, D):
+    def sgbm_debug_volumes(self, rows, w1, D, want_S=True):
         C = np.empty((rows, w1, D), np.int16)
-        S = np.empty((rows, w1, D), np.int16)
-        self._ck(self.lib.wsg_sgbm_debug_volumes(self.h, C.ctypes.data, S.ctypes.data))
+        S = np.empty((rows, w1, D), np.int16) if want_S else None
+        self._ck(self.lib.wsg_sgbm_debug_volumes(self.h, C.ctypes.data, S.ctypes.data if want_S else None))
         return C, S
+
+    def sgbm_set_impl(self, impl):
+        """AGG_PER_DIRECTION | AGG_SWEEPS | AGG_SWEEPS_WTA (default): same results, different HBM traffic."""
+        self._ck(self.lib.wsg_sgbm_set_impl(self.h, int(impl)))
 
     # ---- dense stage ----
     def dense_stereo(self, left_crop, right_crop, params, want_disp16=False):

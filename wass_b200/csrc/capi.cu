@@ -17,6 +17,7 @@ int wsg_create(int device, wsg_handle** out)
     h->device = device;
     if (cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking) != cudaSuccess) { delete h; return WSG_ERR_CUDA; }
     h->stream = h->own_stream;
+    if (const char* e = getenv("WSG_AGG_IMPL")) h->agg_impl = std::min(std::max(atoi(e), 0), 2);
     *out = h;
     return WSG_OK;
 }
@@ -27,7 +28,8 @@ void wsg_destroy(wsg_handle* h)
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
     drain_profile(h);
-    for (DevBuf* b : {&h->pre1, &h->pre2, &h->C, &h->S, &h->raw, &h->img1, &h->img2, &h->disp, &h->scalars, &h->crop_l, &h->crop_r,
+    for (DevBuf* b : {&h->pre1, &h->pre2, &h->C, &h->S, &h->raw, &h->img1, &h->img2, &h->disp, &h->scalars, &h->bnd, &h->keys,
+                      &h->d1, &h->crop_l, &h->crop_r,
                       &h->fa, &h->fb, &h->dispfull, &h->im_left, &h->im_right, &h->mask_l, &h->mask_r, &h->m_valid, &h->m_X, &h->m_Y,
                       &h->m_Z, &h->m_color, &h->m_labels, &h->m_scratch, &h->m_small, &h->m_out})
         if (b->p) cudaFree(b->p);
@@ -80,15 +82,28 @@ int wsg_make_plan(wsg_handle* h, int rows, int cols, const wsg_sgbm_params* p, S
     // cv2 raises for images this narrow (stereosgbm.cpp:511); mirror it as an error code
     if (cols - (pl.minD + pl.D) <= pl.SW2 || pl.W1 <= 0) { h->err = "image too narrow for minDisparity+numDisparities and blockSize"; return WSG_ERR_TOO_SMALL; }
     const int NV = pl.D / 8;
-    if (NV <= 8) { pl.NL = 8; pl.K = 1; }
+    if (h->agg_impl != WSG_AGG_PER_DIRECTION && NV <= 64) { pl.NL = 32; pl.K = (NV + 31) / 32; }   // one warp per pixel
+    else if (NV <= 8) { pl.NL = 8; pl.K = 1; }
     else if (NV <= 16) { pl.NL = 16; pl.K = 1; }
     else { pl.NL = 32; pl.K = (NV + 31) / 32; }
     // tuning override (same results, different lane mapping): WSG_AGG_LANES=8|16 for D=256
     if (const char* e = getenv("WSG_AGG_LANES")) {
         const int nl = atoi(e);
-        if (NV == 32 && (nl == 8 || nl == 16)) { pl.NL = nl; pl.K = 32 / nl; }
+        if (h->agg_impl == WSG_AGG_PER_DIRECTION && NV == 32 && (nl == 8 || nl == 16)) { pl.NL = nl; pl.K = 32 / nl; }
     }
     pl.Dp = pl.NL * pl.K * 8;
+    return WSG_OK;
+}
+
+// The fused sweeps hand states between CTAs with bounded waits; an overrun (never seen on a healthy device) raises a
+// flag instead of hanging.  Synchronises the stream.
+int wsg_check_sweep(wsg_handle* h)
+{
+    if (!h->scalars.p || h->stats.agg_impl == WSG_AGG_PER_DIRECTION) return WSG_OK;
+    int flag = 0;
+    CK(h, cudaMemcpyAsync(&flag, (int*)h->scalars.p + 1, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CK(h, cudaStreamSynchronize(h->stream));
+    if (flag) { h->err = "fused aggregation sweep: hand-off wait overran (code " + std::to_string(flag) + ")"; return WSG_ERR_CUDA; }
     return WSG_OK;
 }
 
@@ -116,18 +131,65 @@ int wsg_run_sgbm(wsg_handle* h, const uint8_t* d_img1, const uint8_t* d_img2, si
         StageTimer t(h, WSG_STAGE_COST, 1);
         launch_cost((const uint2*)h->pre1.p, (const uint2*)h->pre2.p, (int16_t*)h->C.p, (int*)h->scalars.p, pl, h->stream, &launches);
     }
-    {
-        const int ndirs = pl.mode == WSG_MODE_HH ? 8 : 5;
-        StageTimer t(h, WSG_STAGE_AGGREGATE, ndirs);
-        for (int r = 0; r < ndirs; ++r)
-            launch_aggregate_dir((const int16_t*)h->C.p, (int16_t*)h->S.p, r, r == 0, pl, h->stream);
-        launches += ndirs;
+    const int impl = (h->agg_impl != WSG_AGG_PER_DIRECTION && sweep_supported(pl)) ? h->agg_impl : WSG_AGG_PER_DIRECTION;
+    if (impl == WSG_AGG_PER_DIRECTION) {
+        {
+            const int ndirs = pl.mode == WSG_MODE_HH ? 8 : 5;
+            StageTimer t(h, WSG_STAGE_AGGREGATE, ndirs);
+            for (int r = 0; r < ndirs; ++r)
+                launch_aggregate_dir((const int16_t*)h->C.p, (int16_t*)h->S.p, r, r == 0, pl, h->stream);
+            launches += ndirs;
+        }
+        {
+            StageTimer t(h, WSG_STAGE_WTA, 1);
+            launch_wta((const int16_t*)h->S.p, (int16_t*)h->raw.p, pl, h->stream);
+            launches += 1;
+        }
+    } else {
+        // fused wavefront sweeps (sweep_kernels.cu).  scalars: [0] max C, [1] error flag, [2..] band tickets
+        const size_t bbytes = sweep_boundary_bytes(pl);
+        const bool grown = bbytes > h->bnd.cap;
+        if ((rc = ensure(h, h->bnd, bbytes))) return rc;
+        if (grown || h->bnd_H != pl.H || h->bnd_W1 != pl.W1 || h->bnd_K != pl.K) {
+            // epoch tags only tell "this sweep" from "the previous one" for slots that are rewritten every sweep
+            CK(h, cudaMemsetAsync(h->bnd.p, 0, h->bnd.cap, h->stream));
+            h->bnd_H = pl.H; h->bnd_W1 = pl.W1; h->bnd_K = pl.K;
+        }
+        const bool fused_wta = impl == WSG_AGG_SWEEPS_WTA;
+        if (fused_wta) {
+            if ((rc = ensure(h, h->keys, npix * sizeof(unsigned long long)))) return rc;
+            if ((rc = ensure(h, h->d1, npix * sizeof(int16_t)))) return rc;
+        }
+        SweepScratch sc;
+        sc.boundary = h->bnd.p;
+        sc.err = (int*)h->scalars.p + 1;
+        sc.keys = (unsigned long long*)h->keys.p;
+        sc.d1 = (int16_t*)h->d1.p;
+        int* tickets = (int*)h->scalars.p + 2;
+        auto next_epoch = [&]() { h->sweep_epoch = h->sweep_epoch % 3 + 1; return h->sweep_epoch; };
+        const int last_mode = fused_wta ? 2 : 1;
+        {
+            StageTimer t(h, WSG_STAGE_AGGREGATE, 2 + (fused_wta ? 1 : 0));
+            if (fused_wta) { launch_wta_reset(sc, pl, h->stream); launches += 1; }
+            sc.ticket = tickets + 0; sc.epoch = next_epoch();
+            launch_sweep((const int16_t*)h->C.p, (int16_t*)h->S.p, 0, 0, 4, pl, sc, h->stream);
+            sc.ticket = tickets + 1;
+            if (pl.mode == WSG_MODE_HH) {
+                sc.epoch = next_epoch();
+                launch_sweep((const int16_t*)h->C.p, (int16_t*)h->S.p, 1, last_mode, 4, pl, sc, h->stream);
+            } else {
+                launch_sweep((const int16_t*)h->C.p, (int16_t*)h->S.p, 1, last_mode, 1, pl, sc, h->stream);
+            }
+            launches += 2;
+        }
+        {
+            StageTimer t(h, WSG_STAGE_WTA, 1);
+            if (fused_wta) launch_lrcheck(sc, (int16_t*)h->raw.p, pl, h->stream);
+            else launch_wta((const int16_t*)h->S.p, (int16_t*)h->raw.p, pl, h->stream);
+            launches += 1;
+        }
     }
-    {
-        StageTimer t(h, WSG_STAGE_WTA, 1);
-        launch_wta((const int16_t*)h->S.p, (int16_t*)h->raw.p, pl, h->stream);
-        launches += 1;
-    }
+    h->stats.agg_impl = impl;
     {
         StageTimer t(h, WSG_STAGE_MEDIAN, 1);
         launch_median3((const int16_t*)h->raw.p, d_disp, pl.H, pl.W, h->stream);
@@ -176,7 +238,7 @@ int wsg_sgbm_compute(wsg_handle* h, const uint8_t* img1, const uint8_t* img2, in
     if (rc) return rc;
     CK(h, cudaMemcpyAsync(disp16, h->disp.p, npix * sizeof(int16_t), cudaMemcpyDeviceToHost, h->stream));
     CK(h, cudaStreamSynchronize(h->stream));
-    return WSG_OK;
+    return wsg_check_sweep(h);
 }
 
 int wsg_sgbm_get_stats(wsg_handle* h, wsg_sgbm_stats* out)
@@ -189,7 +251,7 @@ int wsg_sgbm_get_stats(wsg_handle* h, wsg_sgbm_stats* out)
     h->stats.max_cost = maxc;
     h->stats.out_of_domain = (maxc + h->plan.P2 > 32767) ? 1 : 0;
     *out = h->stats;
-    return WSG_OK;
+    return wsg_check_sweep(h);
 }
 
 int wsg_sgbm_debug_volumes(wsg_handle* h, int16_t* C_host, int16_t* S_host)
@@ -197,6 +259,10 @@ int wsg_sgbm_debug_volumes(wsg_handle* h, int16_t* C_host, int16_t* S_host)
     if (!h) return WSG_ERR_INVALID_ARG;
     if (!h->have_plan) { h->err = "no compute yet"; return WSG_ERR_STATE; }
     const SgbmPlan& pl = h->plan;
+    if (S_host && h->stats.agg_impl == WSG_AGG_SWEEPS_WTA) {
+        h->err = "S is never materialised by WSG_AGG_SWEEPS_WTA; select WSG_AGG_SWEEPS or WSG_AGG_PER_DIRECTION first";
+        return WSG_ERR_STATE;
+    }
     const size_t npx = (size_t)pl.H * pl.W1;
     std::vector<int16_t> tmp(npx * pl.Dp);
     for (int which = 0; which < 2; ++which) {
@@ -208,6 +274,14 @@ int wsg_sgbm_debug_volumes(wsg_handle* h, int16_t* C_host, int16_t* S_host)
             for (int j = 0; j < pl.D / 8; ++j)
                 memcpy(dst + px * pl.D + (size_t)j * 8, tmp.data() + px * pl.Dp + (size_t)vec_slot(j, pl.NL, pl.K) * 8, 16);
     }
+    return WSG_OK;
+}
+
+int wsg_sgbm_set_impl(wsg_handle* h, int impl)
+{
+    if (!h) return WSG_ERR_INVALID_ARG;
+    if (impl < WSG_AGG_PER_DIRECTION || impl > WSG_AGG_SWEEPS_WTA) { h->err = "unknown aggregation implementation"; return WSG_ERR_INVALID_ARG; }
+    h->agg_impl = impl;
     return WSG_OK;
 }
 

@@ -148,7 +148,7 @@ int wsg_dense_stereo(wsg_handle* h, const uint8_t* left_crop, const uint8_t* rig
         CK(h, cudaMemcpy2DAsync(disp16_roi, (size_t)cols * 2, (const int16_t*)h->disp.p + N, (size_t)wp * 2, (size_t)cols * 2, rows,
                                 cudaMemcpyDeviceToHost, h->stream));
     CK(h, cudaStreamSynchronize(h->stream));
-    return WSG_OK;
+    return wsg_check_sweep(h);
 }
 
 int wsg_disparity_postprocess(wsg_handle* h, const int16_t* disp16_roi, int rows, int cols, int minDisparity, int numDisparities,

@@ -25,6 +25,10 @@ struct wsg_handle {
     std::string err;
     // SGBM arena
     DevBuf pre1, pre2, C, S, raw, img1, img2, disp, scalars;
+    DevBuf bnd, keys, d1;               // fused sweeps: band hand-off buffer, right-view keys, left-view map
+    int agg_impl = WSG_AGG_SWEEPS_WTA;
+    int sweep_epoch = 0;                // 1..3 after the first sweep
+    int bnd_H = 0, bnd_W1 = 0, bnd_K = 0;   // geometry the hand-off buffer was last used with
     SgbmPlan plan{};
     bool have_plan = false;
     wsg_sgbm_stats stats{};
@@ -100,4 +104,5 @@ inline void drain_profile(wsg_handle* h)
 
 // internal helpers implemented in capi.cu (C linkage only because they live inside its extern "C" block)
 extern "C" int wsg_make_plan(wsg_handle* h, int rows, int cols, const wsg_sgbm_params* p, SgbmPlan& pl);
+extern "C" int wsg_check_sweep(wsg_handle* h);
 extern "C" int wsg_run_sgbm(wsg_handle* h, const uint8_t* d_img1, const uint8_t* d_img2, size_t stride, int16_t* d_disp);

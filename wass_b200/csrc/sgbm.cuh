@@ -34,4 +34,23 @@ void launch_wta(const int16_t* S, int16_t* raw, const SgbmPlan& p, cudaStream_t 
 void launch_median3(const int16_t* src, int16_t* dst, int rows, int cols, cudaStream_t st);
 int cost_smem_bytes(const SgbmPlan& p);
 
+// fused wavefront sweeps (sweep_kernels.cu)
+struct SweepScratch {
+    void* boundary;             // band-to-band state hand-off, sweep_boundary_bytes()
+    int* ticket;                // zeroed band counter of THIS launch
+    int* err;                   // raised if a bounded wait overran
+    int epoch;                  // 1..3, changes with every 4-direction sweep that uses `boundary`
+    unsigned long long* keys;   // [H][W] right-view map as packed keys (fused WTA)
+    int16_t* d1;                // [H][W] left-view disparity before the LR check (fused WTA)
+};
+bool sweep_supported(const SgbmPlan& p);
+size_t sweep_boundary_bytes(const SgbmPlan& p);
+// flip 0: directions r0..r3 (top->bottom); flip 1: r4..r7 (bottom->top).  mode 0: S = sum L (write only);
+// 1: S += sum L;  2: S += sum L, then winner-take-all into sc.keys / sc.d1 (S is not written).
+// ndir 4: all four directions of the sweep;  1: the horizontal one only (fifth path of MODE_SGBM).
+void launch_sweep(const int16_t* C, int16_t* S, int flip, int mode, int ndir, const SgbmPlan& p, const SweepScratch& sc,
+                  cudaStream_t st);
+void launch_wta_reset(const SweepScratch& sc, const SgbmPlan& p, cudaStream_t st);
+void launch_lrcheck(const SweepScratch& sc, int16_t* raw, const SgbmPlan& p, cudaStream_t st);
+
 }  // namespace wsg

@@ -1,0 +1,75 @@
+// Device helpers shared by the per-direction aggregation kernels (sgbm_kernels.cu) and the fused
+// wavefront sweeps (sweep_kernels.cu): streaming 16-byte accesses and one step of the A.4 recurrence.
+#pragma once
+#include "sgbm.cuh"
+
+namespace wsg {
+
+static constexpr unsigned FULL = 0xffffffffu;
+static constexpr unsigned SAT2 = 0x7FFF7FFFu;
+
+__device__ __forceinline__ uint4 ldg_stream(const uint4* p)
+{
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ uint4 ldg_rw(const uint4* p)
+{
+    uint4 r;
+    asm volatile("ld.global.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void stg_stream(uint4* p, const uint4& v)
+{
+    asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
+                 : "memory");
+}
+
+template <int NL>
+__device__ __forceinline__ unsigned group_min_u32(unsigned v)
+{
+    if constexpr (NL == 32) {
+        return __reduce_min_sync(FULL, v);
+    } else {
+#pragma unroll
+        for (int o = NL / 2; o > 0; o >>= 1) v = min(v, __shfl_xor_sync(FULL, v, o, NL));
+        return v;
+    }
+}
+
+// One step of the recurrence for one direction.  R: normalised state of the predecessor (in/out),
+// Cw: cost of this pixel, v: L of this pixel (out).  NR packed registers, 2 disparities each.
+template <int NL, int NR, bool HASPAD>
+__device__ __forceinline__ void agg_step(unsigned (&R)[NR], const unsigned (&Cw)[NR], unsigned (&v)[NR], int l,
+                                         unsigned P1p, unsigned P2mP1p, const unsigned* padm)
+{
+    unsigned up = __shfl_up_sync(FULL, R[NR - 1], 1, NL);
+    unsigned dn = __shfl_down_sync(FULL, R[0], 1, NL);
+    if (l == 0) up = SAT2;
+    if (l == NL - 1) dn = SAT2;
+    unsigned q[NR + 1];
+    q[0] = __byte_perm(up, R[0], 0x5432);
+#pragma unroll
+    for (int j = 1; j < NR; ++j) q[j] = __byte_perm(R[j - 1], R[j], 0x5432);
+    q[NR] = __byte_perm(R[NR - 1], dn, 0x5432);
+#pragma unroll
+    for (int j = 0; j < NR; ++j) {
+        unsigned t = __vimin3_s16x2(q[j], q[j + 1], P2mP1p);
+        t = __viaddmin_s16x2(t, P1p, R[j]);
+        v[j] = __viaddmin_u16x2(t, Cw[j], SAT2);
+        if (HASPAD) v[j] |= padm[j / 4];
+    }
+    unsigned m = v[0];
+#pragma unroll
+    for (int j = 1; j < NR; ++j) m = __vmins2(m, v[j]);
+    unsigned mm = min(m & 0xFFFFu, m >> 16);
+    mm = group_min_u32<NL>(mm);
+    const unsigned mpk = mm * 0x10001u;
+#pragma unroll
+    for (int j = 0; j < NR; ++j) R[j] = v[j] - mpk;  // both halves >= mm: no borrow between them
+}
+
+}  // namespace wsg

@@ -1,0 +1,458 @@
+// Fused path aggregation of cv::StereoSGBM (call site
+// src/wass_stereo/wass_stereo.cpp:837): one launch per SWEEP instead of one per direction.
+//
+// A sweep runs the four directions whose predecessors are (x-1,y) (x-1,y-1) (x,y-1) (x+1,y-1)
+// [sweep 1: r0..r3] -- or, rotated by 180 degrees, (x+1,y) (x+1,y+1) (x,y+1) (x-1,y+1)
+// [sweep 2: r4,r7,r6,r5] -- as a skew-2 wavefront: one warp walks one image row, row y+1 trails
+// row y by two columns, so every predecessor state already exists when a pixel is reached.  The
+// cost vector C(p,.) is read from HBM exactly once per sweep, the four L_r(p,.) are summed in
+// registers, and S is written once (sweep 1) or consumed on the spot by the winner-take-all
+// stage (sweep 2): 4V of HBM traffic for MODE_HH instead of the 23V of eight separate launches.
+//
+//   CTA      = R consecutive rows (one warp each) + one helper warp
+//   row->row = normalised states N_r = L_r - min L_r handed down through a shared-memory ring
+//              (NS columns deep, progress counters instead of CTA barriers: warps drift freely)
+//   CTA->CTA = the last row of a band publishes its states to a global boundary buffer; every
+//              32-bit word carries a 2-bit epoch tag in the two sign bits a state never uses, so
+//              the consumer validates data word by word without fences or flags; the helper warp
+//              of the next band polls them (L2) into that CTA's ring 0
+//   order    = bands are handed out by an atomic ticket, so a band only ever waits for bands that
+//              are already running: no co-residency assumption, no deadlock
+//
+// All spin loops are bounded: on overrun the kernel raises an error flag and runs to completion.
+#include "sgbm_dev.cuh"
+#include <algorithm>
+
+namespace wsg {
+
+static constexpr int SW_R = 8;             // rows (compute warps) per CTA
+static constexpr int SW_THREADS = (SW_R + 1) * 32;
+static constexpr int SW_PF = 4;            // register prefetch depth of the C (and S) stream, in pixels
+static constexpr int SW_HD = 2;            // boundary columns the helper keeps in flight
+static constexpr unsigned TAGBITS = 0x80008000u;
+static constexpr int SPIN_LIMIT = 1 << 26;
+
+template <int K> struct SweepCfg {
+    static constexpr int NS = K == 1 ? 8 : 6;                 // ring depth in columns
+    static constexpr int SLOT_V = 3 * K * 32;                 // uint4 per ring slot: [dir][k][lane]
+    static constexpr int RING_V = NS * SLOT_V;
+    static constexpr int SMEM = SW_R * RING_V * 16 + SW_R * K * 32 * 16;   // rings + per-warp WTA scratch
+};
+
+struct SweepArgs {
+    int H, W1, W, D;
+    int Dp8;                 // 16-byte vectors per pixel (= 32*K)
+    int flip;                // 0: top->bottom, left->right;  1: rotated by 180 degrees
+    unsigned P1p, P2mP1p;
+    unsigned tag;            // epoch tag of this launch (bits 15 and 31)
+    uint4* bnd;              // [nbands-1][W1][3][K][32]
+    int* ticket;
+    int* err;
+    // winner-take-all (MODE 2)
+    unsigned long long* keys;   // [H][W]  (minS, W1-1-x, d) of the best match that lands on x2 (A.5)
+    int16_t* d1;                // [H][W]  left-view disparity before the LR check
+    int minD, minX1, uniq, INVALID;
+};
+
+__device__ __forceinline__ uint4 ld_volatile(const uint4* p)
+{
+    uint4 r;
+    asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p) : "memory");
+    return r;
+}
+__device__ __forceinline__ void st_volatile(uint4* p, const uint4& v)
+{
+    asm volatile("st.volatile.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
+                 : "memory");
+}
+
+// Wait until *flag >= need (shared-memory progress counter of a neighbouring warp).  Bounded: on overrun (or when
+// any other waiter has already given up) raise the error flag and stop waiting for good.
+__device__ __forceinline__ void wait_prog(volatile int* flag, int need, int& seen, int* err)
+{
+    if (seen < need) {
+        int spins = 0;
+        while ((seen = *flag) < need) {
+            if ((++spins & 1023) == 0 && (spins > SPIN_LIMIT || *reinterpret_cast<volatile int*>(err) != 0)) {
+                *err = 1;
+                seen = 0x7fffffff;
+                break;
+            }
+        }
+    }
+    __threadfence_block();   // orders the data reads after the counter read (and is a compiler barrier)
+}
+
+// A.5 for one pixel held by one warp: s = final S, 8*K consecutive disparities per lane.
+template <int K>
+__device__ __forceinline__ void wta_pixel(const unsigned (&s)[4 * K], int l, int xh, int y, const SweepArgs& a,
+                                          int16_t* scratch)
+{
+    constexpr int NV8 = 8 * K;
+    const int dlane = l * NV8;
+    unsigned key[NV8];
+#pragma unroll
+    for (int e = 0; e < 4 * K; ++e) {
+        key[2 * e] = (s[e] << 16) + (unsigned)(dlane + 2 * e);
+        key[2 * e + 1] = (s[e] & 0xFFFF0000u) + (unsigned)(dlane + 2 * e + 1);
+    }
+    unsigned kmin = 0xFFFFFFFFu;
+#pragma unroll
+    for (int e = 0; e < NV8; ++e)
+        if (dlane + e < a.D) kmin = min(kmin, key[e]);
+    kmin = __reduce_min_sync(FULL, kmin);
+    const int minS = (int)(kmin >> 16), best = (int)(kmin & 0xFFFFu);
+    const int udiv = 100 - a.uniq;
+    int bad = 0;
+    if (udiv > 0) {
+        // S(d)*(100-uniq) < minS*100  <=>  S(d) <= Tm,  Tm = floor((minS*100-1)/(100-uniq))
+        const int n = minS * 100 - 1;                    // < 3.3e6: exact in float
+        int Tm = n < 0 ? -1 : (int)((float)n * (1.0f / (float)udiv));
+        if (n >= 0) { if ((Tm + 1) * udiv <= n) ++Tm; else if (Tm * udiv > n) --Tm; }
+        const unsigned Tkey = Tm < 0 ? 0u : (((unsigned)Tm << 16) | 0xFFFFu);
+        const int rel = best - dlane;
+#pragma unroll
+        for (int e = 0; e < NV8; ++e) {
+            const bool near = (unsigned)(e - rel + 1) <= 2u;
+            if (Tm >= 0 && key[e] <= Tkey && !near && dlane + e < a.D) bad = 1;
+        }
+    } else {
+#pragma unroll
+        for (int e = 0; e < NV8; ++e) {
+            const int sv = (int)(key[e] >> 16), d = dlane + e;
+            if (d < a.D && sv * udiv < minS * 100 && abs(best - d) > 1) bad = 1;
+        }
+    }
+    if (__any_sync(FULL, bad)) return;
+    // neighbours of the winner for the parabola: stage this pixel's S in shared memory
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < K; ++k)
+        reinterpret_cast<uint4*>(scratch)[l * K + k] = make_uint4(s[4 * k], s[4 * k + 1], s[4 * k + 2], s[4 * k + 3]);
+    __syncwarp();
+    if (l == 0) {
+        const int x = xh + a.minX1;
+        const int x2 = x - best - a.minD;
+        const unsigned long long k64 = ((unsigned long long)minS << 40) |
+                                       ((unsigned long long)(a.W1 - 1 - xh) << 16) | (unsigned long long)best;
+        atomicMin(a.keys + (size_t)y * a.W + x2, k64);
+        int dd = best * 16;
+        if (best > 0 && best < a.D - 1) {
+            const int sm = scratch[best - 1], sp = scratch[best + 1];
+            const int den = max(sm + sp - 2 * minS, 1);
+            dd += ((sm - sp) * 16 + den) / (2 * den);
+        }
+        a.d1[(size_t)y * a.W + x] = (int16_t)(dd + a.minD * 16);
+    }
+}
+
+// MODE 0: S = sum of this sweep's L (no read);  1: S += sum (read-modify-write);  2: S += sum, then WTA (S not written)
+// NDIR 4: full sweep;  1: horizontal direction only (the fifth path of MODE_SGBM): rows are independent.
+template <int K, int MODE, int NDIR, bool HASPAD>
+__global__ void __launch_bounds__(SW_THREADS, K == 1 ? 2 : 1)
+sweep_kernel(const uint4* __restrict__ C, uint4* __restrict__ S, SweepArgs a)
+{
+    using Cfg = SweepCfg<K>;
+    constexpr int NR = 4 * K;
+    constexpr int NS = Cfg::NS;
+    extern __shared__ __align__(16) uint4 smem[];
+    __shared__ volatile int prog[SW_R + 1];   // prog[0]: helper (row above the band); prog[r+1]: warp r
+    __shared__ int s_band;
+
+    const int tid = threadIdx.x, warp = tid >> 5, l = tid & 31;
+    if (tid == 0) s_band = atomicAdd(a.ticket, 1);
+    if (tid <= SW_R) prog[tid] = 0;
+    __syncthreads();
+    const int band = s_band;
+    const size_t bstride = (size_t)a.W1 * Cfg::SLOT_V;      // uint4 per boundary row
+
+    // ------------------------------------------------------------------ helper warp
+    if (warp == SW_R) {
+        if (NDIR == 1 || band == 0) return;
+        const uint4* src = a.bnd + (size_t)(band - 1) * bstride + l;
+        uint4* ring = smem;                                // ring 0
+        uint4 hb[SW_HD][3 * K];
+        int seen = 0;
+        bool dead = false;
+#pragma unroll
+        for (int u = 0; u < SW_HD; ++u)
+#pragma unroll
+            for (int j = 0; j < 3 * K; ++j) hb[u][j] = ld_volatile(src + (size_t)min(u, a.W1 - 1) * Cfg::SLOT_V + j * 32);
+        for (int base = 0; base < a.W1; base += SW_HD) {
+#pragma unroll
+            for (int u = 0; u < SW_HD; ++u) {
+                const int x = base + u;
+                if (x < a.W1) {
+                    int spins = 0;
+                    while (!dead) {
+                        bool ok = true;
+#pragma unroll
+                        for (int j = 0; j < 3 * K; ++j)
+                            ok = ok && ((hb[u][j].x & TAGBITS) == a.tag) && ((hb[u][j].y & TAGBITS) == a.tag) &&
+                                 ((hb[u][j].z & TAGBITS) == a.tag) && ((hb[u][j].w & TAGBITS) == a.tag);
+                        if (__all_sync(FULL, ok)) break;
+                        if ((++spins & 255) == 0 && (spins > (SPIN_LIMIT >> 4) || *reinterpret_cast<volatile int*>(a.err) != 0)) {
+                            *a.err = 2;
+                            dead = true;
+                            break;
+                        }
+                        __nanosleep(32);
+#pragma unroll
+                        for (int j = 0; j < 3 * K; ++j) hb[u][j] = ld_volatile(src + (size_t)x * Cfg::SLOT_V + j * 32);
+                    }
+                    // ring 0 slot x is free once warp 0 has completed column x-NS+1
+                    wait_prog(&prog[1], x - NS + 2, seen, a.err);
+                    uint4* dst = ring + (x % NS) * Cfg::SLOT_V + l;
+#pragma unroll
+                    for (int j = 0; j < 3 * K; ++j)
+                        dst[j * 32] = make_uint4(hb[u][j].x & ~TAGBITS, hb[u][j].y & ~TAGBITS, hb[u][j].z & ~TAGBITS,
+                                                 hb[u][j].w & ~TAGBITS);
+                    __syncwarp();
+                    __threadfence_block();
+                    if (l == 0) prog[0] = x + 1;
+                    const int xn = x + SW_HD;
+                    if (xn < a.W1) {
+#pragma unroll
+                        for (int j = 0; j < 3 * K; ++j) hb[u][j] = ld_volatile(src + (size_t)xn * Cfg::SLOT_V + j * 32);
+                    }
+                }
+            }
+        }
+        return;
+    }
+
+    // ------------------------------------------------------------------ compute warp = one row
+    const int r = warp;
+    const int yl = band * SW_R + r;                 // logical row (sweep order)
+    if (yl >= a.H) return;
+    const bool top = NDIR == 1 || yl == 0;          // no predecessor row
+    const int out_mode = (NDIR == 1 || yl == a.H - 1) ? 0 : (r < SW_R - 1 ? 1 : 2);
+    const int yp = a.flip ? a.H - 1 - yl : yl;      // physical row
+    const long long dstep = a.flip ? -(long long)a.Dp8 : (long long)a.Dp8;
+    const size_t first = ((size_t)yp * a.W1 + (a.flip ? a.W1 - 1 : 0)) * a.Dp8 + l;
+    const uint4* cpf = C + first;                   // prefetch cursors
+    uint4* spf = S + first;
+    uint4* scur = S + first;                        // compute cursor
+    const uint4* ring_in = smem + (size_t)r * Cfg::RING_V + l;
+    uint4* ring_out = smem + (size_t)(r + 1) * Cfg::RING_V + l;     // only used when out_mode == 1
+    uint4* bnd_out = a.bnd + (size_t)band * bstride + l;            // only used when out_mode == 2
+    int16_t* scratch = reinterpret_cast<int16_t*>(smem + (size_t)SW_R * Cfg::RING_V + (size_t)r * K * 32);
+    volatile int* prog_in = &prog[r];
+    volatile int* prog_me = &prog[r + 1];
+    volatile int* prog_next = &prog[r + 2 <= SW_R ? r + 2 : SW_R];
+    int seen_in = 0, seen_next = 0;
+
+    unsigned padm[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) padm[k] = ((l * K + k) * 8 >= a.D) ? SAT2 : 0u;
+
+    uint4 cb[SW_PF][K], sb[SW_PF][K];
+#pragma unroll
+    for (int u = 0; u < SW_PF; ++u) {
+        if (u < a.W1) {
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                cb[u][k] = ldg_stream(cpf + k * 32);
+                if (MODE != 0) sb[u][k] = ldg_rw(spf + k * 32);
+            }
+        }
+        cpf += dstep; spf += dstep;
+    }
+
+    unsigned Nh[NR];
+#pragma unroll
+    for (int j = 0; j < NR; ++j) Nh[j] = 0;
+
+    for (int base = 0; base < a.W1; base += SW_PF) {
+#pragma unroll
+        for (int u = 0; u < SW_PF; ++u) {
+            const int x = base + u;                // logical column
+            if (x < a.W1) {
+                unsigned Cw[NR], vs[NR], v[NR];
+#pragma unroll
+                for (int k = 0; k < K; ++k) {
+                    Cw[4 * k] = cb[u][k].x; Cw[4 * k + 1] = cb[u][k].y; Cw[4 * k + 2] = cb[u][k].z; Cw[4 * k + 3] = cb[u][k].w;
+                }
+                // ---- horizontal direction: state stays in registers
+                agg_step<32, NR, HASPAD>(Nh, Cw, v, l, a.P1p, a.P2mP1p, padm);
+                if (MODE == 0) {
+#pragma unroll
+                    for (int j = 0; j < NR; ++j) vs[j] = v[j];
+                } else {
+#pragma unroll
+                    for (int k = 0; k < K; ++k) {
+                        vs[4 * k] = __viaddmin_u16x2(sb[u][k].x, v[4 * k], SAT2);
+                        vs[4 * k + 1] = __viaddmin_u16x2(sb[u][k].y, v[4 * k + 1], SAT2);
+                        vs[4 * k + 2] = __viaddmin_u16x2(sb[u][k].z, v[4 * k + 2], SAT2);
+                        vs[4 * k + 3] = __viaddmin_u16x2(sb[u][k].w, v[4 * k + 3], SAT2);
+                    }
+                }
+                if (NDIR == 4) {
+                    // ---- the three directions that come from the row above
+                    unsigned Nd[3][NR];
+                    if (top) {
+#pragma unroll
+                        for (int q = 0; q < 3; ++q)
+#pragma unroll
+                            for (int j = 0; j < NR; ++j) Nd[q][j] = 0;
+                    } else {
+                        wait_prog(prog_in, min(x + 2, a.W1), seen_in, a.err);
+                        const int sl[3] = {(x + NS - 1) % NS, x % NS, (x + 1) % NS};
+                        const bool have[3] = {x > 0, true, x + 1 < a.W1};
+#pragma unroll
+                        for (int q = 0; q < 3; ++q) {
+#pragma unroll
+                            for (int k = 0; k < K; ++k) {
+                                uint4 t = make_uint4(0, 0, 0, 0);
+                                if (have[q]) t = ring_in[sl[q] * Cfg::SLOT_V + (q * K + k) * 32];
+                                Nd[q][4 * k] = t.x; Nd[q][4 * k + 1] = t.y; Nd[q][4 * k + 2] = t.z; Nd[q][4 * k + 3] = t.w;
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int q = 0; q < 3; ++q) {
+                        agg_step<32, NR, HASPAD>(Nd[q], Cw, v, l, a.P1p, a.P2mP1p, padm);
+#pragma unroll
+                        for (int j = 0; j < NR; ++j) vs[j] = __viaddmin_u16x2(vs[j], v[j], SAT2);
+                    }
+                    // ---- hand the new states down
+                    if (out_mode == 1) {
+                        wait_prog(prog_next, x - NS + 2, seen_next, a.err);
+                        uint4* dst = ring_out + (x % NS) * Cfg::SLOT_V;
+#pragma unroll
+                        for (int q = 0; q < 3; ++q)
+#pragma unroll
+                            for (int k = 0; k < K; ++k)
+                                dst[(q * K + k) * 32] = make_uint4(Nd[q][4 * k], Nd[q][4 * k + 1], Nd[q][4 * k + 2], Nd[q][4 * k + 3]);
+                    } else if (out_mode == 2) {
+                        uint4* dst = bnd_out + (size_t)x * Cfg::SLOT_V;
+#pragma unroll
+                        for (int q = 0; q < 3; ++q)
+#pragma unroll
+                            for (int k = 0; k < K; ++k)
+                                st_volatile(dst + (q * K + k) * 32,
+                                            make_uint4(Nd[q][4 * k] | a.tag, Nd[q][4 * k + 1] | a.tag, Nd[q][4 * k + 2] | a.tag,
+                                                       Nd[q][4 * k + 3] | a.tag));
+                    }
+                    __syncwarp();
+                    __threadfence_block();
+                    if (l == 0) *prog_me = x + 1;
+                }
+                // ---- S out, or winner-take-all on the spot
+                if (MODE == 2) {
+                    const int xh = a.flip ? a.W1 - 1 - x : x;
+                    wta_pixel<K>(vs, l, xh, yp, a, scratch);
+                } else {
+#pragma unroll
+                    for (int k = 0; k < K; ++k)
+                        stg_stream(scur + k * 32, make_uint4(vs[4 * k], vs[4 * k + 1], vs[4 * k + 2], vs[4 * k + 3]));
+                }
+                scur += dstep;
+                // ---- refill this prefetch stage
+                if (x + SW_PF < a.W1) {
+#pragma unroll
+                    for (int k = 0; k < K; ++k) {
+                        cb[u][k] = ldg_stream(cpf + k * 32);
+                        if (MODE != 0) sb[u][k] = ldg_rw(spf + k * 32);
+                    }
+                }
+                cpf += dstep; spf += dstep;
+            }
+        }
+    }
+}
+
+template <int K, int MODE, int NDIR, bool HASPAD>
+static void launch_sweep_t(const int16_t* C, int16_t* S, const SweepArgs& a, cudaStream_t st)
+{
+    using Cfg = SweepCfg<K>;
+    const int nbands = (a.H + SW_R - 1) / SW_R;
+    auto kern = sweep_kernel<K, MODE, NDIR, HASPAD>;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
+    cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    kern<<<nbands, SW_THREADS, Cfg::SMEM, st>>>(reinterpret_cast<const uint4*>(C), reinterpret_cast<uint4*>(S), a);
+}
+
+size_t sweep_boundary_bytes(const SgbmPlan& p)
+{
+    const int nbands = (p.H + SW_R - 1) / SW_R;
+    return (size_t)std::max(nbands - 1, 1) * p.W1 * 3 * p.K * 32 * 16;
+}
+
+bool sweep_supported(const SgbmPlan& p) { return p.NL == 32 && (p.K == 1 || p.K == 2); }
+
+// mode: 0 first (write S), 1 accumulate (read+write S), 2 accumulate + winner-take-all.  ndir: 4 or 1.
+void launch_sweep(const int16_t* C, int16_t* S, int flip, int mode, int ndir, const SgbmPlan& p, const SweepScratch& sc,
+                  cudaStream_t st)
+{
+    SweepArgs a;
+    a.H = p.H; a.W1 = p.W1; a.W = p.W; a.D = p.D; a.Dp8 = p.Dp / 8; a.flip = flip;
+    a.P1p = ((unsigned)p.P1 & 0xFFFFu) * 0x10001u;
+    a.P2mP1p = ((unsigned)(p.P2 - p.P1) & 0xFFFFu) * 0x10001u;
+    a.tag = ((sc.epoch & 1) ? 0x8000u : 0u) | ((sc.epoch & 2) ? 0x80000000u : 0u);
+    a.bnd = reinterpret_cast<uint4*>(sc.boundary);
+    a.ticket = sc.ticket; a.err = sc.err;
+    a.keys = sc.keys; a.d1 = sc.d1;
+    a.minD = p.minD; a.minX1 = p.minX1; a.uniq = p.uniq; a.INVALID = p.INVALID;
+    const bool pad = p.Dp != p.D;
+#define WSG_SW_CASE(k, m, n)                                                         \
+    if (p.K == k && mode == m && ndir == n) {                                        \
+        if (pad) launch_sweep_t<k, m, n, true>(C, S, a, st);                        \
+        else     launch_sweep_t<k, m, n, false>(C, S, a, st);                       \
+        return;                                                                      \
+    }
+    WSG_SW_CASE(1, 0, 4) WSG_SW_CASE(1, 1, 4) WSG_SW_CASE(1, 2, 4) WSG_SW_CASE(1, 1, 1) WSG_SW_CASE(1, 2, 1)
+    WSG_SW_CASE(2, 0, 4) WSG_SW_CASE(2, 1, 4) WSG_SW_CASE(2, 2, 4) WSG_SW_CASE(2, 1, 1) WSG_SW_CASE(2, 2, 1)
+#undef WSG_SW_CASE
+}
+
+// ------------------------------------------------------------------------------------------------
+// Around the fused WTA: reset of the right-view keys / left-view map, and the LR check (A.6).
+// ------------------------------------------------------------------------------------------------
+__global__ void wta_reset_kernel(unsigned long long* __restrict__ keys, int16_t* __restrict__ d1, size_t n, int invalid)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { keys[i] = ~0ull; d1[i] = (int16_t)invalid; }
+}
+
+__global__ void lrcheck_kernel(const unsigned long long* __restrict__ keys, const int16_t* __restrict__ d1,
+                               int16_t* __restrict__ raw, SgbmPlan p)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y;
+    if (x >= p.W) return;
+    const unsigned long long* krow = keys + (size_t)y * p.W;
+    int dv = d1[(size_t)y * p.W + x];
+    if (x >= p.minX1 && x < p.maxX1 && dv != p.INVALID) {
+        const int a = dv >> 4, b = (dv + 15) >> 4;
+        const int xa = x - a, xb = x - b;
+        bool ca = false, cb = false;
+        if (xa >= 0 && xa < p.W) {
+            const unsigned long long k = krow[xa];
+            const int d2 = (k == ~0ull) ? p.INVALID : (int)(k & 0xFFFFu) + p.minD;
+            ca = d2 >= p.minD && abs(d2 - a) > p.d12;
+        }
+        if (xb >= 0 && xb < p.W) {
+            const unsigned long long k = krow[xb];
+            const int d2 = (k == ~0ull) ? p.INVALID : (int)(k & 0xFFFFu) + p.minD;
+            cb = d2 >= p.minD && abs(d2 - b) > p.d12;
+        }
+        if (ca && cb) dv = p.INVALID;
+    }
+    raw[(size_t)y * p.W + x] = (int16_t)dv;
+}
+
+void launch_wta_reset(const SweepScratch& sc, const SgbmPlan& p, cudaStream_t st)
+{
+    const size_t n = (size_t)p.H * p.W;
+    wta_reset_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(sc.keys, sc.d1, n, p.INVALID);
+}
+
+void launch_lrcheck(const SweepScratch& sc, int16_t* raw, const SgbmPlan& p, cudaStream_t st)
+{
+    dim3 b(256), g((p.W + 255) / 256, p.H);
+    lrcheck_kernel<<<g, b, 0, st>>>(sc.keys, sc.d1, raw, p);
+}
+
+}  // namespace wsg
