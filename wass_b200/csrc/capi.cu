@@ -155,7 +155,7 @@ int wsg_run_sgbm(wsg_handle* h, const uint8_t* d_img1, const uint8_t* d_img2, si
             CK(h, cudaMemsetAsync(h->bnd.p, 0, h->bnd.cap, h->stream));
             h->bnd_H = pl.H; h->bnd_W1 = pl.W1; h->bnd_K = pl.K;
         }
-        const bool fused_wta = impl == WSG_AGG_SWEEPS_WTA;
+        const bool fused_wta = impl == WSG_AGG_SWEEPS_WTA && pl.uniq < 100;   // the in-sweep WTA needs 100-uniq > 0
         if (fused_wta) {
             if ((rc = ensure(h, h->keys, npix * sizeof(unsigned long long)))) return rc;
             if ((rc = ensure(h, h->d1, npix * sizeof(int16_t)))) return rc;

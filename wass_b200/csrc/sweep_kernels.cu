@@ -27,17 +27,29 @@ namespace wsg {
 
 static constexpr int SW_R = 8;             // rows (compute warps) per CTA
 static constexpr int SW_THREADS = (SW_R + 1) * 32;
-static constexpr int SW_PF = 4;            // register prefetch depth of the C (and S) stream, in pixels
-static constexpr int SW_HD = 2;            // boundary columns the helper keeps in flight
+static constexpr int SW_HD = 4;            // boundary columns the helper polls per round trip (<= NS/2)
 static constexpr unsigned TAGBITS = 0x80008000u;
-static constexpr int SPIN_LIMIT = 1 << 26;
+static constexpr int SPIN_LIMIT = 1 << 22;
 
 template <int K> struct SweepCfg {
-    static constexpr int NS = K == 1 ? 8 : 6;                 // ring depth in columns
+    static constexpr int NS = K == 1 ? 8 : 6;                 // state ring depth in columns
     static constexpr int SLOT_V = 3 * K * 32;                 // uint4 per ring slot: [dir][k][lane]
     static constexpr int RING_V = NS * SLOT_V;
-    static constexpr int SMEM = SW_R * RING_V * 16 + SW_R * K * 32 * 16;   // rings + per-warp WTA scratch
+    static constexpr int PFD = K == 1 ? 12 : 4;               // pixels of C (and S) in flight per row (cp.async staging)
+    static constexpr int PIX_V = K * 32;                      // uint4 per pixel
+    static constexpr int RINGS_V = SW_R * RING_V;             // smem map (uint4 units): state rings
+    static constexpr int SCR_V = SW_R * PIX_V;                //   per-warp WTA scratch
+    static constexpr int STAGE_V = SW_R * PFD * PIX_V;        //   per-warp staging of the C stream (and again for S)
+    static constexpr int SMEM = (RINGS_V + SCR_V + 2 * STAGE_V) * 16;
 };
+
+// 16-byte asynchronous global->shared copy (L2 only), one per lane; completion is tracked per thread in commit groups
+__device__ __forceinline__ void cp_async16(unsigned smem_dst, const void* gsrc)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_dst), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 struct SweepArgs {
     int H, W1, W, D;
@@ -52,6 +64,7 @@ struct SweepArgs {
     unsigned long long* keys;   // [H][W]  (minS, W1-1-x, d) of the best match that lands on x2 (A.5)
     int16_t* d1;                // [H][W]  left-view disparity before the LR check
     int minD, minX1, uniq, INVALID;
+    float urcp;                 // 1 / (100 - uniq)
 };
 
 __device__ __forceinline__ uint4 ld_volatile(const uint4* p)
@@ -74,83 +87,91 @@ __device__ __forceinline__ void wait_prog(volatile int* flag, int need, int& see
     if (seen < need) {
         int spins = 0;
         while ((seen = *flag) < need) {
-            if ((++spins & 1023) == 0 && (spins > SPIN_LIMIT || *reinterpret_cast<volatile int*>(err) != 0)) {
+            if (++spins > 64) __nanosleep(spins > 4096 ? 400 : 40);     // a band that is not yet due must not steal issue slots
+            if ((spins & 1023) == 0 && (spins > SPIN_LIMIT || *reinterpret_cast<volatile int*>(err) != 0)) {
                 *err = 1;
                 seen = 0x7fffffff;
                 break;
             }
         }
     }
-    __threadfence_block();   // orders the data reads after the counter read (and is a compiler barrier)
+    // Shared-memory requests of one warp are served in issue order, so a counter read that saw the value is followed
+    // by data reads that see the data; only the compiler has to be kept from moving them.
+    asm volatile("" ::: "memory");
 }
 
-// A.5 for one pixel held by one warp: s = final S, 8*K consecutive disparities per lane.
-template <int K>
+// A.5 for one pixel held by one warp: s = final S, 8*K consecutive disparities per lane (a lane is all real or all pad:
+// numDisparities is a multiple of 16).  Needs 0 <= uniquenessRatio < 100 (the host routes anything else to wta_kernel).
+//   winner      first d with minimal S: warp minimum of the 32-bit keys (S << 16 | d)
+//   uniqueness  reject iff some d outside {best-1,best,best+1} has S(d)*(100-uniq) < minS*100, i.e. S(d) <= Tm with
+//               Tm = floor((minS*100-1)/(100-uniq)).  Counted instead of searched: #(S <= Tm) over all d, by a packed
+//               subtract whose sign bits are the comparison results, against the same count inside the window, which
+//               lane 0 gets from the two neighbours it needs for the parabola anyway.
+template <int K, bool HASPAD>
 __device__ __forceinline__ void wta_pixel(const unsigned (&s)[4 * K], int l, int xh, int y, const SweepArgs& a,
                                           int16_t* scratch)
 {
     constexpr int NV8 = 8 * K;
     const int dlane = l * NV8;
-    unsigned key[NV8];
-#pragma unroll
-    for (int e = 0; e < 4 * K; ++e) {
-        key[2 * e] = (s[e] << 16) + (unsigned)(dlane + 2 * e);
-        key[2 * e + 1] = (s[e] & 0xFFFF0000u) + (unsigned)(dlane + 2 * e + 1);
-    }
-    unsigned kmin = 0xFFFFFFFFu;
-#pragma unroll
-    for (int e = 0; e < NV8; ++e)
-        if (dlane + e < a.D) kmin = min(kmin, key[e]);
-    kmin = __reduce_min_sync(FULL, kmin);
-    const int minS = (int)(kmin >> 16), best = (int)(kmin & 0xFFFFu);
-    const int udiv = 100 - a.uniq;
-    int bad = 0;
-    if (udiv > 0) {
-        // S(d)*(100-uniq) < minS*100  <=>  S(d) <= Tm,  Tm = floor((minS*100-1)/(100-uniq))
-        const int n = minS * 100 - 1;                    // < 3.3e6: exact in float
-        int Tm = n < 0 ? -1 : (int)((float)n * (1.0f / (float)udiv));
-        if (n >= 0) { if ((Tm + 1) * udiv <= n) ++Tm; else if (Tm * udiv > n) --Tm; }
-        const unsigned Tkey = Tm < 0 ? 0u : (((unsigned)Tm << 16) | 0xFFFFu);
-        const int rel = best - dlane;
-#pragma unroll
-        for (int e = 0; e < NV8; ++e) {
-            const bool near = (unsigned)(e - rel + 1) <= 2u;
-            if (Tm >= 0 && key[e] <= Tkey && !near && dlane + e < a.D) bad = 1;
-        }
-    } else {
-#pragma unroll
-        for (int e = 0; e < NV8; ++e) {
-            const int sv = (int)(key[e] >> 16), d = dlane + e;
-            if (d < a.D && sv * udiv < minS * 100 && abs(best - d) > 1) bad = 1;
-        }
-    }
-    if (__any_sync(FULL, bad)) return;
-    // neighbours of the winner for the parabola: stage this pixel's S in shared memory
-    __syncwarp();
+    const bool padlane = HASPAD && dlane >= a.D;
+    // stage this pixel's S for lane 0 (previous pixel's reads are over: lane 0 passed the __syncwarp below)
 #pragma unroll
     for (int k = 0; k < K; ++k)
         reinterpret_cast<uint4*>(scratch)[l * K + k] = make_uint4(s[4 * k], s[4 * k + 1], s[4 * k + 2], s[4 * k + 3]);
+    unsigned kmin = 0xFFFFFFFFu;
+#pragma unroll
+    for (int e = 0; e < 4 * K; ++e) {
+        const unsigned klo = s[e] * 65536u + (unsigned)(dlane + 2 * e);
+        const unsigned khi = (s[e] & 0xFFFF0000u) | (unsigned)(dlane + 2 * e + 1);
+        kmin = __vimin3_u32(kmin, klo, khi);
+    }
+    if (padlane) kmin = 0xFFFFFFFFu;
+    kmin = __reduce_min_sync(FULL, kmin);
+    const int minS = (int)(kmin >> 16), best = (int)(kmin & 0xFFFFu);
+    const int udiv = 100 - a.uniq;
+    const int n = minS * 100 - 1;                        // < 3.3e6: exact in float
+    int Tm = n < 0 ? -1 : (int)((float)n * a.urcp);
+    if (n >= 0) { if ((Tm + 1) * udiv <= n) ++Tm; else if (Tm * udiv > n) --Tm; }
+    // packed count of S <= Tm: (0x8000 + T - S) keeps bit 15 iff T >= S (S, T <= 0x7fff: no borrow between the halves)
+    const unsigned T2 = ((unsigned)min(max(Tm, 0), 32767) | 0x8000u) * 0x10001u;
+    unsigned bits = 0;
+#pragma unroll
+    for (int e = 0; e < 4 * K; ++e) bits |= ((T2 - s[e]) & 0x80008000u) >> (e & 15);
+    int cnt = __popc(bits);
+    if (padlane || Tm < 0) cnt = 0;
+    const int total = __reduce_add_sync(FULL, cnt);
     __syncwarp();
     if (l == 0) {
-        const int x = xh + a.minX1;
-        const int x2 = x - best - a.minD;
-        const unsigned long long k64 = ((unsigned long long)minS << 40) |
-                                       ((unsigned long long)(a.W1 - 1 - xh) << 16) | (unsigned long long)best;
-        atomicMin(a.keys + (size_t)y * a.W + x2, k64);
-        int dd = best * 16;
-        if (best > 0 && best < a.D - 1) {
-            const int sm = scratch[best - 1], sp = scratch[best + 1];
-            const int den = max(sm + sp - 2 * minS, 1);
-            dd += ((sm - sp) * 16 + den) / (2 * den);
+        int sm = 0, sp = 0, inwin = minS <= Tm;
+        const bool inner = best > 0 && best < a.D - 1;
+        if (best > 0) { sm = scratch[best - 1]; inwin += sm <= Tm; }
+        if (best < a.D - 1) { sp = scratch[best + 1]; inwin += sp <= Tm; }
+        if (total <= inwin) {
+            const int x = xh + a.minX1;
+            const int x2 = x - best - a.minD;
+            const unsigned long long k64 = ((unsigned long long)minS << 40) |
+                                           ((unsigned long long)(a.W1 - 1 - xh) << 16) | (unsigned long long)best;
+            atomicMin(a.keys + (size_t)y * a.W + x2, k64);
+            int dd = best * 16;
+            if (inner) {
+                // trunc(((sm-sp)*16 + den) / (2*den)): |numerator| < 2^24, so a float quotient is off by at most one
+                const int den = max(sm + sp - 2 * minS, 1), den2 = 2 * den;
+                const int num = (sm - sp) * 16 + den, an = abs(num);
+                int q = (int)__fdividef((float)an, (float)den2);
+                const int rem = an - q * den2;
+                q += rem >= den2 ? 1 : (rem < 0 ? -1 : 0);
+                dd += num < 0 ? -q : q;
+            }
+            a.d1[(size_t)y * a.W + x] = (int16_t)(dd + a.minD * 16);
         }
-        a.d1[(size_t)y * a.W + x] = (int16_t)(dd + a.minD * 16);
     }
+    __syncwarp();
 }
 
 // MODE 0: S = sum of this sweep's L (no read);  1: S += sum (read-modify-write);  2: S += sum, then WTA (S not written)
 // NDIR 4: full sweep;  1: horizontal direction only (the fifth path of MODE_SGBM): rows are independent.
 template <int K, int MODE, int NDIR, bool HASPAD>
-__global__ void __launch_bounds__(SW_THREADS, K == 1 ? 2 : 1)
+__global__ void __launch_bounds__(SW_THREADS, 1)
 sweep_kernel(const uint4* __restrict__ C, uint4* __restrict__ S, SweepArgs a)
 {
     using Cfg = SweepCfg<K>;
@@ -163,6 +184,8 @@ sweep_kernel(const uint4* __restrict__ C, uint4* __restrict__ S, SweepArgs a)
     const int tid = threadIdx.x, warp = tid >> 5, l = tid & 31;
     if (tid == 0) s_band = atomicAdd(a.ticket, 1);
     if (tid <= SW_R) prog[tid] = 0;
+    if (NDIR == 4)
+        for (int i = tid; i < Cfg::RINGS_V; i += SW_THREADS) smem[i] = make_uint4(0, 0, 0, 0);
     __syncthreads();
     const int band = s_band;
     const size_t bstride = (size_t)a.W1 * Cfg::SLOT_V;      // uint4 per boundary row
@@ -173,52 +196,60 @@ sweep_kernel(const uint4* __restrict__ C, uint4* __restrict__ S, SweepArgs a)
         const uint4* src = a.bnd + (size_t)(band - 1) * bstride + l;
         uint4* ring = smem;                                // ring 0
         uint4 hb[SW_HD][3 * K];
-        int seen = 0;
-        bool dead = false;
+        int seen = 0, spins = 0;
+        // Poll a window of SW_HD columns per round trip to L2 and forward its valid prefix: the throughput adapts to the
+        // producer (up to SW_HD columns per round trip) and the band ends up trailing it by about one window.
+        for (int x = 0; x < a.W1;) {
 #pragma unroll
-        for (int u = 0; u < SW_HD; ++u)
+            for (int u = 0; u < SW_HD; ++u)
 #pragma unroll
-            for (int j = 0; j < 3 * K; ++j) hb[u][j] = ld_volatile(src + (size_t)min(u, a.W1 - 1) * Cfg::SLOT_V + j * 32);
-        for (int base = 0; base < a.W1; base += SW_HD) {
+                for (int j = 0; j < 3 * K; ++j)
+                    hb[u][j] = ld_volatile(src + (size_t)min(x + u, a.W1 - 1) * Cfg::SLOT_V + j * 32);
+            int n = 0;
+            bool prefix = true;
 #pragma unroll
             for (int u = 0; u < SW_HD; ++u) {
-                const int x = base + u;
-                if (x < a.W1) {
-                    int spins = 0;
-                    while (!dead) {
-                        bool ok = true;
+                bool ok = x + u < a.W1;
 #pragma unroll
-                        for (int j = 0; j < 3 * K; ++j)
-                            ok = ok && ((hb[u][j].x & TAGBITS) == a.tag) && ((hb[u][j].y & TAGBITS) == a.tag) &&
-                                 ((hb[u][j].z & TAGBITS) == a.tag) && ((hb[u][j].w & TAGBITS) == a.tag);
-                        if (__all_sync(FULL, ok)) break;
-                        if ((++spins & 255) == 0 && (spins > (SPIN_LIMIT >> 4) || *reinterpret_cast<volatile int*>(a.err) != 0)) {
-                            *a.err = 2;
-                            dead = true;
-                            break;
-                        }
-                        __nanosleep(32);
+                for (int j = 0; j < 3 * K; ++j)
+                    ok = ok && ((hb[u][j].x & TAGBITS) == a.tag) && ((hb[u][j].y & TAGBITS) == a.tag) &&
+                         ((hb[u][j].z & TAGBITS) == a.tag) && ((hb[u][j].w & TAGBITS) == a.tag);
+                prefix = prefix && __all_sync(FULL, ok);
+                if (prefix) n = u + 1;
+            }
+            if (n == 0) {
+                if ((++spins & 255) == 0 && (spins > (SPIN_LIMIT >> 2) || *reinterpret_cast<volatile int*>(a.err) != 0)) {
+                    *a.err = 2;
+                    return;
+                }
+                __nanosleep(spins > 64 ? 200 : 20);
+                continue;
+            }
+            spins = 0;
+            // ring 0 slot c is free once warp 0 has completed column c-NS+1
+            wait_prog(&prog[1], x + n - 1 - NS + 2, seen, a.err);
 #pragma unroll
-                        for (int j = 0; j < 3 * K; ++j) hb[u][j] = ld_volatile(src + (size_t)x * Cfg::SLOT_V + j * 32);
-                    }
-                    // ring 0 slot x is free once warp 0 has completed column x-NS+1
-                    wait_prog(&prog[1], x - NS + 2, seen, a.err);
-                    uint4* dst = ring + (x % NS) * Cfg::SLOT_V + l;
+            for (int u = 0; u < SW_HD; ++u) {
+                if (u < n) {
+                    uint4* dst = ring + ((x + u) % NS) * Cfg::SLOT_V + l;
 #pragma unroll
                     for (int j = 0; j < 3 * K; ++j)
                         dst[j * 32] = make_uint4(hb[u][j].x & ~TAGBITS, hb[u][j].y & ~TAGBITS, hb[u][j].z & ~TAGBITS,
                                                  hb[u][j].w & ~TAGBITS);
-                    __syncwarp();
-                    __threadfence_block();
-                    if (l == 0) prog[0] = x + 1;
-                    const int xn = x + SW_HD;
-                    if (xn < a.W1) {
-#pragma unroll
-                        for (int j = 0; j < 3 * K; ++j) hb[u][j] = ld_volatile(src + (size_t)xn * Cfg::SLOT_V + j * 32);
-                    }
                 }
             }
+            __syncwarp();
+            asm volatile("" ::: "memory");
+            x += n;
+            if (l == 0) prog[0] = x;
         }
+        // one more column of zeros: the out-of-image predecessor of the last pixel's (x+1,y-1) path
+        wait_prog(&prog[1], a.W1 - NS + 2, seen, a.err);
+#pragma unroll
+        for (int j = 0; j < 3 * K; ++j) ring[(a.W1 % NS) * Cfg::SLOT_V + l + j * 32] = make_uint4(0, 0, 0, 0);
+        __syncwarp();
+        asm volatile("" ::: "memory");
+        if (l == 0) prog[0] = a.W1 + 1;
         return;
     }
 
@@ -232,12 +263,14 @@ sweep_kernel(const uint4* __restrict__ C, uint4* __restrict__ S, SweepArgs a)
     const long long dstep = a.flip ? -(long long)a.Dp8 : (long long)a.Dp8;
     const size_t first = ((size_t)yp * a.W1 + (a.flip ? a.W1 - 1 : 0)) * a.Dp8 + l;
     const uint4* cpf = C + first;                   // prefetch cursors
-    uint4* spf = S + first;
+    const uint4* spf = S + first;
     uint4* scur = S + first;                        // compute cursor
     const uint4* ring_in = smem + (size_t)r * Cfg::RING_V + l;
     uint4* ring_out = smem + (size_t)(r + 1) * Cfg::RING_V + l;     // only used when out_mode == 1
     uint4* bnd_out = a.bnd + (size_t)band * bstride + l;            // only used when out_mode == 2
-    int16_t* scratch = reinterpret_cast<int16_t*>(smem + (size_t)SW_R * Cfg::RING_V + (size_t)r * K * 32);
+    int16_t* scratch = reinterpret_cast<int16_t*>(smem + Cfg::RINGS_V + (size_t)r * Cfg::PIX_V);
+    uint4* stageC = smem + Cfg::RINGS_V + Cfg::SCR_V + (size_t)r * Cfg::PFD * Cfg::PIX_V + l;
+    uint4* stageS = stageC + Cfg::STAGE_V;
     volatile int* prog_in = &prog[r];
     volatile int* prog_me = &prog[r + 1];
     volatile int* prog_next = &prog[r + 2 <= SW_R ? r + 2 : SW_R];
@@ -247,119 +280,143 @@ sweep_kernel(const uint4* __restrict__ C, uint4* __restrict__ S, SweepArgs a)
 #pragma unroll
     for (int k = 0; k < K; ++k) padm[k] = ((l * K + k) * 8 >= a.D) ? SAT2 : 0u;
 
-    uint4 cb[SW_PF][K], sb[SW_PF][K];
-#pragma unroll
-    for (int u = 0; u < SW_PF; ++u) {
-        if (u < a.W1) {
+    // one commit group per pixel, PFD pixels ahead; each lane copies and later reads back its own 16 bytes
+    const unsigned stC = (unsigned)__cvta_generic_to_shared(stageC), stS = (unsigned)__cvta_generic_to_shared(stageS);
+    for (int i = 0; i < Cfg::PFD; ++i) {
+        if (i < a.W1) {
 #pragma unroll
             for (int k = 0; k < K; ++k) {
-                cb[u][k] = ldg_stream(cpf + k * 32);
-                if (MODE != 0) sb[u][k] = ldg_rw(spf + k * 32);
+                cp_async16(stC + (i * Cfg::PIX_V + k * 32) * 16, cpf + k * 32);
+                if (MODE != 0) cp_async16(stS + (i * Cfg::PIX_V + k * 32) * 16, spf + k * 32);
             }
         }
+        cp_async_commit();
         cpf += dstep; spf += dstep;
     }
 
-    unsigned Nh[NR];
+    // The horizontal direction runs ONE PIXEL AHEAD of the three directions that come from the row above: its step for
+    // pixel x+1 and their steps for pixel x are four independent dependency chains in one basic block.
+    unsigned Nh[NR], Cc[NR], Lh[NR];
 #pragma unroll
     for (int j = 0; j < NR; ++j) Nh[j] = 0;
+    cp_async_wait<Cfg::PFD - 1>();
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        const uint4 c = stageC[k * 32];
+        Cc[4 * k] = c.x; Cc[4 * k + 1] = c.y; Cc[4 * k + 2] = c.z; Cc[4 * k + 3] = c.w;
+    }
+    agg_step<32, NR, HASPAD>(Nh, Cc, Lh, l, a.P1p, a.P2mP1p, padm);
 
-    for (int base = 0; base < a.W1; base += SW_PF) {
+    int pslot = 0;                                  // x % PFD
+    for (int x = 0; x < a.W1; ++x) {                // logical column
+        const int nslot = pslot + 1 == Cfg::PFD ? 0 : pslot + 1;
+        unsigned Cn[NR], Lhn[NR], vs[NR], v[3][NR], Nd[3][NR];
+        cp_async_wait<Cfg::PFD - 2>();              // pixel x+1 has landed (past the row end: a stale slot, result unused)
 #pragma unroll
-        for (int u = 0; u < SW_PF; ++u) {
-            const int x = base + u;                // logical column
-            if (x < a.W1) {
-                unsigned Cw[NR], vs[NR], v[NR];
+        for (int k = 0; k < K; ++k) {
+            const uint4 c = stageC[nslot * Cfg::PIX_V + k * 32];
+            Cn[4 * k] = c.x; Cn[4 * k + 1] = c.y; Cn[4 * k + 2] = c.z; Cn[4 * k + 3] = c.w;
+        }
+        if (MODE == 0) {
 #pragma unroll
-                for (int k = 0; k < K; ++k) {
-                    Cw[4 * k] = cb[u][k].x; Cw[4 * k + 1] = cb[u][k].y; Cw[4 * k + 2] = cb[u][k].z; Cw[4 * k + 3] = cb[u][k].w;
-                }
-                // ---- horizontal direction: state stays in registers
-                agg_step<32, NR, HASPAD>(Nh, Cw, v, l, a.P1p, a.P2mP1p, padm);
-                if (MODE == 0) {
+            for (int j = 0; j < NR; ++j) vs[j] = Lh[j];
+        } else {
 #pragma unroll
-                    for (int j = 0; j < NR; ++j) vs[j] = v[j];
-                } else {
-#pragma unroll
-                    for (int k = 0; k < K; ++k) {
-                        vs[4 * k] = __viaddmin_u16x2(sb[u][k].x, v[4 * k], SAT2);
-                        vs[4 * k + 1] = __viaddmin_u16x2(sb[u][k].y, v[4 * k + 1], SAT2);
-                        vs[4 * k + 2] = __viaddmin_u16x2(sb[u][k].z, v[4 * k + 2], SAT2);
-                        vs[4 * k + 3] = __viaddmin_u16x2(sb[u][k].w, v[4 * k + 3], SAT2);
-                    }
-                }
-                if (NDIR == 4) {
-                    // ---- the three directions that come from the row above
-                    unsigned Nd[3][NR];
-                    if (top) {
-#pragma unroll
-                        for (int q = 0; q < 3; ++q)
-#pragma unroll
-                            for (int j = 0; j < NR; ++j) Nd[q][j] = 0;
-                    } else {
-                        wait_prog(prog_in, min(x + 2, a.W1), seen_in, a.err);
-                        const int sl[3] = {(x + NS - 1) % NS, x % NS, (x + 1) % NS};
-                        const bool have[3] = {x > 0, true, x + 1 < a.W1};
-#pragma unroll
-                        for (int q = 0; q < 3; ++q) {
-#pragma unroll
-                            for (int k = 0; k < K; ++k) {
-                                uint4 t = make_uint4(0, 0, 0, 0);
-                                if (have[q]) t = ring_in[sl[q] * Cfg::SLOT_V + (q * K + k) * 32];
-                                Nd[q][4 * k] = t.x; Nd[q][4 * k + 1] = t.y; Nd[q][4 * k + 2] = t.z; Nd[q][4 * k + 3] = t.w;
-                            }
-                        }
-                    }
-#pragma unroll
-                    for (int q = 0; q < 3; ++q) {
-                        agg_step<32, NR, HASPAD>(Nd[q], Cw, v, l, a.P1p, a.P2mP1p, padm);
-#pragma unroll
-                        for (int j = 0; j < NR; ++j) vs[j] = __viaddmin_u16x2(vs[j], v[j], SAT2);
-                    }
-                    // ---- hand the new states down
-                    if (out_mode == 1) {
-                        wait_prog(prog_next, x - NS + 2, seen_next, a.err);
-                        uint4* dst = ring_out + (x % NS) * Cfg::SLOT_V;
-#pragma unroll
-                        for (int q = 0; q < 3; ++q)
-#pragma unroll
-                            for (int k = 0; k < K; ++k)
-                                dst[(q * K + k) * 32] = make_uint4(Nd[q][4 * k], Nd[q][4 * k + 1], Nd[q][4 * k + 2], Nd[q][4 * k + 3]);
-                    } else if (out_mode == 2) {
-                        uint4* dst = bnd_out + (size_t)x * Cfg::SLOT_V;
-#pragma unroll
-                        for (int q = 0; q < 3; ++q)
-#pragma unroll
-                            for (int k = 0; k < K; ++k)
-                                st_volatile(dst + (q * K + k) * 32,
-                                            make_uint4(Nd[q][4 * k] | a.tag, Nd[q][4 * k + 1] | a.tag, Nd[q][4 * k + 2] | a.tag,
-                                                       Nd[q][4 * k + 3] | a.tag));
-                    }
-                    __syncwarp();
-                    __threadfence_block();
-                    if (l == 0) *prog_me = x + 1;
-                }
-                // ---- S out, or winner-take-all on the spot
-                if (MODE == 2) {
-                    const int xh = a.flip ? a.W1 - 1 - x : x;
-                    wta_pixel<K>(vs, l, xh, yp, a, scratch);
-                } else {
-#pragma unroll
-                    for (int k = 0; k < K; ++k)
-                        stg_stream(scur + k * 32, make_uint4(vs[4 * k], vs[4 * k + 1], vs[4 * k + 2], vs[4 * k + 3]));
-                }
-                scur += dstep;
-                // ---- refill this prefetch stage
-                if (x + SW_PF < a.W1) {
-#pragma unroll
-                    for (int k = 0; k < K; ++k) {
-                        cb[u][k] = ldg_stream(cpf + k * 32);
-                        if (MODE != 0) sb[u][k] = ldg_rw(spf + k * 32);
-                    }
-                }
-                cpf += dstep; spf += dstep;
+            for (int k = 0; k < K; ++k) {
+                const uint4 sv = stageS[pslot * Cfg::PIX_V + k * 32];
+                vs[4 * k] = __viaddmin_u16x2(sv.x, Lh[4 * k], SAT2);
+                vs[4 * k + 1] = __viaddmin_u16x2(sv.y, Lh[4 * k + 1], SAT2);
+                vs[4 * k + 2] = __viaddmin_u16x2(sv.z, Lh[4 * k + 2], SAT2);
+                vs[4 * k + 3] = __viaddmin_u16x2(sv.w, Lh[4 * k + 3], SAT2);
             }
         }
+        if (NDIR == 4) {
+            // ---- states of the three directions that come from the row above
+            if (top) {
+#pragma unroll
+                for (int q = 0; q < 3; ++q)
+#pragma unroll
+                    for (int j = 0; j < NR; ++j) Nd[q][j] = 0;
+            } else {
+                // columns -1 and W1 of the row above exist in the ring as zeros (zero-initialised slot NS-1, and
+                // one extra column written by the producer): L = 0 for an out-of-image predecessor
+                wait_prog(prog_in, x + 2, seen_in, a.err);
+                const int sl[3] = {(x + NS - 1) % NS, x % NS, (x + 1) % NS};
+#pragma unroll
+                for (int q = 0; q < 3; ++q) {
+#pragma unroll
+                    for (int k = 0; k < K; ++k) {
+                        const uint4 t = ring_in[sl[q] * Cfg::SLOT_V + (q * K + k) * 32];
+                        Nd[q][4 * k] = t.x; Nd[q][4 * k + 1] = t.y; Nd[q][4 * k + 2] = t.z; Nd[q][4 * k + 3] = t.w;
+                    }
+                }
+            }
+            // ---- four independent chains
+            agg_step<32, NR, HASPAD>(Nh, Cn, Lhn, l, a.P1p, a.P2mP1p, padm);
+#pragma unroll
+            for (int q = 0; q < 3; ++q) agg_step<32, NR, HASPAD>(Nd[q], Cc, v[q], l, a.P1p, a.P2mP1p, padm);
+            // ---- hand the new states down
+            if (out_mode == 1) {
+                wait_prog(prog_next, x - NS + 2, seen_next, a.err);
+                uint4* dst = ring_out + (x % NS) * Cfg::SLOT_V;
+#pragma unroll
+                for (int q = 0; q < 3; ++q)
+#pragma unroll
+                    for (int k = 0; k < K; ++k)
+                        dst[(q * K + k) * 32] = make_uint4(Nd[q][4 * k], Nd[q][4 * k + 1], Nd[q][4 * k + 2], Nd[q][4 * k + 3]);
+            } else if (out_mode == 2) {
+                uint4* dst = bnd_out + (size_t)x * Cfg::SLOT_V;
+#pragma unroll
+                for (int q = 0; q < 3; ++q)
+#pragma unroll
+                    for (int k = 0; k < K; ++k)
+                        st_volatile(dst + (q * K + k) * 32,
+                                    make_uint4(Nd[q][4 * k] | a.tag, Nd[q][4 * k + 1] | a.tag, Nd[q][4 * k + 2] | a.tag,
+                                               Nd[q][4 * k + 3] | a.tag));
+            }
+            __syncwarp();                      // every lane's state stores are issued before the counter store
+            asm volatile("" ::: "memory");
+            if (l == 0) *prog_me = x + 1;
+#pragma unroll
+            for (int q = 0; q < 3; ++q)
+#pragma unroll
+                for (int j = 0; j < NR; ++j) vs[j] = __viaddmin_u16x2(vs[j], v[q][j], SAT2);
+        } else {
+            agg_step<32, NR, HASPAD>(Nh, Cn, Lhn, l, a.P1p, a.P2mP1p, padm);
+        }
+        // ---- S out, or winner-take-all on the spot
+        if (MODE == 2) {
+            const int xh = a.flip ? a.W1 - 1 - x : x;
+            wta_pixel<K, HASPAD>(vs, l, xh, yp, a, scratch);
+        } else {
+#pragma unroll
+            for (int k = 0; k < K; ++k)
+                stg_stream(scur + k * 32, make_uint4(vs[4 * k], vs[4 * k + 1], vs[4 * k + 2], vs[4 * k + 3]));
+        }
+        scur += dstep;
+        // ---- refill the staging slot just consumed with pixel x + PFD
+        if (x + Cfg::PFD < a.W1) {
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                cp_async16(stC + (pslot * Cfg::PIX_V + k * 32) * 16, cpf + k * 32);
+                if (MODE != 0) cp_async16(stS + (pslot * Cfg::PIX_V + k * 32) * 16, spf + k * 32);
+            }
+        }
+        cp_async_commit();
+        cpf += dstep; spf += dstep;
+        pslot = nslot;
+#pragma unroll
+        for (int j = 0; j < NR; ++j) { Cc[j] = Cn[j]; Lh[j] = Lhn[j]; }
+    }
+    cp_async_wait<0>();
+    if (NDIR == 4 && out_mode == 1) {
+        // the extra zero column (see above)
+        wait_prog(prog_next, a.W1 - NS + 2, seen_next, a.err);
+#pragma unroll
+        for (int j = 0; j < 3 * K; ++j) ring_out[(a.W1 % NS) * Cfg::SLOT_V + j * 32] = make_uint4(0, 0, 0, 0);
+        __syncwarp();
+        asm volatile("" ::: "memory");
+        if (l == 0) *prog_me = a.W1 + 1;
     }
 }
 
@@ -395,6 +452,7 @@ void launch_sweep(const int16_t* C, int16_t* S, int flip, int mode, int ndir, co
     a.ticket = sc.ticket; a.err = sc.err;
     a.keys = sc.keys; a.d1 = sc.d1;
     a.minD = p.minD; a.minX1 = p.minX1; a.uniq = p.uniq; a.INVALID = p.INVALID;
+    a.urcp = p.uniq < 100 ? 1.0f / (float)(100 - p.uniq) : 0.f;
     const bool pad = p.Dp != p.D;
 #define WSG_SW_CASE(k, m, n)                                                         \
     if (p.K == k && mode == m && ndir == n) {                                        \
