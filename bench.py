@@ -178,56 +178,88 @@ def run_ours(args, rank, world):
         torch.cuda.synchronize()
 
     p = wass_params(NDISP, capi.MODE_HH)
-    img1, img2 = make_frame(rank)            # frame index = rank (frames shard one per GPU)
-    H, Wp = img1.shape
-    h = capi.Handle(local)
-    h.sgbm_set_impl(args.agg_impl)
-    # a dedicated (non-default) torch stream: the library launches on it, torch events time it
-    stream = torch.cuda.Stream()
-    torch.cuda.set_stream(stream)
-    h.set_stream(stream.cuda_stream)
+    depth = max(1, args.pipeline_depth)
+    frames = [make_frame(depth * rank + i) for i in range(depth)]      # frames shard across GPUs, `depth` in flight per GPU
+    H, Wp = frames[0][0].shape
+    # One handle (= one device arena + one CUDA stream) per frame in flight.  The library launches on dedicated
+    # (non-default) torch streams; torch events on a third stream bracket the timed region.
+    main = torch.cuda.Stream()
+    torch.cuda.set_stream(main)
+    hs, streams, dev, pin = [], [], [], []
+    for i in range(depth):
+        h = capi.Handle(local)
+        h.sgbm_set_impl(args.agg_impl)
+        st = torch.cuda.Stream()
+        h.set_stream(st.cuda_stream)
+        hs.append(h); streams.append(st)
+        i1, i2 = frames[i]
+        dev.append((torch.from_numpy(i1).cuda(), torch.from_numpy(i2).cuda(),
+                    torch.empty((H, Wp), dtype=torch.int16, device="cuda")))
+        pin.append((torch.from_numpy(i1).pin_memory(), torch.from_numpy(i2).pin_memory(),
+                    torch.empty((H, Wp), dtype=torch.int16).pin_memory()))
+    torch.cuda.synchronize()
 
-    d1 = torch.from_numpy(img1).cuda()
-    d2 = torch.from_numpy(img2).cuda()
-    dd = torch.empty((H, Wp), dtype=torch.int16, device="cuda")
-    p1 = torch.from_numpy(img1).pin_memory()
-    p2 = torch.from_numpy(img2).pin_memory()
-    pd = torch.empty((H, Wp), dtype=torch.int16).pin_memory()
+    def step_dev(i):
+        d1, d2, dd = dev[i]
+        hs[i].sgbm_compute_device(d1.data_ptr(), d2.data_ptr(), H, Wp, Wp, p, dd.data_ptr())
 
-    def step_dev():
-        h.sgbm_compute_device(d1.data_ptr(), d2.data_ptr(), H, Wp, Wp, p, dd.data_ptr())
+    def step_e2e(i):
+        p1, p2, pd = pin[i]
+        hs[i].sgbm_compute_ptr(p1.data_ptr(), p2.data_ptr(), H, Wp, Wp, p, pd.data_ptr())
 
-    def step_e2e():
-        h.sgbm_compute_ptr(p1.data_ptr(), p2.data_ptr(), H, Wp, Wp, p, pd.data_ptr())
+    def timed_device(nsteps, nstreams):
+        """nsteps frames, frame k on handle k % nstreams; device time between two events on `main`."""
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record(main)
+        for st in streams[:nstreams]:
+            st.wait_event(e0)
+        for k in range(nsteps):
+            step_dev(k % nstreams)
+        for st in streams[:nstreams]:
+            ev = torch.cuda.Event()
+            ev.record(st)
+            main.wait_event(ev)
+        e1.record(main)
+        barrier()
+        return e0.elapsed_time(e1)
 
-    # ---- device-resident throughput ("value") with per-stage events for the roofline
+    # ---- warm-up, then the per-stage profile of ONE frame at a time (kernels timed alone: roofline numbers)
     for _ in range(max(args.warmup, 3)):
-        step_dev()
+        for i in range(depth):
+            step_dev(i)
     barrier()
-    h.profile_enable(True)
-    h.profile_reset()
+    hs[0].profile_enable(True)
+    hs[0].profile_reset()
+    ms_serial = timed_device(args.steps, 1)
+    prof = hs[0].profile_get()
+    hs[0].profile_enable(False)
+    stats = hs[0].sgbm_stats()
+
+    # ---- device-resident throughput ("value"): `depth` frames in flight on as many streams
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    e0.record(stream)
-    for _ in range(args.steps):
-        step_dev()
-    e1.record(stream)
-    barrier()
-    ms_dev = e0.elapsed_time(e1)
-    prof = h.profile_get()
-    h.profile_enable(False)
-    stats = h.sgbm_stats()
+    ms_dev = timed_device(args.steps, depth)
 
-    # ---- end to end through the C ABI with HOST buffers (pinned): H2D + kernels + D2H per step
-    for _ in range(2):
-        step_e2e()
+    # ---- end to end through the C ABI with HOST buffers (pinned): H2D + kernels + D2H per step, one host thread per
+    #      frame in flight (the call is synchronous and releases the GIL)
+    def e2e_worker(i, n):
+        torch.cuda.set_device(local)
+        for _ in range(n):
+            step_e2e(i)
+
+    def run_e2e(nsteps):
+        ths = [threading.Thread(target=e2e_worker, args=(i, len(range(i, nsteps, depth)))) for i in range(depth)]
+        for t_ in ths:
+            t_.start()
+        for t_ in ths:
+            t_.join()
+
+    run_e2e(2 * depth)
     barrier()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        step_e2e()
+    run_e2e(args.steps)
     torch.cuda.synchronize()
     ms_e2e = (time.perf_counter() - t0) * 1e3
     clocks = sampler.stop() if rank == 0 else None
@@ -237,8 +269,8 @@ def run_ours(args, rank, world):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_dev, ms_e2e = float(t[0]), float(t[1])
 
-    # cross-check of the two paths on this rank (bit-exact)
-    same = bool(torch.equal(dd.cpu(), pd))
+    # cross-check of the two paths on this rank (bit-exact), every frame in flight
+    same = all(bool(torch.equal(dev[i][2].cpu(), pin[i][2])) for i in range(depth))
 
     if rank == 0:
         px = W_IMG * H_IMG
@@ -262,7 +294,8 @@ def run_ours(args, rank, world):
             "metric": "Mdisparities/s", "value": value, "unit": "Mdisp/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "s16", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "frames_per_step_per_gpu": 1, "padded_width": Wp, "W1": stats["width1"],
+            "config": {"workload": WORKLOAD, "frames_per_step_per_gpu": 1, "frames_in_flight_per_gpu": depth,
+                       "single_frame_ms": ms_serial / args.steps, "padded_width": Wp, "W1": stats["width1"],
                        "l2": "inputs larger than L2 (C and S volumes %.2f GB each)" % (V / 1e9),
                        "parallelism": "frame-per-GPU x%d" % world, "device_vs_e2e_bit_exact": same,
                        "max_cost": stats["max_cost"], "out_of_domain": stats["out_of_domain"]},
@@ -281,7 +314,8 @@ def run_ours(args, rank, world):
         if world == 1 and not args.no_cpu:
             line["cpu_baseline"] = cpu_baseline_single()
         print(json.dumps(line), flush=True)
-    h.close()
+    for h in hs:
+        h.close()
     if world > 1:
         dist.destroy_process_group()
 
@@ -293,6 +327,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--pipeline-depth", type=int, default=2,
+                    help="frames in flight per GPU (one handle + stream each); 1 = strictly one frame at a time")
     ap.add_argument("--agg-impl", type=int, default=2, choices=[0, 1, 2],
                     help="0 per-direction launches, 1 fused sweeps, 2 fused sweeps + fused WTA (default)")
     args = ap.parse_args()

@@ -10,7 +10,7 @@ python - <<PY
 import json
 try:
     d = json.loads(open("gpurun_out/bench_$TAG.json").read().strip().splitlines()[-1])
-    print("value %.1f e2e %.1f frac %.3f stages %s" % (d["value"], d["e2e"]["value"], d["roofline"]["frac"], d["stage_ms_per_frame"]))
+    print("value %.1f e2e %.1f frac %.3f single_frame_ms %.2f stages %s" % (d["value"], d["e2e"]["value"], d["roofline"]["frac"], d["config"].get("single_frame_ms", 0), d["stage_ms_per_frame"]))
 except Exception as e:
     print("no json", e); print(open("gpurun_out/bench_$TAG.err").read()[-2000:])
 PY

@@ -29,7 +29,7 @@ void wsg_destroy(wsg_handle* h)
     cudaStreamSynchronize(h->stream);
     drain_profile(h);
     for (DevBuf* b : {&h->pre1, &h->pre2, &h->C, &h->S, &h->raw, &h->img1, &h->img2, &h->disp, &h->scalars, &h->bnd, &h->keys,
-                      &h->d1, &h->crop_l, &h->crop_r,
+                      &h->d1, &h->dbg, &h->crop_l, &h->crop_r,
                       &h->fa, &h->fb, &h->dispfull, &h->im_left, &h->im_right, &h->mask_l, &h->mask_r, &h->m_valid, &h->m_X, &h->m_Y,
                       &h->m_Z, &h->m_color, &h->m_labels, &h->m_scratch, &h->m_small, &h->m_out})
         if (b->p) cudaFree(b->p);
@@ -103,6 +103,13 @@ int wsg_check_sweep(wsg_handle* h)
     int flag = 0;
     CK(h, cudaMemcpyAsync(&flag, (int*)h->scalars.p + 1, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     CK(h, cudaStreamSynchronize(h->stream));
+    if (h->dbg.p && getenv("WSG_SWEEP_DEBUG")) {
+        std::vector<int> sm((h->plan.H + 7) / 8);
+        cudaMemcpy(sm.data(), h->dbg.p, sm.size() * sizeof(int), cudaMemcpyDeviceToHost);
+        fprintf(stderr, "[wsg] band->SM:");
+        for (size_t i = 0; i < sm.size(); ++i) fprintf(stderr, " %d", sm[i]);
+        fprintf(stderr, "\n");
+    }
     if (flag) { h->err = "fused aggregation sweep: hand-off wait overran (code " + std::to_string(flag) + ")"; return WSG_ERR_CUDA; }
     return WSG_OK;
 }
@@ -118,9 +125,10 @@ int wsg_run_sgbm(wsg_handle* h, const uint8_t* d_img1, const uint8_t* d_img2, si
     if ((rc = ensure(h, h->C, vol))) return rc;
     if ((rc = ensure(h, h->S, vol))) return rc;
     if ((rc = ensure(h, h->raw, npix * sizeof(int16_t)))) return rc;
-    if ((rc = ensure(h, h->scalars, 64))) return rc;
+    const size_t scal_bytes = (16 + 2 * WSG_SWEEP_TICKET_INTS) * sizeof(int);   // [0] max C, [1] sweep error, [16..] hand-out counters
+    if ((rc = ensure(h, h->scalars, scal_bytes))) return rc;
     int launches = 0;
-    CK(h, cudaMemsetAsync(h->scalars.p, 0, 64, h->stream));
+    CK(h, cudaMemsetAsync(h->scalars.p, 0, scal_bytes, h->stream));
     {
         StageTimer t(h, WSG_STAGE_PREFILTER, 2);
         launch_prefilter(d_img1, stride, (uint2*)h->pre1.p, pl, h->stream);
@@ -163,9 +171,16 @@ int wsg_run_sgbm(wsg_handle* h, const uint8_t* d_img1, const uint8_t* d_img2, si
         SweepScratch sc;
         sc.boundary = h->bnd.p;
         sc.err = (int*)h->scalars.p + 1;
+        sc.dbg = nullptr;
+        if (getenv("WSG_SWEEP_DEBUG")) {
+            if ((rc = ensure(h, h->dbg, 4096 * sizeof(int)))) return rc;
+            sc.dbg = (int*)h->dbg.p;
+        }
         sc.keys = (unsigned long long*)h->keys.p;
         sc.d1 = (int16_t*)h->d1.p;
-        int* tickets = (int*)h->scalars.p + 2;
+        int* tickets = (int*)h->scalars.p + 16;
+        if (h->num_sms == 0) CK(h, cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, h->device));
+        sc.num_sms = h->num_sms;
         auto next_epoch = [&]() { h->sweep_epoch = h->sweep_epoch % 3 + 1; return h->sweep_epoch; };
         const int last_mode = fused_wta ? 2 : 1;
         {
@@ -173,7 +188,7 @@ int wsg_run_sgbm(wsg_handle* h, const uint8_t* d_img1, const uint8_t* d_img2, si
             if (fused_wta) { launch_wta_reset(sc, pl, h->stream); launches += 1; }
             sc.ticket = tickets + 0; sc.epoch = next_epoch();
             launch_sweep((const int16_t*)h->C.p, (int16_t*)h->S.p, 0, 0, 4, pl, sc, h->stream);
-            sc.ticket = tickets + 1;
+            sc.ticket = tickets + WSG_SWEEP_TICKET_INTS;
             if (pl.mode == WSG_MODE_HH) {
                 sc.epoch = next_epoch();
                 launch_sweep((const int16_t*)h->C.p, (int16_t*)h->S.p, 1, last_mode, 4, pl, sc, h->stream);

@@ -1,0 +1,210 @@
+// Cost volume of cv::StereoSGBM (SURVEY.md Appendix A.2 + A.3; call site src/wass_stereo/wass_stereo.cpp:837),
+// wide-tile form: one CTA owns 128 columns x 32 disparities and marches down a band of rows.
+//
+// Three stages run CONCURRENTLY on different warps of the CTA, one image row apart, with one barrier per row:
+//   T   (group B)  unpack the prefilter records of row r+2 into broadcast tables (img1 side) and a reversed,
+//                  pre-negated table (img2 side) in shared memory
+//   P1  (19 warps) Birchfield-Tomasi pixel cost of row r+1 for 128+2*SW2 columns x 32 disparities, two disparities
+//                  per 32-bit register (VIADD.16x2 / VIADDMNMX.S16x2.RELU / VIMNMX.S16x2)
+//   P2  (group B)  row r: horizontal box sum (sliding over 4 adjacent columns per thread), a ring of 2*SH2+1 row sums in
+//                  shared memory for the vertical sliding sum, 16-byte stores of C
+// Compared with the 32x64 tile of cost_kernel (sgbm_kernels.cu) the halo columns recomputed by P1 drop from 75 % to
+// 19 % at the reference's window of 13, P1 runs at 95 % lane occupancy, and no stage waits for another.
+// Shared memory grows with the window: windows above 17 use cost_kernel.
+#include "sgbm_dev.cuh"
+
+namespace wsg {
+
+static constexpr int WXT = 128;            // output columns per CTA
+static constexpr int WDT = 32;             // disparities per CTA
+static constexpr int WDTP = 40;            // u16 per column in shared memory (80 B: kills the 4-column bank aliasing)
+static constexpr int WP1 = 19 * 32;        // stage P1 threads: (128 + 2*8 + ...) columns x 4 groups of 8 disparities
+static constexpr int WGB = 5 * 32;         // group B threads: stages T and P2
+static constexpr int WCT = WP1 + WGB;
+static constexpr int WRB = 256;            // rows per band
+static constexpr int WMAXSW = 8;           // windows up to 17
+static constexpr int WNCOL = WXT + 2 * WMAXSW;
+static constexpr int WVT = 180;            // entries of the reversed img2 tables (>= WNCOL + WDT + 1, even)
+static constexpr int WRVPAD = 4;
+static constexpr int WRV = 2 * 8 * WVT + WRVPAD;   // s16 per img2 table set (two copies, one element apart)
+
+struct WideSmem { int pd, uu, rv, ring, total; };
+__host__ __device__ inline WideSmem wide_layout(int SH2)
+{
+    WideSmem s;
+    s.pd = 0;                                          // u16 [2][WNCOL][WDTP]
+    s.uu = s.pd + 2 * WNCOL * WDTP * 2;                // u32 [2][WNCOL][8]
+    s.rv = s.uu + 2 * WNCOL * 8 * 4;                   // s16 [2][WRV]
+    s.ring = (s.rv + 2 * WRV * 2 + 15) & ~15;          // u16 [2*SH2+1][WXT][WDTP]
+    s.total = s.ring + (2 * SH2 + 1) * WXT * WDTP * 2;
+    return s;
+}
+
+bool cost_wide_supported(const SgbmPlan& p) { return p.SW2 <= WMAXSW && p.SH2 <= WMAXSW && p.Dp % WDT == 0; }
+
+__global__ void __launch_bounds__(WCT, 1) cost_wide_kernel(const uint2* __restrict__ pre1, const uint2* __restrict__ pre2,
+                                                           int16_t* __restrict__ C, int* __restrict__ maxC, SgbmPlan p)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    const WideSmem L = wide_layout(p.SH2);
+    uint16_t* pd = reinterpret_cast<uint16_t*>(smem + L.pd);
+    unsigned* uu = reinterpret_cast<unsigned*>(smem + L.uu);
+    int16_t* rv = reinterpret_cast<int16_t*>(smem + L.rv);
+    uint16_t* ring = reinterpret_cast<uint16_t*>(smem + L.ring);
+
+    const int tid = threadIdx.x;
+    const int x0 = blockIdx.x * WXT;          // first output column (W1 space)
+    const int d0 = blockIdx.y * WDT;          // first disparity slot (relative to minD)
+    const int y0 = blockIdx.z * WRB;
+    const int y1 = min(y0 + WRB, p.H);
+    const int ncol = WXT + 2 * p.SW2;
+    const int NR = 2 * p.SH2 + 1;
+    const int win = 2 * p.SW2 + 1;
+    const int xb = p.minX1 + min(max(x0 + WXT - 1 + p.SW2, 0), p.W1 - 1);   // image x of the last (clamped) halo column
+    const int vtop = xb - (p.minD + d0);      // largest img2 column touched; table index i <-> x' = vtop - i
+    const int nsteps = (y1 - y0) + 2 * p.SH2;
+
+    // stage P2 role (group B, first 128 threads): columns 4*c4..+3, disparities d0+8g..+7
+    const int tb = tid - WP1;
+    const int g = tb & 3, c4 = tb >> 2;
+    const bool real_vec = (d0 + 8 * g) < p.D;
+    unsigned acc[4][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}, {0, 0, 0, 0}, {0, 0, 0, 0}};
+    int vmax = 0;
+
+    for (int s = 0; s < nsteps + 2; ++s) {
+        if (tid < WP1) {
+            // ---------------- P1: pixel cost of row-step s-1 from tables[(s-1)&1] into pd[(s-1)&1]
+            const int rs = s - 1;
+            if (rs >= 0 && rs < nsteps && tid < ncol * 4) {
+                const int b = rs & 1;
+                const int cc = tid >> 2, gg = tid & 3;
+                uint4 out = make_uint4(0, 0, 0, 0);
+                if (d0 + 8 * gg < p.D) {
+                    const int xx = p.minX1 + min(max(x0 - p.SW2 + cc, 0), p.W1 - 1);
+                    const int i0 = (xb - xx) + 8 * gg;
+                    const int par = i0 & 1;
+                    const unsigned* rvw = reinterpret_cast<const unsigned*>(rv + b * WRV + par * (8 * WVT + WRVPAD)) + ((i0 - par) >> 1);
+                    const uint4 ua = *reinterpret_cast<const uint4*>(uu + (b * WNCOL + cc) * 8);
+                    const uint4 ub = *reinterpret_cast<const uint4*>(uu + (b * WNCOL + cc) * 8 + 4);
+                    unsigned res[4];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const unsigned V0 = rvw[0 * (WVT / 2) + k], nV0 = rvw[1 * (WVT / 2) + k];
+                        const unsigned Vl0 = rvw[2 * (WVT / 2) + k], nVh0 = rvw[3 * (WVT / 2) + k];
+                        const unsigned V1 = rvw[4 * (WVT / 2) + k], nV1 = rvw[5 * (WVT / 2) + k];
+                        const unsigned Vl1 = rvw[6 * (WVT / 2) + k], nVh1 = rvw[7 * (WVT / 2) + k];
+                        // per channel: c0 = max(0,u-vhi,vlo-u), c1 = max(0,v-uhi,ulo-v), c = min(c0,c1)
+                        const unsigned e0 = __vimax_s16x2_relu(__vadd2(ua.x, nVh0), __vadd2(Vl0, ua.y));
+                        const unsigned e1 = __vimax_s16x2_relu(__vadd2(V0, ua.w), __vadd2(ua.z, nV0));
+                        const unsigned ca = __vmins2(e0, e1);
+                        const unsigned f0 = __vimax_s16x2_relu(__vadd2(ub.x, nVh1), __vadd2(Vl1, ub.y));
+                        const unsigned f1 = __vimax_s16x2_relu(__vadd2(V1, ub.w), __vadd2(ub.z, nV1));
+                        const unsigned cb = __vmins2(f0, f1);
+                        res[k] = ca + ((cb >> 2) & 0x3FFF3FFFu);
+                    }
+                    out = make_uint4(res[0], res[1], res[2], res[3]);
+                }
+                *reinterpret_cast<uint4*>(pd + (b * WNCOL + cc) * WDTP + gg * 8) = out;
+            }
+        } else {
+            // ---------------- T: tables of row-step s into tables[s&1]
+            if (s < nsteps) {
+                const int b = s & 1;
+                const int r = y0 - p.SH2 + s;
+                const int yy = min(max(r, 0), p.H - 1);
+                for (int e = tb; e < ncol; e += WGB) {
+                    const int xx = p.minX1 + min(max(x0 - p.SW2 + e, 0), p.W1 - 1);
+                    const uint2 q = pre1[(size_t)yy * p.W + xx];
+                    const int u0 = q.x & 255, l0 = (q.x >> 8) & 255, h0 = (q.x >> 16) & 255;
+                    const int u1 = q.x >> 24, l1 = q.y & 255, h1 = (q.y >> 8) & 255;
+                    auto bc = [](int v) -> unsigned { return ((unsigned)v & 0xFFFFu) * 0x10001u; };
+                    uint4* o = reinterpret_cast<uint4*>(uu + (b * WNCOL + e) * 8);
+                    o[0] = make_uint4(bc(u0), bc(-u0), bc(l0), bc(-h0));
+                    o[1] = make_uint4(bc(u1), bc(-u1), bc(l1), bc(-h1));
+                }
+                for (int e = tb; e < WVT; e += WGB) {
+                    const int xp = min(max(vtop - e, 0), p.W - 1);
+                    const uint2 q = pre2[(size_t)yy * p.W + xp];
+                    const int v0 = q.x & 255, l0 = (q.x >> 8) & 255, h0 = (q.x >> 16) & 255;
+                    const int v1 = q.x >> 24, l1 = q.y & 255, h1 = (q.y >> 8) & 255;
+                    const int16_t val[8] = {(int16_t)v0, (int16_t)-v0, (int16_t)l0, (int16_t)-h0,
+                                            (int16_t)v1, (int16_t)-v1, (int16_t)l1, (int16_t)-h1};
+                    int16_t* t = rv + b * WRV;
+#pragma unroll
+                    for (int qn = 0; qn < 8; ++qn) {
+                        t[(0 * 8 + qn) * WVT + e] = val[qn];                              // copy A: rv[i]
+                        if (e > 0) t[WRVPAD + (1 * 8 + qn) * WVT + e - 1] = val[qn];      // copy B: rv[i+1]
+                    }
+                }
+            }
+            // ---------------- P2: box sums of row-step s-2 from pd[(s-2)&1]
+            const int idx = s - 2;
+            if (idx >= 0 && tb < 128) {
+                const int b = idx & 1;
+                const int r = y0 - p.SH2 + idx;
+                unsigned hs[4] = {0, 0, 0, 0};
+                uint4 head[3];
+                const uint16_t* prow = pd + (b * WNCOL + c4 * 4) * WDTP + g * 8;
+#pragma unroll
+                for (int i = 0; i < 3; ++i) {   // the three columns that leave the window while sliding
+                    head[i] = *reinterpret_cast<const uint4*>(prow + i * WDTP);
+                    if (i < win) {
+                        hs[0] = __vadd2(hs[0], head[i].x); hs[1] = __vadd2(hs[1], head[i].y);
+                        hs[2] = __vadd2(hs[2], head[i].z); hs[3] = __vadd2(hs[3], head[i].w);
+                    }
+                }
+                for (int i = 3; i < win; ++i) {
+                    const uint4 v = *reinterpret_cast<const uint4*>(prow + i * WDTP);
+                    hs[0] = __vadd2(hs[0], v.x); hs[1] = __vadd2(hs[1], v.y);
+                    hs[2] = __vadd2(hs[2], v.z); hs[3] = __vadd2(hs[3], v.w);
+                }
+#pragma unroll
+                for (int cc = 0; cc < 4; ++cc) {
+                    const int col = c4 * 4 + cc;
+                    if (cc > 0) {
+                        const uint4 vn = *reinterpret_cast<const uint4*>(prow + (win - 1 + cc) * WDTP);
+                        const uint4 vo = head[cc - 1];
+                        hs[0] = __vsub2(__vadd2(hs[0], vn.x), vo.x); hs[1] = __vsub2(__vadd2(hs[1], vn.y), vo.y);
+                        hs[2] = __vsub2(__vadd2(hs[2], vn.z), vo.z); hs[3] = __vsub2(__vadd2(hs[3], vn.w), vo.w);
+                    }
+                    uint4* slot = reinterpret_cast<uint4*>(ring + ((idx % NR) * WXT + col) * WDTP + g * 8);
+                    unsigned* ac = acc[cc];
+                    if (idx >= NR) {
+                        const uint4 o = *slot;
+                        ac[0] = __vsub2(ac[0], o.x); ac[1] = __vsub2(ac[1], o.y);
+                        ac[2] = __vsub2(ac[2], o.z); ac[3] = __vsub2(ac[3], o.w);
+                    }
+                    *slot = make_uint4(hs[0], hs[1], hs[2], hs[3]);
+                    ac[0] = __vadd2(ac[0], hs[0]); ac[1] = __vadd2(ac[1], hs[1]);
+                    ac[2] = __vadd2(ac[2], hs[2]); ac[3] = __vadd2(ac[3], hs[3]);
+                    if (idx >= 2 * p.SH2 && x0 + col < p.W1) {
+                        const int y = r - p.SH2;
+                        const int j = (d0 >> 3) + g;
+                        int16_t* dst = C + ((size_t)y * p.W1 + (x0 + col)) * p.Dp + vec_slot(j, p.NL, p.K) * 8;
+                        if (real_vec) {
+                            *reinterpret_cast<uint4*>(dst) = make_uint4(ac[0], ac[1], ac[2], ac[3]);
+                            const unsigned m = __vmaxs2(__vmaxs2(ac[0], ac[1]), __vmaxs2(ac[2], ac[3]));
+                            vmax = max(vmax, max((int)(short)(m & 0xFFFF), (int)(short)(m >> 16)));
+                        } else {
+                            *reinterpret_cast<uint4*>(dst) = make_uint4(0, 0, 0, 0);
+                        }
+                    }
+                }
+            }
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) vmax = max(vmax, __shfl_xor_sync(FULL, vmax, o));
+    if ((tid & 31) == 0 && vmax > 0) atomicMax(maxC, vmax);
+}
+
+void launch_cost_wide(const uint2* pre1, const uint2* pre2, int16_t* C, int* maxC, const SgbmPlan& p, cudaStream_t st)
+{
+    const int smem = wide_layout(p.SH2).total;
+    cudaFuncSetAttribute(cost_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    dim3 g((p.W1 + WXT - 1) / WXT, p.Dp / WDT, (p.H + WRB - 1) / WRB);
+    cost_wide_kernel<<<g, WCT, smem, st>>>(pre1, pre2, C, maxC, p);
+}
+
+}  // namespace wsg

@@ -25,8 +25,9 @@ struct wsg_handle {
     std::string err;
     // SGBM arena
     DevBuf pre1, pre2, C, S, raw, img1, img2, disp, scalars;
-    DevBuf bnd, keys, d1;               // fused sweeps: band hand-off buffer, right-view keys, left-view map
+    DevBuf bnd, keys, d1, dbg;               // fused sweeps: band hand-off buffer, right-view keys, left-view map
     int agg_impl = WSG_AGG_SWEEPS_WTA;
+    int num_sms = 0;
     int sweep_epoch = 0;                // 1..3 after the first sweep
     int bnd_H = 0, bnd_W1 = 0, bnd_K = 0;   // geometry the hand-off buffer was last used with
     SgbmPlan plan{};

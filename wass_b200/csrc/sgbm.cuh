@@ -33,12 +33,18 @@ void launch_aggregate_dir(const int16_t* C, int16_t* S, int dir, bool first, con
 void launch_wta(const int16_t* S, int16_t* raw, const SgbmPlan& p, cudaStream_t st);
 void launch_median3(const int16_t* src, int16_t* dst, int rows, int cols, cudaStream_t st);
 int cost_smem_bytes(const SgbmPlan& p);
+// wide-tile cost kernel (cost_kernels.cu): windows up to 17; launch_cost picks it unless WSG_COST_IMPL=0
+bool cost_wide_supported(const SgbmPlan& p);
+void launch_cost_wide(const uint2* pre1, const uint2* pre2, int16_t* C, int* maxC, const SgbmPlan& p, cudaStream_t st);
 
 // fused wavefront sweeps (sweep_kernels.cu)
+static constexpr int WSG_SWEEP_TICKET_INTS = 256;
 struct SweepScratch {
     void* boundary;             // band-to-band state hand-off, sweep_boundary_bytes()
-    int* ticket;                // zeroed band counter of THIS launch
+    int* ticket;                // zeroed hand-out counters of THIS launch: WSG_SWEEP_TICKET_INTS ints
+    int num_sms;
     int* err;                   // raised if a bounded wait overran
+    int* dbg;                   // optional [nbands]: SM id per band (WSG_SWEEP_DEBUG=1), else null
     int epoch;                  // 1..3, changes with every 4-direction sweep that uses `boundary`
     unsigned long long* keys;   // [H][W] right-view map as packed keys (fused WTA)
     int16_t* d1;                // [H][W] left-view disparity before the LR check (fused WTA)

@@ -10,6 +10,7 @@
 // All arithmetic is 16-bit integer, two disparities per 32-bit register, on the native packed
 // instructions of sm_100a (VIADD.16x2, VIMNMX.S16x2, VIMNMX3.S16x2, VIADDMNMX.{S,U}16x2).
 #include "sgbm_dev.cuh"
+#include <cstdlib>
 
 namespace wsg {
 
@@ -229,6 +230,13 @@ __global__ void __launch_bounds__(CT) cost_kernel(const uint2* __restrict__ pre1
 void launch_cost(const uint2* pre1, const uint2* pre2, int16_t* C, int* maxC, const SgbmPlan& p, cudaStream_t st,
                  int* launches)
 {
+    static int impl = -1;
+    if (impl < 0) { const char* e = getenv("WSG_COST_IMPL"); impl = e ? atoi(e) : 1; }
+    if (impl != 0 && cost_wide_supported(p)) {
+        launch_cost_wide(pre1, pre2, C, maxC, p, st);
+        if (launches) *launches += 1;
+        return;
+    }
     const int smem = cost_smem_bytes(p);
     cudaFuncSetAttribute(cost_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     dim3 g((p.W1 + XT - 1) / XT, p.Dp / DT, (p.H + RB - 1) / RB);

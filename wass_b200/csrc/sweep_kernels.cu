@@ -22,25 +22,36 @@
 // All spin loops are bounded: on overrun the kernel raises an error flag and runs to completion.
 #include "sgbm_dev.cuh"
 #include <algorithm>
+#include <cstdlib>
 
 namespace wsg {
 
 static constexpr int SW_R = 8;             // rows (compute warps) per CTA
 static constexpr int SW_THREADS = (SW_R + 1) * 32;
-static constexpr int SW_HD = 4;            // boundary columns the helper polls per round trip (<= NS/2)
 static constexpr unsigned TAGBITS = 0x80008000u;
 static constexpr int SPIN_LIMIT = 1 << 22;
 
-template <int K> struct SweepCfg {
-    static constexpr int NS = K == 1 ? 8 : 6;                 // state ring depth in columns
+// Shared-memory budget of a CTA.  CFG 0 ("lean", 104 KB at K == 1): two CTAs fit one SM, so the sweep of another frame
+// (another stream) can fill the SMs this sweep's wavefront has not reached yet or has already left.  CFG 1 ("deep",
+// 200 KB): one CTA per SM, deeper rings and prefetch -- the better choice for one frame at a time.  CFG 2/3: experiments.
+template <int K, int CFG> struct SweepCfg {
+    static constexpr bool LEAN = K == 1 && (CFG == 0 || CFG == 2);
+    static constexpr int NS = K != 1 ? 6 : (LEAN ? 5 : 8);    // state ring depth in columns
     static constexpr int SLOT_V = 3 * K * 32;                 // uint4 per ring slot: [dir][k][lane]
     static constexpr int RING_V = NS * SLOT_V;
-    static constexpr int PFD = K == 1 ? 12 : 4;               // pixels of C (and S) in flight per row (cp.async staging)
+    static constexpr int PFD = K != 1 ? 4 : (CFG == 1 ? 12 : 6);   // pixels of C in flight per row (cp.async staging)
+    static constexpr int PFS = K == 1 && CFG == 1 ? 12 : 4;   // pixels of S in flight per row
     static constexpr int PIX_V = K * 32;                      // uint4 per pixel
     static constexpr int RINGS_V = SW_R * RING_V;             // smem map (uint4 units): state rings
     static constexpr int SCR_V = SW_R * PIX_V;                //   per-warp WTA scratch
-    static constexpr int STAGE_V = SW_R * PFD * PIX_V;        //   per-warp staging of the C stream (and again for S)
-    static constexpr int SMEM = (RINGS_V + SCR_V + 2 * STAGE_V) * 16;
+    static constexpr int STAGEC_V = SW_R * PFD * PIX_V;       //   per-warp staging of the C stream
+    static constexpr int STAGES_V = SW_R * PFS * PIX_V;       //   per-warp staging of the S stream
+    static constexpr int SMEM_USED = (RINGS_V + SCR_V + STAGEC_V + STAGES_V) * 16;
+    static constexpr int CTAS_PER_SM = K == 1 && CFG == 0 ? 2 : 1;
+    static constexpr int SMEM = CTAS_PER_SM == 1 && SMEM_USED < 120 * 1024 ? 120 * 1024 : SMEM_USED;   // (forces 1 CTA/SM)
+    // boundary columns the helper polls per round trip.  At most NS-2: it may only overwrite ring-0 slots of columns
+    // its consumer has completed, and the consumer can complete nothing beyond the columns already published.
+    static constexpr int HD = NS - 2 < 4 ? NS - 2 : 4;
 };
 
 // 16-byte asynchronous global->shared copy (L2 only), one per lane; completion is tracked per thread in commit groups
@@ -58,13 +69,15 @@ struct SweepArgs {
     unsigned P1p, P2mP1p;
     unsigned tag;            // epoch tag of this launch (bits 15 and 31)
     uint4* bnd;              // [nbands-1][W1][3][K][32]
-    int* ticket;
+    int* ticket;             // [0] bands handed out, [1] bands handed out beyond n0, [2..] CTAs arrived per SM
+    int n0;                  // min(#SMs, #bands)
     int* err;
+    int* dbg;                // optional: SM id of every band (placement diagnostics), or null
     // winner-take-all (MODE 2)
     unsigned long long* keys;   // [H][W]  (minS, W1-1-x, d) of the best match that lands on x2 (A.5)
     int16_t* d1;                // [H][W]  left-view disparity before the LR check
     int minD, minX1, uniq, INVALID;
-    float urcp;                 // 1 / (100 - uniq)
+    unsigned umagic;            // ceil(2^32 / (100 - uniq))
 };
 
 __device__ __forceinline__ uint4 ld_volatile(const uint4* p)
@@ -101,23 +114,22 @@ __device__ __forceinline__ void wait_prog(volatile int* flag, int need, int& see
 }
 
 // A.5 for one pixel held by one warp: s = final S, 8*K consecutive disparities per lane (a lane is all real or all pad:
-// numDisparities is a multiple of 16).  Needs 0 <= uniquenessRatio < 100 (the host routes anything else to wta_kernel).
+// numDisparities is a multiple of 16); `scratch` holds the same S in shared memory, lane-major.  Needs
+// 0 <= uniquenessRatio < 100 (the host routes anything else to wta_kernel).
 //   winner      first d with minimal S: warp minimum of the 32-bit keys (S << 16 | d)
 //   uniqueness  reject iff some d outside {best-1,best,best+1} has S(d)*(100-uniq) < minS*100, i.e. S(d) <= Tm with
 //               Tm = floor((minS*100-1)/(100-uniq)).  Counted instead of searched: #(S <= Tm) over all d, by a packed
-//               subtract whose sign bits are the comparison results, against the same count inside the window, which
-//               lane 0 gets from the two neighbours it needs for the parabola anyway.
+//               subtract whose sign bits are the comparison results, against the same count inside the window.
+// Everything after the two warp reductions is warp-uniform and branch-free (only the two global writes are predicated),
+// so the caller can run it one pixel late, interleaved with the next pixel's path steps: its long dependency chain
+// (reduce -> threshold -> count -> reduce -> parabola) then costs issue slots but no latency.
 template <int K, bool HASPAD>
 __device__ __forceinline__ void wta_pixel(const unsigned (&s)[4 * K], int l, int xh, int y, const SweepArgs& a,
-                                          int16_t* scratch)
+                                          const int16_t* scratch, bool commit)
 {
     constexpr int NV8 = 8 * K;
     const int dlane = l * NV8;
     const bool padlane = HASPAD && dlane >= a.D;
-    // stage this pixel's S for lane 0 (previous pixel's reads are over: lane 0 passed the __syncwarp below)
-#pragma unroll
-    for (int k = 0; k < K; ++k)
-        reinterpret_cast<uint4*>(scratch)[l * K + k] = make_uint4(s[4 * k], s[4 * k + 1], s[4 * k + 2], s[4 * k + 3]);
     unsigned kmin = 0xFFFFFFFFu;
 #pragma unroll
     for (int e = 0; e < 4 * K; ++e) {
@@ -128,53 +140,47 @@ __device__ __forceinline__ void wta_pixel(const unsigned (&s)[4 * K], int l, int
     if (padlane) kmin = 0xFFFFFFFFu;
     kmin = __reduce_min_sync(FULL, kmin);
     const int minS = (int)(kmin >> 16), best = (int)(kmin & 0xFFFFu);
-    const int udiv = 100 - a.uniq;
-    const int n = minS * 100 - 1;                        // < 3.3e6: exact in float
-    int Tm = n < 0 ? -1 : (int)((float)n * a.urcp);
-    if (n >= 0) { if ((Tm + 1) * udiv <= n) ++Tm; else if (Tm * udiv > n) --Tm; }
+    const int n = minS * 100 - 1;                                   // < 2^22
+    const int Tm = n < 0 ? -1 : (int)__umulhi((unsigned)n, a.umagic);   // floor(n / (100-uniq)), exact for n < 2^22
     // packed count of S <= Tm: (0x8000 + T - S) keeps bit 15 iff T >= S (S, T <= 0x7fff: no borrow between the halves)
     const unsigned T2 = ((unsigned)min(max(Tm, 0), 32767) | 0x8000u) * 0x10001u;
     unsigned bits = 0;
 #pragma unroll
-    for (int e = 0; e < 4 * K; ++e) bits |= ((T2 - s[e]) & 0x80008000u) >> (e & 15);
+    for (int e = 0; e < 4 * K; ++e) bits |= ((T2 - s[e]) & 0x80008000u) >> e;
     int cnt = __popc(bits);
     if (padlane || Tm < 0) cnt = 0;
     const int total = __reduce_add_sync(FULL, cnt);
-    __syncwarp();
-    if (l == 0) {
-        int sm = 0, sp = 0, inwin = minS <= Tm;
-        const bool inner = best > 0 && best < a.D - 1;
-        if (best > 0) { sm = scratch[best - 1]; inwin += sm <= Tm; }
-        if (best < a.D - 1) { sp = scratch[best + 1]; inwin += sp <= Tm; }
-        if (total <= inwin) {
-            const int x = xh + a.minX1;
-            const int x2 = x - best - a.minD;
-            const unsigned long long k64 = ((unsigned long long)minS << 40) |
-                                           ((unsigned long long)(a.W1 - 1 - xh) << 16) | (unsigned long long)best;
-            atomicMin(a.keys + (size_t)y * a.W + x2, k64);
-            int dd = best * 16;
-            if (inner) {
-                // trunc(((sm-sp)*16 + den) / (2*den)): |numerator| < 2^24, so a float quotient is off by at most one
-                const int den = max(sm + sp - 2 * minS, 1), den2 = 2 * den;
-                const int num = (sm - sp) * 16 + den, an = abs(num);
-                int q = (int)__fdividef((float)an, (float)den2);
-                const int rem = an - q * den2;
-                q += rem >= den2 ? 1 : (rem < 0 ? -1 : 0);
-                dd += num < 0 ? -q : q;
-            }
-            a.d1[(size_t)y * a.W + x] = (int16_t)(dd + a.minD * 16);
-        }
+    // the winner's neighbours (clamped addresses; the values only count where they exist)
+    const bool hasm = best > 0, hasp = best < a.D - 1;
+    const int sm = scratch[max(best - 1, 0)], sp = scratch[min(best + 1, a.D - 1)];
+    const int inwin = (minS <= Tm) + (hasm && sm <= Tm) + (hasp && sp <= Tm);
+    int dd = best * 16;
+    {
+        // trunc(((sm-sp)*16 + den) / (2*den)): |numerator| < 2^24, so an approximate float quotient is off by at most one
+        const int den = max(sm + sp - 2 * minS, 1), den2 = 2 * den;
+        const int num = (sm - sp) * 16 + den, an = abs(num);
+        int q = (int)__fdividef((float)an, (float)den2);
+        const int rem = an - q * den2;
+        q += rem >= den2 ? 1 : (rem < 0 ? -1 : 0);
+        if (hasm && hasp) dd += num < 0 ? -q : q;
     }
-    __syncwarp();
+    if (commit && total <= inwin && l == 0) {
+        const int x = xh + a.minX1;
+        const int x2 = x - best - a.minD;
+        const unsigned long long k64 = ((unsigned long long)minS << 40) |
+                                       ((unsigned long long)(a.W1 - 1 - xh) << 16) | (unsigned long long)best;
+        atomicMin(a.keys + (size_t)y * a.W + x2, k64);
+        a.d1[(size_t)y * a.W + x] = (int16_t)(dd + a.minD * 16);
+    }
 }
 
 // MODE 0: S = sum of this sweep's L (no read);  1: S += sum (read-modify-write);  2: S += sum, then WTA (S not written)
 // NDIR 4: full sweep;  1: horizontal direction only (the fifth path of MODE_SGBM): rows are independent.
-template <int K, int MODE, int NDIR, bool HASPAD>
-__global__ void __launch_bounds__(SW_THREADS, 1)
+template <int K, int MODE, int NDIR, bool HASPAD, int CFG>
+__global__ void __launch_bounds__(SW_THREADS, SweepCfg<K, CFG>::CTAS_PER_SM)
 sweep_kernel(const uint4* __restrict__ C, uint4* __restrict__ S, SweepArgs a)
 {
-    using Cfg = SweepCfg<K>;
+    using Cfg = SweepCfg<K, CFG>;
     constexpr int NR = 4 * K;
     constexpr int NS = Cfg::NS;
     extern __shared__ __align__(16) uint4 smem[];
@@ -182,7 +188,25 @@ sweep_kernel(const uint4* __restrict__ C, uint4* __restrict__ S, SweepArgs a)
     __shared__ int s_band;
 
     const int tid = threadIdx.x, warp = tid >> 5, l = tid & 31;
-    if (tid == 0) s_band = atomicAdd(a.ticket, 1);
+    if (tid == 0) {
+        // Band hand-out.  Bands must start in (roughly) increasing order, and the ~W1/20 bands that are active at the
+        // same time should sit on different SMs.  With two CTAs per SM the hardware fills an SM's second slot right
+        // after its first, so plain arrival order would pair neighbouring bands on one SM and leave half the SMs
+        // idle.  Hence: the first CTA to arrive on an SM ("primary") takes the next of the first n0 = #SMs bands; later
+        // arrivals wait (bounded) until those are gone and then take the rest in order.  Every band is handed out
+        // exactly once, and a band is only handed out after all lower ones: nothing depends on how CTAs were placed.
+        unsigned sm;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(sm));
+        const int slot = atomicAdd(a.ticket + 2 + min(sm, 250u), 1);
+        if (slot != 0) {
+            const long long t0 = clock64();
+            while (*reinterpret_cast<volatile int*>(a.ticket) < a.n0 && clock64() - t0 < 40000) __nanosleep(100);
+        }
+        int band = atomicAdd(a.ticket, 1);
+        if (band >= a.n0) band = a.n0 + atomicAdd(a.ticket + 1, 1);
+        s_band = band;
+        if (a.dbg) a.dbg[band] = (int)sm;
+    }
     if (tid <= SW_R) prog[tid] = 0;
     if (NDIR == 4)
         for (int i = tid; i < Cfg::RINGS_V; i += SW_THREADS) smem[i] = make_uint4(0, 0, 0, 0);
@@ -195,20 +219,20 @@ sweep_kernel(const uint4* __restrict__ C, uint4* __restrict__ S, SweepArgs a)
         if (NDIR == 1 || band == 0) return;
         const uint4* src = a.bnd + (size_t)(band - 1) * bstride + l;
         uint4* ring = smem;                                // ring 0
-        uint4 hb[SW_HD][3 * K];
+        uint4 hb[Cfg::HD][3 * K];
         int seen = 0, spins = 0;
-        // Poll a window of SW_HD columns per round trip to L2 and forward its valid prefix: the throughput adapts to the
-        // producer (up to SW_HD columns per round trip) and the band ends up trailing it by about one window.
+        // Poll a window of Cfg::HD columns per round trip to L2 and forward its valid prefix: the throughput adapts to the
+        // producer (up to Cfg::HD columns per round trip) and the band ends up trailing it by about one window.
         for (int x = 0; x < a.W1;) {
 #pragma unroll
-            for (int u = 0; u < SW_HD; ++u)
+            for (int u = 0; u < Cfg::HD; ++u)
 #pragma unroll
                 for (int j = 0; j < 3 * K; ++j)
                     hb[u][j] = ld_volatile(src + (size_t)min(x + u, a.W1 - 1) * Cfg::SLOT_V + j * 32);
             int n = 0;
             bool prefix = true;
 #pragma unroll
-            for (int u = 0; u < SW_HD; ++u) {
+            for (int u = 0; u < Cfg::HD; ++u) {
                 bool ok = x + u < a.W1;
 #pragma unroll
                 for (int j = 0; j < 3 * K; ++j)
@@ -229,7 +253,7 @@ sweep_kernel(const uint4* __restrict__ C, uint4* __restrict__ S, SweepArgs a)
             // ring 0 slot c is free once warp 0 has completed column c-NS+1
             wait_prog(&prog[1], x + n - 1 - NS + 2, seen, a.err);
 #pragma unroll
-            for (int u = 0; u < SW_HD; ++u) {
+            for (int u = 0; u < Cfg::HD; ++u) {
                 if (u < n) {
                     uint4* dst = ring + ((x + u) % NS) * Cfg::SLOT_V + l;
 #pragma unroll
@@ -270,7 +294,7 @@ sweep_kernel(const uint4* __restrict__ C, uint4* __restrict__ S, SweepArgs a)
     uint4* bnd_out = a.bnd + (size_t)band * bstride + l;            // only used when out_mode == 2
     int16_t* scratch = reinterpret_cast<int16_t*>(smem + Cfg::RINGS_V + (size_t)r * Cfg::PIX_V);
     uint4* stageC = smem + Cfg::RINGS_V + Cfg::SCR_V + (size_t)r * Cfg::PFD * Cfg::PIX_V + l;
-    uint4* stageS = stageC + Cfg::STAGE_V;
+    uint4* stageS = smem + Cfg::RINGS_V + Cfg::SCR_V + Cfg::STAGEC_V + (size_t)r * Cfg::PFS * Cfg::PIX_V + l;
     volatile int* prog_in = &prog[r];
     volatile int* prog_me = &prog[r + 1];
     volatile int* prog_next = &prog[r + 2 <= SW_R ? r + 2 : SW_R];
@@ -282,21 +306,25 @@ sweep_kernel(const uint4* __restrict__ C, uint4* __restrict__ S, SweepArgs a)
 
     // one commit group per pixel, PFD pixels ahead; each lane copies and later reads back its own 16 bytes
     const unsigned stC = (unsigned)__cvta_generic_to_shared(stageC), stS = (unsigned)__cvta_generic_to_shared(stageS);
+    static_assert(Cfg::PFS <= Cfg::PFD, "the S stream rides in the commit groups of the C stream");
     for (int i = 0; i < Cfg::PFD; ++i) {
         if (i < a.W1) {
 #pragma unroll
             for (int k = 0; k < K; ++k) {
                 cp_async16(stC + (i * Cfg::PIX_V + k * 32) * 16, cpf + k * 32);
-                if (MODE != 0) cp_async16(stS + (i * Cfg::PIX_V + k * 32) * 16, spf + k * 32);
+                if (MODE != 0 && i < Cfg::PFS) cp_async16(stS + (i * Cfg::PIX_V + k * 32) * 16, spf + k * 32);
             }
         }
         cp_async_commit();
-        cpf += dstep; spf += dstep;
+        cpf += dstep;
+        if (i < Cfg::PFS) spf += dstep;
     }
 
     // The horizontal direction runs ONE PIXEL AHEAD of the three directions that come from the row above: its step for
     // pixel x+1 and their steps for pixel x are four independent dependency chains in one basic block.
-    unsigned Nh[NR], Cc[NR], Lh[NR];
+    unsigned Nh[NR], Cc[NR], Lh[NR], vsp[NR];
+#pragma unroll
+    for (int j = 0; j < NR; ++j) vsp[j] = 0;
 #pragma unroll
     for (int j = 0; j < NR; ++j) Nh[j] = 0;
     cp_async_wait<Cfg::PFD - 1>();
@@ -307,7 +335,7 @@ sweep_kernel(const uint4* __restrict__ C, uint4* __restrict__ S, SweepArgs a)
     }
     agg_step<32, NR, HASPAD>(Nh, Cc, Lh, l, a.P1p, a.P2mP1p, padm);
 
-    int pslot = 0;                                  // x % PFD
+    int pslot = 0, sslot = 0;                       // x % PFD, x % PFS
     for (int x = 0; x < a.W1; ++x) {                // logical column
         const int nslot = pslot + 1 == Cfg::PFD ? 0 : pslot + 1;
         unsigned Cn[NR], Lhn[NR], vs[NR], v[3][NR], Nd[3][NR];
@@ -321,9 +349,11 @@ sweep_kernel(const uint4* __restrict__ C, uint4* __restrict__ S, SweepArgs a)
 #pragma unroll
             for (int j = 0; j < NR; ++j) vs[j] = Lh[j];
         } else {
+            // S(x) was committed PFS iterations ago; PFD + x groups exist by now
+            if (Cfg::PFS < Cfg::PFD - 1) cp_async_wait<Cfg::PFS - 1>();
 #pragma unroll
             for (int k = 0; k < K; ++k) {
-                const uint4 sv = stageS[pslot * Cfg::PIX_V + k * 32];
+                const uint4 sv = stageS[sslot * Cfg::PIX_V + k * 32];
                 vs[4 * k] = __viaddmin_u16x2(sv.x, Lh[4 * k], SAT2);
                 vs[4 * k + 1] = __viaddmin_u16x2(sv.y, Lh[4 * k + 1], SAT2);
                 vs[4 * k + 2] = __viaddmin_u16x2(sv.z, Lh[4 * k + 2], SAT2);
@@ -351,7 +381,8 @@ sweep_kernel(const uint4* __restrict__ C, uint4* __restrict__ S, SweepArgs a)
                     }
                 }
             }
-            // ---- four independent chains
+            // ---- independent chains: the winner-take-all of the PREVIOUS pixel, and the four path steps
+            if (MODE == 2) wta_pixel<K, HASPAD>(vsp, l, a.flip ? a.W1 - x : x - 1, yp, a, scratch, x > 0);
             agg_step<32, NR, HASPAD>(Nh, Cn, Lhn, l, a.P1p, a.P2mP1p, padm);
 #pragma unroll
             for (int q = 0; q < 3; ++q) agg_step<32, NR, HASPAD>(Nd[q], Cc, v[q], l, a.P1p, a.P2mP1p, padm);
@@ -382,33 +413,39 @@ sweep_kernel(const uint4* __restrict__ C, uint4* __restrict__ S, SweepArgs a)
 #pragma unroll
                 for (int j = 0; j < NR; ++j) vs[j] = __viaddmin_u16x2(vs[j], v[q][j], SAT2);
         } else {
+            if (MODE == 2) wta_pixel<K, HASPAD>(vsp, l, a.flip ? a.W1 - x : x - 1, yp, a, scratch, x > 0);
             agg_step<32, NR, HASPAD>(Nh, Cn, Lhn, l, a.P1p, a.P2mP1p, padm);
         }
-        // ---- S out, or winner-take-all on the spot
+        // ---- S out, or kept (registers + shared memory) for the winner-take-all one iteration later
         if (MODE == 2) {
-            const int xh = a.flip ? a.W1 - 1 - x : x;
-            wta_pixel<K, HASPAD>(vs, l, xh, yp, a, scratch);
+            __syncwarp();                       // all lanes are done reading the previous pixel's S
+#pragma unroll
+            for (int k = 0; k < K; ++k)
+                reinterpret_cast<uint4*>(scratch)[l * K + k] = make_uint4(vs[4 * k], vs[4 * k + 1], vs[4 * k + 2], vs[4 * k + 3]);
+#pragma unroll
+            for (int j = 0; j < NR; ++j) vsp[j] = vs[j];
+            __syncwarp();
         } else {
 #pragma unroll
             for (int k = 0; k < K; ++k)
                 stg_stream(scur + k * 32, make_uint4(vs[4 * k], vs[4 * k + 1], vs[4 * k + 2], vs[4 * k + 3]));
         }
         scur += dstep;
-        // ---- refill the staging slot just consumed with pixel x + PFD
-        if (x + Cfg::PFD < a.W1) {
+        // ---- refill the staging slots just consumed with pixels x + PFD (C) and x + PFS (S)
 #pragma unroll
-            for (int k = 0; k < K; ++k) {
-                cp_async16(stC + (pslot * Cfg::PIX_V + k * 32) * 16, cpf + k * 32);
-                if (MODE != 0) cp_async16(stS + (pslot * Cfg::PIX_V + k * 32) * 16, spf + k * 32);
-            }
+        for (int k = 0; k < K; ++k) {
+            if (x + Cfg::PFD < a.W1) cp_async16(stC + (pslot * Cfg::PIX_V + k * 32) * 16, cpf + k * 32);
+            if (MODE != 0 && x + Cfg::PFS < a.W1) cp_async16(stS + (sslot * Cfg::PIX_V + k * 32) * 16, spf + k * 32);
         }
         cp_async_commit();
         cpf += dstep; spf += dstep;
         pslot = nslot;
+        sslot = sslot + 1 == Cfg::PFS ? 0 : sslot + 1;
 #pragma unroll
         for (int j = 0; j < NR; ++j) { Cc[j] = Cn[j]; Lh[j] = Lhn[j]; }
     }
     cp_async_wait<0>();
+    if (MODE == 2) wta_pixel<K, HASPAD>(vsp, l, a.flip ? 0 : a.W1 - 1, yp, a, scratch, true);
     if (NDIR == 4 && out_mode == 1) {
         // the extra zero column (see above)
         wait_prog(prog_next, a.W1 - NS + 2, seen_next, a.err);
@@ -420,15 +457,36 @@ sweep_kernel(const uint4* __restrict__ C, uint4* __restrict__ S, SweepArgs a)
     }
 }
 
-template <int K, int MODE, int NDIR, bool HASPAD>
-static void launch_sweep_t(const int16_t* C, int16_t* S, const SweepArgs& a, cudaStream_t st)
+template <int K, int MODE, int NDIR, bool HASPAD, int CFG>
+static void launch_sweep_c(const int16_t* C, int16_t* S, const SweepArgs& a, cudaStream_t st)
 {
-    using Cfg = SweepCfg<K>;
+    using Cfg = SweepCfg<K, CFG>;
     const int nbands = (a.H + SW_R - 1) / SW_R;
-    auto kern = sweep_kernel<K, MODE, NDIR, HASPAD>;
+    auto kern = sweep_kernel<K, MODE, NDIR, HASPAD, CFG>;
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
     cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     kern<<<nbands, SW_THREADS, Cfg::SMEM, st>>>(reinterpret_cast<const uint4*>(C), reinterpret_cast<uint4*>(S), a);
+}
+
+static int g_sweep_cfg = -1;
+void set_sweep_cfg(int cfg) { g_sweep_cfg = cfg; }
+
+template <int K, int MODE, int NDIR, bool HASPAD>
+static void launch_sweep_t(const int16_t* C, int16_t* S, const SweepArgs& a, cudaStream_t st)
+{
+    if (g_sweep_cfg < 0) {
+        const char* e = getenv("WSG_SWEEP_CFG");
+        g_sweep_cfg = e ? atoi(e) : 1;
+    }
+    if (K == 1 && NDIR == 4) {
+        switch (g_sweep_cfg) {
+        case 1: launch_sweep_c<K, MODE, NDIR, HASPAD, (K == 1 && NDIR == 4) ? 1 : 0>(C, S, a, st); return;
+        case 2: launch_sweep_c<K, MODE, NDIR, HASPAD, (K == 1 && NDIR == 4) ? 2 : 0>(C, S, a, st); return;
+        case 3: launch_sweep_c<K, MODE, NDIR, HASPAD, (K == 1 && NDIR == 4) ? 3 : 0>(C, S, a, st); return;
+        default: break;
+        }
+    }
+    launch_sweep_c<K, MODE, NDIR, HASPAD, 0>(C, S, a, st);
 }
 
 size_t sweep_boundary_bytes(const SgbmPlan& p)
@@ -449,10 +507,11 @@ void launch_sweep(const int16_t* C, int16_t* S, int flip, int mode, int ndir, co
     a.P2mP1p = ((unsigned)(p.P2 - p.P1) & 0xFFFFu) * 0x10001u;
     a.tag = ((sc.epoch & 1) ? 0x8000u : 0u) | ((sc.epoch & 2) ? 0x80000000u : 0u);
     a.bnd = reinterpret_cast<uint4*>(sc.boundary);
-    a.ticket = sc.ticket; a.err = sc.err;
+    a.ticket = sc.ticket; a.err = sc.err; a.dbg = sc.dbg;
+    a.n0 = std::min(sc.num_sms, (p.H + SW_R - 1) / SW_R);
     a.keys = sc.keys; a.d1 = sc.d1;
     a.minD = p.minD; a.minX1 = p.minX1; a.uniq = p.uniq; a.INVALID = p.INVALID;
-    a.urcp = p.uniq < 100 ? 1.0f / (float)(100 - p.uniq) : 0.f;
+    a.umagic = p.uniq < 100 ? (unsigned)((0x100000000ull + (100 - p.uniq) - 1) / (unsigned)(100 - p.uniq)) : 0u;
     const bool pad = p.Dp != p.D;
 #define WSG_SW_CASE(k, m, n)                                                         \
     if (p.K == k && mode == m && ndir == n) {                                        \
