@@ -39,3 +39,22 @@ def test_oracle_volumes_shape_and_domain():
     assert out["C"].max() == out["maxC"]
     assert out["maxC"] + p["P2"] <= 32767  # fixtures stay inside the verified domain
     assert (out["S"] >= out["C"]).all()
+
+
+def test_uniqueness_extremes_vs_cv2():
+    """uniquenessRatio in {1, 40, 99, 100, 150}: the oracle equals cv2 where cv2 is importable (it is not on the GPU box).
+    uniquenessRatio == 0 is OUTSIDE the verified domain: cv2 4.13 then also drops pixels whose minimum is tied by a
+    disparity further than one step away (saturated S), which the published inequality S(d)*(100-u) < minS*100 never
+    does; the reference's default is 1 (wass_stereo.cpp:755)."""
+    cv2 = pytest.importorskip("cv2")
+    from oracle import sgbm
+    from wass_b200 import synth
+    for uniq in (1, 40, 99, 100, 150):
+        r, l, _ = synth.make_pair(180, 40, 64, seed=uniq)
+        i1, i2 = synth.pad_for_sgbm(r, l, 64)
+        p = sgbm.wass_params(64, mode=1)
+        p["uniquenessRatio"] = uniq
+        m = cv2.StereoSGBM_create(p["minDisparity"], p["numDisparities"], p["blockSize"], p["P1"], p["P2"])
+        m.setUniquenessRatio(uniq); m.setDisp12MaxDiff(p["disp12MaxDiff"]); m.setPreFilterCap(p["preFilterCap"])
+        m.setSpeckleRange(p["speckleRange"]); m.setSpeckleWindowSize(p["speckleWindowSize"]); m.setMode(1)
+        assert np.array_equal(m.compute(i1, i2), sgbm.compute(i1, i2, p)["disp"]), uniq

@@ -106,6 +106,21 @@ def test_sweeps_many_bands_and_reuse(handle, mode):
             assert np.array_equal(out, ref["disp"])
 
 
+@pytest.mark.parametrize("uniq", [40, 99, 100, 150])
+def test_uniqueness_ratio_extremes(handle, impl, uniq):
+    """Large uniquenessRatio, and >= 100 (100-uniq <= 0: the in-sweep WTA hands over to wta_kernel).  The oracle agrees
+    with cv2 4.13 on these (checked in tests/test_oracle_golden.py::test_uniqueness_extremes_vs_cv2 when cv2 is there)."""
+    from oracle import sgbm
+    from wass_b200 import synth
+    r, l, _ = synth.make_pair(180, 40, 64, seed=uniq)
+    i1, i2 = synth.pad_for_sgbm(r, l, 64)
+    p = sgbm.wass_params(64, mode=1)
+    p["uniquenessRatio"] = uniq
+    ref = sgbm.compute(i1, i2, p)
+    out = handle.sgbm_compute(i1, i2, p)
+    assert np.array_equal(out, ref["disp"])
+
+
 def test_too_narrow_image_is_an_error(handle):
     from wass_b200 import capi
     a = np.zeros((8, 20), np.uint8)

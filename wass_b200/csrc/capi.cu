@@ -170,6 +170,7 @@ int wsg_run_sgbm(wsg_handle* h, const uint8_t* d_img1, const uint8_t* d_img2, si
         }
         SweepScratch sc;
         sc.boundary = h->bnd.p;
+        sc.maxC = (const int*)h->scalars.p;
         sc.err = (int*)h->scalars.p + 1;
         sc.dbg = nullptr;
         if (getenv("WSG_SWEEP_DEBUG")) {

@@ -2,51 +2,60 @@
 // wide-tile form: one CTA owns 128 columns x 32 disparities and marches down a band of rows.
 //
 // Three stages run CONCURRENTLY on different warps of the CTA, one image row apart, with one barrier per row:
-//   T   (group B)  unpack the prefilter records of row r+2 into broadcast tables (img1 side) and a reversed,
-//                  pre-negated table (img2 side) in shared memory
-//   P1  (19 warps) Birchfield-Tomasi pixel cost of row r+1 for 128+2*SW2 columns x 32 disparities, two disparities
+//   T   (19 warps) unpack the prefilter records of row r+2 into broadcast tables (img1 side) and a reversed,
+//                  pre-negated table (img2 side) in shared memory; the global load is issued before P1, used after it
+//   P1  (same)     Birchfield-Tomasi pixel cost of row r+1 for 128+2*SW2 columns x 32 disparities, two disparities
 //                  per 32-bit register (VIADD.16x2 / VIADDMNMX.S16x2.RELU / VIMNMX.S16x2)
-//   P2  (group B)  row r: horizontal box sum (sliding over 4 adjacent columns per thread), a ring of 2*SH2+1 row sums in
+//   P2  (4 warps)  row r: horizontal box sum (sliding over 4 adjacent columns per thread), a ring of 2*SH2+1 row sums in
 //                  shared memory for the vertical sliding sum, 16-byte stores of C
 // Compared with the 32x64 tile of cost_kernel (sgbm_kernels.cu) the halo columns recomputed by P1 drop from 75 % to
 // 19 % at the reference's window of 13, P1 runs at 95 % lane occupancy, and no stage waits for another.
 // Shared memory grows with the window: windows above 17 use cost_kernel.
 #include "sgbm_dev.cuh"
+#include <cstdlib>
 
 namespace wsg {
 
-static constexpr int WXT = 128;            // output columns per CTA
 static constexpr int WDT = 32;             // disparities per CTA
 static constexpr int WDTP = 40;            // u16 per column in shared memory (80 B: kills the 4-column bank aliasing)
-static constexpr int WP1 = 19 * 32;        // stage P1 threads: (128 + 2*8 + ...) columns x 4 groups of 8 disparities
-static constexpr int WGB = 5 * 32;         // group B threads: stages T and P2
-static constexpr int WCT = WP1 + WGB;
 static constexpr int WRB = 256;            // rows per band
 static constexpr int WMAXSW = 8;           // windows up to 17
-static constexpr int WNCOL = WXT + 2 * WMAXSW;
-static constexpr int WVT = 180;            // entries of the reversed img2 tables (>= WNCOL + WDT + 1, even)
 static constexpr int WRVPAD = 4;
-static constexpr int WRV = 2 * 8 * WVT + WRVPAD;   // s16 per img2 table set (two copies, one element apart)
+
+// XT = output columns per CTA: 128 (one CTA per SM) or 64 (two CTAs per SM at the reference's window)
+template <int XT> struct WideCfg {
+    static constexpr int NCOL = XT + 2 * WMAXSW;
+    static constexpr int P1 = (NCOL * 4 + 31) / 32 * 32;   // stage P1 + T threads: NCOL columns x 4 groups of 8 disparities
+    static constexpr int GB = XT;                          // stage P2 threads: XT/4 column groups x 4 groups of 8 disparities
+    static constexpr int CT = P1 + GB;
+    static constexpr int VT = (NCOL + WDT + 4) / 2 * 2;    // entries of the reversed img2 tables
+    static constexpr int RV = 2 * 8 * VT + WRVPAD;         // s16 per img2 table set (two copies, one element apart)
+    static constexpr int CTAS = XT == 64 ? 2 : 1;
+};
 
 struct WideSmem { int pd, uu, rv, ring, total; };
-__host__ __device__ inline WideSmem wide_layout(int SH2)
+template <int XT> __host__ __device__ inline WideSmem wide_layout(int SH2)
 {
+    using Cfg = WideCfg<XT>;
     WideSmem s;
-    s.pd = 0;                                          // u16 [2][WNCOL][WDTP]
-    s.uu = s.pd + 2 * WNCOL * WDTP * 2;                // u32 [2][WNCOL][8]
-    s.rv = s.uu + 2 * WNCOL * 8 * 4;                   // s16 [2][WRV]
-    s.ring = (s.rv + 2 * WRV * 2 + 15) & ~15;          // u16 [2*SH2+1][WXT][WDTP]
-    s.total = s.ring + (2 * SH2 + 1) * WXT * WDTP * 2;
+    s.pd = 0;                                          // u16 [2][NCOL][WDTP]
+    s.uu = s.pd + 2 * Cfg::NCOL * WDTP * 2;            // u32 [2][NCOL][8]
+    s.rv = s.uu + 2 * Cfg::NCOL * 8 * 4;               // s16 [2][RV]
+    s.ring = (s.rv + 2 * Cfg::RV * 2 + 15) & ~15;      // u16 [2*SH2+1][XT][WDTP]
+    s.total = s.ring + (2 * SH2 + 1) * XT * WDTP * 2;
     return s;
 }
 
 bool cost_wide_supported(const SgbmPlan& p) { return p.SW2 <= WMAXSW && p.SH2 <= WMAXSW && p.Dp % WDT == 0; }
 
-__global__ void __launch_bounds__(WCT, 1) cost_wide_kernel(const uint2* __restrict__ pre1, const uint2* __restrict__ pre2,
+template <int XT>
+__global__ void __launch_bounds__(WideCfg<XT>::CT, WideCfg<XT>::CTAS) cost_wide_kernel(const uint2* __restrict__ pre1, const uint2* __restrict__ pre2,
                                                            int16_t* __restrict__ C, int* __restrict__ maxC, SgbmPlan p)
 {
     extern __shared__ __align__(16) unsigned char smem[];
-    const WideSmem L = wide_layout(p.SH2);
+    using Cfg = WideCfg<XT>;
+    constexpr int WXT = XT, WNCOL = Cfg::NCOL, WP1 = Cfg::P1, WVT = Cfg::VT, WRV = Cfg::RV;
+    const WideSmem L = wide_layout<XT>(p.SH2);
     uint16_t* pd = reinterpret_cast<uint16_t*>(smem + L.pd);
     unsigned* uu = reinterpret_cast<unsigned*>(smem + L.uu);
     int16_t* rv = reinterpret_cast<int16_t*>(smem + L.rv);
@@ -73,6 +82,17 @@ __global__ void __launch_bounds__(WCT, 1) cost_wide_kernel(const uint2* __restri
 
     for (int s = 0; s < nsteps + 2; ++s) {
         if (tid < WP1) {
+            // ---------------- T (first half): fetch this thread's prefilter record of row-step s; the latency hides
+            //                  behind P1 below.  Threads [0,ncol): img1 column; [ncol, ncol+WVT): img2 table entry.
+            const bool doT = s < nsteps && tid < ncol + WVT;
+            const bool isU = tid < ncol;
+            const int te = isU ? tid : tid - ncol;
+            uint2 q = make_uint2(0, 0);
+            if (doT) {
+                const int yy = min(max(y0 - p.SH2 + s, 0), p.H - 1);
+                const int xx = isU ? p.minX1 + min(max(x0 - p.SW2 + te, 0), p.W1 - 1) : min(max(vtop - te, 0), p.W - 1);
+                q = (isU ? pre1 : pre2)[(size_t)yy * p.W + xx];
+            }
             // ---------------- P1: pixel cost of row-step s-1 from tables[(s-1)&1] into pd[(s-1)&1]
             const int rs = s - 1;
             if (rs >= 0 && rs < nsteps && tid < ncol * 4) {
@@ -106,40 +126,31 @@ __global__ void __launch_bounds__(WCT, 1) cost_wide_kernel(const uint2* __restri
                 }
                 *reinterpret_cast<uint4*>(pd + (b * WNCOL + cc) * WDTP + gg * 8) = out;
             }
-        } else {
-            // ---------------- T: tables of row-step s into tables[s&1]
-            if (s < nsteps) {
+            // ---------------- T (second half): unpack into tables[s&1]
+            if (doT) {
                 const int b = s & 1;
-                const int r = y0 - p.SH2 + s;
-                const int yy = min(max(r, 0), p.H - 1);
-                for (int e = tb; e < ncol; e += WGB) {
-                    const int xx = p.minX1 + min(max(x0 - p.SW2 + e, 0), p.W1 - 1);
-                    const uint2 q = pre1[(size_t)yy * p.W + xx];
-                    const int u0 = q.x & 255, l0 = (q.x >> 8) & 255, h0 = (q.x >> 16) & 255;
-                    const int u1 = q.x >> 24, l1 = q.y & 255, h1 = (q.y >> 8) & 255;
+                const int v0 = q.x & 255, l0 = (q.x >> 8) & 255, h0 = (q.x >> 16) & 255;
+                const int v1 = q.x >> 24, l1 = q.y & 255, h1 = (q.y >> 8) & 255;
+                if (isU) {
                     auto bc = [](int v) -> unsigned { return ((unsigned)v & 0xFFFFu) * 0x10001u; };
-                    uint4* o = reinterpret_cast<uint4*>(uu + (b * WNCOL + e) * 8);
-                    o[0] = make_uint4(bc(u0), bc(-u0), bc(l0), bc(-h0));
-                    o[1] = make_uint4(bc(u1), bc(-u1), bc(l1), bc(-h1));
-                }
-                for (int e = tb; e < WVT; e += WGB) {
-                    const int xp = min(max(vtop - e, 0), p.W - 1);
-                    const uint2 q = pre2[(size_t)yy * p.W + xp];
-                    const int v0 = q.x & 255, l0 = (q.x >> 8) & 255, h0 = (q.x >> 16) & 255;
-                    const int v1 = q.x >> 24, l1 = q.y & 255, h1 = (q.y >> 8) & 255;
+                    uint4* o = reinterpret_cast<uint4*>(uu + (b * WNCOL + te) * 8);
+                    o[0] = make_uint4(bc(v0), bc(-v0), bc(l0), bc(-h0));
+                    o[1] = make_uint4(bc(v1), bc(-v1), bc(l1), bc(-h1));
+                } else {
                     const int16_t val[8] = {(int16_t)v0, (int16_t)-v0, (int16_t)l0, (int16_t)-h0,
                                             (int16_t)v1, (int16_t)-v1, (int16_t)l1, (int16_t)-h1};
                     int16_t* t = rv + b * WRV;
 #pragma unroll
                     for (int qn = 0; qn < 8; ++qn) {
-                        t[(0 * 8 + qn) * WVT + e] = val[qn];                              // copy A: rv[i]
-                        if (e > 0) t[WRVPAD + (1 * 8 + qn) * WVT + e - 1] = val[qn];      // copy B: rv[i+1]
+                        t[(0 * 8 + qn) * WVT + te] = val[qn];                              // copy A: rv[i]
+                        if (te > 0) t[WRVPAD + (1 * 8 + qn) * WVT + te - 1] = val[qn];     // copy B: rv[i+1]
                     }
                 }
             }
+        } else {
             // ---------------- P2: box sums of row-step s-2 from pd[(s-2)&1]
             const int idx = s - 2;
-            if (idx >= 0 && tb < 128) {
+            if (idx >= 0) {
                 const int b = idx & 1;
                 const int r = y0 - p.SH2 + idx;
                 unsigned hs[4] = {0, 0, 0, 0};
@@ -199,12 +210,22 @@ __global__ void __launch_bounds__(WCT, 1) cost_wide_kernel(const uint2* __restri
     if ((tid & 31) == 0 && vmax > 0) atomicMax(maxC, vmax);
 }
 
+template <int XT>
+static void launch_cost_wide_t(const uint2* pre1, const uint2* pre2, int16_t* C, int* maxC, const SgbmPlan& p, cudaStream_t st)
+{
+    const int smem = wide_layout<XT>(p.SH2).total;
+    cudaFuncSetAttribute(cost_wide_kernel<XT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaFuncSetAttribute(cost_wide_kernel<XT>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    dim3 g((p.W1 + XT - 1) / XT, p.Dp / WDT, (p.H + WRB - 1) / WRB);
+    cost_wide_kernel<XT><<<g, WideCfg<XT>::CT, smem, st>>>(pre1, pre2, C, maxC, p);
+}
+
 void launch_cost_wide(const uint2* pre1, const uint2* pre2, int16_t* C, int* maxC, const SgbmPlan& p, cudaStream_t st)
 {
-    const int smem = wide_layout(p.SH2).total;
-    cudaFuncSetAttribute(cost_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    dim3 g((p.W1 + WXT - 1) / WXT, p.Dp / WDT, (p.H + WRB - 1) / WRB);
-    cost_wide_kernel<<<g, WCT, smem, st>>>(pre1, pre2, C, maxC, p);
+    static int xt = -1;
+    if (xt < 0) { const char* e = getenv("WSG_COST_XT"); xt = e ? atoi(e) : 64; }
+    if (xt == 128) launch_cost_wide_t<128>(pre1, pre2, C, maxC, p, st);
+    else           launch_cost_wide_t<64>(pre1, pre2, C, maxC, p, st);
 }
 
 }  // namespace wsg

@@ -43,6 +43,7 @@ struct SweepScratch {
     void* boundary;             // band-to-band state hand-off, sweep_boundary_bytes()
     int* ticket;                // zeroed hand-out counters of THIS launch: WSG_SWEEP_TICKET_INTS ints
     int num_sms;
+    const int* maxC;            // device scalar: max over the cost volume of this frame
     int* err;                   // raised if a bounded wait overran
     int* dbg;                   // optional [nbands]: SM id per band (WSG_SWEEP_DEBUG=1), else null
     int epoch;                  // 1..3, changes with every 4-direction sweep that uses `boundary`

@@ -42,9 +42,25 @@ __device__ __forceinline__ unsigned group_min_u32(unsigned v)
 
 // One step of the recurrence for one direction.  R: normalised state of the predecessor (in/out),
 // Cw: cost of this pixel, v: L of this pixel (out).  NR packed registers, 2 disparities each.
-template <int NL, int NR, bool HASPAD>
+// a*one + b with `one` == 1 at run time: an integer add the compiler has to issue on the FMA pipe (IMAD), which is
+// idle next to the integer ALU that bounds these kernels.
+__device__ __forceinline__ unsigned add_on_fma(unsigned a, unsigned b, unsigned one)
+{
+    unsigned r;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(one), "r"(b));
+    return r;
+}
+// min(a + b, 32767) per 16-bit half for a, b <= 32767: the add on the FMA pipe, the full-rate two-input minimum on the ALU
+__device__ __forceinline__ unsigned sat_add_split(unsigned a, unsigned b, unsigned one)
+{
+    return __vminu2(add_on_fma(a, b, one), SAT2);
+}
+
+// FASTL: max(C) + P2 <= 32767 is known (the domain in which cv2 is reproduced at all), so t + C cannot leave
+// int16 and the saturating add becomes a plain add on the FMA pipe.
+template <int NL, int NR, bool HASPAD, bool FASTL = false>
 __device__ __forceinline__ void agg_step(unsigned (&R)[NR], const unsigned (&Cw)[NR], unsigned (&v)[NR], int l,
-                                         unsigned P1p, unsigned P2mP1p, const unsigned* padm)
+                                         unsigned P1p, unsigned P2mP1p, const unsigned* padm, unsigned one = 1u)
 {
     unsigned up = __shfl_up_sync(FULL, R[NR - 1], 1, NL);
     unsigned dn = __shfl_down_sync(FULL, R[0], 1, NL);
@@ -59,7 +75,7 @@ __device__ __forceinline__ void agg_step(unsigned (&R)[NR], const unsigned (&Cw)
     for (int j = 0; j < NR; ++j) {
         unsigned t = __vimin3_s16x2(q[j], q[j + 1], P2mP1p);
         t = __viaddmin_s16x2(t, P1p, R[j]);
-        v[j] = __viaddmin_u16x2(t, Cw[j], SAT2);
+        v[j] = FASTL ? add_on_fma(t, Cw[j], one) : __viaddmin_u16x2(t, Cw[j], SAT2);
         if (HASPAD) v[j] |= padm[j / 4];
     }
     unsigned m = v[0];

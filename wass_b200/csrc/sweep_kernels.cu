@@ -31,11 +31,15 @@ static constexpr int SW_THREADS = (SW_R + 1) * 32;
 static constexpr unsigned TAGBITS = 0x80008000u;
 static constexpr int SPIN_LIMIT = 1 << 22;
 
-// Shared-memory budget of a CTA.  CFG 0 ("lean", 104 KB at K == 1): two CTAs fit one SM, so the sweep of another frame
-// (another stream) can fill the SMs this sweep's wavefront has not reached yet or has already left.  CFG 1 ("deep",
-// 200 KB): one CTA per SM, deeper rings and prefetch -- the better choice for one frame at a time.  CFG 2/3: experiments.
+// Shared-memory budget of a CTA (K == 1; K == 2 always takes one SM to itself).
+//   CFG 0 (default)  104 KB of rings and staging, padded to 120 KB: one sweep CTA per SM, and room beside it for a CTA of
+//                    the cost kernel of ANOTHER frame (92 KB) -- measured best both for one frame at a time and for two
+//                    frames in flight (bench.py --pipeline-depth 2)
+//   CFG 1            200 KB: deeper rings and prefetch; same speed (neither depth is the limit)
+//   CFG 2            104 KB unpadded: two sweep CTAs of different frames may share an SM; no faster, because the
+//                    plateau of a sweep already keeps the integer ALU of its SM ~80 % busy
 template <int K, int CFG> struct SweepCfg {
-    static constexpr bool LEAN = K == 1 && (CFG == 0 || CFG == 2);
+    static constexpr bool LEAN = K == 1 && CFG != 1;
     static constexpr int NS = K != 1 ? 6 : (LEAN ? 5 : 8);    // state ring depth in columns
     static constexpr int SLOT_V = 3 * K * 32;                 // uint4 per ring slot: [dir][k][lane]
     static constexpr int RING_V = NS * SLOT_V;
@@ -47,7 +51,7 @@ template <int K, int CFG> struct SweepCfg {
     static constexpr int STAGEC_V = SW_R * PFD * PIX_V;       //   per-warp staging of the C stream
     static constexpr int STAGES_V = SW_R * PFS * PIX_V;       //   per-warp staging of the S stream
     static constexpr int SMEM_USED = (RINGS_V + SCR_V + STAGEC_V + STAGES_V) * 16;
-    static constexpr int CTAS_PER_SM = K == 1 && CFG == 0 ? 2 : 1;
+    static constexpr int CTAS_PER_SM = K == 1 && CFG == 2 ? 2 : 1;
     static constexpr int SMEM = CTAS_PER_SM == 1 && SMEM_USED < 120 * 1024 ? 120 * 1024 : SMEM_USED;   // (forces 1 CTA/SM)
     // boundary columns the helper polls per round trip.  At most NS-2: it may only overwrite ring-0 slots of columns
     // its consumer has completed, and the consumer can complete nothing beyond the columns already published.
@@ -67,10 +71,13 @@ struct SweepArgs {
     int Dp8;                 // 16-byte vectors per pixel (= 32*K)
     int flip;                // 0: top->bottom, left->right;  1: rotated by 180 degrees
     unsigned P1p, P2mP1p;
+    int P2;
+    const int* maxC;         // max over the cost volume (written by the cost kernel)
+    unsigned one;            // 1 (kept opaque to the compiler: see add_on_fma)
     unsigned tag;            // epoch tag of this launch (bits 15 and 31)
     uint4* bnd;              // [nbands-1][W1][3][K][32]
-    int* ticket;             // [0] bands handed out, [1] bands handed out beyond n0, [2..] CTAs arrived per SM
-    int n0;                  // min(#SMs, #bands)
+    int* ticket;             // [0] bands handed out, [2..] CTAs of this launch arrived per SM
+    int num_sms;
     int* err;
     int* dbg;                // optional: SM id of every band (placement diagnostics), or null
     // winner-take-all (MODE 2)
@@ -174,49 +181,207 @@ __device__ __forceinline__ void wta_pixel(const unsigned (&s)[4 * K], int l, int
     }
 }
 
-// MODE 0: S = sum of this sweep's L (no read);  1: S += sum (read-modify-write);  2: S += sum, then WTA (S not written)
-// NDIR 4: full sweep;  1: horizontal direction only (the fifth path of MODE_SGBM): rows are independent.
-template <int K, int MODE, int NDIR, bool HASPAD, int CFG>
-__global__ void __launch_bounds__(SW_THREADS, SweepCfg<K, CFG>::CTAS_PER_SM)
-sweep_kernel(const uint4* __restrict__ C, uint4* __restrict__ S, SweepArgs a)
+// One image row of a sweep, walked by one warp (see the kernel below for the surrounding protocol).
+template <int K, int MODE, int NDIR, bool HASPAD, int CFG, bool FAST>
+__device__ __forceinline__ void sweep_row(const uint4* __restrict__ C, uint4* __restrict__ S, const SweepArgs& a, uint4* smem,
+                                          volatile int* prog, int band, int warp, int l)
 {
     using Cfg = SweepCfg<K, CFG>;
     constexpr int NR = 4 * K;
     constexpr int NS = Cfg::NS;
-    extern __shared__ __align__(16) uint4 smem[];
-    __shared__ volatile int prog[SW_R + 1];   // prog[0]: helper (row above the band); prog[r+1]: warp r
-    __shared__ int s_band;
+    const size_t bstride = (size_t)a.W1 * Cfg::SLOT_V;
+    const unsigned one = a.one;
+    const int r = warp;
+    const int yl = band * SW_R + r;                 // logical row (sweep order)
+    if (yl >= a.H) return;
+    const bool top = NDIR == 1 || yl == 0;          // no predecessor row
+    const int out_mode = (NDIR == 1 || yl == a.H - 1) ? 0 : (r < SW_R - 1 ? 1 : 2);
+    const int yp = a.flip ? a.H - 1 - yl : yl;      // physical row
+    const long long dstep = a.flip ? -(long long)a.Dp8 : (long long)a.Dp8;
+    const size_t first = ((size_t)yp * a.W1 + (a.flip ? a.W1 - 1 : 0)) * a.Dp8 + l;
+    const uint4* cpf = C + first;                   // prefetch cursors
+    const uint4* spf = S + first;
+    uint4* scur = S + first;                        // compute cursor
+    const uint4* ring_in = smem + (size_t)r * Cfg::RING_V + l;
+    uint4* ring_out = smem + (size_t)(r + 1) * Cfg::RING_V + l;     // only used when out_mode == 1
+    uint4* bnd_out = a.bnd + (size_t)band * bstride + l;            // only used when out_mode == 2
+    int16_t* scratch = reinterpret_cast<int16_t*>(smem + Cfg::RINGS_V + (size_t)r * Cfg::PIX_V);
+    uint4* stageC = smem + Cfg::RINGS_V + Cfg::SCR_V + (size_t)r * Cfg::PFD * Cfg::PIX_V + l;
+    uint4* stageS = smem + Cfg::RINGS_V + Cfg::SCR_V + Cfg::STAGEC_V + (size_t)r * Cfg::PFS * Cfg::PIX_V + l;
+    volatile int* prog_in = &prog[r];
+    volatile int* prog_me = &prog[r + 1];
+    volatile int* prog_next = &prog[r + 2 <= SW_R ? r + 2 : SW_R];
+    int seen_in = 0, seen_next = 0;
 
-    const int tid = threadIdx.x, warp = tid >> 5, l = tid & 31;
-    if (tid == 0) {
-        // Band hand-out.  Bands must start in (roughly) increasing order, and the ~W1/20 bands that are active at the
-        // same time should sit on different SMs.  With two CTAs per SM the hardware fills an SM's second slot right
-        // after its first, so plain arrival order would pair neighbouring bands on one SM and leave half the SMs
-        // idle.  Hence: the first CTA to arrive on an SM ("primary") takes the next of the first n0 = #SMs bands; later
-        // arrivals wait (bounded) until those are gone and then take the rest in order.  Every band is handed out
-        // exactly once, and a band is only handed out after all lower ones: nothing depends on how CTAs were placed.
-        unsigned sm;
-        asm volatile("mov.u32 %0, %%smid;" : "=r"(sm));
-        const int slot = atomicAdd(a.ticket + 2 + min(sm, 250u), 1);
-        if (slot != 0) {
-            const long long t0 = clock64();
-            while (*reinterpret_cast<volatile int*>(a.ticket) < a.n0 && clock64() - t0 < 40000) __nanosleep(100);
+    unsigned padm[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) padm[k] = ((l * K + k) * 8 >= a.D) ? SAT2 : 0u;
+
+    // one commit group per pixel, PFD pixels ahead; each lane copies and later reads back its own 16 bytes
+    const unsigned stC = (unsigned)__cvta_generic_to_shared(stageC), stS = (unsigned)__cvta_generic_to_shared(stageS);
+    static_assert(Cfg::PFS <= Cfg::PFD, "the S stream rides in the commit groups of the C stream");
+    for (int i = 0; i < Cfg::PFD; ++i) {
+        if (i < a.W1) {
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                cp_async16(stC + (i * Cfg::PIX_V + k * 32) * 16, cpf + k * 32);
+                if (MODE != 0 && i < Cfg::PFS) cp_async16(stS + (i * Cfg::PIX_V + k * 32) * 16, spf + k * 32);
+            }
         }
-        int band = atomicAdd(a.ticket, 1);
-        if (band >= a.n0) band = a.n0 + atomicAdd(a.ticket + 1, 1);
-        s_band = band;
-        if (a.dbg) a.dbg[band] = (int)sm;
+        cp_async_commit();
+        cpf += dstep;
+        if (i < Cfg::PFS) spf += dstep;
     }
-    if (tid <= SW_R) prog[tid] = 0;
-    if (NDIR == 4)
-        for (int i = tid; i < Cfg::RINGS_V; i += SW_THREADS) smem[i] = make_uint4(0, 0, 0, 0);
-    __syncthreads();
-    const int band = s_band;
-    const size_t bstride = (size_t)a.W1 * Cfg::SLOT_V;      // uint4 per boundary row
 
-    // ------------------------------------------------------------------ helper warp
-    if (warp == SW_R) {
-        if (NDIR == 1 || band == 0) return;
+    // The horizontal direction runs ONE PIXEL AHEAD of the three directions that come from the row above: its step for
+    // pixel x+1 and their steps for pixel x are four independent dependency chains in one basic block.
+    unsigned Nh[NR], Cc[NR], Lh[NR], vsp[NR];
+#pragma unroll
+    for (int j = 0; j < NR; ++j) vsp[j] = 0;
+#pragma unroll
+    for (int j = 0; j < NR; ++j) Nh[j] = 0;
+    cp_async_wait<Cfg::PFD - 1>();
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        const uint4 c = stageC[k * 32];
+        Cc[4 * k] = c.x; Cc[4 * k + 1] = c.y; Cc[4 * k + 2] = c.z; Cc[4 * k + 3] = c.w;
+    }
+    agg_step<32, NR, HASPAD, FAST>(Nh, Cc, Lh, l, a.P1p, a.P2mP1p, padm, one);
+
+    int pslot = 0, sslot = 0;                       // x % PFD, x % PFS
+    for (int x = 0; x < a.W1; ++x) {                // logical column
+        const int nslot = pslot + 1 == Cfg::PFD ? 0 : pslot + 1;
+        unsigned Cn[NR], Lhn[NR], vs[NR], v[3][NR], Nd[3][NR];
+        cp_async_wait<Cfg::PFD - 2>();              // pixel x+1 has landed (past the row end: a stale slot, result unused)
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            const uint4 c = stageC[nslot * Cfg::PIX_V + k * 32];
+            Cn[4 * k] = c.x; Cn[4 * k + 1] = c.y; Cn[4 * k + 2] = c.z; Cn[4 * k + 3] = c.w;
+        }
+        if (MODE == 0) {
+#pragma unroll
+            for (int j = 0; j < NR; ++j) vs[j] = Lh[j];
+        } else {
+            // S(x) was committed PFS iterations ago; PFD + x groups exist by now
+            if (Cfg::PFS < Cfg::PFD - 1) cp_async_wait<Cfg::PFS - 1>();
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                const uint4 sv = stageS[sslot * Cfg::PIX_V + k * 32];
+                vs[4 * k] = sat_add_split(sv.x, Lh[4 * k], one);
+                vs[4 * k + 1] = sat_add_split(sv.y, Lh[4 * k + 1], one);
+                vs[4 * k + 2] = sat_add_split(sv.z, Lh[4 * k + 2], one);
+                vs[4 * k + 3] = sat_add_split(sv.w, Lh[4 * k + 3], one);
+            }
+        }
+        if (NDIR == 4) {
+            // ---- states of the three directions that come from the row above
+            if (top) {
+#pragma unroll
+                for (int q = 0; q < 3; ++q)
+#pragma unroll
+                    for (int j = 0; j < NR; ++j) Nd[q][j] = 0;
+            } else {
+                // columns -1 and W1 of the row above exist in the ring as zeros (zero-initialised slot NS-1, and
+                // one extra column written by the producer): L = 0 for an out-of-image predecessor
+                wait_prog(prog_in, x + 2, seen_in, a.err);
+                const int sl[3] = {(x + NS - 1) % NS, x % NS, (x + 1) % NS};
+#pragma unroll
+                for (int q = 0; q < 3; ++q) {
+#pragma unroll
+                    for (int k = 0; k < K; ++k) {
+                        const uint4 t = ring_in[sl[q] * Cfg::SLOT_V + (q * K + k) * 32];
+                        Nd[q][4 * k] = t.x; Nd[q][4 * k + 1] = t.y; Nd[q][4 * k + 2] = t.z; Nd[q][4 * k + 3] = t.w;
+                    }
+                }
+            }
+            // ---- independent chains: the winner-take-all of the PREVIOUS pixel, and the four path steps
+            if (MODE == 2) wta_pixel<K, HASPAD>(vsp, l, a.flip ? a.W1 - x : x - 1, yp, a, scratch, x > 0);
+            agg_step<32, NR, HASPAD, FAST>(Nh, Cn, Lhn, l, a.P1p, a.P2mP1p, padm, one);
+#pragma unroll
+            for (int q = 0; q < 3; ++q) agg_step<32, NR, HASPAD, FAST>(Nd[q], Cc, v[q], l, a.P1p, a.P2mP1p, padm, one);
+            // ---- hand the new states down
+            if (out_mode == 1) {
+                wait_prog(prog_next, x - NS + 2, seen_next, a.err);
+                uint4* dst = ring_out + (x % NS) * Cfg::SLOT_V;
+#pragma unroll
+                for (int q = 0; q < 3; ++q)
+#pragma unroll
+                    for (int k = 0; k < K; ++k)
+                        dst[(q * K + k) * 32] = make_uint4(Nd[q][4 * k], Nd[q][4 * k + 1], Nd[q][4 * k + 2], Nd[q][4 * k + 3]);
+            } else if (out_mode == 2) {
+                uint4* dst = bnd_out + (size_t)x * Cfg::SLOT_V;
+#pragma unroll
+                for (int q = 0; q < 3; ++q)
+#pragma unroll
+                    for (int k = 0; k < K; ++k)
+                        st_volatile(dst + (q * K + k) * 32,
+                                    make_uint4(Nd[q][4 * k] | a.tag, Nd[q][4 * k + 1] | a.tag, Nd[q][4 * k + 2] | a.tag,
+                                               Nd[q][4 * k + 3] | a.tag));
+            }
+            __syncwarp();                      // every lane's state stores are issued before the counter store
+            asm volatile("" ::: "memory");
+            if (l == 0) *prog_me = x + 1;
+#pragma unroll
+            for (int q = 0; q < 3; ++q)
+#pragma unroll
+                for (int j = 0; j < NR; ++j) vs[j] = sat_add_split(vs[j], v[q][j], one);
+        } else {
+            if (MODE == 2) wta_pixel<K, HASPAD>(vsp, l, a.flip ? a.W1 - x : x - 1, yp, a, scratch, x > 0);
+            agg_step<32, NR, HASPAD, FAST>(Nh, Cn, Lhn, l, a.P1p, a.P2mP1p, padm, one);
+        }
+        // ---- S out, or kept (registers + shared memory) for the winner-take-all one iteration later
+        if (MODE == 2) {
+            __syncwarp();                       // all lanes are done reading the previous pixel's S
+#pragma unroll
+            for (int k = 0; k < K; ++k)
+                reinterpret_cast<uint4*>(scratch)[l * K + k] = make_uint4(vs[4 * k], vs[4 * k + 1], vs[4 * k + 2], vs[4 * k + 3]);
+#pragma unroll
+            for (int j = 0; j < NR; ++j) vsp[j] = vs[j];
+            __syncwarp();
+        } else {
+#pragma unroll
+            for (int k = 0; k < K; ++k)
+                stg_stream(scur + k * 32, make_uint4(vs[4 * k], vs[4 * k + 1], vs[4 * k + 2], vs[4 * k + 3]));
+        }
+        scur += dstep;
+        // ---- refill the staging slots just consumed with pixels x + PFD (C) and x + PFS (S)
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            if (x + Cfg::PFD < a.W1) cp_async16(stC + (pslot * Cfg::PIX_V + k * 32) * 16, cpf + k * 32);
+            if (MODE != 0 && x + Cfg::PFS < a.W1) cp_async16(stS + (sslot * Cfg::PIX_V + k * 32) * 16, spf + k * 32);
+        }
+        cp_async_commit();
+        cpf += dstep; spf += dstep;
+        pslot = nslot;
+        sslot = sslot + 1 == Cfg::PFS ? 0 : sslot + 1;
+#pragma unroll
+        for (int j = 0; j < NR; ++j) { Cc[j] = Cn[j]; Lh[j] = Lhn[j]; }
+    }
+    cp_async_wait<0>();
+    if (MODE == 2) wta_pixel<K, HASPAD>(vsp, l, a.flip ? 0 : a.W1 - 1, yp, a, scratch, true);
+    if (NDIR == 4 && out_mode == 1) {
+        // the extra zero column (see above)
+        wait_prog(prog_next, a.W1 - NS + 2, seen_next, a.err);
+#pragma unroll
+        for (int j = 0; j < 3 * K; ++j) ring_out[(a.W1 % NS) * Cfg::SLOT_V + j * 32] = make_uint4(0, 0, 0, 0);
+        __syncwarp();
+        asm volatile("" ::: "memory");
+        if (l == 0) *prog_me = a.W1 + 1;
+    }
+}
+
+
+// MODE 0: S = sum of this sweep's L (no read);  1: S += sum (read-modify-write);  2: S += sum, then WTA (S not written)
+// NDIR 4: full sweep;  1: horizontal direction only (the fifth path of MODE_SGBM): rows are independent.
+// The helper warp of a band: polls the states the previous band's last row published (global memory, L2) into ring 0.
+template <int K, int CFG>
+__device__ __forceinline__ void sweep_helper(const SweepArgs& a, uint4* smem, volatile int* prog, int band, int l)
+{
+    using Cfg = SweepCfg<K, CFG>;
+    constexpr int NS = Cfg::NS;
+    const size_t bstride = (size_t)a.W1 * Cfg::SLOT_V;      // uint4 per boundary row
+    {
+        if (band == 0) return;
         const uint4* src = a.bnd + (size_t)(band - 1) * bstride + l;
         uint4* ring = smem;                                // ring 0
         uint4 hb[Cfg::HD][3 * K];
@@ -276,184 +441,51 @@ sweep_kernel(const uint4* __restrict__ C, uint4* __restrict__ S, SweepArgs a)
         if (l == 0) prog[0] = a.W1 + 1;
         return;
     }
+}
 
-    // ------------------------------------------------------------------ compute warp = one row
-    const int r = warp;
-    const int yl = band * SW_R + r;                 // logical row (sweep order)
-    if (yl >= a.H) return;
-    const bool top = NDIR == 1 || yl == 0;          // no predecessor row
-    const int out_mode = (NDIR == 1 || yl == a.H - 1) ? 0 : (r < SW_R - 1 ? 1 : 2);
-    const int yp = a.flip ? a.H - 1 - yl : yl;      // physical row
-    const long long dstep = a.flip ? -(long long)a.Dp8 : (long long)a.Dp8;
-    const size_t first = ((size_t)yp * a.W1 + (a.flip ? a.W1 - 1 : 0)) * a.Dp8 + l;
-    const uint4* cpf = C + first;                   // prefetch cursors
-    const uint4* spf = S + first;
-    uint4* scur = S + first;                        // compute cursor
-    const uint4* ring_in = smem + (size_t)r * Cfg::RING_V + l;
-    uint4* ring_out = smem + (size_t)(r + 1) * Cfg::RING_V + l;     // only used when out_mode == 1
-    uint4* bnd_out = a.bnd + (size_t)band * bstride + l;            // only used when out_mode == 2
-    int16_t* scratch = reinterpret_cast<int16_t*>(smem + Cfg::RINGS_V + (size_t)r * Cfg::PIX_V);
-    uint4* stageC = smem + Cfg::RINGS_V + Cfg::SCR_V + (size_t)r * Cfg::PFD * Cfg::PIX_V + l;
-    uint4* stageS = smem + Cfg::RINGS_V + Cfg::SCR_V + Cfg::STAGEC_V + (size_t)r * Cfg::PFS * Cfg::PIX_V + l;
-    volatile int* prog_in = &prog[r];
-    volatile int* prog_me = &prog[r + 1];
-    volatile int* prog_next = &prog[r + 2 <= SW_R ? r + 2 : SW_R];
-    int seen_in = 0, seen_next = 0;
+template <int K, int MODE, int NDIR, bool HASPAD, int CFG>
+__global__ void __launch_bounds__(SW_THREADS, SweepCfg<K, CFG>::CTAS_PER_SM)
+sweep_kernel(const uint4* __restrict__ C, uint4* __restrict__ S, SweepArgs a)
+{
+    using Cfg = SweepCfg<K, CFG>;
+    extern __shared__ __align__(16) uint4 smem[];
+    __shared__ volatile int prog[SW_R + 1];   // prog[0]: helper (row above the band); prog[r+1]: warp r
+    __shared__ int s_band;
 
-    unsigned padm[K];
-#pragma unroll
-    for (int k = 0; k < K; ++k) padm[k] = ((l * K + k) * 8 >= a.D) ? SAT2 : 0u;
-
-    // one commit group per pixel, PFD pixels ahead; each lane copies and later reads back its own 16 bytes
-    const unsigned stC = (unsigned)__cvta_generic_to_shared(stageC), stS = (unsigned)__cvta_generic_to_shared(stageS);
-    static_assert(Cfg::PFS <= Cfg::PFD, "the S stream rides in the commit groups of the C stream");
-    for (int i = 0; i < Cfg::PFD; ++i) {
-        if (i < a.W1) {
-#pragma unroll
-            for (int k = 0; k < K; ++k) {
-                cp_async16(stC + (i * Cfg::PIX_V + k * 32) * 16, cpf + k * 32);
-                if (MODE != 0 && i < Cfg::PFS) cp_async16(stS + (i * Cfg::PIX_V + k * 32) * 16, spf + k * 32);
-            }
-        }
-        cp_async_commit();
-        cpf += dstep;
-        if (i < Cfg::PFS) spf += dstep;
+    const int tid = threadIdx.x, warp = tid >> 5, l = tid & 31;
+    // One WORKER per SM and launch: the first CTA of this launch to arrive on an SM stays and takes bands from a ticket
+    // counter until none is left; every other CTA exits at once.  Bands therefore start in increasing order on
+    // different SMs whatever the hardware's placement, nothing waits for a CTA that is not running, and the second
+    // CTA slot of each SM stays free for the sweep (or cost kernel) of ANOTHER frame on another stream -- whose warps
+    // fill the issue slots this latency-bound wavefront leaves empty.
+    if (tid == 0) {
+        unsigned sm;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(sm));
+        s_band = atomicAdd(a.ticket + 2 + min(sm, 250u), 1) == 0 ? 0 : -1;
     }
-
-    // The horizontal direction runs ONE PIXEL AHEAD of the three directions that come from the row above: its step for
-    // pixel x+1 and their steps for pixel x are four independent dependency chains in one basic block.
-    unsigned Nh[NR], Cc[NR], Lh[NR], vsp[NR];
-#pragma unroll
-    for (int j = 0; j < NR; ++j) vsp[j] = 0;
-#pragma unroll
-    for (int j = 0; j < NR; ++j) Nh[j] = 0;
-    cp_async_wait<Cfg::PFD - 1>();
-#pragma unroll
-    for (int k = 0; k < K; ++k) {
-        const uint4 c = stageC[k * 32];
-        Cc[4 * k] = c.x; Cc[4 * k + 1] = c.y; Cc[4 * k + 2] = c.z; Cc[4 * k + 3] = c.w;
-    }
-    agg_step<32, NR, HASPAD>(Nh, Cc, Lh, l, a.P1p, a.P2mP1p, padm);
-
-    int pslot = 0, sslot = 0;                       // x % PFD, x % PFS
-    for (int x = 0; x < a.W1; ++x) {                // logical column
-        const int nslot = pslot + 1 == Cfg::PFD ? 0 : pslot + 1;
-        unsigned Cn[NR], Lhn[NR], vs[NR], v[3][NR], Nd[3][NR];
-        cp_async_wait<Cfg::PFD - 2>();              // pixel x+1 has landed (past the row end: a stale slot, result unused)
-#pragma unroll
-        for (int k = 0; k < K; ++k) {
-            const uint4 c = stageC[nslot * Cfg::PIX_V + k * 32];
-            Cn[4 * k] = c.x; Cn[4 * k + 1] = c.y; Cn[4 * k + 2] = c.z; Cn[4 * k + 3] = c.w;
+    __syncthreads();
+    if (s_band < 0) return;
+    const bool fast = *a.maxC + a.P2 <= 32767;   // the verified domain (known since the cost kernel ran): cheaper arithmetic
+    const int nbands = (a.H + SW_R - 1) / SW_R;
+    while (true) {
+        __syncthreads();                         // the previous band is finished by every warp
+        if (tid == 0) {
+            s_band = atomicAdd(a.ticket, 1);
+            if (a.dbg && s_band < nbands) { unsigned sm; asm volatile("mov.u32 %0, %%smid;" : "=r"(sm)); a.dbg[s_band] = (int)sm; }
         }
-        if (MODE == 0) {
-#pragma unroll
-            for (int j = 0; j < NR; ++j) vs[j] = Lh[j];
+        if (tid <= SW_R) prog[tid] = 0;
+        if (NDIR == 4)
+            for (int i = tid; i < Cfg::RINGS_V; i += SW_THREADS) smem[i] = make_uint4(0, 0, 0, 0);
+        __syncthreads();
+        const int band = s_band;
+        if (band >= nbands) break;
+        if (warp == SW_R) {
+            if (NDIR == 4) sweep_helper<K, CFG>(a, smem, prog, band, l);
+        } else if (fast) {
+            sweep_row<K, MODE, NDIR, HASPAD, CFG, true>(C, S, a, smem, prog, band, warp, l);
         } else {
-            // S(x) was committed PFS iterations ago; PFD + x groups exist by now
-            if (Cfg::PFS < Cfg::PFD - 1) cp_async_wait<Cfg::PFS - 1>();
-#pragma unroll
-            for (int k = 0; k < K; ++k) {
-                const uint4 sv = stageS[sslot * Cfg::PIX_V + k * 32];
-                vs[4 * k] = __viaddmin_u16x2(sv.x, Lh[4 * k], SAT2);
-                vs[4 * k + 1] = __viaddmin_u16x2(sv.y, Lh[4 * k + 1], SAT2);
-                vs[4 * k + 2] = __viaddmin_u16x2(sv.z, Lh[4 * k + 2], SAT2);
-                vs[4 * k + 3] = __viaddmin_u16x2(sv.w, Lh[4 * k + 3], SAT2);
-            }
+            sweep_row<K, MODE, NDIR, HASPAD, CFG, false>(C, S, a, smem, prog, band, warp, l);
         }
-        if (NDIR == 4) {
-            // ---- states of the three directions that come from the row above
-            if (top) {
-#pragma unroll
-                for (int q = 0; q < 3; ++q)
-#pragma unroll
-                    for (int j = 0; j < NR; ++j) Nd[q][j] = 0;
-            } else {
-                // columns -1 and W1 of the row above exist in the ring as zeros (zero-initialised slot NS-1, and
-                // one extra column written by the producer): L = 0 for an out-of-image predecessor
-                wait_prog(prog_in, x + 2, seen_in, a.err);
-                const int sl[3] = {(x + NS - 1) % NS, x % NS, (x + 1) % NS};
-#pragma unroll
-                for (int q = 0; q < 3; ++q) {
-#pragma unroll
-                    for (int k = 0; k < K; ++k) {
-                        const uint4 t = ring_in[sl[q] * Cfg::SLOT_V + (q * K + k) * 32];
-                        Nd[q][4 * k] = t.x; Nd[q][4 * k + 1] = t.y; Nd[q][4 * k + 2] = t.z; Nd[q][4 * k + 3] = t.w;
-                    }
-                }
-            }
-            // ---- independent chains: the winner-take-all of the PREVIOUS pixel, and the four path steps
-            if (MODE == 2) wta_pixel<K, HASPAD>(vsp, l, a.flip ? a.W1 - x : x - 1, yp, a, scratch, x > 0);
-            agg_step<32, NR, HASPAD>(Nh, Cn, Lhn, l, a.P1p, a.P2mP1p, padm);
-#pragma unroll
-            for (int q = 0; q < 3; ++q) agg_step<32, NR, HASPAD>(Nd[q], Cc, v[q], l, a.P1p, a.P2mP1p, padm);
-            // ---- hand the new states down
-            if (out_mode == 1) {
-                wait_prog(prog_next, x - NS + 2, seen_next, a.err);
-                uint4* dst = ring_out + (x % NS) * Cfg::SLOT_V;
-#pragma unroll
-                for (int q = 0; q < 3; ++q)
-#pragma unroll
-                    for (int k = 0; k < K; ++k)
-                        dst[(q * K + k) * 32] = make_uint4(Nd[q][4 * k], Nd[q][4 * k + 1], Nd[q][4 * k + 2], Nd[q][4 * k + 3]);
-            } else if (out_mode == 2) {
-                uint4* dst = bnd_out + (size_t)x * Cfg::SLOT_V;
-#pragma unroll
-                for (int q = 0; q < 3; ++q)
-#pragma unroll
-                    for (int k = 0; k < K; ++k)
-                        st_volatile(dst + (q * K + k) * 32,
-                                    make_uint4(Nd[q][4 * k] | a.tag, Nd[q][4 * k + 1] | a.tag, Nd[q][4 * k + 2] | a.tag,
-                                               Nd[q][4 * k + 3] | a.tag));
-            }
-            __syncwarp();                      // every lane's state stores are issued before the counter store
-            asm volatile("" ::: "memory");
-            if (l == 0) *prog_me = x + 1;
-#pragma unroll
-            for (int q = 0; q < 3; ++q)
-#pragma unroll
-                for (int j = 0; j < NR; ++j) vs[j] = __viaddmin_u16x2(vs[j], v[q][j], SAT2);
-        } else {
-            if (MODE == 2) wta_pixel<K, HASPAD>(vsp, l, a.flip ? a.W1 - x : x - 1, yp, a, scratch, x > 0);
-            agg_step<32, NR, HASPAD>(Nh, Cn, Lhn, l, a.P1p, a.P2mP1p, padm);
-        }
-        // ---- S out, or kept (registers + shared memory) for the winner-take-all one iteration later
-        if (MODE == 2) {
-            __syncwarp();                       // all lanes are done reading the previous pixel's S
-#pragma unroll
-            for (int k = 0; k < K; ++k)
-                reinterpret_cast<uint4*>(scratch)[l * K + k] = make_uint4(vs[4 * k], vs[4 * k + 1], vs[4 * k + 2], vs[4 * k + 3]);
-#pragma unroll
-            for (int j = 0; j < NR; ++j) vsp[j] = vs[j];
-            __syncwarp();
-        } else {
-#pragma unroll
-            for (int k = 0; k < K; ++k)
-                stg_stream(scur + k * 32, make_uint4(vs[4 * k], vs[4 * k + 1], vs[4 * k + 2], vs[4 * k + 3]));
-        }
-        scur += dstep;
-        // ---- refill the staging slots just consumed with pixels x + PFD (C) and x + PFS (S)
-#pragma unroll
-        for (int k = 0; k < K; ++k) {
-            if (x + Cfg::PFD < a.W1) cp_async16(stC + (pslot * Cfg::PIX_V + k * 32) * 16, cpf + k * 32);
-            if (MODE != 0 && x + Cfg::PFS < a.W1) cp_async16(stS + (sslot * Cfg::PIX_V + k * 32) * 16, spf + k * 32);
-        }
-        cp_async_commit();
-        cpf += dstep; spf += dstep;
-        pslot = nslot;
-        sslot = sslot + 1 == Cfg::PFS ? 0 : sslot + 1;
-#pragma unroll
-        for (int j = 0; j < NR; ++j) { Cc[j] = Cn[j]; Lh[j] = Lhn[j]; }
-    }
-    cp_async_wait<0>();
-    if (MODE == 2) wta_pixel<K, HASPAD>(vsp, l, a.flip ? 0 : a.W1 - 1, yp, a, scratch, true);
-    if (NDIR == 4 && out_mode == 1) {
-        // the extra zero column (see above)
-        wait_prog(prog_next, a.W1 - NS + 2, seen_next, a.err);
-#pragma unroll
-        for (int j = 0; j < 3 * K; ++j) ring_out[(a.W1 % NS) * Cfg::SLOT_V + j * 32] = make_uint4(0, 0, 0, 0);
-        __syncwarp();
-        asm volatile("" ::: "memory");
-        if (l == 0) *prog_me = a.W1 + 1;
     }
 }
 
@@ -461,11 +493,12 @@ template <int K, int MODE, int NDIR, bool HASPAD, int CFG>
 static void launch_sweep_c(const int16_t* C, int16_t* S, const SweepArgs& a, cudaStream_t st)
 {
     using Cfg = SweepCfg<K, CFG>;
-    const int nbands = (a.H + SW_R - 1) / SW_R;
+    // enough CTAs for every SM to see one even when other kernels hold slots; all but one per SM exit immediately
+    const int grid = Cfg::CTAS_PER_SM * a.num_sms;
     auto kern = sweep_kernel<K, MODE, NDIR, HASPAD, CFG>;
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
     cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    kern<<<nbands, SW_THREADS, Cfg::SMEM, st>>>(reinterpret_cast<const uint4*>(C), reinterpret_cast<uint4*>(S), a);
+    kern<<<grid, SW_THREADS, Cfg::SMEM, st>>>(reinterpret_cast<const uint4*>(C), reinterpret_cast<uint4*>(S), a);
 }
 
 static int g_sweep_cfg = -1;
@@ -476,13 +509,12 @@ static void launch_sweep_t(const int16_t* C, int16_t* S, const SweepArgs& a, cud
 {
     if (g_sweep_cfg < 0) {
         const char* e = getenv("WSG_SWEEP_CFG");
-        g_sweep_cfg = e ? atoi(e) : 1;
+        g_sweep_cfg = e ? atoi(e) : 0;
     }
     if (K == 1 && NDIR == 4) {
         switch (g_sweep_cfg) {
         case 1: launch_sweep_c<K, MODE, NDIR, HASPAD, (K == 1 && NDIR == 4) ? 1 : 0>(C, S, a, st); return;
         case 2: launch_sweep_c<K, MODE, NDIR, HASPAD, (K == 1 && NDIR == 4) ? 2 : 0>(C, S, a, st); return;
-        case 3: launch_sweep_c<K, MODE, NDIR, HASPAD, (K == 1 && NDIR == 4) ? 3 : 0>(C, S, a, st); return;
         default: break;
         }
     }
@@ -505,10 +537,11 @@ void launch_sweep(const int16_t* C, int16_t* S, int flip, int mode, int ndir, co
     a.H = p.H; a.W1 = p.W1; a.W = p.W; a.D = p.D; a.Dp8 = p.Dp / 8; a.flip = flip;
     a.P1p = ((unsigned)p.P1 & 0xFFFFu) * 0x10001u;
     a.P2mP1p = ((unsigned)(p.P2 - p.P1) & 0xFFFFu) * 0x10001u;
+    a.P2 = p.P2; a.maxC = sc.maxC; a.one = 1u;
     a.tag = ((sc.epoch & 1) ? 0x8000u : 0u) | ((sc.epoch & 2) ? 0x80000000u : 0u);
     a.bnd = reinterpret_cast<uint4*>(sc.boundary);
     a.ticket = sc.ticket; a.err = sc.err; a.dbg = sc.dbg;
-    a.n0 = std::min(sc.num_sms, (p.H + SW_R - 1) / SW_R);
+    a.num_sms = sc.num_sms;
     a.keys = sc.keys; a.d1 = sc.d1;
     a.minD = p.minD; a.minX1 = p.minX1; a.uniq = p.uniq; a.INVALID = p.INVALID;
     a.umagic = p.uniq < 100 ? (unsigned)((0x100000000ull + (100 - p.uniq) - 1) / (unsigned)(100 - p.uniq)) : 0u;
