@@ -445,7 +445,7 @@ __global__ void __launch_bounds__(256) wta_kernel(const int16_t* __restrict__ S,
             const int n = minS * 100 - 1;                    // < 3.3e6: exact in float
             int Tm = n < 0 ? -1 : (int)((float)n * urcp);
             if (n >= 0) { if ((Tm + 1) * udiv <= n) ++Tm; else if (Tm * udiv > n) --Tm; }
-            const unsigned Tkey = Tm < 0 ? 0u : (((unsigned)Tm << 16) | 0xFFFFu);
+            const unsigned Tkey = Tm < 0 ? 0u : (((unsigned)min(Tm, 65535) << 16) | 0xFFFFu);   // S <= 32767 < 65535
             const int rel = best - dlane;                   // position of best inside this lane (may be outside)
 #pragma unroll
             for (int e = 0; e < NV8; ++e) {

@@ -84,7 +84,7 @@ struct SweepArgs {
     unsigned long long* keys;   // [H][W]  (minS, W1-1-x, d) of the best match that lands on x2 (A.5)
     int16_t* d1;                // [H][W]  left-view disparity before the LR check
     int minD, minX1, uniq, INVALID;
-    unsigned umagic;            // ceil(2^32 / (100 - uniq))
+    unsigned umagic;            // ceil(2^32 / (100 - uniq)), or 0 when 100 - uniq == 1
 };
 
 __device__ __forceinline__ uint4 ld_volatile(const uint4* p)
@@ -120,19 +120,20 @@ __device__ __forceinline__ void wait_prog(volatile int* flag, int need, int& see
     asm volatile("" ::: "memory");
 }
 
-// A.5 for one pixel held by one warp: s = final S, 8*K consecutive disparities per lane (a lane is all real or all pad:
-// numDisparities is a multiple of 16); `scratch` holds the same S in shared memory, lane-major.  Needs
-// 0 <= uniquenessRatio < 100 (the host routes anything else to wta_kernel).
+// A.5, split in two so that the scalar tail is paid once per 32 pixels instead of once per pixel.
+//
+// wta_eval (every pixel, warp-uniform result): s = final S of one pixel, 8*K consecutive disparities per lane (a lane is
+// all real or all pad: numDisparities is a multiple of 16); `scratch` holds the same S in shared memory, lane-major.
 //   winner      first d with minimal S: warp minimum of the 32-bit keys (S << 16 | d)
 //   uniqueness  reject iff some d outside {best-1,best,best+1} has S(d)*(100-uniq) < minS*100, i.e. S(d) <= Tm with
 //               Tm = floor((minS*100-1)/(100-uniq)).  Counted instead of searched: #(S <= Tm) over all d, by a packed
 //               subtract whose sign bits are the comparison results, against the same count inside the window.
-// Everything after the two warp reductions is warp-uniform and branch-free (only the two global writes are predicated),
-// so the caller can run it one pixel late, interleaved with the next pixel's path steps: its long dependency chain
-// (reduce -> threshold -> count -> reduce -> parabola) then costs issue slots but no latency.
+//   returns     key = minS << 16 | best, and nb = S(best-1) | S(best+1) << 16 | accepted << 31
+// Branch-free, so the caller can run it one pixel late, interleaved with the next pixel's path steps.  Needs
+// 0 <= uniquenessRatio < 100 (the host routes anything else to wta_kernel).
 template <int K, bool HASPAD>
-__device__ __forceinline__ void wta_pixel(const unsigned (&s)[4 * K], int l, int xh, int y, const SweepArgs& a,
-                                          const int16_t* scratch, bool commit)
+__device__ __forceinline__ void wta_eval(const unsigned (&s)[4 * K], int l, const SweepArgs& a, const int16_t* scratch,
+                                         unsigned& key, unsigned& nb)
 {
     constexpr int NV8 = 8 * K;
     const int dlane = l * NV8;
@@ -148,7 +149,8 @@ __device__ __forceinline__ void wta_pixel(const unsigned (&s)[4 * K], int l, int
     kmin = __reduce_min_sync(FULL, kmin);
     const int minS = (int)(kmin >> 16), best = (int)(kmin & 0xFFFFu);
     const int n = minS * 100 - 1;                                   // < 2^22
-    const int Tm = n < 0 ? -1 : (int)__umulhi((unsigned)n, a.umagic);   // floor(n / (100-uniq)), exact for n < 2^22
+    // floor(n / (100-uniq)): multiply-high by ceil(2^32/(100-uniq)) is exact for n < 2^22; a divisor of 1 has no such constant
+    const int Tm = n < 0 ? -1 : (a.umagic ? (int)__umulhi((unsigned)n, a.umagic) : n);
     // packed count of S <= Tm: (0x8000 + T - S) keeps bit 15 iff T >= S (S, T <= 0x7fff: no borrow between the halves)
     const unsigned T2 = ((unsigned)min(max(Tm, 0), 32767) | 0x8000u) * 0x10001u;
     unsigned bits = 0;
@@ -158,27 +160,36 @@ __device__ __forceinline__ void wta_pixel(const unsigned (&s)[4 * K], int l, int
     if (padlane || Tm < 0) cnt = 0;
     const int total = __reduce_add_sync(FULL, cnt);
     // the winner's neighbours (clamped addresses; the values only count where they exist)
-    const bool hasm = best > 0, hasp = best < a.D - 1;
     const int sm = scratch[max(best - 1, 0)], sp = scratch[min(best + 1, a.D - 1)];
-    const int inwin = (minS <= Tm) + (hasm && sm <= Tm) + (hasp && sp <= Tm);
+    const int inwin = (minS <= Tm) + (best > 0 && sm <= Tm) + (best < a.D - 1 && sp <= Tm);
+    key = kmin;
+    nb = (unsigned)sm | ((unsigned)sp << 16) | (total <= inwin ? 0x80000000u : 0u);
+}
+
+// wta_flush (every 32 pixels): lane i holds the record of logical column xbase + i.  Sub-pixel parabola, right-view map
+// (A.5) and the left-view map, all 32 lanes busy on 32 different pixels; the d1 row segment is one coalesced store.
+__device__ __forceinline__ void wta_flush(unsigned key, unsigned nb, int xl, bool valid, const SweepArgs& a,
+                                          unsigned long long* keys_row, int16_t* d1_row)
+{
+    if (!valid || !(nb & 0x80000000u)) return;
+    const int minS = (int)(key >> 16), best = (int)(key & 0xFFFFu);
+    const int sm = (int)(nb & 0xFFFFu), sp = (int)((nb >> 16) & 0x7FFFu);
+    const int xh = a.flip ? a.W1 - 1 - xl : xl;     // physical column in W1 space
+    const int x = xh + a.minX1;
+    const unsigned long long k64 = ((unsigned long long)minS << 40) | ((unsigned long long)(a.W1 - 1 - xh) << 16) |
+                                   (unsigned long long)best;
+    atomicMin(keys_row + (x - best - a.minD), k64);
     int dd = best * 16;
-    {
+    if (best > 0 && best < a.D - 1) {
         // trunc(((sm-sp)*16 + den) / (2*den)): |numerator| < 2^24, so an approximate float quotient is off by at most one
         const int den = max(sm + sp - 2 * minS, 1), den2 = 2 * den;
         const int num = (sm - sp) * 16 + den, an = abs(num);
         int q = (int)__fdividef((float)an, (float)den2);
         const int rem = an - q * den2;
         q += rem >= den2 ? 1 : (rem < 0 ? -1 : 0);
-        if (hasm && hasp) dd += num < 0 ? -q : q;
+        dd += num < 0 ? -q : q;
     }
-    if (commit && total <= inwin && l == 0) {
-        const int x = xh + a.minX1;
-        const int x2 = x - best - a.minD;
-        const unsigned long long k64 = ((unsigned long long)minS << 40) |
-                                       ((unsigned long long)(a.W1 - 1 - xh) << 16) | (unsigned long long)best;
-        atomicMin(a.keys + (size_t)y * a.W + x2, k64);
-        a.d1[(size_t)y * a.W + x] = (int16_t)(dd + a.minD * 16);
-    }
+    d1_row[x] = (int16_t)(dd + a.minD * 16);
 }
 
 // One image row of a sweep, walked by one warp (see the kernel below for the surrounding protocol).
@@ -236,6 +247,9 @@ __device__ __forceinline__ void sweep_row(const uint4* __restrict__ C, uint4* __
     // The horizontal direction runs ONE PIXEL AHEAD of the three directions that come from the row above: its step for
     // pixel x+1 and their steps for pixel x are four independent dependency chains in one basic block.
     unsigned Nh[NR], Cc[NR], Lh[NR], vsp[NR];
+    unsigned wkey = 0, wnb = 0, rkey = 0, rnb = 0;      // winner-take-all: last evaluation, and this lane's kept record
+    unsigned long long* keys_row = a.keys + (size_t)yp * a.W;
+    int16_t* d1_row = a.d1 + (size_t)yp * a.W;
 #pragma unroll
     for (int j = 0; j < NR; ++j) vsp[j] = 0;
 #pragma unroll
@@ -295,7 +309,7 @@ __device__ __forceinline__ void sweep_row(const uint4* __restrict__ C, uint4* __
                 }
             }
             // ---- independent chains: the winner-take-all of the PREVIOUS pixel, and the four path steps
-            if (MODE == 2) wta_pixel<K, HASPAD>(vsp, l, a.flip ? a.W1 - x : x - 1, yp, a, scratch, x > 0);
+            if (MODE == 2) wta_eval<K, HASPAD>(vsp, l, a, scratch, wkey, wnb);
             agg_step<32, NR, HASPAD, FAST>(Nh, Cn, Lhn, l, a.P1p, a.P2mP1p, padm, one);
 #pragma unroll
             for (int q = 0; q < 3; ++q) agg_step<32, NR, HASPAD, FAST>(Nd[q], Cc, v[q], l, a.P1p, a.P2mP1p, padm, one);
@@ -326,11 +340,14 @@ __device__ __forceinline__ void sweep_row(const uint4* __restrict__ C, uint4* __
 #pragma unroll
                 for (int j = 0; j < NR; ++j) vs[j] = sat_add_split(vs[j], v[q][j], one);
         } else {
-            if (MODE == 2) wta_pixel<K, HASPAD>(vsp, l, a.flip ? a.W1 - x : x - 1, yp, a, scratch, x > 0);
+            if (MODE == 2) wta_eval<K, HASPAD>(vsp, l, a, scratch, wkey, wnb);
             agg_step<32, NR, HASPAD, FAST>(Nh, Cn, Lhn, l, a.P1p, a.P2mP1p, padm, one);
         }
         // ---- S out, or kept (registers + shared memory) for the winner-take-all one iteration later
         if (MODE == 2) {
+            // the evaluation above was for logical column x-1: lane (x-1)%32 keeps it; every 32 columns all lanes flush
+            if (l == ((x - 1) & 31)) { rkey = wkey; rnb = wnb; }
+            if (x > 0 && (x & 31) == 0) wta_flush(rkey, rnb, x - 32 + l, true, a, keys_row, d1_row);
             __syncwarp();                       // all lanes are done reading the previous pixel's S
 #pragma unroll
             for (int k = 0; k < K; ++k)
@@ -358,7 +375,13 @@ __device__ __forceinline__ void sweep_row(const uint4* __restrict__ C, uint4* __
         for (int j = 0; j < NR; ++j) { Cc[j] = Cn[j]; Lh[j] = Lhn[j]; }
     }
     cp_async_wait<0>();
-    if (MODE == 2) wta_pixel<K, HASPAD>(vsp, l, a.flip ? 0 : a.W1 - 1, yp, a, scratch, true);
+    if (MODE == 2) {
+        // last column, then the columns still held in registers: xb .. W1-1 with xb = 32*floor((W1-1)/32)
+        wta_eval<K, HASPAD>(vsp, l, a, scratch, wkey, wnb);
+        if (l == ((a.W1 - 1) & 31)) { rkey = wkey; rnb = wnb; }
+        const int xb = (a.W1 - 1) & ~31;
+        wta_flush(rkey, rnb, xb + l, xb + l < a.W1, a, keys_row, d1_row);
+    }
     if (NDIR == 4 && out_mode == 1) {
         // the extra zero column (see above)
         wait_prog(prog_next, a.W1 - NS + 2, seen_next, a.err);
@@ -544,7 +567,7 @@ void launch_sweep(const int16_t* C, int16_t* S, int flip, int mode, int ndir, co
     a.num_sms = sc.num_sms;
     a.keys = sc.keys; a.d1 = sc.d1;
     a.minD = p.minD; a.minX1 = p.minX1; a.uniq = p.uniq; a.INVALID = p.INVALID;
-    a.umagic = p.uniq < 100 ? (unsigned)((0x100000000ull + (100 - p.uniq) - 1) / (unsigned)(100 - p.uniq)) : 0u;
+    a.umagic = p.uniq < 99 ? (unsigned)((0x100000000ull + (100 - p.uniq) - 1) / (unsigned)(100 - p.uniq)) : 0u;
     const bool pad = p.Dp != p.D;
 #define WSG_SW_CASE(k, m, n)                                                         \
     if (p.K == k && mode == m && ndir == n) {                                        \
