@@ -129,3 +129,30 @@ def test_too_narrow_image_is_an_error(handle):
     with pytest.raises(capi.WsgError) as e:
         handle.sgbm_compute(a, a, p)
     assert e.value.code == -4
+
+
+@pytest.mark.parametrize("W,H,D,mode", [(2448, 2048, 256, 1), (2448, 2048, 256, 0), (4096, 3000, 512, 1)],
+                         ids=["config2_hh", "config2_sgbm", "config4_hh"])
+def test_full_size_implementations_agree(handle, W, H, D, mode):
+    """BASELINE configs[1] and configs[3] at full size: the fused sweeps (the product path) against the per-direction
+    launches -- the decomposition that is checked against the oracle pixel by pixel at oracle-sized inputs above -- plus
+    size-independent properties (ground-truth disparity of the generator, inside the verified domain)."""
+    from oracle import sgbm
+    from wass_b200 import capi, synth
+    r, l, d_true = synth.make_pair(W, H, D, seed=7)
+    i1, i2 = synth.pad_for_sgbm(r, l, D)
+    p = sgbm.wass_params(D, mode=mode)
+    outs = {}
+    for impl in (capi.AGG_SWEEPS_WTA, capi.AGG_SWEEPS, capi.AGG_PER_DIRECTION):
+        handle.sgbm_set_impl(impl)
+        outs[impl] = handle.sgbm_compute(i1, i2, p).copy()
+        st = handle.sgbm_stats()
+        assert st["agg_impl"] == impl and st["out_of_domain"] == 0
+    handle.sgbm_set_impl(capi.AGG_SWEEPS_WTA)
+    assert np.array_equal(outs[capi.AGG_SWEEPS_WTA], outs[capi.AGG_PER_DIRECTION])
+    assert np.array_equal(outs[capi.AGG_SWEEPS], outs[capi.AGG_PER_DIRECTION])
+    disp = outs[capi.AGG_SWEEPS_WTA][:, D:].astype(np.float32) / 16.0
+    valid = disp > 1
+    assert valid.mean() > 0.85
+    err = np.abs(disp - d_true)[valid]
+    assert np.median(err) < 0.25 and (err < 1.0).mean() > 0.97

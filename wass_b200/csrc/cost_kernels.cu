@@ -26,7 +26,8 @@ static constexpr int WRVPAD = 4;
 template <int XT> struct WideCfg {
     static constexpr int NCOL = XT + 2 * WMAXSW;
     static constexpr int P1 = (NCOL * 4 + 31) / 32 * 32;   // stage P1 + T threads: NCOL columns x 4 groups of 8 disparities
-    static constexpr int GB = XT;                          // stage P2 threads: XT/4 column groups x 4 groups of 8 disparities
+    static constexpr int CPT = XT == 64 ? 2 : 4;           // adjacent columns per P2 thread (sliding horizontal sum)
+    static constexpr int GB = XT / CPT * 4;                // stage P2 threads: XT/CPT column groups x 4 groups of 8 disparities
     static constexpr int CT = P1 + GB;
     static constexpr int VT = (NCOL + WDT + 4) / 2 * 2;    // entries of the reversed img2 tables
     static constexpr int RV = 2 * 8 * VT + WRVPAD;         // s16 per img2 table set (two copies, one element apart)
@@ -73,12 +74,18 @@ __global__ void __launch_bounds__(WideCfg<XT>::CT, WideCfg<XT>::CTAS) cost_wide_
     const int vtop = xb - (p.minD + d0);      // largest img2 column touched; table index i <-> x' = vtop - i
     const int nsteps = (y1 - y0) + 2 * p.SH2;
 
-    // stage P2 role (group B, first 128 threads): columns 4*c4..+3, disparities d0+8g..+7
+    // stage P2 role (group B): columns CPT*cg..+CPT-1, disparities d0+8g..+7
+    constexpr int CPT = Cfg::CPT;
     const int tb = tid - WP1;
-    const int g = tb & 3, c4 = tb >> 2;
+    const int g = tb & 3, cg = tb >> 2;
     const bool real_vec = (d0 + 8 * g) < p.D;
-    unsigned acc[4][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}, {0, 0, 0, 0}, {0, 0, 0, 0}};
+    unsigned acc[CPT][4];
+#pragma unroll
+    for (int i = 0; i < CPT; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0;
     int vmax = 0;
+    int rslot = 0;                            // ring slot of this row-step (idx % NR)
+    // first output row of this band, this thread's first column and disparity vector
+    int16_t* dst0 = C + ((size_t)y0 * p.W1 + (x0 + cg * CPT)) * p.Dp + vec_slot((d0 >> 3) + g, p.NL, p.K) * 8;
 
     for (int s = 0; s < nsteps + 2; ++s) {
         if (tid < WP1) {
@@ -152,55 +159,54 @@ __global__ void __launch_bounds__(WideCfg<XT>::CT, WideCfg<XT>::CTAS) cost_wide_
             const int idx = s - 2;
             if (idx >= 0) {
                 const int b = idx & 1;
-                const int r = y0 - p.SH2 + idx;
                 unsigned hs[4] = {0, 0, 0, 0};
-                uint4 head[3];
-                const uint16_t* prow = pd + (b * WNCOL + c4 * 4) * WDTP + g * 8;
+                uint4 head[CPT > 1 ? CPT - 1 : 1];
+                const uint16_t* prow = pd + (b * WNCOL + cg * CPT) * WDTP + g * 8;
 #pragma unroll
-                for (int i = 0; i < 3; ++i) {   // the three columns that leave the window while sliding
+                for (int i = 0; i < CPT - 1; ++i) {   // the columns that leave the window while sliding
                     head[i] = *reinterpret_cast<const uint4*>(prow + i * WDTP);
                     if (i < win) {
                         hs[0] = __vadd2(hs[0], head[i].x); hs[1] = __vadd2(hs[1], head[i].y);
                         hs[2] = __vadd2(hs[2], head[i].z); hs[3] = __vadd2(hs[3], head[i].w);
                     }
                 }
-                for (int i = 3; i < win; ++i) {
+                for (int i = CPT - 1; i < win; ++i) {
                     const uint4 v = *reinterpret_cast<const uint4*>(prow + i * WDTP);
                     hs[0] = __vadd2(hs[0], v.x); hs[1] = __vadd2(hs[1], v.y);
                     hs[2] = __vadd2(hs[2], v.z); hs[3] = __vadd2(hs[3], v.w);
                 }
+                const bool store = idx >= 2 * p.SH2;
+                uint4* slot = reinterpret_cast<uint4*>(ring + (rslot * WXT + cg * CPT) * WDTP + g * 8);
 #pragma unroll
-                for (int cc = 0; cc < 4; ++cc) {
-                    const int col = c4 * 4 + cc;
+                for (int cc = 0; cc < CPT; ++cc) {
                     if (cc > 0) {
                         const uint4 vn = *reinterpret_cast<const uint4*>(prow + (win - 1 + cc) * WDTP);
                         const uint4 vo = head[cc - 1];
                         hs[0] = __vsub2(__vadd2(hs[0], vn.x), vo.x); hs[1] = __vsub2(__vadd2(hs[1], vn.y), vo.y);
                         hs[2] = __vsub2(__vadd2(hs[2], vn.z), vo.z); hs[3] = __vsub2(__vadd2(hs[3], vn.w), vo.w);
                     }
-                    uint4* slot = reinterpret_cast<uint4*>(ring + ((idx % NR) * WXT + col) * WDTP + g * 8);
                     unsigned* ac = acc[cc];
                     if (idx >= NR) {
-                        const uint4 o = *slot;
+                        const uint4 o = slot[cc * (WDTP / 8)];
                         ac[0] = __vsub2(ac[0], o.x); ac[1] = __vsub2(ac[1], o.y);
                         ac[2] = __vsub2(ac[2], o.z); ac[3] = __vsub2(ac[3], o.w);
                     }
-                    *slot = make_uint4(hs[0], hs[1], hs[2], hs[3]);
+                    slot[cc * (WDTP / 8)] = make_uint4(hs[0], hs[1], hs[2], hs[3]);
                     ac[0] = __vadd2(ac[0], hs[0]); ac[1] = __vadd2(ac[1], hs[1]);
                     ac[2] = __vadd2(ac[2], hs[2]); ac[3] = __vadd2(ac[3], hs[3]);
-                    if (idx >= 2 * p.SH2 && x0 + col < p.W1) {
-                        const int y = r - p.SH2;
-                        const int j = (d0 >> 3) + g;
-                        int16_t* dst = C + ((size_t)y * p.W1 + (x0 + col)) * p.Dp + vec_slot(j, p.NL, p.K) * 8;
+                    if (store && x0 + cg * CPT + cc < p.W1) {
+                        uint4* dst = reinterpret_cast<uint4*>(dst0 + (size_t)cc * p.Dp);
                         if (real_vec) {
-                            *reinterpret_cast<uint4*>(dst) = make_uint4(ac[0], ac[1], ac[2], ac[3]);
+                            *dst = make_uint4(ac[0], ac[1], ac[2], ac[3]);
                             const unsigned m = __vmaxs2(__vmaxs2(ac[0], ac[1]), __vmaxs2(ac[2], ac[3]));
                             vmax = max(vmax, max((int)(short)(m & 0xFFFF), (int)(short)(m >> 16)));
                         } else {
-                            *reinterpret_cast<uint4*>(dst) = make_uint4(0, 0, 0, 0);
+                            *dst = make_uint4(0, 0, 0, 0);
                         }
                     }
                 }
+                rslot = rslot + 1 == NR ? 0 : rslot + 1;
+                if (store) dst0 += (size_t)p.W1 * p.Dp;
             }
         }
         __syncthreads();
