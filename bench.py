@@ -34,6 +34,17 @@ def wass_params(num_disp, mode):
                 disp12MaxDiff=-1, preFilterCap=60, uniquenessRatio=1, speckleWindowSize=-70, speckleRange=16, mode=mode)
 
 
+def ncu_traffic():
+    """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture (profiles/traffic.json,
+    written by tools/ncu_summary.py traffic): never measured under the timed run, so None when the file is missing."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            t = json.load(f)
+        return float(t["sweep_kernel"]["dram_bytes_per_launch"]), t.get("source")
+    except Exception:
+        return None, None
+
+
 def measured_peak_gbs():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -188,7 +199,8 @@ def run_ours(args, rank, world):
     hs, streams, dev, pin = [], [], [], []
     for i in range(depth):
         h = capi.Handle(local)
-        h.sgbm_set_impl(args.agg_impl)
+        if args.agg_impl >= 0:
+            h.sgbm_set_impl(args.agg_impl)
         st = torch.cuda.Stream()
         h.set_stream(st.cuda_stream)
         hs.append(h); streams.append(st)
@@ -225,6 +237,9 @@ def run_ours(args, rank, world):
         return e0.elapsed_time(e1)
 
     # ---- warm-up, then the per-stage profile of ONE frame at a time (kernels timed alone: roofline numbers)
+    sampler = ClockSampler(local)          # clocks are sampled from the warm-up to the end of the e2e leg
+    if rank == 0:
+        sampler.start()
     for _ in range(max(args.warmup, 3)):
         for i in range(depth):
             step_dev(i)
@@ -237,9 +252,6 @@ def run_ours(args, rank, world):
     stats = hs[0].sgbm_stats()
 
     # ---- device-resident throughput ("value"): `depth` frames in flight on as many streams
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
     ms_dev = timed_device(args.steps, depth)
 
     # ---- end to end through the C ABI with HOST buffers (pinned): H2D + kernels + D2H per step, one host thread per
@@ -288,8 +300,12 @@ def run_ours(args, rank, world):
             phys_bytes, kname = (2 + 3 * 7) * V, "aggregate_kernel (8 launches/frame)"
         elif impl == 1:    # sweep 1: read C, write S; sweep 2: read C, read S, write S; separate WTA reads V
             phys_bytes, kname = 5 * V, "sweep_kernel (2 launches/frame), S written, separate WTA"
-        else:              # sweep 1: read C, write S; sweep 2: read C, read S, WTA inside
+        elif impl == 2:    # sweep 1: read C, write S; sweep 2: read C, read S, WTA inside
             phys_bytes, kname = 4 * V, "sweep_kernel (2 launches/frame), WTA fused into the second"
+        else:              # 3-direction sweeps (2V, 2V) + two per-direction launches for the anti-diagonals (3V each)
+            phys_bytes, kname = 10 * V, "sweep_kernel<NDIR=3> x2 + aggregate_kernel x2 (anti-diagonals), WTA fused into the last sweep"
+        nlaunch = 2.0                             # sweep launches per frame (the reset kernel in the stage is ~13 us)
+        traffic, traffic_src = ncu_traffic() if impl >= 2 else (None, None)
         line = {
             "metric": "Mdisparities/s", "value": value, "unit": "Mdisp/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -300,7 +316,11 @@ def run_ours(args, rank, world):
                        "parallelism": "frame-per-GPU x%d" % world, "device_vs_e2e_bit_exact": same,
                        "max_cost": stats["max_cost"], "out_of_domain": stats["out_of_domain"]},
             "roofline": {"bound": "hbm", "kernel": kname, "agg_impl": impl, "achieved": achieved, "peak": peak,
-                         "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
+                         "peak_source": peak_src, "bound_note": "the sweeps are integer-ALU bound, not HBM bound (DESIGN.md section 4); "
+                         "frac is the HBM-roofline fraction BASELINE.json asks for",
+                         "algorithmic_bytes_per_launch": alg_bytes / nlaunch if impl != 0 else alg_bytes / 8,
+                         "ms_per_launch": agg_ms_per_frame / (nlaunch if impl != 0 else 8),
                          "algorithmic_bytes_per_frame": alg_bytes, "ms_per_frame": agg_ms_per_frame,
                          "launches_per_frame": agg_launches / args.steps,
                          "moved_bytes_per_frame_this_build": phys_bytes,
@@ -329,8 +349,9 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--pipeline-depth", type=int, default=2,
                     help="frames in flight per GPU (one handle + stream each); 1 = strictly one frame at a time")
-    ap.add_argument("--agg-impl", type=int, default=2, choices=[0, 1, 2],
-                    help="0 per-direction launches, 1 fused sweeps, 2 fused sweeps + fused WTA (default)")
+    ap.add_argument("--agg-impl", type=int, default=-1, choices=[-1, 0, 1, 2, 3],
+                    help="-1 library default, 0 per-direction launches, 1 fused sweeps, 2 fused sweeps + fused WTA, "
+                         "3 three-direction sweeps + anti-diagonal launches + fused WTA")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))

@@ -93,11 +93,14 @@ int wsg_sgbm_debug_volumes(wsg_handle* h, int16_t* C_host, int16_t* S_host);
  * All three produce identical results; the choice only moves HBM traffic:
  *   WSG_AGG_PER_DIRECTION  one launch per path direction (8 or 5), separate WTA kernel          (23V moved)
  *   WSG_AGG_SWEEPS         fused 4-direction wavefront sweeps, S written out, separate WTA      ( 6V moved)
- *   WSG_AGG_SWEEPS_WTA     fused sweeps, WTA inside the last sweep, S never written (default)   ( 4V moved)
+ *   WSG_AGG_SWEEPS_WTA     fused sweeps, WTA inside the last sweep, S never written             ( 4V moved)
+ *   WSG_AGG_SWEEPS3_WTA    3-direction sweeps (rows skewed by one column instead of two) + the two
+ *                          anti-diagonal directions as per-direction launches, WTA inside the last sweep   (10V moved)
  * The fused forms need numDisparities <= 512; above that the per-direction form is used regardless. */
 #define WSG_AGG_PER_DIRECTION 0
 #define WSG_AGG_SWEEPS 1
 #define WSG_AGG_SWEEPS_WTA 2
+#define WSG_AGG_SWEEPS3_WTA 3
 int wsg_sgbm_set_impl(wsg_handle* h, int impl);
 
 /* ---- dense stereo stage as a whole ------------------------------------------------------------ */
@@ -206,6 +209,19 @@ void wsg_rt_from_plane(const double plane[4], double R[9], double T[3], double R
 int wsg_mesh_export_xyzc(wsg_handle* h, const double plane[4], void* dst, size_t capacity, size_t* nbytes);
 /* PovMesh::save_as_xyz_binary, PovMesh.cpp:346-375: the exact bytes of mesh_cam.xyzbin. */
 int wsg_mesh_export_xyzbin(wsg_handle* h, void* dst, size_t capacity, size_t* nbytes);
+
+/* ---- consumer side of the mesh (the step right after the hot path) -------------------------------- */
+/* Replaces load_camera_mesh + align_on_sea_plane (gridding/wassgridsurface/wass_utils.py:22-35 and 38-68, called at
+ * gridding/wassgridsurface/wassgridsurface.py:86-87 and 316-318): decodes the bytes of a mesh_cam.xyzC file (HOST
+ * pointer) on the device -- u16 / scale + min, Rinv @ p + Tinv -- then rotates/translates onto `align_plane` (normally
+ * the mean plane of the sequence, wassgridsurface.py:677-678), flips z and multiplies by `baseline`.
+ * out_xyz: HOST, 3 rows of *n_points doubles (the reference's 3xN array, row-major); capacity_points >= the file's n. */
+int wsg_xyzc_decode_align(wsg_handle* h, const void* xyzc, size_t nbytes, const double align_plane[4], double baseline,
+                          double* out_xyz, size_t capacity_points, size_t* n_points);
+/* Same result without the file round trip: quantises the device-resident mesh exactly as wsg_mesh_export_xyzc(plane)
+ * would and decodes/aligns that copy on the device. */
+int wsg_mesh_aligned_points(wsg_handle* h, const double plane[4], const double align_plane[4], double baseline,
+                            double* out_xyz, size_t capacity_points, size_t* n_points);
 
 /* ---- rectification (the step before the hot path) ---------------------- */
 /* cv::stereoRectify(K0, 0, K1, 0, size, R, T, R1, R2, P1, P2, Q, flags=0, alpha=1.0, size, &roi1, &roi2)

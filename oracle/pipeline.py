@@ -402,6 +402,31 @@ def xyz_compressed_decode(buf):
     return (Rinv @ p_plane.T).T + Tinv
 
 
+def load_camera_mesh_bytes(buf):
+    """gridding/wassgridsurface/wass_utils.py:22-35 (load_camera_mesh), on bytes instead of a file name, same arithmetic:
+    u16 -> float32 -> (promoted to float64) / scale + min, then Rinv @ p + Tinv.  Returns 3xN."""
+    n = struct.unpack_from("<I", buf, 0)[0]
+    limits = np.array(struct.unpack_from("<6d", buf, 4))
+    Rinv = np.array(struct.unpack_from("<9d", buf, 52)).reshape(3, 3)
+    Tinv = np.array(struct.unpack_from("<3d", buf, 124)).reshape(3, 1)
+    data = np.frombuffer(buf, "<u2", count=3 * n, offset=148).reshape((3, n), order="F")
+    m = data.astype(np.float32)
+    m = m / np.expand_dims(limits[0:3], axis=1) + np.expand_dims(limits[3:6], axis=1)
+    return Rinv @ m + Tinv
+
+
+def align_on_sea_plane(mesh, plane, baseline=1.0):
+    """wass_utils.py:38-68 (compute_sea_plane_RT, align_on_sea_plane_RT) and the `* baseline` of
+    wassgridsurface.py:87,318.  mesh: 3xN."""
+    a, b, c, d = plane
+    q = (1 - c) / (a * a + b * b)
+    R = np.array([[1 - a * a * q, -a * b * q, -a], [-a * b * q, 1 - b * b * q, -b], [a, b, c]])
+    T = np.expand_dims(np.array([0, 0, d]), axis=1)
+    out = R @ mesh + T
+    out[2, :] *= -1.0
+    return out * baseline
+
+
 def rectified_calibration_identity(K, T, W, H):
     """Calibration of the synthetic rig of SURVEY.md §8d (already rectified: R=I, K0=K1, T along +x):
     what cv::stereoRectify(alpha=1) returns there -- R1=R2=I, P1=[K|0], P2=[K|(f*Tx,0,0)], ROIs (0,0,W-1,H-1)

@@ -2,6 +2,7 @@
 """Summarise ncu outputs brought back in gpurun_out/ into small text files under profiles/.
     python tools/ncu_summary.py launches <launches.csv> <out.txt>
     python tools/ncu_summary.py rep <file.ncu-rep> <out.txt>
+    python tools/ncu_summary.py traffic <file.ncu-rep> <out.json> "<note>"
 """
 import collections
 import csv
@@ -54,5 +55,36 @@ def rep(path, out):
     print(open(out).read())
 
 
+def traffic(rep, out_json, source_note):
+    """profiles/traffic.json: DRAM bytes per launch (read+write, averaged over the captured launches) per kernel family."""
+    import json
+    txt = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv", "--metrics",
+                          "dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum"],
+                         capture_output=True, text=True).stdout
+    rows = list(csv.reader(txt.splitlines()))
+    H = rows[0]
+    ki, ri, wi, ti = H.index("Kernel Name"), H.index("dram__bytes_read.sum"), H.index("dram__bytes_write.sum"), H.index("gpu__time_duration.sum")
+    units = rows[1]
+    def scale(u):
+        return {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0, "ms": 1e-3, "us": 1e-6, "ns": 1e-9, "msecond": 1e-3, "usecond": 1e-6, "nsecond": 1e-9}.get(u, 1.0)
+    fam = collections.OrderedDict()
+    for r in rows[2:]:
+        name = r[ki].split("(")[0].split("<")[0].replace("void ", "").replace("wsg::", "").strip()
+        rd = float(r[ri].replace(",", "")) * scale(units[ri]); wr = float(r[wi].replace(",", "")) * scale(units[wi])
+        t = float(r[ti].replace(",", "")) * scale(units[ti])
+        fam.setdefault(name, []).append((rd, wr, t))
+    out = {"source": source_note}
+    for n, v in fam.items():
+        out[n] = {"launches_captured": len(v), "dram_read_bytes_per_launch": sum(x[0] for x in v) / len(v),
+                  "dram_write_bytes_per_launch": sum(x[1] for x in v) / len(v),
+                  "dram_bytes_per_launch": sum(x[0] + x[1] for x in v) / len(v),
+                  "ncu_duration_ms_per_launch": 1e3 * sum(x[2] for x in v) / len(v)}
+    json.dump(out, open(out_json, "w"), indent=1)
+    print(json.dumps(out, indent=1))
+
+
 if __name__ == "__main__":
-    {"launches": launches, "rep": rep}[sys.argv[1]](sys.argv[2], sys.argv[3])
+    if sys.argv[1] == "traffic":
+        traffic(sys.argv[2], sys.argv[3], sys.argv[4] if len(sys.argv) > 4 else "")
+    else:
+        {"launches": launches, "rep": rep}[sys.argv[1]](sys.argv[2], sys.argv[3])

@@ -82,7 +82,7 @@ def make_calib(c, left_shape, right_shape, rect_shape):
     return k
 
 
-AGG_PER_DIRECTION, AGG_SWEEPS, AGG_SWEEPS_WTA = 0, 1, 2
+AGG_PER_DIRECTION, AGG_SWEEPS, AGG_SWEEPS_WTA, AGG_SWEEPS3_WTA = 0, 1, 2, 3
 
 _lib = None
 
@@ -138,6 +138,8 @@ def load():
     lib.wsg_rt_from_plane.restype = None
     lib.wsg_mesh_export_xyzc.argtypes = [vp, dp, vp, sz, ctypes.POINTER(sz)]
     lib.wsg_mesh_export_xyzbin.argtypes = [vp, vp, sz, ctypes.POINTER(sz)]
+    lib.wsg_xyzc_decode_align.argtypes = [vp, vp, sz, dp, ctypes.c_double, vp, sz, ctypes.POINTER(sz)]
+    lib.wsg_mesh_aligned_points.argtypes = [vp, dp, dp, ctypes.c_double, vp, sz, ctypes.POINTER(sz)]
     ip = ctypes.POINTER(ci)
     lib.wsg_stereo_rectify.argtypes = [dp, dp, dp, dp, ci, ci, dp, dp, dp, dp, ip, ip]
     lib.wsg_rectify_image.argtypes = [vp, vp, ci, ci, sz, dp, dp, dp, vp]
@@ -394,6 +396,25 @@ class Handle:
         nb = ctypes.c_size_t()
         self._ck(self.lib.wsg_mesh_export_xyzbin(self.h, buf.ctypes.data, buf.size, ctypes.byref(nb)))
         return buf[:nb.value].tobytes()
+
+    def xyzc_decode_align(self, xyzc_bytes, align_plane, baseline=1.0):
+        """mesh_cam.xyzC bytes -> 3xN float64 points on `align_plane` (load_camera_mesh + align_on_sea_plane * baseline)."""
+        buf = np.frombuffer(xyzc_bytes, np.uint8)
+        n = int(np.frombuffer(xyzc_bytes[:4], "<u4")[0]) if len(xyzc_bytes) >= 4 else 0
+        out = np.empty((3, max(n, 1)), np.float64)
+        npts = ctypes.c_size_t()
+        self._ck(self.lib.wsg_xyzc_decode_align(self.h, buf.ctypes.data, buf.size, _d4(align_plane), float(baseline),
+                                                out.ctypes.data, max(n, 1), ctypes.byref(npts)))
+        return out[:, :npts.value].reshape(3, npts.value) if npts.value == max(n, 1) else np.ascontiguousarray(out.reshape(-1)[:3 * npts.value].reshape(3, npts.value))
+
+    def mesh_aligned_points(self, plane, align_plane, baseline=1.0):
+        """Device mesh -> 3xN float64 aligned points, bit-identical to xyzc_decode_align(mesh_export_xyzc(plane), ...)."""
+        W, H, _ = self.mesh_size()
+        out = np.empty(3 * W * H, np.float64)
+        npts = ctypes.c_size_t()
+        self._ck(self.lib.wsg_mesh_aligned_points(self.h, _d4(plane), _d4(align_plane), float(baseline), out.ctypes.data,
+                                                  W * H, ctypes.byref(npts)))
+        return out[:3 * npts.value].reshape(3, npts.value).copy()
 
     def rectify_image(self, img, K, Rrect, P):
         img = np.ascontiguousarray(img, np.uint8)

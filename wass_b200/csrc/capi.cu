@@ -17,7 +17,7 @@ int wsg_create(int device, wsg_handle** out)
     h->device = device;
     if (cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking) != cudaSuccess) { delete h; return WSG_ERR_CUDA; }
     h->stream = h->own_stream;
-    if (const char* e = getenv("WSG_AGG_IMPL")) h->agg_impl = std::min(std::max(atoi(e), 0), 2);
+    if (const char* e = getenv("WSG_AGG_IMPL")) h->agg_impl = std::min(std::max(atoi(e), 0), 3);
     *out = h;
     return WSG_OK;
 }
@@ -104,11 +104,12 @@ int wsg_check_sweep(wsg_handle* h)
     CK(h, cudaMemcpyAsync(&flag, (int*)h->scalars.p + 1, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     CK(h, cudaStreamSynchronize(h->stream));
     if (h->dbg.p && getenv("WSG_SWEEP_DEBUG")) {
-        std::vector<int> sm((h->plan.H + 7) / 8);
-        cudaMemcpy(sm.data(), h->dbg.p, sm.size() * sizeof(int), cudaMemcpyDeviceToHost);
-        fprintf(stderr, "[wsg] band->SM:");
-        for (size_t i = 0; i < sm.size(); ++i) fprintf(stderr, " %d", sm[i]);
-        fprintf(stderr, "\n");
+        const size_t nb = (h->plan.H + 7) / 8;
+        std::vector<int> d(16384);
+        cudaMemcpy(d.data(), h->dbg.p, d.size() * sizeof(int), cudaMemcpyDeviceToHost);
+        fprintf(stderr, "[wsg] last sweep: band sm start_us end_us\n");
+        for (size_t i = 0; i < nb && i < 2048; ++i)
+            fprintf(stderr, "[wsg] %zu %d %.1f %.1f\n", i, d[i], (d[4096 + 2 * i] - d[4096]) * 1e-3, (d[4096 + 2 * i + 1] - d[4096]) * 1e-3);
     }
     if (flag) { h->err = "fused aggregation sweep: hand-off wait overran (code " + std::to_string(flag) + ")"; return WSG_ERR_CUDA; }
     return WSG_OK;
@@ -163,7 +164,7 @@ int wsg_run_sgbm(wsg_handle* h, const uint8_t* d_img1, const uint8_t* d_img2, si
             CK(h, cudaMemsetAsync(h->bnd.p, 0, h->bnd.cap, h->stream));
             h->bnd_H = pl.H; h->bnd_W1 = pl.W1; h->bnd_K = pl.K;
         }
-        const bool fused_wta = impl == WSG_AGG_SWEEPS_WTA && pl.uniq < 100;   // the in-sweep WTA needs 100-uniq > 0
+        const bool fused_wta = (impl == WSG_AGG_SWEEPS_WTA || impl == WSG_AGG_SWEEPS3_WTA) && pl.uniq < 100;   // the in-sweep WTA needs 100-uniq > 0
         if (fused_wta) {
             if ((rc = ensure(h, h->keys, npix * sizeof(unsigned long long)))) return rc;
             if ((rc = ensure(h, h->d1, npix * sizeof(int16_t)))) return rc;
@@ -174,7 +175,7 @@ int wsg_run_sgbm(wsg_handle* h, const uint8_t* d_img1, const uint8_t* d_img2, si
         sc.err = (int*)h->scalars.p + 1;
         sc.dbg = nullptr;
         if (getenv("WSG_SWEEP_DEBUG")) {
-            if ((rc = ensure(h, h->dbg, 4096 * sizeof(int)))) return rc;
+            if ((rc = ensure(h, h->dbg, 16384 * sizeof(int)))) return rc;
             sc.dbg = (int*)h->dbg.p;
         }
         sc.keys = (unsigned long long*)h->keys.p;
@@ -184,19 +185,28 @@ int wsg_run_sgbm(wsg_handle* h, const uint8_t* d_img1, const uint8_t* d_img2, si
         sc.num_sms = h->num_sms;
         auto next_epoch = [&]() { h->sweep_epoch = h->sweep_epoch % 3 + 1; return h->sweep_epoch; };
         const int last_mode = fused_wta ? 2 : 1;
+        // WSG_AGG_SWEEPS3_WTA: the sweeps leave out the (x+1,y-1)-type path (directions 3 and 5), which forces a skew of two
+        // columns per row on the wavefront; those two run as independent per-direction launches (HBM-bound) in between.
+        const bool split = impl == WSG_AGG_SWEEPS3_WTA;
+        const int nd = split ? 3 : 4;
         {
-            StageTimer t(h, WSG_STAGE_AGGREGATE, 2 + (fused_wta ? 1 : 0));
-            if (fused_wta) { launch_wta_reset(sc, pl, h->stream); launches += 1; }
+            const int nl = 2 + (fused_wta ? 1 : 0) + (split ? (pl.mode == WSG_MODE_HH ? 2 : 1) : 0);
+            StageTimer t(h, WSG_STAGE_AGGREGATE, nl);
+            if (fused_wta) launch_wta_reset(sc, pl, h->stream);
             sc.ticket = tickets + 0; sc.epoch = next_epoch();
-            launch_sweep((const int16_t*)h->C.p, (int16_t*)h->S.p, 0, 0, 4, pl, sc, h->stream);
+            launch_sweep((const int16_t*)h->C.p, (int16_t*)h->S.p, 0, 0, nd, pl, sc, h->stream);
+            if (split) {
+                launch_aggregate_dir((const int16_t*)h->C.p, (int16_t*)h->S.p, 3, false, pl, h->stream);
+                if (pl.mode == WSG_MODE_HH) launch_aggregate_dir((const int16_t*)h->C.p, (int16_t*)h->S.p, 5, false, pl, h->stream);
+            }
             sc.ticket = tickets + WSG_SWEEP_TICKET_INTS;
             if (pl.mode == WSG_MODE_HH) {
                 sc.epoch = next_epoch();
-                launch_sweep((const int16_t*)h->C.p, (int16_t*)h->S.p, 1, last_mode, 4, pl, sc, h->stream);
+                launch_sweep((const int16_t*)h->C.p, (int16_t*)h->S.p, 1, last_mode, nd, pl, sc, h->stream);
             } else {
                 launch_sweep((const int16_t*)h->C.p, (int16_t*)h->S.p, 1, last_mode, 1, pl, sc, h->stream);
             }
-            launches += 2;
+            launches += nl;
         }
         {
             StageTimer t(h, WSG_STAGE_WTA, 1);
@@ -275,7 +285,7 @@ int wsg_sgbm_debug_volumes(wsg_handle* h, int16_t* C_host, int16_t* S_host)
     if (!h) return WSG_ERR_INVALID_ARG;
     if (!h->have_plan) { h->err = "no compute yet"; return WSG_ERR_STATE; }
     const SgbmPlan& pl = h->plan;
-    if (S_host && h->stats.agg_impl == WSG_AGG_SWEEPS_WTA) {
+    if (S_host && (h->stats.agg_impl == WSG_AGG_SWEEPS_WTA || h->stats.agg_impl == WSG_AGG_SWEEPS3_WTA)) {
         h->err = "S is never materialised by WSG_AGG_SWEEPS_WTA; select WSG_AGG_SWEEPS or WSG_AGG_PER_DIRECTION first";
         return WSG_ERR_STATE;
     }
@@ -296,7 +306,7 @@ int wsg_sgbm_debug_volumes(wsg_handle* h, int16_t* C_host, int16_t* S_host)
 int wsg_sgbm_set_impl(wsg_handle* h, int impl)
 {
     if (!h) return WSG_ERR_INVALID_ARG;
-    if (impl < WSG_AGG_PER_DIRECTION || impl > WSG_AGG_SWEEPS_WTA) { h->err = "unknown aggregation implementation"; return WSG_ERR_INVALID_ARG; }
+    if (impl < WSG_AGG_PER_DIRECTION || impl > WSG_AGG_SWEEPS3_WTA) { h->err = "unknown aggregation implementation"; return WSG_ERR_INVALID_ARG; }
     h->agg_impl = impl;
     return WSG_OK;
 }

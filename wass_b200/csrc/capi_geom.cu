@@ -564,4 +564,72 @@ void wsg_plane_mean_finish(const double acc[5], double mean[4])
     for (int k = 0; k < 4; ++k) mean[k] = acc[4] > 0 ? acc[k] / acc[4] : std::nan("");
 }
 
+
+// ---- consumer side: mesh_cam.xyzC -> points aligned on the sea plane ---------------------------------------------------
+static int decode_align_device(wsg_handle* h, const uint16_t* d_q, size_t n, const double scale[3], const double mins[3],
+                               const double Rinv[9], const double Tinv[3], const double align_plane[4], double baseline,
+                               double* out_host)
+{
+    double P[31], RT[12], Ri[9], Ti[3];
+    for (int k = 0; k < 3; ++k) { P[k] = scale[k]; P[3 + k] = mins[k]; P[15 + k] = Tinv[k]; }
+    for (int k = 0; k < 9; ++k) P[6 + k] = Rinv[k];
+    wsg_rt_from_plane(align_plane, RT, RT + 9, Ri, Ti);           // compute_sea_plane_RT (wass_utils.py:38-48)
+    for (int k = 0; k < 9; ++k) P[18 + k] = RT[k];
+    for (int k = 0; k < 3; ++k) P[27 + k] = RT[9 + k];
+    P[30] = baseline;
+    int rc;
+    if ((rc = ensure(h, h->m_small, 4096))) return rc;
+    if ((rc = ensure(h, h->m_labels, n * 3 * sizeof(double) + 16))) return rc;     // reused as the output staging buffer
+    CK(h, cudaMemcpyAsync(h->m_small.p, P, sizeof(P), cudaMemcpyHostToDevice, h->stream));
+    StageTimer t(h, WSG_STAGE_MESH, 1);
+    launch_xyzc_decode_align(d_q, n, (const double*)h->m_small.p, (double*)h->m_labels.p, h->stream);
+    CK(h, cudaMemcpyAsync(out_host, h->m_labels.p, n * 3 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CK(h, cudaStreamSynchronize(h->stream));
+    CK(h, cudaGetLastError());
+    return WSG_OK;
+}
+
+int wsg_xyzc_decode_align(wsg_handle* h, const void* xyzc, size_t nbytes, const double align_plane[4], double baseline,
+                          double* out_xyz, size_t capacity_points, size_t* n_points)
+{
+    if (!h) return WSG_ERR_INVALID_ARG;
+    if (!xyzc || !align_plane || !n_points || nbytes < 148) { h->err = "bad argument or truncated header"; return WSG_ERR_INVALID_ARG; }
+    CK(h, cudaSetDevice(h->device));
+    const char* b = (const char*)xyzc;
+    uint32_t n32; memcpy(&n32, b, 4);
+    double lim[6], Rinv[9], Tinv[3];
+    memcpy(lim, b + 4, 48); memcpy(Rinv, b + 52, 72); memcpy(Tinv, b + 124, 24);
+    const size_t n = n32;
+    *n_points = n;
+    if (nbytes < 148 + n * 6) { h->err = "truncated point data"; return WSG_ERR_INVALID_ARG; }
+    if (!out_xyz || capacity_points < n) { h->err = "destination too small"; return WSG_ERR_INVALID_ARG; }
+    if (n == 0) return WSG_OK;
+    int rc;
+    if ((rc = ensure(h, h->m_out, n * 6 + 16))) return rc;
+    CK(h, cudaMemcpyAsync(h->m_out.p, b + 148, n * 6, cudaMemcpyHostToDevice, h->stream));
+    return decode_align_device(h, (const uint16_t*)h->m_out.p, n, lim, lim + 3, Rinv, Tinv, align_plane, baseline, out_xyz);
+}
+
+int wsg_mesh_aligned_points(wsg_handle* h, const double plane[4], const double align_plane[4], double baseline,
+                            double* out_xyz, size_t capacity_points, size_t* n_points)
+{
+    int rc = need_mesh(h);
+    if (rc) return rc;
+    if (!plane || !align_plane || !n_points) return WSG_ERR_INVALID_ARG;
+    // quantise exactly as save_as_xyz_compressed would (the consumer sees the u16 grid, not the fp64 mesh) ...
+    std::vector<char> hdr(148);
+    size_t nb = 0;
+    const int n = h->mesh_w * h->mesh_h;
+    std::vector<char> file((size_t)148 + (size_t)n * 6);
+    if ((rc = wsg_mesh_export_xyzc(h, plane, file.data(), file.size(), &nb))) return rc;
+    uint32_t n32; memcpy(&n32, file.data(), 4);
+    *n_points = n32;
+    if (!out_xyz || capacity_points < n32) { h->err = "destination too small"; return WSG_ERR_INVALID_ARG; }
+    if (n32 == 0) return WSG_OK;
+    double lim[6], Rinv[9], Tinv[3];
+    memcpy(lim, file.data() + 4, 48); memcpy(Rinv, file.data() + 52, 72); memcpy(Tinv, file.data() + 124, 24);
+    // ... and decode + align the copy that is still on the device (h->m_out)
+    return decode_align_device(h, (const uint16_t*)h->m_out.p, n32, lim, lim + 3, Rinv, Tinv, align_plane, baseline, out_xyz);
+}
+
 }  // extern "C"

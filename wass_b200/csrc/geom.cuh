@@ -60,4 +60,9 @@ int mesh_compact_xyz(const MeshView& m, float* out /*n x 3*/, unsigned* scan_tmp
                      unsigned long long* n_host, cudaStream_t st);
 void launch_count_valid(const MeshView& m, unsigned long long* counter, cudaStream_t st);
 
+// consumer side of mesh_cam.xyzC (gridding/wassgridsurface/wass_utils.py:22-68): u16 -> plane frame -> camera frame ->
+// aligned on the (mean) sea plane, z flipped, scaled by the baseline.  q: n x (x,y,z) u16 on the device; M: 24 doubles
+// {inv scale[3], min[3], Rinv[9], Tinv[3], R[9] of the mean plane ... see capi}; out: 3 x n doubles (row-major 3 rows).
+void launch_xyzc_decode_align(const uint16_t* q, size_t n, const double* d_params, double* out, cudaStream_t st);
+
 }  // namespace wsg

@@ -634,4 +634,35 @@ int mesh_compact_xyz(const MeshView& m, float* out, unsigned* scan_tmp, void* cu
     return 0;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Consumer side of mesh_cam.xyzC: load_camera_mesh + align_on_sea_plane (gridding/wassgridsurface/wass_utils.py:22-35,
+// 38-68), the step right after the hot path.  params (doubles): [0..2] scale, [3..5] min,
+// [6..14] Rinv, [15..17] Tinv, [18..26] R of the plane to align on, [27..29] T, [30] baseline.
+// Operation order of the reference: p = u16/scale + min;  c = Rinv@p + Tinv;  a = R@c + T;  a.z = -a.z;  a *= baseline.
+// ------------------------------------------------------------------------------------------------
+__global__ void xyzc_decode_align_kernel(const uint16_t* __restrict__ q, size_t n, const double* __restrict__ P,
+                                         double* __restrict__ out)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double p[3], c[3], a[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) p[k] = (double)(float)q[i * 3 + k] / P[k] + P[3 + k];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) c[r] = (P[6 + 3 * r] * p[0] + P[6 + 3 * r + 1] * p[1] + P[6 + 3 * r + 2] * p[2]) + P[15 + r];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) a[r] = (P[18 + 3 * r] * c[0] + P[18 + 3 * r + 1] * c[1] + P[18 + 3 * r + 2] * c[2]) + P[27 + r];
+    a[2] = -a[2];
+    const double b = P[30];
+    out[i] = a[0] * b;
+    out[n + i] = a[1] * b;
+    out[2 * n + i] = a[2] * b;
+}
+
+void launch_xyzc_decode_align(const uint16_t* q, size_t n, const double* d_params, double* out, cudaStream_t st)
+{
+    if (n == 0) return;
+    xyzc_decode_align_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(q, n, d_params, out);
+}
+
 }  // namespace wsg

@@ -202,6 +202,7 @@ __device__ __forceinline__ void sweep_row(const uint4* __restrict__ C, uint4* __
     constexpr int NS = Cfg::NS;
     const size_t bstride = (size_t)a.W1 * Cfg::SLOT_V;
     const unsigned one = a.one;
+    constexpr int NQ = NDIR == 4 ? 3 : 2;            // directions whose predecessor lies in the row above
     const int r = warp;
     const int yl = band * SW_R + r;                 // logical row (sweep order)
     if (yl >= a.H) return;
@@ -287,20 +288,21 @@ __device__ __forceinline__ void sweep_row(const uint4* __restrict__ C, uint4* __
                 vs[4 * k + 3] = sat_add_split(sv.w, Lh[4 * k + 3], one);
             }
         }
-        if (NDIR == 4) {
-            // ---- states of the three directions that come from the row above
+        if (NDIR >= 3) {
+            // ---- states of the NQ directions that come from the row above (3 with, 2 without the (x+1,y-1) path)
             if (top) {
 #pragma unroll
-                for (int q = 0; q < 3; ++q)
+                for (int q = 0; q < NQ; ++q)
 #pragma unroll
                     for (int j = 0; j < NR; ++j) Nd[q][j] = 0;
             } else {
                 // columns -1 and W1 of the row above exist in the ring as zeros (zero-initialised slot NS-1, and
                 // one extra column written by the producer): L = 0 for an out-of-image predecessor
-                wait_prog(prog_in, x + 2, seen_in, a.err);
+                // NDIR 4 needs column x+1 of the row above (skew 2), NDIR 3 only column x (skew 1)
+                wait_prog(prog_in, x + NQ - 1, seen_in, a.err);
                 const int sl[3] = {(x + NS - 1) % NS, x % NS, (x + 1) % NS};
 #pragma unroll
-                for (int q = 0; q < 3; ++q) {
+                for (int q = 0; q < NQ; ++q) {
 #pragma unroll
                     for (int k = 0; k < K; ++k) {
                         const uint4 t = ring_in[sl[q] * Cfg::SLOT_V + (q * K + k) * 32];
@@ -312,20 +314,20 @@ __device__ __forceinline__ void sweep_row(const uint4* __restrict__ C, uint4* __
             if (MODE == 2) wta_eval<K, HASPAD>(vsp, l, a, scratch, wkey, wnb);
             agg_step<32, NR, HASPAD, FAST>(Nh, Cn, Lhn, l, a.P1p, a.P2mP1p, padm, one);
 #pragma unroll
-            for (int q = 0; q < 3; ++q) agg_step<32, NR, HASPAD, FAST>(Nd[q], Cc, v[q], l, a.P1p, a.P2mP1p, padm, one);
+            for (int q = 0; q < NQ; ++q) agg_step<32, NR, HASPAD, FAST>(Nd[q], Cc, v[q], l, a.P1p, a.P2mP1p, padm, one);
             // ---- hand the new states down
             if (out_mode == 1) {
                 wait_prog(prog_next, x - NS + 2, seen_next, a.err);
                 uint4* dst = ring_out + (x % NS) * Cfg::SLOT_V;
 #pragma unroll
-                for (int q = 0; q < 3; ++q)
+                for (int q = 0; q < NQ; ++q)
 #pragma unroll
                     for (int k = 0; k < K; ++k)
                         dst[(q * K + k) * 32] = make_uint4(Nd[q][4 * k], Nd[q][4 * k + 1], Nd[q][4 * k + 2], Nd[q][4 * k + 3]);
             } else if (out_mode == 2) {
                 uint4* dst = bnd_out + (size_t)x * Cfg::SLOT_V;
 #pragma unroll
-                for (int q = 0; q < 3; ++q)
+                for (int q = 0; q < NQ; ++q)
 #pragma unroll
                     for (int k = 0; k < K; ++k)
                         st_volatile(dst + (q * K + k) * 32,
@@ -336,7 +338,7 @@ __device__ __forceinline__ void sweep_row(const uint4* __restrict__ C, uint4* __
             asm volatile("" ::: "memory");
             if (l == 0) *prog_me = x + 1;
 #pragma unroll
-            for (int q = 0; q < 3; ++q)
+            for (int q = 0; q < NQ; ++q)
 #pragma unroll
                 for (int j = 0; j < NR; ++j) vs[j] = sat_add_split(vs[j], v[q][j], one);
         } else {
@@ -382,7 +384,7 @@ __device__ __forceinline__ void sweep_row(const uint4* __restrict__ C, uint4* __
         const int xb = (a.W1 - 1) & ~31;
         wta_flush(rkey, rnb, xb + l, xb + l < a.W1, a, keys_row, d1_row);
     }
-    if (NDIR == 4 && out_mode == 1) {
+    if (NDIR >= 3 && out_mode == 1) {
         // the extra zero column (see above)
         wait_prog(prog_next, a.W1 - NS + 2, seen_next, a.err);
 #pragma unroll
@@ -395,9 +397,16 @@ __device__ __forceinline__ void sweep_row(const uint4* __restrict__ C, uint4* __
 
 
 // MODE 0: S = sum of this sweep's L (no read);  1: S += sum (read-modify-write);  2: S += sum, then WTA (S not written)
-// NDIR 4: full sweep;  1: horizontal direction only (the fifth path of MODE_SGBM): rows are independent.
+// NDIR 4: full sweep (skew 2);  3: without the (x+1,y-1) path (skew 1: rows trail each other by ONE column, which nearly
+// halves the wavefront's critical path; that path then runs as its own HBM-bound launch);  1: horizontal direction only
+// (the fifth path of MODE_SGBM): rows are independent.
 // The helper warp of a band: polls the states the previous band's last row published (global memory, L2) into ring 0.
-template <int K, int CFG>
+// MODE 0: S = sum of this sweep's L (no read);  1: S += sum (read-modify-write);  2: S += sum, then WTA (S not written)
+// NDIR 4: full sweep (skew 2);  3: without the (x+1,y-1) path (skew 1: rows trail each other by ONE column, which nearly
+// halves the wavefront's critical path; that path then runs as its own HBM-bound launch);  1: horizontal direction only
+// (the fifth path of MODE_SGBM): rows are independent.
+// The helper warp of a band: polls the states the previous band's last row published (global memory, L2) into ring 0.
+template <int K, int CFG, int NQ>
 __device__ __forceinline__ void sweep_helper(const SweepArgs& a, uint4* smem, volatile int* prog, int band, int l)
 {
     using Cfg = SweepCfg<K, CFG>;
@@ -407,7 +416,7 @@ __device__ __forceinline__ void sweep_helper(const SweepArgs& a, uint4* smem, vo
         if (band == 0) return;
         const uint4* src = a.bnd + (size_t)(band - 1) * bstride + l;
         uint4* ring = smem;                                // ring 0
-        uint4 hb[Cfg::HD][3 * K];
+        uint4 hb[Cfg::HD][NQ * K];
         int seen = 0, spins = 0;
         // Poll a window of Cfg::HD columns per round trip to L2 and forward its valid prefix: the throughput adapts to the
         // producer (up to Cfg::HD columns per round trip) and the band ends up trailing it by about one window.
@@ -415,7 +424,7 @@ __device__ __forceinline__ void sweep_helper(const SweepArgs& a, uint4* smem, vo
 #pragma unroll
             for (int u = 0; u < Cfg::HD; ++u)
 #pragma unroll
-                for (int j = 0; j < 3 * K; ++j)
+                for (int j = 0; j < NQ * K; ++j)
                     hb[u][j] = ld_volatile(src + (size_t)min(x + u, a.W1 - 1) * Cfg::SLOT_V + j * 32);
             int n = 0;
             bool prefix = true;
@@ -423,7 +432,7 @@ __device__ __forceinline__ void sweep_helper(const SweepArgs& a, uint4* smem, vo
             for (int u = 0; u < Cfg::HD; ++u) {
                 bool ok = x + u < a.W1;
 #pragma unroll
-                for (int j = 0; j < 3 * K; ++j)
+                for (int j = 0; j < NQ * K; ++j)
                     ok = ok && ((hb[u][j].x & TAGBITS) == a.tag) && ((hb[u][j].y & TAGBITS) == a.tag) &&
                          ((hb[u][j].z & TAGBITS) == a.tag) && ((hb[u][j].w & TAGBITS) == a.tag);
                 prefix = prefix && __all_sync(FULL, ok);
@@ -445,7 +454,7 @@ __device__ __forceinline__ void sweep_helper(const SweepArgs& a, uint4* smem, vo
                 if (u < n) {
                     uint4* dst = ring + ((x + u) % NS) * Cfg::SLOT_V + l;
 #pragma unroll
-                    for (int j = 0; j < 3 * K; ++j)
+                    for (int j = 0; j < NQ * K; ++j)
                         dst[j * 32] = make_uint4(hb[u][j].x & ~TAGBITS, hb[u][j].y & ~TAGBITS, hb[u][j].z & ~TAGBITS,
                                                  hb[u][j].w & ~TAGBITS);
                 }
@@ -458,7 +467,7 @@ __device__ __forceinline__ void sweep_helper(const SweepArgs& a, uint4* smem, vo
         // one more column of zeros: the out-of-image predecessor of the last pixel's (x+1,y-1) path
         wait_prog(&prog[1], a.W1 - NS + 2, seen, a.err);
 #pragma unroll
-        for (int j = 0; j < 3 * K; ++j) ring[(a.W1 % NS) * Cfg::SLOT_V + l + j * 32] = make_uint4(0, 0, 0, 0);
+        for (int j = 0; j < NQ * K; ++j) ring[(a.W1 % NS) * Cfg::SLOT_V + l + j * 32] = make_uint4(0, 0, 0, 0);
         __syncwarp();
         asm volatile("" ::: "memory");
         if (l == 0) prog[0] = a.W1 + 1;
@@ -494,20 +503,31 @@ sweep_kernel(const uint4* __restrict__ C, uint4* __restrict__ S, SweepArgs a)
         __syncthreads();                         // the previous band is finished by every warp
         if (tid == 0) {
             s_band = atomicAdd(a.ticket, 1);
-            if (a.dbg && s_band < nbands) { unsigned sm; asm volatile("mov.u32 %0, %%smid;" : "=r"(sm)); a.dbg[s_band] = (int)sm; }
+            if (a.dbg && s_band < nbands) {
+                unsigned sm; unsigned long long t;
+                asm volatile("mov.u32 %0, %%smid;" : "=r"(sm));
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+                a.dbg[s_band] = (int)sm;
+                a.dbg[4096 + 2 * s_band] = (int)(t & 0x7fffffff);      // start, ns (low bits)
+            }
         }
         if (tid <= SW_R) prog[tid] = 0;
-        if (NDIR == 4)
+        if (NDIR >= 3)
             for (int i = tid; i < Cfg::RINGS_V; i += SW_THREADS) smem[i] = make_uint4(0, 0, 0, 0);
         __syncthreads();
         const int band = s_band;
         if (band >= nbands) break;
         if (warp == SW_R) {
-            if (NDIR == 4) sweep_helper<K, CFG>(a, smem, prog, band, l);
+            if (NDIR >= 3) sweep_helper<K, CFG, NDIR == 4 ? 3 : 2>(a, smem, prog, band, l);
         } else if (fast) {
             sweep_row<K, MODE, NDIR, HASPAD, CFG, true>(C, S, a, smem, prog, band, warp, l);
         } else {
             sweep_row<K, MODE, NDIR, HASPAD, CFG, false>(C, S, a, smem, prog, band, warp, l);
+        }
+        if (a.dbg && warp == SW_R - 1 && l == 0) {           // the band's last row is done
+            unsigned long long t;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+            a.dbg[4096 + 2 * band + 1] = (int)(t & 0x7fffffff);
         }
     }
 }
@@ -577,6 +597,7 @@ void launch_sweep(const int16_t* C, int16_t* S, int flip, int mode, int ndir, co
     }
     WSG_SW_CASE(1, 0, 4) WSG_SW_CASE(1, 1, 4) WSG_SW_CASE(1, 2, 4) WSG_SW_CASE(1, 1, 1) WSG_SW_CASE(1, 2, 1)
     WSG_SW_CASE(2, 0, 4) WSG_SW_CASE(2, 1, 4) WSG_SW_CASE(2, 2, 4) WSG_SW_CASE(2, 1, 1) WSG_SW_CASE(2, 2, 1)
+    WSG_SW_CASE(1, 0, 3) WSG_SW_CASE(1, 1, 3) WSG_SW_CASE(1, 2, 3) WSG_SW_CASE(2, 0, 3) WSG_SW_CASE(2, 1, 3) WSG_SW_CASE(2, 2, 3)
 #undef WSG_SW_CASE
 }
 
