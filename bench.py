@@ -300,7 +300,7 @@ def run_ours(args, rank, world):
             phys_bytes, kname = (2 + 3 * 7) * V, "aggregate_kernel (8 launches/frame)"
         elif impl == 1:    # sweep 1: read C, write S; sweep 2: read C, read S, write S; separate WTA reads V
             phys_bytes, kname = 5 * V, "sweep_kernel (2 launches/frame), S written, separate WTA"
-        elif impl == 2:    # sweep 1: read C, write S; sweep 2: read C, read S, WTA inside
+        elif impl in (2, 4):   # sweep 1: read C, write S; sweep 2: read C, read S, WTA inside
             phys_bytes, kname = 4 * V, "sweep_kernel (2 launches/frame), WTA fused into the second"
         else:              # 3-direction sweeps (2V, 2V) + two per-direction launches for the anti-diagonals (3V each)
             phys_bytes, kname = 10 * V, "sweep_kernel<NDIR=3> x2 + aggregate_kernel x2 (anti-diagonals), WTA fused into the last sweep"
@@ -349,7 +349,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--pipeline-depth", type=int, default=2,
                     help="frames in flight per GPU (one handle + stream each); 1 = strictly one frame at a time")
-    ap.add_argument("--agg-impl", type=int, default=-1, choices=[-1, 0, 1, 2, 3],
+    ap.add_argument("--agg-impl", type=int, default=-1, choices=[-1, 0, 1, 2, 3, 4],
                     help="-1 library default, 0 per-direction launches, 1 fused sweeps, 2 fused sweeps + fused WTA, "
                          "3 three-direction sweeps + anti-diagonal launches + fused WTA")
     args = ap.parse_args()

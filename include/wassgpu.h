@@ -96,11 +96,14 @@ int wsg_sgbm_debug_volumes(wsg_handle* h, int16_t* C_host, int16_t* S_host);
  *   WSG_AGG_SWEEPS_WTA     fused sweeps, WTA inside the last sweep, S never written             ( 4V moved)
  *   WSG_AGG_SWEEPS3_WTA    3-direction sweeps (rows skewed by one column instead of two) + the two
  *                          anti-diagonal directions as per-direction launches, WTA inside the last sweep   (10V moved)
+ *   WSG_AGG_SWEEPS2W_WTA   as WSG_AGG_SWEEPS_WTA with every image row split over two warps                  ( 4V moved)
+ * WSG_AGG_SWEEPS_WTA is the default; the last two measured no faster and serve as cross-checks.
  * The fused forms need numDisparities <= 512; above that the per-direction form is used regardless. */
 #define WSG_AGG_PER_DIRECTION 0
 #define WSG_AGG_SWEEPS 1
 #define WSG_AGG_SWEEPS_WTA 2
 #define WSG_AGG_SWEEPS3_WTA 3
+#define WSG_AGG_SWEEPS2W_WTA 4
 int wsg_sgbm_set_impl(wsg_handle* h, int impl);
 
 /* ---- dense stereo stage as a whole ------------------------------------------------------------ */

@@ -21,10 +21,10 @@ def _supported(p):
     return p["speckleWindowSize"] <= 0
 
 
-IMPLS = [0, 1, 2, 3]   # capi.AGG_PER_DIRECTION, AGG_SWEEPS, AGG_SWEEPS_WTA, AGG_SWEEPS3_WTA: four decompositions, one result
+IMPLS = [0, 1, 2, 3, 4]   # capi.AGG_*: five device decompositions of the aggregation, one result
 
 
-@pytest.fixture(params=IMPLS, ids=["per_direction", "sweeps", "sweeps_wta", "sweeps3_wta"])
+@pytest.fixture(params=IMPLS, ids=["per_direction", "sweeps", "sweeps_wta", "sweeps3_wta", "sweeps2w_wta"])
 def impl(request, handle):
     handle.sgbm_set_impl(request.param)
     yield request.param
@@ -143,7 +143,7 @@ def test_full_size_implementations_agree(handle, W, H, D, mode):
     i1, i2 = synth.pad_for_sgbm(r, l, D)
     p = sgbm.wass_params(D, mode=mode)
     outs = {}
-    for impl in (capi.AGG_SWEEPS3_WTA, capi.AGG_SWEEPS_WTA, capi.AGG_SWEEPS, capi.AGG_PER_DIRECTION):
+    for impl in (capi.AGG_SWEEPS2W_WTA, capi.AGG_SWEEPS3_WTA, capi.AGG_SWEEPS_WTA, capi.AGG_SWEEPS, capi.AGG_PER_DIRECTION):
         handle.sgbm_set_impl(impl)
         outs[impl] = handle.sgbm_compute(i1, i2, p).copy()
         st = handle.sgbm_stats()
@@ -152,6 +152,7 @@ def test_full_size_implementations_agree(handle, W, H, D, mode):
     assert np.array_equal(outs[capi.AGG_SWEEPS_WTA], outs[capi.AGG_PER_DIRECTION])
     assert np.array_equal(outs[capi.AGG_SWEEPS], outs[capi.AGG_PER_DIRECTION])
     assert np.array_equal(outs[capi.AGG_SWEEPS3_WTA], outs[capi.AGG_PER_DIRECTION])
+    assert np.array_equal(outs[capi.AGG_SWEEPS2W_WTA], outs[capi.AGG_PER_DIRECTION])
     disp = outs[capi.AGG_SWEEPS_WTA][:, D:].astype(np.float32) / 16.0
     valid = disp > 1
     assert valid.mean() > 0.85

@@ -82,7 +82,7 @@ def make_calib(c, left_shape, right_shape, rect_shape):
     return k
 
 
-AGG_PER_DIRECTION, AGG_SWEEPS, AGG_SWEEPS_WTA, AGG_SWEEPS3_WTA = 0, 1, 2, 3
+AGG_PER_DIRECTION, AGG_SWEEPS, AGG_SWEEPS_WTA, AGG_SWEEPS3_WTA, AGG_SWEEPS2W_WTA = 0, 1, 2, 3, 4
 
 _lib = None
 

@@ -17,7 +17,7 @@ int wsg_create(int device, wsg_handle** out)
     h->device = device;
     if (cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking) != cudaSuccess) { delete h; return WSG_ERR_CUDA; }
     h->stream = h->own_stream;
-    if (const char* e = getenv("WSG_AGG_IMPL")) h->agg_impl = std::min(std::max(atoi(e), 0), 3);
+    if (const char* e = getenv("WSG_AGG_IMPL")) h->agg_impl = std::min(std::max(atoi(e), 0), 4);
     *out = h;
     return WSG_OK;
 }
@@ -164,13 +164,14 @@ int wsg_run_sgbm(wsg_handle* h, const uint8_t* d_img1, const uint8_t* d_img2, si
             CK(h, cudaMemsetAsync(h->bnd.p, 0, h->bnd.cap, h->stream));
             h->bnd_H = pl.H; h->bnd_W1 = pl.W1; h->bnd_K = pl.K;
         }
-        const bool fused_wta = (impl == WSG_AGG_SWEEPS_WTA || impl == WSG_AGG_SWEEPS3_WTA) && pl.uniq < 100;   // the in-sweep WTA needs 100-uniq > 0
+        const bool fused_wta = (impl == WSG_AGG_SWEEPS_WTA || impl == WSG_AGG_SWEEPS3_WTA || impl == WSG_AGG_SWEEPS2W_WTA) && pl.uniq < 100;   // the in-sweep WTA needs 100-uniq > 0
         if (fused_wta) {
             if ((rc = ensure(h, h->keys, npix * sizeof(unsigned long long)))) return rc;
             if ((rc = ensure(h, h->d1, npix * sizeof(int16_t)))) return rc;
         }
         SweepScratch sc;
         sc.boundary = h->bnd.p;
+        sc.two_warps = impl == WSG_AGG_SWEEPS2W_WTA;
         sc.maxC = (const int*)h->scalars.p;
         sc.err = (int*)h->scalars.p + 1;
         sc.dbg = nullptr;
@@ -285,7 +286,7 @@ int wsg_sgbm_debug_volumes(wsg_handle* h, int16_t* C_host, int16_t* S_host)
     if (!h) return WSG_ERR_INVALID_ARG;
     if (!h->have_plan) { h->err = "no compute yet"; return WSG_ERR_STATE; }
     const SgbmPlan& pl = h->plan;
-    if (S_host && (h->stats.agg_impl == WSG_AGG_SWEEPS_WTA || h->stats.agg_impl == WSG_AGG_SWEEPS3_WTA)) {
+    if (S_host && (h->stats.agg_impl >= WSG_AGG_SWEEPS_WTA)) {
         h->err = "S is never materialised by WSG_AGG_SWEEPS_WTA; select WSG_AGG_SWEEPS or WSG_AGG_PER_DIRECTION first";
         return WSG_ERR_STATE;
     }
@@ -298,7 +299,8 @@ int wsg_sgbm_debug_volumes(wsg_handle* h, int16_t* C_host, int16_t* S_host)
         CK(h, cudaStreamSynchronize(h->stream));
         for (size_t px = 0; px < npx; ++px)
             for (int j = 0; j < pl.D / 8; ++j)
-                memcpy(dst + px * pl.D + (size_t)j * 8, tmp.data() + px * pl.Dp + (size_t)vec_slot(j, pl.NL, pl.K) * 8, 16);
+                for (int i = 0; i < 8; ++i)     // undo the in-vector interleave (vec_pos)
+                    dst[px * pl.D + (size_t)j * 8 + i] = tmp[px * pl.Dp + (size_t)vec_slot(j, pl.NL, pl.K) * 8 + vec_pos(i)];
     }
     return WSG_OK;
 }
@@ -306,7 +308,7 @@ int wsg_sgbm_debug_volumes(wsg_handle* h, int16_t* C_host, int16_t* S_host)
 int wsg_sgbm_set_impl(wsg_handle* h, int impl)
 {
     if (!h) return WSG_ERR_INVALID_ARG;
-    if (impl < WSG_AGG_PER_DIRECTION || impl > WSG_AGG_SWEEPS3_WTA) { h->err = "unknown aggregation implementation"; return WSG_ERR_INVALID_ARG; }
+    if (impl < WSG_AGG_PER_DIRECTION || impl > WSG_AGG_SWEEPS2W_WTA) { h->err = "unknown aggregation implementation"; return WSG_ERR_INVALID_ARG; }
     h->agg_impl = impl;
     return WSG_OK;
 }

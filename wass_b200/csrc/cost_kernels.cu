@@ -197,7 +197,7 @@ __global__ void __launch_bounds__(WideCfg<XT>::CT, WideCfg<XT>::CTAS) cost_wide_
                     if (store && x0 + cg * CPT + cc < p.W1) {
                         uint4* dst = reinterpret_cast<uint4*>(dst0 + (size_t)cc * p.Dp);
                         if (real_vec) {
-                            *dst = make_uint4(ac[0], ac[1], ac[2], ac[3]);
+                            *dst = interleave8(ac[0], ac[1], ac[2], ac[3]);
                             const unsigned m = __vmaxs2(__vmaxs2(ac[0], ac[1]), __vmaxs2(ac[2], ac[3]));
                             vmax = max(vmax, max((int)(short)(m & 0xFFFF), (int)(short)(m >> 16)));
                         } else {

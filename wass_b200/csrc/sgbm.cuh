@@ -16,7 +16,7 @@ struct SgbmPlan {
     int minX1, maxX1, W1;     // matched column range in image space, W1 = maxX1-minX1
     int INVALID;              // (minD-1)*16
     int mode;                 // 0 = 5 paths, 1 = 8 paths
-    // volume layout: int16 [H][W1][Dp]; a pixel's Dp slots are NL*K vectors of 8 disparities.
+    // volume layout: int16 [H][W1][Dp]; a pixel's Dp slots are NL*K vectors of 8 disparities (interleaved: vec_pos).
     // memory vector slot s = k*NL + l holds logical vector j = l*K + k (disparities 8j..8j+7), so
     // that lane l of a pixel group owns K*8 consecutive disparities and each of its K loads is
     // one fully coalesced 16-byte access across the group.
@@ -24,6 +24,11 @@ struct SgbmPlan {
 };
 
 __host__ __device__ inline int vec_slot(int j, int NL, int K) { return (j % K) * NL + (j / K); }
+// Inside a 16-byte vector the 8 disparities are interleaved so that register i (i = 0..3) holds (a+i, a+4+i) in its
+// (low, high) half: the d-1 / d+1 neighbours of three of the four registers are then simply the adjacent registers, and
+// only two byte-permutes per vector remain in the path recurrence (instead of five with consecutive pairs).
+// vec_pos(i): int16 position of disparity a+i inside its vector.
+__host__ __device__ inline int vec_pos(int i) { return i < 4 ? 2 * i : 2 * (i - 4) + 1; }
 
 // kernels (sgbm_kernels.cu)
 void launch_prefilter(const uint8_t* img, size_t stride, uint2* pre, const SgbmPlan& p, cudaStream_t st);
@@ -47,6 +52,7 @@ struct SweepScratch {
     int* err;                   // raised if a bounded wait overran
     int* dbg;                   // optional [nbands]: SM id per band (WSG_SWEEP_DEBUG=1), else null
     int epoch;                  // 1..3, changes with every 4-direction sweep that uses `boundary`
+    int two_warps;              // 1: split every row over two warps (sweep2w_kernel; K == 1, four directions)
     unsigned long long* keys;   // [H][W] right-view map as packed keys (fused WTA)
     int16_t* d1;                // [H][W] left-view disparity before the LR check (fused WTA)
 };

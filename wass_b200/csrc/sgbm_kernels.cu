@@ -211,7 +211,7 @@ __global__ void __launch_bounds__(CT) cost_kernel(const uint2* __restrict__ pre1
                     const int j = (d0 >> 3) + g;
                     int16_t* dst = C + ((size_t)y * p.W1 + (x0 + col)) * p.Dp + vec_slot(j, p.NL, p.K) * 8;
                     if (real_vec) {
-                        *reinterpret_cast<uint4*>(dst) = make_uint4(ac[0], ac[1], ac[2], ac[3]);
+                        *reinterpret_cast<uint4*>(dst) = interleave8(ac[0], ac[1], ac[2], ac[3]);
                         unsigned m = __vmaxs2(__vmaxs2(ac[0], ac[1]), __vmaxs2(ac[2], ac[3]));
                         vmax = max(vmax, max((int)(short)(m & 0xFFFF), (int)(short)(m >> 16)));
                     } else {
@@ -429,9 +429,9 @@ __global__ void __launch_bounds__(256) wta_kernel(const int16_t* __restrict__ S,
             const uint4 v = *reinterpret_cast<const uint4*>(Sp + ((size_t)k * NL + l) * 8);
             const unsigned w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                key[k * 8 + 2 * e] = (w[e] << 16) + (unsigned)(dlane + k * 8 + 2 * e);
-                key[k * 8 + 2 * e + 1] = (w[e] & 0xFFFF0000u) + (unsigned)(dlane + k * 8 + 2 * e + 1);
+            for (int e = 0; e < 4; ++e) {   // interleaved vector: register e = (disparity e, disparity 4+e), see vec_pos
+                key[k * 8 + e] = (w[e] << 16) + (unsigned)(dlane + k * 8 + e);
+                key[k * 8 + 4 + e] = (w[e] & 0xFFFF0000u) + (unsigned)(dlane + k * 8 + 4 + e);
             }
         }
         unsigned kmin = 0xFFFFFFFFu;
@@ -474,8 +474,8 @@ __global__ void __launch_bounds__(256) wta_kernel(const int16_t* __restrict__ S,
             int dd = best * 16;
             if (best > 0 && best < p.D - 1) {
                 const int jm = (best - 1) >> 3, jp = (best + 1) >> 3;
-                const int sm = Sp[vec_slot(jm, NL, K) * 8 + ((best - 1) & 7)];
-                const int sp = Sp[vec_slot(jp, NL, K) * 8 + ((best + 1) & 7)];
+                const int sm = Sp[vec_slot(jm, NL, K) * 8 + vec_pos((best - 1) & 7)];
+                const int sp = Sp[vec_slot(jp, NL, K) * 8 + vec_pos((best + 1) & 7)];
                 const int den = max(sm + sp - 2 * minS, 1);
                 dd += ((sm - sp) * 16 + den) / (2 * den);
             }

@@ -31,6 +31,7 @@ static constexpr int SW_THREADS = (SW_R + 1) * 32;
 static constexpr unsigned TAGBITS = 0x80008000u;
 static constexpr int SPIN_LIMIT = 1 << 22;
 
+
 // Shared-memory budget of a CTA (K == 1; K == 2 always takes one SM to itself).
 //   CFG 0 (default)  104 KB of rings and staging, padded to 120 KB: one sweep CTA per SM, and room beside it for a CTA of
 //                    the cost kernel of ANOTHER frame (92 KB) -- measured best both for one frame at a time and for two
@@ -102,12 +103,16 @@ __device__ __forceinline__ void st_volatile(uint4* p, const uint4& v)
 
 // Wait until *flag >= need (shared-memory progress counter of a neighbouring warp).  Bounded: on overrun (or when
 // any other waiter has already given up) raise the error flag and stop waiting for good.
-__device__ __forceinline__ void wait_prog(volatile int* flag, int need, int& seen, int* err)
+__device__ __forceinline__ void wait_prog(volatile int* flag, int need, int& seen, int* err, int eager_spins = 64)
 {
     if (seen < need) {
         int spins = 0;
         while ((seen = *flag) < need) {
-            if (++spins > 64) __nanosleep(spins > 4096 ? 400 : 40);     // a band that is not yet due must not steal issue slots
+            // A warp that is not yet due (or is held back by back-pressure: small eager_spins) must not steal issue slots.
+            // Measured alternatives, all ~5 % SLOWER: a tight load/compare/branch poll (it issues more often than this
+            // loop and takes slots from the warps that do the work), the same with a 32 ns sleep per poll, and sleeping
+            // sooner (a sleep on the band-to-band critical path costs more than the polling it saves).
+            if (++spins > eager_spins) __nanosleep(spins > 4096 ? 400 : (eager_spins > 1 ? 40 : 150));
             if ((spins & 1023) == 0 && (spins > SPIN_LIMIT || *reinterpret_cast<volatile int*>(err) != 0)) {
                 *err = 1;
                 seen = 0x7fffffff;
@@ -140,9 +145,10 @@ __device__ __forceinline__ void wta_eval(const unsigned (&s)[4 * K], int l, cons
     const bool padlane = HASPAD && dlane >= a.D;
     unsigned kmin = 0xFFFFFFFFu;
 #pragma unroll
-    for (int e = 0; e < 4 * K; ++e) {
-        const unsigned klo = s[e] * 65536u + (unsigned)(dlane + 2 * e);
-        const unsigned khi = (s[e] & 0xFFFF0000u) | (unsigned)(dlane + 2 * e + 1);
+    for (int e = 0; e < 4 * K; ++e) {   // register 4k+i holds disparities (8k+i, 8k+4+i) of the lane, see vec_pos
+        const int d = dlane + 8 * (e >> 2) + (e & 3);
+        const unsigned klo = s[e] * 65536u + (unsigned)d;
+        const unsigned khi = (s[e] & 0xFFFF0000u) | (unsigned)(d + 4);
         kmin = __vimin3_u32(kmin, klo, khi);
     }
     if (padlane) kmin = 0xFFFFFFFFu;
@@ -160,7 +166,8 @@ __device__ __forceinline__ void wta_eval(const unsigned (&s)[4 * K], int l, cons
     if (padlane || Tm < 0) cnt = 0;
     const int total = __reduce_add_sync(FULL, cnt);
     // the winner's neighbours (clamped addresses; the values only count where they exist)
-    const int sm = scratch[max(best - 1, 0)], sp = scratch[min(best + 1, a.D - 1)];
+    const int dm = max(best - 1, 0), dp = min(best + 1, a.D - 1);
+    const int sm = scratch[(dm & ~7) + vec_pos(dm & 7)], sp = scratch[(dp & ~7) + vec_pos(dp & 7)];
     const int inwin = (minS <= Tm) + (best > 0 && sm <= Tm) + (best < a.D - 1 && sp <= Tm);
     key = kmin;
     nb = (unsigned)sm | ((unsigned)sp << 16) | (total <= inwin ? 0x80000000u : 0u);
@@ -544,6 +551,363 @@ static void launch_sweep_c(const int16_t* C, int16_t* S, const SweepArgs& a, cud
     kern<<<grid, SW_THREADS, Cfg::SMEM, st>>>(reinterpret_cast<const uint4*>(C), reinterpret_cast<uint4*>(S), a);
 }
 
+// ================================================================================================
+// Two warps per image row (K == 1, four directions).  A sweep is latency-bound per warp (one SM runs 8 row-warps at
+// ~0.55 IPC per scheduler; 16 rows per CTA showed +40 % SM throughput at twice the warps), but the number of rows in
+// flight is fixed by the wavefront -- so the work of ONE row is split over two warps instead:
+//   warp A   horizontal path (one pixel ahead) + the (x-1,y-1) path [+ the (x,y-1) path in the winner-take-all sweep]
+//            -> partial sum of its L into a small exchange ring
+//   warp B   the (x+1,y-1) path [+ the (x,y-1) path otherwise], S stream, total, S store or winner-take-all
+// A rows trail each other by one column, B rows by two; A runs ahead of B by at most the exchange depth.  Each role has
+// its own progress counters, its own part of every ring slot and of the band hand-off buffer, and its own helper warp.
+// ================================================================================================
+struct W2Cfg {
+    static constexpr int NS = 5, NE = 4, PFA = 5, PFB = 4, PFS = 4, HD = 3;
+    static constexpr int SLOT_V = 3 * 32, RING_V = NS * SLOT_V;
+    static constexpr int RINGS_V = SW_R * RING_V;
+    static constexpr int EX_V = SW_R * NE * 32;
+    static constexpr int SCR_V = SW_R * 32;
+    static constexpr int STA_V = SW_R * PFA * 32, STB_V = SW_R * PFB * 32, STS_V = SW_R * PFS * 32;
+    static constexpr int SMEM = (RINGS_V + EX_V + SCR_V + STA_V + STB_V + STS_V) * 16;
+    static constexpr int THREADS = (2 * SW_R + 2) * 32;
+};
+
+// helper warp of one role: forwards states q in [QLO, QLO+QN) of the previous band's last row into ring 0
+template <int QLO, int QN>
+__device__ __forceinline__ void w2_helper(const SweepArgs& a, uint4* smem, volatile int* prog, int band, int l)
+{
+    using Cfg = W2Cfg;
+    constexpr int NS = Cfg::NS;
+    if (band == 0) return;
+    const uint4* src = a.bnd + (size_t)(band - 1) * ((size_t)a.W1 * Cfg::SLOT_V) + QLO * 32 + l;
+    uint4* ring = smem + QLO * 32 + l;                     // ring 0
+    uint4 hb[Cfg::HD][QN];
+    int seen = 0, spins = 0;
+    for (int x = 0; x < a.W1;) {
+#pragma unroll
+        for (int u = 0; u < Cfg::HD; ++u)
+#pragma unroll
+            for (int j = 0; j < QN; ++j) hb[u][j] = ld_volatile(src + (size_t)min(x + u, a.W1 - 1) * Cfg::SLOT_V + j * 32);
+        int n = 0;
+        bool prefix = true;
+#pragma unroll
+        for (int u = 0; u < Cfg::HD; ++u) {
+            bool ok = x + u < a.W1;
+#pragma unroll
+            for (int j = 0; j < QN; ++j)
+                ok = ok && ((hb[u][j].x & TAGBITS) == a.tag) && ((hb[u][j].y & TAGBITS) == a.tag) &&
+                     ((hb[u][j].z & TAGBITS) == a.tag) && ((hb[u][j].w & TAGBITS) == a.tag);
+            prefix = prefix && __all_sync(FULL, ok);
+            if (prefix) n = u + 1;
+        }
+        if (n == 0) {
+            if ((++spins & 255) == 0 && (spins > (SPIN_LIMIT >> 2) || *reinterpret_cast<volatile int*>(a.err) != 0)) {
+                *a.err = 2;
+                return;
+            }
+            __nanosleep(spins > 64 ? 200 : 20);
+            continue;
+        }
+        spins = 0;
+        wait_prog(&prog[1], x + n - 1 - NS + 2, seen, a.err);
+#pragma unroll
+        for (int u = 0; u < Cfg::HD; ++u)
+            if (u < n) {
+#pragma unroll
+                for (int j = 0; j < QN; ++j)
+                    ring[((x + u) % NS) * Cfg::SLOT_V + j * 32] =
+                        make_uint4(hb[u][j].x & ~TAGBITS, hb[u][j].y & ~TAGBITS, hb[u][j].z & ~TAGBITS, hb[u][j].w & ~TAGBITS);
+            }
+        __syncwarp();
+        asm volatile("" ::: "memory");
+        x += n;
+        if (l == 0) prog[0] = x;
+    }
+    if (QLO + QN == 3) {      // the role that owns the (x+1,y-1) path: one more column of zeros (out-of-image predecessor)
+        wait_prog(&prog[1], a.W1 - NS + 2, seen, a.err);
+#pragma unroll
+        for (int j = 0; j < QN; ++j) ring[(a.W1 % NS) * Cfg::SLOT_V + j * 32] = make_uint4(0, 0, 0, 0);
+        __syncwarp();
+        asm volatile("" ::: "memory");
+        if (l == 0) prog[0] = a.W1 + 1;
+    }
+}
+
+// role A of row r
+template <int MODE, bool HASPAD, bool FAST>
+__device__ __forceinline__ void w2_row_a(const uint4* __restrict__ C, const SweepArgs& a, uint4* smem, volatile int* progA,
+                                         volatile int* progB, int band, int r, int l)
+{
+    using Cfg = W2Cfg;
+    constexpr int NS = Cfg::NS, NE = Cfg::NE, PF = Cfg::PFA;
+    constexpr int NA = MODE == 2 ? 2 : 1;            // paths from the row above handled here: q = 0 (x-1,y-1) [, q = 1 (x,y-1)]
+    const unsigned one = a.one;
+    const int yl = band * SW_R + r;
+    if (yl >= a.H) return;
+    const bool top = yl == 0;
+    const int out_mode = yl == a.H - 1 ? 0 : (r < SW_R - 1 ? 1 : 2);
+    const int yp = a.flip ? a.H - 1 - yl : yl;
+    const long long dstep = a.flip ? -(long long)a.Dp8 : (long long)a.Dp8;
+    const uint4* cpf = C + ((size_t)yp * a.W1 + (a.flip ? a.W1 - 1 : 0)) * a.Dp8 + l;
+    const uint4* ring_in = smem + (size_t)r * Cfg::RING_V + l;
+    uint4* ring_out = smem + (size_t)(r + 1) * Cfg::RING_V + l;
+    uint4* bnd_out = a.bnd + (size_t)band * ((size_t)a.W1 * Cfg::SLOT_V) + l;
+    uint4* ex = smem + Cfg::RINGS_V + (size_t)r * NE * 32 + l;
+    uint4* stage = smem + Cfg::RINGS_V + Cfg::EX_V + Cfg::SCR_V + (size_t)r * PF * 32 + l;
+    volatile int* prog_in = &progA[r];
+    volatile int* prog_me = &progA[r + 1];
+    volatile int* prog_next = &progA[r + 2 <= SW_R ? r + 2 : SW_R];
+    volatile int* prog_b = &progB[r + 1];
+    int seen_in = 0, seen_next = 0, seen_b = 0;
+    unsigned padm[1] = {(l * 8 >= a.D) ? SAT2 : 0u};
+
+    const unsigned st = (unsigned)__cvta_generic_to_shared(stage);
+    for (int i = 0; i < PF; ++i) {
+        if (i < a.W1) cp_async16(st + i * 32 * 16, cpf);
+        cp_async_commit();
+        cpf += dstep;
+    }
+    unsigned Nh[4] = {0, 0, 0, 0}, Cc[4], Lh[4];
+    cp_async_wait<PF - 1>();
+    { const uint4 c = stage[0]; Cc[0] = c.x; Cc[1] = c.y; Cc[2] = c.z; Cc[3] = c.w; }
+    agg_step<32, 4, HASPAD, FAST>(Nh, Cc, Lh, l, a.P1p, a.P2mP1p, padm, one);
+
+    int pslot = 0;
+    for (int x = 0; x < a.W1; ++x) {
+        const int nslot = pslot + 1 == PF ? 0 : pslot + 1;
+        unsigned Cn[4], Lhn[4], v[NA][4], Nd[NA][4];
+        cp_async_wait<PF - 2>();
+        { const uint4 c = stage[nslot * 32]; Cn[0] = c.x; Cn[1] = c.y; Cn[2] = c.z; Cn[3] = c.w; }
+        if (top) {
+#pragma unroll
+            for (int q = 0; q < NA; ++q) Nd[q][0] = Nd[q][1] = Nd[q][2] = Nd[q][3] = 0;
+        } else {
+            wait_prog(prog_in, x + 1, seen_in, a.err);          // column x of the row above (its column -1 is a zero slot)
+            const int sl[2] = {(x + NS - 1) % NS, x % NS};
+#pragma unroll
+            for (int q = 0; q < NA; ++q) {
+                const uint4 t = ring_in[sl[q] * Cfg::SLOT_V + q * 32];
+                Nd[q][0] = t.x; Nd[q][1] = t.y; Nd[q][2] = t.z; Nd[q][3] = t.w;
+            }
+        }
+        agg_step<32, 4, HASPAD, FAST>(Nh, Cn, Lhn, l, a.P1p, a.P2mP1p, padm, one);
+#pragma unroll
+        for (int q = 0; q < NA; ++q) agg_step<32, 4, HASPAD, FAST>(Nd[q], Cc, v[q], l, a.P1p, a.P2mP1p, padm, one);
+        if (out_mode == 1) {
+            wait_prog(prog_next, x - NS + 2, seen_next, a.err);
+#pragma unroll
+            for (int q = 0; q < NA; ++q)
+                ring_out[(x % NS) * Cfg::SLOT_V + q * 32] = make_uint4(Nd[q][0], Nd[q][1], Nd[q][2], Nd[q][3]);
+        } else if (out_mode == 2) {
+#pragma unroll
+            for (int q = 0; q < NA; ++q)
+                st_volatile(bnd_out + (size_t)x * Cfg::SLOT_V + q * 32,
+                            make_uint4(Nd[q][0] | a.tag, Nd[q][1] | a.tag, Nd[q][2] | a.tag, Nd[q][3] | a.tag));
+        }
+        // partial sum of this warp's L for warp B (B publishes column c before it reads the exchange slot of c: hence +2)
+        unsigned pa[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            pa[j] = sat_add_split(Lh[j], v[0][j], one);
+            if (NA == 2) pa[j] = sat_add_split(pa[j], v[1][j], one);
+        }
+        wait_prog(prog_b, x - NE + 2, seen_b, a.err, 0);       // back-pressure: warp A has slack, let it sleep
+        ex[(x % NE) * 32] = make_uint4(pa[0], pa[1], pa[2], pa[3]);
+        __syncwarp();
+        asm volatile("" ::: "memory");
+        if (l == 0) *prog_me = x + 1;
+        if (x + PF < a.W1) cp_async16(st + pslot * 32 * 16, cpf);
+        cp_async_commit();
+        cpf += dstep;
+        pslot = nslot;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { Cc[j] = Cn[j]; Lh[j] = Lhn[j]; }
+    }
+    cp_async_wait<0>();
+}
+
+// role B of row r
+template <int MODE, bool HASPAD, bool FAST>
+__device__ __forceinline__ void w2_row_b(const uint4* __restrict__ C, uint4* __restrict__ S, const SweepArgs& a, uint4* smem,
+                                         volatile int* progA, volatile int* progB, int band, int r, int l)
+{
+    using Cfg = W2Cfg;
+    constexpr int NS = Cfg::NS, NE = Cfg::NE, PF = Cfg::PFB, PFS = Cfg::PFS;
+    constexpr int NB = MODE == 2 ? 1 : 2;            // paths from the row above handled here: [q = 1 (x,y-1),] q = 2 (x+1,y-1)
+    constexpr int Q0 = 3 - NB;
+    const unsigned one = a.one;
+    const int yl = band * SW_R + r;
+    if (yl >= a.H) return;
+    const bool top = yl == 0;
+    const int out_mode = yl == a.H - 1 ? 0 : (r < SW_R - 1 ? 1 : 2);
+    const int yp = a.flip ? a.H - 1 - yl : yl;
+    const long long dstep = a.flip ? -(long long)a.Dp8 : (long long)a.Dp8;
+    const size_t first = ((size_t)yp * a.W1 + (a.flip ? a.W1 - 1 : 0)) * a.Dp8 + l;
+    const uint4* cpf = C + first;
+    const uint4* spf = S + first;
+    uint4* scur = S + first;
+    const uint4* ring_in = smem + (size_t)r * Cfg::RING_V + l;
+    uint4* ring_out = smem + (size_t)(r + 1) * Cfg::RING_V + l;
+    uint4* bnd_out = a.bnd + (size_t)band * ((size_t)a.W1 * Cfg::SLOT_V) + l;
+    const uint4* ex = smem + Cfg::RINGS_V + (size_t)r * NE * 32 + l;
+    int16_t* scratch = reinterpret_cast<int16_t*>(smem + Cfg::RINGS_V + Cfg::EX_V + (size_t)r * 32);
+    uint4* stageC = smem + Cfg::RINGS_V + Cfg::EX_V + Cfg::SCR_V + Cfg::STA_V + (size_t)r * PF * 32 + l;
+    uint4* stageS = smem + Cfg::RINGS_V + Cfg::EX_V + Cfg::SCR_V + Cfg::STA_V + Cfg::STB_V + (size_t)r * PFS * 32 + l;
+    volatile int* prog_in = &progB[r];
+    volatile int* prog_me = &progB[r + 1];
+    volatile int* prog_next = &progB[r + 2 <= SW_R ? r + 2 : SW_R];
+    volatile int* prog_a = &progA[r + 1];
+    int seen_in = 0, seen_next = 0, seen_a = 0;
+    unsigned padm[1] = {(l * 8 >= a.D) ? SAT2 : 0u};
+    static_assert(PFS == PF, "one commit group per pixel carries C(x+PF) and S(x+PF)");
+
+    const unsigned stC = (unsigned)__cvta_generic_to_shared(stageC), stS = (unsigned)__cvta_generic_to_shared(stageS);
+    for (int i = 0; i < PF; ++i) {
+        if (i < a.W1) {
+            cp_async16(stC + i * 32 * 16, cpf);
+            if (MODE != 0) cp_async16(stS + i * 32 * 16, spf);
+        }
+        cp_async_commit();
+        cpf += dstep; spf += dstep;
+    }
+    unsigned vsp[4] = {0, 0, 0, 0};
+    unsigned wkey = 0, wnb = 0, rkey = 0, rnb = 0;
+    unsigned long long* keys_row = a.keys + (size_t)yp * a.W;
+    int16_t* d1_row = a.d1 + (size_t)yp * a.W;
+
+    int pslot = 0;
+    for (int x = 0; x < a.W1; ++x) {
+        unsigned Cc[4], vs[4], v[NB][4], Nd[NB][4];
+        cp_async_wait<PF - 1>();
+        { const uint4 c = stageC[pslot * 32]; Cc[0] = c.x; Cc[1] = c.y; Cc[2] = c.z; Cc[3] = c.w; }
+        if (top) {
+#pragma unroll
+            for (int q = 0; q < NB; ++q) Nd[q][0] = Nd[q][1] = Nd[q][2] = Nd[q][3] = 0;
+        } else {
+            wait_prog(prog_in, x + 2, seen_in, a.err);          // column x+1 of the row above (its column W1 is a zero slot)
+            const int sl[3] = {0, x % NS, (x + 1) % NS};
+#pragma unroll
+            for (int q = 0; q < NB; ++q) {
+                const uint4 t = ring_in[sl[Q0 + q] * Cfg::SLOT_V + (Q0 + q) * 32];
+                Nd[q][0] = t.x; Nd[q][1] = t.y; Nd[q][2] = t.z; Nd[q][3] = t.w;
+            }
+        }
+        if (MODE == 2) wta_eval<1, HASPAD>(vsp, l, a, scratch, wkey, wnb);      // previous pixel, an independent chain
+#pragma unroll
+        for (int q = 0; q < NB; ++q) agg_step<32, 4, HASPAD, FAST>(Nd[q], Cc, v[q], l, a.P1p, a.P2mP1p, padm, one);
+        if (out_mode == 1) {
+            wait_prog(prog_next, x - NS + 2, seen_next, a.err);
+#pragma unroll
+            for (int q = 0; q < NB; ++q)
+                ring_out[(x % NS) * Cfg::SLOT_V + (Q0 + q) * 32] = make_uint4(Nd[q][0], Nd[q][1], Nd[q][2], Nd[q][3]);
+        } else if (out_mode == 2) {
+#pragma unroll
+            for (int q = 0; q < NB; ++q)
+                st_volatile(bnd_out + (size_t)x * Cfg::SLOT_V + (Q0 + q) * 32,
+                            make_uint4(Nd[q][0] | a.tag, Nd[q][1] | a.tag, Nd[q][2] | a.tag, Nd[q][3] | a.tag));
+        }
+        __syncwarp();
+        asm volatile("" ::: "memory");
+        if (l == 0) *prog_me = x + 1;               // rows below may go on; the exchange slot of x is read only now
+        // ---- total: S_in + warp A's partial sum + this warp's L
+        wait_prog(prog_a, x + 1, seen_a, a.err);
+        { const uint4 pa = ex[(x % NE) * 32]; vs[0] = pa.x; vs[1] = pa.y; vs[2] = pa.z; vs[3] = pa.w; }
+        if (MODE != 0) {
+            const uint4 sv = stageS[pslot * 32];
+            vs[0] = sat_add_split(vs[0], sv.x, one); vs[1] = sat_add_split(vs[1], sv.y, one);
+            vs[2] = sat_add_split(vs[2], sv.z, one); vs[3] = sat_add_split(vs[3], sv.w, one);
+        }
+#pragma unroll
+        for (int q = 0; q < NB; ++q)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) vs[j] = sat_add_split(vs[j], v[q][j], one);
+        if (MODE == 2) {
+            if (l == ((x - 1) & 31)) { rkey = wkey; rnb = wnb; }
+            if (x > 0 && (x & 31) == 0) wta_flush(rkey, rnb, x - 32 + l, true, a, keys_row, d1_row);
+            __syncwarp();
+            reinterpret_cast<uint4*>(scratch)[l] = make_uint4(vs[0], vs[1], vs[2], vs[3]);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) vsp[j] = vs[j];
+            __syncwarp();
+        } else {
+            stg_stream(scur, make_uint4(vs[0], vs[1], vs[2], vs[3]));
+        }
+        scur += dstep;
+        if (x + PF < a.W1) {
+            cp_async16(stC + pslot * 32 * 16, cpf);
+            if (MODE != 0) cp_async16(stS + pslot * 32 * 16, spf);
+        }
+        cp_async_commit();
+        cpf += dstep; spf += dstep;
+        pslot = pslot + 1 == PF ? 0 : pslot + 1;
+    }
+    cp_async_wait<0>();
+    if (MODE == 2) {
+        wta_eval<1, HASPAD>(vsp, l, a, scratch, wkey, wnb);
+        if (l == ((a.W1 - 1) & 31)) { rkey = wkey; rnb = wnb; }
+        const int xb = (a.W1 - 1) & ~31;
+        wta_flush(rkey, rnb, xb + l, xb + l < a.W1, a, keys_row, d1_row);
+    }
+    if (out_mode == 1) {      // the extra zero column for the (x+1,y-1) path of the row below
+        wait_prog(prog_next, a.W1 - NS + 2, seen_next, a.err);
+#pragma unroll
+        for (int q = 0; q < NB; ++q) ring_out[(a.W1 % NS) * Cfg::SLOT_V + (Q0 + q) * 32] = make_uint4(0, 0, 0, 0);
+        __syncwarp();
+        asm volatile("" ::: "memory");
+        if (l == 0) *prog_me = a.W1 + 1;
+    }
+}
+
+template <int MODE, bool HASPAD>
+__global__ void __launch_bounds__(W2Cfg::THREADS, 1)
+sweep2w_kernel(const uint4* __restrict__ C, uint4* __restrict__ S, SweepArgs a)
+{
+    using Cfg = W2Cfg;
+    extern __shared__ __align__(16) uint4 smem[];
+    __shared__ volatile int progA[SW_R + 1], progB[SW_R + 1];
+    __shared__ int s_band;
+    const int tid = threadIdx.x, warp = tid >> 5, l = tid & 31;
+    if (tid == 0) {      // one worker per SM and launch (see sweep_kernel)
+        unsigned sm;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(sm));
+        s_band = atomicAdd(a.ticket + 2 + min(sm, 250u), 1) == 0 ? 0 : -1;
+    }
+    __syncthreads();
+    if (s_band < 0) return;
+    const bool fast = *a.maxC + a.P2 <= 32767;
+    const int nbands = (a.H + SW_R - 1) / SW_R;
+    constexpr int NA = MODE == 2 ? 2 : 1;
+    while (true) {
+        __syncthreads();
+        if (tid == 0) s_band = atomicAdd(a.ticket, 1);
+        if (tid <= SW_R) { progA[tid] = 0; progB[tid] = 0; }
+        for (int i = tid; i < Cfg::RINGS_V; i += Cfg::THREADS) smem[i] = make_uint4(0, 0, 0, 0);
+        __syncthreads();
+        const int band = s_band;
+        if (band >= nbands) break;
+        if (warp == 2 * SW_R) {
+            w2_helper<0, NA>(a, smem, progA, band, l);
+        } else if (warp == 2 * SW_R + 1) {
+            w2_helper<NA, 3 - NA>(a, smem, progB, band, l);
+        } else if ((warp & 1) == 0) {
+            if (fast) w2_row_a<MODE, HASPAD, true>(C, a, smem, progA, progB, band, warp >> 1, l);
+            else      w2_row_a<MODE, HASPAD, false>(C, a, smem, progA, progB, band, warp >> 1, l);
+        } else {
+            if (fast) w2_row_b<MODE, HASPAD, true>(C, S, a, smem, progA, progB, band, warp >> 1, l);
+            else      w2_row_b<MODE, HASPAD, false>(C, S, a, smem, progA, progB, band, warp >> 1, l);
+        }
+    }
+}
+
+template <int MODE, bool HASPAD>
+static void launch_sweep2w_t(const int16_t* C, int16_t* S, const SweepArgs& a, cudaStream_t st)
+{
+    auto kern = sweep2w_kernel<MODE, HASPAD>;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, W2Cfg::SMEM);
+    cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    kern<<<a.num_sms, W2Cfg::THREADS, W2Cfg::SMEM, st>>>(reinterpret_cast<const uint4*>(C), reinterpret_cast<uint4*>(S), a);
+}
+
 static int g_sweep_cfg = -1;
 void set_sweep_cfg(int cfg) { g_sweep_cfg = cfg; }
 
@@ -589,6 +953,15 @@ void launch_sweep(const int16_t* C, int16_t* S, int flip, int mode, int ndir, co
     a.minD = p.minD; a.minX1 = p.minX1; a.uniq = p.uniq; a.INVALID = p.INVALID;
     a.umagic = p.uniq < 99 ? (unsigned)((0x100000000ull + (100 - p.uniq) - 1) / (unsigned)(100 - p.uniq)) : 0u;
     const bool pad = p.Dp != p.D;
+    // two warps per row (WSG_AGG_SWEEPS2W_WTA): measured equal to one warp per row at 2448x2048x256 (8.6 ms per frame for
+    // both sweeps): the scheduler issue rate rises from 40 % to 58 %, but the split costs 25 % more instructions per
+    // pixel and the extra progress-counter polling takes the rest.  Kept selectable, not the default.
+    if (sc.two_warps && p.K == 1 && ndir == 4) {
+        if (mode == 0) { if (pad) launch_sweep2w_t<0, true>(C, S, a, st); else launch_sweep2w_t<0, false>(C, S, a, st); }
+        else if (mode == 1) { if (pad) launch_sweep2w_t<1, true>(C, S, a, st); else launch_sweep2w_t<1, false>(C, S, a, st); }
+        else { if (pad) launch_sweep2w_t<2, true>(C, S, a, st); else launch_sweep2w_t<2, false>(C, S, a, st); }
+        return;
+    }
 #define WSG_SW_CASE(k, m, n)                                                         \
     if (p.K == k && mode == m && ndir == n) {                                        \
         if (pad) launch_sweep_t<k, m, n, true>(C, S, a, st);                        \
