@@ -159,10 +159,13 @@ int wsg_run_sgbm(wsg_handle* h, const uint8_t* d_img1, const uint8_t* d_img2, si
         const size_t bbytes = sweep_boundary_bytes(pl);
         const bool grown = bbytes > h->bnd.cap;
         if ((rc = ensure(h, h->bnd, bbytes))) return rc;
-        if (grown || h->bnd_H != pl.H || h->bnd_W1 != pl.W1 || h->bnd_K != pl.K) {
-            // epoch tags only tell "this sweep" from "the previous one" for slots that are rewritten every sweep
+        const int bnd_nd = impl == WSG_AGG_SWEEPS3_WTA ? 3 : 4;
+        if (grown || h->bnd_H != pl.H || h->bnd_W1 != pl.W1 || h->bnd_K != pl.K || h->bnd_nd != bnd_nd) {
+            // epoch tags only tell "this sweep" from "the previous one" for slots that are rewritten every sweep: a change
+            // of geometry, or of the set of states a sweep hands down (the 3-direction sweeps leave one third of every slot
+            // untouched), would let data of an older sweep with the same 2-bit epoch pass for current
             CK(h, cudaMemsetAsync(h->bnd.p, 0, h->bnd.cap, h->stream));
-            h->bnd_H = pl.H; h->bnd_W1 = pl.W1; h->bnd_K = pl.K;
+            h->bnd_H = pl.H; h->bnd_W1 = pl.W1; h->bnd_K = pl.K; h->bnd_nd = bnd_nd;
         }
         const bool fused_wta = (impl == WSG_AGG_SWEEPS_WTA || impl == WSG_AGG_SWEEPS3_WTA || impl == WSG_AGG_SWEEPS2W_WTA) && pl.uniq < 100;   // the in-sweep WTA needs 100-uniq > 0
         if (fused_wta) {

@@ -29,7 +29,7 @@ struct wsg_handle {
     int agg_impl = WSG_AGG_SWEEPS_WTA;
     int num_sms = 0;
     int sweep_epoch = 0;                // 1..3 after the first sweep
-    int bnd_H = 0, bnd_W1 = 0, bnd_K = 0;   // geometry the hand-off buffer was last used with
+    int bnd_H = 0, bnd_W1 = 0, bnd_K = 0, bnd_nd = 0;   // geometry / state set the hand-off buffer was last used with
     SgbmPlan plan{};
     bool have_plan = false;
     wsg_sgbm_stats stats{};
