@@ -18,7 +18,7 @@ def handle():
 
 
 def _supported(p):
-    return p["speckleWindowSize"] <= 0
+    return True
 
 
 IMPLS = [0, 1, 2, 3, 4]   # capi.AGG_*: five device decompositions of the aggregation, one result

@@ -64,7 +64,6 @@ int wsg_make_plan(wsg_handle* h, int rows, int cols, const wsg_sgbm_params* p, S
         h->err = "blockSize must be odd and <= 25"; return WSG_ERR_INVALID_ARG;
     }
     if (p->mode != WSG_MODE_SGBM && p->mode != WSG_MODE_HH) { h->err = "mode must be 0 (SGBM) or 1 (HH)"; return WSG_ERR_INVALID_ARG; }
-    if (p->speckleWindowSize > 0) { h->err = "speckleWindowSize > 0 is not supported yet (off at WASS defaults)"; return WSG_ERR_INVALID_ARG; }
     pl.H = rows; pl.W = cols;
     pl.minD = p->minDisparity; pl.D = p->numDisparities; pl.maxD = pl.minD + pl.D;
     pl.SW2 = pl.SH2 = p->blockSize > 0 ? p->blockSize / 2 : 1;
@@ -79,6 +78,8 @@ int wsg_make_plan(wsg_handle* h, int rows, int cols, const wsg_sgbm_params* p, S
     pl.W1 = pl.maxX1 - pl.minX1;
     pl.INVALID = (pl.minD - 1) * 16;
     pl.mode = p->mode;
+    pl.speckleWindow = p->speckleWindowSize > 0 ? p->speckleWindowSize : 0;
+    pl.speckleMaxDiff = 16 * p->speckleRange;
     // cv2 raises for images this narrow (stereosgbm.cpp:511); mirror it as an error code
     if (cols - (pl.minD + pl.D) <= pl.SW2 || pl.W1 <= 0) { h->err = "image too narrow for minDisparity+numDisparities and blockSize"; return WSG_ERR_TOO_SMALL; }
     const int NV = pl.D / 8;
@@ -221,9 +222,14 @@ int wsg_run_sgbm(wsg_handle* h, const uint8_t* d_img1, const uint8_t* d_img2, si
     }
     h->stats.agg_impl = impl;
     {
-        StageTimer t(h, WSG_STAGE_MEDIAN, 1);
+        const int nsp = pl.speckleWindow > 0 ? 4 : 0;
+        if (nsp && (rc = ensure(h, h->keys, npix * sizeof(unsigned long long)))) return rc;   // free again after the LR check
+        StageTimer t(h, WSG_STAGE_MEDIAN, 1 + nsp);
         launch_median3((const int16_t*)h->raw.p, d_disp, pl.H, pl.W, h->stream);
-        launches += 1;
+        if (nsp)
+            launch_filter_speckles(d_disp, pl.H, pl.W, pl.INVALID, pl.speckleWindow, pl.speckleMaxDiff, (int*)h->keys.p,
+                                   (unsigned*)h->keys.p + npix, h->stream);
+        launches += 1 + nsp;
     }
     CK(h, cudaGetLastError());
     h->stats.kernel_launches = launches;

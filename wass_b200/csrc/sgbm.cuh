@@ -16,6 +16,7 @@ struct SgbmPlan {
     int minX1, maxX1, W1;     // matched column range in image space, W1 = maxX1-minX1
     int INVALID;              // (minD-1)*16
     int mode;                 // 0 = 5 paths, 1 = 8 paths
+    int speckleWindow, speckleMaxDiff;   // cv::filterSpeckles after the median when speckleWindow > 0 (maxDiff = 16*speckleRange)
     // volume layout: int16 [H][W1][Dp]; a pixel's Dp slots are NL*K vectors of 8 disparities (interleaved: vec_pos).
     // memory vector slot s = k*NL + l holds logical vector j = l*K + k (disparities 8j..8j+7), so
     // that lane l of a pixel group owns K*8 consecutive disparities and each of its K loads is
@@ -37,6 +38,9 @@ void launch_cost(const uint2* pre1, const uint2* pre2, int16_t* C, int* maxC, co
 void launch_aggregate_dir(const int16_t* C, int16_t* S, int dir, bool first, const SgbmPlan& p, cudaStream_t st);
 void launch_wta(const int16_t* S, int16_t* raw, const SgbmPlan& p, cudaStream_t st);
 void launch_median3(const int16_t* src, int16_t* dst, int rows, int cols, cudaStream_t st);
+// cv::filterSpeckles on the final x16 disparity (in place); labels / counts: rows*cols ints each
+void launch_filter_speckles(int16_t* disp, int rows, int cols, int invalid, int maxSpeckleSize, int maxDiff, int* labels,
+                            unsigned* counts, cudaStream_t st);
 int cost_smem_bytes(const SgbmPlan& p);
 // wide-tile cost kernel (cost_kernels.cu): windows up to 17; launch_cost picks it unless WSG_COST_IMPL=0
 bool cost_wide_supported(const SgbmPlan& p);

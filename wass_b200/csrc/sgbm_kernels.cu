@@ -556,4 +556,73 @@ void launch_median3(const int16_t* src, int16_t* dst, int rows, int cols, cudaSt
     median3_kernel<<<g, b, 0, st>>>(src, dst, rows, cols);
 }
 
+// ------------------------------------------------------------------------------------------------
+// A.7 (optional): cv::filterSpeckles as StereoSGBM::compute calls it when speckleWindowSize > 0
+// (wass_stereo.cpp:781-782 sets the two parameters; off at the reference's defaults).  The flood fill of the
+// reference visits 4-neighbours whose values differ by at most maxDiff = 16*speckleRange, so its regions are the
+// connected components of that (symmetric) relation among valid pixels: lock-free union-find with atomicMin,
+// component sizes, then every pixel of a component of at most speckleWindowSize pixels becomes invalid.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int sp_find(const int* L, int x)
+{
+    int p = L[x];
+    while (p != x) { x = p; p = L[x]; }
+    return x;
+}
+__device__ __forceinline__ void sp_union(int* L, int a, int b)
+{
+    while (true) {
+        a = sp_find(L, a); b = sp_find(L, b);
+        if (a == b) return;
+        if (a > b) { const int t = a; a = b; b = t; }
+        const int old = atomicMin(&L[b], a);
+        if (old == b) return;
+        b = old;
+    }
+}
+__global__ void speckle_init_kernel(const int16_t* __restrict__ d, int* __restrict__ L, unsigned* __restrict__ cnt, int n, int invalid)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    L[i] = d[i] == invalid ? -1 : i;
+    cnt[i] = 0;
+}
+__global__ void speckle_merge_kernel(const int16_t* __restrict__ d, int* L, int rows, int cols, int invalid, int maxDiff)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= cols) return;
+    const int i = y * cols + x;
+    const int v = d[i];
+    if (v == invalid) return;
+    if (x + 1 < cols) { const int w = d[i + 1]; if (w != invalid && abs(v - w) <= maxDiff) sp_union(L, i, i + 1); }
+    if (y + 1 < rows) { const int w = d[i + cols]; if (w != invalid && abs(v - w) <= maxDiff) sp_union(L, i, i + cols); }
+}
+__global__ void speckle_count_kernel(int* L, unsigned* cnt, int n)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n || L[i] < 0) return;
+    const int r = sp_find(L, i);
+    L[i] = r;
+    atomicAdd(&cnt[r], 1u);
+}
+__global__ void speckle_apply_kernel(int16_t* d, const int* __restrict__ L, const unsigned* __restrict__ cnt, int n, int invalid,
+                                     unsigned maxSize)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n || L[i] < 0) return;
+    if (cnt[L[i]] <= maxSize) d[i] = (int16_t)invalid;
+}
+
+void launch_filter_speckles(int16_t* disp, int rows, int cols, int invalid, int maxSpeckleSize, int maxDiff, int* labels,
+                            unsigned* counts, cudaStream_t st)
+{
+    const int n = rows * cols;
+    const int nb = (n + 255) / 256;
+    speckle_init_kernel<<<nb, 256, 0, st>>>(disp, labels, counts, n, invalid);
+    dim3 b(256), g((cols + 255) / 256, rows);
+    speckle_merge_kernel<<<g, b, 0, st>>>(disp, labels, rows, cols, invalid, maxDiff);
+    speckle_count_kernel<<<nb, 256, 0, st>>>(labels, counts, n);
+    speckle_apply_kernel<<<nb, 256, 0, st>>>(disp, labels, counts, n, invalid, (unsigned)maxSpeckleSize);
+}
+
 }  // namespace wsg
