@@ -128,6 +128,8 @@ typedef struct wsg_dense_params {
     int DENSE_SPECKLE_RANGE;
     int DENSE_SPECKLE_WINDOW_SIZE;
     int mode;                     /* WSG_MODE_SGBM (reference default) or WSG_MODE_HH */
+    int MEDIAN_FILTER_WSIZE;      /* 0 = off (default); 3 or 5: cv::medianBlur on the float disparity (wass_stereo.cpp:941-945) */
+    int DENSE_DISPARITY_BIGGEST_COMPONENT_THRESHOLD;   /* 0 = off (default); > 0: wass_stereo.cpp:947-986 */
 } wsg_dense_params;
 void wsg_dense_params_default(wsg_dense_params* p);
 
@@ -141,6 +143,11 @@ int wsg_dense_stereo(wsg_handle* h, const uint8_t* left_crop, const uint8_t* rig
 int wsg_disparity_postprocess(wsg_handle* h, const int16_t* disp16_roi, int rows, int cols, int minDisparity,
                               int numDisparities, int disparityOffset, double denseScale, int dilateSteps,
                               int erosionSteps, float* disp_roi);
+
+/* Replaces wass_stereo.cpp:941-986 alone (both steps off at the reference defaults): optional cv::medianBlur (3 or 5) of
+ * the float ROI disparity, then -- if bc_threshold > 0 -- zero where the squared Sobel gradient magnitude exceeds it and
+ * keep only the biggest 8-connected component of the non-zero pixels.  disp_roi: HOST, rows x cols float32, in place. */
+int wsg_disparity_refine(wsg_handle* h, float* disp_roi, int rows, int cols, int median_wsize, int bc_threshold);
 
 /* ---- triangulation + PovMesh ---------------------------------------------------------------------- */
 /* Calibration after load_data()+rectify() (wass_stereo.cpp:337-613), all row-major doubles.

@@ -92,6 +92,77 @@ def postprocess_disparity(disp16_roi, mindisp, num_disp, disparity_offset=0, den
 # ----------------------------------------------------------------------------------------------
 # triangulation  (wass_stereo.cpp:299-324, 1039-1386; src/wass_lib/triangulate.hpp:26-72)
 # ----------------------------------------------------------------------------------------------
+def median_f32(img, ksize):
+    """cv::medianBlur on float32 (ksize 3 or 5, replicate border), wass_stereo.cpp:941-945."""
+    r = ksize // 2
+    p = np.pad(np.asarray(img, np.float32), r, mode="edge")
+    H, W = img.shape
+    st = np.stack([p[i:i + H, j:j + W] for i in range(ksize) for j in range(ksize)], 0)
+    return np.sort(st, 0)[ksize * ksize // 2]
+
+
+def gradient_mask(img, threshold):
+    """wass_stereo.cpp:947-963: zero where Sobel gx^2 + gy^2 > threshold.  Float operation order of cv::Sobel (3x3,
+    BORDER_REFLECT_101), found by matching cv2 bit for bit: gx = ((d[y-1]+d[y+1]) + 2 d[y]), d = p[x+1]-p[x-1];
+    gy = s[y+1]-s[y-1], s = ((p[x-1]+p[x+1]) + 2 p[x])."""
+    f = np.float32
+    a = np.asarray(img, f)
+    p = np.pad(a, 1, mode="reflect")
+    d = (p[:, 2:] - p[:, :-2]).astype(f)
+    gx = ((d[:-2] + d[2:]).astype(f) + (f(2) * d[1:-1]).astype(f)).astype(f)
+    sm = ((p[:, :-2] + p[:, 2:]).astype(f) + (f(2) * p[:, 1:-1]).astype(f)).astype(f)
+    gy = (sm[2:] - sm[:-2]).astype(f)
+    g2 = ((gx * gx).astype(f) + (gy * gy).astype(f)).astype(f)
+    out = a.copy()
+    out[g2 > f(threshold)] = 0
+    return out
+
+
+def keep_biggest_component8(img):
+    """wass_stereo.cpp:965-985: biggest 8-connected component of the non-zero pixels (cv::connectedComponentsWithStats,
+    strict '>' over increasing labels).  cv2 numbers components by their first 2x2 block in block-raster order, which
+    decides ties."""
+    a = np.asarray(img, np.float32)
+    H, W = a.shape
+    lab = -np.ones((H, W), np.int64)
+    nxt = 0
+    for y in range(H):
+        for x in range(W):
+            if a[y, x] == 0 or lab[y, x] >= 0:
+                continue
+            stack = [(y, x)]
+            lab[y, x] = nxt
+            while stack:
+                cy, cx = stack.pop()
+                for dy in (-1, 0, 1):
+                    for dx in (-1, 0, 1):
+                        yy, xx = cy + dy, cx + dx
+                        if 0 <= yy < H and 0 <= xx < W and a[yy, xx] != 0 and lab[yy, xx] < 0:
+                            lab[yy, xx] = nxt
+                            stack.append((yy, xx))
+            nxt += 1
+    out = a.copy()
+    if nxt == 0:
+        return out
+    ys, xs = np.nonzero(lab >= 0)
+    area = np.bincount(lab[ys, xs], minlength=nxt)
+    key = np.full(nxt, 1 << 62)
+    np.minimum.at(key, lab[ys, xs], (ys // 2) * ((W + 1) // 2) + xs // 2)
+    best = min(range(nxt), key=lambda i: (-area[i], key[i]))
+    out[lab != best] = 0
+    return out
+
+
+def refine_disparity(disp, median_wsize=0, bc_threshold=0):
+    """wass_stereo.cpp:941-986 in order."""
+    d = np.asarray(disp, np.float32)
+    if median_wsize >= 3:
+        d = median_f32(d, median_wsize)
+    if bc_threshold > 0:
+        d = keep_biggest_component8(gradient_mask(d, bc_threshold))
+    return d
+
+
 def solve3_lu(A, b):
     """cv::solve(A,b,x,DECOMP_LU) for 3x3: OpenCV's closed-form (Cramer) fast path, in double."""
     det = (A[0, 0] * (A[1, 1] * A[2, 2] - A[1, 2] * A[2, 1]) - A[0, 1] * (A[1, 0] * A[2, 2] - A[1, 2] * A[2, 0]) +

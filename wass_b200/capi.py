@@ -42,7 +42,8 @@ class DenseParams(ctypes.Structure):
                 ("DISP_EROSION_STEPS", ctypes.c_int), ("DENSE_P1_MULT", ctypes.c_int), ("DENSE_P2_MULT", ctypes.c_int),
                 ("DENSE_UNIQUENESS_RATIO", ctypes.c_int), ("DENSE_DISP12MAXDIFF", ctypes.c_int),
                 ("DENSE_PREFILTER_CAP", ctypes.c_int), ("DENSE_SPECKLE_RANGE", ctypes.c_int),
-                ("DENSE_SPECKLE_WINDOW_SIZE", ctypes.c_int), ("mode", ctypes.c_int)]
+                ("DENSE_SPECKLE_WINDOW_SIZE", ctypes.c_int), ("mode", ctypes.c_int),
+                ("MEDIAN_FILTER_WSIZE", ctypes.c_int), ("DENSE_DISPARITY_BIGGEST_COMPONENT_THRESHOLD", ctypes.c_int)]
 
 
 class Calib(ctypes.Structure):
@@ -123,6 +124,7 @@ def load():
     lib.wsg_refine_params_default.restype = None
     lib.wsg_dense_stereo.argtypes = [vp, vp, vp, ci, ci, sz, ctypes.POINTER(DenseParams), vp, vp]
     lib.wsg_disparity_postprocess.argtypes = [vp, vp, ci, ci, ci, ci, ci, ctypes.c_double, ci, ci, vp]
+    lib.wsg_disparity_refine.argtypes = [vp, vp, ci, ci, ci, ci]
     lib.wsg_triangulate.argtypes = [vp, vp, vp, vp, vp, vp, ctypes.POINTER(Calib), ctypes.POINTER(TriParams), u64p]
     lib.wsg_triangulate_from_dense.argtypes = [vp, vp, vp, vp, vp, ctypes.POINTER(Calib), ctypes.POINTER(TriParams), u64p]
     lib.wsg_mesh_upload.argtypes = [vp, ci, ci, vp, vp, vp]
@@ -310,6 +312,12 @@ class Handle:
         return out
 
     # ---- triangulation + mesh ----
+    def disparity_refine(self, disp_roi, median_wsize=0, bc_threshold=0):
+        """wass_stereo.cpp:941-986: optional float median (3|5) and gradient mask + biggest 8-connected component."""
+        d = np.ascontiguousarray(disp_roi, np.float32).copy()
+        self._ck(self.lib.wsg_disparity_refine(self.h, d.ctypes.data, d.shape[0], d.shape[1], int(median_wsize), int(bc_threshold)))
+        return d
+
     def triangulate(self, disparity, left, right, calib, params=None, left_mask=None, right_mask=None):
         disparity = np.ascontiguousarray(disparity, np.float32)
         left = np.ascontiguousarray(left, np.uint8)

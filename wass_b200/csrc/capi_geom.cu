@@ -58,6 +58,36 @@ int postprocess_device(wsg_handle* h, const int16_t* d_disp16, int rows, int col
     return WSG_OK;
 }
 
+// device part of wass_stereo.cpp:941-986 on the float ROI disparity held in h->fa (result back in h->fa)
+int refine_device(wsg_handle* h, int rows, int cols, int median_wsize, int bc_threshold)
+{
+    if (median_wsize < 3 && bc_threshold <= 0) return WSG_OK;
+    if (median_wsize >= 3 && median_wsize != 3 && median_wsize != 5) {
+        h->err = "MEDIAN_FILTER_WSIZE must be 3 or 5 (cv::medianBlur on float32 images accepts nothing else)";
+        return WSG_ERR_INVALID_ARG;
+    }
+    const size_t n = (size_t)rows * cols;
+    int rc;
+    if ((rc = ensure(h, h->fb, n * 4))) return rc;
+    StageTimer t(h, WSG_STAGE_POSTFILTER, (median_wsize >= 3 ? 1 : 0) + (bc_threshold > 0 ? 6 : 0));
+    if (median_wsize >= 3) {
+        launch_median_f32((const float*)h->fa.p, (float*)h->fb.p, rows, cols, median_wsize, h->stream);
+        std::swap(h->fa, h->fb);
+    }
+    if (bc_threshold > 0) {
+        if ((rc = ensure(h, h->m_labels, n * 12 + 64))) return rc;      // labels, counts, keys, best
+        launch_gradient_mask((const float*)h->fa.p, (float*)h->fb.p, rows, cols, (float)bc_threshold, h->stream);
+        std::swap(h->fa, h->fb);
+        int* L = (int*)h->m_labels.p;
+        unsigned* cnt = (unsigned*)(L + n);
+        unsigned* key = cnt + n;
+        unsigned long long* best = (unsigned long long*)(((uintptr_t)(key + n) + 15) & ~(uintptr_t)15);
+        launch_keep_biggest_cc8((float*)h->fa.p, rows, cols, L, cnt, key, best, h->stream);
+    }
+    CK(h, cudaGetLastError());
+    return WSG_OK;
+}
+
 void jacobi_eigen3(double A[3][3], double V[3][3], double w[3])
 {
     for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) V[i][j] = i == j;
@@ -90,6 +120,7 @@ void wsg_dense_params_default(wsg_dense_params* p)
     p->DISP_DILATE_STEPS = 1; p->DISP_EROSION_STEPS = 2; p->DENSE_P1_MULT = 2; p->DENSE_P2_MULT = 64;
     p->DENSE_UNIQUENESS_RATIO = 1; p->DENSE_DISP12MAXDIFF = -1; p->DENSE_PREFILTER_CAP = 60; p->DENSE_SPECKLE_RANGE = 16;
     p->DENSE_SPECKLE_WINDOW_SIZE = -70; p->mode = WSG_MODE_SGBM;
+    p->MEDIAN_FILTER_WSIZE = 0; p->DENSE_DISPARITY_BIGGEST_COMPONENT_THRESHOLD = 0;
 }
 
 void wsg_tri_params_default(wsg_tri_params* p)
@@ -143,6 +174,7 @@ int wsg_dense_stereo(wsg_handle* h, const uint8_t* left_crop, const uint8_t* rig
     rc = postprocess_device(h, (const int16_t*)h->disp.p, rows, wp, N, cols, p->MIN_DISPARITY, N, off, p->DENSE_SCALE,
                             p->DISP_DILATE_STEPS, p->DISP_EROSION_STEPS);
     if (rc) return rc;
+    if ((rc = refine_device(h, rows, cols, p->MEDIAN_FILTER_WSIZE, p->DENSE_DISPARITY_BIGGEST_COMPONENT_THRESHOLD))) return rc;
     CK(h, cudaMemcpyAsync(disp_roi, h->fa.p, ncrop * 4, cudaMemcpyDeviceToHost, h->stream));
     if (disp16_roi)
         CK(h, cudaMemcpy2DAsync(disp16_roi, (size_t)cols * 2, (const int16_t*)h->disp.p + N, (size_t)wp * 2, (size_t)cols * 2, rows,
@@ -167,6 +199,22 @@ int wsg_disparity_postprocess(wsg_handle* h, const int16_t* disp16_roi, int rows
     if (rc) return rc;
     CK(h, cudaMemcpyAsync(disp_roi, h->fa.p, n * 4, cudaMemcpyDeviceToHost, h->stream));
     CK(h, cudaStreamSynchronize(h->stream));
+    return WSG_OK;
+}
+
+int wsg_disparity_refine(wsg_handle* h, float* disp_roi, int rows, int cols, int median_wsize, int bc_threshold)
+{
+    if (!h) return WSG_ERR_INVALID_ARG;
+    if (!disp_roi || rows <= 0 || cols <= 0) { h->err = "bad argument"; return WSG_ERR_INVALID_ARG; }
+    CK(h, cudaSetDevice(h->device));
+    const size_t n = (size_t)rows * cols;
+    int rc;
+    if ((rc = ensure(h, h->fa, n * 4))) return rc;
+    CK(h, cudaMemcpyAsync(h->fa.p, disp_roi, n * 4, cudaMemcpyHostToDevice, h->stream));
+    if ((rc = refine_device(h, rows, cols, median_wsize, bc_threshold))) return rc;
+    CK(h, cudaMemcpyAsync(disp_roi, h->fa.p, n * 4, cudaMemcpyDeviceToHost, h->stream));
+    CK(h, cudaStreamSynchronize(h->stream));
+    h->have_dense = false;      // h->fa no longer holds the output of wsg_dense_stereo
     return WSG_OK;
 }
 

@@ -60,6 +60,12 @@ int mesh_compact_xyz(const MeshView& m, float* out /*n x 3*/, unsigned* scan_tmp
                      unsigned long long* n_host, cudaStream_t st);
 void launch_count_valid(const MeshView& m, unsigned long long* counter, cudaStream_t st);
 
+// optional refinement of the ROI disparity (wass_stereo.cpp:941-986)
+void launch_median_f32(const float* src, float* dst, int rows, int cols, int ksize, cudaStream_t st);
+void launch_gradient_mask(const float* src, float* dst, int rows, int cols, float thr, cudaStream_t st);
+void launch_keep_biggest_cc8(float* d, int rows, int cols, int* labels, unsigned* cnt, unsigned* key, unsigned long long* best,
+                             cudaStream_t st);
+
 // consumer side of mesh_cam.xyzC (gridding/wassgridsurface/wass_utils.py:22-68): u16 -> plane frame -> camera frame ->
 // aligned on the (mean) sea plane, z flipped, scaled by the baseline.  q: n x (x,y,z) u16 on the device; M: 24 doubles
 // {inv scale[3], min[3], Rinv[9], Tinv[3], R[9] of the mean plane ... see capi}; out: 3 x n doubles (row-major 3 rows).

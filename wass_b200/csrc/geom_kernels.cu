@@ -635,6 +635,137 @@ int mesh_compact_xyz(const MeshView& m, float* out, unsigned* scan_tmp, void* cu
 }
 
 // ------------------------------------------------------------------------------------------------
+// Optional refinement of the ROI disparity (wass_stereo.cpp:941-986), both off at the reference defaults:
+//  * MEDIAN_FILTER_WSIZE >= 3: cv::medianBlur on float32 (3 or 5; replicate border)
+//  * DENSE_DISPARITY_BIGGEST_COMPONENT_THRESHOLD > 0: zero where the squared Sobel gradient magnitude exceeds the
+//    threshold, then keep only the biggest 8-connected component of the non-zero pixels
+//    (cv::connectedComponentsWithStats; ties go to the smallest label, and cv2's labels are ordered by the first 2x2 block
+//    of a component in block-raster order -- checked against cv2 in tests/test_oracle_pipeline.py)
+// Float operation order of cv::Sobel (3x3, scale 1): gx = ((d[y-1] + d[y+1]) + 2 d[y]) with d = p[x+1] - p[x-1];
+// gy = s[y+1] - s[y-1] with s = ((p[x-1] + p[x+1]) + 2 p[x]); border BORDER_REFLECT_101.  No FMA (file is -fmad=false).
+// ------------------------------------------------------------------------------------------------
+template <int KS>
+__global__ void median_f32_kernel(const float* __restrict__ src, float* __restrict__ dst, int rows, int cols)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= cols) return;
+    constexpr int N = KS * KS, R = KS / 2;
+    float v[N];
+#pragma unroll
+    for (int j = 0; j < KS; ++j) {
+        const int yy = min(max(y + j - R, 0), rows - 1);
+#pragma unroll
+        for (int i = 0; i < KS; ++i) v[j * KS + i] = src[(size_t)yy * cols + min(max(x + i - R, 0), cols - 1)];
+    }
+    // partial selection sort up to the median (N <= 25)
+#pragma unroll
+    for (int a = 0; a <= N / 2; ++a) {
+#pragma unroll
+        for (int b = a + 1; b < N; ++b) {
+            const float lo = fminf(v[a], v[b]), hi = fmaxf(v[a], v[b]);
+            v[a] = lo; v[b] = hi;
+        }
+    }
+    dst[(size_t)y * cols + x] = v[N / 2];
+}
+
+void launch_median_f32(const float* src, float* dst, int rows, int cols, int ksize, cudaStream_t st)
+{
+    dim3 b(128), g((cols + 127) / 128, rows);
+    if (ksize == 3) median_f32_kernel<3><<<g, b, 0, st>>>(src, dst, rows, cols);
+    else            median_f32_kernel<5><<<g, b, 0, st>>>(src, dst, rows, cols);
+}
+
+__device__ __forceinline__ int refl101(int i, int n) { return n == 1 ? 0 : (i < 0 ? -i : (i >= n ? 2 * n - 2 - i : i)); }
+
+__global__ void gradient_mask_kernel(const float* __restrict__ src, float* __restrict__ dst, int rows, int cols, float thr)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= cols) return;
+    const int xm = refl101(x - 1, cols), xp = refl101(x + 1, cols);
+    float d[3], sm[3];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        const float* r = src + (size_t)refl101(y + j - 1, rows) * cols;
+        d[j] = r[xp] - r[xm];
+        sm[j] = (r[xm] + r[xp]) + 2.0f * r[x];
+    }
+    const float gx = (d[0] + d[2]) + 2.0f * d[1];
+    const float gy = sm[2] - sm[0];
+    const float g2 = gx * gx + gy * gy;
+    const float c = src[(size_t)y * cols + x];
+    dst[(size_t)y * cols + x] = g2 > thr ? 0.0f : c;
+}
+
+void launch_gradient_mask(const float* src, float* dst, int rows, int cols, float thr, cudaStream_t st)
+{
+    dim3 b(128), g((cols + 127) / 128, rows);
+    gradient_mask_kernel<<<g, b, 0, st>>>(src, dst, rows, cols, thr);
+}
+
+// 8-connected components of the non-zero pixels; L: rows*cols ints; cnt / key: rows*cols unsigned each
+__global__ void cc8_init_kernel(const float* __restrict__ d, int* L, unsigned* cnt, unsigned* key, int n)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    L[i] = d[i] != 0.0f ? i : -1;
+    cnt[i] = 0;
+    key[i] = 0xFFFFFFFFu;
+}
+__global__ void cc8_merge_kernel(const float* __restrict__ d, int* L, int rows, int cols)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= cols) return;
+    const int i = y * cols + x;
+    if (d[i] == 0.0f) return;
+    if (x + 1 < cols && d[i + 1] != 0.0f) uf_union(L, i, i + 1);
+    if (y + 1 < rows) {
+        if (d[i + cols] != 0.0f) uf_union(L, i, i + cols);
+        if (x + 1 < cols && d[i + cols + 1] != 0.0f) uf_union(L, i, i + cols + 1);
+        if (x > 0 && d[i + cols - 1] != 0.0f) uf_union(L, i, i + cols - 1);
+    }
+}
+__global__ void cc8_count_kernel(int* L, unsigned* cnt, unsigned* key, int rows, int cols)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= cols) return;
+    const int i = y * cols + x;
+    if (L[i] < 0) return;
+    const int r = uf_find(L, i);
+    L[i] = r;
+    atomicAdd(&cnt[r], 1u);
+    atomicMin(&key[r], (unsigned)((y >> 1) * ((cols + 1) >> 1) + (x >> 1)));   // order of cv2's labels
+}
+__global__ void cc8_best_kernel(const unsigned* cnt, const unsigned* key, int n, unsigned long long* best, int* best_root)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n || cnt[i] == 0) return;
+    atomicMax(best, ((unsigned long long)cnt[i] << 32) | (unsigned long long)(0xFFFFFFFFu - key[i]));
+}
+__global__ void cc8_apply_kernel(float* d, const int* __restrict__ L, const unsigned* __restrict__ cnt, const unsigned* __restrict__ key,
+                                 int n, const unsigned long long* best)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n || L[i] < 0) return;
+    const int r = L[i];
+    const unsigned long long mine = ((unsigned long long)cnt[r] << 32) | (unsigned long long)(0xFFFFFFFFu - key[r]);
+    if (mine != *best) d[i] = 0.0f;
+}
+
+void launch_keep_biggest_cc8(float* d, int rows, int cols, int* labels, unsigned* cnt, unsigned* key, unsigned long long* best,
+                             cudaStream_t st)
+{
+    const int n = rows * cols, nb = (n + 255) / 256;
+    dim3 b(128), g((cols + 127) / 128, rows);
+    cudaMemsetAsync(best, 0, 8, st);
+    cc8_init_kernel<<<nb, 256, 0, st>>>(d, labels, cnt, key, n);
+    cc8_merge_kernel<<<g, b, 0, st>>>(d, labels, rows, cols);
+    cc8_count_kernel<<<g, b, 0, st>>>(labels, cnt, key, rows, cols);
+    cc8_best_kernel<<<nb, 256, 0, st>>>(cnt, key, n, best, nullptr);
+    cc8_apply_kernel<<<nb, 256, 0, st>>>(d, labels, cnt, key, n, best);
+}
+
+// ------------------------------------------------------------------------------------------------
 // Consumer side of mesh_cam.xyzC: load_camera_mesh + align_on_sea_plane (gridding/wassgridsurface/wass_utils.py:22-35,
 // 38-68), the step right after the hot path.  params (doubles): [0..2] scale, [3..5] min,
 // [6..14] Rinv, [15..17] Tinv, [18..26] R of the plane to align on, [27..29] T, [30] baseline.

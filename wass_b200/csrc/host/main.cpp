@@ -357,8 +357,6 @@ int main(int argc, char* argv[])
 
         // ---- dense stereo (wass_stereo.cpp:764-1020)
         LOG_SCOPE("sgbm_dense_stereo");
-        if (cfg.geti("MEDIAN_FILTER_WSIZE") >= 3 || cfg.geti("DENSE_DISPARITY_BIGGEST_COMPONENT_THRESHOLD") > 0)
-            throw std::runtime_error("MEDIAN_FILTER_WSIZE / DENSE_DISPARITY_BIGGEST_COMPONENT_THRESHOLD are not supported by this build");
         wsg_dense_params dp;
         wsg_dense_params_default(&dp);
         dp.MIN_DISPARITY = cfg.geti("MIN_DISPARITY"); dp.MAX_DISPARITY = cfg.geti("MAX_DISPARITY"); dp.WINSIZE = cfg.geti("WINSIZE");
@@ -369,6 +367,10 @@ int main(int argc, char* argv[])
         dp.DENSE_PREFILTER_CAP = cfg.geti("DENSE_PREFILTER_CAP"); dp.DENSE_SPECKLE_RANGE = cfg.geti("DENSE_SPECKLE_RANGE");
         dp.DENSE_SPECKLE_WINDOW_SIZE = cfg.geti("DENSE_SPECKLE_WINDOW_SIZE");
         dp.mode = cfg.getb("SGM_FULL_8PATH") ? WSG_MODE_HH : WSG_MODE_SGBM;
+        dp.MEDIAN_FILTER_WSIZE = cfg.geti("MEDIAN_FILTER_WSIZE");
+        dp.DENSE_DISPARITY_BIGGEST_COMPONENT_THRESHOLD = cfg.geti("DENSE_DISPARITY_BIGGEST_COMPONENT_THRESHOLD");
+        if (dp.MEDIAN_FILTER_WSIZE >= 3) LOGI << "applying median filter (window size " << dp.MEDIAN_FILTER_WSIZE << " px.)";
+        if (dp.DENSE_DISPARITY_BIGGEST_COMPONENT_THRESHOLD > 0) LOGI << "extracting the biggest connected component from the disparity map";
         LOGI << "Disparity offset: " << dp.DISPARITY_OFFSET << " px";
         env.disparity_compensation = dp.DISPARITY_OFFSET > 0 ? 0 : -dp.DISPARITY_OFFSET;
         LOGI << "computing dense disparity map... (may take a while)";
