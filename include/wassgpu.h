@@ -220,6 +220,12 @@ int wsg_mesh_export_xyzc(wsg_handle* h, const double plane[4], void* dst, size_t
 /* PovMesh::save_as_xyz_binary, PovMesh.cpp:346-375: the exact bytes of mesh_cam.xyzbin. */
 int wsg_mesh_export_xyzbin(wsg_handle* h, void* dst, size_t capacity, size_t* nbytes);
 
+/* Replaces cv::undistort(img, out, K, dist) of the stage two steps up (src/wass_prepare/wass_prepare.cpp:268; SURVEY section 8f
+ * rank 4): 8-bit grey HOST image in and out, dist = (k1 k2 p1 p2 [k3 [k4 k5 k6]]), bilinear in OpenCV's 1/32-pixel fixed
+ * point, constant (0) border.  CLAHE and the polarimetric demosaic of wass_prepare are not part of this entry point. */
+int wsg_undistort_image(wsg_handle* h, const uint8_t* img, int rows, int cols, size_t stride, const double K[9], const double* dist,
+                        int ndist, uint8_t* out);
+
 /* ---- consumer side of the mesh (the step right after the hot path) -------------------------------- */
 /* Replaces load_camera_mesh + align_on_sea_plane (gridding/wassgridsurface/wass_utils.py:22-35 and 38-68, called at
  * gridding/wassgridsurface/wassgridsurface.py:86-87 and 316-318): decodes the bytes of a mesh_cam.xyzC file (HOST

@@ -145,6 +145,7 @@ def load():
     ip = ctypes.POINTER(ci)
     lib.wsg_stereo_rectify.argtypes = [dp, dp, dp, dp, ci, ci, dp, dp, dp, dp, ip, ip]
     lib.wsg_rectify_image.argtypes = [vp, vp, ci, ci, sz, dp, dp, dp, vp]
+    lib.wsg_undistort_image.argtypes = [vp, vp, ci, ci, sz, dp, dp, ci, vp]
     lib.wsg_plane_mean_accumulate.argtypes = [dp, dp]
     lib.wsg_plane_mean_accumulate.restype = None
     lib.wsg_plane_mean_finish.argtypes = [dp, dp]
@@ -423,6 +424,17 @@ class Handle:
         self._ck(self.lib.wsg_mesh_aligned_points(self.h, _d4(plane), _d4(align_plane), float(baseline), out.ctypes.data,
                                                   W * H, ctypes.byref(npts)))
         return out[:3 * npts.value].reshape(3, npts.value).copy()
+
+    def undistort_image(self, img, K, dist):
+        """cv::undistort(img, K, dist) as wass_prepare applies it (8-bit grey)."""
+        img = np.ascontiguousarray(img, np.uint8)
+        H, W = img.shape
+        out = np.empty((H, W), np.uint8)
+        d = np.ascontiguousarray(np.asarray(dist, np.float64).reshape(-1))
+        self._ck(self.lib.wsg_undistort_image(self.h, img.ctypes.data, H, W, W, _darr(K, 9),
+                                              d.ctypes.data_as(ctypes.POINTER(ctypes.c_double)) if d.size else None, int(d.size),
+                                              out.ctypes.data))
+        return out
 
     def rectify_image(self, img, K, Rrect, P):
         img = np.ascontiguousarray(img, np.uint8)

@@ -4,6 +4,7 @@
 // The published OpenCV algorithm (Bouguet's method, fixed-point bicubic remap with 1/32-pixel
 // phases) is restated here; tests/test_rectify.py pins both functions against cv2.
 #include "handle.cuh"
+#include <vector>
 
 #include <cfloat>
 #include <cmath>
@@ -248,6 +249,114 @@ int wsg_stereo_rectify(const double K0[9], const double K1[9], const double R[9]
     };
     if (roi1) roi(in1, cx1_0, cy1_0, cx1, cy1, roi1);
     if (roi2) roi(in2, cx2_0, cy2_0, cx2, cy2, roi2);
+    return WSG_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// cv::undistort as wass_prepare calls it (src/wass_prepare/wass_prepare.cpp:268, 474-497):
+// stripes of max(1, 4096/cols) rows, per stripe initUndistortRectifyMap(K, dist, I, K') with K'(1,2) = cy - y0 into 1/32-pixel
+// fixed-point maps (CV_16SC2), then remap(INTER_LINEAR, BORDER_CONSTANT 0).  One thread per image row walks its columns
+// with the same running sums as the reference (_x += ir[0] ...), so the quantised map matches bit for bit; the bilinear
+// weights (32-fx)(32-fy)*32 ... are exact integers (only 32768 saturates to 32767, which cannot change a u8 result).
+// ------------------------------------------------------------------------------------------------
+struct UndistortArgs {
+    double k[8];        // k1 k2 p1 p2 k3 k4 k5 k6
+    double fx, fy, u0, v0;
+    int rows, cols, stripe;
+};
+
+__global__ void undistort_map_kernel(UndistortArgs a, const double* __restrict__ ir_per_stripe, int2* __restrict__ map)
+{
+    const int y = blockIdx.x * blockDim.x + threadIdx.x;
+    if (y >= a.rows) return;
+    const double* ir = ir_per_stripe + (size_t)(y / a.stripe) * 9;
+    const int i = y % a.stripe;
+    double _x = i * ir[1] + ir[2], _y = i * ir[4] + ir[5], _w = i * ir[7] + ir[8];
+    const double k1 = a.k[0], k2 = a.k[1], p1 = a.k[2], p2 = a.k[3], k3 = a.k[4], k4 = a.k[5], k5 = a.k[6], k6 = a.k[7];
+    for (int j = 0; j < a.cols; ++j, _x += ir[0], _y += ir[3], _w += ir[6]) {
+        const double w = 1. / _w, x = _x * w, yy = _y * w;
+        const double x2 = x * x, y2 = yy * yy;
+        const double r2 = x2 + y2, _2xy = 2 * x * yy;
+        const double kr = (1 + ((k3 * r2 + k2) * r2 + k1) * r2) / (1 + ((k6 * r2 + k5) * r2 + k4) * r2);
+        const double xd = (x * kr + p1 * _2xy + p2 * (r2 + 2 * x2));
+        const double yd = (yy * kr + p1 * (r2 + 2 * y2) + p2 * _2xy);
+        const double u = a.fx * xd + a.u0, v = a.fy * yd + a.v0;
+        // saturate_cast<int>(u*INTER_TAB_SIZE) == cvRound (round half to even)
+        const double us = u * 32, vs = v * 32;
+        const int iu = us >= 2147483647. ? 2147483647 : (us <= -2147483648. ? (int)-2147483648LL : __double2int_rn(us));
+        const int iv = vs >= 2147483647. ? 2147483647 : (vs <= -2147483648. ? (int)-2147483648LL : __double2int_rn(vs));
+        map[(size_t)y * a.cols + j] = make_int2(iu, iv);
+    }
+}
+
+__global__ void undistort_remap_kernel(const uint8_t* __restrict__ src, int rows, int cols, size_t stride, const int2* __restrict__ map,
+                                       uint8_t* __restrict__ dst)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= cols) return;
+    const int2 m = map[(size_t)y * cols + x];
+    // map1 = (short)(iu >> 5), (short)(iv >> 5): the narrowing cast wraps like the reference's
+    const int sx = (short)(m.x >> 5), sy = (short)(m.y >> 5);
+    const int fx = m.x & 31, fy = m.y & 31;
+    int w[4] = {(32 - fx) * (32 - fy) * 32, fx * (32 - fy) * 32, (32 - fx) * fy * 32, fx * fy * 32};
+    if (w[0] > 32767) w[0] = 32767;
+    auto px = [&](int yy, int xx) -> int { return (xx >= 0 && xx < cols && yy >= 0 && yy < rows) ? (int)src[(size_t)yy * stride + xx] : 0; };
+    int out = 0;
+    if (!(sx >= cols || sx + 1 < 0 || sy >= rows || sy + 1 < 0)) {
+        const int sum = px(sy, sx) * w[0] + px(sy, sx + 1) * w[1] + px(sy + 1, sx) * w[2] + px(sy + 1, sx + 1) * w[3];
+        out = (sum + (1 << 14)) >> 15;
+        out = min(max(out, 0), 255);
+    }
+    dst[(size_t)y * cols + x] = (uint8_t)out;
+}
+
+// cv::invert of a 3x3 double matrix (the closed form OpenCV uses for n <= 3 with DECOMP_LU)
+static bool inv3_cv(const double* S, double* D)
+{
+    const double d = S[0] * (S[4] * S[8] - S[5] * S[7]) - S[1] * (S[3] * S[8] - S[5] * S[6]) + S[2] * (S[3] * S[7] - S[4] * S[6]);
+    if (d == 0.) return false;
+    const double id = 1. / d;
+    double t[9];
+    t[0] = (S[4] * S[8] - S[5] * S[7]) * id; t[1] = (S[2] * S[7] - S[1] * S[8]) * id; t[2] = (S[1] * S[5] - S[2] * S[4]) * id;
+    t[3] = (S[5] * S[6] - S[3] * S[8]) * id; t[4] = (S[0] * S[8] - S[2] * S[6]) * id; t[5] = (S[2] * S[3] - S[0] * S[5]) * id;
+    t[6] = (S[3] * S[7] - S[4] * S[6]) * id; t[7] = (S[1] * S[6] - S[0] * S[7]) * id; t[8] = (S[0] * S[4] - S[1] * S[3]) * id;
+    for (int i = 0; i < 9; ++i) D[i] = t[i];
+    return true;
+}
+
+int wsg_undistort_image(wsg_handle* h, const uint8_t* img, int rows, int cols, size_t stride, const double K[9], const double* dist,
+                        int ndist, uint8_t* out)
+{
+    if (!h) return WSG_ERR_INVALID_ARG;
+    if (!img || !K || !out || rows <= 0 || cols <= 0 || stride < (size_t)cols || ndist < 0 || (ndist && !dist)) { h->err = "bad argument"; return WSG_ERR_INVALID_ARG; }
+    if (ndist != 0 && ndist != 4 && ndist != 5 && ndist != 8) { h->err = "distortion vector must have 0, 4, 5 or 8 coefficients"; return WSG_ERR_INVALID_ARG; }
+    CK(h, cudaSetDevice(h->device));
+    UndistortArgs a;
+    for (int i = 0; i < 8; ++i) a.k[i] = i < ndist ? dist[i] : 0.;
+    a.fx = K[0]; a.fy = K[4]; a.u0 = K[2]; a.v0 = K[5];
+    a.rows = rows; a.cols = cols;
+    a.stripe = std::min(std::max(1, (1 << 12) / std::max(cols, 1)), rows);
+    const int nstripes = (rows + a.stripe - 1) / a.stripe;
+    std::vector<double> ir((size_t)nstripes * 9);
+    for (int sidx = 0; sidx < nstripes; ++sidx) {
+        double Ar[9] = {K[0], K[1], K[2], K[3], K[4], K[5] - (double)(sidx * a.stripe), K[6], K[7], K[8]};
+        if (!inv3_cv(Ar, &ir[(size_t)sidx * 9])) { h->err = "singular camera matrix"; return WSG_ERR_INVALID_ARG; }
+    }
+    const size_t n = (size_t)rows * cols;
+    int rc;
+    if ((rc = ensure(h, h->im_left, n))) return rc;
+    if ((rc = ensure(h, h->im_right, n))) return rc;
+    if ((rc = ensure(h, h->m_scratch, n * sizeof(int2) + ir.size() * 8 + 64))) return rc;
+    int2* d_map = (int2*)h->m_scratch.p;
+    double* d_ir = (double*)((char*)h->m_scratch.p + n * sizeof(int2));
+    CK(h, cudaMemcpyAsync(d_ir, ir.data(), ir.size() * 8, cudaMemcpyHostToDevice, h->stream));
+    CK(h, cudaMemcpy2DAsync(h->im_left.p, cols, img, stride, cols, rows, cudaMemcpyHostToDevice, h->stream));
+    undistort_map_kernel<<<(rows + 63) / 64, 64, 0, h->stream>>>(a, d_ir, d_map);
+    dim3 b(128), g((cols + 127) / 128, rows);
+    undistort_remap_kernel<<<g, b, 0, h->stream>>>((const uint8_t*)h->im_left.p, rows, cols, cols, d_map, (uint8_t*)h->im_right.p);
+    CK(h, cudaMemcpyAsync(out, h->im_right.p, n, cudaMemcpyDeviceToHost, h->stream));
+    CK(h, cudaStreamSynchronize(h->stream));
+    CK(h, cudaGetLastError());
     return WSG_OK;
 }
 
