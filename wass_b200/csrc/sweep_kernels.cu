@@ -101,6 +101,45 @@ __device__ __forceinline__ void st_volatile(uint4* p, const uint4& v)
                  : "memory");
 }
 
+// ---- thread-block cluster / distributed shared memory (CTA pairs: the even band hands its last row's states straight into
+// the ring of the odd band on the neighbouring SM instead of going through the hand-off buffer in L2)
+__device__ __forceinline__ unsigned cluster_ctarank() { unsigned r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ unsigned cluster_nctarank() { unsigned r; asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all()
+{
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ unsigned dsmem_addr(const void* local_smem, unsigned rank)
+{
+    unsigned r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"((unsigned)__cvta_generic_to_shared(local_smem)), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void dsmem_st_v4(unsigned addr, const uint4& v)
+{
+    asm volatile("st.shared::cluster.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ void dsmem_st_release_u32(unsigned addr, int v)   // (a plain volatile store: see WSG_SWEEP_PAIRS)
+{
+    asm volatile("st.volatile.shared::cluster.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ int dsmem_ld_u32(unsigned addr)
+{
+    int v;
+    asm volatile("ld.volatile.shared::cluster.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+    return v;
+}
+// wait_prog on a counter that lives in the shared memory of another CTA of the cluster
+__device__ __forceinline__ void wait_prog_remote(unsigned addr, int need, int& seen, int* err)
+{
+    if (seen >= need) return;
+    int spins = 0;
+    while ((seen = dsmem_ld_u32(addr)) < need) {
+        if (++spins > 16) __nanosleep(100);
+        if ((spins & 1023) == 0 && (spins > SPIN_LIMIT || *reinterpret_cast<volatile int*>(err) != 0)) { *err = 4; seen = 0x7fffffff; break; }
+    }
+}
+
 // Wait until *flag >= need (shared-memory progress counter of a neighbouring warp).  Bounded: on overrun (or when
 // any other waiter has already given up) raise the error flag and stop waiting for good.
 __device__ __forceinline__ void wait_prog(volatile int* flag, int need, int& seen, int* err, int eager_spins = 64)
@@ -202,7 +241,7 @@ __device__ __forceinline__ void wta_flush(unsigned key, unsigned nb, int xl, boo
 // One image row of a sweep, walked by one warp (see the kernel below for the surrounding protocol).
 template <int K, int MODE, int NDIR, bool HASPAD, int CFG, bool FAST>
 __device__ __forceinline__ void sweep_row(const uint4* __restrict__ C, uint4* __restrict__ S, const SweepArgs& a, uint4* smem,
-                                          volatile int* prog, int band, int warp, int l)
+                                          volatile int* prog, int band, int warp, int l, bool to_peer, bool from_peer_cta = false)
 {
     using Cfg = SweepCfg<K, CFG>;
     constexpr int NR = 4 * K;
@@ -213,8 +252,10 @@ __device__ __forceinline__ void sweep_row(const uint4* __restrict__ C, uint4* __
     const int r = warp;
     const int yl = band * SW_R + r;                 // logical row (sweep order)
     if (yl >= a.H) return;
+    const bool from_peer = from_peer_cta && r == 0;
     const bool top = NDIR == 1 || yl == 0;          // no predecessor row
-    const int out_mode = (NDIR == 1 || yl == a.H - 1) ? 0 : (r < SW_R - 1 ? 1 : 2);
+    // 0: no row below; 1: ring of the next warp; 2: hand-off buffer in global memory; 3: ring 0 of the peer CTA (DSMEM)
+    const int out_mode = (NDIR == 1 || yl == a.H - 1) ? 0 : (r < SW_R - 1 ? 1 : (to_peer ? 3 : 2));
     const int yp = a.flip ? a.H - 1 - yl : yl;      // physical row
     const long long dstep = a.flip ? -(long long)a.Dp8 : (long long)a.Dp8;
     const size_t first = ((size_t)yp * a.W1 + (a.flip ? a.W1 - 1 : 0)) * a.Dp8 + l;
@@ -231,6 +272,13 @@ __device__ __forceinline__ void sweep_row(const uint4* __restrict__ C, uint4* __
     volatile int* prog_me = &prog[r + 1];
     volatile int* prog_next = &prog[r + 2 <= SW_R ? r + 2 : SW_R];
     int seen_in = 0, seen_next = 0;
+    // peer CTA (cluster rank 1): its ring 0, its prog[0] (which this warp advances) and prog[1] (its first row: back-pressure)
+    unsigned peer_ring = 0, peer_prog0 = 0, peer_prog1 = 0;
+    if (out_mode == 3) {
+        peer_ring = dsmem_addr(smem + l, 1);
+        peer_prog0 = dsmem_addr(const_cast<int*>(&prog[0]), 1);
+        peer_prog1 = dsmem_addr(const_cast<int*>(&prog[1]), 1);
+    }
 
     unsigned padm[K];
 #pragma unroll
@@ -340,6 +388,16 @@ __device__ __forceinline__ void sweep_row(const uint4* __restrict__ C, uint4* __
                         st_volatile(dst + (q * K + k) * 32,
                                     make_uint4(Nd[q][4 * k] | a.tag, Nd[q][4 * k + 1] | a.tag, Nd[q][4 * k + 2] | a.tag,
                                                Nd[q][4 * k + 3] | a.tag));
+            } else if (out_mode == 3) {
+                wait_prog_remote(peer_prog1, x - NS + 2, seen_next, a.err);
+                const unsigned dst = peer_ring + ((x % NS) * Cfg::SLOT_V) * 16;
+#pragma unroll
+                for (int q = 0; q < NQ; ++q)
+#pragma unroll
+                    for (int k = 0; k < K; ++k)
+                        dsmem_st_v4(dst + ((q * K + k) * 32) * 16, make_uint4(Nd[q][4 * k], Nd[q][4 * k + 1], Nd[q][4 * k + 2], Nd[q][4 * k + 3]));
+                __syncwarp();
+                if (l == 0) dsmem_st_release_u32(peer_prog0, x + 1);
             }
             __syncwarp();                      // every lane's state stores are issued before the counter store
             asm volatile("" ::: "memory");
@@ -399,6 +457,13 @@ __device__ __forceinline__ void sweep_row(const uint4* __restrict__ C, uint4* __
         __syncwarp();
         asm volatile("" ::: "memory");
         if (l == 0) *prog_me = a.W1 + 1;
+    }
+    if (NDIR >= 3 && out_mode == 3) {
+        wait_prog_remote(peer_prog1, a.W1 - NS + 2, seen_next, a.err);
+#pragma unroll
+        for (int j = 0; j < 3 * K; ++j) dsmem_st_v4(peer_ring + ((a.W1 % NS) * Cfg::SLOT_V + j * 32) * 16, make_uint4(0, 0, 0, 0));
+        __syncwarp();
+        if (l == 0) dsmem_st_release_u32(peer_prog0, a.W1 + 1);
     }
 }
 
@@ -492,6 +557,39 @@ sweep_kernel(const uint4* __restrict__ C, uint4* __restrict__ S, SweepArgs a)
     __shared__ int s_band;
 
     const int tid = threadIdx.x, warp = tid >> 5, l = tid & 31;
+    const int nbands = (a.H + SW_R - 1) / SW_R;
+    const unsigned csize = cluster_nctarank(), crank = cluster_ctarank();
+    if (csize == 2) {
+        // ---- CTA pairs (thread-block cluster of two, one CTA per SM by its shared-memory size): the pair takes bands 2t and
+        // 2t+1; rank 0's last row writes its states and its progress straight into rank 1's ring 0 (distributed shared
+        // memory, release store on the counter), so every second band boundary costs an SM-to-SM hop instead of an L2
+        // round trip.  Rank 1's last row uses the global hand-off buffer as before.
+        const bool fast = *a.maxC + a.P2 <= 32767;
+        while (true) {
+            if (crank == 0 && tid == 0) {
+                const int pair = atomicAdd(a.ticket, 1);
+                s_band = pair;
+                asm volatile("st.shared::cluster.u32 [%0], %1;" ::"r"(dsmem_addr(&s_band, 1)), "r"(pair) : "memory");
+            }
+            if (tid <= SW_R) prog[tid] = 0;
+            if (NDIR >= 3)
+                for (int i = tid; i < Cfg::RINGS_V; i += SW_THREADS) smem[i] = make_uint4(0, 0, 0, 0);
+            cluster_sync_all();                  // ticket visible in both CTAs; both rings clean before anyone writes into them
+            const int band = 2 * s_band + (int)crank;
+            if (2 * s_band >= nbands) break;
+            if (band < nbands) {
+                if (warp == SW_R) {
+                    if (NDIR >= 3 && crank == 0) sweep_helper<K, CFG, NDIR == 4 ? 3 : 2>(a, smem, prog, band, l);
+                } else if (fast) {
+                    sweep_row<K, MODE, NDIR, HASPAD, CFG, true>(C, S, a, smem, prog, band, warp, l, crank == 0 && band + 1 < nbands, crank == 1);
+                } else {
+                    sweep_row<K, MODE, NDIR, HASPAD, CFG, false>(C, S, a, smem, prog, band, warp, l, crank == 0 && band + 1 < nbands, crank == 1);
+                }
+            }
+            cluster_sync_all();                  // both bands done: nobody writes into a ring that is about to be reset
+        }
+        return;
+    }
     // One WORKER per SM and launch: the first CTA of this launch to arrive on an SM stays and takes bands from a ticket
     // counter until none is left; every other CTA exits at once.  Bands therefore start in increasing order on
     // different SMs whatever the hardware's placement, nothing waits for a CTA that is not running, and the second
@@ -505,7 +603,6 @@ sweep_kernel(const uint4* __restrict__ C, uint4* __restrict__ S, SweepArgs a)
     __syncthreads();
     if (s_band < 0) return;
     const bool fast = *a.maxC + a.P2 <= 32767;   // the verified domain (known since the cost kernel ran): cheaper arithmetic
-    const int nbands = (a.H + SW_R - 1) / SW_R;
     while (true) {
         __syncthreads();                         // the previous band is finished by every warp
         if (tid == 0) {
@@ -527,9 +624,9 @@ sweep_kernel(const uint4* __restrict__ C, uint4* __restrict__ S, SweepArgs a)
         if (warp == SW_R) {
             if (NDIR >= 3) sweep_helper<K, CFG, NDIR == 4 ? 3 : 2>(a, smem, prog, band, l);
         } else if (fast) {
-            sweep_row<K, MODE, NDIR, HASPAD, CFG, true>(C, S, a, smem, prog, band, warp, l);
+            sweep_row<K, MODE, NDIR, HASPAD, CFG, true>(C, S, a, smem, prog, band, warp, l, false);
         } else {
-            sweep_row<K, MODE, NDIR, HASPAD, CFG, false>(C, S, a, smem, prog, band, warp, l);
+            sweep_row<K, MODE, NDIR, HASPAD, CFG, false>(C, S, a, smem, prog, band, warp, l, false);
         }
         if (a.dbg && warp == SW_R - 1 && l == 0) {           // the band's last row is done
             unsigned long long t;
@@ -543,12 +640,35 @@ template <int K, int MODE, int NDIR, bool HASPAD, int CFG>
 static void launch_sweep_c(const int16_t* C, int16_t* S, const SweepArgs& a, cudaStream_t st)
 {
     using Cfg = SweepCfg<K, CFG>;
-    // enough CTAs for every SM to see one even when other kernels hold slots; all but one per SM exit immediately
-    const int grid = Cfg::CTAS_PER_SM * a.num_sms;
     auto kern = sweep_kernel<K, MODE, NDIR, HASPAD, CFG>;
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
     cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    kern<<<grid, SW_THREADS, Cfg::SMEM, st>>>(reinterpret_cast<const uint4*>(C), reinterpret_cast<uint4*>(S), a);
+    static int pairs = -1;
+    // Opt-in experiment (WSG_SWEEP_PAIRS=1), not the default: 8.35 ms instead of 8.60 ms per frame for both sweeps, but the
+    // counter store that follows the 32 lanes' remote data stores is only ordered behind them by the in-order delivery of
+    // one warp's DSMEM stores (as with the CTA-local rings); with cluster-scope fences on both sides, which would make it
+    // formally ordered, the last row of every even band takes so long that the frame needs 18.3 ms.
+    if (pairs < 0) { const char* e = getenv("WSG_SWEEP_PAIRS"); pairs = e ? atoi(e) : 0; }
+    const uint4* c = reinterpret_cast<const uint4*>(C);
+    uint4* s = reinterpret_cast<uint4*>(S);
+    if (pairs && NDIR >= 3 && Cfg::CTAS_PER_SM == 1) {
+        // CTA pairs with a DSMEM hand-off between the two bands of a pair (see the kernel)
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)(a.num_sms & ~1));
+        cfg.blockDim = dim3(SW_THREADS);
+        cfg.dynamicSmemBytes = Cfg::SMEM;
+        cfg.stream = st;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at;
+        cfg.numAttrs = 1;
+        if (cudaLaunchKernelEx(&cfg, kern, c, s, a) == cudaSuccess) return;
+        cudaGetLastError();      // cluster launch not possible here: fall through to the plain launch
+    }
+    // enough CTAs for every SM to see one even when other kernels hold slots; all but one per SM exit immediately
+    const int grid = Cfg::CTAS_PER_SM * a.num_sms;
+    kern<<<grid, SW_THREADS, Cfg::SMEM, st>>>(c, s, a);
 }
 
 // ================================================================================================
