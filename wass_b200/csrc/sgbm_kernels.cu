@@ -563,10 +563,15 @@ void launch_median3(const int16_t* src, int16_t* dst, int rows, int cols, cudaSt
 // connected components of that (symmetric) relation among valid pixels: lock-free union-find with atomicMin,
 // component sizes, then every pixel of a component of at most speckleWindowSize pixels becomes invalid.
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ int sp_find(const int* L, int x)
+__device__ __forceinline__ int sp_find(int* L, int x)
 {
+    // path halving; the shortcut is installed with a compare-and-swap so that it can never undo a concurrent union
     int p = L[x];
-    while (p != x) { x = p; p = L[x]; }
+    while (p != x) {
+        const int g = L[p];
+        if (g != p) atomicCAS(&L[x], p, g);
+        x = p; p = g;
+    }
     return x;
 }
 __device__ __forceinline__ void sp_union(int* L, int a, int b)
