@@ -158,3 +158,37 @@ def test_full_size_implementations_agree(handle, W, H, D, mode):
     assert valid.mean() > 0.85
     err = np.abs(disp - d_true)[valid]
     assert np.median(err) < 0.25 and (err < 1.0).mean() > 0.97
+
+
+EDGE = [
+    # (W, H, D, minD, block, mode)   -- W is the image width INCLUDING the maxD columns cv2 leaves invalid
+    (40, 1, 16, 0, 3, 1),        # a single row
+    (40, 2, 16, 1, 5, 0),
+    (60, 7, 32, 1, 7, 1),        # fewer rows than one 8-row band
+    (60, 9, 32, 1, 7, 1),        # one band and one row
+    (23, 17, 16, 0, 1, 1),       # blockSize 1, 7 matched columns
+    (36, 20, 16, 3, 9, 0),
+    (30, 24, 16, -5, 5, 1),      # negative minDisparity
+    (130, 33, 96, 2, 25, 1),     # window 25: the narrow-tile cost kernel (the wide one stops at 17)
+    (130, 33, 96, 2, 19, 0),
+    (1400, 12, 1280, 0, 5, 1),   # 1280 disparities: more than the fused sweeps take, per-direction launches
+]
+
+
+@pytest.mark.parametrize("W,H,D,minD,block,mode", EDGE)
+def test_edge_shapes_match_oracle(handle, impl, W, H, D, minD, block, mode):
+    """Ragged and extreme shapes: single rows, partial bands, a handful of matched columns, negative minDisparity,
+    the largest window and disparity count the API accepts."""
+    from oracle import sgbm
+    rng = np.random.default_rng(W * 131 + H)
+    coarse = rng.integers(90, 170, (H // 3 + 2, W // 3 + 2)).astype(np.float32)
+    img = np.kron(coarse, np.ones((3, 3), np.float32))[:H, :W]
+    img1 = np.clip(img + rng.normal(0, 2, img.shape), 0, 255).astype(np.uint8)
+    img2 = np.clip(np.roll(img, -3, axis=1) + rng.normal(0, 2, img.shape), 0, 255).astype(np.uint8)
+    p = dict(minDisparity=minD, numDisparities=D, blockSize=block, P1=min(8 * block * block, 1200),
+             P2=min(32 * block * block, 5000), disp12MaxDiff=1, preFilterCap=31, uniquenessRatio=5, speckleWindowSize=0,
+             speckleRange=0, mode=mode)
+    ref = sgbm.compute(img1, img2, p)
+    assert ref["maxC"] + p["P2"] <= 32767
+    out = handle.sgbm_compute(img1, img2, p)
+    assert np.array_equal(out, ref["disp"])
