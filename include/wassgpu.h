@@ -134,7 +134,8 @@ typedef struct wsg_dense_params {
 void wsg_dense_params_default(wsg_dense_params* p);
 
 /* left_crop/right_crop: rows x cols uint8 HOST images (the rectified ROI crops, wass_stereo.cpp:607-608).
- * disp_roi: rows x cols float32 HOST, 0 = invalid.  disp16_roi (optional, may be NULL): the raw
+ * disp_roi: rows x cols float32 HOST, 0 = invalid; may be NULL when the caller goes on with wsg_triangulate_from_dense (the
+ * disparity stays on the device).  disp16_roi (optional, may be NULL): the raw
  * matcher output cropped to the ROI, int16 x16. */
 int wsg_dense_stereo(wsg_handle* h, const uint8_t* left_crop, const uint8_t* right_crop, int rows, int cols,
                      size_t stride, const wsg_dense_params* p, float* disp_roi, int16_t* disp16_roi);

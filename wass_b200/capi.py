@@ -293,15 +293,16 @@ class Handle:
         self._ck(self.lib.wsg_sgbm_set_impl(self.h, int(impl)))
 
     # ---- dense stage ----
-    def dense_stereo(self, left_crop, right_crop, params, want_disp16=False):
-        """Mirrors sgbm_dense_stereo (wass_stereo.cpp:764-1020): crops in, float ROI disparity out."""
+    def dense_stereo(self, left_crop, right_crop, params, want_disp16=False, want_host=True):
+        """Mirrors sgbm_dense_stereo (wass_stereo.cpp:764-1020): crops in, float ROI disparity out.
+        want_host=False keeps the disparity on the device only (for triangulate_from_dense) and returns None."""
         left_crop = np.ascontiguousarray(left_crop, np.uint8)
         right_crop = np.ascontiguousarray(right_crop, np.uint8)
         H, W = left_crop.shape
-        out = np.empty((H, W), np.float32)
+        out = np.empty((H, W), np.float32) if want_host else None
         d16 = np.empty((H, W), np.int16) if want_disp16 else None
         self._ck(self.lib.wsg_dense_stereo(self.h, left_crop.ctypes.data, right_crop.ctypes.data, H, W, W, ctypes.byref(params),
-                                           out.ctypes.data, d16.ctypes.data if want_disp16 else None))
+                                           out.ctypes.data if want_host else None, d16.ctypes.data if want_disp16 else None))
         return (out, d16) if want_disp16 else out
 
     def disparity_postprocess(self, disp16_roi, min_disp, num_disp, disparity_offset=0, dense_scale=1.0, dilate=1, erode=2):
@@ -392,12 +393,17 @@ class Handle:
         self._ck(self.lib.wsg_mesh_refine_plane(self.h, ctypes.byref(p), plane, ctypes.byref(n)))
         return np.array(list(plane)), n.value
 
-    def mesh_export_xyzc(self, plane):
+    def mesh_export_xyzc(self, plane, out=None):
+        """Bytes of mesh_cam.xyzC.  `out`: optional reusable uint8 destination of at least 148 + 6*W*H bytes (e.g. a numpy
+        view of pinned memory); a view of it is returned instead of a fresh bytes object (no allocation, no extra copy)."""
         W, H, _ = self.mesh_size()
-        buf = np.empty(148 + W * H * 6, np.uint8)
+        need = 148 + W * H * 6
+        buf = out if out is not None else np.empty(need, np.uint8)
+        if buf.size < need:
+            raise ValueError("destination too small")
         nb = ctypes.c_size_t()
         self._ck(self.lib.wsg_mesh_export_xyzc(self.h, _d4(plane), buf.ctypes.data, buf.size, ctypes.byref(nb)))
-        return buf[:nb.value].tobytes()
+        return buf[:nb.value] if out is not None else buf[:nb.value].tobytes()
 
     def mesh_export_xyzbin(self):
         W, H, _ = self.mesh_size()

@@ -143,7 +143,7 @@ int wsg_dense_stereo(wsg_handle* h, const uint8_t* left_crop, const uint8_t* rig
                      const wsg_dense_params* p, float* disp_roi, int16_t* disp16_roi)
 {
     if (!h) return WSG_ERR_INVALID_ARG;
-    if (!left_crop || !right_crop || !p || !disp_roi || rows <= 0 || cols <= 0 || stride < (size_t)cols) { h->err = "bad argument"; return WSG_ERR_INVALID_ARG; }
+    if (!left_crop || !right_crop || !p || rows <= 0 || cols <= 0 || stride < (size_t)cols) { h->err = "bad argument"; return WSG_ERR_INVALID_ARG; }
     if (p->DENSE_SCALE != 1.0) { h->err = "DENSE_SCALE != 1 is not supported (cv::resize INTER_CUBIC parity not implemented)"; return WSG_ERR_INVALID_ARG; }
     CK(h, cudaSetDevice(h->device));
     const int N = p->MAX_DISPARITY;
@@ -175,7 +175,7 @@ int wsg_dense_stereo(wsg_handle* h, const uint8_t* left_crop, const uint8_t* rig
                             p->DISP_DILATE_STEPS, p->DISP_EROSION_STEPS);
     if (rc) return rc;
     if ((rc = refine_device(h, rows, cols, p->MEDIAN_FILTER_WSIZE, p->DENSE_DISPARITY_BIGGEST_COMPONENT_THRESHOLD))) return rc;
-    CK(h, cudaMemcpyAsync(disp_roi, h->fa.p, ncrop * 4, cudaMemcpyDeviceToHost, h->stream));
+    if (disp_roi) CK(h, cudaMemcpyAsync(disp_roi, h->fa.p, ncrop * 4, cudaMemcpyDeviceToHost, h->stream));
     if (disp16_roi)
         CK(h, cudaMemcpy2DAsync(disp16_roi, (size_t)cols * 2, (const int16_t*)h->disp.p + N, (size_t)wp * 2, (size_t)cols * 2, rows,
                                 cudaMemcpyDeviceToHost, h->stream));

@@ -608,7 +608,9 @@ __global__ void speckle_count_kernel(int* L, unsigned* cnt, int n)
     if (i >= n || L[i] < 0) return;
     const int r = sp_find(L, i);
     L[i] = r;
-    atomicAdd(&cnt[r], 1u);
+    const unsigned act = __activemask();
+    const unsigned peers = __match_any_sync(act, r);
+    if ((threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&cnt[r], (unsigned)__popc(peers));
 }
 __global__ void speckle_apply_kernel(int16_t* d, const int* __restrict__ L, const unsigned* __restrict__ cnt, int n, int invalid,
                                      unsigned maxSize)
