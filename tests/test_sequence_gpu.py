@@ -1,0 +1,81 @@
+"""In-process sequence runner (wass_b200/sequence.py): the per-frame order of main() (wass_stereo.cpp:1976-2135) through the
+C ABI.  Results must not depend on how many frames are in flight, nor on which handle processed a frame."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _frames(W, H, D, n):
+    from wass_b200 import synth
+    out = []
+    for s in range(n):
+        right, left, _ = synth.make_pair(W, H, D, seed=50 + s, d0=10.0 + s)
+        out.append((left, right))
+    return out
+
+
+def test_frames_in_flight_do_not_change_results():
+    from wass_b200 import capi, sequence, synth
+    W, H, D = 640, 400, 64
+    c = synth.make_calibration(W, H)
+    calib = sequence.rectified_calib(c["K0"], c["K1"], c["R"], c["T"], W, H)
+    dense = capi.dense_params(MAX_DISPARITY=D, mode=capi.MODE_SGBM)
+    frames = _frames(W, H, D, 5)
+    h1 = capi.Handle(0)
+    hs = [capi.Handle(0), capi.Handle(0)]
+    try:
+        m1, p1, r1 = sequence.run_sequence(frames, calib, dense, handle=h1, ransac_rounds=60)
+        outs = [np.empty(148 + 6 * W * H, np.uint8) for _ in hs]
+        m2, p2, r2 = sequence.run_sequence(frames, calib, dense, handle=hs, xyzc_out=outs, ransac_rounds=60, keep_xyzc=False)
+        assert not np.isnan(p1).any()
+        np.testing.assert_array_equal(p1, p2)
+        np.testing.assert_array_equal(m1, m2)
+        assert [r.n_points for r in r1] == [r.n_points for r in r2]
+        # the same frame on another handle gives the same bytes
+        a = sequence.process_frame(h1, frames[3][0], frames[3][1], calib, dense, seed=3, ransac_rounds=60)
+        b = sequence.process_frame(hs[1], frames[3][0], frames[3][1], calib, dense, seed=3, ransac_rounds=60, xyzc_out=outs[1])
+        assert bytes(a.xyzc) == bytes(b.xyzc) == bytes(r1[3].xyzc)
+        np.testing.assert_array_equal(a.plane, p1[3])
+        # every plane is a unit normal close to the synthetic fronto-parallel scene's
+        assert np.allclose(np.linalg.norm(p1[:, :3], axis=1), 1.0, atol=1e-9)
+    finally:
+        h1.close()
+        for h in hs:
+            h.close()
+
+
+def test_shared_output_buffer_is_refused():
+    from wass_b200 import capi, sequence, synth
+    W, H, D = 320, 200, 32
+    c = synth.make_calibration(W, H)
+    calib = sequence.rectified_calib(c["K0"], c["K1"], c["R"], c["T"], W, H)
+    hs = [capi.Handle(0), capi.Handle(0)]
+    try:
+        buf = np.empty(148 + 6 * W * H, np.uint8)
+        with pytest.raises(ValueError):
+            sequence.run_sequence(_frames(W, H, D, 2), calib, capi.dense_params(MAX_DISPARITY=D), handle=hs, xyzc_out=buf)
+    finally:
+        for h in hs:
+            h.close()
+
+
+def test_sharded_ranks_cover_the_sequence():
+    """Two 'ranks' run one after the other on one GPU: the union of their frames is the single-rank result."""
+    from wass_b200 import capi, sequence, synth
+    W, H, D = 480, 300, 48
+    c = synth.make_calibration(W, H)
+    calib = sequence.rectified_calib(c["K0"], c["K1"], c["R"], c["T"], W, H)
+    dense = capi.dense_params(MAX_DISPARITY=D)
+    frames = _frames(W, H, D, 4)
+    h = capi.Handle(0)
+    try:
+        _, pall, _ = sequence.run_sequence(frames, calib, dense, handle=h, ransac_rounds=40, keep_xyzc=False)
+        parts = np.full_like(pall, np.nan)
+        for r in range(2):
+            _, pr, res = sequence.run_sequence(frames, calib, dense, handle=h, rank=r, world=2, ransac_rounds=40, keep_xyzc=False)
+            own = list(range(r, 4, 2))
+            parts[own] = np.array([x.plane for x in res])
+        np.testing.assert_array_equal(parts, pall)
+    finally:
+        h.close()

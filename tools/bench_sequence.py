@@ -26,6 +26,7 @@ def main():
     ap.add_argument("--frames", type=int, default=16, help="frames of the whole sequence")
     ap.add_argument("--distinct", type=int, default=2, help="distinct synthetic frames generated per rank (cycled)")
     ap.add_argument("--mode", default="sgbm", choices=["sgbm", "hh"])
+    ap.add_argument("--depth", type=int, default=2, help="frames in flight per GPU (one handle, stream and host thread each)")
     a = ap.parse_args()
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", 0))
@@ -42,9 +43,9 @@ def main():
     frames = [pool[i % a.distinct] for i in range(a.frames)]
     dense = capi.dense_params(MAX_DISPARITY=D, mode=capi.MODE_HH if a.mode == "hh" else capi.MODE_SGBM)
     # warm-up (arena allocation, first launches) on the handle the timed run uses
-    h = capi.Handle(local)
-    xyzc_out = torch.empty(148 + 6 * W * H, dtype=torch.uint8).pin_memory().numpy()   # reusable pinned destination
-    sequence.run_sequence(frames[: 2 * world], calib, dense, device=local, rank=rank, world=world, dist=None, handle=h, xyzc_out=xyzc_out)
+    h = [capi.Handle(local) for _ in range(a.depth)]
+    xyzc_out = [torch.empty(148 + 6 * W * H, dtype=torch.uint8).pin_memory().numpy() for _ in range(a.depth)]   # reusable pinned destinations
+    sequence.run_sequence(frames[: 2 * a.depth * world], calib, dense, device=local, rank=rank, world=world, dist=None, handle=h, xyzc_out=xyzc_out)
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
@@ -59,11 +60,12 @@ def main():
         stages = {k: float(np.mean([r.ms[k] for r in res])) for k in sequence.STAGES}
         line = {"metric": "end-to-end Mdisparities/s (stereo + triangulation + plane + xyzC in memory)",
                 "value": a.frames * W * H / float(dt[0]) / 1e6, "unit": "Mdisp/s", "frames_per_s": a.frames / float(dt[0]),
-                "n_gpus": world, "frames": a.frames, "mode": a.mode, "ms_per_frame_per_gpu": float(dt[0]) * 1e3 / (a.frames / world),
+                "n_gpus": world, "frames": a.frames, "mode": a.mode, "frames_in_flight": a.depth, "ms_per_frame_per_gpu": float(dt[0]) * 1e3 / (a.frames / world),
                 "stage_ms_host_clock": stages, "points_per_frame": int(np.mean([r.n_points for r in res])),
                 "planes_valid": int(np.sum(~np.isnan(planes[:, 0]))), "mean_plane": [float(v) for v in mean]}
         print(json.dumps(line), flush=True)
-    h.close()
+    for x in h:
+        x.close()
     if world > 1:
         dist.destroy_process_group()
 

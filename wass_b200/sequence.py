@@ -10,12 +10,14 @@ The launcher (wass_b200/launcher.py) does the same through the drop-in executabl
 reference's drivers do; this module is for callers that already hold rectified images in memory.
 """
 import ctypes
+import threading
 import time
 import numpy as np
 
 from . import capi
 
 STAGES = ("dense", "triangulate", "zgap", "component", "ransac", "refine", "export")
+_rand_lock = threading.Lock()      # libc's rand() state is process-wide: seed + draw is one critical section
 
 
 class FrameResult:
@@ -59,9 +61,11 @@ def process_frame(h, left_rect, right_rect, calib, dense, ransac_rounds=400, ran
     lap("zgap")
     h.mesh_biggest_component(zg)
     lap("component")
-    if seed is not None:
-        ctypes.CDLL("libc.so.6").srand(int(seed))
-    ok, plane, _ = h.mesh_ransac_plane(capi.ransac_draw(rr[2], rr[3], ransac_rounds), ransac_threshold)
+    with _rand_lock:
+        if seed is not None:
+            ctypes.CDLL("libc.so.6").srand(int(seed))
+        draws = capi.ransac_draw(rr[2], rr[3], ransac_rounds)
+    ok, plane, _ = h.mesh_ransac_plane(draws, ransac_threshold)
     lap("ransac")
     if ok:
         h.mesh_crop_plane(plane, ransac_threshold)
@@ -80,20 +84,47 @@ def process_frame(h, left_rect, right_rect, calib, dense, ransac_rounds=400, ran
     return FrameResult(np.asarray(plane, np.float64), int(npts), buf, ms)
 
 
-def run_sequence(frames, calib, dense, device=0, rank=0, world=1, dist=None, handle=None, **kw):
+def run_sequence(frames, calib, dense, device=0, rank=0, world=1, dist=None, handle=None, xyzc_out=None, **kw):
     """frames: list of callables or (left, right) tuples, one per frame of the WHOLE sequence; this rank processes frames
-    rank, rank+world, ...  Returns (mean_plane, planes[n_frames][4], results of the owned frames).  Pass `handle` to keep
-    the device arena (several GB) across calls; otherwise one is created and destroyed here."""
+    rank, rank+world, ...  Returns (mean_plane, planes[n_frames][4], results of the owned frames).
+
+    handle: one capi.Handle or a list of them.  With a list of k handles, k frames are in flight on this GPU, one host
+    thread and one stream each (the C calls release the GIL): the aggregation sweeps are latency-bound (DESIGN.md section
+    4), so a second frame's kernels fill the SMs' idle issue slots.  Frame i gets seed i either way, so the planes do not
+    depend on k.  xyzc_out: a reusable buffer, or a list with one per handle.  Without `handle` one is created and
+    destroyed here (the arena is several GB: keep one across calls when processing more than one sequence)."""
     from . import launcher
-    h = handle if handle is not None else capi.Handle(device)
+    own = handle is None
+    hs = [capi.Handle(device)] if own else (list(handle) if isinstance(handle, (list, tuple)) else [handle])
+    outs = list(xyzc_out) if isinstance(xyzc_out, (list, tuple)) else [xyzc_out] * len(hs)
+    if len(hs) > 1 and xyzc_out is not None and len({id(o) for o in outs}) != len(hs):
+        raise ValueError("one xyzc_out buffer per handle is needed when frames are in flight concurrently")
     try:
         owned = launcher.shard(len(frames), rank, world)
-        results = []
-        for i in owned:
-            f = frames[i]() if callable(frames[i]) else frames[i]
-            results.append(process_frame(h, f[0], f[1], calib, dense, seed=i, **kw))
+        results = [None] * len(owned)
+        errors = []
+
+        def work(k):
+            try:
+                for j in range(k, len(owned), len(hs)):
+                    i = owned[j]
+                    f = frames[i]() if callable(frames[i]) else frames[i]
+                    results[j] = process_frame(hs[k], f[0], f[1], calib, dense, seed=i, xyzc_out=outs[k], **kw)
+            except BaseException as e:      # re-raised on the caller's thread
+                errors.append(e)
+
+        if len(hs) == 1:
+            work(0)
+        else:
+            ths = [threading.Thread(target=work, args=(k,)) for k in range(len(hs))]
+            for t in ths:
+                t.start()
+            for t in ths:
+                t.join()
+        if errors:
+            raise errors[0]
         mean, allp = launcher.reduce_planes([r.plane for r in results], len(frames), owned, dist)
         return mean, allp, results
     finally:
-        if handle is None:
-            h.close()
+        if own:
+            hs[0].close()
