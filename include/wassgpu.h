@@ -116,7 +116,7 @@ typedef struct wsg_dense_params {
     int MIN_DISPARITY;
     int MAX_DISPARITY;            /* = numberOfDisparities (wass_stereo.cpp:768) */
     int WINSIZE;
-    double DENSE_SCALE;           /* only 1.0 is supported */
+    double DENSE_SCALE;           /* != 1: cv::resize INTER_CUBIC before the matcher, NEAREST + CUBIC after (OpenCV's own arithmetic, IPP-free) */
     int DISPARITY_OFFSET;
     int DISP_DILATE_STEPS;
     int DISP_EROSION_STEPS;
@@ -140,10 +140,34 @@ void wsg_dense_params_default(wsg_dense_params* p);
 int wsg_dense_stereo(wsg_handle* h, const uint8_t* left_crop, const uint8_t* right_crop, int rows, int cols,
                      size_t stride, const wsg_dense_params* p, float* disp_roi, int16_t* disp16_roi);
 
-/* Replaces wass_stereo.cpp:853-928 alone: int16 x16 ROI disparity -> cleaned float32 disparity. HOST pointers. */
+/* Size of the matcher's input for a rows x cols crop (wass_stereo.cpp:788-797): x is scaled when DENSE_SCALE > 1, both
+ * axes when < 1; lengths are cv::resize's saturate_cast<int>(n * scale).  With DENSE_SCALE != 1 wsg_dense_stereo's
+ * disp16_roi has this size; disp_roi always has the crop's. */
+void wsg_dense_scaled_size(int rows, int cols, double dense_scale, int* rows_s, int* cols_s);
+
+/* Replaces wass_stereo.cpp:853-928 alone: int16 x16 ROI disparity -> cleaned float32 disparity. HOST pointers.
+ * denseScale must be 1 here (the output has the input's size). */
 int wsg_disparity_postprocess(wsg_handle* h, const int16_t* disp16_roi, int rows, int cols, int minDisparity,
                               int numDisparities, int disparityOffset, double denseScale, int dilateSteps,
                               int erosionSteps, float* disp_roi);
+/* The same with DENSE_SCALE != 1: disp16_roi is rows x cols (the resized matcher input's size), disp_roi is
+ * out_rows x out_cols (roi_comb_right's size, wass_stereo.cpp:903-904): values are multiplied by 1/denseScale, filtered,
+ * enlarged with INTER_NEAREST and INTER_CUBIC, and the bicubic map is zeroed where the eroded nearest map is zero. */
+int wsg_disparity_postprocess_resized(wsg_handle* h, const int16_t* disp16_roi, int rows, int cols, int minDisparity,
+                                      int numDisparities, int disparityOffset, double denseScale, int dilateSteps,
+                                      int erosionSteps, float* disp_roi, int out_rows, int out_cols);
+
+/* cv::resize as the path uses it (OpenCV's own resize code; the Intel IPP path some OpenCV builds substitute differs by
+ * +-1 on a few % of 8-bit pixels -- DESIGN.md section 2).  HOST pointers.
+ * wsg_resize_u8_cubic == cv::resize(src, dst, Size(), fx, fy, INTER_CUBIC) on CV_8UC1 (wass_stereo.cpp:790-795);
+ *   dst must be round(rows*fy) x round(cols*fx).
+ * wsg_resize_f32 == cv::resize(src, dst, Size(dst_cols,dst_rows), 0, 0, interpolation) on CV_32FC1 (:903-904). */
+#define WSG_INTER_NEAREST 0
+#define WSG_INTER_CUBIC 2
+int wsg_resize_u8_cubic(wsg_handle* h, const uint8_t* src, int rows, int cols, size_t stride, double fx, double fy,
+                        uint8_t* dst, int dst_rows, int dst_cols);
+int wsg_resize_f32(wsg_handle* h, const float* src, int rows, int cols, float* dst, int dst_rows, int dst_cols,
+                   int interpolation);
 
 /* Replaces wass_stereo.cpp:941-986 alone (both steps off at the reference defaults): optional cv::medianBlur (3 or 5) of
  * the float ROI disparity, then -- if bc_threshold > 0 -- zero where the squared Sobel gradient magnitude exceeds it and

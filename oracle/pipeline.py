@@ -73,18 +73,128 @@ def matrix_erode_zero(src):
     return out
 
 
+# -- cv::resize as wass_stereo uses it at DENSE_SCALE != 1 (wass_stereo.cpp:790-795, 903-904) -----------------------------
+# OpenCV's own resize code (modules/imgproc/src/resize.cpp: resizeGeneric_ with HResizeCubic / VResizeCubic, resizeNN),
+# restated from its published algorithm and pinned bit for bit against cv2 4.13 with Intel IPP switched off
+# (cv2.setUseOptimized(False); cv2.ipp.setUseIPP(False)) in tests/test_resize.py.  The cv2 wheel's DEFAULT path hands
+# INTER_CUBIC to IPP, whose arithmetic differs (u8: +-1 on 2-6 % of pixels); conda-forge's libopencv, which the reference
+# pins (meta.yaml), is built without IPP, so the non-IPP code is the reference's own arithmetic.
+def _cubic_coeffs(x):
+    """interpolateCubic, A = -0.75, float32, in OpenCV's operation order."""
+    x = x.astype(F32)
+    A, one = F32(-0.75), F32(1)
+    xp = (x + one).astype(F32)
+    c0 = ((((A * xp).astype(F32) - F32(5) * A).astype(F32) * xp).astype(F32) + F32(8) * A).astype(F32)
+    c0 = ((c0 * xp).astype(F32) - F32(4) * A).astype(F32)
+    c1 = (((((A + F32(2)) * x).astype(F32) - (A + F32(3))).astype(F32) * x).astype(F32) * x).astype(F32) + one
+    xm = (one - x).astype(F32)
+    c2 = (((((A + F32(2)) * xm).astype(F32) - (A + F32(3))).astype(F32) * xm).astype(F32) * xm).astype(F32) + one
+    c3 = (((one - c0).astype(F32) - c1).astype(F32) - c2).astype(F32)
+    return np.stack([c0, c1.astype(F32), c2.astype(F32), c3], -1).astype(F32)
+
+
+def _cubic_taps(dn, sn, inv_scale):
+    """Source indices (replicate-clamped) and float32 coefficients of the 4 taps of every destination coordinate."""
+    scale = 1.0 / inv_scale
+    f = ((np.arange(dn) + 0.5) * scale - 0.5).astype(F32)          # the coordinate is rounded to float32 first
+    s = np.floor(f).astype(np.int64)
+    fr = (f - s.astype(F32)).astype(F32)
+    idx = np.clip(s[:, None] + np.arange(-1, 3)[None, :], 0, sn - 1)
+    return idx, _cubic_coeffs(fr)
+
+
+def resize_size(n, factor):
+    """saturate_cast<int>(n * factor): round half to even."""
+    return int(np.rint(n * factor))
+
+
+def resize_cubic_u8(src, fx, fy):
+    """cv::resize(src, dst, Size(), fx, fy, INTER_CUBIC) on CV_8UC1: 11-bit fixed-point coefficients, int32 horizontal pass;
+    vertical pass in float32 (S0*b0 + (S1*b1 + (S2*b2 + S3*b3)), round half to even) on the columns the 8-lane baseline
+    SIMD loop covers and in 22-bit fixed point ((sum + 2^21) >> 22) on the remaining dw % 8 columns."""
+    src = np.asarray(src, np.uint8)
+    sh, sw = src.shape
+    dw, dh = resize_size(sw, fx), resize_size(sh, fy)
+    xi, xc = _cubic_taps(dw, sw, fx)
+    yi, yc = _cubic_taps(dh, sh, fy)
+    sat = lambda v: np.clip(np.rint(v), -32768, 32767).astype(np.int64)
+    ia, ib = sat(xc * F32(2048)), sat(yc * F32(2048))
+    S = src.astype(np.int64)
+    Hh = np.zeros((sh, dw), np.int64)
+    for k in range(4):
+        Hh += S[:, xi[:, k]] * ia[None, :, k]
+    acc = np.zeros((dh, dw), np.int64)
+    for k in range(4):
+        acc += Hh[yi[:, k]] * ib[:, k][:, None]
+    fixed = np.clip((acc + (1 << 21)) >> 22, 0, 255).astype(np.uint8)
+    b = (ib.astype(F32) * F32(1.0 / (2048 * 2048))).astype(F32)
+    R = [Hh[yi[:, k]].astype(F32) for k in range(4)]
+    t = (R[3] * b[:, 3][:, None]).astype(F32)
+    for k in (2, 1, 0):
+        t = ((R[k] * b[:, k][:, None]).astype(F32) + t).astype(F32)
+    out = np.clip(np.rint(t), 0, 255).astype(np.uint8)
+    kx = dw // 8 * 8
+    out[:, kx:] = fixed[:, kx:]
+    return out
+
+
+def resize_cubic_f32(src, dw, dh):
+    """cv::resize(src, dst, Size(dw,dh), 0, 0, INTER_CUBIC) on CV_32FC1: horizontal ((S0*a0 + S1*a1) + S2*a2) + S3*a3,
+    vertical S0*b0 + (S1*b1 + (S2*b2 + S3*b3)) on the 4-lane SIMD columns, left to right on the remaining dw % 4."""
+    src = np.asarray(src, F32)
+    sh, sw = src.shape
+    xi, xc = _cubic_taps(dw, sw, dw / sw)
+    yi, yc = _cubic_taps(dh, sh, dh / sh)
+    Hh = (src[:, xi[:, 0]] * xc[None, :, 0]).astype(F32)
+    for k in (1, 2, 3):
+        Hh = (Hh + (src[:, xi[:, k]] * xc[None, :, k]).astype(F32)).astype(F32)
+    R = [Hh[yi[:, k]] for k in range(4)]
+    t = (R[3] * yc[:, 3][:, None]).astype(F32)
+    for k in (2, 1, 0):
+        t = ((R[k] * yc[:, k][:, None]).astype(F32) + t).astype(F32)
+    u = (R[0] * yc[:, 0][:, None]).astype(F32)
+    for k in (1, 2, 3):
+        u = (u + (R[k] * yc[:, k][:, None]).astype(F32)).astype(F32)
+    kx = dw // 4 * 4
+    t[:, kx:] = u[:, kx:]
+    return t
+
+
+def resize_nearest(src, dw, dh):
+    """cv::resize(..., INTER_NEAREST): sx = min(floor(x / (dw/sw)), sw-1) in double."""
+    sh, sw = src.shape
+    ifx, ify = 1.0 / (dw / sw), 1.0 / (dh / sh)
+    xs = np.minimum(np.floor(np.arange(dw) * ifx).astype(np.int64), sw - 1)
+    ys = np.minimum(np.floor(np.arange(dh) * ify).astype(np.int64), sh - 1)
+    return src[ys][:, xs]
+
+
+def dense_input_resize(crop, dense_scale):
+    """wass_stereo.cpp:788-797: x only when enlarging, both axes when shrinking."""
+    if dense_scale > 1.0:
+        return resize_cubic_u8(crop, dense_scale, 1.0)
+    if dense_scale < 1.0:
+        return resize_cubic_u8(crop, dense_scale, dense_scale)
+    return crop
+
+
 def postprocess_disparity(disp16_roi, mindisp, num_disp, disparity_offset=0, dense_scale=1.0,
-                          dilate_steps=1, erosion_steps=2):
-    """wass_stereo.cpp:853-928 at DENSE_SCALE==1 (both cv::resize calls are exact copies then)."""
-    assert dense_scale == 1.0
+                          dilate_steps=1, erosion_steps=2, out_size=None):
+    """wass_stereo.cpp:853-928.  disp16_roi has the size of the (resized) matcher input; out_size = (rows, cols) of
+    roi_comb_right, needed when DENSE_SCALE != 1 (at 1 both cv::resize calls are exact copies)."""
     off = max(disparity_offset, 0)
     d = clean_and_convert_disparity(disp16_roi, mindisp, num_disp, off, 1.0 / dense_scale)
     for _ in range(max(dilate_steps, 0)):
         d = matrix_dilate_zero(d)
     for _ in range(max(erosion_steps, 0)):
         d = matrix_erode_zero(d)
-    nn = matrix_erode_zero(d)
-    out = d.copy()
+    if dense_scale == 1.0 and (out_size is None or tuple(out_size) == d.shape):
+        nn, cub = d, d
+    else:
+        nn = resize_nearest(d, out_size[1], out_size[0])
+        cub = resize_cubic_f32(d, out_size[1], out_size[0])
+    nn = matrix_erode_zero(nn)
+    out = cub.copy()
     out[nn == 0] = 0
     return out
 

@@ -116,3 +116,28 @@ def test_full_workdir_run(tmp_path):
     z_true = W / dtrue
     # (the exported cloud is cropped to PLANE_MAX_DISTANCE around the fitted plane, so compare ranges, not medians)
     assert z_true.min() * 0.9 < np.percentile(pts[:, 2], 1) and np.percentile(pts[:, 2], 99) < z_true.max() * 1.1
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("scale", [0.5, 1.5])
+def test_workdir_run_with_dense_scale(tmp_path, scale):
+    """DENSE_SCALE != 1 through the executable (wass_stereo.cpp:783-797, 903-928, 1172-1180): the matcher runs on resized
+    crops and the disparity comes back in full-resolution pixels, so the fitted plane must agree with the DENSE_SCALE=1 run."""
+    from wass_b200 import synth, workdir
+    W, H, D = 640, 480, 64
+    right, left, _ = synth.make_pair(W, H, D, seed=2, d0=8.0)
+    c = synth.make_calibration(W, H)
+    planes = []
+    for s in (1.0, scale):
+        wd = tmp_path / ("wd_%g" % s)
+        workdir.write_workdir(str(wd), left, right, c["K0"], c["K1"], c["R"], c["T"])
+        cfg = tmp_path / ("cfg_%g.txt" % s)
+        # at scale s the disparities are s times as large: keep the search range covering them
+        workdir.write_config(str(cfg), MAX_DISPARITY=D if s <= 1 else 2 * D, RANDOM_SEED=7, PLANE_RANSAC_ROUNDS=60, DENSE_SCALE=s)
+        r = run([str(cfg), str(wd)])
+        assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+        planes.append(np.array([float(x) for x in (wd / "plane.txt").read_text().split()]))
+        pts = workdir.load_camera_mesh(str(wd / "mesh_cam.xyzC"))
+        assert pts.shape[0] > 0.3 * W * H
+    assert np.abs(planes[0][:3] @ planes[1][:3]) > 0.999            # same normal within ~2.5 degrees
+    assert abs(planes[0][3] - planes[1][3]) < 0.05 * abs(planes[0][3])

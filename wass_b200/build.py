@@ -19,7 +19,7 @@ CXX = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 FLAGS = ["-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "-ccbin", CXX]
 # fp32/fp64 parity kernels: reproduce the reference's operation order literally (no FMA contraction)
-PER_FILE = {"geom_kernels.cu": ["-fmad=false"], "capi_geom.cu": ["-fmad=false"], "rectify.cu": ["-fmad=false"]}
+PER_FILE = {"geom_kernels.cu": ["-fmad=false"], "capi_geom.cu": ["-fmad=false"], "rectify.cu": ["-fmad=false"], "resize_kernels.cu": ["-fmad=false"]}
 
 
 def _newer(srcs, out):

@@ -124,6 +124,11 @@ def load():
     lib.wsg_refine_params_default.restype = None
     lib.wsg_dense_stereo.argtypes = [vp, vp, vp, ci, ci, sz, ctypes.POINTER(DenseParams), vp, vp]
     lib.wsg_disparity_postprocess.argtypes = [vp, vp, ci, ci, ci, ci, ci, ctypes.c_double, ci, ci, vp]
+    lib.wsg_disparity_postprocess_resized.argtypes = [vp, vp, ci, ci, ci, ci, ci, ctypes.c_double, ci, ci, vp, ci, ci]
+    lib.wsg_dense_scaled_size.argtypes = [ci, ci, ctypes.c_double, ctypes.POINTER(ci), ctypes.POINTER(ci)]
+    lib.wsg_dense_scaled_size.restype = None
+    lib.wsg_resize_u8_cubic.argtypes = [vp, vp, ci, ci, sz, ctypes.c_double, ctypes.c_double, vp, ci, ci]
+    lib.wsg_resize_f32.argtypes = [vp, vp, ci, ci, vp, ci, ci, ci]
     lib.wsg_disparity_refine.argtypes = [vp, vp, ci, ci, ci, ci]
     lib.wsg_triangulate.argtypes = [vp, vp, vp, vp, vp, vp, ctypes.POINTER(Calib), ctypes.POINTER(TriParams), u64p]
     lib.wsg_triangulate_from_dense.argtypes = [vp, vp, vp, vp, vp, ctypes.POINTER(Calib), ctypes.POINTER(TriParams), u64p]
@@ -300,17 +305,39 @@ class Handle:
         right_crop = np.ascontiguousarray(right_crop, np.uint8)
         H, W = left_crop.shape
         out = np.empty((H, W), np.float32) if want_host else None
-        d16 = np.empty((H, W), np.int16) if want_disp16 else None
+        hs, ws = ctypes.c_int(), ctypes.c_int()      # the matcher runs on the DENSE_SCALE-resized crops
+        self.lib.wsg_dense_scaled_size(H, W, params.DENSE_SCALE, ctypes.byref(hs), ctypes.byref(ws))
+        d16 = np.empty((hs.value, ws.value), np.int16) if want_disp16 else None
         self._ck(self.lib.wsg_dense_stereo(self.h, left_crop.ctypes.data, right_crop.ctypes.data, H, W, W, ctypes.byref(params),
                                            out.ctypes.data if want_host else None, d16.ctypes.data if want_disp16 else None))
         return (out, d16) if want_disp16 else out
 
-    def disparity_postprocess(self, disp16_roi, min_disp, num_disp, disparity_offset=0, dense_scale=1.0, dilate=1, erode=2):
+    def disparity_postprocess(self, disp16_roi, min_disp, num_disp, disparity_offset=0, dense_scale=1.0, dilate=1, erode=2,
+                              out_size=None):
+        """wass_stereo.cpp:853-928; out_size=(rows, cols) of the ROI when dense_scale != 1."""
         d = np.ascontiguousarray(disp16_roi, np.int16)
         H, W = d.shape
-        out = np.empty((H, W), np.float32)
-        self._ck(self.lib.wsg_disparity_postprocess(self.h, d.ctypes.data, H, W, min_disp, num_disp, disparity_offset,
-                                                    dense_scale, dilate, erode, out.ctypes.data))
+        oh, ow = (H, W) if out_size is None else out_size
+        out = np.empty((oh, ow), np.float32)
+        self._ck(self.lib.wsg_disparity_postprocess_resized(self.h, d.ctypes.data, H, W, min_disp, num_disp, disparity_offset,
+                                                            dense_scale, dilate, erode, out.ctypes.data, oh, ow))
+        return out
+
+    def resize_u8_cubic(self, img, fx, fy):
+        """cv::resize(img, None, fx=fx, fy=fy, interpolation=INTER_CUBIC) on uint8 (wass_stereo.cpp:790-795)."""
+        a = np.ascontiguousarray(img, np.uint8)
+        H, W = a.shape
+        dh, dw = int(np.rint(H * fy)), int(np.rint(W * fx))
+        out = np.empty((dh, dw), np.uint8)
+        self._ck(self.lib.wsg_resize_u8_cubic(self.h, a.ctypes.data, H, W, W, fx, fy, out.ctypes.data, dh, dw))
+        return out
+
+    def resize_f32(self, img, dst_rows, dst_cols, interpolation="cubic"):
+        """cv::resize(img, (dst_cols, dst_rows), interpolation=INTER_CUBIC|INTER_NEAREST) on float32 (:903-904)."""
+        a = np.ascontiguousarray(img, np.float32)
+        out = np.empty((dst_rows, dst_cols), np.float32)
+        self._ck(self.lib.wsg_resize_f32(self.h, a.ctypes.data, a.shape[0], a.shape[1], out.ctypes.data, dst_rows, dst_cols,
+                                         {"nearest": 0, "cubic": 2}[interpolation]))
         return out
 
     # ---- triangulation + mesh ----

@@ -29,7 +29,7 @@ void wsg_destroy(wsg_handle* h)
     cudaStreamSynchronize(h->stream);
     drain_profile(h);
     for (DevBuf* b : {&h->pre1, &h->pre2, &h->C, &h->S, &h->raw, &h->img1, &h->img2, &h->disp, &h->scalars, &h->bnd, &h->keys,
-                      &h->d1, &h->dbg, &h->crop_l, &h->crop_r,
+                      &h->d1, &h->dbg, &h->crop_l, &h->crop_r, &h->rs_l, &h->rs_r, &h->rs_tab, &h->fc,
                       &h->fa, &h->fb, &h->dispfull, &h->im_left, &h->im_right, &h->mask_l, &h->mask_r, &h->m_valid, &h->m_X, &h->m_Y,
                       &h->m_Z, &h->m_color, &h->m_labels, &h->m_scratch, &h->m_small, &h->m_out})
         if (b->p) cudaFree(b->p);

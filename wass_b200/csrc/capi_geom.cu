@@ -36,25 +36,43 @@ int need_mesh(wsg_handle* h)
     return WSG_OK;
 }
 
-// device part of wass_stereo.cpp:853-928 on the ROI disparity (int16 x16, `cols_full` per row, ROI starting at x0)
+// saturate_cast<int>(n * factor) of cv::resize's dsize (round half to even)
+int resized_len(int n, double factor) { return (int)nearbyint((double)n * factor); }
+
+// device part of wass_stereo.cpp:853-928 on the ROI disparity (int16 x16, `cols_full` per row, ROI starting at x0, size
+// rows x width = the matcher's (resized) input); the result, out_rows x out_cols (roi_comb_right's size), ends up in h->fa
 int postprocess_device(wsg_handle* h, const int16_t* d_disp16, int rows, int cols_full, int x0, int width, int mindisp,
-                       int ndisp, int disp_offset, double dense_scale, int dilate, int erode)
+                       int ndisp, int disp_offset, double dense_scale, int dilate, int erode, int out_rows, int out_cols)
 {
-    const size_t n = (size_t)rows * width;
+    const bool same = out_rows == rows && out_cols == width;
+    if (dense_scale == 1.0 && !same) { h->err = "output size differs from the input size at DENSE_SCALE == 1"; return WSG_ERR_INVALID_ARG; }
+    const size_t n = (size_t)rows * width, no = (size_t)out_rows * out_cols, nmax = std::max(n, no);
     int rc;
-    if ((rc = ensure(h, h->fa, n * 4))) return rc;
-    if ((rc = ensure(h, h->fb, n * 4))) return rc;
+    if ((rc = ensure(h, h->fa, nmax * 4))) return rc;
+    if ((rc = ensure(h, h->fb, nmax * 4))) return rc;
     float* a = (float*)h->fa.p;
     float* b = (float*)h->fb.p;
-    StageTimer t(h, WSG_STAGE_POSTFILTER, 2 + std::max(dilate, 0) + std::max(erode, 0));
+    StageTimer t(h, WSG_STAGE_POSTFILTER, 2 + std::max(dilate, 0) + std::max(erode, 0) + (same ? 0 : 5));
     launch_clean_convert(d_disp16, rows, cols_full, x0, width, mindisp, ndisp, disp_offset, 1.0 / dense_scale, a, h->stream);
     for (int s = 0; s < dilate; ++s) { launch_dilate_zero(a, b, rows, width, h->stream); std::swap(a, b); }
     for (int s = 0; s < erode; ++s) { launch_erode_zero(a, b, rows, width, h->stream); std::swap(a, b); }
-    launch_mask_by_eroded(a, b, rows, width, h->stream);
-    std::swap(a, b);
+    if (same) {
+        launch_mask_by_eroded(a, b, rows, width, h->stream);
+        std::swap(a, b);
+    } else {
+        // nearest-neighbour and bicubic enlargements; the eroded nearest-neighbour map masks the bicubic one (:903-928)
+        if ((rc = ensure(h, h->fc, no * 4))) return rc;
+        if ((rc = ensure(h, h->rs_tab, resize_tab_bytes(out_cols, out_rows)))) return rc;
+        float* c = (float*)h->fc.p;
+        launch_resize_nn_f32(a, width, rows, b, out_cols, out_rows, h->stream);             // b = nn
+        launch_resize_cubic_f32(a, width, rows, c, out_cols, out_rows, h->rs_tab.p, h->stream);   // c = cubic
+        launch_erode_zero(b, a, out_rows, out_cols, h->stream);                            // a = eroded nn
+        launch_mask_where_zero(c, a, no, b, h->stream);                                    // b = result
+        a = b;
+    }
     if (a != (float*)h->fa.p) std::swap(h->fa, h->fb);   // result always ends up in h->fa
     CK(h, cudaGetLastError());
-    h->dense_rows = rows; h->dense_cols = width; h->have_dense = true;
+    h->dense_rows = out_rows; h->dense_cols = out_cols; h->have_dense = true;
     return WSG_OK;
 }
 
@@ -139,27 +157,38 @@ void wsg_refine_params_default(wsg_refine_params* p)
     p->PLANE_REFINEMENT_MAX_DISTANCE = 70.0; p->PLANE_WEIGHT_PROPORTIONAL_TO_DISTANCE = 1; p->PLANE_USE_CENTRAL_THIRD_ONLY = 0;
 }
 
+void wsg_dense_scaled_size(int rows, int cols, double dense_scale, int* rows_s, int* cols_s)
+{
+    // wass_stereo.cpp:788-797: x only when enlarging, both axes when shrinking
+    if (rows_s) *rows_s = dense_scale < 1.0 ? resized_len(rows, dense_scale) : rows;
+    if (cols_s) *cols_s = dense_scale != 1.0 ? resized_len(cols, dense_scale) : cols;
+}
+
 int wsg_dense_stereo(wsg_handle* h, const uint8_t* left_crop, const uint8_t* right_crop, int rows, int cols, size_t stride,
                      const wsg_dense_params* p, float* disp_roi, int16_t* disp16_roi)
 {
     if (!h) return WSG_ERR_INVALID_ARG;
     if (!left_crop || !right_crop || !p || rows <= 0 || cols <= 0 || stride < (size_t)cols) { h->err = "bad argument"; return WSG_ERR_INVALID_ARG; }
-    if (p->DENSE_SCALE != 1.0) { h->err = "DENSE_SCALE != 1 is not supported (cv::resize INTER_CUBIC parity not implemented)"; return WSG_ERR_INVALID_ARG; }
+    const double scale = p->DENSE_SCALE;
+    if (!(scale > 0.0) || !std::isfinite(scale)) { h->err = "DENSE_SCALE must be positive"; return WSG_ERR_INVALID_ARG; }
     CK(h, cudaSetDevice(h->device));
+    int srows, scols;                      // size of the matcher's input
+    wsg_dense_scaled_size(rows, cols, scale, &srows, &scols);
+    if (srows < 1 || scols < 1) { h->err = "DENSE_SCALE leaves no pixels"; return WSG_ERR_INVALID_ARG; }
     const int N = p->MAX_DISPARITY;
     const int off = std::max(p->DISPARITY_OFFSET, 0), comp = std::max(-p->DISPARITY_OFFSET, 0);
     if (comp > N + off) { h->err = "DISPARITY_OFFSET too negative"; return WSG_ERR_INVALID_ARG; }
-    const int wp = cols + N + off;
+    const int wp = scols + N + off;
     wsg_sgbm_params sp;
     sp.minDisparity = p->MIN_DISPARITY; sp.numDisparities = N; sp.blockSize = p->WINSIZE;
     sp.P1 = p->DENSE_P1_MULT * p->WINSIZE * p->WINSIZE; sp.P2 = p->DENSE_P2_MULT * p->WINSIZE * p->WINSIZE;
     sp.disp12MaxDiff = p->DENSE_DISP12MAXDIFF; sp.preFilterCap = p->DENSE_PREFILTER_CAP; sp.uniquenessRatio = p->DENSE_UNIQUENESS_RATIO;
     sp.speckleWindowSize = p->DENSE_SPECKLE_WINDOW_SIZE; sp.speckleRange = p->DENSE_SPECKLE_RANGE; sp.mode = p->mode;
     SgbmPlan pl{};
-    int rc = wsg_make_plan(h, rows, wp, &sp, pl);
+    int rc = wsg_make_plan(h, srows, wp, &sp, pl);
     if (rc) return rc;
     h->plan = pl;
-    const size_t ncrop = (size_t)rows * cols, npad = (size_t)rows * wp;
+    const size_t ncrop = (size_t)rows * cols, npad = (size_t)srows * wp;
     if ((rc = ensure(h, h->crop_l, ncrop))) return rc;
     if ((rc = ensure(h, h->crop_r, ncrop))) return rc;
     if ((rc = ensure(h, h->img1, npad))) return rc;
@@ -167,37 +196,101 @@ int wsg_dense_stereo(wsg_handle* h, const uint8_t* left_crop, const uint8_t* rig
     if ((rc = ensure(h, h->disp, npad * 2))) return rc;
     CK(h, cudaMemcpy2DAsync(h->crop_l.p, cols, left_crop, stride, cols, rows, cudaMemcpyHostToDevice, h->stream));
     CK(h, cudaMemcpy2DAsync(h->crop_r.p, cols, right_crop, stride, cols, rows, cudaMemcpyHostToDevice, h->stream));
-    launch_pad_images((const uint8_t*)h->crop_l.p, (const uint8_t*)h->crop_r.p, cols, rows, cols, N, off, comp,
-                      (uint8_t*)h->img1.p, (uint8_t*)h->img2.p, wp, h->stream);
+    const uint8_t *dl = (const uint8_t*)h->crop_l.p, *dr = (const uint8_t*)h->crop_r.p;
+    if (scale != 1.0) {
+        // cv::resize(..., INTER_CUBIC) of both crops (wass_stereo.cpp:788-797)
+        const size_t ns = (size_t)srows * scols;
+        if ((rc = ensure(h, h->rs_l, ns))) return rc;
+        if ((rc = ensure(h, h->rs_r, ns))) return rc;
+        if ((rc = ensure(h, h->rs_tab, resize_tab_bytes(scols, srows)))) return rc;
+        const double fy = scale < 1.0 ? scale : 1.0;
+        StageTimer t(h, WSG_STAGE_POSTFILTER, 6);
+        launch_resize_cubic_u8(dl, cols, cols, rows, scale, fy, (uint8_t*)h->rs_l.p, scols, scols, srows, h->rs_tab.p, h->stream);
+        launch_resize_cubic_u8(dr, cols, cols, rows, scale, fy, (uint8_t*)h->rs_r.p, scols, scols, srows, h->rs_tab.p, h->stream);
+        dl = (const uint8_t*)h->rs_l.p; dr = (const uint8_t*)h->rs_r.p;
+    }
+    launch_pad_images(dl, dr, scols, srows, scols, N, off, comp, (uint8_t*)h->img1.p, (uint8_t*)h->img2.p, wp, h->stream);
     rc = wsg_run_sgbm(h, (const uint8_t*)h->img1.p, (const uint8_t*)h->img2.p, wp, (int16_t*)h->disp.p);
     if (rc) return rc;
-    rc = postprocess_device(h, (const int16_t*)h->disp.p, rows, wp, N, cols, p->MIN_DISPARITY, N, off, p->DENSE_SCALE,
-                            p->DISP_DILATE_STEPS, p->DISP_EROSION_STEPS);
+    rc = postprocess_device(h, (const int16_t*)h->disp.p, srows, wp, N, scols, p->MIN_DISPARITY, N, off, scale,
+                            p->DISP_DILATE_STEPS, p->DISP_EROSION_STEPS, rows, cols);
     if (rc) return rc;
     if ((rc = refine_device(h, rows, cols, p->MEDIAN_FILTER_WSIZE, p->DENSE_DISPARITY_BIGGEST_COMPONENT_THRESHOLD))) return rc;
     if (disp_roi) CK(h, cudaMemcpyAsync(disp_roi, h->fa.p, ncrop * 4, cudaMemcpyDeviceToHost, h->stream));
     if (disp16_roi)
-        CK(h, cudaMemcpy2DAsync(disp16_roi, (size_t)cols * 2, (const int16_t*)h->disp.p + N, (size_t)wp * 2, (size_t)cols * 2, rows,
+        CK(h, cudaMemcpy2DAsync(disp16_roi, (size_t)scols * 2, (const int16_t*)h->disp.p + N, (size_t)wp * 2, (size_t)scols * 2, srows,
                                 cudaMemcpyDeviceToHost, h->stream));
     CK(h, cudaStreamSynchronize(h->stream));
     return wsg_check_sweep(h);
 }
 
-int wsg_disparity_postprocess(wsg_handle* h, const int16_t* disp16_roi, int rows, int cols, int minDisparity, int numDisparities,
-                              int disparityOffset, double denseScale, int dilateSteps, int erosionSteps, float* disp_roi)
+int wsg_disparity_postprocess_resized(wsg_handle* h, const int16_t* disp16_roi, int rows, int cols, int minDisparity,
+                                      int numDisparities, int disparityOffset, double denseScale, int dilateSteps,
+                                      int erosionSteps, float* disp_roi, int out_rows, int out_cols)
 {
     if (!h) return WSG_ERR_INVALID_ARG;
-    if (!disp16_roi || !disp_roi || rows <= 0 || cols <= 0) { h->err = "bad argument"; return WSG_ERR_INVALID_ARG; }
-    if (denseScale != 1.0) { h->err = "DENSE_SCALE != 1 is not supported"; return WSG_ERR_INVALID_ARG; }
+    if (!disp16_roi || !disp_roi || rows <= 0 || cols <= 0 || out_rows <= 0 || out_cols <= 0 || !(denseScale > 0.0)) { h->err = "bad argument"; return WSG_ERR_INVALID_ARG; }
     CK(h, cudaSetDevice(h->device));
     const size_t n = (size_t)rows * cols;
     int rc;
     if ((rc = ensure(h, h->disp, n * 2))) return rc;
     CK(h, cudaMemcpyAsync(h->disp.p, disp16_roi, n * 2, cudaMemcpyHostToDevice, h->stream));
     rc = postprocess_device(h, (const int16_t*)h->disp.p, rows, cols, 0, cols, minDisparity, numDisparities,
-                            std::max(disparityOffset, 0), denseScale, dilateSteps, erosionSteps);
+                            std::max(disparityOffset, 0), denseScale, dilateSteps, erosionSteps, out_rows, out_cols);
     if (rc) return rc;
-    CK(h, cudaMemcpyAsync(disp_roi, h->fa.p, n * 4, cudaMemcpyDeviceToHost, h->stream));
+    CK(h, cudaMemcpyAsync(disp_roi, h->fa.p, (size_t)out_rows * out_cols * 4, cudaMemcpyDeviceToHost, h->stream));
+    CK(h, cudaStreamSynchronize(h->stream));
+    return WSG_OK;
+}
+
+int wsg_disparity_postprocess(wsg_handle* h, const int16_t* disp16_roi, int rows, int cols, int minDisparity, int numDisparities,
+                              int disparityOffset, double denseScale, int dilateSteps, int erosionSteps, float* disp_roi)
+{
+    if (h && denseScale != 1.0) { h->err = "DENSE_SCALE != 1 changes the output size: use wsg_disparity_postprocess_resized"; return WSG_ERR_INVALID_ARG; }
+    return wsg_disparity_postprocess_resized(h, disp16_roi, rows, cols, minDisparity, numDisparities, disparityOffset, denseScale,
+                                             dilateSteps, erosionSteps, disp_roi, rows, cols);
+}
+
+int wsg_resize_u8_cubic(wsg_handle* h, const uint8_t* src, int rows, int cols, size_t stride, double fx, double fy,
+                        uint8_t* dst, int dst_rows, int dst_cols)
+{
+    if (!h) return WSG_ERR_INVALID_ARG;
+    if (!src || !dst || rows <= 0 || cols <= 0 || stride < (size_t)cols || !(fx > 0.0) || !(fy > 0.0)) { h->err = "bad argument"; return WSG_ERR_INVALID_ARG; }
+    if (dst_rows != resized_len(rows, fy) || dst_cols != resized_len(cols, fx) || dst_rows < 1 || dst_cols < 1) {
+        h->err = "dst size must be round(rows*fy) x round(cols*fx)"; return WSG_ERR_INVALID_ARG;
+    }
+    CK(h, cudaSetDevice(h->device));
+    int rc;
+    if ((rc = ensure(h, h->crop_l, (size_t)rows * cols))) return rc;
+    if ((rc = ensure(h, h->rs_l, (size_t)dst_rows * dst_cols))) return rc;
+    if ((rc = ensure(h, h->rs_tab, resize_tab_bytes(dst_cols, dst_rows)))) return rc;
+    CK(h, cudaMemcpy2DAsync(h->crop_l.p, cols, src, stride, cols, rows, cudaMemcpyHostToDevice, h->stream));
+    launch_resize_cubic_u8((const uint8_t*)h->crop_l.p, cols, cols, rows, fx, fy, (uint8_t*)h->rs_l.p, dst_cols, dst_cols, dst_rows,
+                           h->rs_tab.p, h->stream);
+    CK(h, cudaGetLastError());
+    CK(h, cudaMemcpyAsync(dst, h->rs_l.p, (size_t)dst_rows * dst_cols, cudaMemcpyDeviceToHost, h->stream));
+    CK(h, cudaStreamSynchronize(h->stream));
+    return WSG_OK;
+}
+
+int wsg_resize_f32(wsg_handle* h, const float* src, int rows, int cols, float* dst, int dst_rows, int dst_cols, int interpolation)
+{
+    if (!h) return WSG_ERR_INVALID_ARG;
+    if (!src || !dst || rows <= 0 || cols <= 0 || dst_rows <= 0 || dst_cols <= 0 ||
+        (interpolation != WSG_INTER_NEAREST && interpolation != WSG_INTER_CUBIC)) { h->err = "bad argument"; return WSG_ERR_INVALID_ARG; }
+    CK(h, cudaSetDevice(h->device));
+    const size_t n = (size_t)rows * cols, no = (size_t)dst_rows * dst_cols;
+    int rc;
+    if ((rc = ensure(h, h->fb, n * 4))) return rc;
+    if ((rc = ensure(h, h->fc, no * 4))) return rc;
+    if ((rc = ensure(h, h->rs_tab, resize_tab_bytes(dst_cols, dst_rows)))) return rc;
+    CK(h, cudaMemcpyAsync(h->fb.p, src, n * 4, cudaMemcpyHostToDevice, h->stream));
+    if (interpolation == WSG_INTER_CUBIC)
+        launch_resize_cubic_f32((const float*)h->fb.p, cols, rows, (float*)h->fc.p, dst_cols, dst_rows, h->rs_tab.p, h->stream);
+    else
+        launch_resize_nn_f32((const float*)h->fb.p, cols, rows, (float*)h->fc.p, dst_cols, dst_rows, h->stream);
+    CK(h, cudaGetLastError());
+    CK(h, cudaMemcpyAsync(dst, h->fc.p, no * 4, cudaMemcpyDeviceToHost, h->stream));
     CK(h, cudaStreamSynchronize(h->stream));
     return WSG_OK;
 }

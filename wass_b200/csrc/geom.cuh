@@ -34,6 +34,13 @@ void launch_clean_convert(const int16_t* disp16, int rows, int cols_full, int x0
                           int disp_offset, double scale, float* out, cudaStream_t st);
 void launch_dilate_zero(const float* src, float* dst, int rows, int cols, cudaStream_t st);
 void launch_erode_zero(const float* src, float* dst, int rows, int cols, cudaStream_t st);
+// resize_kernels.cu: cv::resize of the DENSE_SCALE != 1 path (wass_stereo.cpp:788-797, 903-904)
+size_t resize_tab_bytes(int dw, int dh);
+void launch_resize_cubic_u8(const uint8_t* src, size_t sstride, int sw, int sh, double fx, double fy, uint8_t* dst, size_t dstride,
+                            int dw, int dh, void* tab, cudaStream_t st);
+void launch_resize_cubic_f32(const float* src, int sw, int sh, float* dst, int dw, int dh, void* tab, cudaStream_t st);
+void launch_resize_nn_f32(const float* src, int sw, int sh, float* dst, int dw, int dh, cudaStream_t st);
+void launch_mask_where_zero(const float* cub, const float* nn_eroded, size_t n, float* out, cudaStream_t st);
 void launch_mask_by_eroded(const float* src, float* dst, int rows, int cols, cudaStream_t st);
 void launch_paste_roi(const float* roi, int rh, int rw, float* full, int rows, int cols, int x0, int y0, cudaStream_t st);
 

@@ -34,7 +34,7 @@ struct wsg_handle {
     bool have_plan = false;
     wsg_sgbm_stats stats{};
     // dense stage / geometry arena
-    DevBuf crop_l, crop_r, fa, fb, dispfull, im_left, im_right, mask_l, mask_r;
+    DevBuf crop_l, crop_r, rs_l, rs_r, rs_tab, fa, fb, fc, dispfull, im_left, im_right, mask_l, mask_r;
     int dense_rows = 0, dense_cols = 0;     // size of the ROI disparity held in `fa` after wsg_dense_stereo
     bool have_dense = false;
     DevBuf m_valid, m_X, m_Y, m_Z, m_color, m_labels, m_scratch, m_small, m_out;
