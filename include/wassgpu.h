@@ -247,9 +247,17 @@ int wsg_mesh_export_xyzbin(wsg_handle* h, void* dst, size_t capacity, size_t* nb
 
 /* Replaces cv::undistort(img, out, K, dist) of the stage two steps up (src/wass_prepare/wass_prepare.cpp:268; SURVEY section 8f
  * rank 4): 8-bit grey HOST image in and out, dist = (k1 k2 p1 p2 [k3 [k4 k5 k6]]), bilinear in OpenCV's 1/32-pixel fixed
- * point, constant (0) border.  CLAHE and the polarimetric demosaic of wass_prepare are not part of this entry point. */
+ * point, constant (0) border.  The polarimetric demosaic of wass_prepare is not built. */
 int wsg_undistort_image(wsg_handle* h, const uint8_t* img, int rows, int cols, size_t stride, const double K[9], const double* dist,
                         int ndist, uint8_t* out);
+/* Replaces clahe->apply(img, dst) of wass_prepare (src/wass_prepare/wass_prepare.cpp:257-262; cv::createCLAHE(clip_limit,
+ * Size(tiles, tiles)) at :458-462 and :479-483, keys CAMx_CLAHE_CLIPLIMIT / CAMx_CLAHE_TILEGRIDSIZE): 8-bit grey HOST image
+ * in and out, bit-exact vs cv2.createCLAHE. */
+int wsg_clahe_image(wsg_handle* h, const uint8_t* img, int rows, int cols, size_t stride, double clip_limit, int tiles, uint8_t* out);
+/* process_image() of wass_prepare without the polarimetric branch (wass_prepare.cpp:88-275): optional CLAHE (clahe_tiles > 0)
+ * then cv::undistort (K != NULL), chained on the device with one upload and one download. */
+int wsg_prepare_image(wsg_handle* h, const uint8_t* img, int rows, int cols, size_t stride, int clahe_tiles, double clahe_clip,
+                      const double K[9], const double* dist, int ndist, uint8_t* out);
 
 /* ---- consumer side of the mesh (the step right after the hot path) -------------------------------- */
 /* Replaces load_camera_mesh + align_on_sea_plane (gridding/wassgridsurface/wass_utils.py:22-35 and 38-68, called at

@@ -169,6 +169,52 @@ def resize_nearest(src, dw, dh):
     return src[ys][:, xs]
 
 
+def clahe_u8(src, clip_limit, tiles):
+    """cv::createCLAHE(clip_limit, Size(tiles,tiles))->apply(src) on CV_8UC1 (src/wass_prepare/wass_prepare.cpp:257-262,
+    458-462): OpenCV's published algorithm (modules/imgproc/src/clahe.cpp), pinned bit-exact against cv2 in
+    tests/test_prepare.py."""
+    src = np.asarray(src, np.uint8)
+    H, W = src.shape
+    if W % tiles == 0 and H % tiles == 0:
+        ext = src
+    else:   # both paddings are applied, a whole extra `tiles` where the size already divides
+        ext = np.pad(src, ((0, tiles - H % tiles), (0, tiles - W % tiles)), mode="reflect")
+    tw, th = ext.shape[1] // tiles, ext.shape[0] // tiles
+    area = tw * th
+    lut_scale = F32(255) / F32(area)
+    clip = max(int(clip_limit * area / 256), 1) if clip_limit > 0 else 0
+    luts = np.zeros((tiles, tiles, 256), np.uint8)
+    for j in range(tiles):
+        for i in range(tiles):
+            h = np.bincount(ext[j * th:(j + 1) * th, i * tw:(i + 1) * tw].ravel(), minlength=256).astype(np.int64)
+            if clip > 0:
+                clipped = int(np.maximum(h - clip, 0).sum())
+                h = np.minimum(h, clip)
+                batch = clipped // 256
+                residual = clipped - batch * 256
+                h += batch
+                if residual:
+                    step = max(256 // residual, 1)
+                    k = np.arange(0, 256, step)[:residual]
+                    h[k] += 1
+            luts[j, i] = np.clip(np.rint((np.cumsum(h).astype(F32) * lut_scale).astype(F32)), 0, 255).astype(np.uint8)
+
+    def blend_coords(n, inv, ntiles):
+        f = (np.arange(n).astype(F32) * inv - F32(0.5)).astype(F32)
+        t1 = np.floor(f).astype(np.int64)
+        a = (f - t1.astype(F32)).astype(F32)
+        return np.maximum(t1, 0), np.minimum(t1 + 1, ntiles - 1), a, (F32(1) - a).astype(F32)
+
+    tx1, tx2, xa, xa1 = blend_coords(W, F32(1) / F32(tw), tiles)
+    ty1, ty2, ya, ya1 = blend_coords(H, F32(1) / F32(th), tiles)
+    v = src.astype(np.int64)
+    L = luts.astype(F32)
+    top = ((L[ty1[:, None], tx1[None, :], v] * xa1[None, :]).astype(F32) + (L[ty1[:, None], tx2[None, :], v] * xa[None, :]).astype(F32)).astype(F32)
+    bot = ((L[ty2[:, None], tx1[None, :], v] * xa1[None, :]).astype(F32) + (L[ty2[:, None], tx2[None, :], v] * xa[None, :]).astype(F32)).astype(F32)
+    res = ((top * ya1[:, None]).astype(F32) + (bot * ya[:, None]).astype(F32)).astype(F32)
+    return np.clip(np.rint(res), 0, 255).astype(np.uint8)
+
+
 def dense_input_resize(crop, dense_scale):
     """wass_stereo.cpp:788-797: x only when enlarging, both axes when shrinking."""
     if dense_scale > 1.0:

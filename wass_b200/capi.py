@@ -151,6 +151,8 @@ def load():
     lib.wsg_stereo_rectify.argtypes = [dp, dp, dp, dp, ci, ci, dp, dp, dp, dp, ip, ip]
     lib.wsg_rectify_image.argtypes = [vp, vp, ci, ci, sz, dp, dp, dp, vp]
     lib.wsg_undistort_image.argtypes = [vp, vp, ci, ci, sz, dp, dp, ci, vp]
+    lib.wsg_clahe_image.argtypes = [vp, vp, ci, ci, sz, ctypes.c_double, ci, vp]
+    lib.wsg_prepare_image.argtypes = [vp, vp, ci, ci, sz, ci, ctypes.c_double, dp, dp, ci, vp]
     lib.wsg_plane_mean_accumulate.argtypes = [dp, dp]
     lib.wsg_plane_mean_accumulate.restype = None
     lib.wsg_plane_mean_finish.argtypes = [dp, dp]
@@ -467,6 +469,25 @@ class Handle:
         self._ck(self.lib.wsg_undistort_image(self.h, img.ctypes.data, H, W, W, _darr(K, 9),
                                               d.ctypes.data_as(ctypes.POINTER(ctypes.c_double)) if d.size else None, int(d.size),
                                               out.ctypes.data))
+        return out
+
+    def clahe_image(self, img, clip_limit, tiles):
+        """cv::createCLAHE(clip_limit, (tiles, tiles)).apply(img) as wass_prepare applies it (8-bit grey)."""
+        img = np.ascontiguousarray(img, np.uint8)
+        H, W = img.shape
+        out = np.empty((H, W), np.uint8)
+        self._ck(self.lib.wsg_clahe_image(self.h, img.ctypes.data, H, W, W, float(clip_limit), int(tiles), out.ctypes.data))
+        return out
+
+    def prepare_image(self, img, K, dist, clahe_tiles=0, clahe_clip=2.0):
+        """process_image() of wass_prepare (wass_prepare.cpp:88-275, no demosaic): CLAHE if clahe_tiles > 0, then undistort."""
+        img = np.ascontiguousarray(img, np.uint8)
+        H, W = img.shape
+        out = np.empty((H, W), np.uint8)
+        d = np.ascontiguousarray(np.asarray(dist, np.float64).reshape(-1))
+        self._ck(self.lib.wsg_prepare_image(self.h, img.ctypes.data, H, W, W, int(clahe_tiles), float(clahe_clip), _darr(K, 9),
+                                            d.ctypes.data_as(ctypes.POINTER(ctypes.c_double)) if d.size else None, int(d.size),
+                                            out.ctypes.data))
         return out
 
     def rectify_image(self, img, K, Rrect, P):

@@ -324,13 +324,11 @@ static bool inv3_cv(const double* S, double* D)
     return true;
 }
 
-int wsg_undistort_image(wsg_handle* h, const uint8_t* img, int rows, int cols, size_t stride, const double K[9], const double* dist,
-                        int ndist, uint8_t* out)
+// cv::undistort on device buffers: d_src -> d_dst (both rows x cols, tight)
+static int undistort_device(wsg_handle* h, const uint8_t* d_src, uint8_t* d_dst, int rows, int cols, const double K[9],
+                            const double* dist, int ndist)
 {
-    if (!h) return WSG_ERR_INVALID_ARG;
-    if (!img || !K || !out || rows <= 0 || cols <= 0 || stride < (size_t)cols || ndist < 0 || (ndist && !dist)) { h->err = "bad argument"; return WSG_ERR_INVALID_ARG; }
     if (ndist != 0 && ndist != 4 && ndist != 5 && ndist != 8) { h->err = "distortion vector must have 0, 4, 5 or 8 coefficients"; return WSG_ERR_INVALID_ARG; }
-    CK(h, cudaSetDevice(h->device));
     UndistortArgs a;
     for (int i = 0; i < 8; ++i) a.k[i] = i < ndist ? dist[i] : 0.;
     a.fx = K[0]; a.fy = K[4]; a.u0 = K[2]; a.v0 = K[5];
@@ -344,20 +342,153 @@ int wsg_undistort_image(wsg_handle* h, const uint8_t* img, int rows, int cols, s
     }
     const size_t n = (size_t)rows * cols;
     int rc;
-    if ((rc = ensure(h, h->im_left, n))) return rc;
-    if ((rc = ensure(h, h->im_right, n))) return rc;
     if ((rc = ensure(h, h->m_scratch, n * sizeof(int2) + ir.size() * 8 + 64))) return rc;
     int2* d_map = (int2*)h->m_scratch.p;
     double* d_ir = (double*)((char*)h->m_scratch.p + n * sizeof(int2));
     CK(h, cudaMemcpyAsync(d_ir, ir.data(), ir.size() * 8, cudaMemcpyHostToDevice, h->stream));
-    CK(h, cudaMemcpy2DAsync(h->im_left.p, cols, img, stride, cols, rows, cudaMemcpyHostToDevice, h->stream));
+    CK(h, cudaStreamSynchronize(h->stream));        // `ir` is pageable host memory leaving scope
     undistort_map_kernel<<<(rows + 63) / 64, 64, 0, h->stream>>>(a, d_ir, d_map);
     dim3 b(128), g((cols + 127) / 128, rows);
-    undistort_remap_kernel<<<g, b, 0, h->stream>>>((const uint8_t*)h->im_left.p, rows, cols, cols, d_map, (uint8_t*)h->im_right.p);
-    CK(h, cudaMemcpyAsync(out, h->im_right.p, n, cudaMemcpyDeviceToHost, h->stream));
-    CK(h, cudaStreamSynchronize(h->stream));
+    undistort_remap_kernel<<<g, b, 0, h->stream>>>(d_src, rows, cols, cols, d_map, d_dst);
     CK(h, cudaGetLastError());
     return WSG_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// cv::CLAHE::apply on CV_8UC1 (src/wass_prepare/wass_prepare.cpp:257-262, 458-462, 479-483).  OpenCV's algorithm: the image is
+// padded (BORDER_REFLECT_101, right and bottom) to a multiple of the tile grid -- by a whole extra `tiles` when only one of
+// the two sizes divides --, one 256-bin histogram per tile is clipped at clipLimit*area/256 with the excess redistributed
+// (equal batch + one count on every `256/residual`-th bin), its running sum times 255/area rounded to the tile's LUT, and
+// every pixel is the bilinear blend (float32, products then sums, round half to even) of the four nearest tiles' LUTs.
+// Oracle: oracle/pipeline.py clahe_u8, bit-exact vs cv2.createCLAHE in tests/test_prepare.py.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int reflect101(int p, int len)
+{
+    if (len == 1) return 0;
+    while ((unsigned)p >= (unsigned)len) p = p < 0 ? -p : 2 * (len - 1) - p;
+    return p;
+}
+
+__global__ void __launch_bounds__(256) clahe_lut_kernel(const uint8_t* __restrict__ src, int rows, int cols, int tw, int th,
+                                                        int clip, float lut_scale, uint8_t* __restrict__ luts)
+{
+    __shared__ int hist[256];
+    __shared__ int scan[256];
+    __shared__ int red[8];
+    const int t = threadIdx.x;
+    hist[t] = 0;
+    __syncthreads();
+    const int x0 = blockIdx.x * tw, y0 = blockIdx.y * th;
+    for (int i = t; i < tw * th; i += 256) {
+        const int y = reflect101(y0 + i / tw, rows), x = reflect101(x0 + i % tw, cols);
+        atomicAdd(&hist[src[(size_t)y * cols + x]], 1);
+    }
+    __syncthreads();
+    int hv = hist[t];
+    if (clip > 0) {
+        int over = max(hv - clip, 0);
+        hv = min(hv, clip);
+        for (int o = 16; o; o >>= 1) over += __shfl_xor_sync(0xffffffffu, over, o);
+        if ((t & 31) == 0) red[t >> 5] = over;
+        __syncthreads();
+        int clipped = 0;
+        for (int k = 0; k < 8; ++k) clipped += red[k];
+        const int batch = clipped / 256, residual = clipped - batch * 256;
+        hv += batch;
+        if (residual) {
+            const int step = max(256 / residual, 1);
+            if (t % step == 0 && t / step < residual) ++hv;
+        }
+    }
+    scan[t] = hv;
+    __syncthreads();
+    for (int o = 1; o < 256; o <<= 1) {          // inclusive running sum
+        const int v = t >= o ? scan[t - o] : 0;
+        __syncthreads();
+        scan[t] += v;
+        __syncthreads();
+    }
+    const int v = __float2int_rn(__fmul_rn((float)scan[t], lut_scale));
+    luts[((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 256 + t] = (uint8_t)min(max(v, 0), 255);
+}
+
+__global__ void clahe_apply_kernel(const uint8_t* __restrict__ src, int rows, int cols, int tiles_x, int tiles_y, float inv_tw,
+                                   float inv_th, const uint8_t* __restrict__ luts, uint8_t* __restrict__ dst)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= cols) return;
+    const float txf = __fsub_rn(__fmul_rn((float)x, inv_tw), 0.5f), tyf = __fsub_rn(__fmul_rn((float)y, inv_th), 0.5f);
+    const float fx = floorf(txf), fy = floorf(tyf);
+    const float xa = __fsub_rn(txf, fx), ya = __fsub_rn(tyf, fy);
+    const float xa1 = __fsub_rn(1.f, xa), ya1 = __fsub_rn(1.f, ya);
+    const int tx1 = max((int)fx, 0), tx2 = min((int)fx + 1, tiles_x - 1);
+    const int ty1 = max((int)fy, 0), ty2 = min((int)fy + 1, tiles_y - 1);
+    const int v = src[(size_t)y * cols + x];
+    const uint8_t* l1 = luts + (size_t)ty1 * tiles_x * 256 + v;
+    const uint8_t* l2 = luts + (size_t)ty2 * tiles_x * 256 + v;
+    const float top = __fadd_rn(__fmul_rn((float)l1[tx1 * 256], xa1), __fmul_rn((float)l1[tx2 * 256], xa));
+    const float bot = __fadd_rn(__fmul_rn((float)l2[tx1 * 256], xa1), __fmul_rn((float)l2[tx2 * 256], xa));
+    const int r = __float2int_rn(__fadd_rn(__fmul_rn(top, ya1), __fmul_rn(bot, ya)));
+    dst[(size_t)y * cols + x] = (uint8_t)min(max(r, 0), 255);
+}
+
+// d_src -> d_dst (rows x cols, tight)
+static int clahe_device(wsg_handle* h, const uint8_t* d_src, uint8_t* d_dst, int rows, int cols, double clip_limit, int tiles)
+{
+    if (tiles < 1) { h->err = "CLAHE tile grid size must be positive"; return WSG_ERR_INVALID_ARG; }
+    int erows = rows, ecols = cols;
+    if (cols % tiles != 0 || rows % tiles != 0) { erows = rows + tiles - rows % tiles; ecols = cols + tiles - cols % tiles; }
+    const int tw = ecols / tiles, th = erows / tiles, area = tw * th;
+    int clip = 0;
+    if (clip_limit > 0.0) clip = std::max((int)(clip_limit * area / 256), 1);
+    int rc;
+    if ((rc = ensure(h, h->rs_tab, (size_t)tiles * tiles * 256))) return rc;
+    clahe_lut_kernel<<<dim3(tiles, tiles), 256, 0, h->stream>>>(d_src, rows, cols, tw, th, clip, 255.f / (float)area, (uint8_t*)h->rs_tab.p);
+    dim3 b(128), g((cols + 127) / 128, rows);
+    clahe_apply_kernel<<<g, b, 0, h->stream>>>(d_src, rows, cols, tiles, tiles, 1.f / (float)tw, 1.f / (float)th,
+                                               (const uint8_t*)h->rs_tab.p, d_dst);
+    CK(h, cudaGetLastError());
+    return WSG_OK;
+}
+
+int wsg_prepare_image(wsg_handle* h, const uint8_t* img, int rows, int cols, size_t stride, int clahe_tiles, double clahe_clip,
+                      const double K[9], const double* dist, int ndist, uint8_t* out)
+{
+    if (!h) return WSG_ERR_INVALID_ARG;
+    if (!img || !out || rows <= 0 || cols <= 0 || stride < (size_t)cols || ndist < 0 || (ndist && !dist) || (!K && ndist >= 0 && clahe_tiles <= 0)) {
+        h->err = "bad argument"; return WSG_ERR_INVALID_ARG;
+    }
+    CK(h, cudaSetDevice(h->device));
+    const size_t n = (size_t)rows * cols;
+    int rc;
+    if ((rc = ensure(h, h->im_left, n))) return rc;
+    if ((rc = ensure(h, h->im_right, n))) return rc;
+    uint8_t *a = (uint8_t*)h->im_left.p, *b = (uint8_t*)h->im_right.p;
+    CK(h, cudaMemcpy2DAsync(a, cols, img, stride, cols, rows, cudaMemcpyHostToDevice, h->stream));
+    if (clahe_tiles > 0) {                       // wass_prepare.cpp:257-262
+        if ((rc = clahe_device(h, a, b, rows, cols, clahe_clip, clahe_tiles))) return rc;
+        std::swap(a, b);
+    }
+    if (K) {                                     // wass_prepare.cpp:268
+        if ((rc = undistort_device(h, a, b, rows, cols, K, dist, ndist))) return rc;
+        std::swap(a, b);
+    }
+    CK(h, cudaMemcpyAsync(out, a, n, cudaMemcpyDeviceToHost, h->stream));
+    CK(h, cudaStreamSynchronize(h->stream));
+    return WSG_OK;
+}
+
+int wsg_clahe_image(wsg_handle* h, const uint8_t* img, int rows, int cols, size_t stride, double clip_limit, int tiles, uint8_t* out)
+{
+    if (h && tiles < 1) { h->err = "CLAHE tile grid size must be positive"; return WSG_ERR_INVALID_ARG; }
+    return wsg_prepare_image(h, img, rows, cols, stride, tiles, clip_limit, nullptr, nullptr, 0, out);
+}
+
+int wsg_undistort_image(wsg_handle* h, const uint8_t* img, int rows, int cols, size_t stride, const double K[9], const double* dist,
+                        int ndist, uint8_t* out)
+{
+    if (h && !K) { h->err = "bad argument"; return WSG_ERR_INVALID_ARG; }
+    return wsg_prepare_image(h, img, rows, cols, stride, 0, 0.0, K, dist, ndist, out);
 }
 
 int wsg_rectify_image(wsg_handle* h, const uint8_t* img, int rows, int cols, size_t stride, const double K[9], const double Rrect[9],
