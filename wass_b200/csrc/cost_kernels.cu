@@ -17,7 +17,7 @@
 namespace wsg {
 
 static constexpr int WDT = 32;             // disparities per CTA
-static constexpr int WDTP = 40;            // u16 per column in shared memory (80 B: kills the 4-column bank aliasing)
+static constexpr int WDTP = 32;            // u16 per column in shared memory (64 B, no padding: columns are swizzled, see wcol)
 static constexpr int WRB = 256;            // rows per band
 static constexpr int WMAXSW = 8;           // windows up to 17
 static constexpr int WRVPAD = 4;
@@ -34,6 +34,12 @@ template <int XT> struct WideCfg {
     static constexpr int CTAS = XT == 64 ? 2 : 1;
 };
 
+// Physical column of logical column c in the pd / ring arrays.  A quarter-warp of a 16-byte access covers two columns
+// (P1: c, c+1; P2: c, c+CPT): flipping bit 0 with bit log2(CPT) puts those two in different 64-byte halves of the 128-byte
+// bank line, so every LDS.128 / STS.128 of the kernel is conflict-free (the 80-byte padded layout was 2-way conflicting
+// for CPT = 2: ncu showed the shared-memory pipe 90 % busy, the kernel's limiter).
+template <int CPT> __device__ __forceinline__ int wcol(int c) { return c ^ ((c >> (CPT == 2 ? 1 : 2)) & 1); }
+
 struct WideSmem { int pd, uu, rv, ring, total; };
 template <int XT> __host__ __device__ inline WideSmem wide_layout(int SH2)
 {
@@ -42,7 +48,7 @@ template <int XT> __host__ __device__ inline WideSmem wide_layout(int SH2)
     s.pd = 0;                                          // u16 [2][NCOL][WDTP]
     s.uu = s.pd + 2 * Cfg::NCOL * WDTP * 2;            // u32 [2][NCOL][8]
     s.rv = s.uu + 2 * Cfg::NCOL * 8 * 4;               // s16 [2][RV]
-    s.ring = (s.rv + 2 * Cfg::RV * 2 + 15) & ~15;      // u16 [2*SH2+1][XT][WDTP]
+    s.ring = (s.rv + 2 * Cfg::RV * 2 + 127) & ~127;    // u16 [2*SH2+1][XT][WDTP], bank-line aligned
     s.total = s.ring + (2 * SH2 + 1) * XT * WDTP * 2;
     return s;
 }
@@ -131,7 +137,7 @@ __global__ void __launch_bounds__(WideCfg<XT>::CT, WideCfg<XT>::CTAS) cost_wide_
                     }
                     out = make_uint4(res[0], res[1], res[2], res[3]);
                 }
-                *reinterpret_cast<uint4*>(pd + (b * WNCOL + cc) * WDTP + gg * 8) = out;
+                *reinterpret_cast<uint4*>(pd + (b * WNCOL + wcol<Cfg::CPT>(cc)) * WDTP + gg * 8) = out;
             }
             // ---------------- T (second half): unpack into tables[s&1]
             if (doT) {
@@ -161,37 +167,38 @@ __global__ void __launch_bounds__(WideCfg<XT>::CT, WideCfg<XT>::CTAS) cost_wide_
                 const int b = idx & 1;
                 unsigned hs[4] = {0, 0, 0, 0};
                 uint4 head[CPT > 1 ? CPT - 1 : 1];
-                const uint16_t* prow = pd + (b * WNCOL + cg * CPT) * WDTP + g * 8;
+                const uint16_t* prow = pd + b * WNCOL * WDTP + g * 8;
+                const int c0 = cg * CPT;
 #pragma unroll
                 for (int i = 0; i < CPT - 1; ++i) {   // the columns that leave the window while sliding
-                    head[i] = *reinterpret_cast<const uint4*>(prow + i * WDTP);
+                    head[i] = *reinterpret_cast<const uint4*>(prow + wcol<CPT>(c0 + i) * WDTP);
                     if (i < win) {
                         hs[0] = __vadd2(hs[0], head[i].x); hs[1] = __vadd2(hs[1], head[i].y);
                         hs[2] = __vadd2(hs[2], head[i].z); hs[3] = __vadd2(hs[3], head[i].w);
                     }
                 }
                 for (int i = CPT - 1; i < win; ++i) {
-                    const uint4 v = *reinterpret_cast<const uint4*>(prow + i * WDTP);
+                    const uint4 v = *reinterpret_cast<const uint4*>(prow + wcol<CPT>(c0 + i) * WDTP);
                     hs[0] = __vadd2(hs[0], v.x); hs[1] = __vadd2(hs[1], v.y);
                     hs[2] = __vadd2(hs[2], v.z); hs[3] = __vadd2(hs[3], v.w);
                 }
                 const bool store = idx >= 2 * p.SH2;
-                uint4* slot = reinterpret_cast<uint4*>(ring + (rslot * WXT + cg * CPT) * WDTP + g * 8);
+                uint4* slot = reinterpret_cast<uint4*>(ring + rslot * WXT * WDTP + g * 8);
 #pragma unroll
                 for (int cc = 0; cc < CPT; ++cc) {
                     if (cc > 0) {
-                        const uint4 vn = *reinterpret_cast<const uint4*>(prow + (win - 1 + cc) * WDTP);
+                        const uint4 vn = *reinterpret_cast<const uint4*>(prow + wcol<CPT>(c0 + win - 1 + cc) * WDTP);
                         const uint4 vo = head[cc - 1];
                         hs[0] = __vsub2(__vadd2(hs[0], vn.x), vo.x); hs[1] = __vsub2(__vadd2(hs[1], vn.y), vo.y);
                         hs[2] = __vsub2(__vadd2(hs[2], vn.z), vo.z); hs[3] = __vsub2(__vadd2(hs[3], vn.w), vo.w);
                     }
                     unsigned* ac = acc[cc];
                     if (idx >= NR) {
-                        const uint4 o = slot[cc * (WDTP / 8)];
+                        const uint4 o = slot[wcol<CPT>(c0 + cc) * (WDTP / 8)];
                         ac[0] = __vsub2(ac[0], o.x); ac[1] = __vsub2(ac[1], o.y);
                         ac[2] = __vsub2(ac[2], o.z); ac[3] = __vsub2(ac[3], o.w);
                     }
-                    slot[cc * (WDTP / 8)] = make_uint4(hs[0], hs[1], hs[2], hs[3]);
+                    slot[wcol<CPT>(c0 + cc) * (WDTP / 8)] = make_uint4(hs[0], hs[1], hs[2], hs[3]);
                     ac[0] = __vadd2(ac[0], hs[0]); ac[1] = __vadd2(ac[1], hs[1]);
                     ac[2] = __vadd2(ac[2], hs[2]); ac[3] = __vadd2(ac[3], hs[3]);
                     if (store && x0 + cg * CPT + cc < p.W1) {
