@@ -40,6 +40,14 @@ template <int XT> struct WideCfg {
 // for CPT = 2: ncu showed the shared-memory pipe 90 % busy, the kernel's limiter).
 template <int CPT> __device__ __forceinline__ int wcol(int c) { return c ^ ((c >> (CPT == 2 ? 1 : 2)) & 1); }
 
+// u16 offset of the 8-disparity chunk g of logical column c inside one pd row buffer.  The chunk index is flipped with
+// bit 1 of the column so that a P1 quarter-warp (4 columns x 2 chunks, see the lane mapping in stage P1) also covers all
+// eight 16-byte slots of a bank line.
+template <int CPT> __device__ __forceinline__ int pd_off(int c, int g)
+{
+    return wcol<CPT>(c) * WDTP + ((g ^ (c & 2)) << 3);
+}
+
 struct WideSmem { int pd, uu, rv, ring, total; };
 template <int XT> __host__ __device__ inline WideSmem wide_layout(int SH2)
 {
@@ -108,9 +116,13 @@ __global__ void __launch_bounds__(WideCfg<XT>::CT, WideCfg<XT>::CTAS) cost_wide_
             }
             // ---------------- P1: pixel cost of row-step s-1 from tables[(s-1)&1] into pd[(s-1)&1]
             const int rs = s - 1;
-            if (rs >= 0 && rs < nsteps && tid < ncol * 4) {
+            // lane mapping: a warp covers 16 columns x 2 disparity groups (warps 2k / 2k+1 of a 16-column block take
+            // groups {0,1} / {2,3}).  The 16 lanes of one pair parity then read only 12 distinct table words (the two
+            // groups overlap), so the two parity copies never meet in a bank; with 8 columns x 4 groups every LDS of
+            // the img2 tables was a 2-way conflict (32 distinct words, ranges shifting by one with the tile's parity).
+            const int cc = (tid >> 6) * 16 + ((tid & 31) >> 1), gg = (tid & 1) + ((tid >> 4) & 2);
+            if (rs >= 0 && rs < nsteps && cc < ncol) {
                 const int b = rs & 1;
-                const int cc = tid >> 2, gg = tid & 3;
                 uint4 out = make_uint4(0, 0, 0, 0);
                 if (d0 + 8 * gg < p.D) {
                     const int xx = p.minX1 + min(max(x0 - p.SW2 + cc, 0), p.W1 - 1);
@@ -137,7 +149,7 @@ __global__ void __launch_bounds__(WideCfg<XT>::CT, WideCfg<XT>::CTAS) cost_wide_
                     }
                     out = make_uint4(res[0], res[1], res[2], res[3]);
                 }
-                *reinterpret_cast<uint4*>(pd + (b * WNCOL + wcol<Cfg::CPT>(cc)) * WDTP + gg * 8) = out;
+                *reinterpret_cast<uint4*>(pd + b * WNCOL * WDTP + pd_off<Cfg::CPT>(cc, gg)) = out;
             }
             // ---------------- T (second half): unpack into tables[s&1]
             if (doT) {
@@ -147,8 +159,10 @@ __global__ void __launch_bounds__(WideCfg<XT>::CT, WideCfg<XT>::CTAS) cost_wide_
                 if (isU) {
                     auto bc = [](int v) -> unsigned { return ((unsigned)v & 0xFFFFu) * 0x10001u; };
                     uint4* o = reinterpret_cast<uint4*>(uu + (b * WNCOL + te) * 8);
-                    o[0] = make_uint4(bc(v0), bc(-v0), bc(l0), bc(-h0));
-                    o[1] = make_uint4(bc(v1), bc(-v1), bc(l1), bc(-h1));
+                    const uint4 c0v = make_uint4(bc(v0), bc(-v0), bc(l0), bc(-h0)), c1v = make_uint4(bc(v1), bc(-v1), bc(l1), bc(-h1));
+                    const int first = (te >> 2) & 1;          // 32-byte records: lanes 4 apart would meet in a bank
+                    o[first] = first ? c1v : c0v;
+                    o[first ^ 1] = first ? c0v : c1v;
                 } else {
                     const int16_t val[8] = {(int16_t)v0, (int16_t)-v0, (int16_t)l0, (int16_t)-h0,
                                             (int16_t)v1, (int16_t)-v1, (int16_t)l1, (int16_t)-h1};
@@ -167,18 +181,18 @@ __global__ void __launch_bounds__(WideCfg<XT>::CT, WideCfg<XT>::CTAS) cost_wide_
                 const int b = idx & 1;
                 unsigned hs[4] = {0, 0, 0, 0};
                 uint4 head[CPT > 1 ? CPT - 1 : 1];
-                const uint16_t* prow = pd + b * WNCOL * WDTP + g * 8;
+                const uint16_t* prow = pd + b * WNCOL * WDTP;
                 const int c0 = cg * CPT;
 #pragma unroll
                 for (int i = 0; i < CPT - 1; ++i) {   // the columns that leave the window while sliding
-                    head[i] = *reinterpret_cast<const uint4*>(prow + wcol<CPT>(c0 + i) * WDTP);
+                    head[i] = *reinterpret_cast<const uint4*>(prow + pd_off<CPT>(c0 + i, g));
                     if (i < win) {
                         hs[0] = __vadd2(hs[0], head[i].x); hs[1] = __vadd2(hs[1], head[i].y);
                         hs[2] = __vadd2(hs[2], head[i].z); hs[3] = __vadd2(hs[3], head[i].w);
                     }
                 }
                 for (int i = CPT - 1; i < win; ++i) {
-                    const uint4 v = *reinterpret_cast<const uint4*>(prow + wcol<CPT>(c0 + i) * WDTP);
+                    const uint4 v = *reinterpret_cast<const uint4*>(prow + pd_off<CPT>(c0 + i, g));
                     hs[0] = __vadd2(hs[0], v.x); hs[1] = __vadd2(hs[1], v.y);
                     hs[2] = __vadd2(hs[2], v.z); hs[3] = __vadd2(hs[3], v.w);
                 }
@@ -187,7 +201,7 @@ __global__ void __launch_bounds__(WideCfg<XT>::CT, WideCfg<XT>::CTAS) cost_wide_
 #pragma unroll
                 for (int cc = 0; cc < CPT; ++cc) {
                     if (cc > 0) {
-                        const uint4 vn = *reinterpret_cast<const uint4*>(prow + wcol<CPT>(c0 + win - 1 + cc) * WDTP);
+                        const uint4 vn = *reinterpret_cast<const uint4*>(prow + pd_off<CPT>(c0 + win - 1 + cc, g));
                         const uint4 vo = head[cc - 1];
                         hs[0] = __vsub2(__vadd2(hs[0], vn.x), vo.x); hs[1] = __vsub2(__vadd2(hs[1], vn.y), vo.y);
                         hs[2] = __vsub2(__vadd2(hs[2], vn.z), vo.z); hs[3] = __vsub2(__vadd2(hs[3], vn.w), vo.w);
