@@ -98,6 +98,15 @@ __global__ void __launch_bounds__(WideCfg<XT>::CT, WideCfg<XT>::CTAS) cost_wide_
     for (int i = 0; i < CPT; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0;
     int vmax = 0;
     int rslot = 0;                            // ring slot of this row-step (idx % NR)
+    // P2 addressing, constant over the rows: the swizzle of pd repeats every PER columns, so column c0+i sits at
+    // poff[i % PER] + (i / PER) * PER * WDTP -- with the window loop unrolled the second term is an immediate.
+    constexpr int PER = CPT == 2 ? 4 : 8;
+    const int c0 = cg * CPT;
+    int poff[PER], roff[CPT];
+#pragma unroll
+    for (int j = 0; j < PER; ++j) poff[j] = pd_off<CPT>(c0 + j, g);
+#pragma unroll
+    for (int j = 0; j < CPT; ++j) roff[j] = wcol<CPT>(c0 + j) * WDTP + g * 8;
     // first output row of this band, this thread's first column and disparity vector
     int16_t* dst0 = C + ((size_t)y0 * p.W1 + (x0 + cg * CPT)) * p.Dp + vec_slot((d0 >> 3) + g, p.NL, p.K) * 8;
 
@@ -182,22 +191,24 @@ __global__ void __launch_bounds__(WideCfg<XT>::CT, WideCfg<XT>::CTAS) cost_wide_
                 unsigned hs[4] = {0, 0, 0, 0};
                 uint4 head[CPT > 1 ? CPT - 1 : 1];
                 const uint16_t* prow = pd + b * WNCOL * WDTP;
-                const int c0 = cg * CPT;
 #pragma unroll
                 for (int i = 0; i < CPT - 1; ++i) {   // the columns that leave the window while sliding
-                    head[i] = *reinterpret_cast<const uint4*>(prow + pd_off<CPT>(c0 + i, g));
+                    head[i] = *reinterpret_cast<const uint4*>(prow + poff[i % PER] + (i / PER) * PER * WDTP);
                     if (i < win) {
                         hs[0] = __vadd2(hs[0], head[i].x); hs[1] = __vadd2(hs[1], head[i].y);
                         hs[2] = __vadd2(hs[2], head[i].z); hs[3] = __vadd2(hs[3], head[i].w);
                     }
                 }
-                for (int i = CPT - 1; i < win; ++i) {
-                    const uint4 v = *reinterpret_cast<const uint4*>(prow + pd_off<CPT>(c0 + i, g));
-                    hs[0] = __vadd2(hs[0], v.x); hs[1] = __vadd2(hs[1], v.y);
-                    hs[2] = __vadd2(hs[2], v.z); hs[3] = __vadd2(hs[3], v.w);
+#pragma unroll
+                for (int i = CPT - 1; i < 2 * WMAXSW + 1; ++i) {
+                    if (i < win) {
+                        const uint4 v = *reinterpret_cast<const uint4*>(prow + poff[i % PER] + (i / PER) * PER * WDTP);
+                        hs[0] = __vadd2(hs[0], v.x); hs[1] = __vadd2(hs[1], v.y);
+                        hs[2] = __vadd2(hs[2], v.z); hs[3] = __vadd2(hs[3], v.w);
+                    }
                 }
                 const bool store = idx >= 2 * p.SH2;
-                uint4* slot = reinterpret_cast<uint4*>(ring + rslot * WXT * WDTP + g * 8);
+                uint16_t* slot = ring + rslot * WXT * WDTP;
 #pragma unroll
                 for (int cc = 0; cc < CPT; ++cc) {
                     if (cc > 0) {
@@ -208,11 +219,11 @@ __global__ void __launch_bounds__(WideCfg<XT>::CT, WideCfg<XT>::CTAS) cost_wide_
                     }
                     unsigned* ac = acc[cc];
                     if (idx >= NR) {
-                        const uint4 o = slot[wcol<CPT>(c0 + cc) * (WDTP / 8)];
+                        const uint4 o = *reinterpret_cast<const uint4*>(slot + roff[cc]);
                         ac[0] = __vsub2(ac[0], o.x); ac[1] = __vsub2(ac[1], o.y);
                         ac[2] = __vsub2(ac[2], o.z); ac[3] = __vsub2(ac[3], o.w);
                     }
-                    slot[wcol<CPT>(c0 + cc) * (WDTP / 8)] = make_uint4(hs[0], hs[1], hs[2], hs[3]);
+                    *reinterpret_cast<uint4*>(slot + roff[cc]) = make_uint4(hs[0], hs[1], hs[2], hs[3]);
                     ac[0] = __vadd2(ac[0], hs[0]); ac[1] = __vadd2(ac[1], hs[1]);
                     ac[2] = __vadd2(ac[2], hs[2]); ac[3] = __vadd2(ac[3], hs[3]);
                     if (store && x0 + cg * CPT + cc < p.W1) {
