@@ -110,34 +110,37 @@ __global__ void __launch_bounds__(WideCfg<XT>::CT, WideCfg<XT>::CTAS) cost_wide_
     // first output row of this band, this thread's first column and disparity vector
     int16_t* dst0 = C + ((size_t)y0 * p.W1 + (x0 + cg * CPT)) * p.Dp + vec_slot((d0 >> 3) + g, p.NL, p.K) * 8;
 
+    // P1 addressing, constant over the rows (see the lane mapping at stage P1)
+    const int p1cc = (tid >> 6) * 16 + ((tid & 31) >> 1), p1gg = (tid & 1) + ((tid >> 4) & 2);
+    const bool p1on = tid < WP1 && p1cc < ncol, p1real = d0 + 8 * p1gg < p.D;
+    const int p1i0 = (xb - (p.minX1 + min(max(x0 - p.SW2 + p1cc, 0), p.W1 - 1))) + 8 * p1gg;
+    const int p1rv = (p1i0 & 1) * (8 * WVT + WRVPAD) + (p1i0 & ~1);      // s16 offset into one img2 table set
+    const int p1pd = pd_off<Cfg::CPT>(p1cc, p1gg);
+
+    // T addressing: threads [0,ncol) fetch an img1 column, [ncol, ncol+WVT) an img2 table entry
+    const bool tOn = tid < ncol + WVT, isU = tid < ncol;
+    const int te = isU ? tid : tid - ncol;
+    const uint2* tsrc = isU ? pre1 + (p.minX1 + min(max(x0 - p.SW2 + te, 0), p.W1 - 1)) : pre2 + min(max(vtop - te, 0), p.W - 1);
+
     for (int s = 0; s < nsteps + 2; ++s) {
         if (tid < WP1) {
             // ---------------- T (first half): fetch this thread's prefilter record of row-step s; the latency hides
             //                  behind P1 below.  Threads [0,ncol): img1 column; [ncol, ncol+WVT): img2 table entry.
-            const bool doT = s < nsteps && tid < ncol + WVT;
-            const bool isU = tid < ncol;
-            const int te = isU ? tid : tid - ncol;
+            const bool doT = s < nsteps && tOn;
             uint2 q = make_uint2(0, 0);
-            if (doT) {
-                const int yy = min(max(y0 - p.SH2 + s, 0), p.H - 1);
-                const int xx = isU ? p.minX1 + min(max(x0 - p.SW2 + te, 0), p.W1 - 1) : min(max(vtop - te, 0), p.W - 1);
-                q = (isU ? pre1 : pre2)[(size_t)yy * p.W + xx];
-            }
+            if (doT) q = tsrc[(size_t)min(max(y0 - p.SH2 + s, 0), p.H - 1) * p.W];
             // ---------------- P1: pixel cost of row-step s-1 from tables[(s-1)&1] into pd[(s-1)&1]
             const int rs = s - 1;
             // lane mapping: a warp covers 16 columns x 2 disparity groups (warps 2k / 2k+1 of a 16-column block take
             // groups {0,1} / {2,3}).  The 16 lanes of one pair parity then read only 12 distinct table words (the two
             // groups overlap), so the two parity copies never meet in a bank; with 8 columns x 4 groups every LDS of
             // the img2 tables was a 2-way conflict (32 distinct words, ranges shifting by one with the tile's parity).
-            const int cc = (tid >> 6) * 16 + ((tid & 31) >> 1), gg = (tid & 1) + ((tid >> 4) & 2);
-            if (rs >= 0 && rs < nsteps && cc < ncol) {
+            if (rs >= 0 && rs < nsteps && p1on) {
                 const int b = rs & 1;
+                const int cc = p1cc;
                 uint4 out = make_uint4(0, 0, 0, 0);
-                if (d0 + 8 * gg < p.D) {
-                    const int xx = p.minX1 + min(max(x0 - p.SW2 + cc, 0), p.W1 - 1);
-                    const int i0 = (xb - xx) + 8 * gg;
-                    const int par = i0 & 1;
-                    const unsigned* rvw = reinterpret_cast<const unsigned*>(rv + b * WRV + par * (8 * WVT + WRVPAD)) + ((i0 - par) >> 1);
+                if (p1real) {
+                    const unsigned* rvw = reinterpret_cast<const unsigned*>(rv + b * WRV + p1rv);
                     const uint4 ua = *reinterpret_cast<const uint4*>(uu + (b * WNCOL + cc) * 8);
                     const uint4 ub = *reinterpret_cast<const uint4*>(uu + (b * WNCOL + cc) * 8 + 4);
                     unsigned res[4];
@@ -158,7 +161,7 @@ __global__ void __launch_bounds__(WideCfg<XT>::CT, WideCfg<XT>::CTAS) cost_wide_
                     }
                     out = make_uint4(res[0], res[1], res[2], res[3]);
                 }
-                *reinterpret_cast<uint4*>(pd + b * WNCOL * WDTP + pd_off<Cfg::CPT>(cc, gg)) = out;
+                *reinterpret_cast<uint4*>(pd + b * WNCOL * WDTP + p1pd) = out;
             }
             // ---------------- T (second half): unpack into tables[s&1]
             if (doT) {
