@@ -1,16 +1,18 @@
 // Cost volume of cv::StereoSGBM (SURVEY.md Appendix A.2 + A.3; call site src/wass_stereo/wass_stereo.cpp:837),
-// wide-tile form: one CTA owns 128 columns x 32 disparities and marches down a band of rows.
+// wide-tile form: one CTA owns XT (64) columns x 32 disparities and marches down a band of rows.
 //
 // Three stages run CONCURRENTLY on different warps of the CTA, one image row apart, with one barrier per row:
-//   T   (19 warps) unpack the prefilter records of row r+2 into broadcast tables (img1 side) and a reversed,
+//   T   (10 warps) unpack the prefilter records of row r+2 into broadcast tables (img1 side) and a reversed,
 //                  pre-negated table (img2 side) in shared memory; the global load is issued before P1, used after it
-//   P1  (same)     Birchfield-Tomasi pixel cost of row r+1 for 128+2*SW2 columns x 32 disparities, two disparities
-//                  per 32-bit register (VIADD.16x2 / VIADDMNMX.S16x2.RELU / VIMNMX.S16x2)
-//   P2  (4 warps)  row r: horizontal box sum (sliding over 4 adjacent columns per thread), a ring of 2*SH2+1 row sums in
-//                  shared memory for the vertical sliding sum, 16-byte stores of C
-// Compared with the 32x64 tile of cost_kernel (sgbm_kernels.cu) the halo columns recomputed by P1 drop from 75 % to
-// 19 % at the reference's window of 13, P1 runs at 95 % lane occupancy, and no stage waits for another.
-// Shared memory grows with the window: windows above 17 use cost_kernel.
+//   P1  (same)     Birchfield-Tomasi pixel cost of row r+1 for XT+2*SW2 columns x 32 disparities, two disparities
+//                  per 32-bit register (VIADD.16x2 / VIADDMNMX.S16x2.RELU / VIMNMX.S16x2); also the sums of column pairs
+//   P2  (4 warps)  row r: horizontal box sum (SW2 column pairs + one column, then sliding to the next column), a ring of
+//                  2*SH2+1 row sums in shared memory for the vertical sliding sum, 16-byte stores of C
+// The kernel is bound by the shared-memory pipe and by its longest stage (P2), so the layouts are chosen for zero bank
+// conflicts (ncu: 1.43 -> 0.78 k wavefronts per row step): swizzled unpadded columns (wcol), chunk flip (pd_off), a P1 lane
+// mapping whose two pair-parity table copies never meet in a bank, 32-byte uu records stored in two conflict-free halves.
+// History at the benchmark size (2448x2048, D=256, window 13): 32x64 tile 4.21 ms -> this form 3.77 -> 2.49 ms.
+// Shared memory grows with the window: windows above 17 use cost_kernel (sgbm_kernels.cu).
 #include "sgbm_dev.cuh"
 #include <cstdlib>
 
@@ -48,13 +50,14 @@ template <int CPT> __device__ __forceinline__ int pd_off(int c, int g)
     return wcol<CPT>(c) * WDTP + ((g ^ (c & 2)) << 3);
 }
 
-struct WideSmem { int pd, uu, rv, ring, total; };
+struct WideSmem { int pd, pp, uu, rv, ring, total; };
 template <int XT> __host__ __device__ inline WideSmem wide_layout(int SH2)
 {
     using Cfg = WideCfg<XT>;
     WideSmem s;
     s.pd = 0;                                          // u16 [2][NCOL][WDTP]
-    s.uu = s.pd + 2 * Cfg::NCOL * WDTP * 2;            // u32 [2][NCOL][8]
+    s.pp = s.pd + 2 * Cfg::NCOL * WDTP * 2;            // u16 [2][NCOL/2][WDT]: pd[2j] + pd[2j+1] (used when CPT == 2)
+    s.uu = s.pp + 2 * (Cfg::NCOL / 2) * WDT * 2;       // u32 [2][NCOL][8]
     s.rv = s.uu + 2 * Cfg::NCOL * 8 * 4;               // s16 [2][RV]
     s.ring = (s.rv + 2 * Cfg::RV * 2 + 127) & ~127;    // u16 [2*SH2+1][XT][WDTP], bank-line aligned
     s.total = s.ring + (2 * SH2 + 1) * XT * WDTP * 2;
@@ -72,6 +75,7 @@ __global__ void __launch_bounds__(WideCfg<XT>::CT, WideCfg<XT>::CTAS) cost_wide_
     constexpr int WXT = XT, WNCOL = Cfg::NCOL, WP1 = Cfg::P1, WVT = Cfg::VT, WRV = Cfg::RV;
     const WideSmem L = wide_layout<XT>(p.SH2);
     uint16_t* pd = reinterpret_cast<uint16_t*>(smem + L.pd);
+    uint16_t* pp = reinterpret_cast<uint16_t*>(smem + L.pp);
     unsigned* uu = reinterpret_cast<unsigned*>(smem + L.uu);
     int16_t* rv = reinterpret_cast<int16_t*>(smem + L.rv);
     uint16_t* ring = reinterpret_cast<uint16_t*>(smem + L.ring);
@@ -107,6 +111,7 @@ __global__ void __launch_bounds__(WideCfg<XT>::CT, WideCfg<XT>::CTAS) cost_wide_
     for (int j = 0; j < PER; ++j) poff[j] = pd_off<CPT>(c0 + j, g);
 #pragma unroll
     for (int j = 0; j < CPT; ++j) roff[j] = wcol<CPT>(c0 + j) * WDTP + g * 8;
+    const int plast = pd_off<CPT>(c0 + win - 1, g), pnext = pd_off<CPT>(c0 + win, g);   // CPT == 2: last column of the window, and the next
     // first output row of this band, this thread's first column and disparity vector
     int16_t* dst0 = C + ((size_t)y0 * p.W1 + (x0 + cg * CPT)) * p.Dp + vec_slot((d0 >> 3) + g, p.NL, p.K) * 8;
 
@@ -135,11 +140,11 @@ __global__ void __launch_bounds__(WideCfg<XT>::CT, WideCfg<XT>::CTAS) cost_wide_
             // groups {0,1} / {2,3}).  The 16 lanes of one pair parity then read only 12 distinct table words (the two
             // groups overlap), so the two parity copies never meet in a bank; with 8 columns x 4 groups every LDS of
             // the img2 tables was a 2-way conflict (32 distinct words, ranges shifting by one with the tile's parity).
-            if (rs >= 0 && rs < nsteps && p1on) {
+            if (rs >= 0 && rs < nsteps) {
                 const int b = rs & 1;
                 const int cc = p1cc;
                 uint4 out = make_uint4(0, 0, 0, 0);
-                if (p1real) {
+                if (p1on && p1real) {
                     const unsigned* rvw = reinterpret_cast<const unsigned*>(rv + b * WRV + p1rv);
                     const uint4 ua = *reinterpret_cast<const uint4*>(uu + (b * WNCOL + cc) * 8);
                     const uint4 ub = *reinterpret_cast<const uint4*>(uu + (b * WNCOL + cc) * 8 + 4);
@@ -161,7 +166,16 @@ __global__ void __launch_bounds__(WideCfg<XT>::CT, WideCfg<XT>::CTAS) cost_wide_
                     }
                     out = make_uint4(res[0], res[1], res[2], res[3]);
                 }
-                *reinterpret_cast<uint4*>(pd + b * WNCOL * WDTP + p1pd) = out;
+                if (p1on) *reinterpret_cast<uint4*>(pd + b * WNCOL * WDTP + p1pd) = out;
+                if (Cfg::CPT == 2) {
+                    // sums of column pairs (2j, 2j+1): the neighbour column is two lanes up; halves the window loads of
+                    // the box-sum warps, which are the longest stage of a row step
+                    const uint4 nb = make_uint4(__shfl_down_sync(FULL, out.x, 2), __shfl_down_sync(FULL, out.y, 2),
+                                                __shfl_down_sync(FULL, out.z, 2), __shfl_down_sync(FULL, out.w, 2));
+                    if (p1on && !(cc & 1))
+                        *reinterpret_cast<uint4*>(pp + (b * (WNCOL / 2) + (cc >> 1)) * WDT + p1gg * 8) =
+                            make_uint4(__vadd2(out.x, nb.x), __vadd2(out.y, nb.y), __vadd2(out.z, nb.z), __vadd2(out.w, nb.w));
+                }
             }
             // ---------------- T (second half): unpack into tables[s&1]
             if (doT) {
@@ -194,20 +208,37 @@ __global__ void __launch_bounds__(WideCfg<XT>::CT, WideCfg<XT>::CTAS) cost_wide_
                 unsigned hs[4] = {0, 0, 0, 0};
                 uint4 head[CPT > 1 ? CPT - 1 : 1];
                 const uint16_t* prow = pd + b * WNCOL * WDTP;
+                if (CPT == 2) {
+                    // window of column c0 (even): SW2 column pairs + the single column c0 + win - 1
+                    const uint16_t* qrow = pp + (b * (WNCOL / 2) + (c0 >> 1)) * WDT + g * 8;
 #pragma unroll
-                for (int i = 0; i < CPT - 1; ++i) {   // the columns that leave the window while sliding
-                    head[i] = *reinterpret_cast<const uint4*>(prow + poff[i % PER] + (i / PER) * PER * WDTP);
-                    if (i < win) {
-                        hs[0] = __vadd2(hs[0], head[i].x); hs[1] = __vadd2(hs[1], head[i].y);
-                        hs[2] = __vadd2(hs[2], head[i].z); hs[3] = __vadd2(hs[3], head[i].w);
+                    for (int m = 0; m < WMAXSW; ++m) {
+                        if (m < p.SW2) {
+                            const uint4 v = *reinterpret_cast<const uint4*>(qrow + m * WDT);
+                            hs[0] = __vadd2(hs[0], v.x); hs[1] = __vadd2(hs[1], v.y);
+                            hs[2] = __vadd2(hs[2], v.z); hs[3] = __vadd2(hs[3], v.w);
+                        }
                     }
-                }
+                    const uint4 v = *reinterpret_cast<const uint4*>(prow + plast);
+                    hs[0] = __vadd2(hs[0], v.x); hs[1] = __vadd2(hs[1], v.y);
+                    hs[2] = __vadd2(hs[2], v.z); hs[3] = __vadd2(hs[3], v.w);
+                    head[0] = *reinterpret_cast<const uint4*>(prow + poff[0]);
+                } else {
 #pragma unroll
-                for (int i = CPT - 1; i < 2 * WMAXSW + 1; ++i) {
-                    if (i < win) {
-                        const uint4 v = *reinterpret_cast<const uint4*>(prow + poff[i % PER] + (i / PER) * PER * WDTP);
-                        hs[0] = __vadd2(hs[0], v.x); hs[1] = __vadd2(hs[1], v.y);
-                        hs[2] = __vadd2(hs[2], v.z); hs[3] = __vadd2(hs[3], v.w);
+                    for (int i = 0; i < CPT - 1; ++i) {   // the columns that leave the window while sliding
+                        head[i] = *reinterpret_cast<const uint4*>(prow + poff[i % PER] + (i / PER) * PER * WDTP);
+                        if (i < win) {
+                            hs[0] = __vadd2(hs[0], head[i].x); hs[1] = __vadd2(hs[1], head[i].y);
+                            hs[2] = __vadd2(hs[2], head[i].z); hs[3] = __vadd2(hs[3], head[i].w);
+                        }
+                    }
+#pragma unroll
+                    for (int i = CPT - 1; i < 2 * WMAXSW + 1; ++i) {
+                        if (i < win) {
+                            const uint4 v = *reinterpret_cast<const uint4*>(prow + poff[i % PER] + (i / PER) * PER * WDTP);
+                            hs[0] = __vadd2(hs[0], v.x); hs[1] = __vadd2(hs[1], v.y);
+                            hs[2] = __vadd2(hs[2], v.z); hs[3] = __vadd2(hs[3], v.w);
+                        }
                     }
                 }
                 const bool store = idx >= 2 * p.SH2;
@@ -215,7 +246,7 @@ __global__ void __launch_bounds__(WideCfg<XT>::CT, WideCfg<XT>::CTAS) cost_wide_
 #pragma unroll
                 for (int cc = 0; cc < CPT; ++cc) {
                     if (cc > 0) {
-                        const uint4 vn = *reinterpret_cast<const uint4*>(prow + pd_off<CPT>(c0 + win - 1 + cc, g));
+                        const uint4 vn = *reinterpret_cast<const uint4*>(prow + (CPT == 2 ? pnext : pd_off<CPT>(c0 + win - 1 + cc, g)));
                         const uint4 vo = head[cc - 1];
                         hs[0] = __vsub2(__vadd2(hs[0], vn.x), vo.x); hs[1] = __vsub2(__vadd2(hs[1], vn.y), vo.y);
                         hs[2] = __vsub2(__vadd2(hs[2], vn.z), vo.z); hs[3] = __vsub2(__vadd2(hs[3], vn.w), vo.w);
