@@ -22,7 +22,7 @@ mean, allp = launcher.reduce_planes([planes_all[i] for i in owned], n, owned, di
 ref = np.nanmean(planes_all, axis=0)          # what wassgridsurface computes from planes.txt
 assert np.allclose(mean, ref, rtol=1e-14), (mean, ref)
 assert np.array_equal(np.isnan(allp), np.isnan(planes_all)) and np.allclose(np.nan_to_num(allp), np.nan_to_num(planes_all))
-os.write(1, ("rank %d ok\n" % rank).encode())      # one write: atomic on the shared pipe
+os.write(1, ("rank %%d ok\n" %% rank).encode())      # one write: atomic on the shared pipe
 dist.destroy_process_group()
 '''
 
