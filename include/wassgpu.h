@@ -184,6 +184,11 @@ typedef struct wsg_calib {
     int roi_left[4], roi_right[4];        /* x,y,width,height = roi_comb_left / roi_comb_right */
     int left_cols, left_rows, right_cols, right_rows;   /* original (undistorted) images */
     int rect_cols, rect_rows;             /* rectified images */
+    /* USE_CUSTOM_STEREORECTIFY (wass_stereo.cpp:301-305): when use_homographies != 0, rectified pixels go back to the
+     * original images through HLi / HRi (the inverses of wsg_stereo_rectify_custom's H0 / H1 for the LEFT / RIGHT image)
+     * and R1,R2,P1,P2 are not read. */
+    int use_homographies;
+    double HLi[9], HRi[9];
 } wsg_calib;
 
 typedef struct wsg_tri_params {
@@ -250,6 +255,18 @@ int wsg_mesh_export_xyzbin(wsg_handle* h, void* dst, size_t capacity, size_t* nb
  * point, constant (0) border.  The polarimetric demosaic of wass_prepare is not built. */
 int wsg_undistort_image(wsg_handle* h, const uint8_t* img, int rows, int cols, size_t stride, const double K[9], const double* dist,
                         int ndist, uint8_t* out);
+/* Replaces stereoRectifyUndistorted (src/wass_stereo/stereorectify.cpp:57-244; USE_CUSTOM_STEREORECTIFY, SURVEY section 8f
+ * rank 3), host arithmetic: rectifying homographies H0 (image of camera K0) and H1 (K1) for the pose R,T taking points of
+ * camera 1 into camera 0 (wass_stereo.cpp:502 passes Rinv, Tinv), and the common ROI (x,y,width,height).  rot_angle != 0
+ * (degrees, RECTIFY_ANGLE) is used as given; 0 minimises max(v0, v1), the perspective components of the two homographies,
+ * over the rotation about the baseline with a Nelder-Mead simplex (the reference uses cv::DownhillSolver with the same
+ * start, initial step and tolerance; that solver is not available to pin the iterates, so the optimum -- not the path --
+ * is what is reproduced: parity unpinned).  best_angle (optional) receives the angle used. */
+int wsg_stereo_rectify_custom(const double K0[9], const double K1[9], const double R[9], const double T[3], double rot_angle,
+                              int width, int height, double H0[9], double H1[9], int roi[4], double* best_angle);
+/* Replaces cv::warpPerspective(img, out, H, img.size()) (wass_stereo.cpp:515-516: INTER_LINEAR, constant 0 border): OpenCV's
+ * blocked double-precision coordinates, 1/32-pixel fixed-point bilinear weights -- bit-exact vs cv2.  HOST pointers. */
+int wsg_warp_perspective(wsg_handle* h, const uint8_t* img, int rows, int cols, size_t stride, const double H[9], uint8_t* out);
 /* Replaces clahe->apply(img, dst) of wass_prepare (src/wass_prepare/wass_prepare.cpp:257-262; cv::createCLAHE(clip_limit,
  * Size(tiles, tiles)) at :458-462 and :479-483, keys CAMx_CLAHE_CLIPLIMIT / CAMx_CLAHE_TILEGRIDSIZE): 8-bit grey HOST image
  * in and out, bit-exact vs cv2.createCLAHE. */

@@ -215,6 +215,116 @@ def clahe_u8(src, clip_limit, tiles):
     return np.clip(np.rint(res), 0, 255).astype(np.uint8)
 
 
+# -- custom rectifier (src/wass_stereo/stereorectify.cpp:57-244, USE_CUSTOM_STEREORECTIFY) ------------------------------
+def _custom_rect_functional(K0, K1, R, T):
+    """HFunctional (stereorectify.cpp:70-137): returns f(angle_deg) -> (max(v1, v2), H0, H1)."""
+    K0i, K1i = np.linalg.inv(np.asarray(K0, float)), np.linalg.inv(np.asarray(K1, float))
+    Ri = np.asarray(R, float)
+    Rv = np.asarray(T, float).ravel() / np.linalg.norm(T)
+    N = np.cross(Rv, [0.0, 1.0, 0.0])
+    N /= np.linalg.norm(N)
+    Rplane = np.stack([Rv, np.cross(Rv, N), N])
+
+    def f(x):
+        a = x / 180 * 3.14                       # sic: 3.14
+        c, s_ = np.cos(a), np.sin(a)
+        Radd = np.array([[1.0, 0, 0], [0, c, -s_], [0, s_, c]])       # Rodrigues of (a, 0, 0)
+        H0 = Radd @ Rplane @ K0i
+        H1 = Radd @ Rplane @ Ri @ K1i
+        H0 = H0 / H0[2, 2]
+        H1 = H1 / H1[2, 2]
+        v = max(H0[2, 0] ** 2 + H0[2, 1] ** 2, H1[2, 0] ** 2 + H1[2, 1] ** 2)
+        return v, H0 / np.cbrt(np.linalg.det(H0)), H1 / np.cbrt(np.linalg.det(H1))
+    return f
+
+
+def custom_rectify_best_angle(K0, K1, R, T, lo=-60.0, hi=60.0):
+    """The minimiser of the functional near 0 by an independent method (dense scan + golden section): what
+    cv::DownhillSolver converges to from (0,0) with step -0.5 (cv2 does not export that solver: parity unpinned)."""
+    f = _custom_rect_functional(K0, K1, R, T)
+    xs = np.linspace(lo, hi, 2401)
+    vals = np.array([f(x)[0] for x in xs])
+    # the local minimum a downhill walk from 0 reaches
+    i = int(np.argmin(np.abs(xs)))
+    while 0 < i < len(xs) - 1 and (vals[i - 1] < vals[i] or vals[i + 1] < vals[i]):
+        i = i - 1 if vals[i - 1] < vals[i + 1] else i + 1
+    a, b = xs[max(i - 1, 0)], xs[min(i + 1, len(xs) - 1)]
+    g = (np.sqrt(5) - 1) / 2
+    for _ in range(200):
+        c, d = b - g * (b - a), a + g * (b - a)
+        if f(c)[0] < f(d)[0]:
+            b = d
+        else:
+            a = c
+    return 0.5 * (a + b)
+
+
+def stereo_rectify_custom(K0, K1, R, T, width, height, angle):
+    """stereoRectifyUndistorted for a GIVEN baseline angle (degrees): H0, H1 and the ROI (x, y, w, h)."""
+    f = _custom_rect_functional(K0, K1, R, T)
+    _, H0, H1 = f(angle)
+    pts = np.array([[0, width, width, 0], [0, 0, height, height], [1, 1, 1, 1]], float)
+
+    def corners(H):
+        q = H @ pts
+        return q[0] / q[2], q[1] / q[2]
+
+    def rect(cx, cy):
+        ax, ay, bx, by = min(cx[0], cx[3]), min(cy[0], cy[1]), max(cx[1], cx[2]), max(cy[2], cy[3])
+        return min(ax, bx), min(ay, by), abs(bx - ax), abs(by - ay)
+    r0, r1 = rect(*corners(H0)), rect(*corners(H1))
+    top, bottom = min(r0[1], r1[1]), max(r0[1] + r0[3], r1[1] + r1[3])
+    out = []
+    for H, r in ((H0, r0), (H1, r1)):
+        Tr = np.array([[1, 0, -r[0]], [0, 1, -top], [0, 0, 1.0]])
+        Sc = np.diag([width / r[2], height / (bottom - top), 1.0])
+        Hn = Sc @ Tr @ H
+        out.append(Hn / np.cbrt(np.linalg.det(Hn)))
+    (x0, y0), (x1, y1) = corners(out[0]), corners(out[1])
+    xs, ys = np.sort(np.concatenate([x0, x1])), np.sort(np.concatenate([y0, y1]))
+    rx, ry = int(xs[3]), int(ys[3])
+    return out[0], out[1], (rx, ry, int(xs[4] - rx), int(ys[4] - ry))
+
+
+def warp_perspective_u8(src, H):
+    """cv::warpPerspective(src, dst, H, src.size()) (INTER_LINEAR, constant 0 border; wass_stereo.cpp:515-516): OpenCV's
+    published algorithm -- M = H^-1, coordinates in double per 128-column block (origin term + M*x1), scaled by 32/W,
+    rounded half to even, 1/32-pixel bilinear weights in 15-bit fixed point -- bit-exact vs cv2 in tests/test_custom_rectify.py."""
+    src = np.asarray(src, np.uint8)
+    sh, sw = src.shape
+    M = np.linalg.inv(np.asarray(H, float))
+    S = np.asarray(H, float).ravel()        # cv::invert's closed form for 3x3
+    d = S[0] * (S[4] * S[8] - S[5] * S[7]) - S[1] * (S[3] * S[8] - S[5] * S[6]) + S[2] * (S[3] * S[7] - S[4] * S[6])
+    idet = 1.0 / d
+    M = np.array([(S[4] * S[8] - S[5] * S[7]) * idet, (S[2] * S[7] - S[1] * S[8]) * idet, (S[1] * S[5] - S[2] * S[4]) * idet,
+                  (S[5] * S[6] - S[3] * S[8]) * idet, (S[0] * S[8] - S[2] * S[6]) * idet, (S[2] * S[3] - S[0] * S[5]) * idet,
+                  (S[3] * S[7] - S[4] * S[6]) * idet, (S[1] * S[6] - S[0] * S[7]) * idet, (S[0] * S[4] - S[1] * S[3]) * idet])
+    bh0 = min(32, sh)
+    bw0 = min(64 * 64 // bh0, sw)
+    xs, ys = np.arange(sw), np.arange(sh)
+    xb = (xs // bw0) * bw0
+    x1 = xs - xb
+    X0 = (M[0] * xb[None, :] + M[1] * ys[:, None]) + M[2]
+    Y0 = (M[3] * xb[None, :] + M[4] * ys[:, None]) + M[5]
+    W0 = (M[6] * xb[None, :] + M[7] * ys[:, None]) + M[8]
+    Wv = W0 + M[6] * x1[None, :]
+    with np.errstate(divide="ignore", invalid="ignore"):
+        Wi = np.where(Wv != 0, 32.0 / Wv, 0.0)
+        fX = np.clip((X0 + M[0] * x1[None, :]) * Wi, -2147483648.0, 2147483647.0)
+        fY = np.clip((Y0 + M[3] * x1[None, :]) * Wi, -2147483648.0, 2147483647.0)
+    X, Y = np.rint(fX).astype(np.int64), np.rint(fY).astype(np.int64)
+    ix, iy = np.clip(X >> 5, -32768, 32767), np.clip(Y >> 5, -32768, 32767)
+    fx, fy = X & 31, Y & 31
+    w = np.stack([(32 - fx) * (32 - fy) * 32, fx * (32 - fy) * 32, (32 - fx) * fy * 32, fx * fy * 32], -1)
+    w[..., 0] = np.minimum(w[..., 0], 32767)
+
+    def px(y, x):
+        ok = (x >= 0) & (x < sw) & (y >= 0) & (y < sh)
+        return np.where(ok, src[np.clip(y, 0, sh - 1), np.clip(x, 0, sw - 1)], 0).astype(np.int64)
+    v = px(iy, ix) * w[..., 0] + px(iy, ix + 1) * w[..., 1] + px(iy + 1, ix) * w[..., 2] + px(iy + 1, ix + 1) * w[..., 3]
+    return np.clip((v + (1 << 14)) >> 15, 0, 255).astype(np.uint8)
+
+
 def dense_input_resize(crop, dense_scale):
     """wass_stereo.cpp:788-797: x only when enlarging, both axes when shrinking."""
     if dense_scale > 1.0:

@@ -51,7 +51,8 @@ class Calib(ctypes.Structure):
                 ("R1", ctypes.c_double * 9), ("R2", ctypes.c_double * 9), ("P1", ctypes.c_double * 12), ("P2", ctypes.c_double * 12),
                 ("roi_left", ctypes.c_int * 4), ("roi_right", ctypes.c_int * 4),
                 ("left_cols", ctypes.c_int), ("left_rows", ctypes.c_int), ("right_cols", ctypes.c_int), ("right_rows", ctypes.c_int),
-                ("rect_cols", ctypes.c_int), ("rect_rows", ctypes.c_int)]
+                ("rect_cols", ctypes.c_int), ("rect_rows", ctypes.c_int),
+                ("use_homographies", ctypes.c_int), ("HLi", ctypes.c_double * 9), ("HRi", ctypes.c_double * 9)]
 
 
 class TriParams(ctypes.Structure):
@@ -71,7 +72,11 @@ class RefineParams(ctypes.Structure):
 def make_calib(c, left_shape, right_shape, rect_shape):
     """dict(K0,K1,R,T,R1,R2,P1,P2,roi_left,roi_right) -> Calib"""
     k = Calib()
-    for name, n in (("K0", 9), ("K1", 9), ("R", 9), ("T", 3), ("R1", 9), ("R2", 9), ("P1", 12), ("P2", 12)):
+    custom = "HLi" in c                      # USE_CUSTOM_STEREORECTIFY: homographies instead of R1,R2,P1,P2
+    k.use_homographies = int(custom)
+    names = (("K0", 9), ("K1", 9), ("R", 9), ("T", 3)) + ((("HLi", 9), ("HRi", 9)) if custom else
+                                                             (("R1", 9), ("R2", 9), ("P1", 12), ("P2", 12)))
+    for name, n in names:
         arr = np.asarray(c[name], np.float64).reshape(-1)
         assert arr.size == n, name
         getattr(k, name)[:] = list(arr)
@@ -150,6 +155,8 @@ def load():
     ip = ctypes.POINTER(ci)
     lib.wsg_stereo_rectify.argtypes = [dp, dp, dp, dp, ci, ci, dp, dp, dp, dp, ip, ip]
     lib.wsg_rectify_image.argtypes = [vp, vp, ci, ci, sz, dp, dp, dp, vp]
+    lib.wsg_stereo_rectify_custom.argtypes = [dp, dp, dp, dp, ctypes.c_double, ci, ci, dp, dp, ip, dp]
+    lib.wsg_warp_perspective.argtypes = [vp, vp, ci, ci, sz, dp, vp]
     lib.wsg_undistort_image.argtypes = [vp, vp, ci, ci, sz, dp, dp, ci, vp]
     lib.wsg_clahe_image.argtypes = [vp, vp, ci, ci, sz, ctypes.c_double, ci, vp]
     lib.wsg_prepare_image.argtypes = [vp, vp, ci, ci, sz, ci, ctypes.c_double, dp, dp, ci, vp]
@@ -210,6 +217,19 @@ def stereo_rectify(K0, K1, R, T, width, height):
         raise WsgError(rc, "wsg_stereo_rectify")
     return dict(R1=np.array(list(R1)).reshape(3, 3), R2=np.array(list(R2)).reshape(3, 3), P1=np.array(list(P1)).reshape(3, 4),
                 P2=np.array(list(P2)).reshape(3, 4), roi1=tuple(r1), roi2=tuple(r2))
+
+
+def stereo_rectify_custom(K0, K1, R, T, width, height, rot_angle=0.0):
+    """stereoRectifyUndistorted (src/wass_stereo/stereorectify.cpp:57-244); R,T take camera-1 points into camera 0
+    (wass_stereo.cpp:502 passes Rinv, Tinv).  Host only.  Returns dict(H0, H1, roi, angle)."""
+    H0, H1 = (ctypes.c_double * 9)(), (ctypes.c_double * 9)()
+    roi = (ctypes.c_int * 4)()
+    ang = ctypes.c_double()
+    rc = load().wsg_stereo_rectify_custom(_darr(K0, 9), _darr(K1, 9), _darr(R, 9), _darr(T, 3), float(rot_angle), width, height,
+                                          H0, H1, roi, ctypes.cast(ctypes.byref(ang), ctypes.POINTER(ctypes.c_double)))
+    if rc:
+        raise WsgError(rc, "wsg_stereo_rectify_custom")
+    return dict(H0=np.array(list(H0)).reshape(3, 3), H1=np.array(list(H1)).reshape(3, 3), roi=tuple(roi), angle=ang.value)
 
 
 def rt_from_plane(plane):
@@ -488,6 +508,14 @@ class Handle:
         self._ck(self.lib.wsg_prepare_image(self.h, img.ctypes.data, H, W, W, int(clahe_tiles), float(clahe_clip), _darr(K, 9),
                                             d.ctypes.data_as(ctypes.POINTER(ctypes.c_double)) if d.size else None, int(d.size),
                                             out.ctypes.data))
+        return out
+
+    def warp_perspective(self, img, H):
+        """cv::warpPerspective(img, H, img.size()) as the custom rectifier applies it (wass_stereo.cpp:515-516)."""
+        img = np.ascontiguousarray(img, np.uint8)
+        rows, cols = img.shape
+        out = np.empty((rows, cols), np.uint8)
+        self._ck(self.lib.wsg_warp_perspective(self.h, img.ctypes.data, rows, cols, cols, _darr(H, 9), out.ctypes.data))
         return out
 
     def rectify_image(self, img, K, Rrect, P):

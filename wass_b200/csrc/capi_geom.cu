@@ -333,6 +333,8 @@ static int triangulate_common(wsg_handle* h, const float* d_disp_full, const uin
     cd.discard_burned = p->DISCARD_BURNED_AREAS; cd.has_lmask = left_mask != nullptr; cd.has_rmask = right_mask != nullptr;
     cd.comp_over_scale = (double)p->disparity_compensation / p->DENSE_SCALE;
     cd.cam_distance = p->cam_distance;
+    cd.use_h = c->use_homographies;
+    memcpy(cd.HLi, c->HLi, 72); memcpy(cd.HRi, c->HRi, 72);
     if (cd.rrx < 0 || cd.rry < 0 || cd.rrw <= 0 || cd.rrh <= 0 || cd.rrx + cd.rrw > cd.rect_cols || cd.rry + cd.rrh > cd.rect_rows) {
         h->err = "roi_right outside the rectified image"; return WSG_ERR_INVALID_ARG;
     }

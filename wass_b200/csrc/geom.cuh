@@ -25,6 +25,8 @@ struct CalibDev {
     int discard_burned, has_lmask, has_rmask;
     double comp_over_scale;   // disparity_compensation / DENSE_SCALE
     double cam_distance;
+    int use_h;                // USE_CUSTOM_STEREORECTIFY: unrectify through HLi / HRi
+    double HLi[9], HRi[9];
 };
 
 // disparity clean-up

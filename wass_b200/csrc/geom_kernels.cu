@@ -153,8 +153,19 @@ __global__ void triangulate_kernel(const float* __restrict__ disparity, const ui
     const float yl = (float)yr;
     if (xl < 0.f || xl >= (float)c.rect_cols) return;
     double pix, piy, qix, qiy;
-    unrectify_dev((double)xl, (double)yl, c.K0, c.R1, c.P1fx, c.P1fy, c.P1cx, c.P1cy, pix, piy);
-    unrectify_dev((double)xr, (double)yr, c.K1, c.R2, c.P2fx, c.P2fy, c.P2cx, c.P2cy, qix, qiy);
+    if (c.use_h) {
+        // wass_stereo.cpp:301-305 : uvr = H^-1 * (u, v, 1) (cv::Matx product: ((0 + a0 u) + a1 v) + a2), then / uvr[2]
+        auto hom = [](const double* Hi, double uu, double vv, double& ox, double& oy) {
+            const double a = Hi[0] * uu + Hi[1] * vv + Hi[2] * 1.0, b = Hi[3] * uu + Hi[4] * vv + Hi[5] * 1.0;
+            const double w = Hi[6] * uu + Hi[7] * vv + Hi[8] * 1.0;
+            ox = a / w; oy = b / w;
+        };
+        hom(c.HLi, (double)xl, (double)yl, pix, piy);
+        hom(c.HRi, (double)xr, (double)yr, qix, qiy);
+    } else {
+        unrectify_dev((double)xl, (double)yl, c.K0, c.R1, c.P1fx, c.P1fy, c.P1cx, c.P1cy, pix, piy);
+        unrectify_dev((double)xr, (double)yr, c.K1, c.R2, c.P2fx, c.P2fy, c.P2cx, c.P2cy, qix, qiy);
+    }
     if (pix < 1 || pix >= c.left_cols - 1 || piy < 1 || piy >= c.left_rows - 1 || qix < 1 || qix >= c.right_cols - 1 ||
         qiy < 1 || qiy >= c.right_rows - 1)
         return;

@@ -81,6 +81,8 @@ struct Env {
     int left_index = 0, right_index = 1;
     double cam_distance = 1.0;
     double R1[9], R2[9], P1r[12], P2r[12];
+    bool custom_rectify = false;                 // USE_CUSTOM_STEREORECTIFY: homographies instead of R1,R2,P1,P2
+    double HL[9], HR[9], HLi[9], HRi[9];
     int roi_left[4], roi_right[4];
     int disparity_compensation = 0;
     void computeP() { P0 = mul(K0, stack_matrices(Rpose0, Tpose0)); P1 = mul(K1, stack_matrices(Rpose1, Tpose1)); }
@@ -208,12 +210,48 @@ bool rectify(Env& env, const Config& cfg, wsg_handle* h)   // wass_stereo.cpp:44
         LOGI << "auto-swapping left-right images" << "\n";
         env.swapLeftRight();
     }
-    if (cfg.getb("USE_CUSTOM_STEREORECTIFY")) {
-        LOGE << "USE_CUSTOM_STEREORECTIFY=true is not supported by this build (see DESIGN.md)";
-        return false;
+    const int W = env.left.cols, H = env.left.rows;
+    auto crop = [&](const Image8& src, const int* r, Image8& dst) {
+        dst.rows = r[3]; dst.cols = r[2]; dst.px.resize((size_t)r[2] * r[3]);
+        for (int y = 0; y < r[3]; ++y) memcpy(&dst.px[(size_t)y * r[2]], &src.px[(size_t)(r[1] + y) * src.cols + r[0]], r[2]);
+    };
+    if (cfg.getb("USE_CUSTOM_STEREORECTIFY")) {          // wass_stereo.cpp:496-529
+        const double baseline_rot = cfg.getd("RECTIFY_ANGLE");
+        LOGI << "Using WASS custom stereorectify, baseline angle delta=" << baseline_rot;
+        int roi[4];
+        double best = 0;
+        if (baseline_rot == 0) std::cout << "Optimizing best rectifying plane... ";
+        if (wsg_stereo_rectify_custom(env.intr_left.v.data(), env.intr_right.v.data(), env.Rinv.v.data(), env.Tinv.v.data(), baseline_rot,
+                                      W, H, env.HL, env.HR, roi, &best) != WSG_OK) { LOGE << "custom stereorectify failed"; return false; }
+        if (baseline_rot == 0) std::cout << "DONE" << std::endl << "Best angle: " << best << " deg." << std::endl;
+        auto inv3 = [](const double* S, double* D) {      // cv::Matx33d::inv()
+            const double d = S[0] * (S[4] * S[8] - S[5] * S[7]) - S[1] * (S[3] * S[8] - S[5] * S[6]) + S[2] * (S[3] * S[7] - S[4] * S[6]);
+            const double id = 1. / d;
+            D[0] = (S[4] * S[8] - S[5] * S[7]) * id; D[1] = (S[2] * S[7] - S[1] * S[8]) * id; D[2] = (S[1] * S[5] - S[2] * S[4]) * id;
+            D[3] = (S[5] * S[6] - S[3] * S[8]) * id; D[4] = (S[0] * S[8] - S[2] * S[6]) * id; D[5] = (S[2] * S[3] - S[0] * S[5]) * id;
+            D[6] = (S[3] * S[7] - S[4] * S[6]) * id; D[7] = (S[1] * S[6] - S[0] * S[7]) * id; D[8] = (S[0] * S[4] - S[1] * S[3]) * id;
+        };
+        inv3(env.HL, env.HLi); inv3(env.HR, env.HRi);
+        env.custom_rectify = true;
+        Mat hl, hr; hl.rows = hl.cols = hr.rows = hr.cols = 3; hl.v.assign(env.HL, env.HL + 9); hr.v.assign(env.HR, env.HR + 9);
+        save_matrix_txt(path(env, env.left_index == 0 ? "H0_rect.txt" : "H1_rect.txt"), hl);
+        save_matrix_txt(path(env, env.left_index == 0 ? "H1_rect.txt" : "H0_rect.txt"), hr);
+        env.left_rect.rows = env.right_rect.rows = H; env.left_rect.cols = env.right_rect.cols = W;
+        env.left_rect.px.resize((size_t)W * H); env.right_rect.px.resize((size_t)W * H);
+        if (wsg_warp_perspective(h, env.left.px.data(), H, W, W, env.HL, env.left_rect.px.data()) != WSG_OK ||
+            wsg_warp_perspective(h, env.right.px.data(), H, W, W, env.HR, env.right_rect.px.data()) != WSG_OK) {
+            LOGE << "warpPerspective failed: " << wsg_last_error(h); return false;
+        }
+        if (cfg.getb("DISABLE_RECTIFY_ROI")) { roi[0] = 0; roi[1] = 0; roi[2] = W; roi[3] = H; }
+        if (roi[0] < 0 || roi[1] < 0 || roi[2] <= 0 || roi[3] <= 0 || roi[0] + roi[2] > W || roi[1] + roi[3] > H) {
+            LOGE << "rectification ROI outside the image"; return false;      // (cv::Mat::operator() throws in the reference)
+        }
+        memcpy(env.roi_left, roi, 16); memcpy(env.roi_right, roi, 16);
+        crop(env.left_rect, env.roi_left, env.left_crop);
+        crop(env.right_rect, env.roi_right, env.right_crop);
+        return true;
     }
     LOGI << "Rectifying via cv::stereoRectify";
-    const int W = env.left.cols, H = env.left.rows;
     int roi_l[4], roi_r[4];
     bool ok = false;
     int guard = 0;
@@ -242,10 +280,6 @@ bool rectify(Env& env, const Config& cfg, wsg_handle* h)   // wass_stereo.cpp:44
         wsg_rectify_image(h, env.right.px.data(), H, W, W, env.intr_right.v.data(), env.R2, env.P2r, env.right_rect.px.data()) != WSG_OK) {
         LOGE << "remap failed: " << wsg_last_error(h); return false;
     }
-    auto crop = [&](const Image8& src, const int* r, Image8& dst) {
-        dst.rows = r[3]; dst.cols = r[2]; dst.px.resize((size_t)r[2] * r[3]);
-        for (int y = 0; y < r[3]; ++y) memcpy(&dst.px[(size_t)y * r[2]], &src.px[(size_t)(r[1] + y) * src.cols + r[0]], r[2]);
-    };
     crop(env.left_rect, env.roi_left, env.left_crop);
     crop(env.right_rect, env.roi_right, env.right_crop);
     LOGI << "rectification map generated. Size: " << env.left_crop.cols << "x" << env.left_crop.rows;
@@ -387,6 +421,9 @@ int main(int argc, char* argv[])
         // ---- triangulation (wass_stereo.cpp:1039-1386)
         LOG_SCOPE("triangulate");
         wsg_calib cal;
+        memset(&cal, 0, sizeof cal);
+        cal.use_homographies = env.custom_rectify ? 1 : 0;
+        memcpy(cal.HLi, env.HLi, 72); memcpy(cal.HRi, env.HRi, 72);
         memcpy(cal.K0, env.intr_left.v.data(), 72); memcpy(cal.K1, env.intr_right.v.data(), 72);
         memcpy(cal.R, env.R.v.data(), 72); memcpy(cal.T, env.T.v.data(), 24);
         memcpy(cal.R1, env.R1, 72); memcpy(cal.R2, env.R2, 72); memcpy(cal.P1, env.P1r, 96); memcpy(cal.P2, env.P2r, 96);

@@ -324,6 +324,138 @@ static bool inv3_cv(const double* S, double* D)
     return true;
 }
 
+// ------------------------------------------------------------------------------------------------
+// stereoRectifyUndistorted (src/wass_stereo/stereorectify.cpp:57-244): host arithmetic in cv::Matx order
+// ------------------------------------------------------------------------------------------------
+static void mm3(const double* A, const double* B, double* C)      // cv::Matx product: s = 0; s += a(i,k) * b(k,j)
+{
+    double t[9];
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) {
+            double s_ = 0;
+            for (int k = 0; k < 3; ++k) s_ += A[i * 3 + k] * B[k * 3 + j];
+            t[i * 3 + j] = s_;
+        }
+    memcpy(C, t, sizeof t);
+}
+static double det3(const double* a)                                // cv::determinant(Matx33d)
+{
+    return a[0] * (a[4] * a[8] - a[7] * a[5]) - a[1] * (a[3] * a[8] - a[6] * a[5]) + a[2] * (a[3] * a[7] - a[6] * a[4]);
+}
+static void scale3(double* a, double f) { for (int i = 0; i < 9; ++i) a[i] *= f; }
+
+struct HFunctional {           // stereorectify.cpp:70-137
+    double K0i[9], K1i[9], Ri[9], Rplane[9], H0[9], H1[9];
+    bool init(const double* K0, const double* K1, const double* R, const double* ep1)
+    {
+        if (!inv3_cv(K0, K0i) || !inv3_cv(K1, K1i)) return false;
+        memcpy(Ri, R, 72);
+        const double n = sqrt(ep1[0] * ep1[0] + ep1[1] * ep1[1] + ep1[2] * ep1[2]);
+        if (!(n > 0)) return false;
+        const double Rv[3] = {ep1[0] / n, ep1[1] / n, ep1[2] / n};
+        double N[3] = {Rv[1] * 0 - Rv[2] * 1, Rv[2] * 0 - Rv[0] * 0, Rv[0] * 1 - Rv[1] * 0};      // Rv x (0,1,0)
+        const double nn = sqrt(N[0] * N[0] + N[1] * N[1] + N[2] * N[2]);
+        if (!(nn > 0)) return false;
+        for (double& v : N) v /= nn;
+        const double Rk[3] = {Rv[1] * N[2] - Rv[2] * N[1], Rv[2] * N[0] - Rv[0] * N[2], Rv[0] * N[1] - Rv[1] * N[0]};
+        const double rp[9] = {Rv[0], Rv[1], Rv[2], Rk[0], Rk[1], Rk[2], N[0], N[1], N[2]};
+        memcpy(Rplane, rp, 72);
+        return true;
+    }
+    double calc(double x)
+    {
+        // cv::Rodrigues of (x/180*3.14, 0, 0) -- 3.14, not pi, as in the reference
+        const double a = x / 180 * 3.14, th = fabs(a);
+        double Radd[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+        if (th >= DBL_EPSILON) {
+            const double c = cos(th), s_ = sin(th), c1 = 1. - c, rx = a * (1. / th);
+            Radd[0] = c + c1 * rx * rx; Radd[4] = c; Radd[5] = -s_ * rx; Radd[7] = s_ * rx; Radd[8] = c;
+        }
+        double RP[9];
+        mm3(Radd, Rplane, RP);
+        mm3(RP, K0i, H0);
+        double RPR[9];
+        mm3(RP, Ri, RPR);
+        mm3(RPR, K1i, H1);
+        scale3(H0, 1.0 / H0[8]);
+        scale3(H1, 1.0 / H1[8]);
+        const double v1 = H0[6] * H0[6] + H0[7] * H0[7], v2 = H1[6] * H1[6] + H1[7] * H1[7];
+        scale3(H0, 1.0 / cbrt(det3(H0)));       // det(H) = 1 for numerical stability
+        scale3(H1, 1.0 / cbrt(det3(H1)));
+        return std::max(v1, v2);
+    }
+};
+
+// Nelder-Mead over (x0, x1) exactly as the reference sets the solver up: start (0,0), initial step (-0.5,-0.5), stop when
+// the simplex has collapsed (function range below 1e-40) or after 500000 evaluations; only x0 enters the functional.
+static double minimise_angle(HFunctional& f)
+{
+    double p[3][2] = {{0, 0}, {-0.5, 0}, {0, -0.5}}, y[3];
+    for (int i = 0; i < 3; ++i) y[i] = f.calc(p[i][0]);
+    int nfunk = 3;
+    auto try_move = [&](int ihi, double fac, double& ynew, double pnew[2]) {
+        const double fac1 = (1.0 - fac) / 2, fac2 = fac1 - fac;
+        for (int j = 0; j < 2; ++j) pnew[j] = (p[0][j] + p[1][j] + p[2][j]) * fac1 - p[ihi][j] * fac2;
+        ynew = f.calc(pnew[0]);
+        ++nfunk;
+    };
+    while (nfunk < 500000) {
+        int ilo = 0, ihi = 0, inhi = 0;
+        for (int i = 1; i < 3; ++i) { if (y[i] < y[ilo]) ilo = i; if (y[i] > y[ihi]) ihi = i; }
+        inhi = ilo;
+        for (int i = 0; i < 3; ++i) if (i != ihi && y[i] >= y[inhi]) inhi = i;
+        double ext = 0;
+        for (int i = 0; i < 3; ++i) ext = std::max(ext, fabs(p[i][0] - p[ilo][0]));
+        if (fabs(y[ihi] - y[ilo]) < 1e-40 && ext < 1e-13) break;
+        double yt, pt[2];
+        try_move(ihi, -1.0, yt, pt);                                   // reflection
+        if (yt < y[ihi]) { y[ihi] = yt; p[ihi][0] = pt[0]; p[ihi][1] = pt[1]; }
+        if (yt <= y[ilo]) {
+            double y2, p2[2];
+            try_move(ihi, 2.0, y2, p2);                                // expansion
+            if (y2 < y[ihi]) { y[ihi] = y2; p[ihi][0] = p2[0]; p[ihi][1] = p2[1]; }
+        } else if (yt >= y[inhi]) {
+            const double ysave = y[ihi];
+            double y2, p2[2];
+            try_move(ihi, 0.5, y2, p2);                                // contraction
+            if (y2 < y[ihi]) { y[ihi] = y2; p[ihi][0] = p2[0]; p[ihi][1] = p2[1]; }
+            if (y2 >= ysave) {                                         // shrink towards the best vertex
+                for (int i = 0; i < 3; ++i)
+                    if (i != ilo) {
+                        for (int j = 0; j < 2; ++j) p[i][j] = 0.5 * (p[i][j] + p[ilo][j]);
+                        y[i] = f.calc(p[i][0]);
+                        ++nfunk;
+                    }
+            }
+        }
+    }
+    int ilo = 0;
+    for (int i = 1; i < 3; ++i) if (y[i] < y[ilo]) ilo = i;
+    return p[ilo][0];
+}
+
+// cv::warpPerspective's coordinate map (INTER_LINEAR): M = H^-1, 32-row x 128-column blocks (X0 from the block origin,
+// then + M0 * x1), 32/W scaling, clamp to the int range, round half to even, saturate_cast<short> of the integer part.
+__global__ void warp_map_kernel(int rows, int cols, int bw, const double* __restrict__ Mg, int2* __restrict__ map)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= cols) return;
+    double M[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) M[i] = Mg[i];
+    const int xb = x / bw * bw, x1 = x - xb;
+    const double X0 = __dadd_rn(__dadd_rn(__dmul_rn(M[0], (double)xb), __dmul_rn(M[1], (double)y)), M[2]);
+    const double Y0 = __dadd_rn(__dadd_rn(__dmul_rn(M[3], (double)xb), __dmul_rn(M[4], (double)y)), M[5]);
+    const double W0 = __dadd_rn(__dadd_rn(__dmul_rn(M[6], (double)xb), __dmul_rn(M[7], (double)y)), M[8]);
+    double W = __dadd_rn(W0, __dmul_rn(M[6], (double)x1));
+    W = W != 0. ? __ddiv_rn(32.0, W) : 0.;
+    const double fX = fmax(-2147483648.0, fmin(2147483647.0, __dmul_rn(__dadd_rn(X0, __dmul_rn(M[0], (double)x1)), W)));
+    const double fY = fmax(-2147483648.0, fmin(2147483647.0, __dmul_rn(__dadd_rn(Y0, __dmul_rn(M[3], (double)x1)), W)));
+    const int X = __double2int_rn(fX), Y = __double2int_rn(fY);
+    auto sat = [](int v) { const int i = min(max(v >> 5, -32768), 32767); return (i << 5) | (v & 31); };
+    map[(size_t)y * cols + x] = make_int2(sat(X), sat(Y));
+}
+
 // cv::undistort on device buffers: d_src -> d_dst (both rows x cols, tight)
 static int undistort_device(wsg_handle* h, const uint8_t* d_src, uint8_t* d_dst, int rows, int cols, const double K[9],
                             const double* dist, int ndist)
@@ -448,6 +580,84 @@ static int clahe_device(wsg_handle* h, const uint8_t* d_src, uint8_t* d_dst, int
     clahe_apply_kernel<<<g, b, 0, h->stream>>>(d_src, rows, cols, tiles, tiles, 1.f / (float)tw, 1.f / (float)th,
                                                (const uint8_t*)h->rs_tab.p, d_dst);
     CK(h, cudaGetLastError());
+    return WSG_OK;
+}
+
+int wsg_stereo_rectify_custom(const double K0[9], const double K1[9], const double R[9], const double T[3], double rot_angle,
+                              int width, int height, double H0[9], double H1[9], int roi[4], double* best_angle)
+{
+    if (!K0 || !K1 || !R || !T || !H0 || !H1 || !roi || width <= 0 || height <= 0) return WSG_ERR_INVALID_ARG;
+    HFunctional hf;
+    if (!hf.init(K0, K1, R, T)) return WSG_ERR_INVALID_ARG;
+    double angle = rot_angle;
+    if (rot_angle == 0) angle = minimise_angle(hf);
+    hf.calc(angle);
+    if (best_angle) *best_angle = angle;
+    memcpy(H0, hf.H0, 72); memcpy(H1, hf.H1, 72);
+    // the image corners through both homographies (stereorectify.cpp:168-190)
+    const double px[4] = {0, (double)width, (double)width, 0}, py[4] = {0, 0, (double)height, (double)height};
+    auto corners = [&](const double* H, double* cx, double* cy) {
+        for (int i = 0; i < 4; ++i) {
+            const double a = H[0] * px[i] + H[1] * py[i] + H[2] * 1., b = H[3] * px[i] + H[4] * py[i] + H[5] * 1.;
+            const double w = H[6] * px[i] + H[7] * py[i] + H[8] * 1.;
+            cx[i] = a / w; cy[i] = b / w;
+        }
+    };
+    struct RectD { double x, y, w, h; };
+    auto rect_of = [](const double* cx, const double* cy) {     // cv::Rect_<double>(pt1, pt2)
+        const double ax = std::min(cx[0], cx[3]), ay = std::min(cy[0], cy[1]), bx = std::max(cx[1], cx[2]), by = std::max(cy[2], cy[3]);
+        RectD r; r.x = std::min(ax, bx); r.y = std::min(ay, by); r.w = std::max(ax, bx) - r.x; r.h = std::max(ay, by) - r.y;
+        return r;
+    };
+    double c0x[4], c0y[4], c1x[4], c1y[4];
+    corners(H0, c0x, c0y); corners(H1, c1x, c1y);
+    const RectD r0 = rect_of(c0x, c0y), r1 = rect_of(c1x, c1y);
+    const double top = std::min(r0.y, r1.y), bottom = std::max(r0.y + r0.h, r1.y + r1.h);
+    auto finish = [&](double* H, const RectD& r) {
+        const double Tr[9] = {1, 0, -r.x, 0, 1, -top, 0, 0, 1};
+        const double Sc[9] = {width / r.w, 0, 0, 0, height / (bottom - top), 0, 0, 0, 1};
+        double ST[9];
+        mm3(Sc, Tr, ST);
+        mm3(ST, H, H);
+        scale3(H, 1.0 / cbrt(det3(H)));
+    };
+    finish(H0, r0); finish(H1, r1);
+    // the ROI: 4th and 5th of the eight sorted corner coordinates (stereorectify.cpp:215-243), truncated to int as cv::Rect
+    corners(H0, c0x, c0y); corners(H1, c1x, c1y);
+    double xs[8], ys[8];
+    for (int i = 0; i < 4; ++i) { xs[2 * i] = c0x[i]; ys[2 * i] = c0y[i]; xs[2 * i + 1] = c1x[i]; ys[2 * i + 1] = c1y[i]; }
+    std::sort(xs, xs + 8); std::sort(ys, ys + 8);
+    for (int i = 0; i < 8; ++i) if (!std::isfinite(xs[i]) || !std::isfinite(ys[i])) return WSG_ERR_INVALID_ARG;
+    roi[0] = (int)xs[3]; roi[1] = (int)ys[3];
+    roi[2] = (int)(xs[4] - roi[0]); roi[3] = (int)(ys[4] - roi[1]);
+    return WSG_OK;
+}
+
+int wsg_warp_perspective(wsg_handle* h, const uint8_t* img, int rows, int cols, size_t stride, const double H[9], uint8_t* out)
+{
+    if (!h) return WSG_ERR_INVALID_ARG;
+    if (!img || !H || !out || rows <= 0 || cols <= 0 || stride < (size_t)cols) { h->err = "bad argument"; return WSG_ERR_INVALID_ARG; }
+    double M[9];
+    if (!inv3_cv(H, M)) { h->err = "singular homography"; return WSG_ERR_INVALID_ARG; }
+    CK(h, cudaSetDevice(h->device));
+    const size_t n = (size_t)rows * cols;
+    int rc;
+    if ((rc = ensure(h, h->im_left, n))) return rc;
+    if ((rc = ensure(h, h->im_right, n))) return rc;
+    if ((rc = ensure(h, h->m_scratch, n * sizeof(int2) + 128))) return rc;
+    int2* d_map = (int2*)h->m_scratch.p;
+    double* d_M = (double*)((char*)h->m_scratch.p + n * sizeof(int2));
+    CK(h, cudaMemcpyAsync(d_M, M, 72, cudaMemcpyHostToDevice, h->stream));
+    CK(h, cudaStreamSynchronize(h->stream));        // M is on the stack
+    CK(h, cudaMemcpy2DAsync(h->im_left.p, cols, img, stride, cols, rows, cudaMemcpyHostToDevice, h->stream));
+    // OpenCV's block width: bh0 = min(32, rows); bw0 = min(4096 / bh0, cols)
+    const int bh0 = std::min(32, rows), bw0 = std::min(64 * 64 / bh0, cols);
+    dim3 b(128), g((cols + 127) / 128, rows);
+    warp_map_kernel<<<g, b, 0, h->stream>>>(rows, cols, bw0, d_M, d_map);
+    undistort_remap_kernel<<<g, b, 0, h->stream>>>((const uint8_t*)h->im_left.p, rows, cols, cols, d_map, (uint8_t*)h->im_right.p);
+    CK(h, cudaGetLastError());
+    CK(h, cudaMemcpyAsync(out, h->im_right.p, n, cudaMemcpyDeviceToHost, h->stream));
+    CK(h, cudaStreamSynchronize(h->stream));
     return WSG_OK;
 }
 
