@@ -485,7 +485,7 @@ int wsg_mesh_biggest_component(wsg_handle* h, double zgap, unsigned long long* n
     if ((rc = ensure(h, h->m_labels, n * 4))) return rc;
     if ((rc = ensure(h, h->m_scratch, 64 + n * 4))) return rc;
     unsigned long long left = 0;
-    StageTimer t(h, WSG_STAGE_MESH, 5);
+    StageTimer t(h, WSG_STAGE_MESH, 7);
     if (mesh_biggest_component(mesh_view(h), zgap, (int*)h->m_labels.p, (unsigned long long*)h->m_scratch.p, &left, h->stream)) {
         h->err = "connected components failed"; return WSG_ERR_CUDA;
     }

@@ -392,12 +392,15 @@ __device__ __forceinline__ void uf_union(int* L, int a, int b)
         b = old;
     }
 }
+// Labels are ROW-MAJOR point indices (coalesced with the mesh arrays; the first version indexed them column-major to get
+// the reference's tie rule for free and paid for it with one 32-byte sector per label access).  The tie rule -- among
+// components of equal size the reference keeps the one its column-major seed scan meets first, i.e. the one owning the
+// smallest column-major index -- is restored by a tie-break pass that only does work when two roots share the maximum.
 __global__ void ccl_init_kernel(MeshView m, int* L)
 {
-    const int u = blockIdx.x * blockDim.x + threadIdx.x, v = blockIdx.y;
-    if (u >= m.w) return;
-    const int id = u * m.h + v;
-    L[id] = m.valid[(size_t)v * m.w + u] ? id : INT_MAX;
+    const size_t o = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (o >= (size_t)m.w * m.h) return;
+    L[o] = m.valid[o] ? (int)o : INT_MAX;
 }
 __global__ void ccl_merge_kernel(MeshView m, int* L, double zgap)
 {
@@ -406,52 +409,73 @@ __global__ void ccl_merge_kernel(MeshView m, int* L, double zgap)
     const size_t o = (size_t)v * m.w + u;
     if (!m.valid[o]) return;
     const double z = m.Z[o];
-    const int id = u * m.h + v;
-    if (u + 1 < m.w && m.valid[o + 1] && fabs(z - m.Z[o + 1]) < zgap) uf_union(L, id, id + m.h);
-    if (v + 1 < m.h && m.valid[o + m.w] && fabs(z - m.Z[o + m.w]) < zgap) uf_union(L, id, id + 1);
+    if (u + 1 < m.w && m.valid[o + 1] && fabs(z - m.Z[o + 1]) < zgap) uf_union(L, (int)o, (int)o + 1);
+    if (v + 1 < m.h && m.valid[o + m.w] && fabs(z - m.Z[o + m.w]) < zgap) uf_union(L, (int)o, (int)o + m.w);
 }
 __global__ void ccl_flatten_count_kernel(MeshView m, int* L, unsigned* cnt)
 {
-    const int u = blockIdx.x * blockDim.x + threadIdx.x, v = blockIdx.y;
-    if (u >= m.w) return;
-    const int id = u * m.h + v;
-    if (L[id] == INT_MAX) return;
-    const int r = uf_find(L, id);
-    L[id] = r;
+    const size_t o = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (o >= (size_t)m.w * m.h || L[o] == INT_MAX) return;
+    const int r = uf_find(L, (int)o);
+    L[o] = r;
     // nearly every point belongs to one component: count equal roots inside the warp first
     const unsigned act = __activemask();
     const unsigned peers = __match_any_sync(act, r);
     if ((threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&cnt[r], (unsigned)__popc(peers));
 }
-__global__ void ccl_best_kernel(const unsigned* cnt, int n, unsigned long long* best)
+// best[0] = max count; best[1] = number of roots with that count; best[2] = smallest such root (row-major);
+// best[3] = min over the tied components of (smallest column-major member index << 32 | root), filled only on a tie
+__global__ void ccl_max_kernel(const unsigned* cnt, int n, unsigned long long* best)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n || cnt[i] == 0) return;
-    atomicMax(best, ((unsigned long long)cnt[i] << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)i));
+    unsigned c = i < n ? cnt[i] : 0;
+    const unsigned wmax = __reduce_max_sync(0xffffffffu, c);
+    if (wmax && c == wmax && (threadIdx.x & 31) == __ffs(__ballot_sync(0xffffffffu, c == wmax)) - 1) atomicMax(best, (unsigned long long)wmax);
+}
+__global__ void ccl_ties_kernel(const unsigned* cnt, int n, unsigned long long* best)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n || cnt[i] == 0 || cnt[i] != (unsigned)best[0]) return;
+    atomicAdd(best + 1, 1ull);
+    atomicMin(best + 2, (unsigned long long)i);
+}
+__global__ void ccl_tiebreak_kernel(MeshView m, const int* L, const unsigned* cnt, unsigned long long* best)
+{
+    if (best[1] <= 1) return;                        // the usual case: one biggest component, nothing to decide
+    const int u = blockIdx.x * blockDim.x + threadIdx.x, v = blockIdx.y;
+    if (u >= m.w) return;
+    const size_t o = (size_t)v * m.w + u;
+    const int r = L[o];
+    if (r == INT_MAX || cnt[r] != (unsigned)best[0]) return;
+    atomicMin(best + 3, ((unsigned long long)((unsigned)u * (unsigned)m.h + (unsigned)v) << 32) | (unsigned)r);
 }
 __global__ void ccl_extract_kernel(MeshView m, const int* L, const unsigned long long* best)
 {
-    const int u = blockIdx.x * blockDim.x + threadIdx.x, v = blockIdx.y;
-    if (u >= m.w) return;
-    const int lab = (int)(0xFFFFFFFFu - (unsigned)(*best & 0xFFFFFFFFull));
-    const size_t o = (size_t)v * m.w + u;
-    if (m.valid[o] && L[u * m.h + v] != lab) m.valid[o] = 0;
+    const size_t o = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (o >= (size_t)m.w * m.h) return;
+    const int lab = best[1] <= 1 ? (int)best[2] : (int)(best[3] & 0xFFFFFFFFull);
+    if (m.valid[o] && L[o] != lab) m.valid[o] = 0;
 }
 int mesh_biggest_component(MeshView m, double zgap, int* labels, unsigned long long* scratch, unsigned long long* n_left_host, cudaStream_t st)
 {
     const int n = m.w * m.h;
-    unsigned* cnt = (unsigned*)(scratch + 2);
-    cudaMemsetAsync(scratch, 0, 16 + (size_t)n * sizeof(unsigned), st);
+    unsigned long long* best = scratch;                // 4 words, then the per-root counts
+    unsigned* cnt = (unsigned*)(scratch + 4);
+    cudaMemsetAsync(scratch, 0, 32 + (size_t)n * sizeof(unsigned), st);
+    cudaMemsetAsync(scratch + 2, 0xff, 16, st);        // the two minima start at the maximum
     dim3 b(128), g((m.w + 127) / 128, m.h);
-    ccl_init_kernel<<<g, b, 0, st>>>(m, labels);
+    const int nb = (n + 255) / 256;
+    ccl_init_kernel<<<nb, 256, 0, st>>>(m, labels);
     ccl_merge_kernel<<<g, b, 0, st>>>(m, labels, zgap);
-    ccl_flatten_count_kernel<<<g, b, 0, st>>>(m, labels, cnt);
-    ccl_best_kernel<<<(n + 255) / 256, 256, 0, st>>>(cnt, n, scratch);
-    ccl_extract_kernel<<<g, b, 0, st>>>(m, labels, scratch);
-    unsigned long long best = 0;
-    cudaMemcpyAsync(&best, scratch, 8, cudaMemcpyDeviceToHost, st);
+    ccl_flatten_count_kernel<<<nb, 256, 0, st>>>(m, labels, cnt);
+    ccl_max_kernel<<<nb, 256, 0, st>>>(cnt, n, best);
+    ccl_ties_kernel<<<nb, 256, 0, st>>>(cnt, n, best);
+    ccl_tiebreak_kernel<<<g, b, 0, st>>>(m, labels, cnt, best);
+    ccl_extract_kernel<<<nb, 256, 0, st>>>(m, labels, best);
+    unsigned long long cntmax = 0;
+    cudaMemcpyAsync(&cntmax, best, 8, cudaMemcpyDeviceToHost, st);
     if (cudaStreamSynchronize(st) != cudaSuccess) return -1;
-    *n_left_host = best >> 32;
+    *n_left_host = cntmax;
     return 0;
 }
 
