@@ -26,7 +26,8 @@
 
 namespace wsg {
 
-static constexpr int SW_R = 8;             // rows (compute warps) per CTA
+static constexpr int SW_R = 7;             // rows (compute warps) per CTA: with the helper warp 8 warps, two per scheduler
+                                           // (both sweeps, B200: R=4 10.1, 5 9.9, 6 9.0, 7 8.36, 8 8.58, 10 9.4, 12 9.9, 16 11.7 ms)
 static constexpr int SW_THREADS = (SW_R + 1) * 32;
 static constexpr unsigned TAGBITS = 0x80008000u;
 static constexpr int SPIN_LIMIT = 1 << 22;
