@@ -251,7 +251,15 @@ def run_ours(args, rank, world):
     hs[0].profile_enable(False)
     stats = hs[0].sgbm_stats()
 
-    # ---- device-resident throughput ("value"): `depth` frames in flight on as many streams
+    # ---- device-resident throughput ("value"): `depth` frames in flight on as many streams.  With three or more in
+    #      flight each sweep is confined to half the SMs (wsg_sgbm_set_sweep_workers): a wavefront over H/7 row bands
+    #      leaves ~40 % of 148 workers waiting, so two frames' sweeps side by side move more pixels than one after the other.
+    nsm = torch.cuda.get_device_properties(local).multi_processor_count
+    workers = args.sweep_workers if args.sweep_workers >= 0 else (nsm // 2 if depth >= 3 else 0)
+    for h in hs:
+        h.sgbm_set_sweep_workers(workers)
+    for i in range(depth):
+        step_dev(i)
     ms_dev = timed_device(args.steps, depth)
 
     # ---- end to end through the C ABI with HOST buffers (pinned): H2D + kernels + D2H per step, one host thread per
@@ -311,6 +319,7 @@ def run_ours(args, rank, world):
             "warmup": max(args.warmup, 3), "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "s16", "data": "synthetic",
             "config": {"workload": WORKLOAD, "frames_per_step_per_gpu": 1, "frames_in_flight_per_gpu": depth,
+                       "sms_per_sweep_when_pipelined": workers if workers > 0 else nsm,
                        "single_frame_ms": ms_serial / args.steps, "padded_width": Wp, "W1": stats["width1"],
                        "l2": "inputs larger than L2 (C and S volumes %.2f GB each)" % (V / 1e9),
                        "parallelism": "frame-per-GPU x%d" % world, "device_vs_e2e_bit_exact": same,
@@ -347,8 +356,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--pipeline-depth", type=int, default=2,
-                    help="frames in flight per GPU (one handle + stream each); 1 = strictly one frame at a time")
+    ap.add_argument("--pipeline-depth", type=int, default=3,
+                    help="frames in flight per GPU (one handle + stream each); 1 = one frame at a time")
+    ap.add_argument("--sweep-workers", type=int, default=-1,
+                    help="SMs per fused sweep while frames are pipelined (0 = all; -1 = half the SMs when 3+ frames are in flight)")
     ap.add_argument("--agg-impl", type=int, default=-1, choices=[-1, 0, 1, 2, 3, 4],
                     help="-1 library default, 0 per-direction launches, 1 fused sweeps, 2 fused sweeps + fused WTA, "
                          "3 three-direction sweeps + anti-diagonal launches + fused WTA")

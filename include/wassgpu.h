@@ -105,6 +105,11 @@ int wsg_sgbm_debug_volumes(wsg_handle* h, int16_t* C_host, int16_t* S_host);
 #define WSG_AGG_SWEEPS3_WTA 3
 #define WSG_AGG_SWEEPS2W_WTA 4
 int wsg_sgbm_set_impl(wsg_handle* h, int impl);
+/* Caps the number of SMs the fused sweeps of this handle occupy (0 = all, the default).  A sweep is a wavefront over
+ * H/7 row bands and cannot keep every SM busy, so with three or more frames in flight on one GPU (one handle and stream
+ * each) half the SMs per sweep gives the higher throughput -- two frames' sweeps run side by side -- at the price of a
+ * longer single-frame latency (B200, 2448x2048x256: 11.0 -> 14.8 ms per frame alone, 610 -> 649 Mdisp/s pipelined). */
+int wsg_sgbm_set_sweep_workers(wsg_handle* h, int max_sms);
 
 /* ---- dense stereo stage as a whole ------------------------------------------------------------ */
 /* Replaces sgbm_dense_stereo(env), wass_stereo.cpp:764-1020, between the two rectified crops and the

@@ -115,6 +115,7 @@ def load():
     lib.wsg_sgbm_compute_device.argtypes = [vp, vp, vp, ci, ci, sz, ctypes.POINTER(SgbmParams), vp]
     lib.wsg_sgbm_get_stats.argtypes = [vp, ctypes.POINTER(SgbmStats)]
     lib.wsg_sgbm_debug_volumes.argtypes = [vp, vp, vp]
+    lib.wsg_sgbm_set_sweep_workers.argtypes = [vp, ci]
     lib.wsg_sgbm_set_impl.argtypes = [vp, ci]
     lib.wsg_profile_enable.argtypes = [vp, ci]
     lib.wsg_profile_reset.argtypes = [vp]
@@ -314,6 +315,10 @@ class Handle:
         S = np.empty((rows, w1, D), np.int16) if want_S else None
         self._ck(self.lib.wsg_sgbm_debug_volumes(self.h, C.ctypes.data, S.ctypes.data if want_S else None))
         return C, S
+
+    def sgbm_set_sweep_workers(self, max_sms):
+        """Cap on the SMs the fused sweeps occupy (0 = all): use ~half with three or more frames in flight per GPU."""
+        self._ck(self.lib.wsg_sgbm_set_sweep_workers(self.h, int(max_sms)))
 
     def sgbm_set_impl(self, impl):
         """AGG_PER_DIRECTION | AGG_SWEEPS | AGG_SWEEPS_WTA (default): same results, different HBM traffic."""

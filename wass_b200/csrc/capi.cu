@@ -176,6 +176,7 @@ int wsg_run_sgbm(wsg_handle* h, const uint8_t* d_img1, const uint8_t* d_img2, si
         SweepScratch sc;
         sc.boundary = h->bnd.p;
         sc.two_warps = impl == WSG_AGG_SWEEPS2W_WTA;
+        sc.max_workers = h->sweep_workers;
         sc.maxC = (const int*)h->scalars.p;
         sc.err = (int*)h->scalars.p + 1;
         sc.dbg = nullptr;
@@ -311,6 +312,14 @@ int wsg_sgbm_debug_volumes(wsg_handle* h, int16_t* C_host, int16_t* S_host)
                 for (int i = 0; i < 8; ++i)     // undo the in-vector interleave (vec_pos)
                     dst[px * pl.D + (size_t)j * 8 + i] = tmp[px * pl.Dp + (size_t)vec_slot(j, pl.NL, pl.K) * 8 + vec_pos(i)];
     }
+    return WSG_OK;
+}
+
+int wsg_sgbm_set_sweep_workers(wsg_handle* h, int max_sms)
+{
+    if (!h) return WSG_ERR_INVALID_ARG;
+    if (max_sms < 0) { h->err = "max_sms must be >= 0"; return WSG_ERR_INVALID_ARG; }
+    h->sweep_workers = max_sms;
     return WSG_OK;
 }
 

@@ -28,6 +28,7 @@ struct wsg_handle {
     DevBuf bnd, keys, d1, dbg;               // fused sweeps: band hand-off buffer, right-view keys, left-view map
     int agg_impl = WSG_AGG_SWEEPS_WTA;
     int num_sms = 0;
+    int sweep_workers = 0;              // cap on the SMs a sweep occupies (0 = all)
     int sweep_epoch = 0;                // 1..3 after the first sweep
     int bnd_H = 0, bnd_W1 = 0, bnd_K = 0, bnd_nd = 0;   // geometry / state set the hand-off buffer was last used with
     SgbmPlan plan{};

@@ -51,6 +51,7 @@ static constexpr int WSG_SWEEP_TICKET_INTS = 256;
 struct SweepScratch {
     void* boundary;             // band-to-band state hand-off, sweep_boundary_bytes()
     int* ticket;                // zeroed hand-out counters of THIS launch: WSG_SWEEP_TICKET_INTS ints
+    int max_workers = 0;        // cap on the SMs a sweep occupies (0 = all)
     int num_sms;
     const int* maxC;            // device scalar: max over the cost volume of this frame
     int* err;                   // raised if a bounded wait overran

@@ -78,8 +78,9 @@ struct SweepArgs {
     unsigned one;            // 1 (kept opaque to the compiler: see add_on_fma)
     unsigned tag;            // epoch tag of this launch (bits 15 and 31)
     uint4* bnd;              // [nbands-1][W1][3][K][32]
-    int* ticket;             // [0] bands handed out, [2..] CTAs of this launch arrived per SM
+    int* ticket;             // [0] bands handed out, [1] workers elected, [2..] CTAs of this launch arrived per SM
     int num_sms;
+    int max_workers;         // at most this many SMs work on the sweep (the others stay free for another frame's kernels)
     int* err;
     int* dbg;                // optional: SM id of every band (placement diagnostics), or null
     // winner-take-all (MODE 2)
@@ -666,6 +667,9 @@ sweep_kernel(const uint4* __restrict__ C, uint4* __restrict__ S, SweepArgs a)
         unsigned sm;
         asm volatile("mov.u32 %0, %%smid;" : "=r"(sm));
         s_band = atomicAdd(a.ticket + 2 + min(sm, 250u), 1) == 0 ? 0 : -1;
+        // A wavefront of H/7 bands cannot keep every SM busy (the skew between bands leaves ~40 % of the workers waiting at
+        // any time), so the number of workers may be capped: the SMs given back run the sweep of another frame.
+        if (s_band == 0 && atomicAdd(a.ticket + 1, 1) >= a.max_workers) s_band = -1;
     }
     __syncthreads();
     if (s_band < 0) return;
@@ -737,7 +741,8 @@ static void launch_sweep_c(const int16_t* C, int16_t* S, const SweepArgs& a, cud
         cudaGetLastError();      // cluster launch not possible here: fall through to the plain launch
     }
     // enough CTAs for every SM to see one even when other kernels hold slots; all but one per SM exit immediately
-    const int grid = Cfg::CTAS_PER_SM * a.num_sms;
+    // (one CTA per SM by shared-memory size: launching max_workers CTAs puts them on that many different SMs)
+    const int grid = Cfg::CTAS_PER_SM == 1 ? std::min(a.max_workers, a.num_sms) : Cfg::CTAS_PER_SM * a.num_sms;
     kern<<<grid, SW_THREADS, Cfg::SMEM, st>>>(c, s, a);
 }
 
@@ -1139,6 +1144,9 @@ void launch_sweep(const int16_t* C, int16_t* S, int flip, int mode, int ndir, co
     a.bnd = reinterpret_cast<uint4*>(sc.boundary);
     a.ticket = sc.ticket; a.err = sc.err; a.dbg = sc.dbg;
     a.num_sms = sc.num_sms;
+    static int workers = -1;
+    if (workers < 0) { const char* e = getenv("WSG_SWEEP_WORKERS"); workers = e ? atoi(e) : 0; }
+    a.max_workers = workers > 0 ? workers : (sc.max_workers > 0 ? sc.max_workers : sc.num_sms);
     a.keys = sc.keys; a.d1 = sc.d1;
     a.minD = p.minD; a.minX1 = p.minX1; a.uniq = p.uniq; a.INVALID = p.INVALID;
     a.umagic = p.uniq < 99 ? (unsigned)((0x100000000ull + (100 - p.uniq) - 1) / (unsigned)(100 - p.uniq)) : 0u;
