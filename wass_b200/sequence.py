@@ -90,7 +90,8 @@ def run_sequence(frames, calib, dense, device=0, rank=0, world=1, dist=None, han
 
     handle: one capi.Handle or a list of them.  With a list of k handles, k frames are in flight on this GPU, one host
     thread and one stream each (the C calls release the GIL): the aggregation sweeps are latency-bound (DESIGN.md section
-    4), so a second frame's kernels fill the SMs' idle issue slots.  Frame i gets seed i either way, so the planes do not
+    4), so a second frame's kernels fill the SMs' idle issue slots (with three or more handles, cap each one's sweeps at
+    half the SMs first: h.sgbm_set_sweep_workers).  Frame i gets seed i either way, so the planes do not
     depend on k.  xyzc_out: a reusable buffer, or a list with one per handle.  Without `handle` one is created and
     destroyed here (the arena is several GB: keep one across calls when processing more than one sequence)."""
     from . import launcher
