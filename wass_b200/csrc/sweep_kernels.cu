@@ -81,6 +81,7 @@ struct SweepArgs {
     int* ticket;             // [0] bands handed out, [1] workers elected, [2..] CTAs of this launch arrived per SM
     int num_sms;
     int max_workers;         // at most this many SMs work on the sweep (the others stay free for another frame's kernels)
+    int eager;               // polls of a progress counter before the waiter starts to sleep between polls
     int* err;
     int* dbg;                // optional: SM id of every band (placement diagnostics), or null
     // winner-take-all (MODE 2)
@@ -410,7 +411,7 @@ __device__ __forceinline__ void sweep_row(const uint4* __restrict__ C, uint4* __
                 // one extra column written by the producer): L = 0 for an out-of-image predecessor
                 // NDIR 4 needs column x+1 of the row above (skew 2), NDIR 3 only column x (skew 1)
                 if (use_mbar) wait_col(bars_in, x + NQ - 2, dead, a.err);
-                else wait_prog(prog_in, x + NQ - 1, seen_in, a.err);
+                else wait_prog(prog_in, x + NQ - 1, seen_in, a.err, a.eager);
                 const int sl[3] = {(x + NS - 1) % NS, x % NS, (x + 1) % NS};
 #pragma unroll
                 for (int q = 0; q < NQ; ++q) {
@@ -428,7 +429,7 @@ __device__ __forceinline__ void sweep_row(const uint4* __restrict__ C, uint4* __
             for (int q = 0; q < NQ; ++q) agg_step<32, NR, HASPAD, FAST>(Nd[q], Cc, v[q], l, a.P1p, a.P2mP1p, padm, one);
             // ---- hand the new states down
             if (out_mode == 1) {
-                wait_prog(prog_next, x - NS + 2, seen_next, a.err);
+                wait_prog(prog_next, x - NS + 2, seen_next, a.err, a.eager);
                 uint4* dst = ring_out + (x % NS) * Cfg::SLOT_V;
 #pragma unroll
                 for (int q = 0; q < NQ; ++q)
@@ -510,7 +511,7 @@ __device__ __forceinline__ void sweep_row(const uint4* __restrict__ C, uint4* __
     }
     if (NDIR >= 3 && out_mode == 1) {
         // the extra zero column (see above)
-        wait_prog(prog_next, a.W1 - NS + 2, seen_next, a.err);
+        wait_prog(prog_next, a.W1 - NS + 2, seen_next, a.err, a.eager);
 #pragma unroll
         for (int j = 0; j < 3 * K; ++j) ring_out[(a.W1 % NS) * Cfg::SLOT_V + j * 32] = make_uint4(0, 0, 0, 0);
         __syncwarp();
@@ -582,7 +583,7 @@ __device__ __forceinline__ void sweep_helper(const SweepArgs& a, uint4* smem, vo
             }
             spins = 0;
             // ring 0 slot c is free once warp 0 has completed column c-NS+1
-            wait_prog(&prog[1], x + n - 1 - NS + 2, seen, a.err);
+            wait_prog(&prog[1], x + n - 1 - NS + 2, seen, a.err, a.eager);
 #pragma unroll
             for (int u = 0; u < Cfg::HD; ++u) {
                 if (u < n) {
@@ -600,7 +601,7 @@ __device__ __forceinline__ void sweep_helper(const SweepArgs& a, uint4* smem, vo
             if (l == 0) prog[0] = x;
         }
         // one more column of zeros: the out-of-image predecessor of the last pixel's (x+1,y-1) path
-        wait_prog(&prog[1], a.W1 - NS + 2, seen, a.err);
+        wait_prog(&prog[1], a.W1 - NS + 2, seen, a.err, a.eager);
 #pragma unroll
         for (int j = 0; j < NQ * K; ++j) ring[(a.W1 % NS) * Cfg::SLOT_V + l + j * 32] = make_uint4(0, 0, 0, 0);
         __syncwarp();
@@ -804,7 +805,7 @@ __device__ __forceinline__ void w2_helper(const SweepArgs& a, uint4* smem, volat
             continue;
         }
         spins = 0;
-        wait_prog(&prog[1], x + n - 1 - NS + 2, seen, a.err);
+        wait_prog(&prog[1], x + n - 1 - NS + 2, seen, a.err, a.eager);
 #pragma unroll
         for (int u = 0; u < Cfg::HD; ++u)
             if (u < n) {
@@ -819,7 +820,7 @@ __device__ __forceinline__ void w2_helper(const SweepArgs& a, uint4* smem, volat
         if (l == 0) prog[0] = x;
     }
     if (QLO + QN == 3) {      // the role that owns the (x+1,y-1) path: one more column of zeros (out-of-image predecessor)
-        wait_prog(&prog[1], a.W1 - NS + 2, seen, a.err);
+        wait_prog(&prog[1], a.W1 - NS + 2, seen, a.err, a.eager);
 #pragma unroll
         for (int j = 0; j < QN; ++j) ring[(a.W1 % NS) * Cfg::SLOT_V + j * 32] = make_uint4(0, 0, 0, 0);
         __syncwarp();
@@ -877,7 +878,7 @@ __device__ __forceinline__ void w2_row_a(const uint4* __restrict__ C, const Swee
 #pragma unroll
             for (int q = 0; q < NA; ++q) Nd[q][0] = Nd[q][1] = Nd[q][2] = Nd[q][3] = 0;
         } else {
-            wait_prog(prog_in, x + 1, seen_in, a.err);          // column x of the row above (its column -1 is a zero slot)
+            wait_prog(prog_in, x + 1, seen_in, a.err, a.eager);          // column x of the row above (its column -1 is a zero slot)
             const int sl[2] = {(x + NS - 1) % NS, x % NS};
 #pragma unroll
             for (int q = 0; q < NA; ++q) {
@@ -889,7 +890,7 @@ __device__ __forceinline__ void w2_row_a(const uint4* __restrict__ C, const Swee
 #pragma unroll
         for (int q = 0; q < NA; ++q) agg_step<32, 4, HASPAD, FAST>(Nd[q], Cc, v[q], l, a.P1p, a.P2mP1p, padm, one);
         if (out_mode == 1) {
-            wait_prog(prog_next, x - NS + 2, seen_next, a.err);
+            wait_prog(prog_next, x - NS + 2, seen_next, a.err, a.eager);
 #pragma unroll
             for (int q = 0; q < NA; ++q)
                 ring_out[(x % NS) * Cfg::SLOT_V + q * 32] = make_uint4(Nd[q][0], Nd[q][1], Nd[q][2], Nd[q][3]);
@@ -979,7 +980,7 @@ __device__ __forceinline__ void w2_row_b(const uint4* __restrict__ C, uint4* __r
 #pragma unroll
             for (int q = 0; q < NB; ++q) Nd[q][0] = Nd[q][1] = Nd[q][2] = Nd[q][3] = 0;
         } else {
-            wait_prog(prog_in, x + 2, seen_in, a.err);          // column x+1 of the row above (its column W1 is a zero slot)
+            wait_prog(prog_in, x + 2, seen_in, a.err, a.eager);          // column x+1 of the row above (its column W1 is a zero slot)
             const int sl[3] = {0, x % NS, (x + 1) % NS};
 #pragma unroll
             for (int q = 0; q < NB; ++q) {
@@ -991,7 +992,7 @@ __device__ __forceinline__ void w2_row_b(const uint4* __restrict__ C, uint4* __r
 #pragma unroll
         for (int q = 0; q < NB; ++q) agg_step<32, 4, HASPAD, FAST>(Nd[q], Cc, v[q], l, a.P1p, a.P2mP1p, padm, one);
         if (out_mode == 1) {
-            wait_prog(prog_next, x - NS + 2, seen_next, a.err);
+            wait_prog(prog_next, x - NS + 2, seen_next, a.err, a.eager);
 #pragma unroll
             for (int q = 0; q < NB; ++q)
                 ring_out[(x % NS) * Cfg::SLOT_V + (Q0 + q) * 32] = make_uint4(Nd[q][0], Nd[q][1], Nd[q][2], Nd[q][3]);
@@ -1005,7 +1006,7 @@ __device__ __forceinline__ void w2_row_b(const uint4* __restrict__ C, uint4* __r
         asm volatile("" ::: "memory");
         if (l == 0) *prog_me = x + 1;               // rows below may go on; the exchange slot of x is read only now
         // ---- total: S_in + warp A's partial sum + this warp's L
-        wait_prog(prog_a, x + 1, seen_a, a.err);
+        wait_prog(prog_a, x + 1, seen_a, a.err, a.eager);
         { const uint4 pa = ex[(x % NE) * 32]; vs[0] = pa.x; vs[1] = pa.y; vs[2] = pa.z; vs[3] = pa.w; }
         if (MODE != 0) {
             const uint4 sv = stageS[pslot * 32];
@@ -1044,7 +1045,7 @@ __device__ __forceinline__ void w2_row_b(const uint4* __restrict__ C, uint4* __r
         wta_flush(rkey, rnb, xb + l, xb + l < a.W1, a, keys_row, d1_row);
     }
     if (out_mode == 1) {      // the extra zero column for the (x+1,y-1) path of the row below
-        wait_prog(prog_next, a.W1 - NS + 2, seen_next, a.err);
+        wait_prog(prog_next, a.W1 - NS + 2, seen_next, a.err, a.eager);
 #pragma unroll
         for (int q = 0; q < NB; ++q) ring_out[(a.W1 % NS) * Cfg::SLOT_V + (Q0 + q) * 32] = make_uint4(0, 0, 0, 0);
         __syncwarp();
@@ -1147,6 +1148,9 @@ void launch_sweep(const int16_t* C, int16_t* S, int flip, int mode, int ndir, co
     static int workers = -1;
     if (workers < 0) { const char* e = getenv("WSG_SWEEP_WORKERS"); workers = e ? atoi(e) : 0; }
     a.max_workers = workers > 0 ? workers : (sc.max_workers > 0 ? sc.max_workers : sc.num_sms);
+    static int eager = -1;
+    if (eager < 0) { const char* e = getenv("WSG_SWEEP_EAGER"); eager = e ? atoi(e) : 64; }
+    a.eager = eager;
     a.keys = sc.keys; a.d1 = sc.d1;
     a.minD = p.minD; a.minX1 = p.minX1; a.uniq = p.uniq; a.INVALID = p.INVALID;
     a.umagic = p.uniq < 99 ? (unsigned)((0x100000000ull + (100 - p.uniq) - 1) / (unsigned)(100 - p.uniq)) : 0u;
