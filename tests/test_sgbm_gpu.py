@@ -106,6 +106,26 @@ def test_sweeps_many_bands_and_reuse(handle, mode):
             assert np.array_equal(out, ref["disp"])
 
 
+@pytest.mark.parametrize("workers", [1, 3, 74, 1000])
+def test_sweep_worker_cap_does_not_change_results(handle, workers):
+    """wsg_sgbm_set_sweep_workers: however few SMs take the bands of a sweep (one worker walks all of them in ticket order),
+    the disparity is the oracle's; a cap above the SM count means all of them."""
+    from oracle import sgbm
+    from wass_b200 import capi, synth
+    handle.sgbm_set_impl(capi.AGG_SWEEPS_WTA)
+    try:
+        handle.sgbm_set_sweep_workers(workers)
+        for mode, (W, H, D) in ((1, (96, 331, 64)), (0, (200, 75, 160))):
+            r, l, _ = synth.make_pair(W, H, D, seed=H + D + 1)
+            i1, i2 = synth.pad_for_sgbm(r, l, D)
+            p = sgbm.wass_params(D, mode=mode)
+            assert np.array_equal(handle.sgbm_compute(i1, i2, p), sgbm.compute(i1, i2, p)["disp"])
+        with pytest.raises(capi.WsgError):
+            handle.sgbm_set_sweep_workers(-1)
+    finally:
+        handle.sgbm_set_sweep_workers(0)
+
+
 @pytest.mark.parametrize("uniq", [40, 99, 100, 150])
 def test_uniqueness_ratio_extremes(handle, impl, uniq):
     """Large uniquenessRatio, and >= 100 (100-uniq <= 0: the in-sweep WTA hands over to wta_kernel).  The oracle agrees
