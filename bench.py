@@ -131,8 +131,8 @@ def _cpu_band_worker(args):
     return time.perf_counter() - t
 
 
-def cpu_baseline_single(rows=1024):
-    """1 core, one band of `rows` rows of the benchmark frame (bounded sample)."""
+def cpu_baseline_single(rows=2048):
+    """1 core, `rows` rows of the benchmark frame (bounded sample: the whole frame, ~6 s on the GPU box's host)."""
     from wass_b200 import synth
     r, l, _ = synth.make_pair(W_IMG, rows, NDISP, seed=0)
     i1, i2 = synth.pad_for_sgbm(r, l, NDISP)
