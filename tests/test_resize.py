@@ -137,3 +137,21 @@ def test_dense_stage_with_dense_scale(scale, mode):
         assert np.array_equal(out2.view(np.uint32), ref.view(np.uint32))
     finally:
         h.close()
+
+
+def test_dense_scaled_size_matches_cv2_shapes(no_ipp):
+    """wsg_dense_scaled_size (host only): the matcher-input size of wass_stereo.cpp:788-797 is cv::resize's own dsize."""
+    import ctypes
+    from wass_b200 import capi
+    lib = capi.load()
+    rng = np.random.default_rng(5)
+    for _ in range(40):
+        H, W = int(rng.integers(3, 400)), int(rng.integers(3, 600))
+        s = float(rng.choice([0.25, 0.3, 0.5, 0.55, 0.75, 0.9, 1.0, 1.1, 1.5, 2.0, 2.5]))
+        hs, ws = ctypes.c_int(), ctypes.c_int()
+        lib.wsg_dense_scaled_size(H, W, s, ctypes.byref(hs), ctypes.byref(ws))
+        if s == 1.0:
+            assert (hs.value, ws.value) == (H, W)
+            continue
+        ref = cv2.resize(np.zeros((H, W), np.uint8), None, fx=s, fy=s if s < 1 else 1.0, interpolation=cv2.INTER_CUBIC)
+        assert (hs.value, ws.value) == ref.shape, (H, W, s)
