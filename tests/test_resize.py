@@ -155,3 +155,20 @@ def test_dense_scaled_size_matches_cv2_shapes(no_ipp):
             continue
         ref = cv2.resize(np.zeros((H, W), np.uint8), None, fx=s, fy=s if s < 1 else 1.0, interpolation=cv2.INTER_CUBIC)
         assert (hs.value, ws.value) == ref.shape, (H, W, s)
+
+
+def test_oracle_resizes_extreme_scales_and_thin_images(no_ipp):
+    from oracle import pipeline as op
+    rng = np.random.default_rng(21)
+    for (H, W, s) in [(40, 300, 0.1), (300, 40, 0.15), (9, 9, 4.0), (1, 50, 2.0), (50, 1, 0.5), (2, 2, 3.0), (17, 33, 0.07)]:
+        img = rng.integers(0, 256, (H, W), dtype=np.uint8)
+        fy = s if s < 1 else 1.0
+        if round(H * fy) < 1 or round(W * s) < 1:
+            continue
+        ref = cv2.resize(img, None, fx=s, fy=fy, interpolation=cv2.INTER_CUBIC)
+        assert np.array_equal(op.resize_cubic_u8(img, s, fy), ref), (H, W, s)
+        d = (rng.random((H, W)) * 100).astype(np.float32)
+        dh, dw = max(1, int(round(H / fy))), max(1, int(round(W / s)))
+        assert np.array_equal(op.resize_cubic_f32(d, dw, dh).view(np.uint32),
+                              cv2.resize(d, (dw, dh), interpolation=cv2.INTER_CUBIC).view(np.uint32)), (H, W, s)
+        assert np.array_equal(op.resize_nearest(d, dw, dh), cv2.resize(d, (dw, dh), interpolation=cv2.INTER_NEAREST))
