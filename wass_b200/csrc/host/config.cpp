@@ -6,15 +6,9 @@
 
 namespace wasshost {
 
-bool Config::Option::is_default() const
-{
-    switch (type) {
-        case INT: return i == i0;
-        case DOUBLE: return d == d0;
-        case BOOL: return b == b0;
-        default: return s == s0;
-    }
-}
+// incfg keeps a sticky flag (ext/incfg/incfg.hpp:528-535): an option stays "default" only while every assignment repeats
+// the value it already has -- "WINSIZE=11" followed by "WINSIZE=13" (the default) is NOT written back commented out
+bool Config::Option::is_default() const { return is_def; }
 
 std::string Config::Option::value_str() const
 {
@@ -32,16 +26,20 @@ void Config::Option::parse(const std::string& v)
 {
     if (type == BOOL) {
         if (v != "true" && v != "false") throw ConfigError("Unable to parse " + v + " to \"true\" or \"false\"");
-        b = v == "true";
+        const bool nb = v == "true";
+        is_def = is_def && nb == b;
+        b = nb;
         return;
     }
     if (type == STRING) {
-        s = (v.length() >= 2 && v.front() == '"' && v.back() == '"') ? v.substr(1, v.length() - 2) : v;
+        const std::string ns = (v.length() >= 2 && v.front() == '"' && v.back() == '"') ? v.substr(1, v.length() - 2) : v;
+        is_def = is_def && ns == s;
+        s = ns;
         return;
     }
     std::stringstream ss(v);
-    if (type == INT) { int x; ss >> x; if (ss.fail()) throw ConfigError("Unable to parse " + v + " to its defined type"); i = x; }
-    else { double x; ss >> x; if (ss.fail()) throw ConfigError("Unable to parse " + v + " to its defined type"); d = x; }
+    if (type == INT) { int x; ss >> x; if (ss.fail()) throw ConfigError("Unable to parse " + v + " to its defined type"); is_def = is_def && x == i; i = x; }
+    else { double x; ss >> x; if (ss.fail()) throw ConfigError("Unable to parse " + v + " to its defined type"); is_def = is_def && x == d; d = x; }
 }
 
 void Config::addi(const char* k, int v, const char* d) { Option o; o.type = INT; o.desc = d; o.i = o.i0 = v; options_[k] = o; }
@@ -141,7 +139,8 @@ void Config::load(std::istream& is)
             it->second.parse(value);
         } catch (ConfigError& e) {
             std::stringstream err;
-            err << "Config file error for key <" << key << "> (Line " << linenum - 1 << "): " << e.what();
+            // incfg prints its 0-based counter minus one here, unsigned (incfg.cpp:139): "Line 4294967295" for the first line
+            err << "Config file error for key <" << key << "> (Line " << (unsigned)(linenum - 2) << "): " << e.what();
             throw ConfigError(err.str());
         }
     }

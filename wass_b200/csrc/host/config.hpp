@@ -15,6 +15,7 @@ class Config {
 public:
     enum Type { INT, DOUBLE, BOOL, STRING };
     struct Option {
+        bool is_def = true;      // incfg's sticky default flag, see Option::parse
         Type type; std::string desc;
         long long i = 0, i0 = 0; double d = 0, d0 = 0; bool b = false, b0 = false; std::string s, s0;
         bool is_default() const;
