@@ -73,6 +73,20 @@ int wsg_sgbm_compute(wsg_handle* h, const uint8_t* img1, const uint8_t* img2, in
 int wsg_sgbm_compute_device(wsg_handle* h, const uint8_t* d_img1, const uint8_t* d_img2, int rows, int cols,
                             size_t stride, const wsg_sgbm_params* p, int16_t* d_disp16);
 
+/* Batch forms: `n` frames of equal geometry and parameters in ONE call -- the form a sequence driver uses (the reference
+ * runs one wass_stereo process per frame, cli/wasscli/wasscli.py:326-346; nothing couples the frames).  The cost volumes of
+ * all frames are built first, then ONE launch per aggregation sweep walks the row bands of all frames interleaved, so the
+ * wavefront of one frame fills while another drains.  Results are identical to n single calls.
+ * Device memory: n * 2 * volume_bytes (wsg_sgbm_stats).
+ *   wsg_sgbm_compute_batch         HOST buffers: img1[f], img2[f] (rows x cols, `stride`), disp16[f] (rows x cols dense).
+ *   wsg_sgbm_compute_batch_device  DEVICE buffers: frame f at d_img + f * frame_stride bytes, d_disp16 + f * rows * cols;
+ *                                  asynchronous on the handle's stream. */
+#define WSG_MAX_BATCH 64
+int wsg_sgbm_compute_batch(wsg_handle* h, int n, const uint8_t* const* img1, const uint8_t* const* img2, int rows, int cols,
+                           size_t stride, const wsg_sgbm_params* p, int16_t* const* disp16);
+int wsg_sgbm_compute_batch_device(wsg_handle* h, int n, const uint8_t* d_img1, const uint8_t* d_img2, size_t frame_stride,
+                                  int rows, int cols, size_t stride, const wsg_sgbm_params* p, int16_t* d_disp16);
+
 /* Statistics of the last wsg_sgbm_compute* on this handle (synchronises the stream). */
 typedef struct wsg_sgbm_stats {
     int max_cost;            /* max over the cost volume C */
@@ -94,21 +108,14 @@ int wsg_sgbm_debug_volumes(wsg_handle* h, int16_t* C_host, int16_t* S_host);
  *   WSG_AGG_PER_DIRECTION  one launch per path direction (8 or 5), separate WTA kernel          (23V moved)
  *   WSG_AGG_SWEEPS         fused 4-direction wavefront sweeps, S written out, separate WTA      ( 6V moved)
  *   WSG_AGG_SWEEPS_WTA     fused sweeps, WTA inside the last sweep, S never written             ( 4V moved)
- *   WSG_AGG_SWEEPS3_WTA    3-direction sweeps (rows skewed by one column instead of two) + the two
- *                          anti-diagonal directions as per-direction launches, WTA inside the last sweep   (10V moved)
- *   WSG_AGG_SWEEPS2W_WTA   as WSG_AGG_SWEEPS_WTA with every image row split over two warps                  ( 4V moved)
- * WSG_AGG_SWEEPS_WTA is the default; the last two measured no faster and serve as cross-checks.
+ * WSG_AGG_SWEEPS_WTA is the default; the other two are the cross-checks the parity tests compare it with at full size.
  * The fused forms need numDisparities <= 512; above that the per-direction form is used regardless. */
 #define WSG_AGG_PER_DIRECTION 0
 #define WSG_AGG_SWEEPS 1
 #define WSG_AGG_SWEEPS_WTA 2
-#define WSG_AGG_SWEEPS3_WTA 3
-#define WSG_AGG_SWEEPS2W_WTA 4
 int wsg_sgbm_set_impl(wsg_handle* h, int impl);
-/* Caps the number of SMs the fused sweeps of this handle occupy (0 = all, the default).  A sweep is a wavefront over
- * H/7 row bands and cannot keep every SM busy, so with three or more frames in flight on one GPU (one handle and stream
- * each) half the SMs per sweep gives the higher throughput -- two frames' sweeps run side by side -- at the price of a
- * longer single-frame latency (B200, 2448x2048x256: 11.0 -> 14.8 ms per frame alone, 610 -> 649 Mdisp/s pipelined). */
+/* Caps the number of SMs the fused sweeps of this handle occupy (0 = all, the default): a sweep is a persistent launch of
+ * one worker per SM; a cap leaves the other SMs to kernels of other streams. */
 int wsg_sgbm_set_sweep_workers(wsg_handle* h, int max_sms);
 
 /* ---- dense stereo stage as a whole ------------------------------------------------------------ */

@@ -7,7 +7,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libwassgpu.so")
+LIB_PATH = os.environ.get("WSG_LIB") or os.path.join(_HERE, "libwassgpu.so")     # WSG_LIB: an experiment build (tools/)
 
 MODE_SGBM = 0
 MODE_HH = 1
@@ -88,7 +88,8 @@ def make_calib(c, left_shape, right_shape, rect_shape):
     return k
 
 
-AGG_PER_DIRECTION, AGG_SWEEPS, AGG_SWEEPS_WTA, AGG_SWEEPS3_WTA, AGG_SWEEPS2W_WTA = 0, 1, 2, 3, 4
+AGG_PER_DIRECTION, AGG_SWEEPS, AGG_SWEEPS_WTA = 0, 1, 2
+MAX_BATCH = 64
 
 _lib = None
 
@@ -113,6 +114,9 @@ def load():
     lib.wsg_version.restype = ctypes.c_char_p
     lib.wsg_sgbm_compute.argtypes = [vp, vp, vp, ci, ci, sz, ctypes.POINTER(SgbmParams), vp]
     lib.wsg_sgbm_compute_device.argtypes = [vp, vp, vp, ci, ci, sz, ctypes.POINTER(SgbmParams), vp]
+    lib.wsg_sgbm_compute_batch.argtypes = [vp, ci, ctypes.POINTER(vp), ctypes.POINTER(vp), ci, ci, sz, ctypes.POINTER(SgbmParams),
+                                           ctypes.POINTER(vp)]
+    lib.wsg_sgbm_compute_batch_device.argtypes = [vp, ci, vp, vp, sz, ci, ci, sz, ctypes.POINTER(SgbmParams), vp]
     lib.wsg_sgbm_get_stats.argtypes = [vp, ctypes.POINTER(SgbmStats)]
     lib.wsg_sgbm_debug_volumes.argtypes = [vp, vp, vp]
     lib.wsg_sgbm_set_sweep_workers.argtypes = [vp, ci]
@@ -305,6 +309,34 @@ class Handle:
         p = SgbmParams(**params)
         self._ck(self.lib.wsg_sgbm_compute_device(self.h, d_img1, d_img2, rows, cols, stride, ctypes.byref(p), d_disp))
 
+    def sgbm_compute_batch(self, imgs1, imgs2, params):
+        """n frames of equal shape in one call (wsg_sgbm_compute_batch): lists of host arrays in, list of disparities out."""
+        a = [np.ascontiguousarray(i, np.uint8) for i in imgs1]
+        b = [np.ascontiguousarray(i, np.uint8) for i in imgs2]
+        n = len(a)
+        if n == 0 or len(b) != n or any(x.shape != a[0].shape or x.ndim != 2 for x in a + b):
+            raise ValueError("imgs1/imgs2 must be equally long lists of 2-D uint8 arrays of one shape")
+        H, W = a[0].shape
+        out = [np.empty((H, W), np.int16) for _ in range(n)]
+        arr = ctypes.c_void_p * n
+        p = SgbmParams(**params)
+        self._ck(self.lib.wsg_sgbm_compute_batch(self.h, n, arr(*[x.ctypes.data for x in a]), arr(*[x.ctypes.data for x in b]),
+                                                 H, W, W, ctypes.byref(p), arr(*[x.ctypes.data for x in out])))
+        return out
+
+    def sgbm_compute_batch_ptr(self, n, img1_ptrs, img2_ptrs, rows, cols, stride, params, disp_ptrs):
+        """Raw host pointers (e.g. pinned torch tensors), n of each."""
+        arr = ctypes.c_void_p * n
+        p = SgbmParams(**params)
+        self._ck(self.lib.wsg_sgbm_compute_batch(self.h, n, arr(*img1_ptrs), arr(*img2_ptrs), rows, cols, stride, ctypes.byref(p),
+                                                 arr(*disp_ptrs)))
+
+    def sgbm_compute_batch_device(self, n, d_img1, d_img2, frame_stride, rows, cols, stride, params, d_disp):
+        """Device pointers (ints) to n frames `frame_stride` bytes apart; d_disp: n x rows x cols int16.  Asynchronous."""
+        p = SgbmParams(**params)
+        self._ck(self.lib.wsg_sgbm_compute_batch_device(self.h, n, d_img1, d_img2, frame_stride, rows, cols, stride,
+                                                        ctypes.byref(p), d_disp))
+
     def sgbm_stats(self):
         s = SgbmStats()
         self._ck(self.lib.wsg_sgbm_get_stats(self.h, ctypes.byref(s)))
@@ -317,7 +349,7 @@ class Handle:
         return C, S
 
     def sgbm_set_sweep_workers(self, max_sms):
-        """Cap on the SMs the fused sweeps occupy (0 = all): use ~half with three or more frames in flight per GPU."""
+        """Cap on the SMs the fused sweeps occupy (0 = all)."""
         self._ck(self.lib.wsg_sgbm_set_sweep_workers(self.h, int(max_sms)))
 
     def sgbm_set_impl(self, impl):

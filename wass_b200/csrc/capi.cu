@@ -17,7 +17,7 @@ int wsg_create(int device, wsg_handle** out)
     h->device = device;
     if (cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking) != cudaSuccess) { delete h; return WSG_ERR_CUDA; }
     h->stream = h->own_stream;
-    if (const char* e = getenv("WSG_AGG_IMPL")) h->agg_impl = std::min(std::max(atoi(e), 0), 4);
+    if (const char* e = getenv("WSG_AGG_IMPL")) h->agg_impl = std::min(std::max(atoi(e), 0), 2);
     *out = h;
     return WSG_OK;
 }
@@ -96,149 +96,175 @@ int wsg_make_plan(wsg_handle* h, int rows, int cols, const wsg_sgbm_params* p, S
     return WSG_OK;
 }
 
+// Per-handle scalars (ints): [1] sweep error flag, [16] / [32] band tickets of the two sweeps, [SCAL_MAXC + f] max over the
+// cost volume of frame f of the batch.
+static constexpr int SCAL_ERR = 1, SCAL_TICKET0 = 16, SCAL_TICKET1 = 32, SCAL_MAXC = 48;
+
 // The fused sweeps hand states between CTAs with bounded waits; an overrun (never seen on a healthy device) raises a
 // flag instead of hanging.  Synchronises the stream.
 int wsg_check_sweep(wsg_handle* h)
 {
     if (!h->scalars.p || h->stats.agg_impl == WSG_AGG_PER_DIRECTION) return WSG_OK;
     int flag = 0;
-    CK(h, cudaMemcpyAsync(&flag, (int*)h->scalars.p + 1, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CK(h, cudaMemcpyAsync(&flag, (int*)h->scalars.p + SCAL_ERR, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     CK(h, cudaStreamSynchronize(h->stream));
     if (h->dbg.p && getenv("WSG_SWEEP_DEBUG")) {
-        const size_t nb = (h->plan.H + 7) / 8;
-        std::vector<int> d(16384);
+        const int R = sweep_rows_per_band(h->plan);
+        const size_t nt = (size_t)((h->plan.H + R - 1) / R) * h->batch_n;
+        std::vector<int> d(3 * nt);
         cudaMemcpy(d.data(), h->dbg.p, d.size() * sizeof(int), cudaMemcpyDeviceToHost);
-        fprintf(stderr, "[wsg] last sweep: band sm start_us end_us\n");
-        for (size_t i = 0; i < nb && i < 2048; ++i)
-            fprintf(stderr, "[wsg] %zu %d %.1f %.1f\n", i, d[i], (d[4096 + 2 * i] - d[4096]) * 1e-3, (d[4096 + 2 * i + 1] - d[4096]) * 1e-3);
+        fprintf(stderr, "[wsg] last sweep: ticket frame band sm start_us end_us\n");
+        for (size_t i = 0; i < nt; ++i)
+            fprintf(stderr, "[wsg] %zu %zu %zu %d %.1f %.1f\n", i, i % h->batch_n, i / h->batch_n, d[3 * i],
+                    (d[3 * i + 1] - d[1]) * 1e-3, (d[3 * i + 2] - d[1]) * 1e-3);
     }
     if (flag) { h->err = "fused aggregation sweep: hand-off wait overran (code " + std::to_string(flag) + ")"; return WSG_ERR_CUDA; }
     return WSG_OK;
 }
 
-int wsg_run_sgbm(wsg_handle* h, const uint8_t* d_img1, const uint8_t* d_img2, size_t stride, int16_t* d_disp)
+// The dense matcher on `n` frames of the planned geometry, device pointers, asynchronous on the handle's stream.
+// Prefilter + cost volume frame by frame, then ONE launch per sweep over the bands of all frames (sweep_kernels.cu),
+// then LR check + median frame by frame.
+static int run_sgbm_batch(wsg_handle* h, int n, const uint8_t* const* d_img1, const uint8_t* const* d_img2, size_t stride,
+                          int16_t* const* d_disp)
 {
     const SgbmPlan& pl = h->plan;
     const size_t npix = (size_t)pl.H * pl.W;
     const size_t vol = (size_t)pl.H * pl.W1 * pl.Dp * sizeof(int16_t);
+    const size_t pad = sweep_volume_pad_bytes();
     int rc;
     if ((rc = ensure(h, h->pre1, npix * sizeof(uint2)))) return rc;
     if ((rc = ensure(h, h->pre2, npix * sizeof(uint2)))) return rc;
-    if ((rc = ensure(h, h->C, vol))) return rc;
-    if ((rc = ensure(h, h->S, vol))) return rc;
+    if ((rc = ensure(h, h->C, vol * n + 2 * pad))) return rc;
+    if ((rc = ensure(h, h->S, vol * n + 2 * pad))) return rc;
     if ((rc = ensure(h, h->raw, npix * sizeof(int16_t)))) return rc;
-    const size_t scal_bytes = (16 + 2 * WSG_SWEEP_TICKET_INTS) * sizeof(int);   // [0] max C, [1] sweep error, [16..] hand-out counters
-    if ((rc = ensure(h, h->scalars, scal_bytes))) return rc;
+    const size_t scal_bytes = (size_t)(SCAL_MAXC + n) * sizeof(int);
+    if ((rc = ensure(h, h->scalars, std::max(scal_bytes, (size_t)4096)))) return rc;
+    int16_t* Cv = (int16_t*)((char*)h->C.p + pad);
+    int16_t* Sv = (int16_t*)((char*)h->S.p + pad);
+    int* scal = (int*)h->scalars.p;
     int launches = 0;
     CK(h, cudaMemsetAsync(h->scalars.p, 0, scal_bytes, h->stream));
-    {
-        StageTimer t(h, WSG_STAGE_PREFILTER, 2);
-        launch_prefilter(d_img1, stride, (uint2*)h->pre1.p, pl, h->stream);
-        launch_prefilter(d_img2, stride, (uint2*)h->pre2.p, pl, h->stream);
-        launches += 2;
-    }
-    {
-        StageTimer t(h, WSG_STAGE_COST, 1);
-        launch_cost((const uint2*)h->pre1.p, (const uint2*)h->pre2.p, (int16_t*)h->C.p, (int*)h->scalars.p, pl, h->stream, &launches);
+    for (int f = 0; f < n; ++f) {
+        {
+            StageTimer t(h, WSG_STAGE_PREFILTER, 2);
+            launch_prefilter(d_img1[f], stride, (uint2*)h->pre1.p, pl, h->stream);
+            launch_prefilter(d_img2[f], stride, (uint2*)h->pre2.p, pl, h->stream);
+            launches += 2;
+        }
+        {
+            StageTimer t(h, WSG_STAGE_COST, 1);
+            launch_cost((const uint2*)h->pre1.p, (const uint2*)h->pre2.p, Cv + (size_t)f * (vol / 2), scal + SCAL_MAXC + f, pl,
+                        h->stream, &launches);
+        }
     }
     const int impl = (h->agg_impl != WSG_AGG_PER_DIRECTION && sweep_supported(pl)) ? h->agg_impl : WSG_AGG_PER_DIRECTION;
     if (impl == WSG_AGG_PER_DIRECTION) {
-        {
-            const int ndirs = pl.mode == WSG_MODE_HH ? 8 : 5;
-            StageTimer t(h, WSG_STAGE_AGGREGATE, ndirs);
-            for (int r = 0; r < ndirs; ++r)
-                launch_aggregate_dir((const int16_t*)h->C.p, (int16_t*)h->S.p, r, r == 0, pl, h->stream);
-            launches += ndirs;
-        }
-        {
-            StageTimer t(h, WSG_STAGE_WTA, 1);
-            launch_wta((const int16_t*)h->S.p, (int16_t*)h->raw.p, pl, h->stream);
-            launches += 1;
+        for (int f = 0; f < n; ++f) {
+            int16_t* Cf = Cv + (size_t)f * (vol / 2);
+            {
+                const int ndirs = pl.mode == WSG_MODE_HH ? 8 : 5;
+                StageTimer t(h, WSG_STAGE_AGGREGATE, ndirs);
+                for (int r = 0; r < ndirs; ++r) launch_aggregate_dir(Cf, Sv, r, r == 0, pl, h->stream);
+                launches += ndirs;
+            }
+            {
+                StageTimer t(h, WSG_STAGE_WTA, 1);
+                launch_wta(Sv, (int16_t*)h->raw.p, pl, h->stream);
+                launches += 1;
+            }
+            {
+                StageTimer t(h, WSG_STAGE_MEDIAN, 1);
+                launch_median3((const int16_t*)h->raw.p, d_disp[f], pl.H, pl.W, h->stream);
+                launches += 1;
+            }
         }
     } else {
-        // fused wavefront sweeps (sweep_kernels.cu).  scalars: [0] max C, [1] error flag, [2..] band tickets
-        const size_t bbytes = sweep_boundary_bytes(pl);
+        // fused wavefront sweeps over the whole batch (sweep_kernels.cu)
+        const size_t bbytes = sweep_boundary_bytes(pl) * n;
         const bool grown = bbytes > h->bnd.cap;
         if ((rc = ensure(h, h->bnd, bbytes))) return rc;
-        const int bnd_nd = impl == WSG_AGG_SWEEPS3_WTA ? 3 : 4;
-        if (grown || h->bnd_H != pl.H || h->bnd_W1 != pl.W1 || h->bnd_K != pl.K || h->bnd_nd != bnd_nd) {
+        if (grown || h->bnd_H != pl.H || h->bnd_W1 != pl.W1 || h->bnd_K != pl.K || h->bnd_n != n) {
             // epoch tags only tell "this sweep" from "the previous one" for slots that are rewritten every sweep: a change
-            // of geometry, or of the set of states a sweep hands down (the 3-direction sweeps leave one third of every slot
-            // untouched), would let data of an older sweep with the same 2-bit epoch pass for current
+            // of geometry or batch size would let data of an older sweep with the same 2-bit epoch pass for current
             CK(h, cudaMemsetAsync(h->bnd.p, 0, h->bnd.cap, h->stream));
-            h->bnd_H = pl.H; h->bnd_W1 = pl.W1; h->bnd_K = pl.K; h->bnd_nd = bnd_nd;
+            h->bnd_H = pl.H; h->bnd_W1 = pl.W1; h->bnd_K = pl.K; h->bnd_n = n;
         }
-        const bool fused_wta = (impl == WSG_AGG_SWEEPS_WTA || impl == WSG_AGG_SWEEPS3_WTA || impl == WSG_AGG_SWEEPS2W_WTA) && pl.uniq < 100;   // the in-sweep WTA needs 100-uniq > 0
+        const bool fused_wta = impl == WSG_AGG_SWEEPS_WTA && pl.uniq < 100;   // the in-sweep WTA needs 100-uniq > 0
         if (fused_wta) {
-            if ((rc = ensure(h, h->keys, npix * sizeof(unsigned long long)))) return rc;
-            if ((rc = ensure(h, h->d1, npix * sizeof(int16_t)))) return rc;
+            if ((rc = ensure(h, h->keys, npix * n * sizeof(unsigned long long)))) return rc;
+            if ((rc = ensure(h, h->d1, npix * n * sizeof(int16_t)))) return rc;
         }
         SweepScratch sc;
         sc.boundary = h->bnd.p;
-        sc.two_warps = impl == WSG_AGG_SWEEPS2W_WTA;
         sc.max_workers = h->sweep_workers;
-        sc.maxC = (const int*)h->scalars.p;
-        sc.err = (int*)h->scalars.p + 1;
+        sc.maxC = scal + SCAL_MAXC; sc.maxC_stride = 1;
+        sc.err = scal + SCAL_ERR;
         sc.dbg = nullptr;
+        sc.nframes = n; sc.volume_stride_bytes = vol;
         if (getenv("WSG_SWEEP_DEBUG")) {
-            if ((rc = ensure(h, h->dbg, 16384 * sizeof(int)))) return rc;
+            const int R = sweep_rows_per_band(pl);
+            if ((rc = ensure(h, h->dbg, (size_t)3 * ((pl.H + R - 1) / R) * n * sizeof(int)))) return rc;
             sc.dbg = (int*)h->dbg.p;
         }
         sc.keys = (unsigned long long*)h->keys.p;
         sc.d1 = (int16_t*)h->d1.p;
-        int* tickets = (int*)h->scalars.p + 16;
         if (h->num_sms == 0) CK(h, cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, h->device));
         sc.num_sms = h->num_sms;
         auto next_epoch = [&]() { h->sweep_epoch = h->sweep_epoch % 3 + 1; return h->sweep_epoch; };
         const int last_mode = fused_wta ? 2 : 1;
-        // WSG_AGG_SWEEPS3_WTA: the sweeps leave out the (x+1,y-1)-type path (directions 3 and 5), which forces a skew of two
-        // columns per row on the wavefront; those two run as independent per-direction launches (HBM-bound) in between.
-        const bool split = impl == WSG_AGG_SWEEPS3_WTA;
-        const int nd = split ? 3 : 4;
         {
-            const int nl = 2 + (fused_wta ? 1 : 0) + (split ? (pl.mode == WSG_MODE_HH ? 2 : 1) : 0);
+            const int nl = 2 + (fused_wta ? 1 : 0);
             StageTimer t(h, WSG_STAGE_AGGREGATE, nl);
             if (fused_wta) launch_wta_reset(sc, pl, h->stream);
-            sc.ticket = tickets + 0; sc.epoch = next_epoch();
-            launch_sweep((const int16_t*)h->C.p, (int16_t*)h->S.p, 0, 0, nd, pl, sc, h->stream);
-            if (split) {
-                launch_aggregate_dir((const int16_t*)h->C.p, (int16_t*)h->S.p, 3, false, pl, h->stream);
-                if (pl.mode == WSG_MODE_HH) launch_aggregate_dir((const int16_t*)h->C.p, (int16_t*)h->S.p, 5, false, pl, h->stream);
-            }
-            sc.ticket = tickets + WSG_SWEEP_TICKET_INTS;
+            sc.ticket = scal + SCAL_TICKET0; sc.epoch = next_epoch();
+            launch_sweep(Cv, Sv, 0, 0, 4, pl, sc, h->stream);
+            sc.ticket = scal + SCAL_TICKET1;
             if (pl.mode == WSG_MODE_HH) {
                 sc.epoch = next_epoch();
-                launch_sweep((const int16_t*)h->C.p, (int16_t*)h->S.p, 1, last_mode, nd, pl, sc, h->stream);
+                launch_sweep(Cv, Sv, 1, last_mode, 4, pl, sc, h->stream);
             } else {
-                launch_sweep((const int16_t*)h->C.p, (int16_t*)h->S.p, 1, last_mode, 1, pl, sc, h->stream);
+                launch_sweep(Cv, Sv, 1, last_mode, 1, pl, sc, h->stream);
             }
             launches += nl;
         }
-        {
-            StageTimer t(h, WSG_STAGE_WTA, 1);
-            if (fused_wta) launch_lrcheck(sc, (int16_t*)h->raw.p, pl, h->stream);
-            else launch_wta((const int16_t*)h->S.p, (int16_t*)h->raw.p, pl, h->stream);
-            launches += 1;
+        for (int f = 0; f < n; ++f) {
+            {
+                StageTimer t(h, WSG_STAGE_WTA, 1);
+                if (fused_wta) launch_lrcheck(sc, f, (int16_t*)h->raw.p, pl, h->stream);
+                else launch_wta(Sv + (size_t)f * (vol / 2), (int16_t*)h->raw.p, pl, h->stream);
+                launches += 1;
+            }
+            {
+                StageTimer t(h, WSG_STAGE_MEDIAN, 1);
+                launch_median3((const int16_t*)h->raw.p, d_disp[f], pl.H, pl.W, h->stream);
+                launches += 1;
+            }
         }
     }
     h->stats.agg_impl = impl;
-    {
-        const int nsp = pl.speckleWindow > 0 ? 4 : 0;
-        if (nsp && (rc = ensure(h, h->keys, npix * sizeof(unsigned long long)))) return rc;   // free again after the LR check
-        StageTimer t(h, WSG_STAGE_MEDIAN, 1 + nsp);
-        launch_median3((const int16_t*)h->raw.p, d_disp, pl.H, pl.W, h->stream);
-        if (nsp)
-            launch_filter_speckles(d_disp, pl.H, pl.W, pl.INVALID, pl.speckleWindow, pl.speckleMaxDiff, (int*)h->keys.p,
+    if (pl.speckleWindow > 0) {
+        if ((rc = ensure(h, h->keys, npix * sizeof(unsigned long long)))) return rc;   // free again after the LR check
+        for (int f = 0; f < n; ++f) {
+            StageTimer t(h, WSG_STAGE_MEDIAN, 4);
+            launch_filter_speckles(d_disp[f], pl.H, pl.W, pl.INVALID, pl.speckleWindow, pl.speckleMaxDiff, (int*)h->keys.p,
                                    (unsigned*)h->keys.p + npix, h->stream);
-        launches += 1 + nsp;
+            launches += 4;
+        }
     }
     CK(h, cudaGetLastError());
+    h->batch_n = n;
     h->stats.kernel_launches = launches;
     h->stats.width1 = pl.W1;
     h->stats.d_padded = pl.Dp;
     h->stats.volume_bytes = (long long)vol;
     h->have_plan = true;
     return WSG_OK;
+}
+
+int wsg_run_sgbm(wsg_handle* h, const uint8_t* d_img1, const uint8_t* d_img2, size_t stride, int16_t* d_disp)
+{
+    return run_sgbm_batch(h, 1, &d_img1, &d_img2, stride, &d_disp);
 }
 
 int wsg_sgbm_compute_device(wsg_handle* h, const uint8_t* d_img1, const uint8_t* d_img2, int rows, int cols,
@@ -258,22 +284,61 @@ int wsg_sgbm_compute_device(wsg_handle* h, const uint8_t* d_img1, const uint8_t*
 int wsg_sgbm_compute(wsg_handle* h, const uint8_t* img1, const uint8_t* img2, int rows, int cols, size_t stride,
                      const wsg_sgbm_params* p, int16_t* disp16)
 {
+    return wsg_sgbm_compute_batch(h, 1, &img1, &img2, rows, cols, stride, p, &disp16);
+}
+
+int wsg_sgbm_compute_batch_device(wsg_handle* h, int n, const uint8_t* d_img1, const uint8_t* d_img2, size_t frame_stride,
+                                  int rows, int cols, size_t stride, const wsg_sgbm_params* p, int16_t* d_disp16)
+{
     if (!h) return WSG_ERR_INVALID_ARG;
+    if (n <= 0 || n > WSG_MAX_BATCH) { h->err = "batch size must be 1.." + std::to_string(WSG_MAX_BATCH); return WSG_ERR_INVALID_ARG; }
+    if (!d_img1 || !d_img2 || !d_disp16 || stride < (size_t)std::max(cols, 0) || frame_stride < stride * (size_t)std::max(rows, 0)) {
+        h->err = "null pointer, stride < cols or frame_stride < rows*stride"; return WSG_ERR_INVALID_ARG;
+    }
+    CK(h, cudaSetDevice(h->device));
+    SgbmPlan pl{};
+    int rc = wsg_make_plan(h, rows, cols, p, pl);
+    if (rc) return rc;
+    h->plan = pl;
+    h->stats.out_of_domain = 0; h->stats.max_cost = 0;
+    std::vector<const uint8_t*> a(n), b(n);
+    std::vector<int16_t*> d(n);
+    for (int f = 0; f < n; ++f) {
+        a[f] = d_img1 + (size_t)f * frame_stride; b[f] = d_img2 + (size_t)f * frame_stride;
+        d[f] = d_disp16 + (size_t)f * rows * cols;
+    }
+    return run_sgbm_batch(h, n, a.data(), b.data(), stride, d.data());
+}
+
+int wsg_sgbm_compute_batch(wsg_handle* h, int n, const uint8_t* const* img1, const uint8_t* const* img2, int rows, int cols,
+                           size_t stride, const wsg_sgbm_params* p, int16_t* const* disp16)
+{
+    if (!h) return WSG_ERR_INVALID_ARG;
+    if (n <= 0 || n > WSG_MAX_BATCH) { h->err = "batch size must be 1.." + std::to_string(WSG_MAX_BATCH); return WSG_ERR_INVALID_ARG; }
     if (!img1 || !img2 || !disp16 || stride < (size_t)std::max(cols, 0)) { h->err = "null pointer or stride < cols"; return WSG_ERR_INVALID_ARG; }
+    for (int f = 0; f < n; ++f)
+        if (!img1[f] || !img2[f] || !disp16[f]) { h->err = "null frame pointer"; return WSG_ERR_INVALID_ARG; }
     CK(h, cudaSetDevice(h->device));
     SgbmPlan pl{};
     int rc = wsg_make_plan(h, rows, cols, p, pl);
     if (rc) return rc;
     h->plan = pl;
     const size_t npix = (size_t)rows * cols;
-    if ((rc = ensure(h, h->img1, npix))) return rc;
-    if ((rc = ensure(h, h->img2, npix))) return rc;
-    if ((rc = ensure(h, h->disp, npix * sizeof(int16_t)))) return rc;
-    CK(h, cudaMemcpy2DAsync(h->img1.p, cols, img1, stride, cols, rows, cudaMemcpyHostToDevice, h->stream));
-    CK(h, cudaMemcpy2DAsync(h->img2.p, cols, img2, stride, cols, rows, cudaMemcpyHostToDevice, h->stream));
-    rc = wsg_run_sgbm(h, (const uint8_t*)h->img1.p, (const uint8_t*)h->img2.p, cols, (int16_t*)h->disp.p);
+    if ((rc = ensure(h, h->img1, npix * n))) return rc;
+    if ((rc = ensure(h, h->img2, npix * n))) return rc;
+    if ((rc = ensure(h, h->disp, npix * n * sizeof(int16_t)))) return rc;
+    std::vector<const uint8_t*> a(n), b(n);
+    std::vector<int16_t*> d(n);
+    for (int f = 0; f < n; ++f) {
+        a[f] = (const uint8_t*)h->img1.p + f * npix; b[f] = (const uint8_t*)h->img2.p + f * npix;
+        d[f] = (int16_t*)h->disp.p + f * npix;
+        CK(h, cudaMemcpy2DAsync((void*)a[f], cols, img1[f], stride, cols, rows, cudaMemcpyHostToDevice, h->stream));
+        CK(h, cudaMemcpy2DAsync((void*)b[f], cols, img2[f], stride, cols, rows, cudaMemcpyHostToDevice, h->stream));
+    }
+    rc = run_sgbm_batch(h, n, a.data(), b.data(), cols, d.data());
     if (rc) return rc;
-    CK(h, cudaMemcpyAsync(disp16, h->disp.p, npix * sizeof(int16_t), cudaMemcpyDeviceToHost, h->stream));
+    for (int f = 0; f < n; ++f)
+        CK(h, cudaMemcpyAsync(disp16[f], d[f], npix * sizeof(int16_t), cudaMemcpyDeviceToHost, h->stream));
     CK(h, cudaStreamSynchronize(h->stream));
     return wsg_check_sweep(h);
 }
@@ -282,9 +347,10 @@ int wsg_sgbm_get_stats(wsg_handle* h, wsg_sgbm_stats* out)
 {
     if (!h || !out) return WSG_ERR_INVALID_ARG;
     if (!h->have_plan) { h->err = "no compute yet"; return WSG_ERR_STATE; }
-    int maxc = 0;
-    CK(h, cudaMemcpyAsync(&maxc, h->scalars.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    std::vector<int> mc(std::max(h->batch_n, 1), 0);
+    CK(h, cudaMemcpyAsync(mc.data(), (int*)h->scalars.p + SCAL_MAXC, mc.size() * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     CK(h, cudaStreamSynchronize(h->stream));
+    const int maxc = *std::max_element(mc.begin(), mc.end());      // over the frames of the last batch
     h->stats.max_cost = maxc;
     h->stats.out_of_domain = (maxc + h->plan.P2 > 32767) ? 1 : 0;
     *out = h->stats;
@@ -305,7 +371,7 @@ int wsg_sgbm_debug_volumes(wsg_handle* h, int16_t* C_host, int16_t* S_host)
     for (int which = 0; which < 2; ++which) {
         int16_t* dst = which ? S_host : C_host;
         if (!dst) continue;
-        CK(h, cudaMemcpyAsync(tmp.data(), which ? h->S.p : h->C.p, tmp.size() * 2, cudaMemcpyDeviceToHost, h->stream));
+        CK(h, cudaMemcpyAsync(tmp.data(), (char*)(which ? h->S.p : h->C.p) + sweep_volume_pad_bytes(), tmp.size() * 2, cudaMemcpyDeviceToHost, h->stream));   // frame 0
         CK(h, cudaStreamSynchronize(h->stream));
         for (size_t px = 0; px < npx; ++px)
             for (int j = 0; j < pl.D / 8; ++j)
@@ -326,7 +392,7 @@ int wsg_sgbm_set_sweep_workers(wsg_handle* h, int max_sms)
 int wsg_sgbm_set_impl(wsg_handle* h, int impl)
 {
     if (!h) return WSG_ERR_INVALID_ARG;
-    if (impl < WSG_AGG_PER_DIRECTION || impl > WSG_AGG_SWEEPS2W_WTA) { h->err = "unknown aggregation implementation"; return WSG_ERR_INVALID_ARG; }
+    if (impl < WSG_AGG_PER_DIRECTION || impl > WSG_AGG_SWEEPS_WTA) { h->err = "unknown aggregation implementation"; return WSG_ERR_INVALID_ARG; }
     h->agg_impl = impl;
     return WSG_OK;
 }

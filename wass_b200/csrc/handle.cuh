@@ -30,7 +30,8 @@ struct wsg_handle {
     int num_sms = 0;
     int sweep_workers = 0;              // cap on the SMs a sweep occupies (0 = all)
     int sweep_epoch = 0;                // 1..3 after the first sweep
-    int bnd_H = 0, bnd_W1 = 0, bnd_K = 0, bnd_nd = 0;   // geometry / state set the hand-off buffer was last used with
+    int bnd_H = 0, bnd_W1 = 0, bnd_K = 0, bnd_n = 0;    // geometry / batch size the hand-off buffer was last used with
+    int batch_n = 1;                    // frames of the last dense-matcher call
     SgbmPlan plan{};
     bool have_plan = false;
     wsg_sgbm_stats stats{};

@@ -47,28 +47,32 @@ bool cost_wide_supported(const SgbmPlan& p);
 void launch_cost_wide(const uint2* pre1, const uint2* pre2, int16_t* C, int* maxC, const SgbmPlan& p, cudaStream_t st);
 
 // fused wavefront sweeps (sweep_kernels.cu)
-static constexpr int WSG_SWEEP_TICKET_INTS = 256;
 struct SweepScratch {
-    void* boundary;             // band-to-band state hand-off, sweep_boundary_bytes()
-    int* ticket;                // zeroed hand-out counters of THIS launch: WSG_SWEEP_TICKET_INTS ints
+    void* boundary;             // band-to-band state hand-off: nframes * sweep_boundary_bytes()
+    int* ticket;                // zeroed hand-out counter of THIS launch
     int max_workers = 0;        // cap on the SMs a sweep occupies (0 = all)
     int num_sms;
-    const int* maxC;            // device scalar: max over the cost volume of this frame
+    const int* maxC;            // device: max over the cost volume of frame f at maxC[f * maxC_stride]
+    int maxC_stride = 1;
     int* err;                   // raised if a bounded wait overran
-    int* dbg;                   // optional [nbands]: SM id per band (WSG_SWEEP_DEBUG=1), else null
+    int* dbg;                   // optional [3 * tickets]: {SM id, start ns, end ns} per band (WSG_SWEEP_DEBUG=1), else null
     int epoch;                  // 1..3, changes with every 4-direction sweep that uses `boundary`
-    int two_warps;              // 1: split every row over two warps (sweep2w_kernel; K == 1, four directions)
-    unsigned long long* keys;   // [H][W] right-view map as packed keys (fused WTA)
-    int16_t* d1;                // [H][W] left-view disparity before the LR check (fused WTA)
+    int nframes = 1;            // frames of the batch: C / S volumes `volume_stride_bytes` apart, keys / d1 H*W apart
+    size_t volume_stride_bytes = 0;
+    unsigned long long* keys;   // [nframes][H][W] right-view map as packed keys (fused WTA)
+    int16_t* d1;                // [nframes][H][W] left-view disparity before the LR check (fused WTA)
 };
 bool sweep_supported(const SgbmPlan& p);
-size_t sweep_boundary_bytes(const SgbmPlan& p);
-// flip 0: directions r0..r3 (top->bottom); flip 1: r4..r7 (bottom->top).  mode 0: S = sum L (write only);
-// 1: S += sum L;  2: S += sum L, then winner-take-all into sc.keys / sc.d1 (S is not written).
-// ndir 4: all four directions of the sweep;  1: the horizontal one only (fifth path of MODE_SGBM).
+int sweep_rows_per_band(const SgbmPlan& p);
+size_t sweep_boundary_bytes(const SgbmPlan& p);      // per frame
+size_t sweep_volume_pad_bytes();                     // the C / S volumes must be readable this far beyond either end
+// One launch over the bands of all `sc.nframes` frames.  flip 0: directions r0..r3 (top->bottom); flip 1: r4..r7
+// (bottom->top).  mode 0: S = sum L (write only); 1: S += sum L;  2: S += sum L, then winner-take-all into
+// sc.keys / sc.d1 (S is not written).  ndir 4: all four directions of the sweep;  1: the horizontal one only (fifth
+// path of MODE_SGBM).
 void launch_sweep(const int16_t* C, int16_t* S, int flip, int mode, int ndir, const SgbmPlan& p, const SweepScratch& sc,
                   cudaStream_t st);
 void launch_wta_reset(const SweepScratch& sc, const SgbmPlan& p, cudaStream_t st);
-void launch_lrcheck(const SweepScratch& sc, int16_t* raw, const SgbmPlan& p, cudaStream_t st);
+void launch_lrcheck(const SweepScratch& sc, int frame, int16_t* raw, const SgbmPlan& p, cudaStream_t st);
 
 }  // namespace wsg

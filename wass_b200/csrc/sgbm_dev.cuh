@@ -99,11 +99,20 @@ __device__ __forceinline__ void agg_step(unsigned (&R)[NR], const unsigned (&Cw)
     unsigned m = v[0];
 #pragma unroll
     for (int j = 1; j < NR; ++j) m = __vmins2(m, v[j]);
-    unsigned mm = min(m & 0xFFFFu, m >> 16);
-    mm = group_min_u32<NL>(mm);
-    const unsigned mpk = mm * 0x10001u;
+    unsigned mpk;
+    if constexpr (NL == 32) {
+        // both halves := min of the two halves; values are 0..32767, so the warp minimum of the packed words as unsigned
+        // 32-bit numbers is the packed minimum (one REDUX, no unpack / repack)
+        m = __vmins2(m, __byte_perm(m, m, 0x1032));
+        mpk = __reduce_min_sync(FULL, m);
+    } else {
+        unsigned mm = min(m & 0xFFFFu, m >> 16);
+        mm = group_min_u32<NL>(mm);
+        mpk = mm * 0x10001u;
+    }
+    const unsigned minus_one = 0u - one;     // opaque like `one`: the subtraction is issued as IMAD on the FMA pipe
 #pragma unroll
-    for (int j = 0; j < NR; ++j) R[j] = v[j] - mpk;  // both halves >= mm: no borrow between them
+    for (int j = 0; j < NR; ++j) R[j] = add_on_fma(mpk, v[j], minus_one);  // v - mpk; both halves >= min: no borrow between them
 }
 
 }  // namespace wsg
