@@ -3,12 +3,12 @@
 
 Metric (BASELINE.json): Mdisparities/s (output disparity pixels W*H per second) on
 2448x2048 pairs with 256 disparities, full 8-path SGM (cv::StereoSGBM MODE_HH arithmetic),
-WASS default matcher parameters.  One "step" = one rectified stereo pair through the dense matcher
-(prefilter -> cost volume -> 8-path aggregation -> WTA/LR/sub-pixel -> 3x3 median).
+WASS default matcher parameters.  One "step" = one BATCH of rectified stereo pairs (--batch, default 8 per GPU) through the dense matcher
+(prefilter -> cost volume -> 8-path aggregation -> WTA/LR/sub-pixel -> 3x3 median): one wsg_sgbm_compute_batch call.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
 
-N>1 is launched by the driver through torch.distributed.run (one rank per GPU); frames shard one per
+N>1 is launched by the driver through torch.distributed.run (one rank per GPU); frames shard one batch per
 rank with no data-path collective (weak scaling).  Prints ONE JSON line on rank 0.
 """
 import argparse
@@ -137,11 +137,12 @@ def cpu_baseline_single(rows=2048):
     r, l, _ = synth.make_pair(W_IMG, rows, NDISP, seed=0)
     i1, i2 = synth.pad_for_sgbm(r, l, NDISP)
     t = time.perf_counter()
-    _, what = _cpu_sgbm(i1, i2, wass_params(NDISP, 1))
+    disp, what = _cpu_sgbm(i1, i2, wass_params(NDISP, 1))
     dt = time.perf_counter() - t
     return {"value": W_IMG * rows / dt / 1e6, "unit": "Mdisp/s", "cores": 1, "kind": "port",
-            "sample": "one %dx%d band (D=256, MODE_HH) of the benchmark frame through %s, the routine "
-                      "wass_stereo.cpp:837 calls; %.1f s" % (W_IMG, rows, what, dt)}
+            "sample": "the whole %dx%d benchmark frame of seed 0 (D=256, MODE_HH) through %s, the routine "
+                      "wass_stereo.cpp:837 calls; %.1f s; its disparity is the parity check of the GPU result" % (W_IMG, rows, what, dt)}, \
+        (disp if rows == H_IMG else None)
 
 
 def run_reference(args, rank):
@@ -163,7 +164,10 @@ def run_reference(args, rank):
     line = {"impl": "reference", "metric": "Mdisparities/s", "value": value, "unit": "Mdisp/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "s16", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "sample": sample},
+            "config": {"workload": WORKLOAD, "sample": sample, "frames_per_step_per_gpu": None, "handles_in_flight_per_gpu": None,
+                       "single_frame_ms": None, "padded_width": W_IMG + NDISP, "W1": W_IMG - 1, "l2": None,
+                       "parallelism": "%d host processes" % P, "generator": "as the GPU arm (wass_b200/synth.py)",
+                       "max_cost": None, "out_of_domain": None},
             "cpu_baseline": {"value": value, "unit": "Mdisp/s", "cores": P, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "Mdisp/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -173,6 +177,36 @@ def run_reference(args, rank):
 # --------------------------------------------------------------------------------------------------
 # GPU arm
 # --------------------------------------------------------------------------------------------------
+def _sha(*arrays):
+    import hashlib
+    h = hashlib.sha256()
+    for a in arrays:
+        a = np.ascontiguousarray(a)
+        h.update(str(a.shape).encode() + str(a.dtype).encode())
+        h.update(a.tobytes())
+    return h.hexdigest()
+
+
+def pinned_hashes():
+    """tests/golden/fullsize_hashes.json: SHA-256 of the cv2.StereoSGBM disparity of the benchmark frames (seeds 0..2),
+    made in the build container by tests/golden/make_fullsize_hashes.py."""
+    try:
+        with open(os.path.join(ROOT, "tests", "golden", "fullsize_hashes.json")) as f:
+            j = json.load(f)
+        return {c["seed"]: c for n, c in j["cases"].items() if n.startswith("bench_frame_seed")}, j.get("cv2")
+    except Exception:
+        return {}, None
+
+
+def synthetic_plane(frame):
+    """Stand-in per-frame sea plane for the plane-reduction leg of the multi-GPU run (the dense matcher alone fits no
+    plane; tools/bench_sequence.py runs the whole frame pipeline with real fits).  Every 7th frame is a RANSAC failure."""
+    if frame % 7 == 3:
+        return [float("nan")] * 4
+    th = 0.4 + 1e-3 * frame
+    return [0.01 * np.sin(frame), np.sin(th), np.cos(th), -(8.0 + 0.01 * frame)]
+
+
 def run_ours(args, rank, world):
     import torch
     import torch.distributed as dist
@@ -180,55 +214,51 @@ def run_ours(args, rank, world):
 
     local = int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
     p = wass_params(NDISP, capi.MODE_HH)
-    depth = max(1, args.pipeline_depth)
-    frames = [make_frame(depth * rank + i) for i in range(depth)]      # frames shard across GPUs, `depth` in flight per GPU
+    B, NH = max(1, args.batch), max(1, args.streams)
+    # frames shard across GPUs: rank r owns seeds r*B .. r*B+B-1 (every handle of the rank works on the same B frames)
+    seeds = [rank * B + i for i in range(B)]
+    frames = [make_frame(s) for s in seeds]
     H, Wp = frames[0][0].shape
-    # One handle (= one device arena + one CUDA stream) per frame in flight.  The library launches on dedicated
-    # (non-default) torch streams; torch events on a third stream bracket the timed region.
     main = torch.cuda.Stream()
     torch.cuda.set_stream(main)
-    hs, streams, dev, pin = [], [], [], []
-    for i in range(depth):
+    i1 = torch.from_numpy(np.stack([f[0] for f in frames])).cuda()
+    i2 = torch.from_numpy(np.stack([f[1] for f in frames])).cuda()
+    hs, streams, dev_out, pin = [], [], [], []
+    for k in range(NH):      # one handle = one device arena (B cost + B aggregated volumes) + one CUDA stream
         h = capi.Handle(local)
         if args.agg_impl >= 0:
             h.sgbm_set_impl(args.agg_impl)
         st = torch.cuda.Stream()
         h.set_stream(st.cuda_stream)
         hs.append(h); streams.append(st)
-        i1, i2 = frames[i]
-        dev.append((torch.from_numpy(i1).cuda(), torch.from_numpy(i2).cuda(),
-                    torch.empty((H, Wp), dtype=torch.int16, device="cuda")))
-        pin.append((torch.from_numpy(i1).pin_memory(), torch.from_numpy(i2).pin_memory(),
-                    torch.empty((H, Wp), dtype=torch.int16).pin_memory()))
+        dev_out.append(torch.empty((B, H, Wp), dtype=torch.int16, device="cuda"))
+        pin.append(([torch.from_numpy(f[0]).pin_memory() for f in frames], [torch.from_numpy(f[1]).pin_memory() for f in frames],
+                    [torch.empty((H, Wp), dtype=torch.int16).pin_memory() for _ in frames]))
     torch.cuda.synchronize()
 
-    def step_dev(i):
-        d1, d2, dd = dev[i]
-        hs[i].sgbm_compute_device(d1.data_ptr(), d2.data_ptr(), H, Wp, Wp, p, dd.data_ptr())
+    def step_dev(k):         # one step = one batch of B frames, device-resident inputs and outputs
+        hs[k].sgbm_compute_batch_device(B, i1.data_ptr(), i2.data_ptr(), H * Wp, H, Wp, Wp, p, dev_out[k].data_ptr())
 
-    def step_e2e(i):
-        p1, p2, pd = pin[i]
-        hs[i].sgbm_compute_ptr(p1.data_ptr(), p2.data_ptr(), H, Wp, Wp, p, pd.data_ptr())
+    def step_e2e(k):         # the same through the host-buffer entry point: H2D + kernels + D2H, returns when the result is there
+        a, b, d = pin[k]
+        hs[k].sgbm_compute_batch_ptr(B, [t.data_ptr() for t in a], [t.data_ptr() for t in b], H, Wp, Wp, p, [t.data_ptr() for t in d])
 
-    def timed_device(nsteps, nstreams):
-        """nsteps frames, frame k on handle k % nstreams; device time between two events on `main`."""
+    def timed_device(nsteps, nh):
+        """nsteps batches, batch j on handle j % nh; device time between two events on `main`."""
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
         e0.record(main)
-        for st in streams[:nstreams]:
+        for st in streams[:nh]:
             st.wait_event(e0)
-        for k in range(nsteps):
-            step_dev(k % nstreams)
-        for st in streams[:nstreams]:
+        for j in range(nsteps):
+            step_dev(j % nh)
+        for st in streams[:nh]:
             ev = torch.cuda.Event()
             ev.record(st)
             main.wait_event(ev)
@@ -236,50 +266,66 @@ def run_ours(args, rank, world):
         barrier()
         return e0.elapsed_time(e1)
 
-    # ---- warm-up, then the per-stage profile of ONE frame at a time (kernels timed alone: roofline numbers)
     sampler = ClockSampler(local)          # clocks are sampled from the warm-up to the end of the e2e leg
     if rank == 0:
         sampler.start()
-    for _ in range(max(args.warmup, 3)):
-        for i in range(depth):
-            step_dev(i)
+    warm = max(args.warmup, 3)
+    for _ in range(warm):
+        for k in range(NH):
+            step_dev(k)
     barrier()
+    # ---- per-stage profile, ONE batch at a time on one stream: every kernel timed alone (the roofline numbers)
+    prof_steps = max(2, min(args.steps, 5))
     hs[0].profile_enable(True)
     hs[0].profile_reset()
-    ms_serial = timed_device(args.steps, 1)
+    ms_serial = timed_device(prof_steps, 1)
     prof = hs[0].profile_get()
     hs[0].profile_enable(False)
     stats = hs[0].sgbm_stats()
+    # one frame at a time, for the latency figure
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    hs[0].sgbm_compute_batch_device(1, i1.data_ptr(), i2.data_ptr(), H * Wp, H, Wp, Wp, p, dev_out[0].data_ptr())
+    hs[0].synchronize()
+    e0.record(streams[0])
+    for _ in range(3):
+        hs[0].sgbm_compute_batch_device(1, i1.data_ptr(), i2.data_ptr(), H * Wp, H, Wp, Wp, p, dev_out[0].data_ptr())
+    e1.record(streams[0])
+    hs[0].synchronize()
+    ms_single = e0.elapsed_time(e1) / 3
+    step_dev(0)
 
-    # ---- device-resident throughput ("value"): `depth` frames in flight on as many streams.  With three or more in
-    #      flight each sweep is confined to half the SMs (wsg_sgbm_set_sweep_workers): a wavefront over H/7 row bands
-    #      leaves ~40 % of 148 workers waiting, so two frames' sweeps side by side move more pixels than one after the other.
-    nsm = torch.cuda.get_device_properties(local).multi_processor_count
-    workers = args.sweep_workers if args.sweep_workers >= 0 else (nsm // 2 if depth >= 3 else 0)
-    for h in hs:
-        h.sgbm_set_sweep_workers(workers)
-    for i in range(depth):
-        step_dev(i)
-    ms_dev = timed_device(args.steps, depth)
+    # ---- device-resident throughput ("value"): K batches over NH handles / streams
+    for k in range(NH):
+        step_dev(k)
+    ms_dev = timed_device(args.steps, NH)
 
-    # ---- end to end through the C ABI with HOST buffers (pinned): H2D + kernels + D2H per step, one host thread per
-    #      frame in flight (the call is synchronous and releases the GIL)
-    def e2e_worker(i, n):
+    # ---- end to end through the C ABI with HOST buffers (pinned): one host thread per handle (the call is synchronous
+    #      and releases the GIL), so the copies of one batch overlap the kernels of the other
+    def e2e_worker(k, n):
         torch.cuda.set_device(local)
         for _ in range(n):
-            step_e2e(i)
+            step_e2e(k)
 
     def run_e2e(nsteps):
-        ths = [threading.Thread(target=e2e_worker, args=(i, len(range(i, nsteps, depth)))) for i in range(depth)]
+        ths = [threading.Thread(target=e2e_worker, args=(k, len(range(k, nsteps, NH)))) for k in range(NH)]
         for t_ in ths:
             t_.start()
         for t_ in ths:
             t_.join()
 
-    run_e2e(2 * depth)
+    run_e2e(NH)
     barrier()
     t0 = time.perf_counter()
     run_e2e(args.steps)
+    # multi-GPU: the one collective of the path -- the NaN-aware mean of the per-frame planes -- inside the timed region,
+    # through the C ABI (wsg_plane_allreduce: ncclAllReduce over NVLink).  The matcher alone fits no planes: synthetic ones.
+    plane_info = None
+    if world > 1:
+        tp = time.perf_counter()
+        mine = [synthetic_plane(rank * args.steps * B + j) for j in range(args.steps * B)]
+        _, acc = capi.plane_mean(mine)
+        mean, nfr = hs[0].plane_allreduce(comm_holder["comm"], acc)
+        plane_info = {"ms": (time.perf_counter() - tp) * 1e3, "mean": mean, "frames": nfr}
     torch.cuda.synchronize()
     ms_e2e = (time.perf_counter() - t0) * 1e3
     clocks = sampler.stop() if rank == 0 else None
@@ -289,64 +335,112 @@ def run_ours(args, rank, world):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_dev, ms_e2e = float(t[0]), float(t[1])
 
-    # cross-check of the two paths on this rank (bit-exact), every frame in flight
-    same = all(bool(torch.equal(dev[i][2].cpu(), pin[i][2])) for i in range(depth))
+    # ---- parity on the frames that were timed: device path == host path, and both == cv2
+    outs = [pin[0][2][i].numpy() for i in range(B)]
+    same = all(bool(torch.equal(dev_out[k][i].cpu(), pin[k][2][i])) for k in range(NH) for i in range(B))
 
     if rank == 0:
         px = W_IMG * H_IMG
-        value = world * args.steps * px / (ms_dev * 1e-3) / 1e6
-        e2e = world * args.steps * px / (ms_e2e * 1e-3) / 1e6
+        value = world * args.steps * B * px / (ms_dev * 1e-3) / 1e6
+        e2e = world * args.steps * B * px / (ms_e2e * 1e-3) / 1e6
         V = stats["volume_bytes"]
+        nfr_prof = prof_steps * B
         agg_ms, agg_launches = prof["aggregate"]
-        agg_ms_per_frame = agg_ms / args.steps
+        agg_ms_per_frame = agg_ms / nfr_prof
         peak, peak_src = measured_peak_gbs()
         alg_bytes = 4.0 * V                       # aggregation sweeps alone = 4*V per frame
         achieved = alg_bytes / (agg_ms_per_frame * 1e-3) / 1e9
         impl = stats["agg_impl"]
-        wta_ms = prof["wta"][0] / args.steps
         if impl == 0:      # 8 single-direction launches (first 2V, others 3V); separate WTA reads V
-            phys_bytes, kname = (2 + 3 * 7) * V, "aggregate_kernel (8 launches/frame)"
+            phys_bytes, kname, nlaunch = (2 + 3 * 7) * V, "aggregate_kernel (8 launches per frame)", 8.0 * B
         elif impl == 1:    # sweep 1: read C, write S; sweep 2: read C, read S, write S; separate WTA reads V
-            phys_bytes, kname = 5 * V, "sweep_kernel (2 launches/frame), S written, separate WTA"
-        elif impl in (2, 4):   # sweep 1: read C, write S; sweep 2: read C, read S, WTA inside
-            phys_bytes, kname = 4 * V, "sweep_kernel (2 launches/frame), WTA fused into the second"
-        else:              # 3-direction sweeps (2V, 2V) + two per-direction launches for the anti-diagonals (3V each)
-            phys_bytes, kname = 10 * V, "sweep_kernel<NDIR=3> x2 + aggregate_kernel x2 (anti-diagonals), WTA fused into the last sweep"
-        nlaunch = 2.0                             # sweep launches per frame (the reset kernel in the stage is ~13 us)
+            phys_bytes, kname, nlaunch = 5 * V, "sweep_kernel (2 launches per batch), S written, separate WTA", 2.0
+        else:              # sweep 1: read C, write S; sweep 2: read C, read S, WTA inside
+            phys_bytes, kname, nlaunch = 4 * V, "sweep_kernel (2 launches per batch of %d frames), WTA fused into the second" % B, 2.0
         traffic, traffic_src = ncu_traffic() if impl >= 2 else (None, None)
+        # parity block
+        pins, cv2ver = pinned_hashes()
+        checked, mism, how = 0, 0, []
+        for i, s in enumerate(seeds):
+            c = pins.get(s)
+            if c and _sha(frames[i][0], frames[i][1]) == c["inputs_sha256"]:
+                checked += outs[i].size
+                mism += 0 if _sha(outs[i]) == c["disp_sha256"] else outs[i].size
+                how.append("seed %d: sha256 of cv2 %s output (tests/golden/fullsize_hashes.json)" % (s, cv2ver))
+        cpu = None
+        if world == 1 and not args.no_cpu:
+            cpu, cpu_disp = cpu_baseline_single()
+            if cpu_disp is not None:
+                checked += cpu_disp.size
+                mism += int((cpu_disp != outs[0]).sum())
+                how.append("seed 0: every pixel against the cv2 run of cpu_baseline (same process, same frame)")
+        parity = {"pixels": checked, "mismatches": mism, "against": "; ".join(how) if how else "nothing available",
+                  "device_vs_host_path_bit_exact": same}
         line = {
             "metric": "Mdisparities/s", "value": value, "unit": "Mdisp/s", "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak",
+            "warmup": warm, "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "s16", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "frames_per_step_per_gpu": 1, "frames_in_flight_per_gpu": depth,
-                       "sms_per_sweep_when_pipelined": workers if workers > 0 else nsm,
-                       "single_frame_ms": ms_serial / args.steps, "padded_width": Wp, "W1": stats["width1"],
-                       "l2": "inputs larger than L2 (C and S volumes %.2f GB each)" % (V / 1e9),
-                       "parallelism": "frame-per-GPU x%d" % world, "device_vs_e2e_bit_exact": same,
+            "config": {"workload": WORKLOAD,
+                       "sample": "each step = one batch of %d whole frames per GPU through wsg_sgbm_compute_batch (seeds %d..%d on rank 0)" % (B, seeds[0], seeds[-1]),
+                       "frames_per_step_per_gpu": B, "handles_in_flight_per_gpu": NH,
+                       "single_frame_ms": ms_single, "padded_width": Wp, "W1": stats["width1"],
+                       "l2": "inputs larger than L2 (C and S volumes %.2f GB each per frame, %d frames per batch)" % (V / 1e9, B),
+                       "parallelism": "frame-per-GPU x%d" % world,
+                       "generator": "grey range [80,176), noise sigma 2 (wass_b200/synth.py): softened from SURVEY 8d's full-range "
+                                    "texture so that max(C)+P2 <= 32767, the domain in which cv2 is reproduced bit for bit",
                        "max_cost": stats["max_cost"], "out_of_domain": stats["out_of_domain"]},
+            "parity": parity,
             "roofline": {"bound": "hbm", "kernel": kname, "agg_impl": impl, "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
-                         "peak_source": peak_src, "bound_note": "the sweeps are integer-ALU bound, not HBM bound (DESIGN.md section 4); "
+                         "peak_source": peak_src, "bound_note": "the sweeps are integer-ALU / issue bound, not HBM bound (DESIGN.md section 4); "
                          "frac is the HBM-roofline fraction BASELINE.json asks for",
-                         "algorithmic_bytes_per_launch": alg_bytes / nlaunch if impl != 0 else alg_bytes / 8,
-                         "ms_per_launch": agg_ms_per_frame / (nlaunch if impl != 0 else 8),
+                         "algorithmic_bytes_per_launch": alg_bytes * B / nlaunch,
+                         "ms_per_launch": agg_ms_per_frame * B / nlaunch,
                          "algorithmic_bytes_per_frame": alg_bytes, "ms_per_frame": agg_ms_per_frame,
-                         "launches_per_frame": agg_launches / args.steps,
+                         "frames_per_launch": B, "launches_per_batch": agg_launches / prof_steps,
                          "moved_bytes_per_frame_this_build": phys_bytes,
-                         "moved_gbs": phys_bytes / (agg_ms_per_frame * 1e-3) / 1e9},
-            "stage_ms_per_frame": {k: v[0] / args.steps for k, v in prof.items() if v[1]},
-            "e2e": {"value": e2e, "unit": "Mdisp/s", "h2d_bytes_per_step": 2 * H * Wp, "d2h_bytes_per_step": 2 * H * Wp,
+                         "timed": "CUDA events on the handle's stream around the sweep launches of %d batches run one at a time" % prof_steps},
+            "stage_ms_per_frame": {k: v[0] / nfr_prof for k, v in prof.items() if v[1]},
+            "batch_ms_one_at_a_time": ms_serial / prof_steps,
+            "e2e": {"value": e2e, "unit": "Mdisp/s", "h2d_bytes_per_step": 2 * H * Wp * B, "d2h_bytes_per_step": 2 * H * Wp * B,
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": stats["kernel_launches"] * args.steps,
             "clocks": clocks,
         }
-        if world == 1 and not args.no_cpu:
-            line["cpu_baseline"] = cpu_baseline_single()
+        if plane_info is not None:
+            allp = np.array([synthetic_plane(j) for j in range(world * args.steps * B)])
+            ref = np.nanmean(allp, axis=0)
+            line["plane_reduction"] = {"collective": "ncclAllReduce(sum, 5 x f64) through wsg_plane_allreduce, inside the e2e timed region",
+                                       "frames": plane_info["frames"], "ms": plane_info["ms"],
+                                       "max_abs_err_vs_numpy_nanmean": float(np.abs(plane_info["mean"] - ref).max()),
+                                       "planes": "synthetic (the matcher alone fits none; tools/bench_sequence.py runs the whole frame pipeline)"}
+            assert line["plane_reduction"]["max_abs_err_vs_numpy_nanmean"] < 1e-12 and plane_info["frames"] == int(np.isfinite(allp[:, 0]).sum())
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
         print(json.dumps(line), flush=True)
+        if mism or not same:
+            raise SystemExit("PARITY FAILURE: %d of %d pixels differ from cv2 (device==host path: %s)" % (mism, checked, same))
     for h in hs:
         h.close()
     if world > 1:
+        comm_holder["comm"].close()
         dist.destroy_process_group()
+
+
+comm_holder = {}
+
+
+def setup_comm(rank, world):
+    """The library's own NCCL communicator (wsg_nccl_comm_create): rank 0's unique id travels over torch.distributed."""
+    import torch
+    import torch.distributed as dist
+    from wass_b200 import capi
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    uid = torch.zeros(capi.NCCL_UNIQUE_ID_BYTES, dtype=torch.uint8, device="cuda")
+    if rank == 0:
+        uid = torch.frombuffer(bytearray(capi.nccl_unique_id()), dtype=torch.uint8).cuda()
+    dist.broadcast(uid, 0)
+    comm_holder["comm"] = capi.NcclComm(local, world, rank, bytes(uid.cpu().numpy().tobytes()))
 
 
 def main():
@@ -356,19 +450,22 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--pipeline-depth", type=int, default=3,
-                    help="frames in flight per GPU (one handle + stream each); 1 = one frame at a time")
-    ap.add_argument("--sweep-workers", type=int, default=-1,
-                    help="SMs per fused sweep while frames are pipelined (0 = all; -1 = half the SMs when 3+ frames are in flight)")
-    ap.add_argument("--agg-impl", type=int, default=-1, choices=[-1, 0, 1, 2, 3, 4],
-                    help="-1 library default, 0 per-direction launches, 1 fused sweeps, 2 fused sweeps + fused WTA, "
-                         "3 three-direction sweeps + anti-diagonal launches + fused WTA")
+    ap.add_argument("--batch", type=int, default=8, help="frames per step and GPU (one wsg_sgbm_compute_batch call)")
+    ap.add_argument("--streams", type=int, default=2, help="handles (arena + stream) the batches alternate over per GPU")
+    ap.add_argument("--agg-impl", type=int, default=-1, choices=[-1, 0, 1, 2],
+                    help="-1 library default, 0 per-direction launches, 1 fused sweeps, 2 fused sweeps + fused WTA")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
     if args.impl == "reference":
         run_reference(args, rank)
     else:
+        if world > 1:
+            import torch
+            import torch.distributed as dist
+            torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", 0)))
+            dist.init_process_group("nccl", device_id=torch.device("cuda", int(os.environ.get("LOCAL_RANK", 0))))
+            setup_comm(rank, world)
         run_ours(args, rank, world)
 
 

@@ -151,6 +151,13 @@ void wsg_dense_params_default(wsg_dense_params* p);
  * matcher output cropped to the ROI, int16 x16. */
 int wsg_dense_stereo(wsg_handle* h, const uint8_t* left_crop, const uint8_t* right_crop, int rows, int cols,
                      size_t stride, const wsg_dense_params* p, float* disp_roi, int16_t* disp16_roi);
+/* Batch form (the form a sequence driver uses): n pairs of crops of one size; ONE batched matcher run underneath
+ * (wsg_sgbm_compute_batch).  The float ROI disparity of every frame stays on the device; disp_roi may be NULL or hold
+ * NULLs.  wsg_dense_select(h, f) makes frame f the current dense result, i.e. what wsg_triangulate_from_dense reads. */
+int wsg_dense_stereo_batch(wsg_handle* h, int n, const uint8_t* const* left_crops, const uint8_t* const* right_crops, int rows,
+                           int cols, size_t stride, const wsg_dense_params* p, float* const* disp_roi);
+int wsg_dense_select(wsg_handle* h, int frame);
+
 
 /* Size of the matcher's input for a rows x cols crop (wass_stereo.cpp:788-797): x is scaled when DENSE_SCALE > 1, both
  * axes when < 1; lengths are cv::resize's saturate_cast<int>(n * scale).  With DENSE_SCALE != 1 wsg_dense_stereo's
@@ -241,8 +248,9 @@ int wsg_mesh_biggest_component(wsg_handle* h, double zgap, unsigned long long* n
  * best hypothesis has fewer than width*height/10 inliers. */
 int wsg_mesh_ransac_plane(wsg_handle* h, const int32_t* triples, int n, double threshold, double plane[4], int* ok,
                           unsigned long long* best_inliers);
-/* The draw loop of PovMesh.cpp:678-692 with a defined argument order (u before v, points 1,2,3 in order):
- * consumes libc rand(); rounds whose points are closer than 0.01*height are redrawn. Host only. */
+/* The draw loop of PovMesh.cpp:678-692: consumes libc rand(); rounds whose points are closer than 0.01*height are
+ * redrawn.  Per point v is drawn before u, points 1,2,3 in order: the order a GCC build of the reference produces
+ * (constructor arguments, right to left) -- pinned against the reference's own code with a fixed RANDOM_SEED. Host only. */
 int wsg_ransac_draw(int width, int height, int rounds, int32_t* triples);
 /* PovMesh::crop_plane, PovMesh.cpp:780-815 */
 int wsg_mesh_crop_plane(wsg_handle* h, const double plane[4], double threshold, unsigned long long* n_left);
@@ -316,6 +324,21 @@ int wsg_rectify_image(wsg_handle* h, const uint8_t* img, int rows, int cols, siz
  * and the count; all-reduce acc (sum) across ranks, then wsg_plane_mean_finish. Host only. */
 void wsg_plane_mean_accumulate(double acc[5], const double plane[4]);
 void wsg_plane_mean_finish(const double acc[5], double mean[4]);
+
+/* The same reduction across the ranks of a multi-GPU run (one process per GPU, frames sharded over ranks): ONE
+ * ncclAllReduce(sum) over the 5 doubles of `acc` on the handle's stream, over NVLink / NVSwitch; mean[4] is the
+ * sequence mean plane on every rank (NaN when no frame had a plane), *frames the number of planes in it.
+ * nccl_comm is an ncclComm_t the caller created (its own ncclCommInitRank, or wsg_nccl_comm_create).  NCCL is bound at
+ * run time (dlopen "libnccl.so.2"): libwassgpu.so does not link it.
+ * wsg_plane_allgather: every rank's n_local per-frame planes in rank order (all: nranks x n_local x 4), for an
+ * ORDERED planes.txt (the reference appends in completion order, cli/wasscli/wasscli.py:343). */
+#define WSG_NCCL_UNIQUE_ID_BYTES 128
+int wsg_nccl_unique_id(unsigned char id[WSG_NCCL_UNIQUE_ID_BYTES]);           /* rank 0; hand the bytes to the other ranks */
+int wsg_nccl_comm_create(int device, int nranks, int rank, const unsigned char id[WSG_NCCL_UNIQUE_ID_BYTES], void** comm);
+void wsg_nccl_comm_destroy(void* comm);
+int wsg_plane_allreduce(wsg_handle* h, void* nccl_comm, const double acc[5], double mean[4], long long* frames);
+int wsg_plane_allgather(wsg_handle* h, void* nccl_comm, int nranks, const double* planes, int n_local, double* all);
+const char* wsg_collective_last_error(void);                                  /* for the handle-less calls above */
 
 /* Per-stage device timing (CUDA events on the handle's stream).  enable!=0 turns recording on.
  * Stage ids: see WSG_STAGE_*.  ms[i] receives the accumulated milliseconds of stage i and

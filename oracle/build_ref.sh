@@ -14,3 +14,12 @@ awk '/^#ifdef WASS_ENABLE_OPTFLOW/ {skip=1} /^#endif/ {if (skip) {skip=0; next}}
     "$REF/src/wass_stereo/wass_stereo.cpp" "$REF/src/wass_stereo/PovMesh.cpp" > "$HERE/_ref/keys.inc"
 g++ -O1 -std=c++14 -I"$REF/ext/incfg" -I"$HERE/_ref" "$HERE/incfg_ref_driver.cpp" "$REF/ext/incfg/incfg.cpp" -o "$HERE/_ref/incfg_ref"
 echo "$HERE/_ref/incfg_ref"
+
+# oracle/_ref/povmesh_ref: the reference's OWN mesh stage -- src/wass_stereo/PovMesh.cpp (z-gap percentile, biggest
+# connected component, RANSAC plane, plane refinement, crops, the .xyzC / .xyzbin / PLY writers) and
+# src/wass_lib/triangulate.hpp -- unmodified, compiled where they lie, against the header shim in oracle/shim/ (the image
+# has no OpenCV C++ / Boost headers) and the reference's own ext/incfg.  It pins oracle/pipeline.py
+# (tests/golden/make_povmesh_golden.py -> tests/golden/povmesh_golden.npz -> tests/test_oracle_pipeline.py).
+g++ -O1 -std=c++17 -w -I"$HERE/shim" -I"$REF/src/include" -I"$REF/ext/incfg" -I"$REF/src/wass_stereo" -I"$REF/src/wass_lib" \
+    "$HERE/povmesh_ref_driver.cpp" "$REF/ext/incfg/incfg.cpp" -o "$HERE/_ref/povmesh_ref"
+echo "$HERE/_ref/povmesh_ref"

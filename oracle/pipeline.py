@@ -629,15 +629,20 @@ class LibcRand:
 
 
 def ransac_draw_triples(rng, W, H, rounds):
-    """The draw loop of PovMesh.cpp:678-692 with a DEFINED order (u then v, p1,p2,p3 left to right);
-    the reference's order inside constructor arguments is unspecified by C++.
+    """The draw loop of PovMesh.cpp:678-692.  `cv::Vec2i p(rand()%iW, rand()%iH)` leaves the order of the two calls to
+    the compiler; GCC evaluates constructor arguments right to left, so a Linux build of the reference
+    draws v BEFORE u (points 1, 2, 3 in statement order).  Pinned: tests/golden/povmesh_golden.npz holds planes from the
+    reference's own PovMesh.cpp built with GCC and a fixed seed, and only this order reproduces them.
     Returns int32 [rounds][6] pixel coordinates (u1,v1,u2,v2,u3,v3) of the rounds that pass the
     minimum-distance test (each consumes one round)."""
     out = np.zeros((rounds, 6), np.int32)
     mind = H * 0.01
     r = 0
     while r < rounds:
-        c = [rng.rand() % W, rng.rand() % H, rng.rand() % W, rng.rand() % H, rng.rand() % W, rng.rand() % H]
+        c = [0] * 6
+        for k in range(3):
+            c[2 * k + 1] = rng.rand() % H
+            c[2 * k] = rng.rand() % W
         d12 = np.hypot(c[0] - c[2], c[1] - c[3])
         d23 = np.hypot(c[2] - c[4], c[3] - c[5])
         d13 = np.hypot(c[0] - c[4], c[1] - c[5])

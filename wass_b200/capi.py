@@ -133,6 +133,9 @@ def load():
     lib.wsg_refine_params_default.argtypes = [ctypes.POINTER(RefineParams)]
     lib.wsg_refine_params_default.restype = None
     lib.wsg_dense_stereo.argtypes = [vp, vp, vp, ci, ci, sz, ctypes.POINTER(DenseParams), vp, vp]
+    lib.wsg_dense_stereo_batch.argtypes = [vp, ci, ctypes.POINTER(vp), ctypes.POINTER(vp), ci, ci, sz, ctypes.POINTER(DenseParams),
+                                           ctypes.POINTER(vp)]
+    lib.wsg_dense_select.argtypes = [vp, ci]
     lib.wsg_disparity_postprocess.argtypes = [vp, vp, ci, ci, ci, ci, ci, ctypes.c_double, ci, ci, vp]
     lib.wsg_disparity_postprocess_resized.argtypes = [vp, vp, ci, ci, ci, ci, ci, ctypes.c_double, ci, ci, vp, ci, ci]
     lib.wsg_dense_scaled_size.argtypes = [ci, ci, ctypes.c_double, ctypes.POINTER(ci), ctypes.POINTER(ci)]
@@ -169,6 +172,13 @@ def load():
     lib.wsg_plane_mean_accumulate.restype = None
     lib.wsg_plane_mean_finish.argtypes = [dp, dp]
     lib.wsg_plane_mean_finish.restype = None
+    lib.wsg_nccl_unique_id.argtypes = [ctypes.c_char_p]
+    lib.wsg_nccl_comm_create.argtypes = [ci, ci, ci, ctypes.c_char_p, ctypes.POINTER(vp)]
+    lib.wsg_nccl_comm_destroy.argtypes = [vp]
+    lib.wsg_nccl_comm_destroy.restype = None
+    lib.wsg_plane_allreduce.argtypes = [vp, vp, dp, dp, ctypes.POINTER(ctypes.c_longlong)]
+    lib.wsg_plane_allgather.argtypes = [vp, vp, ci, dp, ci, dp]
+    lib.wsg_collective_last_error.restype = ctypes.c_char_p
     _lib = lib
     return lib
 
@@ -256,6 +266,35 @@ def _d4(a):
     return (ctypes.c_double * 4)(*[float(v) for v in a])
 
 
+NCCL_UNIQUE_ID_BYTES = 128
+
+
+def nccl_unique_id():
+    """128 bytes from ncclGetUniqueId (rank 0 calls this and hands them to the other ranks)."""
+    buf = ctypes.create_string_buffer(NCCL_UNIQUE_ID_BYTES)
+    rc = load().wsg_nccl_unique_id(buf)
+    if rc != 0:
+        raise WsgError(rc, load().wsg_collective_last_error().decode())
+    return buf.raw
+
+
+class NcclComm:
+    """An NCCL communicator owned through the C ABI (wsg_nccl_comm_create): one rank per GPU."""
+
+    def __init__(self, device, nranks, rank, unique_id):
+        self.lib = load()
+        c = ctypes.c_void_p()
+        rc = self.lib.wsg_nccl_comm_create(device, nranks, rank, bytes(unique_id), ctypes.byref(c))
+        if rc != 0:
+            raise WsgError(rc, self.lib.wsg_collective_last_error().decode())
+        self.c, self.nranks, self.rank = c, nranks, rank
+
+    def close(self):
+        if getattr(self, "c", None):
+            self.lib.wsg_nccl_comm_destroy(self.c)
+            self.c = None
+
+
 class Handle:
     """One CUDA device + one stream (wsg_handle)."""
 
@@ -337,6 +376,22 @@ class Handle:
         self._ck(self.lib.wsg_sgbm_compute_batch_device(self.h, n, d_img1, d_img2, frame_stride, rows, cols, stride,
                                                         ctypes.byref(p), d_disp))
 
+    # ---- the cross-frame reduction (NCCL, on this handle's stream) ----
+    def plane_allreduce(self, comm, acc):
+        """acc: this rank's 5 NaN-aware sums (plane_mean(...)[1]).  Returns (mean plane[4], frames in it) on every rank."""
+        a = (ctypes.c_double * 5)(*[float(v) for v in acc])
+        mean, n = (ctypes.c_double * 4)(), ctypes.c_longlong()
+        self._ck(self.lib.wsg_plane_allreduce(self.h, comm.c, a, mean, ctypes.byref(n)))
+        return np.array(list(mean)), int(n.value)
+
+    def plane_allgather(self, comm, planes):
+        """planes: n_local x 4 on every rank (same n_local).  Returns nranks x n_local x 4, rank order."""
+        pl = np.ascontiguousarray(planes, np.float64).reshape(-1, 4)
+        out = np.empty((comm.nranks, pl.shape[0], 4), np.float64)
+        dp = ctypes.POINTER(ctypes.c_double)
+        self._ck(self.lib.wsg_plane_allgather(self.h, comm.c, comm.nranks, pl.ctypes.data_as(dp), pl.shape[0], out.ctypes.data_as(dp)))
+        return out
+
     def sgbm_stats(self):
         s = SgbmStats()
         self._ck(self.lib.wsg_sgbm_get_stats(self.h, ctypes.byref(s)))
@@ -370,6 +425,22 @@ class Handle:
         self._ck(self.lib.wsg_dense_stereo(self.h, left_crop.ctypes.data, right_crop.ctypes.data, H, W, W, ctypes.byref(params),
                                            out.ctypes.data if want_host else None, d16.ctypes.data if want_disp16 else None))
         return (out, d16) if want_disp16 else out
+
+    def dense_stereo_batch(self, left_crops, right_crops, params, want_host=False):
+        """n pairs of crops of one size through ONE batched matcher run (wsg_dense_stereo_batch).  The float ROI disparities
+        stay on the device: dense_select(f) makes frame f the input of triangulate_from_dense.  want_host: also return them."""
+        a = [np.ascontiguousarray(c, np.uint8) for c in left_crops]
+        b = [np.ascontiguousarray(c, np.uint8) for c in right_crops]
+        n = len(a)
+        H, W = a[0].shape
+        arr = ctypes.c_void_p * n
+        outs = [np.empty((H, W), np.float32) for _ in range(n)] if want_host else None
+        self._ck(self.lib.wsg_dense_stereo_batch(self.h, n, arr(*[x.ctypes.data for x in a]), arr(*[x.ctypes.data for x in b]), H, W, W,
+                                                 ctypes.byref(params), arr(*[x.ctypes.data for x in outs]) if want_host else None))
+        return outs
+
+    def dense_select(self, frame):
+        self._ck(self.lib.wsg_dense_select(self.h, int(frame)))
 
     def disparity_postprocess(self, disp16_roi, min_disp, num_disp, disparity_offset=0, dense_scale=1.0, dilate=1, erode=2,
                               out_size=None):

@@ -29,7 +29,7 @@ void wsg_destroy(wsg_handle* h)
     cudaStreamSynchronize(h->stream);
     drain_profile(h);
     for (DevBuf* b : {&h->pre1, &h->pre2, &h->C, &h->S, &h->raw, &h->img1, &h->img2, &h->disp, &h->scalars, &h->bnd, &h->keys,
-                      &h->d1, &h->dbg, &h->crop_l, &h->crop_r, &h->rs_l, &h->rs_r, &h->rs_tab, &h->fc,
+                      &h->d1, &h->dbg, &h->crop_l, &h->crop_r, &h->rs_l, &h->rs_r, &h->rs_tab, &h->fc, &h->fbatch,
                       &h->fa, &h->fb, &h->dispfull, &h->im_left, &h->im_right, &h->mask_l, &h->mask_r, &h->m_valid, &h->m_X, &h->m_Y,
                       &h->m_Z, &h->m_color, &h->m_labels, &h->m_scratch, &h->m_small, &h->m_out})
         if (b->p) cudaFree(b->p);
@@ -125,8 +125,8 @@ int wsg_check_sweep(wsg_handle* h)
 // The dense matcher on `n` frames of the planned geometry, device pointers, asynchronous on the handle's stream.
 // Prefilter + cost volume frame by frame, then ONE launch per sweep over the bands of all frames (sweep_kernels.cu),
 // then LR check + median frame by frame.
-static int run_sgbm_batch(wsg_handle* h, int n, const uint8_t* const* d_img1, const uint8_t* const* d_img2, size_t stride,
-                          int16_t* const* d_disp)
+int wsg_run_sgbm_batch(wsg_handle* h, int n, const uint8_t* const* d_img1, const uint8_t* const* d_img2, size_t stride,
+                       int16_t* const* d_disp)
 {
     const SgbmPlan& pl = h->plan;
     const size_t npix = (size_t)pl.H * pl.W;
@@ -264,7 +264,7 @@ static int run_sgbm_batch(wsg_handle* h, int n, const uint8_t* const* d_img1, co
 
 int wsg_run_sgbm(wsg_handle* h, const uint8_t* d_img1, const uint8_t* d_img2, size_t stride, int16_t* d_disp)
 {
-    return run_sgbm_batch(h, 1, &d_img1, &d_img2, stride, &d_disp);
+    return wsg_run_sgbm_batch(h, 1, &d_img1, &d_img2, stride, &d_disp);
 }
 
 int wsg_sgbm_compute_device(wsg_handle* h, const uint8_t* d_img1, const uint8_t* d_img2, int rows, int cols,
@@ -307,7 +307,7 @@ int wsg_sgbm_compute_batch_device(wsg_handle* h, int n, const uint8_t* d_img1, c
         a[f] = d_img1 + (size_t)f * frame_stride; b[f] = d_img2 + (size_t)f * frame_stride;
         d[f] = d_disp16 + (size_t)f * rows * cols;
     }
-    return run_sgbm_batch(h, n, a.data(), b.data(), stride, d.data());
+    return wsg_run_sgbm_batch(h, n, a.data(), b.data(), stride, d.data());
 }
 
 int wsg_sgbm_compute_batch(wsg_handle* h, int n, const uint8_t* const* img1, const uint8_t* const* img2, int rows, int cols,
@@ -335,7 +335,7 @@ int wsg_sgbm_compute_batch(wsg_handle* h, int n, const uint8_t* const* img1, con
         CK(h, cudaMemcpy2DAsync((void*)a[f], cols, img1[f], stride, cols, rows, cudaMemcpyHostToDevice, h->stream));
         CK(h, cudaMemcpy2DAsync((void*)b[f], cols, img2[f], stride, cols, rows, cudaMemcpyHostToDevice, h->stream));
     }
-    rc = run_sgbm_batch(h, n, a.data(), b.data(), cols, d.data());
+    rc = wsg_run_sgbm_batch(h, n, a.data(), b.data(), cols, d.data());
     if (rc) return rc;
     for (int f = 0; f < n; ++f)
         CK(h, cudaMemcpyAsync(disp16[f], d[f], npix * sizeof(int16_t), cudaMemcpyDeviceToHost, h->stream));

@@ -164,11 +164,12 @@ void wsg_dense_scaled_size(int rows, int cols, double dense_scale, int* rows_s, 
     if (cols_s) *cols_s = dense_scale != 1.0 ? resized_len(cols, dense_scale) : cols;
 }
 
-int wsg_dense_stereo(wsg_handle* h, const uint8_t* left_crop, const uint8_t* right_crop, int rows, int cols, size_t stride,
-                     const wsg_dense_params* p, float* disp_roi, int16_t* disp16_roi)
+// The dense stage on n pairs of crops of one size (n == 1: wsg_dense_stereo).  Per frame: upload, resize, pad; then ONE
+// batched matcher run (run_sgbm_batch: the sweeps walk all frames in one launch each); then per frame the clean-up filters.
+// The float ROI disparity of frame f is left in h->fbatch at f * rows * cols; the last one also in h->fa.
+static int dense_stereo_batch(wsg_handle* h, int n, const uint8_t* const* left_crops, const uint8_t* const* right_crops, int rows, int cols,
+                              size_t stride, const wsg_dense_params* p, float* const* disp_roi, int16_t* disp16_roi)
 {
-    if (!h) return WSG_ERR_INVALID_ARG;
-    if (!left_crop || !right_crop || !p || rows <= 0 || cols <= 0 || stride < (size_t)cols) { h->err = "bad argument"; return WSG_ERR_INVALID_ARG; }
     const double scale = p->DENSE_SCALE;
     if (!(scale > 0.0) || !std::isfinite(scale)) { h->err = "DENSE_SCALE must be positive"; return WSG_ERR_INVALID_ARG; }
     CK(h, cudaSetDevice(h->device));
@@ -189,39 +190,82 @@ int wsg_dense_stereo(wsg_handle* h, const uint8_t* left_crop, const uint8_t* rig
     if (rc) return rc;
     h->plan = pl;
     const size_t ncrop = (size_t)rows * cols, npad = (size_t)srows * wp;
-    if ((rc = ensure(h, h->crop_l, ncrop))) return rc;
-    if ((rc = ensure(h, h->crop_r, ncrop))) return rc;
-    if ((rc = ensure(h, h->img1, npad))) return rc;
-    if ((rc = ensure(h, h->img2, npad))) return rc;
-    if ((rc = ensure(h, h->disp, npad * 2))) return rc;
-    CK(h, cudaMemcpy2DAsync(h->crop_l.p, cols, left_crop, stride, cols, rows, cudaMemcpyHostToDevice, h->stream));
-    CK(h, cudaMemcpy2DAsync(h->crop_r.p, cols, right_crop, stride, cols, rows, cudaMemcpyHostToDevice, h->stream));
-    const uint8_t *dl = (const uint8_t*)h->crop_l.p, *dr = (const uint8_t*)h->crop_r.p;
-    if (scale != 1.0) {
-        // cv::resize(..., INTER_CUBIC) of both crops (wass_stereo.cpp:788-797)
-        const size_t ns = (size_t)srows * scols;
-        if ((rc = ensure(h, h->rs_l, ns))) return rc;
-        if ((rc = ensure(h, h->rs_r, ns))) return rc;
-        if ((rc = ensure(h, h->rs_tab, resize_tab_bytes(scols, srows)))) return rc;
-        const double fy = scale < 1.0 ? scale : 1.0;
-        StageTimer t(h, WSG_STAGE_POSTFILTER, 6);
-        launch_resize_cubic_u8(dl, cols, cols, rows, scale, fy, (uint8_t*)h->rs_l.p, scols, scols, srows, h->rs_tab.p, h->stream);
-        launch_resize_cubic_u8(dr, cols, cols, rows, scale, fy, (uint8_t*)h->rs_r.p, scols, scols, srows, h->rs_tab.p, h->stream);
-        dl = (const uint8_t*)h->rs_l.p; dr = (const uint8_t*)h->rs_r.p;
+    if ((rc = ensure(h, h->crop_l, ncrop * n))) return rc;
+    if ((rc = ensure(h, h->crop_r, ncrop * n))) return rc;
+    if ((rc = ensure(h, h->img1, npad * n))) return rc;
+    if ((rc = ensure(h, h->img2, npad * n))) return rc;
+    if ((rc = ensure(h, h->disp, npad * 2 * n))) return rc;
+    if (n > 1 && (rc = ensure(h, h->fbatch, ncrop * 4 * n))) return rc;
+    std::vector<const uint8_t*> a(n), b(n);
+    std::vector<int16_t*> d(n);
+    for (int f = 0; f < n; ++f) {
+        uint8_t* cl = (uint8_t*)h->crop_l.p + f * ncrop;
+        uint8_t* cr = (uint8_t*)h->crop_r.p + f * ncrop;
+        CK(h, cudaMemcpy2DAsync(cl, cols, left_crops[f], stride, cols, rows, cudaMemcpyHostToDevice, h->stream));
+        CK(h, cudaMemcpy2DAsync(cr, cols, right_crops[f], stride, cols, rows, cudaMemcpyHostToDevice, h->stream));
+        const uint8_t *dl = cl, *dr = cr;
+        if (scale != 1.0) {
+            // cv::resize(..., INTER_CUBIC) of both crops (wass_stereo.cpp:788-797)
+            const size_t ns = (size_t)srows * scols;
+            if ((rc = ensure(h, h->rs_l, ns))) return rc;
+            if ((rc = ensure(h, h->rs_r, ns))) return rc;
+            if ((rc = ensure(h, h->rs_tab, resize_tab_bytes(scols, srows)))) return rc;
+            const double fy = scale < 1.0 ? scale : 1.0;
+            StageTimer t(h, WSG_STAGE_POSTFILTER, 6);
+            launch_resize_cubic_u8(dl, cols, cols, rows, scale, fy, (uint8_t*)h->rs_l.p, scols, scols, srows, h->rs_tab.p, h->stream);
+            launch_resize_cubic_u8(dr, cols, cols, rows, scale, fy, (uint8_t*)h->rs_r.p, scols, scols, srows, h->rs_tab.p, h->stream);
+            dl = (const uint8_t*)h->rs_l.p; dr = (const uint8_t*)h->rs_r.p;
+        }
+        uint8_t* p1 = (uint8_t*)h->img1.p + f * npad;
+        uint8_t* p2 = (uint8_t*)h->img2.p + f * npad;
+        launch_pad_images(dl, dr, scols, srows, scols, N, off, comp, p1, p2, wp, h->stream);
+        a[f] = p1; b[f] = p2; d[f] = (int16_t*)h->disp.p + f * npad;
     }
-    launch_pad_images(dl, dr, scols, srows, scols, N, off, comp, (uint8_t*)h->img1.p, (uint8_t*)h->img2.p, wp, h->stream);
-    rc = wsg_run_sgbm(h, (const uint8_t*)h->img1.p, (const uint8_t*)h->img2.p, wp, (int16_t*)h->disp.p);
+    rc = wsg_run_sgbm_batch(h, n, a.data(), b.data(), wp, d.data());
     if (rc) return rc;
-    rc = postprocess_device(h, (const int16_t*)h->disp.p, srows, wp, N, scols, p->MIN_DISPARITY, N, off, scale,
-                            p->DISP_DILATE_STEPS, p->DISP_EROSION_STEPS, rows, cols);
-    if (rc) return rc;
-    if ((rc = refine_device(h, rows, cols, p->MEDIAN_FILTER_WSIZE, p->DENSE_DISPARITY_BIGGEST_COMPONENT_THRESHOLD))) return rc;
-    if (disp_roi) CK(h, cudaMemcpyAsync(disp_roi, h->fa.p, ncrop * 4, cudaMemcpyDeviceToHost, h->stream));
+    for (int f = 0; f < n; ++f) {
+        rc = postprocess_device(h, d[f], srows, wp, N, scols, p->MIN_DISPARITY, N, off, scale,
+                                p->DISP_DILATE_STEPS, p->DISP_EROSION_STEPS, rows, cols);
+        if (rc) return rc;
+        if ((rc = refine_device(h, rows, cols, p->MEDIAN_FILTER_WSIZE, p->DENSE_DISPARITY_BIGGEST_COMPONENT_THRESHOLD))) return rc;
+        if (n > 1) CK(h, cudaMemcpyAsync((float*)h->fbatch.p + f * ncrop, h->fa.p, ncrop * 4, cudaMemcpyDeviceToDevice, h->stream));
+        if (disp_roi && disp_roi[f]) CK(h, cudaMemcpyAsync(disp_roi[f], h->fa.p, ncrop * 4, cudaMemcpyDeviceToHost, h->stream));
+    }
     if (disp16_roi)
         CK(h, cudaMemcpy2DAsync(disp16_roi, (size_t)scols * 2, (const int16_t*)h->disp.p + N, (size_t)wp * 2, (size_t)scols * 2, srows,
                                 cudaMemcpyDeviceToHost, h->stream));
     CK(h, cudaStreamSynchronize(h->stream));
+    h->dense_batch = n; h->dense_batch_rows = rows; h->dense_batch_cols = cols;
     return wsg_check_sweep(h);
+}
+
+int wsg_dense_stereo(wsg_handle* h, const uint8_t* left_crop, const uint8_t* right_crop, int rows, int cols, size_t stride,
+                     const wsg_dense_params* p, float* disp_roi, int16_t* disp16_roi)
+{
+    if (!h) return WSG_ERR_INVALID_ARG;
+    if (!left_crop || !right_crop || !p || rows <= 0 || cols <= 0 || stride < (size_t)cols) { h->err = "bad argument"; return WSG_ERR_INVALID_ARG; }
+    return dense_stereo_batch(h, 1, &left_crop, &right_crop, rows, cols, stride, p, disp_roi ? &disp_roi : nullptr, disp16_roi);
+}
+
+int wsg_dense_stereo_batch(wsg_handle* h, int n, const uint8_t* const* left_crops, const uint8_t* const* right_crops, int rows, int cols,
+                           size_t stride, const wsg_dense_params* p, float* const* disp_roi)
+{
+    if (!h) return WSG_ERR_INVALID_ARG;
+    if (n <= 0 || n > WSG_MAX_BATCH || !left_crops || !right_crops || !p || rows <= 0 || cols <= 0 || stride < (size_t)cols) { h->err = "bad argument"; return WSG_ERR_INVALID_ARG; }
+    for (int f = 0; f < n; ++f)
+        if (!left_crops[f] || !right_crops[f]) { h->err = "null frame pointer"; return WSG_ERR_INVALID_ARG; }
+    return dense_stereo_batch(h, n, left_crops, right_crops, rows, cols, stride, p, disp_roi, nullptr);
+}
+
+int wsg_dense_select(wsg_handle* h, int frame)
+{
+    if (!h) return WSG_ERR_INVALID_ARG;
+    if (!h->have_dense || frame < 0 || frame >= h->dense_batch) { h->err = "no such frame in the last dense batch"; return WSG_ERR_STATE; }
+    if (h->dense_batch == 1) return WSG_OK;
+    CK(h, cudaSetDevice(h->device));
+    const size_t ncrop = (size_t)h->dense_batch_rows * h->dense_batch_cols;
+    CK(h, cudaMemcpyAsync(h->fa.p, (const float*)h->fbatch.p + frame * ncrop, ncrop * 4, cudaMemcpyDeviceToDevice, h->stream));
+    return WSG_OK;
 }
 
 int wsg_disparity_postprocess_resized(wsg_handle* h, const int16_t* disp16_roi, int rows, int cols, int minDisparity,
@@ -499,8 +543,11 @@ int wsg_ransac_draw(int width, int height, int rounds, int32_t* triples)
     if (width <= 0 || height <= 0 || rounds < 0 || !triples) return WSG_ERR_INVALID_ARG;
     const double mindist = height * 0.01;
     for (int r = 0; r < rounds;) {
+        // cv::Vec2i p(rand()%iW, rand()%iH): the two calls are constructor arguments, which GCC -- the compiler of every
+        // Linux build of the reference -- evaluates right to left: v is drawn BEFORE u.  Pinned against the reference's own
+        // PovMesh.cpp built with GCC (oracle/_ref/povmesh_ref, tests/golden/povmesh_golden.npz).
         int c[6];
-        for (int k = 0; k < 6; ++k) c[k] = rand() % ((k & 1) ? height : width);
+        for (int k = 0; k < 3; ++k) { c[2 * k + 1] = rand() % height; c[2 * k] = rand() % width; }
         auto dist = [&](int a, int b) { const double dx = c[2 * a] - c[2 * b], dy = c[2 * a + 1] - c[2 * b + 1]; return sqrt(dx * dx + dy * dy); };
         if (dist(0, 1) < mindist || dist(1, 2) < mindist || dist(0, 2) < mindist) continue;   // "round--; continue" of the reference
         for (int k = 0; k < 6; ++k) triples[6 * r + k] = c[k];

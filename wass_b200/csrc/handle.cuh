@@ -36,7 +36,8 @@ struct wsg_handle {
     bool have_plan = false;
     wsg_sgbm_stats stats{};
     // dense stage / geometry arena
-    DevBuf crop_l, crop_r, rs_l, rs_r, rs_tab, fa, fb, fc, dispfull, im_left, im_right, mask_l, mask_r;
+    DevBuf crop_l, crop_r, rs_l, rs_r, rs_tab, fa, fb, fc, fbatch, dispfull, im_left, im_right, mask_l, mask_r;
+    int dense_batch = 1, dense_batch_rows = 0, dense_batch_cols = 0;     // frames / ROI size of the last dense batch (fbatch)
     int dense_rows = 0, dense_cols = 0;     // size of the ROI disparity held in `fa` after wsg_dense_stereo
     bool have_dense = false;
     DevBuf m_valid, m_X, m_Y, m_Z, m_color, m_labels, m_scratch, m_small, m_out;
@@ -109,3 +110,5 @@ inline void drain_profile(wsg_handle* h)
 extern "C" int wsg_make_plan(wsg_handle* h, int rows, int cols, const wsg_sgbm_params* p, SgbmPlan& pl);
 extern "C" int wsg_check_sweep(wsg_handle* h);
 extern "C" int wsg_run_sgbm(wsg_handle* h, const uint8_t* d_img1, const uint8_t* d_img2, size_t stride, int16_t* d_disp);
+extern "C" int wsg_run_sgbm_batch(wsg_handle* h, int n, const uint8_t* const* d_img1, const uint8_t* const* d_img2, size_t stride,
+                                  int16_t* const* d_disp);

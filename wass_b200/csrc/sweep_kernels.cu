@@ -29,6 +29,7 @@
 #include "sgbm_dev.cuh"
 #include <algorithm>
 #include <cstdlib>
+#include <type_traits>
 
 namespace wsg {
 
@@ -38,34 +39,46 @@ static constexpr int PROG_INF = 0x3fffffff;
 
 // rows per band / ring depth for D <= 256 (K == 1) and D <= 512 (K == 2); experiments: -DWSG_SW_ROWS1=.. -DWSG_SW_NS1=..
 #ifndef WSG_SW_ROWS1
-#define WSG_SW_ROWS1 15
+#define WSG_SW_ROWS1 14
 #endif
 #ifndef WSG_SW_NS1
-#define WSG_SW_NS1 5
+#define WSG_SW_NS1 8
 #endif
 #ifndef WSG_SW_ROWS2
 #define WSG_SW_ROWS2 7
 #endif
 #ifndef WSG_SW_NS2
-#define WSG_SW_NS2 5
+#define WSG_SW_NS2 6
+#endif
+#ifndef WSG_SW_PFD
+#define WSG_SW_PFD 3      // pixels of C in flight per row in the sweeps that also stream S
+#endif
+#ifndef WSG_SW_STAGGER
+#define WSG_SW_STAGGER -1  // extra columns a row lets the row above get ahead before it starts; -1: half the ring's slack
 #endif
 
 // Shared-memory map of a worker (uint4 units).  K = 16-byte vectors per lane and pixel (D <= 256: 1, D <= 512: 2).
-template <int K, int R, int NS> struct SweepCfg {
-    static constexpr int PFD = 4;                             // pixels of C in flight per row (cp.async staging)
-    static constexpr int PFS = 3;                             // pixels of S in flight per row
+// The first sweep (MODE 0) streams only C and has no winner-take-all: it needs neither S staging nor scratch.
+template <int K, int R, int NS, int MODE> struct SweepCfg {
+    static constexpr int PFD = MODE == 0 ? 4 : WSG_SW_PFD;    // pixels of C in flight per row (cp.async staging)
+    static constexpr int PFS = MODE == 0 ? 0 : 2;             // pixels of S in flight per row
     static constexpr int PIX_V = K * 32;                      // uint4 per pixel
     static constexpr int SLOT_V = 3 * PIX_V;                  // uint4 per ring slot: [dir][k][lane]
     static constexpr int RING_V = NS * SLOT_V;
     static constexpr int RINGS_V = (R + 1) * RING_V;          // ring r: states of the row above row r; ring R: out of the band
-    static constexpr int SCR_V = R * PIX_V;                   // per-row WTA scratch
+    static constexpr int SCR_V = MODE == 2 ? R * PIX_V : 0;   // per-row WTA scratch
     static constexpr int STAGEC_V = R * PFD * PIX_V;          // per-row staging of the C stream
     static constexpr int STAGES_V = R * PFS * PIX_V;          // per-row staging of the S stream
     static constexpr int SMEM = (RINGS_V + SCR_V + STAGEC_V + STAGES_V) * 16;
     static constexpr int THREADS = (R + 1) * 32;
     static constexpr int HD = NS - 2 < 4 ? NS - 2 : 4;        // boundary columns the helper polls per round trip
+    // A row may run lag = 2 .. NS-2 columns behind the row above (2: it needs column x+1; NS-2: the ring is full).  Rows
+    // that start at the minimum stay there -- every row polls for every column of the one above -- so each row first
+    // lets its producer get STAGGER columns further ahead: the chain then sits in the middle of its slack.
+    static constexpr int STAGGER = WSG_SW_STAGGER >= 0 ? WSG_SW_STAGGER : (NS - 4) / 2;
     static_assert(SMEM <= 227 * 1024, "worker does not fit an SM");
     static_assert(PFS <= PFD, "the S stream rides in the commit groups of the C stream");
+    static_assert(STAGGER >= 0 && STAGGER <= NS - 4 + 0 || NS < 4, "stagger beyond the ring's slack");
 };
 
 // 16-byte asynchronous global->shared copy (L2 only), one per lane; completion is tracked per thread in commit groups
@@ -171,12 +184,16 @@ __device__ __forceinline__ void wta_eval(const unsigned (&s)[4 * K], int l, cons
     const int n = minS * 100 - 1;                                   // < 2^22
     // floor(n / (100-uniq)): multiply-high by ceil(2^32/(100-uniq)) is exact for n < 2^22; a divisor of 1 has no such constant
     const int Tm = n < 0 ? -1 : (a.umagic ? (int)__umulhi((unsigned)n, a.umagic) : n);
-    // packed count of S <= Tm: (0x8000 + T - S) keeps bit 15 iff T >= S (S, T <= 0x7fff: no borrow between the halves)
+    // packed count of S <= Tm: (0x8000 + T - S) keeps bit 15 iff T >= S (S, T <= 0x7fff: no borrow between the halves).
+    // The subtractions run on the FMA pipe; one byte gather per register pair collects the four flag bytes.
     const unsigned T2 = ((unsigned)min(max(Tm, 0), 32767) | 0x8000u) * 0x10001u;
-    unsigned bits = 0;
+    const unsigned minus_one = 0u - a.one;
+    int cnt = 0;
 #pragma unroll
-    for (int e = 0; e < 4 * K; ++e) bits |= ((T2 - s[e]) & 0x80008000u) >> e;
-    int cnt = __popc(bits);
+    for (int e = 0; e < 4 * K; e += 2) {
+        const unsigned t0 = add_on_fma(s[e], T2, minus_one), t1 = add_on_fma(s[e + 1], T2, minus_one);     // T2 - s
+        cnt += __popc(__byte_perm(t0, t1, 0x7531) & 0x80808080u);
+    }
     if (padlane || Tm < 0) cnt = 0;
     const int total = __reduce_add_sync(FULL, cnt);
     // the winner's neighbours (clamped addresses; the values only count where they exist)
@@ -213,6 +230,127 @@ __device__ __forceinline__ void wta_flush(unsigned key, unsigned nb, int xl, boo
     d1_row[x] = (int16_t)(dd + a.minD * 16);
 }
 
+// Per-row state of a sweep (everything sweep_step needs besides the pixel's register sets).
+template <int K> struct RowState {
+    const uint4* cpf; const uint4* spf; uint4* scur;      // C / S prefetch cursors, S store cursor
+    long long dstep;
+    const uint4* ring_in; uint4* ring_out;
+    int16_t* scratch;
+    const uint4* stageC; const uint4* stageS;
+    unsigned stC, stS;                                    // the same staging areas as shared-window addresses
+    volatile int* prog_in; volatile int* prog_me; volatile int* prog_next;
+    int seen_in, seen_next;
+    int pslot;                                            // x % PFD, as a uint4 offset into the C staging
+    int o_m1, o_0, o_p1;                                  // ring slots (uint4 offsets) of columns x-1, x, x+1
+    unsigned Nh[4 * K];                                   // normalised state of the horizontal path
+    unsigned padm[K];
+    unsigned wkey, wnb, rkey, rnb;                        // winner-take-all: last evaluation, and this lane's kept record
+    unsigned long long* keys_row; int16_t* d1_row;
+    unsigned one, P1p, P2mP1p;
+    int l;
+};
+
+// One pixel of a row: Cc / Lh = C and horizontal L of pixel x (from the previous step), Cn / Lhn = the same for pixel x+1
+// (made here), vsp = S of pixel x-1 (the winner-take-all runs one pixel late), vsn = S of pixel x (made here).
+// SODD = x % 2: the S staging has two slots.
+template <int K, int R, int NS, int MODE, int NDIR, bool HASPAD, bool FAST, int SODD>
+__device__ __forceinline__ void sweep_step(RowState<K>& st, const SweepArgs& a, const int x, unsigned (&Cc)[4 * K], unsigned (&Lh)[4 * K],
+                                           unsigned (&Cn)[4 * K], unsigned (&Lhn)[4 * K], unsigned (&vsp)[4 * K], unsigned (&vsn)[4 * K])
+{
+    using Cfg = SweepCfg<K, R, NS, MODE>;
+    constexpr int NR = 4 * K;
+    constexpr int PFD = Cfg::PFD, PFS = Cfg::PFS;
+    const int l = st.l;
+    const int nslot = st.pslot + Cfg::PIX_V == PFD * Cfg::PIX_V ? 0 : st.pslot + Cfg::PIX_V;
+    unsigned v[3][NR], Nd[3][NR];
+    cp_async_wait<PFD - 2>();                   // pixel x+1 has landed (past the row end: unused data)
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        const uint4 c = st.stageC[nslot + k * 32];
+        Cn[4 * k] = c.x; Cn[4 * k + 1] = c.y; Cn[4 * k + 2] = c.z; Cn[4 * k + 3] = c.w;
+    }
+    if (MODE == 0) {
+#pragma unroll
+        for (int j = 0; j < NR; ++j) vsn[j] = Lh[j];
+    } else {
+        // S(x) was committed PFS iterations ago; PFD + x groups exist by now
+        if (PFS < PFD - 1) cp_async_wait<(PFS > 0 ? PFS - 1 : 0)>();
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            const uint4 sv = st.stageS[SODD * Cfg::PIX_V + k * 32];
+            vsn[4 * k] = __viaddmin_u16x2(sv.x, Lh[4 * k], SAT2);
+            vsn[4 * k + 1] = __viaddmin_u16x2(sv.y, Lh[4 * k + 1], SAT2);
+            vsn[4 * k + 2] = __viaddmin_u16x2(sv.z, Lh[4 * k + 2], SAT2);
+            vsn[4 * k + 3] = __viaddmin_u16x2(sv.w, Lh[4 * k + 3], SAT2);
+        }
+    }
+    if (NDIR == 4) {
+        // ---- states of the three directions that come from the row above: columns x-1, x, x+1 of ring r.  Columns -1
+        // and W1 exist in the ring as zeros (zero-initialised slot NS-1, and one extra column written by the
+        // producer): L = 0 for an out-of-image predecessor.
+        wait_prog(st.prog_in, x + 2, st.seen_in, a.err, a.eager);
+        const int sl[3] = {st.o_m1, st.o_0, st.o_p1};
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                const uint4 t = st.ring_in[sl[q] + (q * K + k) * 32];
+                Nd[q][4 * k] = t.x; Nd[q][4 * k + 1] = t.y; Nd[q][4 * k + 2] = t.z; Nd[q][4 * k + 3] = t.w;
+            }
+        }
+        // ---- independent chains: the winner-take-all of the PREVIOUS pixel, and the four path steps
+        if (MODE == 2) wta_eval<K, HASPAD>(vsp, l, a, st.scratch, st.wkey, st.wnb);
+        agg_step<32, NR, HASPAD, FAST>(st.Nh, Cn, Lhn, l, st.P1p, st.P2mP1p, st.padm, st.one);
+#pragma unroll
+        for (int q = 0; q < 3; ++q) agg_step<32, NR, HASPAD, FAST>(Nd[q], Cc, v[q], l, st.P1p, st.P2mP1p, st.padm, st.one);
+        // ---- hand the new states down: slot of column x in ring r+1 is free once its reader has completed x-NS+1
+        wait_prog(st.prog_next, x - NS + 2, st.seen_next, a.err, a.eager);
+        uint4* dst = st.ring_out + st.o_0;
+#pragma unroll
+        for (int q = 0; q < 3; ++q)
+#pragma unroll
+            for (int k = 0; k < K; ++k)
+                dst[(q * K + k) * 32] = make_uint4(Nd[q][4 * k], Nd[q][4 * k + 1], Nd[q][4 * k + 2], Nd[q][4 * k + 3]);
+        __syncwarp();                      // every lane's state stores are issued before the counter store
+        asm volatile("" ::: "memory");
+        if (l == 0) *st.prog_me = x + 1;
+#pragma unroll
+        for (int q = 0; q < 3; ++q)
+#pragma unroll
+            for (int j = 0; j < NR; ++j) vsn[j] = __viaddmin_u16x2(vsn[j], v[q][j], SAT2);
+        st.o_m1 = st.o_0; st.o_0 = st.o_p1;
+        st.o_p1 = st.o_p1 + Cfg::SLOT_V == Cfg::RING_V ? 0 : st.o_p1 + Cfg::SLOT_V;
+    } else {
+        if (MODE == 2) wta_eval<K, HASPAD>(vsp, l, a, st.scratch, st.wkey, st.wnb);
+        agg_step<32, NR, HASPAD, FAST>(st.Nh, Cn, Lhn, l, st.P1p, st.P2mP1p, st.padm, st.one);
+    }
+    // ---- S out, or kept (registers + shared memory) for the winner-take-all one iteration later
+    if (MODE == 2) {
+        // the evaluation above was for logical column x-1: lane (x-1)%32 keeps it; every 32 columns all lanes flush
+        if (l == ((x - 1) & 31)) { st.rkey = st.wkey; st.rnb = st.wnb; }
+        if (x > 0 && (x & 31) == 0) wta_flush(st.rkey, st.rnb, x - 32 + l, true, a, st.keys_row, st.d1_row);
+        __syncwarp();                       // all lanes are done reading the previous pixel's S
+#pragma unroll
+        for (int k = 0; k < K; ++k)
+            reinterpret_cast<uint4*>(st.scratch)[l * K + k] = make_uint4(vsn[4 * k], vsn[4 * k + 1], vsn[4 * k + 2], vsn[4 * k + 3]);
+        __syncwarp();
+    } else {
+#pragma unroll
+        for (int k = 0; k < K; ++k)
+            stg_stream(st.scur + k * 32, make_uint4(vsn[4 * k], vsn[4 * k + 1], vsn[4 * k + 2], vsn[4 * k + 3]));
+    }
+    st.scur += st.dstep;
+    // ---- refill the staging slots just consumed with pixels x + PFD (C) and x + PFS (S)
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        cp_async16(st.stC + (st.pslot + k * 32) * 16, st.cpf + k * 32);
+        if (MODE != 0) cp_async16(st.stS + (SODD * Cfg::PIX_V + k * 32) * 16, st.spf + k * 32);
+    }
+    cp_async_commit();
+    st.cpf += st.dstep; st.spf += st.dstep;
+    st.pslot = nslot;
+}
+
 // One image row of a sweep, walked by one warp (see the kernel below for the surrounding protocol).
 //   prog[0]     columns the helper has put into ring 0          (ring r = states of the row above row r of the band)
 //   prog[r+1]   columns row r has completed and written into ring r+1
@@ -223,181 +361,93 @@ template <int K, int R, int NS, int MODE, int NDIR, bool HASPAD, bool FAST>
 __device__ __forceinline__ void sweep_row(const uint4* __restrict__ C, uint4* __restrict__ S, const SweepArgs& a, uint4* smem,
                                           volatile int* prog, int frame, int band, int r, int l)
 {
-    using Cfg = SweepCfg<K, R, NS>;
+    using Cfg = SweepCfg<K, R, NS, MODE>;
     constexpr int NR = 4 * K;
-    const unsigned one = a.one;
+    constexpr int PFD = Cfg::PFD, PFS = Cfg::PFS;
+    const int W1 = a.W1;
     const int yl = band * R + r;                    // logical row (sweep order)
     if (yl >= a.H) {
         if (NDIR == 4 && l == 0) prog[r + 1] = PROG_INF;         // the row above never waits for this one
         return;
     }
     const int yp = a.flip ? a.H - 1 - yl : yl;      // physical row
-    const long long dstep = a.flip ? -(long long)a.Dp8 : (long long)a.Dp8;
-    const size_t first = ((size_t)yp * a.W1 + (a.flip ? a.W1 - 1 : 0)) * a.Dp8 + l;
-    const uint4* cpf = C + first;                   // prefetch cursors
-    const uint4* spf = S + first;
-    uint4* scur = S + first;                        // compute cursor
-    const uint4* ring_in = smem + (size_t)r * Cfg::RING_V + l;
-    uint4* ring_out = smem + (size_t)(r + 1) * Cfg::RING_V + l;
-    int16_t* scratch = reinterpret_cast<int16_t*>(smem + Cfg::RINGS_V + (size_t)r * Cfg::PIX_V);
-    uint4* stageC = smem + Cfg::RINGS_V + Cfg::SCR_V + (size_t)r * Cfg::PFD * Cfg::PIX_V + l;
-    uint4* stageS = smem + Cfg::RINGS_V + Cfg::SCR_V + Cfg::STAGEC_V + (size_t)r * Cfg::PFS * Cfg::PIX_V + l;
-    volatile int* prog_in = &prog[r];
-    volatile int* prog_me = &prog[r + 1];
-    volatile int* prog_next = &prog[r + 2];
-    int seen_in = 0, seen_next = 0;
-
-    unsigned padm[K];
+    const size_t first = ((size_t)yp * W1 + (a.flip ? W1 - 1 : 0)) * a.Dp8 + l;
+    RowState<K> st;
+    st.l = l; st.one = a.one; st.P1p = a.P1p; st.P2mP1p = a.P2mP1p;
+    st.dstep = a.flip ? -(long long)a.Dp8 : (long long)a.Dp8;
+    st.cpf = C + first; st.spf = S + first; st.scur = S + first;
+    st.ring_in = smem + (size_t)r * Cfg::RING_V + l;
+    st.ring_out = smem + (size_t)(r + 1) * Cfg::RING_V + l;
+    st.scratch = reinterpret_cast<int16_t*>(smem + Cfg::RINGS_V + (size_t)r * Cfg::PIX_V);
+    st.stageC = smem + Cfg::RINGS_V + Cfg::SCR_V + (size_t)r * PFD * Cfg::PIX_V + l;
+    st.stageS = smem + Cfg::RINGS_V + Cfg::SCR_V + Cfg::STAGEC_V + (size_t)r * PFS * Cfg::PIX_V + l;
+    st.stC = (unsigned)__cvta_generic_to_shared(st.stageC);
+    st.stS = (unsigned)__cvta_generic_to_shared(st.stageS);
+    st.prog_in = &prog[r]; st.prog_me = &prog[r + 1]; st.prog_next = &prog[r + 2];
+    st.seen_in = 0; st.seen_next = 0;
+    st.wkey = st.wnb = st.rkey = st.rnb = 0;
+    st.keys_row = a.keys + ((size_t)frame * a.H + yp) * a.W;
+    st.d1_row = a.d1 + ((size_t)frame * a.H + yp) * a.W;
 #pragma unroll
-    for (int k = 0; k < K; ++k) padm[k] = ((l * K + k) * 8 >= a.D) ? SAT2 : 0u;
+    for (int k = 0; k < K; ++k) st.padm[k] = ((l * K + k) * 8 >= a.D) ? SAT2 : 0u;
 
     // one commit group per pixel, PFD pixels ahead; each lane copies and later reads back its own 16 bytes.  The
     // prefetch is not guarded at the row end: the volumes are readable PFD pixels beyond either end.
-    const unsigned stC = (unsigned)__cvta_generic_to_shared(stageC), stS = (unsigned)__cvta_generic_to_shared(stageS);
 #pragma unroll
-    for (int i = 0; i < Cfg::PFD; ++i) {
+    for (int i = 0; i < PFD; ++i) {
 #pragma unroll
         for (int k = 0; k < K; ++k) {
-            cp_async16(stC + (i * Cfg::PIX_V + k * 32) * 16, cpf + k * 32);
-            if (MODE != 0 && i < Cfg::PFS) cp_async16(stS + (i * Cfg::PIX_V + k * 32) * 16, spf + k * 32);
+            cp_async16(st.stC + (i * Cfg::PIX_V + k * 32) * 16, st.cpf + k * 32);
+            if (MODE != 0 && i < PFS) cp_async16(st.stS + (i * Cfg::PIX_V + k * 32) * 16, st.spf + k * 32);
         }
         cp_async_commit();
-        cpf += dstep;
-        if (i < Cfg::PFS) spf += dstep;
+        st.cpf += st.dstep;
+        if (i < PFS) st.spf += st.dstep;
     }
 
     // The horizontal direction runs ONE PIXEL AHEAD of the three directions that come from the row above: its step for
-    // pixel x+1 and their steps for pixel x are four independent dependency chains in one basic block.
-    unsigned Nh[NR], Cc[NR], Lh[NR], vsp[NR];
-    unsigned wkey = 0, wnb = 0, rkey = 0, rnb = 0;      // winner-take-all: last evaluation, and this lane's kept record
-    unsigned long long* keys_row = a.keys + ((size_t)frame * a.H + yp) * a.W;
-    int16_t* d1_row = a.d1 + ((size_t)frame * a.H + yp) * a.W;
+    // pixel x+1 and their steps for pixel x are four independent dependency chains in one basic block.  The loop is
+    // unrolled by two with the roles of the register sets swapped, so nothing is copied from one pixel to the next.
+    unsigned Ca[NR], La[NR], Cb[NR], Lb[NR], Va[NR], Vb[NR];
 #pragma unroll
-    for (int j = 0; j < NR; ++j) vsp[j] = 0;
-#pragma unroll
-    for (int j = 0; j < NR; ++j) Nh[j] = 0;
-    cp_async_wait<Cfg::PFD - 1>();
+    for (int j = 0; j < NR; ++j) { Va[j] = 0; Vb[j] = 0; st.Nh[j] = 0; }
+    cp_async_wait<PFD - 1>();
 #pragma unroll
     for (int k = 0; k < K; ++k) {
-        const uint4 c = stageC[k * 32];
-        Cc[4 * k] = c.x; Cc[4 * k + 1] = c.y; Cc[4 * k + 2] = c.z; Cc[4 * k + 3] = c.w;
+        const uint4 c = st.stageC[k * 32];
+        Ca[4 * k] = c.x; Ca[4 * k + 1] = c.y; Ca[4 * k + 2] = c.z; Ca[4 * k + 3] = c.w;
     }
-    agg_step<32, NR, HASPAD, FAST>(Nh, Cc, Lh, l, a.P1p, a.P2mP1p, padm, one);
+    agg_step<32, NR, HASPAD, FAST>(st.Nh, Ca, La, l, st.P1p, st.P2mP1p, st.padm, st.one);
+    if (NDIR == 4 && Cfg::STAGGER > 0) wait_prog(st.prog_in, min(2 + Cfg::STAGGER, W1 + 1), st.seen_in, a.err, a.eager);
+    st.pslot = 0;
+    st.o_m1 = (NS - 1) * Cfg::SLOT_V; st.o_0 = 0; st.o_p1 = Cfg::SLOT_V;      // column -1 is the zero-initialised slot NS-1
 
-    int pslot = 0, sslot = 0;                       // x % PFD, x % PFS
-    // ring slots (uint4 offsets) of columns x-1, x, x+1; column -1 is the zero-initialised slot NS-1
-    int o_m1 = (NS - 1) * Cfg::SLOT_V, o_0 = 0, o_p1 = Cfg::SLOT_V;
-    for (int x = 0; x < a.W1; ++x) {                // logical column
-        const int nslot = pslot + 1 == Cfg::PFD ? 0 : pslot + 1;
-        unsigned Cn[NR], Lhn[NR], vs[NR], v[3][NR], Nd[3][NR];
-        cp_async_wait<Cfg::PFD - 2>();              // pixel x+1 has landed (past the row end: unused data)
+    int x = 0;
+    for (; x + 1 < W1; x += 2) {
+        sweep_step<K, R, NS, MODE, NDIR, HASPAD, FAST, 0>(st, a, x, Ca, La, Cb, Lb, Va, Vb);
+        sweep_step<K, R, NS, MODE, NDIR, HASPAD, FAST, 1>(st, a, x + 1, Cb, Lb, Ca, La, Vb, Va);
+    }
+    if (x < W1) {                                   // odd width: one more pixel; its S ends up where the epilogue expects it
+        sweep_step<K, R, NS, MODE, NDIR, HASPAD, FAST, 0>(st, a, x, Ca, La, Cb, Lb, Va, Vb);
 #pragma unroll
-        for (int k = 0; k < K; ++k) {
-            const uint4 c = stageC[nslot * Cfg::PIX_V + k * 32];
-            Cn[4 * k] = c.x; Cn[4 * k + 1] = c.y; Cn[4 * k + 2] = c.z; Cn[4 * k + 3] = c.w;
-        }
-        if (MODE == 0) {
-#pragma unroll
-            for (int j = 0; j < NR; ++j) vs[j] = Lh[j];
-        } else {
-            // S(x) was committed PFS iterations ago; PFD + x groups exist by now
-            if (Cfg::PFS < Cfg::PFD - 1) cp_async_wait<Cfg::PFS - 1>();
-#pragma unroll
-            for (int k = 0; k < K; ++k) {
-                const uint4 sv = stageS[sslot * Cfg::PIX_V + k * 32];
-                vs[4 * k] = __viaddmin_u16x2(sv.x, Lh[4 * k], SAT2);
-                vs[4 * k + 1] = __viaddmin_u16x2(sv.y, Lh[4 * k + 1], SAT2);
-                vs[4 * k + 2] = __viaddmin_u16x2(sv.z, Lh[4 * k + 2], SAT2);
-                vs[4 * k + 3] = __viaddmin_u16x2(sv.w, Lh[4 * k + 3], SAT2);
-            }
-        }
-        if (NDIR == 4) {
-            // ---- states of the three directions that come from the row above: columns x-1, x, x+1 of ring r.  Columns -1
-            // and W1 exist in the ring as zeros (zero-initialised slot NS-1, and one extra column written by the
-            // producer): L = 0 for an out-of-image predecessor.
-            wait_prog(prog_in, x + 2, seen_in, a.err, a.eager);
-            const int sl[3] = {o_m1, o_0, o_p1};
-#pragma unroll
-            for (int q = 0; q < 3; ++q) {
-#pragma unroll
-                for (int k = 0; k < K; ++k) {
-                    const uint4 t = ring_in[sl[q] + (q * K + k) * 32];
-                    Nd[q][4 * k] = t.x; Nd[q][4 * k + 1] = t.y; Nd[q][4 * k + 2] = t.z; Nd[q][4 * k + 3] = t.w;
-                }
-            }
-            // ---- independent chains: the winner-take-all of the PREVIOUS pixel, and the four path steps
-            if (MODE == 2) wta_eval<K, HASPAD>(vsp, l, a, scratch, wkey, wnb);
-            agg_step<32, NR, HASPAD, FAST>(Nh, Cn, Lhn, l, a.P1p, a.P2mP1p, padm, one);
-#pragma unroll
-            for (int q = 0; q < 3; ++q) agg_step<32, NR, HASPAD, FAST>(Nd[q], Cc, v[q], l, a.P1p, a.P2mP1p, padm, one);
-            // ---- hand the new states down: slot of column x in ring r+1 is free once its reader has completed x-NS+1
-            wait_prog(prog_next, x - NS + 2, seen_next, a.err, a.eager);
-            uint4* dst = ring_out + o_0;
-#pragma unroll
-            for (int q = 0; q < 3; ++q)
-#pragma unroll
-                for (int k = 0; k < K; ++k)
-                    dst[(q * K + k) * 32] = make_uint4(Nd[q][4 * k], Nd[q][4 * k + 1], Nd[q][4 * k + 2], Nd[q][4 * k + 3]);
-            __syncwarp();                      // every lane's state stores are issued before the counter store
-            asm volatile("" ::: "memory");
-            if (l == 0) *prog_me = x + 1;
-#pragma unroll
-            for (int q = 0; q < 3; ++q)
-#pragma unroll
-                for (int j = 0; j < NR; ++j) vs[j] = __viaddmin_u16x2(vs[j], v[q][j], SAT2);
-            o_m1 = o_0; o_0 = o_p1;
-            o_p1 = o_p1 + Cfg::SLOT_V == Cfg::RING_V ? 0 : o_p1 + Cfg::SLOT_V;
-        } else {
-            if (MODE == 2) wta_eval<K, HASPAD>(vsp, l, a, scratch, wkey, wnb);
-            agg_step<32, NR, HASPAD, FAST>(Nh, Cn, Lhn, l, a.P1p, a.P2mP1p, padm, one);
-        }
-        // ---- S out, or kept (registers + shared memory) for the winner-take-all one iteration later
-        if (MODE == 2) {
-            // the evaluation above was for logical column x-1: lane (x-1)%32 keeps it; every 32 columns all lanes flush
-            if (l == ((x - 1) & 31)) { rkey = wkey; rnb = wnb; }
-            if (x > 0 && (x & 31) == 0) wta_flush(rkey, rnb, x - 32 + l, true, a, keys_row, d1_row);
-            __syncwarp();                       // all lanes are done reading the previous pixel's S
-#pragma unroll
-            for (int k = 0; k < K; ++k)
-                reinterpret_cast<uint4*>(scratch)[l * K + k] = make_uint4(vs[4 * k], vs[4 * k + 1], vs[4 * k + 2], vs[4 * k + 3]);
-#pragma unroll
-            for (int j = 0; j < NR; ++j) vsp[j] = vs[j];
-            __syncwarp();
-        } else {
-#pragma unroll
-            for (int k = 0; k < K; ++k)
-                stg_stream(scur + k * 32, make_uint4(vs[4 * k], vs[4 * k + 1], vs[4 * k + 2], vs[4 * k + 3]));
-        }
-        scur += dstep;
-        // ---- refill the staging slots just consumed with pixels x + PFD (C) and x + PFS (S)
-#pragma unroll
-        for (int k = 0; k < K; ++k) {
-            cp_async16(stC + (pslot * Cfg::PIX_V + k * 32) * 16, cpf + k * 32);
-            if (MODE != 0) cp_async16(stS + (sslot * Cfg::PIX_V + k * 32) * 16, spf + k * 32);
-        }
-        cp_async_commit();
-        cpf += dstep; spf += dstep;
-        pslot = nslot;
-        sslot = sslot + 1 == Cfg::PFS ? 0 : sslot + 1;
-#pragma unroll
-        for (int j = 0; j < NR; ++j) { Cc[j] = Cn[j]; Lh[j] = Lhn[j]; }
+        for (int j = 0; j < NR; ++j) Va[j] = Vb[j];
     }
     cp_async_wait<0>();
     if (MODE == 2) {
         // last column, then the columns still held in registers: xb .. W1-1 with xb = 32*floor((W1-1)/32)
-        wta_eval<K, HASPAD>(vsp, l, a, scratch, wkey, wnb);
-        if (l == ((a.W1 - 1) & 31)) { rkey = wkey; rnb = wnb; }
-        const int xb = (a.W1 - 1) & ~31;
-        wta_flush(rkey, rnb, xb + l, xb + l < a.W1, a, keys_row, d1_row);
+        wta_eval<K, HASPAD>(Va, l, a, st.scratch, st.wkey, st.wnb);
+        if (l == ((W1 - 1) & 31)) { st.rkey = st.wkey; st.rnb = st.wnb; }
+        const int xb = (W1 - 1) & ~31;
+        wta_flush(st.rkey, st.rnb, xb + l, xb + l < W1, a, st.keys_row, st.d1_row);
     }
     if (NDIR == 4) {
         // the extra zero column: the out-of-image predecessor of the last pixel's (x+1,y-1) path in the row below
-        wait_prog(prog_next, a.W1 - NS + 2, seen_next, a.err, a.eager);
+        wait_prog(st.prog_next, W1 - NS + 2, st.seen_next, a.err, a.eager);
 #pragma unroll
-        for (int j = 0; j < 3 * K; ++j) ring_out[o_0 + j * 32] = make_uint4(0, 0, 0, 0);
+        for (int j = 0; j < 3 * K; ++j) st.ring_out[st.o_0 + j * 32] = make_uint4(0, 0, 0, 0);
         __syncwarp();
         asm volatile("" ::: "memory");
-        if (l == 0) *prog_me = a.W1 + 1;
+        if (l == 0) *st.prog_me = W1 + 1;
     }
 }
 
@@ -409,7 +459,7 @@ __device__ __forceinline__ void sweep_row(const uint4* __restrict__ C, uint4* __
 template <int K, int R, int NS>
 __device__ __forceinline__ void sweep_helper(const SweepArgs& a, uint4* smem, volatile int* prog, int frame, int band, int nbands, int l)
 {
-    using Cfg = SweepCfg<K, R, NS>;
+    using Cfg = SweepCfg<K, R, NS, 0>;      // the rings come first in every mode's map
     constexpr int NV = 3 * K, HD = Cfg::HD;
     const size_t bstride = (size_t)a.W1 * Cfg::SLOT_V;      // uint4 per boundary row
     uint4* bnd_f = a.bnd + (size_t)frame * a.bnd_v;
@@ -517,10 +567,10 @@ __device__ __forceinline__ void sweep_helper(const SweepArgs& a, uint4* smem, vo
 }
 
 template <int K, int R, int NS, int MODE, int NDIR, bool HASPAD>
-__global__ void __launch_bounds__(SweepCfg<K, R, NS>::THREADS, 1)
+__global__ void __launch_bounds__(SweepCfg<K, R, NS, MODE>::THREADS, 1)
 sweep_kernel(SweepArgs a)
 {
-    using Cfg = SweepCfg<K, R, NS>;
+    using Cfg = SweepCfg<K, R, NS, MODE>;
     extern __shared__ __align__(16) uint4 smem[];
     __shared__ volatile int prog[R + 2];
     __shared__ int s_ticket;
@@ -567,7 +617,7 @@ sweep_kernel(SweepArgs a)
 template <int K, int R, int NS, int MODE, int NDIR, bool HASPAD>
 static void launch_sweep_t(const SweepArgs& a, int workers, cudaStream_t st)
 {
-    using Cfg = SweepCfg<K, R, NS>;
+    using Cfg = SweepCfg<K, R, NS, MODE>;
     auto kern = sweep_kernel<K, R, NS, MODE, NDIR, HASPAD>;
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
     cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);

@@ -34,29 +34,9 @@ def rectified_calib(K0, K1, R, T, width, height):
                 T=np.asarray(T, np.float64), R1=r["R1"], R2=r["R2"], P1=r["P1"], P2=r["P2"], roi_left=r["roi1"], roi_right=r["roi2"])
 
 
-def process_frame(h, left_rect, right_rect, calib, dense, ransac_rounds=400, ransac_threshold=1.0, plane_max_distance=1.5,
-                  zgap_percentile=99.0, min_points=100, seed=None, keep_xyzc=True, xyzc_out=None):
-    """left_rect/right_rect: rectified 8-bit images (full rectified size); calib: dict as rectified_calib returns.
-    xyzc_out: optional reusable (pinned) uint8 buffer for the .xyzC bytes; FrameResult.xyzc is then a view of it.
-    Returns FrameResult; plane is 4 NaNs when RANSAC fails (the reference writes "nan nan nan nan" and carries on)."""
-    ms = {}
-    t = time.perf_counter()
-
-    def lap(name):
-        nonlocal t
-        now = time.perf_counter()
-        ms[name] = (now - t) * 1e3
-        t = now
-
-    rl, rr = calib["roi_left"], calib["roi_right"]
-    lc = np.ascontiguousarray(left_rect[rl[1]:rl[1] + rl[3], rl[0]:rl[0] + rl[2]])
-    rc = np.ascontiguousarray(right_rect[rr[1]:rr[1] + rr[3], rr[0]:rr[0] + rr[2]])
-    h.dense_stereo(lc, rc, dense, want_host=False)      # the disparity stays on the device for the triangulation
-    lap("dense")
-    n = h.triangulate_from_dense(left_rect, right_rect, calib, left_rect.shape)
-    lap("triangulate")
-    if n < min_points:
-        raise RuntimeError("too few triangulated points (%d)" % n)
+def _mesh_stages(h, roi_right, ransac_rounds, ransac_threshold, plane_max_distance, zgap_percentile, seed, keep_xyzc, xyzc_out,
+                 ms, lap):
+    """compute_zgap_percentile .. save_as_xyz_compressed on the mesh the handle holds (wass_stereo.cpp:2046-2135)."""
     zg = h.mesh_zgap_percentile(zgap_percentile)
     lap("zgap")
     h.mesh_biggest_component(zg)
@@ -64,53 +44,121 @@ def process_frame(h, left_rect, right_rect, calib, dense, ransac_rounds=400, ran
     with _rand_lock:
         if seed is not None:
             ctypes.CDLL("libc.so.6").srand(int(seed))
-        draws = capi.ransac_draw(rr[2], rr[3], ransac_rounds)
-    ok, plane, _ = h.mesh_ransac_plane(draws, ransac_threshold)
+        draws = capi.ransac_draw(roi_right[2], roi_right[3], ransac_rounds)
+    ok, ransac_plane, _ = h.mesh_ransac_plane(draws, ransac_threshold)
     lap("ransac")
     if ok:
-        h.mesh_crop_plane(plane, ransac_threshold)
+        h.mesh_crop_plane(ransac_plane, ransac_threshold)
         plane, _ = h.mesh_refine_plane()
         npts = h.mesh_crop_plane(plane, plane_max_distance)
+        export_plane = plane
         lap("refine")
     else:
+        # soft failure (wass_stereo.cpp:2101-2107): plane.txt says nan, but the mesh is still written -- with the best
+        # RANSAC hypothesis, which is what PovMesh keeps in plane_coeffs when ransac_find_plane returns false
+        # (PovMesh.cpp:745-749)
         plane = np.full(4, np.nan)
+        export_plane = ransac_plane
         npts = h.mesh_size()[2]
         ms["refine"] = 0.0
-    buf = None
-    if keep_xyzc:
-        # the file needs a plane to rotate into; the reference writes it with the fitted plane
-        buf = h.mesh_export_xyzc(plane if ok else np.array([0.0, 0.0, 1.0, 0.0]), out=xyzc_out)
+    buf = h.mesh_export_xyzc(export_plane, out=xyzc_out) if keep_xyzc else None
     lap("export")
-    return FrameResult(np.asarray(plane, np.float64), int(npts), buf, ms)
+    return np.asarray(plane, np.float64), int(npts), buf
 
 
-def run_sequence(frames, calib, dense, device=0, rank=0, world=1, dist=None, handle=None, xyzc_out=None, **kw):
-    """frames: list of callables or (left, right) tuples, one per frame of the WHOLE sequence; this rank processes frames
-    rank, rank+world, ...  Returns (mean_plane, planes[n_frames][4], results of the owned frames).
+def _clock():
+    ms = {}
+    t = [time.perf_counter()]
 
-    handle: one capi.Handle or a list of them.  With a list of k handles, k frames are in flight on this GPU, one host
-    thread and one stream each (the C calls release the GIL): the aggregation sweeps are latency-bound (DESIGN.md section
-    4), so a second frame's kernels fill the SMs' idle issue slots (with three or more handles, cap each one's sweeps at
-    half the SMs first: h.sgbm_set_sweep_workers).  Frame i gets seed i either way, so the planes do not
-    depend on k.  xyzc_out: a reusable buffer, or a list with one per handle.  Without `handle` one is created and
-    destroyed here (the arena is several GB: keep one across calls when processing more than one sequence)."""
+    def lap(name):
+        now = time.perf_counter()
+        ms[name] = ms.get(name, 0.0) + (now - t[0]) * 1e3
+        t[0] = now
+    return ms, lap
+
+
+def process_frame(h, left_rect, right_rect, calib, dense, ransac_rounds=400, ransac_threshold=1.0, plane_max_distance=1.5,
+                  zgap_percentile=99.0, min_points=100, seed=None, keep_xyzc=True, xyzc_out=None, left=None, right=None):
+    """left_rect/right_rect: rectified 8-bit images (full rectified size), used for the ROI crops the matcher sees.
+    left/right: the ORIGINAL (undistorted, un-rectified) images: triangulate() tests DISCARD_BURNED_AREAS and takes the
+    point colour at un-rectified coordinates on env.left / env.right (wass_stereo.cpp:1069-1093, 1244-1250, 1342).  They
+    default to the rectified pair, which is only right for a rig whose rectification is the identity (the synthetic rig).
+    calib: dict as rectified_calib returns.  xyzc_out: optional reusable (pinned) uint8 buffer for the .xyzC bytes.
+    Returns FrameResult; plane is 4 NaNs when RANSAC fails (the reference writes "nan nan nan nan" and carries on)."""
+    return process_batch(h, [(left_rect, right_rect, left, right)], calib, dense, ransac_rounds, ransac_threshold, plane_max_distance,
+                         zgap_percentile, min_points, [seed], keep_xyzc, [xyzc_out])[0]
+
+
+def process_batch(h, frames, calib, dense, ransac_rounds=400, ransac_threshold=1.0, plane_max_distance=1.5, zgap_percentile=99.0,
+                  min_points=100, seeds=None, keep_xyzc=True, xyzc_out=None):
+    """frames: list of (left_rect, right_rect[, left, right]) of one size.  ONE batched dense-matcher run for all of them
+    (the aggregation sweeps walk the bands of all frames in one launch each), then the per-frame stages.
+    xyzc_out: None or one reusable buffer per frame (the returned FrameResult.xyzc are views of them)."""
+    n = len(frames)
+    seeds = seeds if seeds is not None else [None] * n
+    outs = xyzc_out if xyzc_out is not None else [None] * n
+    rl, rr = calib["roi_left"], calib["roi_right"]
+    ms0, lap0 = _clock()
+    lcs = [np.ascontiguousarray(f[0][rl[1]:rl[1] + rl[3], rl[0]:rl[0] + rl[2]]) for f in frames]
+    rcs = [np.ascontiguousarray(f[1][rr[1]:rr[1] + rr[3], rr[0]:rr[0] + rr[2]]) for f in frames]
+    h.dense_stereo_batch(lcs, rcs, dense)                # the disparities stay on the device for the triangulation
+    lap0("dense")
+    results = []
+    for i, f in enumerate(frames):
+        ms, lap = _clock()
+        ms["dense"] = ms0["dense"] / n
+        left = f[2] if len(f) > 2 and f[2] is not None else f[0]
+        right = f[3] if len(f) > 3 and f[3] is not None else f[1]
+        h.dense_select(i)
+        npts = h.triangulate_from_dense(left, right, calib, f[0].shape)
+        lap("triangulate")
+        if npts < min_points:
+            raise RuntimeError("too few triangulated points (%d)" % npts)
+        plane, npts, buf = _mesh_stages(h, rr, ransac_rounds, ransac_threshold, plane_max_distance, zgap_percentile, seeds[i],
+                                        keep_xyzc, outs[i], ms, lap)
+        results.append(FrameResult(plane, npts, buf, ms))
+    return results
+
+
+def run_sequence(frames, calib, dense, device=0, rank=0, world=1, dist=None, handle=None, xyzc_out=None, batch=1, **kw):
+    """frames: list of callables or (left_rect, right_rect[, left, right]) tuples, one per frame of the WHOLE sequence;
+    this rank processes frames rank, rank+world, ...  Returns (mean_plane, planes[n_frames][4], results of the owned frames).
+
+    handle: one capi.Handle or a list of them; every handle works through its share of the owned frames `batch` at a time
+    (one batched matcher run per `batch` frames: process_batch), one host thread and one stream per handle (the C calls
+    release the GIL), so the copies and mesh stages of one batch overlap the matcher of another.  Frame i gets seed i
+    either way, so the planes depend on neither.  xyzc_out: None, or a list with `batch` reusable buffers per handle.
+    Without `handle` one is created and destroyed here (the arena is several GB per frame of a batch: keep one across
+    calls when processing more than one sequence).
+    dist: a torch.distributed module for the final plane reduction, or None; see also capi.Handle.plane_allreduce for the
+    same reduction through the C ABI's own NCCL communicator."""
     from . import launcher
     own = handle is None
     hs = [capi.Handle(device)] if own else (list(handle) if isinstance(handle, (list, tuple)) else [handle])
-    outs = list(xyzc_out) if isinstance(xyzc_out, (list, tuple)) else [xyzc_out] * len(hs)
-    if len(hs) > 1 and xyzc_out is not None and len({id(o) for o in outs}) != len(hs):
-        raise ValueError("one xyzc_out buffer per handle is needed when frames are in flight concurrently")
+    batch = max(1, int(batch))
+    if xyzc_out is None:
+        outs = [None] * len(hs)
+    else:
+        outs = list(xyzc_out)
+        if len(outs) != len(hs) or any(len(o) < batch for o in outs):
+            raise ValueError("xyzc_out needs one list of `batch` buffers per handle")
     try:
         owned = launcher.shard(len(frames), rank, world)
         results = [None] * len(owned)
         errors = []
+        chunks = [list(range(j, min(j + batch, len(owned)))) for j in range(0, len(owned), batch)]
 
         def work(k):
             try:
-                for j in range(k, len(owned), len(hs)):
-                    i = owned[j]
-                    f = frames[i]() if callable(frames[i]) else frames[i]
-                    results[j] = process_frame(hs[k], f[0], f[1], calib, dense, seed=i, xyzc_out=outs[k], **kw)
+                for c in chunks[k::len(hs)]:
+                    fr = []
+                    for j in c:
+                        f = frames[owned[j]]
+                        fr.append(f() if callable(f) else f)
+                    res = process_batch(hs[k], fr, calib, dense, seeds=[owned[j] for j in c],
+                                        xyzc_out=None if outs[k] is None else outs[k][:len(c)], **kw)
+                    for j, r in zip(c, res):
+                        results[j] = r
             except BaseException as e:      # re-raised on the caller's thread
                 errors.append(e)
 
