@@ -245,3 +245,45 @@ def test_workdir_run_matches_oracle_pipeline(tmp_path, rounds, thr, expect_plane
     assert rec.shape[0] == n
     assert np.abs(rec["p"] - p3d[mask].astype(np.float32)).max() <= 1e-5 * np.abs(p3d[mask]).max()
     assert np.array_equal(rec["c"], np.repeat(tri["color"][mask][:, None], 3, axis=1))
+
+
+@pytest.mark.gpu
+def test_batch_mode_equals_one_process_per_frame(tmp_path):
+    """`wass_stereo --batch <config> <wd>...` (one process, one warm arena, one batched matcher run per --batch-size frames,
+    PNG decode of the next frames on a second thread) leaves in every workdir exactly what one process per frame leaves
+    (cli/wasscli/wasscli.py:326-346), and writes the planes in frame order."""
+    from wass_b200 import synth, workdir
+    W, H, D, n = 320, 240, 48, 5
+    c = synth.make_calibration(W, H)
+    cfg = tmp_path / "stereo_config.txt"
+    workdir.write_config(str(cfg), MAX_DISPARITY=D, RANDOM_SEED=5, PLANE_RANSAC_ROUNDS=40, SGM_FULL_8PATH=True)
+    single, batch = [], []
+    for i in range(n):
+        right, left, _ = synth.make_pair(W, H, D, seed=20 + i, d0=8.0 + i)
+        for tag, lst in (("s", single), ("b", batch)):
+            wd = tmp_path / ("%s_%06d_wd" % (tag, i))
+            workdir.write_workdir(str(wd), left, right, c["K0"], c["K1"], c["R"], c["T"])
+            lst.append(wd)
+    (tmp_path / "b_000003_wd" / "undistorted" / "00000001.png").unlink()       # one broken frame must not stop the others
+    (tmp_path / "s_000003_wd" / "undistorted" / "00000001.png").unlink()
+    for wd in single:
+        r = run([str(cfg), str(wd)])
+        assert (r.returncode == 0) == (wd.name != "s_000003_wd")
+    planes_out = tmp_path / "planes.txt"
+    r = run(["--batch", "--batch-size", "2", "--planes-out", str(planes_out), str(cfg)] + [str(w) for w in batch])
+    assert r.returncode == 255 and "[batch] FAILED" in r.stdout and "1 failed" in r.stdout, r.stdout[-3000:] + r.stderr[-2000:]
+    rows = [l.split() for l in planes_out.read_text().splitlines()]
+    assert len(rows) == n and rows[3] == ["nan"] * 4
+    for i, (ws, wb) in enumerate(zip(single, batch)):
+        if i == 3:
+            assert not (wb / "mesh_cam.xyzC").exists()
+            continue
+        assert (ws / "plane.txt").read_text() == (wb / "plane.txt").read_text()
+        assert (ws / "mesh_cam.xyzC").read_bytes() == (wb / "mesh_cam.xyzC").read_bytes()
+        assert (ws / "stereo_config.txt").read_text() == (wb / "stereo_config.txt").read_text()
+        for f in ("P0cam.txt", "P1cam.txt", "Cam1_poseT.txt", "plane_refinement_inliers.xyz", "00000000_s.png"):
+            assert (ws / f).read_bytes() == (wb / f).read_bytes(), f
+        assert "All done." in (wb / "wass_stereo_log.txt").read_text()
+        assert np.allclose([float(v) for v in rows[i]], [float(v) for v in (wb / "plane.txt").read_text().split()], rtol=0, atol=1e-15)
+    mean = [float(v) for v in r.stdout.split("frames: ")[1].split()[:4]]
+    assert np.allclose(mean, np.nanmean(np.array(rows, float), axis=0), atol=1e-14)

@@ -1,0 +1,34 @@
+#!/bin/bash
+# Round 2, visit G (2 GPUs): the executable's new tests, then everything that uses NCCL through the C ABI
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests/test_host_exe.py tests/test_sequence_gpu.py -x -q -m gpu > gpurun_out/pytest_exe_r2g.log 2>&1
+echo "pytest exe rc=$?"; tail -6 gpurun_out/pytest_exe_r2g.log
+timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 4 --warmup 3 > gpurun_out/bench_2gpu_r2g.json 2> gpurun_out/bench_2gpu_r2g.err
+echo "bench 2gpu rc=$?"; cut -c1-600 gpurun_out/bench_2gpu_r2g.json; grep -o '"plane_reduction.*' gpurun_out/bench_2gpu_r2g.json | cut -c1-500; tail -4 gpurun_out/bench_2gpu_r2g.err
+timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 tools/bench_sequence.py --frames 64 --mode hh --batch 8 --depth 2 > gpurun_out/seq_2gpu_r2g.json 2> gpurun_out/seq_2gpu_r2g.err
+echo "sequence 2gpu rc=$?"; cat gpurun_out/seq_2gpu_r2g.json; tail -4 gpurun_out/seq_2gpu_r2g.err
+# the C++ batch host on two ranks (one process per GPU, NCCL id through a file)
+python - <<'PY' > gpurun_out/exe_2rank_r2g.log 2>&1
+import os, subprocess, sys, tempfile, time
+import numpy as np
+sys.path.insert(0, os.getcwd())
+from wass_b200 import synth, workdir
+W, H, D, n = 640, 480, 64, 8
+c = synth.make_calibration(W, H)
+td = tempfile.mkdtemp()
+cfg = os.path.join(td, "cfg.txt"); workdir.write_config(cfg, MAX_DISPARITY=D, RANDOM_SEED=3, PLANE_RANSAC_ROUNDS=60)
+wds = []
+for i in range(n):
+    r, l, _ = synth.make_pair(W, H, D, seed=i, d0=8.0 + 0.5 * i)
+    wd = os.path.join(td, "%06d_wd" % i); workdir.write_workdir(wd, l, r, c["K0"], c["K1"], c["R"], c["T"]); wds.append(wd)
+exe = "wass_b200/bin/wass_stereo"
+ps = [subprocess.Popen([exe, "--batch", "--batch-size", "2", "--ranks", "2", "--rank", str(r), "--nccl-id-file", os.path.join(td, "id"),
+                        "--planes-out", os.path.join(td, "planes.txt"), cfg] + wds, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True) for r in range(2)]
+outs = [p.communicate(timeout=300)[0] for p in ps]
+print([p.returncode for p in ps])
+for o in outs: print("\n".join(o.strip().splitlines()[-3:]))
+rows = np.loadtxt(os.path.join(td, "planes.txt"))
+mine = np.array([[float(v) for v in open(os.path.join(w, "plane.txt")).read().split()] for w in wds])
+print("planes file in frame order:", bool(np.allclose(rows, mine, atol=1e-15)), "mean", np.nanmean(mine, axis=0))
+PY
+echo "exe 2 ranks rc=$?"; tail -9 gpurun_out/exe_2rank_r2g.log

@@ -60,7 +60,7 @@ def build_host(force=False):
     os.makedirs(os.path.dirname(exe), exist_ok=True)
     deps = srcs + glob.glob(os.path.join(host, "*.hpp")) + glob.glob(os.path.join(ROOT, "include", "*.h")) + [LIB]
     if force or _newer(deps, exe):
-        cmd = [CXX, "-O2", "-std=c++17", "-Wall", "-o", exe] + srcs + ["-L" + HERE, "-lwassgpu", "-lz", "-Wl,-rpath,$ORIGIN/.."]
+        cmd = [CXX, "-O2", "-std=c++17", "-Wall", "-pthread", "-o", exe] + srcs + ["-L" + HERE, "-lwassgpu", "-lz", "-Wl,-rpath,$ORIGIN/.."]
         subprocess.check_call(cmd)
     return exe
 

@@ -190,7 +190,7 @@ int wsg_run_sgbm_batch(wsg_handle* h, int n, const uint8_t* const* d_img1, const
             CK(h, cudaMemsetAsync(h->bnd.p, 0, h->bnd.cap, h->stream));
             h->bnd_H = pl.H; h->bnd_W1 = pl.W1; h->bnd_K = pl.K; h->bnd_n = n;
         }
-        const bool fused_wta = impl == WSG_AGG_SWEEPS_WTA && pl.uniq < 100;   // the in-sweep WTA needs 100-uniq > 0
+        const bool fused_wta = impl == WSG_AGG_SWEEPS_WTA && pl.uniq < 99;    // the in-sweep WTA needs 100-uniq >= 2 (its multiply-high division)
         if (fused_wta) {
             if ((rc = ensure(h, h->keys, npix * n * sizeof(unsigned long long)))) return rc;
             if ((rc = ensure(h, h->d1, npix * n * sizeof(int16_t)))) return rc;

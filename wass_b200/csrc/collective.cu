@@ -81,6 +81,16 @@ int wsg_nccl_comm_create(int device, int nranks, int rank, const unsigned char i
     ncclComm_t c = nullptr;
     const ncclResult_t r = n.CommInitRank(&c, nranks, u, rank);
     if (r != ncclSuccess) return fail(std::string("ncclCommInitRank: ") + n.GetErrorString(r));
+    // NCCL connects the ranks lazily, inside the first collective (~2 s on an NVSwitch box): pay that here, once, so that
+    // the plane reduction at the end of a sequence costs what 40 bytes over NVLink cost
+    double* d = nullptr;
+    if (cudaMalloc(&d, 16 * sizeof(double)) == cudaSuccess) {
+        cudaMemset(d, 0, 16 * sizeof(double));
+        const ncclResult_t w = n.AllReduce(d, d + 8, 5, ncclDouble, ncclSum, c, (cudaStream_t)0);
+        cudaStreamSynchronize((cudaStream_t)0);
+        cudaFree(d);
+        if (w != ncclSuccess) { n.CommDestroy(c); return fail(std::string("ncclAllReduce (warm-up): ") + n.GetErrorString(w)); }
+    }
     *comm = c;
     return WSG_OK;
 }

@@ -22,7 +22,7 @@ static constexpr int WDT = 32;             // disparities per CTA
 static constexpr int WDTP = 32;            // u16 per column in shared memory (64 B, no padding: columns are swizzled, see wcol)
 static constexpr int WRB = 256;            // rows per band
 static constexpr int WMAXSW = 8;           // windows up to 17
-static constexpr int WRVPAD = 4;
+static constexpr int WRVPAD = 40;           // puts the second table copy half a bank line (16 words) away from the first
 
 // XT = output columns per CTA: 128 (one CTA per SM) or 64 (two CTAs per SM at the reference's window)
 template <int XT> struct WideCfg {
@@ -32,8 +32,11 @@ template <int XT> struct WideCfg {
     static constexpr int GB = XT / CPT * 4;                // stage P2 threads: XT/CPT column groups x 4 groups of 8 disparities
     static constexpr int CT = P1 + GB;
     static constexpr int VT = (NCOL + WDT + 4) / 2 * 2;    // entries of the reversed img2 tables
-    static constexpr int RV = 2 * 8 * VT + WRVPAD;         // s16 per img2 table set (two copies, one element apart)
+    static constexpr int NTAB = 6;                         // img2 tables per set: V, Vlo, -Vhi for the two channels (-V is made in the ALU)
+    static constexpr int RV = 2 * NTAB * VT + WRVPAD;      // s16 per img2 table set (two copies, one element apart)
     static constexpr int CTAS = XT == 64 ? 2 : 1;
+    // the two parity copies are read by one LDS (even / odd lanes of a 24-entry span): their bank ranges must not overlap
+    static_assert(((NTAB * VT + WRVPAD) / 2) % 32 >= 12 && ((NTAB * VT + WRVPAD) / 2) % 32 <= 20, "table copies share banks");
 };
 
 // Physical column of logical column c in the pd / ring arrays.  A quarter-warp of a 16-byte access covers two columns
@@ -119,7 +122,7 @@ __global__ void __launch_bounds__(WideCfg<XT>::CT, WideCfg<XT>::CTAS) cost_wide_
     const int p1cc = (tid >> 6) * 16 + ((tid & 31) >> 1), p1gg = (tid & 1) + ((tid >> 4) & 2);
     const bool p1on = tid < WP1 && p1cc < ncol, p1real = d0 + 8 * p1gg < p.D;
     const int p1i0 = (xb - (p.minX1 + min(max(x0 - p.SW2 + p1cc, 0), p.W1 - 1))) + 8 * p1gg;
-    const int p1rv = (p1i0 & 1) * (8 * WVT + WRVPAD) + (p1i0 & ~1);      // s16 offset into one img2 table set
+    const int p1rv = (p1i0 & 1) * (Cfg::NTAB * WVT + WRVPAD) + (p1i0 & ~1);      // s16 offset into one img2 table set
     const int p1pd = pd_off<Cfg::CPT>(p1cc, p1gg);
 
     // T addressing: threads [0,ncol) fetch an img1 column, [ncol, ncol+WVT) an img2 table entry
@@ -151,10 +154,11 @@ __global__ void __launch_bounds__(WideCfg<XT>::CT, WideCfg<XT>::CTAS) cost_wide_
                     unsigned res[4];
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
-                        const unsigned V0 = rvw[0 * (WVT / 2) + k], nV0 = rvw[1 * (WVT / 2) + k];
-                        const unsigned Vl0 = rvw[2 * (WVT / 2) + k], nVh0 = rvw[3 * (WVT / 2) + k];
-                        const unsigned V1 = rvw[4 * (WVT / 2) + k], nV1 = rvw[5 * (WVT / 2) + k];
-                        const unsigned Vl1 = rvw[6 * (WVT / 2) + k], nVh1 = rvw[7 * (WVT / 2) + k];
+                        // six table words per disparity pair; -V costs two ALU instructions (~V + 1 per half), a seventh and
+                        // eighth table would cost two more shared-memory wavefronts per warp -- and that pipe bounds the kernel
+                        const unsigned V0 = rvw[0 * (WVT / 2) + k], Vl0 = rvw[1 * (WVT / 2) + k], nVh0 = rvw[2 * (WVT / 2) + k];
+                        const unsigned V1 = rvw[3 * (WVT / 2) + k], Vl1 = rvw[4 * (WVT / 2) + k], nVh1 = rvw[5 * (WVT / 2) + k];
+                        const unsigned nV0 = __vadd2(~V0, 0x00010001u), nV1 = __vadd2(~V1, 0x00010001u);
                         // per channel: c0 = max(0,u-vhi,vlo-u), c1 = max(0,v-uhi,ulo-v), c = min(c0,c1)
                         const unsigned e0 = __vimax_s16x2_relu(__vadd2(ua.x, nVh0), __vadd2(Vl0, ua.y));
                         const unsigned e1 = __vimax_s16x2_relu(__vadd2(V0, ua.w), __vadd2(ua.z, nV0));
@@ -190,13 +194,12 @@ __global__ void __launch_bounds__(WideCfg<XT>::CT, WideCfg<XT>::CTAS) cost_wide_
                     o[first] = first ? c1v : c0v;
                     o[first ^ 1] = first ? c0v : c1v;
                 } else {
-                    const int16_t val[8] = {(int16_t)v0, (int16_t)-v0, (int16_t)l0, (int16_t)-h0,
-                                            (int16_t)v1, (int16_t)-v1, (int16_t)l1, (int16_t)-h1};
+                    const int16_t val[Cfg::NTAB] = {(int16_t)v0, (int16_t)l0, (int16_t)-h0, (int16_t)v1, (int16_t)l1, (int16_t)-h1};
                     int16_t* t = rv + b * WRV;
 #pragma unroll
-                    for (int qn = 0; qn < 8; ++qn) {
-                        t[(0 * 8 + qn) * WVT + te] = val[qn];                              // copy A: rv[i]
-                        if (te > 0) t[WRVPAD + (1 * 8 + qn) * WVT + te - 1] = val[qn];     // copy B: rv[i+1]
+                    for (int qn = 0; qn < Cfg::NTAB; ++qn) {
+                        t[(0 * Cfg::NTAB + qn) * WVT + te] = val[qn];                              // copy A: rv[i]
+                        if (te > 0) t[WRVPAD + (1 * Cfg::NTAB + qn) * WVT + te - 1] = val[qn];     // copy B: rv[i+1]
                     }
                 }
             }

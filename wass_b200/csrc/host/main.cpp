@@ -19,6 +19,8 @@
 #include <sstream>
 #include <stdexcept>
 #include <string>
+#include <thread>
+#include <unistd.h>
 #include <vector>
 
 using namespace wasshost;
@@ -85,6 +87,8 @@ struct Env {
     double HL[9], HR[9], HLi[9], HRi[9];
     int roi_left[4], roi_right[4];
     int disparity_compensation = 0;
+    const Image8* pre_left = nullptr;            // batch mode: images already decoded by the prefetch thread
+    const Image8* pre_right = nullptr;
     void computeP() { P0 = mul(K0, stack_matrices(Rpose0, Tpose0)); P1 = mul(K1, stack_matrices(Rpose1, Tpose1)); }
     void swapLeftRight()   // wass_stereo.cpp:262-297
     {
@@ -163,10 +167,12 @@ bool load_data(Env& env, const Config& cfg)   // wass_stereo.cpp:337-442
     if (env.K0.rows != 3 || env.K0.cols != 3 || env.K1.rows != 3 || env.K1.cols != 3) { LOGE << "invalid intrinsics"; return false; }
     env.intr_left = env.K0; env.intr_right = env.K1;
     env.computeP();
-    if (!read_png_gray(path(env, "undistorted/00000000.png"), env.left, &err)) { LOGE << "unable to load input images"; LOGE << err; return false; }
+    if (env.pre_left) env.left = *env.pre_left;
+    else if (!read_png_gray(path(env, "undistorted/00000000.png"), env.left, &err)) { LOGE << "unable to load input images"; LOGE << err; return false; }
     env.left_index = 0;
     LOGI << "image 0 loaded, Size: " << env.left.cols << "x" << env.left.rows;
-    if (!read_png_gray(path(env, "undistorted/00000001.png"), env.right, &err)) { LOGE << "unable to load input images"; LOGE << err; return false; }
+    if (env.pre_right) env.right = *env.pre_right;
+    else if (!read_png_gray(path(env, "undistorted/00000001.png"), env.right, &err)) { LOGE << "unable to load input images"; LOGE << err; return false; }
     env.right_index = 1;
     LOGI << "image 1 loaded, Size: " << env.right.cols << "x" << env.right.rows;
     if (env.left.cols != env.right.cols || env.left.rows != env.right.rows) { LOGE << "left and right images differ in size"; return false; }
@@ -340,84 +346,71 @@ void show_time_stats(const Timer& t)   // src/wass_stereo/render.hpp:175-191
 
 }  // namespace
 
-int main(int argc, char* argv[])
+// wsg_dense_params from the configuration (wass_stereo.cpp:742-761, 772-782)
+static wsg_dense_params make_dense_params(const Config& cfg)
 {
-    std::cout << "wass_stereo  v. " << "1.7_b200-0.1" << std::endl;
-    std::cout << "----------------------------------------------" << std::endl;
-    std::cout << " [Release] " << wsg_version() << ", OpenCV none" << std::endl << std::endl;
-    Config cfg;
-    if (argc == 1) {
-        std::cout << "Usage:" << std::endl;
-        std::cout << "wass_stereo [--genconfig] <config_file> <workdir> [--measure] [--rectify-only]" << std::endl << std::endl;
-        std::cout << "Not enough arguments, aborting." << std::endl;
-        return 0;
-    }
-    if (argc > 1 && std::string("--genconfig") == argv[1]) return save_configuration(cfg, "stereo_config.txt");
-    if (argc != 3 && argc != 4) { std::cerr << "Invalid arguments" << std::endl; return -1; }
-    Env env;
-    env.workdir = argv[2];
-    if (!exists(env.workdir)) { std::cerr << "\"" << env.workdir << "\" does not exists, aborting." << std::endl; return -1; }
-    g_logfile = new std::ofstream(path(env, "wass_stereo_log.txt").c_str());
+    wsg_dense_params dp;
+    wsg_dense_params_default(&dp);
+    dp.MIN_DISPARITY = cfg.geti("MIN_DISPARITY"); dp.MAX_DISPARITY = cfg.geti("MAX_DISPARITY"); dp.WINSIZE = cfg.geti("WINSIZE");
+    dp.DENSE_SCALE = cfg.getd("DENSE_SCALE"); dp.DISPARITY_OFFSET = cfg.geti("DISPARITY_OFFSET");
+    dp.DISP_DILATE_STEPS = cfg.geti("DISP_DILATE_STEPS"); dp.DISP_EROSION_STEPS = cfg.geti("DISP_EROSION_STEPS");
+    dp.DENSE_P1_MULT = cfg.geti("DENSE_P1_MULT"); dp.DENSE_P2_MULT = cfg.geti("DENSE_P2_MULT");
+    dp.DENSE_UNIQUENESS_RATIO = cfg.geti("DENSE_UNIQUENESS_RATIO"); dp.DENSE_DISP12MAXDIFF = cfg.geti("DENSE_DISP12MAXDIFF");
+    dp.DENSE_PREFILTER_CAP = cfg.geti("DENSE_PREFILTER_CAP"); dp.DENSE_SPECKLE_RANGE = cfg.geti("DENSE_SPECKLE_RANGE");
+    dp.DENSE_SPECKLE_WINDOW_SIZE = cfg.geti("DENSE_SPECKLE_WINDOW_SIZE");
+    dp.mode = cfg.getb("SGM_FULL_8PATH") ? WSG_MODE_HH : WSG_MODE_SGBM;
+    dp.MEDIAN_FILTER_WSIZE = cfg.geti("MEDIAN_FILTER_WSIZE");
+    dp.DENSE_DISPARITY_BIGGEST_COMPONENT_THRESHOLD = cfg.geti("DENSE_DISPARITY_BIGGEST_COMPONENT_THRESHOLD");
+    return dp;
+}
+
+// Everything up to the dense matcher: load_data, poses, rectify, poses (wass_stereo.cpp:1877-1926).
+// Returns 0, or -1 on failure.
+static int stage_load_rectify(Env& env, const Config& cfg, wsg_handle* h)
+{
     LOG_SCOPE("wass_stereo");
-    {
-        LOGI << "Loading configuration file " << argv[1];
-        std::ifstream ifs(argv[1]);
-        if (!ifs.is_open()) { LOGE << "Unable to load " << argv[1]; return -1; }
-        try { cfg.load(ifs); } catch (std::runtime_error& er) { LOGE << er.what(); return -1; }
-        if (save_configuration(cfg, path(env, "stereo_config.txt")) != 0) LOGE << "Unable to save stereo configuration file";
-    }
-    if (cfg.geti("RANDOM_SEED") == -1) srand((unsigned)time(0));
-    else { srand(cfg.geti("RANDOM_SEED")); LOGI << "random seed set to: " << cfg.geti("RANDOM_SEED"); }
+    LOGI << "Reconstructing \"" << env.workdir << "\"";
+    env.timer.start();
+    env.cam_distance = 1.0;
+    if (!load_data(env, cfg)) return -1;
+    env.timer.mark("Data load");
+    std::cout << "[P|10|100]" << std::endl;
+    save_poses(env);
+    if (!rectify(env, cfg, h)) return -1;   // the reference ignores this return value and runs on undefined state
+    env.timer.mark("Rectification");
+    std::cout << "[P|20|100]" << std::endl;
+    LOG_SCOPE("wass_stereo");
+    save_poses(env);
+    return 0;
+}
 
-    wsg_handle* h = nullptr;
-    int device = 0;
-    if (const char* e = getenv("WASS_GPU_DEVICE")) device = atoi(e);
-    if (wsg_create(device, &h) != WSG_OK) { LOGE << "no usable CUDA device " << device << " (this build has no CPU path)"; return -1; }
+static void log_dense_begin(Env& env, const wsg_dense_params& dp)
+{
+    LOG_SCOPE("sgbm_dense_stereo");
+    if (dp.MEDIAN_FILTER_WSIZE >= 3) LOGI << "applying median filter (window size " << dp.MEDIAN_FILTER_WSIZE << " px.)";
+    if (dp.DENSE_DISPARITY_BIGGEST_COMPONENT_THRESHOLD > 0) LOGI << "extracting the biggest connected component from the disparity map";
+    LOGI << "Disparity offset: " << dp.DISPARITY_OFFSET << " px";
+    env.disparity_compensation = dp.DISPARITY_OFFSET > 0 ? 0 : -dp.DISPARITY_OFFSET;
+    LOGI << "computing dense disparity map... (may take a while)";
+}
+
+static void log_dense_end(Env& env, wsg_handle* h)
+{
+    LOG_SCOPE("sgbm_dense_stereo");
+    wsg_sgbm_stats st;
+    if (wsg_sgbm_get_stats(h, &st) == WSG_OK && st.out_of_domain)
+        LOGE << "matching cost range exceeds int16 headroom (max cost " << st.max_cost << "): results may deviate from OpenCV";
+    LOGI << "dense stereo completed successfully";
+    env.timer.mark("Dense Stereo");
+    std::cout << "[P|40|100]" << std::endl;
+}
+
+// Everything after the dense matcher, on the disparity the handle holds: triangulation, outlier removal, plane, export
+// (wass_stereo.cpp:1981-2141).  plane_out: the four numbers of plane.txt (NaN on a soft RANSAC failure).  Returns 0 / -1.
+static int stage_after_dense(Env& env, const Config& cfg, wsg_handle* h, const wsg_dense_params& dp, double plane_out[4])
+{
+    for (int i = 0; i < 4; ++i) plane_out[i] = std::nan("");
     try {
-        LOGI << "Reconstructing \"" << env.workdir << "\"";
-        env.timer.start();
-        env.cam_distance = 1.0;
-        if (!load_data(env, cfg)) return -1;
-        env.timer.mark("Data load");
-        std::cout << "[P|10|100]" << std::endl;
-        save_poses(env);
-        if (!rectify(env, cfg, h)) return -1;   // the reference ignores this return value and runs on undefined state
-        env.timer.mark("Rectification");
-        std::cout << "[P|20|100]" << std::endl;
-        LOG_SCOPE("wass_stereo");
-        save_poses(env);
-        if (argc == 4 && std::string("--rectify-only") == argv[3]) { LOGI << "All done."; return 0; }
-        if (argc == 4 && std::string("--measure") == argv[3]) { LOGE << "--measure needs the interactive HighGUI point picker; not available in this build"; return -1; }
-
-        // ---- dense stereo (wass_stereo.cpp:764-1020)
-        LOG_SCOPE("sgbm_dense_stereo");
-        wsg_dense_params dp;
-        wsg_dense_params_default(&dp);
-        dp.MIN_DISPARITY = cfg.geti("MIN_DISPARITY"); dp.MAX_DISPARITY = cfg.geti("MAX_DISPARITY"); dp.WINSIZE = cfg.geti("WINSIZE");
-        dp.DENSE_SCALE = cfg.getd("DENSE_SCALE"); dp.DISPARITY_OFFSET = cfg.geti("DISPARITY_OFFSET");
-        dp.DISP_DILATE_STEPS = cfg.geti("DISP_DILATE_STEPS"); dp.DISP_EROSION_STEPS = cfg.geti("DISP_EROSION_STEPS");
-        dp.DENSE_P1_MULT = cfg.geti("DENSE_P1_MULT"); dp.DENSE_P2_MULT = cfg.geti("DENSE_P2_MULT");
-        dp.DENSE_UNIQUENESS_RATIO = cfg.geti("DENSE_UNIQUENESS_RATIO"); dp.DENSE_DISP12MAXDIFF = cfg.geti("DENSE_DISP12MAXDIFF");
-        dp.DENSE_PREFILTER_CAP = cfg.geti("DENSE_PREFILTER_CAP"); dp.DENSE_SPECKLE_RANGE = cfg.geti("DENSE_SPECKLE_RANGE");
-        dp.DENSE_SPECKLE_WINDOW_SIZE = cfg.geti("DENSE_SPECKLE_WINDOW_SIZE");
-        dp.mode = cfg.getb("SGM_FULL_8PATH") ? WSG_MODE_HH : WSG_MODE_SGBM;
-        dp.MEDIAN_FILTER_WSIZE = cfg.geti("MEDIAN_FILTER_WSIZE");
-        dp.DENSE_DISPARITY_BIGGEST_COMPONENT_THRESHOLD = cfg.geti("DENSE_DISPARITY_BIGGEST_COMPONENT_THRESHOLD");
-        if (dp.MEDIAN_FILTER_WSIZE >= 3) LOGI << "applying median filter (window size " << dp.MEDIAN_FILTER_WSIZE << " px.)";
-        if (dp.DENSE_DISPARITY_BIGGEST_COMPONENT_THRESHOLD > 0) LOGI << "extracting the biggest connected component from the disparity map";
-        LOGI << "Disparity offset: " << dp.DISPARITY_OFFSET << " px";
-        env.disparity_compensation = dp.DISPARITY_OFFSET > 0 ? 0 : -dp.DISPARITY_OFFSET;
-        LOGI << "computing dense disparity map... (may take a while)";
-        std::vector<float> disp_roi((size_t)env.right_crop.rows * env.right_crop.cols);
-        WSG_CHECK(wsg_dense_stereo(h, env.left_crop.px.data(), env.right_crop.px.data(), env.right_crop.rows, env.right_crop.cols,
-                                   env.right_crop.cols, &dp, disp_roi.data(), nullptr));
-        wsg_sgbm_stats st;
-        if (wsg_sgbm_get_stats(h, &st) == WSG_OK && st.out_of_domain)
-            LOGE << "matching cost range exceeds int16 headroom (max cost " << st.max_cost << "): results may deviate from OpenCV";
-        LOGI << "dense stereo completed successfully";
-        env.timer.mark("Dense Stereo");
-        std::cout << "[P|40|100]" << std::endl;
-
         // ---- triangulation (wass_stereo.cpp:1039-1386)
         LOG_SCOPE("triangulate");
         wsg_calib cal;
@@ -509,7 +502,11 @@ int main(int argc, char* argv[])
                 WSG_CHECK(wsg_mesh_download(h, valid.data(), xyz.data(), nullptr));
                 const bool ct = rp.PLANE_USE_CENTRAL_THIRD_ONLY != 0;
                 const int umin = ct ? mw / 4 : 0, umax = ct ? mw * 3 / 4 : mw - 1, vmin = ct ? mh / 4 : 0, vmax = ct ? mh * 2 / 3 : mh - 1;
-                std::ofstream ofs(path(env, "plane_refinement_inliers.xyz").c_str());
+                // (same bytes as `ofs << x << " " << y << " " << z << std::endl` -- %g is the stream's default format --
+                // without one flush per line: ~460 000 lines at the benchmark size)
+                std::string txt;
+                txt.reserve(np / 8);
+                char line[128];
                 size_t idx = 0;
                 for (int v = vmin; v <= vmax; ++v)
                     for (int u = umin; u <= umax; ++u) {
@@ -518,10 +515,11 @@ int main(int argc, char* argv[])
                         const double x = xyz[3 * i], y = xyz[3 * i + 1], z = xyz[3 * i + 2];
                         if (x > rp.PLANE_REFINE_XMIN && x < rp.PLANE_REFINE_XMAX && y > rp.PLANE_REFINE_YMIN && y < rp.PLANE_REFINE_YMAX &&
                             sqrt(x * x + y * y + z * z) < rp.PLANE_REFINEMENT_MAX_DISTANCE) {
-                            if (idx % 10 == 0) ofs << x << " " << y << " " << z << std::endl;
+                            if (idx % 10 == 0) txt.append(line, (size_t)snprintf(line, sizeof line, "%g %g %g\n", x, y, z));
                             ++idx;
                         }
                     }
+                write_file(path(env, "plane_refinement_inliers.xyz"), txt.data(), txt.size());
             }
             unsigned long long nin = 0;
             WSG_CHECK(wsg_mesh_refine_plane(h, &rp, plane, &nin));
@@ -560,6 +558,7 @@ int main(int argc, char* argv[])
                 if (!write_file(path(env, "mesh_cam.xyzbin"), buf.data(), nb)) { LOGE << "unable to save mesh data"; return -1; }
             }
         }
+        if (ok) for (int i = 0; i < 4; ++i) plane_out[i] = plane[i];
         LOG_SCOPE("wass_stereo");
         env.timer.stop();
         std::cout << "[P|100|100]" << std::endl;
@@ -569,6 +568,232 @@ int main(int argc, char* argv[])
         LOGE << e.what();
         return -1;
     }
+    return 0;
+}
+
+static void print_usage()
+{
+    std::cout << "Usage:" << std::endl;
+    std::cout << "wass_stereo [--genconfig] <config_file> <workdir> [--measure] [--rectify-only]" << std::endl << std::endl;
+}
+
+// ---- batch mode (an extension; the reference runs one process per frame, cli/wasscli/wasscli.py:326-346) ------------------
+//   wass_stereo --batch [--batch-size B] [--planes-out FILE] [--ranks N --rank R --nccl-id-file F]
+//               <config_file> (<workdir>... | --workdirs-from FILE)
+// One process, one warm device arena: B frames at a time go through ONE batched matcher run (wsg_dense_stereo_batch), the
+// PNGs of the next B frames are decoded by a second thread meanwhile.  Every workdir gets exactly the files and the log
+// of a single-frame run.  With --ranks N this process takes the workdirs i = R (mod N); the mean plane over ALL ranks'
+// frames comes from one NCCL all-reduce (wsg_plane_allreduce), the per-frame planes from an all-gather, and rank 0 writes
+// them in frame order to --planes-out (the reference's planes.txt is in completion order, wasscli.py:343).
+struct Prefetched { Image8 img0, img1; bool ok0 = false, ok1 = false; };
+
+static int run_batch(int argc, char* argv[])
+{
+    int B = 8, ranks = 1, rank = 0;
+    std::string planes_out, id_file, cfg_file, list_file;
+    std::vector<std::string> all;
+    for (int i = 2; i < argc; ++i) {
+        const std::string a = argv[i];
+        auto next = [&]() -> std::string { if (i + 1 >= argc) throw std::runtime_error("missing value after " + a); return argv[++i]; };
+        try {
+            if (a == "--batch-size") B = std::max(1, atoi(next().c_str()));
+            else if (a == "--planes-out") planes_out = next();
+            else if (a == "--ranks") ranks = std::max(1, atoi(next().c_str()));
+            else if (a == "--rank") rank = atoi(next().c_str());
+            else if (a == "--nccl-id-file") id_file = next();
+            else if (a == "--workdirs-from") list_file = next();
+            else if (cfg_file.empty()) cfg_file = a;
+            else all.push_back(a);
+        } catch (std::runtime_error& e) { std::cerr << e.what() << std::endl; return -1; }
+    }
+    if (!list_file.empty()) {
+        std::ifstream f(list_file.c_str());
+        if (!f.is_open()) { std::cerr << "cannot open " << list_file << std::endl; return -1; }
+        for (std::string l; std::getline(f, l);) { while (!l.empty() && (l.back() == '\r' || l.back() == ' ')) l.pop_back(); if (!l.empty()) all.push_back(l); }
+    }
+    if (cfg_file.empty() || all.empty() || rank < 0 || rank >= ranks || (ranks > 1 && id_file.empty())) {
+        std::cerr << "Invalid arguments (batch mode: --batch [--batch-size B] [--planes-out F] [--ranks N --rank R --nccl-id-file F] "
+                     "<config_file> <workdir>... | --workdirs-from FILE)" << std::endl;
+        return -1;
+    }
+    Config cfg;
+    {
+        std::ifstream ifs(cfg_file.c_str());
+        if (!ifs.is_open()) { std::cerr << "Unable to load " << cfg_file << std::endl; return -1; }
+        try { cfg.load(ifs); } catch (std::runtime_error& er) { std::cerr << er.what() << std::endl; return -1; }
+    }
+    int device = rank;
+    if (const char* e = getenv("WASS_GPU_DEVICE")) device = atoi(e);
+    wsg_handle* h = nullptr;
+    if (wsg_create(device, &h) != WSG_OK) { std::cerr << "no usable CUDA device " << device << " (this build has no CPU path)" << std::endl; return -1; }
+    std::vector<int> mine;
+    for (int i = rank; i < (int)all.size(); i += ranks) mine.push_back(i);
+    const wsg_dense_params dp = make_dense_params(cfg);
+    std::vector<double> planes(mine.size() * 4, std::nan(""));
+    int failed = 0;
+    const double t_begin = Timer::now();
+
+    auto prefetch = [&](size_t g0, std::vector<Prefetched>* out) {
+        out->clear();
+        for (size_t j = g0; j < std::min(g0 + (size_t)B, mine.size()); ++j) {
+            Prefetched p; std::string err;
+            p.ok0 = read_png_gray(all[mine[j]] + "/undistorted/00000000.png", p.img0, &err);
+            p.ok1 = read_png_gray(all[mine[j]] + "/undistorted/00000001.png", p.img1, &err);
+            out->push_back(std::move(p));
+        }
+    };
+    std::vector<Prefetched> cur, nxt;
+    prefetch(0, &cur);
+    for (size_t g0 = 0; g0 < mine.size(); g0 += B) {
+        const size_t g1 = std::min(g0 + (size_t)B, mine.size());
+        std::thread loader;
+        if (g1 < mine.size()) loader = std::thread(prefetch, g1, &nxt);
+        std::vector<Env> envs(g1 - g0);
+        std::vector<std::ofstream*> logs(g1 - g0, nullptr);
+        std::vector<int> state(g1 - g0, 0);                      // 0 ready for the matcher, -1 failed
+        for (size_t j = g0; j < g1; ++j) {
+            Env& env = envs[j - g0];
+            env.workdir = all[mine[j]];
+            if (!exists(env.workdir)) { std::cerr << "\"" << env.workdir << "\" does not exists" << std::endl; state[j - g0] = -1; continue; }
+            logs[j - g0] = new std::ofstream(path(env, "wass_stereo_log.txt").c_str());
+            g_logfile = logs[j - g0];
+            LOG_SCOPE("wass_stereo");
+            LOGI << "Loading configuration file " << cfg_file;
+            if (save_configuration(cfg, path(env, "stereo_config.txt")) != 0) LOGE << "Unable to save stereo configuration file";
+            if (cur[j - g0].ok0 && cur[j - g0].ok1) { env.pre_left = &cur[j - g0].img0; env.pre_right = &cur[j - g0].img1; }
+            if (stage_load_rectify(env, cfg, h) != 0) state[j - g0] = -1;
+            env.pre_left = env.pre_right = nullptr;
+        }
+        // frames whose crops have the same size go through the matcher together (one sequence = one size in practice)
+        std::vector<char> done(g1 - g0, 0);
+        for (size_t a0 = 0; a0 < g1 - g0; ++a0) {
+            if (state[a0] != 0 || done[a0]) continue;
+            std::vector<size_t> grp;
+            for (size_t b = a0; b < g1 - g0; ++b)
+                if (state[b] == 0 && !done[b] && envs[b].right_crop.rows == envs[a0].right_crop.rows && envs[b].right_crop.cols == envs[a0].right_crop.cols)
+                    grp.push_back(b);
+            std::vector<const uint8_t*> lc, rc;
+            for (size_t b : grp) { g_logfile = logs[b]; log_dense_begin(envs[b], dp); lc.push_back(envs[b].left_crop.px.data()); rc.push_back(envs[b].right_crop.px.data()); }
+            const int rcode = wsg_dense_stereo_batch(h, (int)grp.size(), lc.data(), rc.data(), envs[a0].right_crop.rows, envs[a0].right_crop.cols,
+                                                     envs[a0].right_crop.cols, &dp, nullptr);
+            for (size_t k = 0; k < grp.size(); ++k) {
+                const size_t b = grp[k];
+                done[b] = 1;
+                g_logfile = logs[b];
+                if (rcode != WSG_OK) { LOG_SCOPE("sgbm_dense_stereo"); LOGE << "wsg_dense_stereo_batch: " << wsg_last_error(h); state[b] = -1; continue; }
+                log_dense_end(envs[b], h);
+                // the per-frame seed of a single-frame run: RANDOM_SEED (or the clock) at process start, then one rand() stream
+                // per process.  One process per SEQUENCE would couple the frames' draws, so every frame re-seeds.
+                if (cfg.geti("RANDOM_SEED") == -1) srand((unsigned)time(0) + (unsigned)mine[g0 + b]); else srand(cfg.geti("RANDOM_SEED"));
+                if (wsg_dense_select(h, (int)k) != WSG_OK || stage_after_dense(envs[b], cfg, h, dp, &planes[(g0 + b) * 4]) != 0) state[b] = -1;
+            }
+        }
+        for (size_t b = 0; b < g1 - g0; ++b) {
+            if (state[b] != 0) { ++failed; std::cout << "[batch] FAILED " << envs[b].workdir << std::endl; }
+            if (logs[b]) { logs[b]->close(); delete logs[b]; }
+        }
+        g_logfile = nullptr;
+        if (loader.joinable()) loader.join();
+        cur.swap(nxt);
+    }
+    // ---- the sequence's mean plane (np.nanmean over planes.txt, wassgridsurface.py:672-678)
+    double acc[5] = {0, 0, 0, 0, 0}, mean[4];
+    for (size_t j = 0; j < mine.size(); ++j) wsg_plane_mean_accumulate(acc, &planes[j * 4]);
+    long long nfr = (long long)acc[4];
+    std::vector<double> every(all.size() * 4, std::nan(""));
+    if (ranks > 1) {
+        unsigned char id[WSG_NCCL_UNIQUE_ID_BYTES];
+        if (rank == 0) {
+            if (wsg_nccl_unique_id(id) != WSG_OK) { std::cerr << wsg_collective_last_error() << std::endl; return -1; }
+            write_file(id_file + ".tmp", (const char*)id, sizeof id);
+            rename((id_file + ".tmp").c_str(), id_file.c_str());
+        } else {
+            for (int tries = 0;; ++tries) {
+                std::ifstream f(id_file.c_str(), std::ios::binary);
+                if (f.is_open() && f.read((char*)id, sizeof id)) break;
+                if (tries > 6000) { std::cerr << "no NCCL id in " << id_file << std::endl; return -1; }
+                usleep(10000);
+            }
+        }
+        void* comm = nullptr;
+        if (wsg_nccl_comm_create(device, ranks, rank, id, &comm) != WSG_OK) { std::cerr << wsg_collective_last_error() << std::endl; return -1; }
+        if (wsg_plane_allreduce(h, comm, acc, mean, &nfr) != WSG_OK) { std::cerr << wsg_last_error(h) << std::endl; return -1; }
+        const int per = (int)((all.size() + ranks - 1) / ranks);
+        std::vector<double> padded((size_t)per * 4, std::nan("")), gathered((size_t)per * 4 * ranks);
+        std::copy(planes.begin(), planes.end(), padded.begin());
+        if (wsg_plane_allgather(h, comm, ranks, padded.data(), per, gathered.data()) != WSG_OK) { std::cerr << wsg_last_error(h) << std::endl; return -1; }
+        for (int r = 0; r < ranks; ++r)
+            for (int j = 0; r + j * ranks < (int)all.size(); ++j)
+                for (int k = 0; k < 4; ++k) every[(size_t)(r + j * ranks) * 4 + k] = gathered[((size_t)r * per + j) * 4 + k];
+        wsg_nccl_comm_destroy(comm);
+        if (rank == 0) remove(id_file.c_str());
+    } else {
+        wsg_plane_mean_finish(acc, mean);
+        every = planes;
+    }
+    const double dt = Timer::now() - t_begin;
+    std::cout << std::setprecision(17);
+    std::cout << "[batch] rank " << rank << "/" << ranks << ": " << mine.size() << " workdirs in " << std::setprecision(4) << dt << " s ("
+              << (mine.empty() ? 0.0 : dt / mine.size() * 1e3) << " ms per workdir), " << failed << " failed" << std::endl;
+    if (rank == 0) {
+        std::cout << std::setprecision(17) << "[batch] mean plane over " << nfr << " frames: " << mean[0] << " " << mean[1] << " " << mean[2] << " " << mean[3] << std::endl;
+        if (!planes_out.empty()) {
+            std::ofstream ofs(planes_out.c_str());
+            ofs << std::setprecision(17);
+            for (size_t i = 0; i < all.size(); ++i) ofs << every[i * 4] << " " << every[i * 4 + 1] << " " << every[i * 4 + 2] << " " << every[i * 4 + 3] << "\n";
+        }
+    }
+    wsg_destroy(h);
+    return failed ? -1 : 0;
+}
+
+int main(int argc, char* argv[])
+{
+    std::cout << "wass_stereo  v. " << "1.7_b200-0.2" << std::endl;
+    std::cout << "----------------------------------------------" << std::endl;
+    std::cout << " [Release] " << wsg_version() << ", OpenCV none" << std::endl << std::endl;
+    Config cfg;
+    if (argc == 1) {
+        print_usage();
+        std::cout << "Not enough arguments, aborting." << std::endl;
+        return 0;
+    }
+    if (argc > 1 && std::string("--genconfig") == argv[1]) return save_configuration(cfg, "stereo_config.txt");
+    if (argc > 1 && std::string("--batch") == argv[1]) return run_batch(argc, argv);
+    if (argc != 3 && argc != 4) { std::cerr << "Invalid arguments" << std::endl; return -1; }
+    Env env;
+    env.workdir = argv[2];
+    if (!exists(env.workdir)) { std::cerr << "\"" << env.workdir << "\" does not exists, aborting." << std::endl; return -1; }
+    g_logfile = new std::ofstream(path(env, "wass_stereo_log.txt").c_str());
+    LOG_SCOPE("wass_stereo");
+    {
+        LOGI << "Loading configuration file " << argv[1];
+        std::ifstream ifs(argv[1]);
+        if (!ifs.is_open()) { LOGE << "Unable to load " << argv[1]; return -1; }
+        try { cfg.load(ifs); } catch (std::runtime_error& er) { LOGE << er.what(); return -1; }
+        if (save_configuration(cfg, path(env, "stereo_config.txt")) != 0) LOGE << "Unable to save stereo configuration file";
+    }
+    if (cfg.geti("RANDOM_SEED") == -1) srand((unsigned)time(0));
+    else { srand(cfg.geti("RANDOM_SEED")); LOGI << "random seed set to: " << cfg.geti("RANDOM_SEED"); }
+
+    wsg_handle* h = nullptr;
+    int device = 0;
+    if (const char* e = getenv("WASS_GPU_DEVICE")) device = atoi(e);
+    if (wsg_create(device, &h) != WSG_OK) { LOGE << "no usable CUDA device " << device << " (this build has no CPU path)"; return -1; }
+    if (stage_load_rectify(env, cfg, h) != 0) return -1;
+    if (argc == 4 && std::string("--rectify-only") == argv[3]) { LOGI << "All done."; return 0; }
+    if (argc == 4 && std::string("--measure") == argv[3]) { LOGE << "--measure needs the interactive HighGUI point picker; not available in this build"; return -1; }
+    // ---- dense stereo (wass_stereo.cpp:764-1020)
+    const wsg_dense_params dp = make_dense_params(cfg);
+    log_dense_begin(env, dp);
+    if (wsg_dense_stereo(h, env.left_crop.px.data(), env.right_crop.px.data(), env.right_crop.rows, env.right_crop.cols,
+                         env.right_crop.cols, &dp, nullptr, nullptr) != WSG_OK) {
+        LOGE << "wsg_dense_stereo: " << wsg_last_error(h);
+        return -1;
+    }
+    log_dense_end(env, h);
+    double plane[4];
+    if (stage_after_dense(env, cfg, h, dp, plane) != 0) return -1;
     wsg_destroy(h);
     return 0;
 }

@@ -113,7 +113,8 @@ struct SweepArgs {
     unsigned long long* keys;   // [nframes][H][W]  (minS, W1-1-x, d) of the best match that lands on x2 (A.5)
     int16_t* d1;                // [nframes][H][W]  left-view disparity before the LR check
     int minD, minX1, uniq, INVALID;
-    unsigned umagic;            // ceil(2^32 / (100 - uniq)), or 0 when 100 - uniq == 1
+    unsigned umagic;            // ceil(2^32 / (100 - uniq)); the fused WTA needs 100 - uniq >= 2
+    int qm1;                    // 100 - uniq - 1
 };
 
 __device__ __forceinline__ uint4 ld_volatile(const uint4* p)
@@ -162,9 +163,9 @@ __device__ __forceinline__ void wait_prog(volatile int* flag, int need, int& see
 //               subtract whose sign bits are the comparison results, against the same count inside the window.
 //   returns     key = minS << 16 | best, and nb = S(best-1) | S(best+1) << 16 | accepted << 31
 // Branch-free, so the caller can run it one pixel late, interleaved with the next pixel's path steps.  Needs
-// 0 <= uniquenessRatio < 100 (the host routes anything else to wta_kernel).
+// 0 <= uniquenessRatio < 99 (the host routes anything else to wta_kernel).
 template <int K, bool HASPAD>
-__device__ __forceinline__ void wta_eval(const unsigned (&s)[4 * K], int l, const SweepArgs& a, const int16_t* scratch,
+__device__ __forceinline__ void wta_eval(const unsigned (&s)[4 * K], int l, const SweepArgs& a, const uint16_t* scratch,
                                          unsigned& key, unsigned& nb)
 {
     constexpr int NV8 = 8 * K;
@@ -173,20 +174,21 @@ __device__ __forceinline__ void wta_eval(const unsigned (&s)[4 * K], int l, cons
     unsigned kmin = 0xFFFFFFFFu;
 #pragma unroll
     for (int e = 0; e < 4 * K; ++e) {   // register 4k+i holds disparities (8k+i, 8k+4+i) of the lane, see vec_pos
-        const int d = dlane + 8 * (e >> 2) + (e & 3);
-        const unsigned klo = s[e] * 65536u + (unsigned)d;
-        const unsigned khi = (s[e] & 0xFFFF0000u) | (unsigned)(d + 4);
+        const unsigned dlo = (unsigned)(dlane + 8 * (e >> 2) + (e & 3)), dhi = dlo + 4u;
+        const unsigned klo = s[e] * 65536u + dlo;
+        const unsigned khi = (s[e] & 0xFFFF0000u) | dhi;
         kmin = __vimin3_u32(kmin, klo, khi);
     }
     if (padlane) kmin = 0xFFFFFFFFu;
     kmin = __reduce_min_sync(FULL, kmin);
     const int minS = (int)(kmin >> 16), best = (int)(kmin & 0xFFFFu);
-    const int n = minS * 100 - 1;                                   // < 2^22
-    // floor(n / (100-uniq)): multiply-high by ceil(2^32/(100-uniq)) is exact for n < 2^22; a divisor of 1 has no such constant
-    const int Tm = n < 0 ? -1 : (a.umagic ? (int)__umulhi((unsigned)n, a.umagic) : n);
-    // packed count of S <= Tm: (0x8000 + T - S) keeps bit 15 iff T >= S (S, T <= 0x7fff: no borrow between the halves).
+    // Tm = floor((100 minS - 1) / q), q = 100 - uniq; for minS = 0 that is -1 (nothing can be below the winner).
+    // floor((n - 1) / q) = ceil(n / q) - 1 = floor((n + q - 1) / q) - 1 has a non-negative numerator for every minS, so one
+    // multiply-high by ceil(2^32 / q) does it (exact below 2^22; q = 1 has no such constant: the host routes it to wta_kernel).
+    const int Tm = (int)__umulhi((unsigned)(minS * 100 + a.qm1), a.umagic) - 1;
+    // packed count of S <= Tm: (0x8000 + T - S) keeps bit 15 iff T >= S (S <= 0x7fff; T = -1 gives 0x7fff - S: never).
     // The subtractions run on the FMA pipe; one byte gather per register pair collects the four flag bytes.
-    const unsigned T2 = ((unsigned)min(max(Tm, 0), 32767) | 0x8000u) * 0x10001u;
+    const unsigned T2 = (unsigned)(min(Tm, 32767) + 0x8000) * 0x10001u;
     const unsigned minus_one = 0u - a.one;
     int cnt = 0;
 #pragma unroll
@@ -194,14 +196,14 @@ __device__ __forceinline__ void wta_eval(const unsigned (&s)[4 * K], int l, cons
         const unsigned t0 = add_on_fma(s[e], T2, minus_one), t1 = add_on_fma(s[e + 1], T2, minus_one);     // T2 - s
         cnt += __popc(__byte_perm(t0, t1, 0x7531) & 0x80808080u);
     }
-    if (padlane || Tm < 0) cnt = 0;
+    if (padlane) cnt = 0;
     const int total = __reduce_add_sync(FULL, cnt);
-    // the winner's neighbours (clamped addresses; the values only count where they exist)
-    const int dm = max(best - 1, 0), dp = min(best + 1, a.D - 1);
-    const int sm = scratch[(dm & ~7) + vec_pos(dm & 7)], sp = scratch[(dp & ~7) + vec_pos(dp & 7)];
+    // the winner's neighbours from the copy of S in shared memory (natural disparity order); the elements at -1 and D are
+    // whatever lies beside the row's scratch area -- they only count where they exist
+    const int sm = scratch[best - 1], sp = scratch[best + 1];
     const int inwin = (minS <= Tm) + (best > 0 && sm <= Tm) + (best < a.D - 1 && sp <= Tm);
     key = kmin;
-    nb = (unsigned)sm | ((unsigned)sp << 16) | (total <= inwin ? 0x80000000u : 0u);
+    nb = (unsigned)sm | ((unsigned)(sp & 0x7FFF) << 16) | (total <= inwin ? 0x80000000u : 0u);   // (bit 31 is the flag: mask a stray sp)
 }
 
 // wta_flush (every 32 pixels): lane i holds the record of logical column xbase + i.  Sub-pixel parabola, right-view map
@@ -211,7 +213,7 @@ __device__ __forceinline__ void wta_flush(unsigned key, unsigned nb, int xl, boo
 {
     if (!valid || !(nb & 0x80000000u)) return;
     const int minS = (int)(key >> 16), best = (int)(key & 0xFFFFu);
-    const int sm = (int)(nb & 0xFFFFu), sp = (int)((nb >> 16) & 0x7FFFu);
+    const int sm = (int)(nb & 0xFFFFu), sp = (int)((nb >> 16) & 0x7FFFu);      // (a real S is <= 32767)
     const int xh = a.flip ? a.W1 - 1 - xl : xl;     // physical column in W1 space
     const int x = xh + a.minX1;
     const unsigned long long k64 = ((unsigned long long)minS << 40) | ((unsigned long long)(a.W1 - 1 - xh) << 16) |
@@ -235,7 +237,7 @@ template <int K> struct RowState {
     const uint4* cpf; const uint4* spf; uint4* scur;      // C / S prefetch cursors, S store cursor
     long long dstep;
     const uint4* ring_in; uint4* ring_out;
-    int16_t* scratch;
+    uint16_t* scratch;                                    // final S of the previous pixel, natural disparity order
     const uint4* stageC; const uint4* stageS;
     unsigned stC, stS;                                    // the same staging areas as shared-window addresses
     volatile int* prog_in; volatile int* prog_me; volatile int* prog_next;
@@ -331,8 +333,10 @@ __device__ __forceinline__ void sweep_step(RowState<K>& st, const SweepArgs& a, 
         if (x > 0 && (x & 31) == 0) wta_flush(st.rkey, st.rnb, x - 32 + l, true, a, st.keys_row, st.d1_row);
         __syncwarp();                       // all lanes are done reading the previous pixel's S
 #pragma unroll
-        for (int k = 0; k < K; ++k)
-            reinterpret_cast<uint4*>(st.scratch)[l * K + k] = make_uint4(vsn[4 * k], vsn[4 * k + 1], vsn[4 * k + 2], vsn[4 * k + 3]);
+        for (int k = 0; k < K; ++k)      // registers hold (d, d+4) pairs: undo the interleave, so that S(d) sits at scratch[d]
+            reinterpret_cast<uint4*>(st.scratch)[l * K + k] =
+                make_uint4(__byte_perm(vsn[4 * k], vsn[4 * k + 1], 0x5410), __byte_perm(vsn[4 * k + 2], vsn[4 * k + 3], 0x5410),
+                           __byte_perm(vsn[4 * k], vsn[4 * k + 1], 0x7632), __byte_perm(vsn[4 * k + 2], vsn[4 * k + 3], 0x7632));
         __syncwarp();
     } else {
 #pragma unroll
@@ -378,7 +382,7 @@ __device__ __forceinline__ void sweep_row(const uint4* __restrict__ C, uint4* __
     st.cpf = C + first; st.spf = S + first; st.scur = S + first;
     st.ring_in = smem + (size_t)r * Cfg::RING_V + l;
     st.ring_out = smem + (size_t)(r + 1) * Cfg::RING_V + l;
-    st.scratch = reinterpret_cast<int16_t*>(smem + Cfg::RINGS_V + (size_t)r * Cfg::PIX_V);
+    st.scratch = reinterpret_cast<uint16_t*>(smem + Cfg::RINGS_V + (size_t)r * Cfg::PIX_V);
     st.stageC = smem + Cfg::RINGS_V + Cfg::SCR_V + (size_t)r * PFD * Cfg::PIX_V + l;
     st.stageS = smem + Cfg::RINGS_V + Cfg::SCR_V + Cfg::STAGEC_V + (size_t)r * PFS * Cfg::PIX_V + l;
     st.stC = (unsigned)__cvta_generic_to_shared(st.stageC);
@@ -665,6 +669,7 @@ void launch_sweep(const int16_t* C, int16_t* S, int flip, int mode, int ndir, co
     a.keys = sc.keys; a.d1 = sc.d1;
     a.minD = p.minD; a.minX1 = p.minX1; a.uniq = p.uniq; a.INVALID = p.INVALID;
     a.umagic = p.uniq < 99 ? (unsigned)((0x100000000ull + (100 - p.uniq) - 1) / (unsigned)(100 - p.uniq)) : 0u;
+    a.qm1 = 100 - p.uniq - 1;
     const bool pad = p.Dp != p.D;
 #define WSG_SW_CASE(k, r, ns, m, n)                                                  \
     if (p.K == k && mode == m && ndir == n) {                                        \
