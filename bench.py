@@ -165,6 +165,7 @@ def run_reference(args, rank):
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "s16", "data": "synthetic",
             "config": {"workload": WORKLOAD, "sample": sample, "frames_per_step_per_gpu": None, "handles_in_flight_per_gpu": None,
+                       "rows_per_band": None,
                        "single_frame_ms": None, "padded_width": W_IMG + NDISP, "W1": W_IMG - 1, "l2": None,
                        "parallelism": "%d host processes" % P, "generator": "as the GPU arm (wass_b200/synth.py)",
                        "max_cost": None, "out_of_domain": None},
@@ -220,8 +221,8 @@ def run_ours(args, rank, world):
         torch.cuda.synchronize()
 
     p = wass_params(NDISP, capi.MODE_HH)
-    B, NH = max(1, args.batch), max(1, args.streams)
-    # frames shard across GPUs: rank r owns seeds r*B .. r*B+B-1 (every handle of the rank works on the same B frames)
+    B = max(1, args.batch)
+    # frames shard across GPUs: rank r owns seeds r*B .. r*B+B-1
     seeds = [rank * B + i for i in range(B)]
     frames = [make_frame(s) for s in seeds]
     H, Wp = frames[0][0].shape
@@ -229,39 +230,45 @@ def run_ours(args, rank, world):
     torch.cuda.set_stream(main)
     i1 = torch.from_numpy(np.stack([f[0] for f in frames])).cuda()
     i2 = torch.from_numpy(np.stack([f[1] for f in frames])).cuda()
-    hs, streams, dev_out, pin = [], [], [], []
-    for k in range(NH):      # one handle = one device arena (B cost + B aggregated volumes) + one CUDA stream
-        h = capi.Handle(local)
-        if args.agg_impl >= 0:
-            h.sgbm_set_impl(args.agg_impl)
-        st = torch.cuda.Stream()
-        h.set_stream(st.cuda_stream)
-        hs.append(h); streams.append(st)
-        dev_out.append(torch.empty((B, H, Wp), dtype=torch.int16, device="cuda"))
-        pin.append(([torch.from_numpy(f[0]).pin_memory() for f in frames], [torch.from_numpy(f[1]).pin_memory() for f in frames],
-                    [torch.empty((H, Wp), dtype=torch.int16).pin_memory() for _ in frames]))
+    # ONE handle = one device arena (B cost + B aggregated volumes) + one compute stream (+ two copy streams for the
+    # asynchronous host-buffer path)
+    h = capi.Handle(local)
+    if args.agg_impl >= 0:
+        h.sgbm_set_impl(args.agg_impl)
+    st = torch.cuda.Stream()
+    h.set_stream(st.cuda_stream)
+    dev_out = torch.empty((B, H, Wp), dtype=torch.int16, device="cuda")
+    pin_in1 = [torch.from_numpy(f[0]).pin_memory() for f in frames]
+    pin_in2 = [torch.from_numpy(f[1]).pin_memory() for f in frames]
+    pin_out = [[torch.empty((H, Wp), dtype=torch.int16).pin_memory() for _ in frames] for _ in range(2)]      # one set per slot
     torch.cuda.synchronize()
 
-    def step_dev(k):         # one step = one batch of B frames, device-resident inputs and outputs
-        hs[k].sgbm_compute_batch_device(B, i1.data_ptr(), i2.data_ptr(), H * Wp, H, Wp, Wp, p, dev_out[k].data_ptr())
+    def step_dev():          # one step = one batch of B frames, device-resident inputs and outputs
+        h.sgbm_compute_batch_device(B, i1.data_ptr(), i2.data_ptr(), H * Wp, H, Wp, Wp, p, dev_out.data_ptr())
 
-    def step_e2e(k):         # the same through the host-buffer entry point: H2D + kernels + D2H, returns when the result is there
-        a, b, d = pin[k]
-        hs[k].sgbm_compute_batch_ptr(B, [t.data_ptr() for t in a], [t.data_ptr() for t in b], H, Wp, Wp, p, [t.data_ptr() for t in d])
+    def submit(slot):        # the same through the host-buffer entry points: H2D + kernels + D2H, asynchronous
+        h.sgbm_batch_submit(slot, B, [t.data_ptr() for t in pin_in1], [t.data_ptr() for t in pin_in2], H, Wp, Wp, p,
+                            [t.data_ptr() for t in pin_out[slot]])
 
-    def timed_device(nsteps, nh):
-        """nsteps batches, batch j on handle j % nh; device time between two events on `main`."""
+    def run_e2e(nsteps):
+        """nsteps batches through wsg_sgbm_batch_submit / _wait, two in flight: the copies of one batch run beside the
+        kernels of the other.  Returns when the last result is in host memory."""
+        submit(0)
+        for k in range(1, nsteps):
+            submit(k & 1)
+            h.sgbm_batch_wait((k - 1) & 1)
+        h.sgbm_batch_wait((nsteps - 1) & 1)
+
+    def timed_device(nsteps):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
         e0.record(main)
-        for st in streams[:nh]:
-            st.wait_event(e0)
-        for j in range(nsteps):
-            step_dev(j % nh)
-        for st in streams[:nh]:
-            ev = torch.cuda.Event()
-            ev.record(st)
-            main.wait_event(ev)
+        st.wait_event(e0)
+        for _ in range(nsteps):
+            step_dev()
+        ev = torch.cuda.Event()
+        ev.record(st)
+        main.wait_event(ev)
         e1.record(main)
         barrier()
         return e0.elapsed_time(e1)
@@ -271,49 +278,33 @@ def run_ours(args, rank, world):
         sampler.start()
     warm = max(args.warmup, 3)
     for _ in range(warm):
-        for k in range(NH):
-            step_dev(k)
+        step_dev()
     barrier()
-    # ---- per-stage profile, ONE batch at a time on one stream: every kernel timed alone (the roofline numbers)
+    # ---- per-stage profile: every kernel timed alone by CUDA events on the handle's stream (the roofline numbers)
     prof_steps = max(2, min(args.steps, 5))
-    hs[0].profile_enable(True)
-    hs[0].profile_reset()
-    ms_serial = timed_device(prof_steps, 1)
-    prof = hs[0].profile_get()
-    hs[0].profile_enable(False)
-    stats = hs[0].sgbm_stats()
+    h.profile_enable(True)
+    h.profile_reset()
+    ms_serial = timed_device(prof_steps)
+    prof = h.profile_get()
+    h.profile_enable(False)
+    stats = h.sgbm_stats()
     # one frame at a time, for the latency figure
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    hs[0].sgbm_compute_batch_device(1, i1.data_ptr(), i2.data_ptr(), H * Wp, H, Wp, Wp, p, dev_out[0].data_ptr())
-    hs[0].synchronize()
-    e0.record(streams[0])
+    h.sgbm_compute_batch_device(1, i1.data_ptr(), i2.data_ptr(), H * Wp, H, Wp, Wp, p, dev_out.data_ptr())
+    h.synchronize()
+    e0.record(st)
     for _ in range(3):
-        hs[0].sgbm_compute_batch_device(1, i1.data_ptr(), i2.data_ptr(), H * Wp, H, Wp, Wp, p, dev_out[0].data_ptr())
-    e1.record(streams[0])
-    hs[0].synchronize()
+        h.sgbm_compute_batch_device(1, i1.data_ptr(), i2.data_ptr(), H * Wp, H, Wp, Wp, p, dev_out.data_ptr())
+    e1.record(st)
+    h.synchronize()
     ms_single = e0.elapsed_time(e1) / 3
-    step_dev(0)
+    step_dev()
 
-    # ---- device-resident throughput ("value"): K batches over NH handles / streams
-    for k in range(NH):
-        step_dev(k)
-    ms_dev = timed_device(args.steps, NH)
+    # ---- device-resident throughput ("value"): K batches back to back
+    ms_dev = timed_device(args.steps)
 
-    # ---- end to end through the C ABI with HOST buffers (pinned): one host thread per handle (the call is synchronous
-    #      and releases the GIL), so the copies of one batch overlap the kernels of the other
-    def e2e_worker(k, n):
-        torch.cuda.set_device(local)
-        for _ in range(n):
-            step_e2e(k)
-
-    def run_e2e(nsteps):
-        ths = [threading.Thread(target=e2e_worker, args=(k, len(range(k, nsteps, NH)))) for k in range(NH)]
-        for t_ in ths:
-            t_.start()
-        for t_ in ths:
-            t_.join()
-
-    run_e2e(NH)
+    # ---- end to end through the C ABI with HOST buffers (pinned)
+    run_e2e(2)
     barrier()
     t0 = time.perf_counter()
     run_e2e(args.steps)
@@ -324,7 +315,7 @@ def run_ours(args, rank, world):
         tp = time.perf_counter()
         mine = [synthetic_plane(rank * args.steps * B + j) for j in range(args.steps * B)]
         _, acc = capi.plane_mean(mine)
-        mean, nfr = hs[0].plane_allreduce(comm_holder["comm"], acc)
+        mean, nfr = h.plane_allreduce(comm_holder["comm"], acc)
         plane_info = {"ms": (time.perf_counter() - tp) * 1e3, "mean": mean, "frames": nfr}
     torch.cuda.synchronize()
     ms_e2e = (time.perf_counter() - t0) * 1e3
@@ -336,14 +327,15 @@ def run_ours(args, rank, world):
     ms_dev, ms_e2e = float(t[0]), float(t[1])
 
     # ---- parity on the frames that were timed: device path == host path, and both == cv2
-    outs = [pin[0][2][i].numpy() for i in range(B)]
-    same = all(bool(torch.equal(dev_out[k][i].cpu(), pin[k][2][i])) for k in range(NH) for i in range(B))
+    outs = [pin_out[0][i].numpy() for i in range(B)]
+    same = all(bool(torch.equal(dev_out[i].cpu(), pin_out[k][i])) for k in range(2) for i in range(B))
 
     if rank == 0:
         px = W_IMG * H_IMG
         value = world * args.steps * B * px / (ms_dev * 1e-3) / 1e6
         e2e = world * args.steps * B * px / (ms_e2e * 1e-3) / 1e6
         V = stats["volume_bytes"]
+        rows_per_band = int(os.environ.get("WSG_SWEEP_ROWS", 0)) or "chosen per launch by the wave model of sweep_rows_per_band (sweep_kernels.cu)"
         nfr_prof = prof_steps * B
         agg_ms, agg_launches = prof["aggregate"]
         agg_ms_per_frame = agg_ms / nfr_prof
@@ -381,8 +373,9 @@ def run_ours(args, rank, world):
             "warmup": warm, "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "s16", "data": "synthetic",
             "config": {"workload": WORKLOAD,
-                       "sample": "each step = one batch of %d whole frames per GPU through wsg_sgbm_compute_batch (seeds %d..%d on rank 0)" % (B, seeds[0], seeds[-1]),
-                       "frames_per_step_per_gpu": B, "handles_in_flight_per_gpu": NH,
+                       "sample": "each step = one batch of %d whole frames per GPU (seeds %d..%d on rank 0): wsg_sgbm_compute_batch_device for `value`, "
+                                 "wsg_sgbm_batch_submit / _wait with pinned host buffers, two batches in flight, for `e2e`" % (B, seeds[0], seeds[-1]),
+                       "frames_per_step_per_gpu": B, "handles_in_flight_per_gpu": 1, "rows_per_band": rows_per_band,
                        "single_frame_ms": ms_single, "padded_width": Wp, "W1": stats["width1"],
                        "l2": "inputs larger than L2 (C and S volumes %.2f GB each per frame, %d frames per batch)" % (V / 1e9, B),
                        "parallelism": "frame-per-GPU x%d" % world,
@@ -420,8 +413,7 @@ def run_ours(args, rank, world):
         print(json.dumps(line), flush=True)
         if mism or not same:
             raise SystemExit("PARITY FAILURE: %d of %d pixels differ from cv2 (device==host path: %s)" % (mism, checked, same))
-    for h in hs:
-        h.close()
+    h.close()
     if world > 1:
         comm_holder["comm"].close()
         dist.destroy_process_group()
@@ -450,8 +442,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--batch", type=int, default=8, help="frames per step and GPU (one wsg_sgbm_compute_batch call)")
-    ap.add_argument("--streams", type=int, default=2, help="handles (arena + stream) the batches alternate over per GPU")
+    ap.add_argument("--batch", type=int, default=16, help="frames per step and GPU (one wsg_sgbm_compute_batch call); "
+                    "device memory: batch x 5.7 GB")
     ap.add_argument("--agg-impl", type=int, default=-1, choices=[-1, 0, 1, 2],
                     help="-1 library default, 0 per-direction launches, 1 fused sweeps, 2 fused sweeps + fused WTA")
     args = ap.parse_args()

@@ -87,6 +87,15 @@ int wsg_sgbm_compute_batch(wsg_handle* h, int n, const uint8_t* const* img1, con
 int wsg_sgbm_compute_batch_device(wsg_handle* h, int n, const uint8_t* d_img1, const uint8_t* d_img2, size_t frame_stride,
                                   int rows, int cols, size_t stride, const wsg_sgbm_params* p, int16_t* d_disp16);
 
+/* Asynchronous batches, for a driver that overlaps its own work (PNG decode, disk) and the PCIe copies with the GPU:
+ * wsg_sgbm_batch_submit enqueues the host->device copies, the matcher and the device->host copies of one batch and
+ * returns at once; wsg_sgbm_batch_wait blocks until that batch's disparities are in the caller's buffers.  Two batches can
+ * be in flight (slot 0 and 1): the copies of one run beside the kernels of the other, on their own streams.  The host
+ * buffers must stay valid until the wait, and should be pinned (otherwise the copies are staged and synchronous). */
+int wsg_sgbm_batch_submit(wsg_handle* h, int slot, int n, const uint8_t* const* img1, const uint8_t* const* img2, int rows, int cols,
+                          size_t stride, const wsg_sgbm_params* p, int16_t* const* disp16);
+int wsg_sgbm_batch_wait(wsg_handle* h, int slot);
+
 /* Statistics of the last wsg_sgbm_compute* on this handle (synchronises the stream). */
 typedef struct wsg_sgbm_stats {
     int max_cost;            /* max over the cost volume C */

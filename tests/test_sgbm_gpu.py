@@ -183,6 +183,61 @@ def test_batch_then_single_then_other_batch_size(handle):
             assert np.array_equal(outs[f], refs[f]), "batch of %d, frame %d" % (n, f)
 
 
+def test_async_batches_match_the_synchronous_call(handle):
+    """wsg_sgbm_batch_submit / _wait: two batches in flight on one handle (copies on their own streams); results are those
+    of wsg_sgbm_compute_batch, slot misuse is a state error."""
+    import torch
+    from oracle import sgbm
+    from wass_b200 import capi, synth
+    handle.sgbm_set_impl(capi.AGG_SWEEPS_WTA)
+    W, H, D, n = 150, 61, 64, 3
+    p = sgbm.wass_params(D, mode=1)
+    sets = []
+    for k in range(3):
+        fr = [synth.pad_for_sgbm(*synth.make_pair(W, H, D, seed=700 + 10 * k + f)[:2], D) for f in range(n)]
+        sets.append(fr)
+    refs = [handle.sgbm_compute_batch([f[0] for f in fr], [f[1] for f in fr], p) for fr in sets]
+    Hh, Wp = sets[0][0][0].shape
+    pins = [([torch.from_numpy(f[0]).pin_memory() for f in fr], [torch.from_numpy(f[1]).pin_memory() for f in fr],
+             [torch.empty((Hh, Wp), dtype=torch.int16).pin_memory() for _ in fr]) for fr in sets]
+
+    def submit(slot, k):
+        a, b, d = pins[k]
+        handle.sgbm_batch_submit(slot, n, [t.data_ptr() for t in a], [t.data_ptr() for t in b], Hh, Wp, Wp, p, [t.data_ptr() for t in d])
+
+    with pytest.raises(capi.WsgError) as e:
+        handle.sgbm_batch_wait(0)
+    assert e.value.code == -5
+    submit(0, 0)
+    submit(1, 1)
+    with pytest.raises(capi.WsgError) as e:
+        submit(0, 2)                      # slot 0 has not been waited for
+    assert e.value.code == -5
+    handle.sgbm_batch_wait(0)
+    submit(0, 2)
+    handle.sgbm_batch_wait(1)
+    handle.sgbm_batch_wait(0)
+    for k in range(3):
+        for f in range(n):
+            assert np.array_equal(pins[k][2][f].numpy(), refs[k][f]), "set %d frame %d" % (k, f)
+
+
+def test_rows_per_band_do_not_change_results(handle):
+    """A launch may use fewer rows per band than the worker has row warps (sweep_rows_per_band picks them by batch size);
+    WSG_SWEEP_ROWS is read once per process, so this test drives the choice through the batch size instead."""
+    from oracle import sgbm
+    from wass_b200 import capi, synth
+    handle.sgbm_set_impl(capi.AGG_SWEEPS_WTA)
+    W, H, D = 100, 230, 64                 # 230 rows: 16 bands of 15, 17 of 14, 18 of 13 -- the wave model moves with n
+    p = sgbm.wass_params(D, mode=1)
+    frames = [synth.pad_for_sgbm(*synth.make_pair(W, H, D, seed=40 + f)[:2], D) for f in range(9)]
+    refs = [sgbm.compute(a, b, p)["disp"] for a, b in frames[:3]]
+    for n in (1, 2, 3, 5, 9):
+        outs = handle.sgbm_compute_batch([f[0] for f in frames[:n]], [f[1] for f in frames[:n]], p)
+        for f in range(min(n, 3)):
+            assert np.array_equal(outs[f], refs[f]), "batch of %d, frame %d" % (n, f)
+
+
 def test_batch_argument_errors(handle):
     from wass_b200 import capi
     a = np.zeros((16, 200), np.uint8)

@@ -117,6 +117,9 @@ def load():
     lib.wsg_sgbm_compute_batch.argtypes = [vp, ci, ctypes.POINTER(vp), ctypes.POINTER(vp), ci, ci, sz, ctypes.POINTER(SgbmParams),
                                            ctypes.POINTER(vp)]
     lib.wsg_sgbm_compute_batch_device.argtypes = [vp, ci, vp, vp, sz, ci, ci, sz, ctypes.POINTER(SgbmParams), vp]
+    lib.wsg_sgbm_batch_submit.argtypes = [vp, ci, ci, ctypes.POINTER(vp), ctypes.POINTER(vp), ci, ci, sz, ctypes.POINTER(SgbmParams),
+                                          ctypes.POINTER(vp)]
+    lib.wsg_sgbm_batch_wait.argtypes = [vp, ci]
     lib.wsg_sgbm_get_stats.argtypes = [vp, ctypes.POINTER(SgbmStats)]
     lib.wsg_sgbm_debug_volumes.argtypes = [vp, vp, vp]
     lib.wsg_sgbm_set_sweep_workers.argtypes = [vp, ci]
@@ -369,6 +372,16 @@ class Handle:
         p = SgbmParams(**params)
         self._ck(self.lib.wsg_sgbm_compute_batch(self.h, n, arr(*img1_ptrs), arr(*img2_ptrs), rows, cols, stride, ctypes.byref(p),
                                                  arr(*disp_ptrs)))
+
+    def sgbm_batch_submit(self, slot, n, img1_ptrs, img2_ptrs, rows, cols, stride, params, disp_ptrs):
+        """Asynchronous: enqueue H2D + matcher + D2H of one batch (raw host pointers, pinned) and return; slot 0 or 1."""
+        arr = ctypes.c_void_p * n
+        p = SgbmParams(**params)
+        self._ck(self.lib.wsg_sgbm_batch_submit(self.h, slot, n, arr(*img1_ptrs), arr(*img2_ptrs), rows, cols, stride, ctypes.byref(p),
+                                                arr(*disp_ptrs)))
+
+    def sgbm_batch_wait(self, slot):
+        self._ck(self.lib.wsg_sgbm_batch_wait(self.h, slot))
 
     def sgbm_compute_batch_device(self, n, d_img1, d_img2, frame_stride, rows, cols, stride, params, d_disp):
         """Device pointers (ints) to n frames `frame_stride` bytes apart; d_disp: n x rows x cols int16.  Asynchronous."""

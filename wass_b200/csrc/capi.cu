@@ -34,6 +34,13 @@ void wsg_destroy(wsg_handle* h)
                       &h->m_Z, &h->m_color, &h->m_labels, &h->m_scratch, &h->m_small, &h->m_out})
         if (b->p) cudaFree(b->p);
     for (auto e : h->ev_pool) cudaEventDestroy(e);
+    if (h->h2d_stream) {
+        cudaStreamSynchronize(h->h2d_stream); cudaStreamSynchronize(h->d2h_stream);
+        cudaStreamDestroy(h->h2d_stream); cudaStreamDestroy(h->d2h_stream);
+        for (int k = 0; k < 2; ++k) { cudaEventDestroy(h->ev_h2d[k]); cudaEventDestroy(h->ev_done[k]); cudaEventDestroy(h->ev_d2h[k]); }
+        cudaFreeHost(h->async_flag);
+        for (int k = 0; k < 2; ++k) for (DevBuf* b : {&h->a_img1[k], &h->a_img2[k], &h->a_disp[k]}) if (b->p) cudaFree(b->p);
+    }
     cudaStreamDestroy(h->own_stream);
     delete h;
 }
@@ -109,7 +116,7 @@ int wsg_check_sweep(wsg_handle* h)
     CK(h, cudaMemcpyAsync(&flag, (int*)h->scalars.p + SCAL_ERR, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     CK(h, cudaStreamSynchronize(h->stream));
     if (h->dbg.p && getenv("WSG_SWEEP_DEBUG")) {
-        const int R = sweep_rows_per_band(h->plan);
+        const int R = h->sweep_rows;
         const size_t nt = (size_t)((h->plan.H + R - 1) / R) * h->batch_n;
         std::vector<int> d(3 * nt);
         cudaMemcpy(d.data(), h->dbg.p, d.size() * sizeof(int), cudaMemcpyDeviceToHost);
@@ -181,14 +188,18 @@ int wsg_run_sgbm_batch(wsg_handle* h, int n, const uint8_t* const* d_img1, const
         }
     } else {
         // fused wavefront sweeps over the whole batch (sweep_kernels.cu)
-        const size_t bbytes = sweep_boundary_bytes(pl) * n;
+        if (h->num_sms == 0) CK(h, cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, h->device));
+        const int workers = h->sweep_workers > 0 ? std::min(h->sweep_workers, h->num_sms) : h->num_sms;
+        const int rows = sweep_rows_per_band(pl, n, workers);
+        h->sweep_rows = rows;
+        const size_t bbytes = sweep_boundary_bytes(pl, rows) * n;
         const bool grown = bbytes > h->bnd.cap;
         if ((rc = ensure(h, h->bnd, bbytes))) return rc;
-        if (grown || h->bnd_H != pl.H || h->bnd_W1 != pl.W1 || h->bnd_K != pl.K || h->bnd_n != n) {
+        if (grown || h->bnd_H != pl.H || h->bnd_W1 != pl.W1 || h->bnd_K != pl.K || h->bnd_n != n || h->bnd_rows != rows) {
             // epoch tags only tell "this sweep" from "the previous one" for slots that are rewritten every sweep: a change
             // of geometry or batch size would let data of an older sweep with the same 2-bit epoch pass for current
             CK(h, cudaMemsetAsync(h->bnd.p, 0, h->bnd.cap, h->stream));
-            h->bnd_H = pl.H; h->bnd_W1 = pl.W1; h->bnd_K = pl.K; h->bnd_n = n;
+            h->bnd_H = pl.H; h->bnd_W1 = pl.W1; h->bnd_K = pl.K; h->bnd_n = n; h->bnd_rows = rows;
         }
         const bool fused_wta = impl == WSG_AGG_SWEEPS_WTA && pl.uniq < 99;    // the in-sweep WTA needs 100-uniq >= 2 (its multiply-high division)
         if (fused_wta) {
@@ -201,15 +212,14 @@ int wsg_run_sgbm_batch(wsg_handle* h, int n, const uint8_t* const* d_img1, const
         sc.maxC = scal + SCAL_MAXC; sc.maxC_stride = 1;
         sc.err = scal + SCAL_ERR;
         sc.dbg = nullptr;
-        sc.nframes = n; sc.volume_stride_bytes = vol;
+        sc.nframes = n; sc.volume_stride_bytes = vol; sc.rows = rows;
         if (getenv("WSG_SWEEP_DEBUG")) {
-            const int R = sweep_rows_per_band(pl);
+            const int R = rows;
             if ((rc = ensure(h, h->dbg, (size_t)3 * ((pl.H + R - 1) / R) * n * sizeof(int)))) return rc;
             sc.dbg = (int*)h->dbg.p;
         }
         sc.keys = (unsigned long long*)h->keys.p;
         sc.d1 = (int16_t*)h->d1.p;
-        if (h->num_sms == 0) CK(h, cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, h->device));
         sc.num_sms = h->num_sms;
         auto next_epoch = [&]() { h->sweep_epoch = h->sweep_epoch % 3 + 1; return h->sweep_epoch; };
         const int last_mode = fused_wta ? 2 : 1;
@@ -341,6 +351,75 @@ int wsg_sgbm_compute_batch(wsg_handle* h, int n, const uint8_t* const* img1, con
         CK(h, cudaMemcpyAsync(disp16[f], d[f], npix * sizeof(int16_t), cudaMemcpyDeviceToHost, h->stream));
     CK(h, cudaStreamSynchronize(h->stream));
     return wsg_check_sweep(h);
+}
+
+// ---- asynchronous batches: submit enqueues H2D + matcher + D2H and returns, wait blocks for the result ---------------------
+static int async_init(wsg_handle* h)
+{
+    if (h->h2d_stream) return WSG_OK;
+    CK(h, cudaStreamCreateWithFlags(&h->h2d_stream, cudaStreamNonBlocking));
+    CK(h, cudaStreamCreateWithFlags(&h->d2h_stream, cudaStreamNonBlocking));
+    for (int s = 0; s < 2; ++s) {
+        CK(h, cudaEventCreateWithFlags(&h->ev_h2d[s], cudaEventDisableTiming));
+        CK(h, cudaEventCreateWithFlags(&h->ev_done[s], cudaEventDisableTiming));
+        CK(h, cudaEventCreateWithFlags(&h->ev_d2h[s], cudaEventDisableTiming));
+    }
+    CK(h, cudaHostAlloc((void**)&h->async_flag, 2 * sizeof(int), cudaHostAllocDefault));
+    return WSG_OK;
+}
+
+int wsg_sgbm_batch_submit(wsg_handle* h, int slot, int n, const uint8_t* const* img1, const uint8_t* const* img2, int rows, int cols,
+                          size_t stride, const wsg_sgbm_params* p, int16_t* const* disp16)
+{
+    if (!h) return WSG_ERR_INVALID_ARG;
+    if (slot < 0 || slot > 1 || n <= 0 || n > WSG_MAX_BATCH) { h->err = "slot must be 0 or 1, batch size 1.." + std::to_string(WSG_MAX_BATCH); return WSG_ERR_INVALID_ARG; }
+    if (!img1 || !img2 || !disp16 || stride < (size_t)std::max(cols, 0)) { h->err = "null pointer or stride < cols"; return WSG_ERR_INVALID_ARG; }
+    for (int f = 0; f < n; ++f)
+        if (!img1[f] || !img2[f] || !disp16[f]) { h->err = "null frame pointer"; return WSG_ERR_INVALID_ARG; }
+    if (h->async_busy[slot]) { h->err = "slot still in flight: wsg_sgbm_batch_wait first"; return WSG_ERR_STATE; }
+    CK(h, cudaSetDevice(h->device));
+    int rc = async_init(h);
+    if (rc) return rc;
+    SgbmPlan pl{};
+    if ((rc = wsg_make_plan(h, rows, cols, p, pl))) return rc;
+    h->plan = pl;
+    const size_t npix = (size_t)rows * cols;
+    if ((rc = ensure(h, h->a_img1[slot], npix * n))) return rc;
+    if ((rc = ensure(h, h->a_img2[slot], npix * n))) return rc;
+    if ((rc = ensure(h, h->a_disp[slot], npix * n * sizeof(int16_t)))) return rc;
+    std::vector<const uint8_t*> a(n), b(n);
+    std::vector<int16_t*> d(n);
+    for (int f = 0; f < n; ++f) {
+        a[f] = (const uint8_t*)h->a_img1[slot].p + f * npix; b[f] = (const uint8_t*)h->a_img2[slot].p + f * npix;
+        d[f] = (int16_t*)h->a_disp[slot].p + f * npix;
+        CK(h, cudaMemcpy2DAsync((void*)a[f], cols, img1[f], stride, cols, rows, cudaMemcpyHostToDevice, h->h2d_stream));
+        CK(h, cudaMemcpy2DAsync((void*)b[f], cols, img2[f], stride, cols, rows, cudaMemcpyHostToDevice, h->h2d_stream));
+    }
+    CK(h, cudaEventRecord(h->ev_h2d[slot], h->h2d_stream));
+    CK(h, cudaStreamWaitEvent(h->stream, h->ev_h2d[slot], 0));
+    if ((rc = wsg_run_sgbm_batch(h, n, a.data(), b.data(), cols, d.data()))) return rc;
+    // the sweep error flag of this batch: read on the compute stream, before the next batch resets the scalars
+    CK(h, cudaMemcpyAsync(h->async_flag + slot, (int*)h->scalars.p + SCAL_ERR, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CK(h, cudaEventRecord(h->ev_done[slot], h->stream));
+    CK(h, cudaStreamWaitEvent(h->d2h_stream, h->ev_done[slot], 0));
+    for (int f = 0; f < n; ++f)
+        CK(h, cudaMemcpyAsync(disp16[f], d[f], npix * sizeof(int16_t), cudaMemcpyDeviceToHost, h->d2h_stream));
+    CK(h, cudaEventRecord(h->ev_d2h[slot], h->d2h_stream));
+    h->async_busy[slot] = true;
+    return WSG_OK;
+}
+
+int wsg_sgbm_batch_wait(wsg_handle* h, int slot)
+{
+    if (!h) return WSG_ERR_INVALID_ARG;
+    if (slot < 0 || slot > 1 || !h->async_busy[slot]) { h->err = "nothing in flight in this slot"; return WSG_ERR_STATE; }
+    CK(h, cudaEventSynchronize(h->ev_d2h[slot]));
+    h->async_busy[slot] = false;
+    if (h->stats.agg_impl != WSG_AGG_PER_DIRECTION && h->async_flag[slot]) {
+        h->err = "fused aggregation sweep: hand-off wait overran (code " + std::to_string(h->async_flag[slot]) + ")";
+        return WSG_ERR_CUDA;
+    }
+    return WSG_OK;
 }
 
 int wsg_sgbm_get_stats(wsg_handle* h, wsg_sgbm_stats* out)

@@ -31,7 +31,14 @@ struct wsg_handle {
     int sweep_workers = 0;              // cap on the SMs a sweep occupies (0 = all)
     int sweep_epoch = 0;                // 1..3 after the first sweep
     int bnd_H = 0, bnd_W1 = 0, bnd_K = 0, bnd_n = 0;    // geometry / batch size the hand-off buffer was last used with
+    int bnd_rows = 0, sweep_rows = 0;   // rows per band the hand-off buffer was last used with / of the last batch
     int batch_n = 1;                    // frames of the last dense-matcher call
+    // asynchronous batches (wsg_sgbm_batch_submit / _wait): two slots, copies on their own streams
+    cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
+    cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr}, ev_d2h[2] = {nullptr, nullptr};
+    DevBuf a_img1[2], a_img2[2], a_disp[2];
+    bool async_busy[2] = {false, false};
+    int* async_flag = nullptr;          // pinned: the sweep error flag of each slot's batch
     SgbmPlan plan{};
     bool have_plan = false;
     wsg_sgbm_stats stats{};

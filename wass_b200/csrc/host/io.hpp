@@ -29,5 +29,7 @@ bool save_matrix_txt(const std::string& path, const Mat& m);
 bool read_png_gray(const std::string& path, Image8& out, std::string* err);
 bool write_png_gray(const std::string& path, const Image8& img);
 bool write_file(const std::string& path, const void* data, size_t n);
+// cv::imwrite(name.jpg, img): baseline JPEG (jpeg.cpp); px = rows x cols x channels (1 grey, 3 RGB), quality as OpenCV's default 95
+bool write_jpeg(const std::string& path, const unsigned char* px, int rows, int cols, int channels, int quality = 95);
 
 }  // namespace wasshost

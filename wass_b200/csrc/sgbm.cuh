@@ -57,14 +57,15 @@ struct SweepScratch {
     int* err;                   // raised if a bounded wait overran
     int* dbg;                   // optional [3 * tickets]: {SM id, start ns, end ns} per band (WSG_SWEEP_DEBUG=1), else null
     int epoch;                  // 1..3, changes with every 4-direction sweep that uses `boundary`
+    int rows = 0;               // rows per band of this batch (sweep_rows_per_band)
     int nframes = 1;            // frames of the batch: C / S volumes `volume_stride_bytes` apart, keys / d1 H*W apart
     size_t volume_stride_bytes = 0;
     unsigned long long* keys;   // [nframes][H][W] right-view map as packed keys (fused WTA)
     int16_t* d1;                // [nframes][H][W] left-view disparity before the LR check (fused WTA)
 };
 bool sweep_supported(const SgbmPlan& p);
-int sweep_rows_per_band(const SgbmPlan& p);
-size_t sweep_boundary_bytes(const SgbmPlan& p);      // per frame
+int sweep_rows_per_band(const SgbmPlan& p, int nframes, int workers);
+size_t sweep_boundary_bytes(const SgbmPlan& p, int rows);      // per frame
 size_t sweep_volume_pad_bytes();                     // the C / S volumes must be readable this far beyond either end
 // One launch over the bands of all `sc.nframes` frames.  flip 0: directions r0..r3 (top->bottom); flip 1: r4..r7
 // (bottom->top).  mode 0: S = sum L (write only); 1: S += sum L;  2: S += sum L, then winner-take-all into

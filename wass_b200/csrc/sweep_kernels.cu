@@ -28,6 +28,7 @@
 // All spin loops are bounded: on overrun the kernel raises an error flag and runs to completion.
 #include "sgbm_dev.cuh"
 #include <algorithm>
+#include <cmath>
 #include <cstdlib>
 #include <type_traits>
 
@@ -39,7 +40,7 @@ static constexpr int PROG_INF = 0x3fffffff;
 
 // rows per band / ring depth for D <= 256 (K == 1) and D <= 512 (K == 2); experiments: -DWSG_SW_ROWS1=.. -DWSG_SW_NS1=..
 #ifndef WSG_SW_ROWS1
-#define WSG_SW_ROWS1 14
+#define WSG_SW_ROWS1 15
 #endif
 #ifndef WSG_SW_NS1
 #define WSG_SW_NS1 8
@@ -50,9 +51,6 @@ static constexpr int PROG_INF = 0x3fffffff;
 #ifndef WSG_SW_NS2
 #define WSG_SW_NS2 6
 #endif
-#ifndef WSG_SW_PFD
-#define WSG_SW_PFD 3      // pixels of C in flight per row in the sweeps that also stream S
-#endif
 #ifndef WSG_SW_STAGGER
 #define WSG_SW_STAGGER -1  // extra columns a row lets the row above get ahead before it starts; -1: half the ring's slack
 #endif
@@ -60,16 +58,12 @@ static constexpr int PROG_INF = 0x3fffffff;
 // Shared-memory map of a worker (uint4 units).  K = 16-byte vectors per lane and pixel (D <= 256: 1, D <= 512: 2).
 // The first sweep (MODE 0) streams only C and has no winner-take-all: it needs neither S staging nor scratch.
 template <int K, int R, int NS, int MODE> struct SweepCfg {
-    static constexpr int PFD = MODE == 0 ? 4 : WSG_SW_PFD;    // pixels of C in flight per row (cp.async staging)
-    static constexpr int PFS = MODE == 0 ? 0 : 2;             // pixels of S in flight per row
     static constexpr int PIX_V = K * 32;                      // uint4 per pixel
     static constexpr int SLOT_V = 3 * PIX_V;                  // uint4 per ring slot: [dir][k][lane]
     static constexpr int RING_V = NS * SLOT_V;
     static constexpr int RINGS_V = (R + 1) * RING_V;          // ring r: states of the row above row r; ring R: out of the band
     static constexpr int SCR_V = MODE == 2 ? R * PIX_V : 0;   // per-row WTA scratch
-    static constexpr int STAGEC_V = R * PFD * PIX_V;          // per-row staging of the C stream
-    static constexpr int STAGES_V = R * PFS * PIX_V;          // per-row staging of the S stream
-    static constexpr int SMEM = (RINGS_V + SCR_V + STAGEC_V + STAGES_V) * 16;
+    static constexpr int SMEM = (RINGS_V + SCR_V) * 16 + 64;  // (+64: the scratch of the last row is read one element beyond)
     static constexpr int THREADS = (R + 1) * 32;
     static constexpr int HD = NS - 2 < 4 ? NS - 2 : 4;        // boundary columns the helper polls per round trip
     // A row may run lag = 2 .. NS-2 columns behind the row above (2: it needs column x+1; NS-2: the ring is full).  Rows
@@ -77,23 +71,15 @@ template <int K, int R, int NS, int MODE> struct SweepCfg {
     // lets its producer get STAGGER columns further ahead: the chain then sits in the middle of its slack.
     static constexpr int STAGGER = WSG_SW_STAGGER >= 0 ? WSG_SW_STAGGER : (NS - 4) / 2;
     static_assert(SMEM <= 227 * 1024, "worker does not fit an SM");
-    static_assert(PFS <= PFD, "the S stream rides in the commit groups of the C stream");
     static_assert(STAGGER >= 0 && STAGGER <= NS - 4 + 0 || NS < 4, "stagger beyond the ring's slack");
 };
-
-// 16-byte asynchronous global->shared copy (L2 only), one per lane; completion is tracked per thread in commit groups
-__device__ __forceinline__ void cp_async16(unsigned smem_dst, const void* gsrc)
-{
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_dst), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 struct SweepArgs {
     int H, W1, W, D;
     int Dp8;                 // 16-byte vectors per pixel (= 32*K)
     int flip;                // 0: top->bottom, left->right;  1: rotated by 180 degrees
     int nframes;             // frames of the batch (tickets interleave them)
+    int rows;                // rows per band of THIS launch, <= R (the kernel's row warps): see sweep_rows_per_band
     const uint4* C;          // [nframes] cost volumes, vol_v uint4 apart (readable PFD pixels beyond either end)
     uint4* S;                // [nframes] aggregated volumes, same spacing
     size_t vol_v;
@@ -232,19 +218,22 @@ __device__ __forceinline__ void wta_flush(unsigned key, unsigned nb, int xl, boo
     d1_row[x] = (int16_t)(dd + a.minD * 16);
 }
 
-// Per-row state of a sweep (everything sweep_step needs besides the pixel's register sets).
+// Per-row state of a sweep.  The C and S streams are prefetched into REGISTERS: a row warp takes ~1500 clocks per pixel
+// (15 rows share an SM), so a load issued two pixels ahead has thousands of clocks to land, and the register sets rotate
+// through a loop unrolled by four -- no staging in shared memory, no copies from one pixel to the next.
 template <int K> struct RowState {
     const uint4* cpf; const uint4* spf; uint4* scur;      // C / S prefetch cursors, S store cursor
     long long dstep;
     const uint4* ring_in; uint4* ring_out;
     uint16_t* scratch;                                    // final S of the previous pixel, natural disparity order
-    const uint4* stageC; const uint4* stageS;
-    unsigned stC, stS;                                    // the same staging areas as shared-window addresses
     volatile int* prog_in; volatile int* prog_me; volatile int* prog_next;
     int seen_in, seen_next;
-    int pslot;                                            // x % PFD, as a uint4 offset into the C staging
     int o_m1, o_0, o_p1;                                  // ring slots (uint4 offsets) of columns x-1, x, x+1
     unsigned Nh[4 * K];                                   // normalised state of the horizontal path
+    unsigned Cs[4][4 * K];                                // C(x) lives in set x % 4: x and x+1 in use, x+2 and x+3 in flight
+    unsigned Ls[2][4 * K];                                // horizontal L(x) in set x % 2 (made one pixel ahead)
+    unsigned Vs[2][4 * K];                                // final S(x) in set (x+1) % 2, for the winner-take-all one pixel later
+    unsigned Ss[2][4 * K];                                // S of the first sweep: S(x) in set x % 2, reloaded with S(x+2) once read
     unsigned padm[K];
     unsigned wkey, wnb, rkey, rnb;                        // winner-take-all: last evaluation, and this lane's kept record
     unsigned long long* keys_row; int16_t* d1_row;
@@ -252,39 +241,39 @@ template <int K> struct RowState {
     int l;
 };
 
-// One pixel of a row: Cc / Lh = C and horizontal L of pixel x (from the previous step), Cn / Lhn = the same for pixel x+1
-// (made here), vsp = S of pixel x-1 (the winner-take-all runs one pixel late), vsn = S of pixel x (made here).
-// SODD = x % 2: the S staging has two slots.
-template <int K, int R, int NS, int MODE, int NDIR, bool HASPAD, bool FAST, int SODD>
-__device__ __forceinline__ void sweep_step(RowState<K>& st, const SweepArgs& a, const int x, unsigned (&Cc)[4 * K], unsigned (&Lh)[4 * K],
-                                           unsigned (&Cn)[4 * K], unsigned (&Lhn)[4 * K], unsigned (&vsp)[4 * K], unsigned (&vsn)[4 * K])
+template <int K> __device__ __forceinline__ void load_set(unsigned (&dst)[4 * K], const uint4* p)
+{
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        const uint4 c = ldg_stream(p + k * 32);
+        dst[4 * k] = c.x; dst[4 * k + 1] = c.y; dst[4 * k + 2] = c.z; dst[4 * k + 3] = c.w;
+    }
+}
+
+// One pixel of a row; U = x % 4 selects the register sets at compile time.
+template <int K, int R, int NS, int MODE, int NDIR, bool HASPAD, bool FAST, int U>
+__device__ __forceinline__ void sweep_step(RowState<K>& st, const SweepArgs& a, const int x)
 {
     using Cfg = SweepCfg<K, R, NS, MODE>;
     constexpr int NR = 4 * K;
-    constexpr int PFD = Cfg::PFD, PFS = Cfg::PFS;
     const int l = st.l;
-    const int nslot = st.pslot + Cfg::PIX_V == PFD * Cfg::PIX_V ? 0 : st.pslot + Cfg::PIX_V;
+    unsigned (&Cc)[NR] = st.Cs[U];                  // C(x)
+    unsigned (&Cn)[NR] = st.Cs[(U + 1) & 3];        // C(x+1): issued two iterations ago
+    unsigned (&Lh)[NR] = st.Ls[U & 1];              // horizontal L(x), made by the previous step
+    unsigned (&Lhn)[NR] = st.Ls[(U + 1) & 1];       // horizontal L(x+1), made here
+    unsigned (&vsp)[NR] = st.Vs[U & 1];             // S(x-1)
+    unsigned (&vsn)[NR] = st.Vs[(U + 1) & 1];       // S(x), made here
     unsigned v[3][NR], Nd[3][NR];
-    cp_async_wait<PFD - 2>();                   // pixel x+1 has landed (past the row end: unused data)
-#pragma unroll
-    for (int k = 0; k < K; ++k) {
-        const uint4 c = st.stageC[nslot + k * 32];
-        Cn[4 * k] = c.x; Cn[4 * k + 1] = c.y; Cn[4 * k + 2] = c.z; Cn[4 * k + 3] = c.w;
-    }
+    load_set<K>(st.Cs[(U + 3) & 3], st.cpf);        // C(x+3) into the set C(x-1) has left (past the row end: unused data)
+    st.cpf += st.dstep;
     if (MODE == 0) {
 #pragma unroll
         for (int j = 0; j < NR; ++j) vsn[j] = Lh[j];
     } else {
-        // S(x) was committed PFS iterations ago; PFD + x groups exist by now
-        if (PFS < PFD - 1) cp_async_wait<(PFS > 0 ? PFS - 1 : 0)>();
 #pragma unroll
-        for (int k = 0; k < K; ++k) {
-            const uint4 sv = st.stageS[SODD * Cfg::PIX_V + k * 32];
-            vsn[4 * k] = __viaddmin_u16x2(sv.x, Lh[4 * k], SAT2);
-            vsn[4 * k + 1] = __viaddmin_u16x2(sv.y, Lh[4 * k + 1], SAT2);
-            vsn[4 * k + 2] = __viaddmin_u16x2(sv.z, Lh[4 * k + 2], SAT2);
-            vsn[4 * k + 3] = __viaddmin_u16x2(sv.w, Lh[4 * k + 3], SAT2);
-        }
+        for (int j = 0; j < NR; ++j) vsn[j] = __viaddmin_u16x2(st.Ss[U & 1][j], Lh[j], SAT2);
+        load_set<K>(st.Ss[U & 1], st.spf);          // S(x+2)
+        st.spf += st.dstep;
     }
     if (NDIR == 4) {
         // ---- states of the three directions that come from the row above: columns x-1, x, x+1 of ring r.  Columns -1
@@ -344,15 +333,6 @@ __device__ __forceinline__ void sweep_step(RowState<K>& st, const SweepArgs& a, 
             stg_stream(st.scur + k * 32, make_uint4(vsn[4 * k], vsn[4 * k + 1], vsn[4 * k + 2], vsn[4 * k + 3]));
     }
     st.scur += st.dstep;
-    // ---- refill the staging slots just consumed with pixels x + PFD (C) and x + PFS (S)
-#pragma unroll
-    for (int k = 0; k < K; ++k) {
-        cp_async16(st.stC + (st.pslot + k * 32) * 16, st.cpf + k * 32);
-        if (MODE != 0) cp_async16(st.stS + (SODD * Cfg::PIX_V + k * 32) * 16, st.spf + k * 32);
-    }
-    cp_async_commit();
-    st.cpf += st.dstep; st.spf += st.dstep;
-    st.pslot = nslot;
 }
 
 // One image row of a sweep, walked by one warp (see the kernel below for the surrounding protocol).
@@ -367,9 +347,9 @@ __device__ __forceinline__ void sweep_row(const uint4* __restrict__ C, uint4* __
 {
     using Cfg = SweepCfg<K, R, NS, MODE>;
     constexpr int NR = 4 * K;
-    constexpr int PFD = Cfg::PFD, PFS = Cfg::PFS;
     const int W1 = a.W1;
-    const int yl = band * R + r;                    // logical row (sweep order)
+    const int yl = band * a.rows + r;               // logical row (sweep order)
+    if (r >= a.rows) return;                        // a launch may use fewer rows per band than the worker has row warps
     if (yl >= a.H) {
         if (NDIR == 4 && l == 0) prog[r + 1] = PROG_INF;         // the row above never waits for this one
         return;
@@ -383,10 +363,6 @@ __device__ __forceinline__ void sweep_row(const uint4* __restrict__ C, uint4* __
     st.ring_in = smem + (size_t)r * Cfg::RING_V + l;
     st.ring_out = smem + (size_t)(r + 1) * Cfg::RING_V + l;
     st.scratch = reinterpret_cast<uint16_t*>(smem + Cfg::RINGS_V + (size_t)r * Cfg::PIX_V);
-    st.stageC = smem + Cfg::RINGS_V + Cfg::SCR_V + (size_t)r * PFD * Cfg::PIX_V + l;
-    st.stageS = smem + Cfg::RINGS_V + Cfg::SCR_V + Cfg::STAGEC_V + (size_t)r * PFS * Cfg::PIX_V + l;
-    st.stC = (unsigned)__cvta_generic_to_shared(st.stageC);
-    st.stS = (unsigned)__cvta_generic_to_shared(st.stageS);
     st.prog_in = &prog[r]; st.prog_me = &prog[r + 1]; st.prog_next = &prog[r + 2];
     st.seen_in = 0; st.seen_next = 0;
     st.wkey = st.wnb = st.rkey = st.rnb = 0;
@@ -395,51 +371,39 @@ __device__ __forceinline__ void sweep_row(const uint4* __restrict__ C, uint4* __
 #pragma unroll
     for (int k = 0; k < K; ++k) st.padm[k] = ((l * K + k) * 8 >= a.D) ? SAT2 : 0u;
 
-    // one commit group per pixel, PFD pixels ahead; each lane copies and later reads back its own 16 bytes.  The
-    // prefetch is not guarded at the row end: the volumes are readable PFD pixels beyond either end.
+    // C(0), C(1), C(2) and S(0), S(1) up front; every step then issues C(x+3) and S(x+2).  The loads are not guarded at the
+    // row end: the volumes are readable a few pixels beyond either end.
 #pragma unroll
-    for (int i = 0; i < PFD; ++i) {
+    for (int i = 0; i < 3; ++i) { load_set<K>(st.Cs[i], st.cpf); st.cpf += st.dstep; }
+    if (MODE != 0) {
 #pragma unroll
-        for (int k = 0; k < K; ++k) {
-            cp_async16(st.stC + (i * Cfg::PIX_V + k * 32) * 16, st.cpf + k * 32);
-            if (MODE != 0 && i < PFS) cp_async16(st.stS + (i * Cfg::PIX_V + k * 32) * 16, st.spf + k * 32);
-        }
-        cp_async_commit();
-        st.cpf += st.dstep;
-        if (i < PFS) st.spf += st.dstep;
+        for (int i = 0; i < 2; ++i) { load_set<K>(st.Ss[i], st.spf); st.spf += st.dstep; }
     }
-
+#pragma unroll
+    for (int j = 0; j < NR; ++j) { st.Vs[0][j] = 0; st.Vs[1][j] = 0; st.Nh[j] = 0; }
     // The horizontal direction runs ONE PIXEL AHEAD of the three directions that come from the row above: its step for
-    // pixel x+1 and their steps for pixel x are four independent dependency chains in one basic block.  The loop is
-    // unrolled by two with the roles of the register sets swapped, so nothing is copied from one pixel to the next.
-    unsigned Ca[NR], La[NR], Cb[NR], Lb[NR], Va[NR], Vb[NR];
-#pragma unroll
-    for (int j = 0; j < NR; ++j) { Va[j] = 0; Vb[j] = 0; st.Nh[j] = 0; }
-    cp_async_wait<PFD - 1>();
-#pragma unroll
-    for (int k = 0; k < K; ++k) {
-        const uint4 c = st.stageC[k * 32];
-        Ca[4 * k] = c.x; Ca[4 * k + 1] = c.y; Ca[4 * k + 2] = c.z; Ca[4 * k + 3] = c.w;
-    }
-    agg_step<32, NR, HASPAD, FAST>(st.Nh, Ca, La, l, st.P1p, st.P2mP1p, st.padm, st.one);
+    // pixel x+1 and their steps for pixel x are four independent dependency chains in one basic block.
+    agg_step<32, NR, HASPAD, FAST>(st.Nh, st.Cs[0], st.Ls[0], l, st.P1p, st.P2mP1p, st.padm, st.one);
     if (NDIR == 4 && Cfg::STAGGER > 0) wait_prog(st.prog_in, min(2 + Cfg::STAGGER, W1 + 1), st.seen_in, a.err, a.eager);
-    st.pslot = 0;
     st.o_m1 = (NS - 1) * Cfg::SLOT_V; st.o_0 = 0; st.o_p1 = Cfg::SLOT_V;      // column -1 is the zero-initialised slot NS-1
 
     int x = 0;
-    for (; x + 1 < W1; x += 2) {
-        sweep_step<K, R, NS, MODE, NDIR, HASPAD, FAST, 0>(st, a, x, Ca, La, Cb, Lb, Va, Vb);
-        sweep_step<K, R, NS, MODE, NDIR, HASPAD, FAST, 1>(st, a, x + 1, Cb, Lb, Ca, La, Vb, Va);
+    for (; x + 3 < W1; x += 4) {
+        sweep_step<K, R, NS, MODE, NDIR, HASPAD, FAST, 0>(st, a, x);
+        sweep_step<K, R, NS, MODE, NDIR, HASPAD, FAST, 1>(st, a, x + 1);
+        sweep_step<K, R, NS, MODE, NDIR, HASPAD, FAST, 2>(st, a, x + 2);
+        sweep_step<K, R, NS, MODE, NDIR, HASPAD, FAST, 3>(st, a, x + 3);
     }
-    if (x < W1) {                                   // odd width: one more pixel; its S ends up where the epilogue expects it
-        sweep_step<K, R, NS, MODE, NDIR, HASPAD, FAST, 0>(st, a, x, Ca, La, Cb, Lb, Va, Vb);
-#pragma unroll
-        for (int j = 0; j < NR; ++j) Va[j] = Vb[j];
-    }
-    cp_async_wait<0>();
+    if (x < W1) { sweep_step<K, R, NS, MODE, NDIR, HASPAD, FAST, 0>(st, a, x); ++x; }
+    if (x < W1) { sweep_step<K, R, NS, MODE, NDIR, HASPAD, FAST, 1>(st, a, x); ++x; }
+    if (x < W1) { sweep_step<K, R, NS, MODE, NDIR, HASPAD, FAST, 2>(st, a, x); ++x; }
     if (MODE == 2) {
-        // last column, then the columns still held in registers: xb .. W1-1 with xb = 32*floor((W1-1)/32)
-        wta_eval<K, HASPAD>(Va, l, a, st.scratch, st.wkey, st.wnb);
+        // last column (its S sits in set W1 % 2), then the columns still held in registers: xb .. W1-1, xb = 32*floor((W1-1)/32)
+        if (W1 & 1) {
+#pragma unroll
+            for (int j = 0; j < NR; ++j) st.Vs[0][j] = st.Vs[1][j];
+        }
+        wta_eval<K, HASPAD>(st.Vs[0], l, a, st.scratch, st.wkey, st.wnb);
         if (l == ((W1 - 1) & 31)) { st.rkey = st.wkey; st.rnb = st.wnb; }
         const int xb = (W1 - 1) & ~31;
         wta_flush(st.rkey, st.rnb, xb + l, xb + l < W1, a, st.keys_row, st.d1_row);
@@ -470,14 +434,15 @@ __device__ __forceinline__ void sweep_helper(const SweepArgs& a, uint4* smem, vo
     const uint4* src = bnd_f + (size_t)(band > 0 ? band - 1 : 0) * bstride + l;
     uint4* dst = bnd_f + (size_t)band * bstride + l;
     uint4* ring0 = smem + l;
-    const uint4* ringR = smem + (size_t)R * Cfg::RING_V + l;
+    const int RR = a.rows;                                  // the band's last row is row RR-1: it fills ring RR
+    const uint4* ringR = smem + (size_t)RR * Cfg::RING_V + l;
     int pulled = 0, pushed = 0, idle = 0;
     if (band == 0) {                         // image border: ring 0 stays all zeros (L = 0 for out-of-image predecessors)
         if (l == 0) prog[0] = a.W1 + 1;
         pulled = a.W1 + 1;
     }
     if (band + 1 >= nbands) {                // nothing below this band
-        if (l == 0) prog[R + 1] = PROG_INF;
+        if (l == 0) prog[RR + 1] = PROG_INF;
         pushed = a.W1;
     }
     while (pulled <= a.W1 || pushed < a.W1) {
@@ -536,7 +501,7 @@ __device__ __forceinline__ void sweep_helper(const SweepArgs& a, uint4* smem, vo
             }
         }
         if (pushed < a.W1) {
-            const int avail = min((int)prog[R], a.W1) - pushed;
+            const int avail = min((int)prog[RR], a.W1) - pushed;
             if (avail > 0) {
                 asm volatile("" ::: "memory");
                 const int n = min(avail, 3);
@@ -552,7 +517,7 @@ __device__ __forceinline__ void sweep_helper(const SweepArgs& a, uint4* smem, vo
                 __syncwarp();
                 asm volatile("" ::: "memory");
                 pushed += n;
-                if (l == 0) prog[R + 1] = pushed;
+                if (l == 0) prog[RR + 1] = pushed;
                 did = true;
             }
         }
@@ -562,7 +527,7 @@ __device__ __forceinline__ void sweep_helper(const SweepArgs& a, uint4* smem, vo
             ++idle;
             if ((idle & 255) == 0 && (idle > (SPIN_LIMIT >> 2) || *reinterpret_cast<volatile int*>(a.err) != 0)) {
                 *a.err = 2;
-                if (l == 0) { prog[0] = PROG_INF; prog[R + 1] = PROG_INF; }
+                if (l == 0) { prog[0] = PROG_INF; prog[RR + 1] = PROG_INF; }
                 return;
             }
             __nanosleep(idle > 64 ? 200 : 20);
@@ -580,7 +545,7 @@ sweep_kernel(SweepArgs a)
     __shared__ int s_ticket;
 
     const int tid = threadIdx.x, warp = tid >> 5, l = tid & 31;
-    const int nbands = (a.H + R - 1) / R;
+    const int nbands = (a.H + a.rows - 1) / a.rows;
     const int total = nbands * a.nframes;
     while (true) {
         __syncthreads();                         // the previous band is finished by every warp
@@ -610,7 +575,7 @@ sweep_kernel(SweepArgs a)
         } else {
             sweep_row<K, R, NS, MODE, NDIR, HASPAD, false>(C, S, a, smem, prog, frame, band, warp, l);
         }
-        if (a.dbg && warp == R - 1 && l == 0) {              // the band's last row is done
+        if (a.dbg && warp == a.rows - 1 && l == 0) {         // the band's last row is done
             unsigned long long ns;
             asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns));
             a.dbg[3 * t + 2] = (int)(ns & 0x7fffffff);
@@ -625,21 +590,40 @@ static void launch_sweep_t(const SweepArgs& a, int workers, cudaStream_t st)
     auto kern = sweep_kernel<K, R, NS, MODE, NDIR, HASPAD>;
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
     cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    const int nbands = (a.H + R - 1) / R;
+    const int nbands = (a.H + a.rows - 1) / a.rows;
     const int grid = std::max(1, std::min(workers, nbands * a.nframes));
     kern<<<grid, Cfg::THREADS, Cfg::SMEM, st>>>(a);
 }
 
-int sweep_rows_per_band(const SgbmPlan& p) { return p.K == 1 ? WSG_SW_ROWS1 : WSG_SW_ROWS2; }
-
-size_t sweep_boundary_bytes(const SgbmPlan& p)
+// Rows per band of a launch.  The kernel has RMAX row warps per worker (15 for D <= 256); a launch may use fewer of them.
+// More rows per band = more warps per SM (throughput per SM grows like rows^0.6, measured) -- but the bands of a batch are
+// handed out in WAVES of one per worker, and a launch whose last wave is mostly empty wastes more than a shorter band
+// costs: 8 frames of 2048 rows are 8 x 137 = 7.4 waves of 15-row bands (8 waves of time) but 8 x 147 = 7.95 waves of
+// 14-row bands.  Picks the rows in [RMAX-2, RMAX] with the least modelled time.
+int sweep_rows_per_band(const SgbmPlan& p, int nframes, int workers)
 {
-    const int R = sweep_rows_per_band(p);
-    const int nbands = (p.H + R - 1) / R;
+    const int rmax = p.K == 1 ? WSG_SW_ROWS1 : WSG_SW_ROWS2;
+    static int forced = -1;
+    if (forced < 0) { const char* e = getenv("WSG_SWEEP_ROWS"); forced = e ? atoi(e) : 0; }
+    if (forced > 0) return std::min(std::max(forced, 1), rmax);
+    int best = rmax;
+    double best_t = 1e300;
+    for (int r = rmax; r >= std::max(rmax - 2, 1); --r) {
+        const long long tickets = (long long)((p.H + r - 1) / r) * std::max(nframes, 1);
+        const long long waves = (tickets + workers - 1) / std::max(workers, 1);
+        const double t = (double)waves * std::pow((double)r / rmax, 0.4);       // band time ~ rows / rows^0.6
+        if (t < best_t * 0.995) { best_t = t; best = r; }
+    }
+    return best;
+}
+
+size_t sweep_boundary_bytes(const SgbmPlan& p, int rows)
+{
+    const int nbands = (p.H + rows - 1) / rows;
     return (size_t)std::max(nbands - 1, 1) * p.W1 * 3 * p.K * 32 * 16;
 }
 
-size_t sweep_volume_pad_bytes() { return 8192; }     // >= PFD pixels of 1 KB: the unguarded prefetch at the row ends
+size_t sweep_volume_pad_bytes() { return 8192; }     // >= 4 pixels of 1 KB: the unguarded prefetch at the row ends
 
 bool sweep_supported(const SgbmPlan& p) { return p.NL == 32 && (p.K == 1 || p.K == 2); }
 
@@ -658,7 +642,8 @@ void launch_sweep(const int16_t* C, int16_t* S, int flip, int mode, int ndir, co
     a.P2 = p.P2; a.maxC = sc.maxC; a.scal_stride = sc.maxC_stride; a.one = 1u;
     a.tag = ((sc.epoch & 1) ? 0x8000u : 0u) | ((sc.epoch & 2) ? 0x80000000u : 0u);
     a.bnd = reinterpret_cast<uint4*>(sc.boundary);
-    a.bnd_v = sweep_boundary_bytes(p) / 16;
+    a.rows = sc.rows;
+    a.bnd_v = sweep_boundary_bytes(p, sc.rows) / 16;
     a.ticket = sc.ticket; a.err = sc.err; a.dbg = sc.dbg;
     static int workers_env = -1;
     if (workers_env < 0) { const char* e = getenv("WSG_SWEEP_WORKERS"); workers_env = e ? atoi(e) : 0; }
