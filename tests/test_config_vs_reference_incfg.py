@@ -9,8 +9,10 @@ from helpers import ROOT
 
 REF = os.path.join(ROOT, "oracle", "_ref", "incfg_ref")
 EXE = os.path.join(ROOT, "wass_b200", "bin", "wass_stereo")
-EXT_BLOCK = ("# B200 extension: use the 8-path (MODE_HH) aggregation instead of the reference's 5-path MODE_SGBM\n"
-             "# \n#SGM_FULL_8PATH=false\n\n")
+EXT_BLOCKS = ("# B200 extension: use the 8-path (MODE_HH) aggregation instead of the reference's 5-path MODE_SGBM\n"
+              "# \n#SGM_FULL_8PATH=false\n\n",
+              "# B200 extension: write the diagnostic JPEGs (stereo.jpg, disparity_*.jpg, graph_components.jpg) as the reference "
+              "always does\n# \n#SAVE_DEBUG_IMAGES=true\n\n")
 
 
 @pytest.fixture(scope="module", autouse=True)
@@ -24,8 +26,10 @@ def _built():
 
 
 def _ours_without_extension(text):
-    assert EXT_BLOCK in text
-    return text.replace(EXT_BLOCK, "")
+    for b in EXT_BLOCKS:
+        assert b in text
+        text = text.replace(b, "")
+    return text
 
 
 def test_genconfig_is_the_reference_string(tmp_path):

@@ -89,6 +89,23 @@ def test_full_workdir_run(tmp_path):
               "Cam1_poseT.txt", "wass_stereo_log.txt", "stereo_config.txt", "mesh.ply", "plane_refinement_inliers.xyz",
               "00000000_s.png", "K0_small.txt", "scale.txt"):
         assert (wd / f).exists(), f
+    # the diagnostic JPEGs the reference writes (wass_stereo.cpp:833, 854, 1001-1017, 1911-1926; PovMesh.cpp:982): present,
+    # decodable by an independent decoder, of the reference's sizes, and showing what they should
+    import cv2
+    shapes = {"stereo.jpg": (H, 2 * W, 3), "stereo_input.jpg": (2 * H, W + D, 1), "disparity_stereo_ouput.jpg": (H, W, 1),
+              "disparity_final_scaled.jpg": (H, W, 1), "disparity_coverage.jpg": (H // 2, W // 2, 3),
+              "graph_components.jpg": (H // 2, W // 2, 3)}
+    for f, shp in shapes.items():
+        im = cv2.imread(str(wd / f), cv2.IMREAD_UNCHANGED)
+        assert im is not None, f
+        assert im.shape == (shp[:2] if shp[2] == 1 else shp), (f, im.shape)
+    st = cv2.imread(str(wd / "stereo.jpg"), cv2.IMREAD_GRAYSCALE).astype(int)
+    assert np.abs(st[5:15, 10:W - 10] - left[5:15, 10:W - 10].astype(int)).mean() < 3        # left | right side by side
+    assert np.abs(st[5:15, W + 10:2 * W - 10] - right[5:15, 10:W - 10].astype(int)).mean() < 3
+    gc = cv2.imread(str(wd / "graph_components.jpg"))
+    assert (gc[..., 1] > 128).mean() > 0.5                                                  # the kept component, in green
+    dj = cv2.imread(str(wd / "disparity_final_scaled.jpg"), cv2.IMREAD_GRAYSCALE)
+    assert dj[H // 2, W // 2 - 50:W // 2 + 50].mean() > 20 and dj[:, :4].max() < 16            # disparities inside, nothing at the border
     P1 = workdir.load_matrix_txt(str(wd / "P1cam.txt"))
     assert np.allclose(P1, c["K1"] @ np.hstack([c["R"], c["T"].reshape(3, 1)]))
     assert (wd / "P0cam.txt").read_text().count("\n") == 2 and "e+" in (wd / "P0cam.txt").read_text()
@@ -116,6 +133,21 @@ def test_full_workdir_run(tmp_path):
     z_true = W / dtrue
     # (the exported cloud is cropped to PLANE_MAX_DISTANCE around the fitted plane, so compare ranges, not medians)
     assert z_true.min() * 0.9 < np.percentile(pts[:, 2], 1) and np.percentile(pts[:, 2], 99) < z_true.max() * 1.1
+
+
+@pytest.mark.gpu
+def test_debug_images_can_be_switched_off(tmp_path):
+    from wass_b200 import synth, workdir
+    W, H, D = 320, 240, 48
+    right, left, _ = synth.make_pair(W, H, D, seed=5, d0=8.0)
+    c = synth.make_calibration(W, H)
+    wd = tmp_path / "000000_wd"
+    workdir.write_workdir(str(wd), left, right, c["K0"], c["K1"], c["R"], c["T"])
+    cfg = tmp_path / "stereo_config.txt"
+    workdir.write_config(str(cfg), MAX_DISPARITY=D, RANDOM_SEED=7, PLANE_RANSAC_ROUNDS=60, SAVE_DEBUG_IMAGES=False)
+    r = run([str(cfg), str(wd)])
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+    assert (wd / "mesh_cam.xyzC").exists() and not [f for f in os.listdir(wd) if f.endswith(".jpg")]
 
 
 @pytest.mark.gpu

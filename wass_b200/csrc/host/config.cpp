@@ -108,6 +108,7 @@ Config::Config()
     addd("PLANE_REFINEMENT_MAX_DISTANCE", 70.0, "max point distance for plane refinement");
     // extension of this implementation (absent key == reference behaviour)
     addb("SGM_FULL_8PATH", false, "B200 extension: use the 8-path (MODE_HH) aggregation instead of the reference's 5-path MODE_SGBM");
+    addb("SAVE_DEBUG_IMAGES", true, "B200 extension: write the diagnostic JPEGs (stereo.jpg, disparity_*.jpg, graph_components.jpg) as the reference always does");
 }
 
 void Config::load(std::istream& is)

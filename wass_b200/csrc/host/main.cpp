@@ -342,6 +342,97 @@ void show_time_stats(const Timer& t)   // src/wass_stereo/render.hpp:175-191
     LOGI << "+----------------------------+-------------------+";
 }
 
+// ---- diagnostic images (the reference writes them unconditionally through cv::imwrite; content is informative only) ------
+struct Rgb { int rows = 0, cols = 0; std::vector<uint8_t> px; };
+Rgb gray2rgb(const Image8& g)
+{
+    Rgb o; o.rows = g.rows; o.cols = g.cols; o.px.resize((size_t)g.rows * g.cols * 3);
+    for (size_t i = 0; i < g.px.size(); ++i) o.px[3 * i] = o.px[3 * i + 1] = o.px[3 * i + 2] = g.px[i];
+    return o;
+}
+void rect_red(Rgb& im, int x0, int y0, int w, int h, int xoff = 0, int t = 3)   // cv::rectangle(..., CV_RGB(255,0,0), 3)
+{
+    auto put = [&](int x, int y) {
+        if (x < 0 || y < 0 || x >= im.cols || y >= im.rows) return;
+        uint8_t* p = &im.px[((size_t)y * im.cols + x) * 3]; p[0] = 255; p[1] = 0; p[2] = 0;
+    };
+    for (int k = -(t / 2); k <= t / 2; ++k) {
+        for (int x = x0; x < x0 + w; ++x) { put(x + xoff, y0 + k); put(x + xoff, y0 + h - 1 + k); }
+        for (int y = y0; y < y0 + h; ++y) { put(x0 + k + xoff, y); put(x0 + w - 1 + k + xoff, y); }
+    }
+}
+Rgb half_size(const Rgb& s)      // cv::resize(.., 0.5, 0.5, INTER_LINEAR) up to rounding
+{
+    Rgb o; o.rows = s.rows / 2; o.cols = s.cols / 2; o.px.resize((size_t)o.rows * o.cols * 3);
+    for (int y = 0; y < o.rows; ++y)
+        for (int x = 0; x < o.cols; ++x)
+            for (int c = 0; c < 3; ++c) {
+                const size_t a = ((size_t)(2 * y) * s.cols + 2 * x) * 3 + c, b = a + (size_t)s.cols * 3;
+                o.px[((size_t)y * o.cols + x) * 3 + c] = (uint8_t)((s.px[a] + s.px[a + 3] + s.px[b] + s.px[b + 3] + 2) >> 2);
+            }
+    return o;
+}
+void save_stereo_jpg(const Env& env)           // wass_stereo.cpp:1911-1926
+{
+    const int H = env.left_rect.rows, W = env.left_rect.cols;
+    Rgb o; o.rows = H; o.cols = 2 * W; o.px.resize((size_t)H * 2 * W * 3);
+    for (int y = 0; y < H; ++y)
+        for (int x = 0; x < 2 * W; ++x) {
+            const uint8_t g = x < W ? env.left_rect.px[(size_t)y * W + x] : env.right_rect.px[(size_t)y * W + x - W];
+            uint8_t* p = &o.px[((size_t)y * 2 * W + x) * 3]; p[0] = p[1] = p[2] = g;
+        }
+    rect_red(o, env.roi_left[0], env.roi_left[1], env.roi_left[2], env.roi_left[3]);
+    rect_red(o, env.roi_right[0], env.roi_right[1], env.roi_right[2], env.roi_right[3], W);
+    for (int y = 0; y < H; y += 20)
+        for (int x = 0; x < 2 * W; ++x) { uint8_t* p = &o.px[((size_t)y * 2 * W + x) * 3]; p[0] = 255; p[1] = 0; p[2] = 0; }
+    write_jpeg(path(env, "stereo.jpg"), o.px.data(), o.rows, o.cols, 3);
+}
+void save_disparity_float_jpg(const std::string& fn, const float* d, int rows, int cols)   // render.hpp:97-136
+{
+    float mn = (float)(cols + 1), mx = 0.f;
+    for (size_t i = 0; i < (size_t)rows * cols; ++i) { mn = std::min(mn, d[i]); mx = std::max(mx, d[i]); }
+    std::vector<uint8_t> g((size_t)rows * cols);
+    const float sc = mx > mn ? 255.f / (mx - mn) : 0.f;
+    for (size_t i = 0; i < g.size(); ++i) g[i] = (uint8_t)((d[i] - mn) * sc);
+    write_jpeg(fn, g.data(), rows, cols, 1);
+}
+// stereo_input.jpg, disparity_stereo_ouput.jpg, disparity_final_scaled.jpg, disparity_coverage.jpg (wass_stereo.cpp:833, 854,
+// 1001-1017) from the final float disparity of the ROI.  (The reference renders disparity_stereo_ouput.jpg before its
+// dilate / erode passes; that intermediate never leaves the device here, so both renderings show the final map.)
+void save_dense_jpgs(const Env& env, const wsg_dense_params& dp, const float* disp_roi)
+{
+    const int rh = env.right_crop.rows, rw = env.right_crop.cols;
+    if (dp.DENSE_SCALE == 1.0) {
+        const int N = dp.MAX_DISPARITY, off = std::max(dp.DISPARITY_OFFSET, 0), comp = std::max(-dp.DISPARITY_OFFSET, 0), wp = rw + N + off;
+        std::vector<uint8_t> g((size_t)2 * rh * wp, 0);
+        for (int y = 0; y < rh; ++y) {
+            memcpy(&g[(size_t)y * wp + N + off - comp], &env.left_crop.px[(size_t)y * rw], rw);
+            memcpy(&g[(size_t)(rh + y) * wp + N], &env.right_crop.px[(size_t)y * rw], rw);
+        }
+        write_jpeg(path(env, "stereo_input.jpg"), g.data(), 2 * rh, wp, 1);
+    }
+    save_disparity_float_jpg(path(env, "disparity_stereo_ouput.jpg"), disp_roi, rh, rw);
+    const int H = env.right_rect.rows, W = env.right_rect.cols;
+    std::vector<float> full((size_t)H * W, 0.f);
+    for (int y = 0; y < rh; ++y) memcpy(&full[(size_t)(env.roi_right[1] + y) * W + env.roi_right[0]], disp_roi + (size_t)y * rw, (size_t)rw * 4);
+    save_disparity_float_jpg(path(env, "disparity_final_scaled.jpg"), full.data(), H, W);
+    Rgb cov = gray2rgb(env.right_rect);
+    for (size_t i = 0; i < full.size(); ++i) if (full[i] > 1.f) cov.px[3 * i + 1] = 100;
+    rect_red(cov, env.roi_right[0], env.roi_right[1], env.roi_right[2], env.roi_right[3]);
+    const Rgb h2 = half_size(cov);
+    write_jpeg(path(env, "disparity_coverage.jpg"), h2.px.data(), h2.rows, h2.cols, 3);
+}
+// graph_components.jpg (PovMesh.cpp:222-252, 982-984): the biggest component in green, at half size.  The reference gives
+// every other component its own palette colour; the component labels stay on the device here, so all of them are drawn red.
+void save_components_jpg(const Env& env, const std::vector<uint8_t>& before, const std::vector<uint8_t>& after, int w, int h)
+{
+    Rgb im; im.rows = h; im.cols = w; im.px.assign((size_t)w * h * 3, 0);
+    for (size_t i = 0; i < before.size(); ++i)
+        if (after[i]) im.px[3 * i + 1] = 255; else if (before[i]) im.px[3 * i] = 255;
+    const Rgb h2 = half_size(im);
+    write_jpeg(path(env, "graph_components.jpg"), h2.px.data(), h2.rows, h2.cols, 3);
+}
+
 #define WSG_CHECK(call) do { if ((call) != WSG_OK) throw std::runtime_error(std::string(#call) + ": " + wsg_last_error(h)); } while (0)
 
 }  // namespace
@@ -381,6 +472,7 @@ static int stage_load_rectify(Env& env, const Config& cfg, wsg_handle* h)
     std::cout << "[P|20|100]" << std::endl;
     LOG_SCOPE("wass_stereo");
     save_poses(env);
+    if (cfg.getb("SAVE_DEBUG_IMAGES")) save_stereo_jpg(env);
     return 0;
 }
 
@@ -407,9 +499,12 @@ static void log_dense_end(Env& env, wsg_handle* h)
 
 // Everything after the dense matcher, on the disparity the handle holds: triangulation, outlier removal, plane, export
 // (wass_stereo.cpp:1981-2141).  plane_out: the four numbers of plane.txt (NaN on a soft RANSAC failure).  Returns 0 / -1.
-static int stage_after_dense(Env& env, const Config& cfg, wsg_handle* h, const wsg_dense_params& dp, double plane_out[4])
+static int stage_after_dense(Env& env, const Config& cfg, wsg_handle* h, const wsg_dense_params& dp, double plane_out[4],
+                             const float* disp_roi = nullptr)
 {
     for (int i = 0; i < 4; ++i) plane_out[i] = std::nan("");
+    const bool dbg_images = cfg.getb("SAVE_DEBUG_IMAGES");
+    if (dbg_images && disp_roi) save_dense_jpgs(env, dp, disp_roi);
     try {
         // ---- triangulation (wass_stereo.cpp:1039-1386)
         LOG_SCOPE("triangulate");
@@ -460,7 +555,19 @@ static int stage_after_dense(Env& env, const Config& cfg, wsg_handle* h, const w
         unsigned long long nleft = 0;
         LOG_SCOPE("cluster");
         LOGI << "extracting connected-components";
+        std::vector<uint8_t> valid_before, valid_after;
+        int cw = 0, ch = 0;
+        if (dbg_images) {
+            WSG_CHECK(wsg_mesh_size(h, &cw, &ch, nullptr));
+            valid_before.resize((size_t)cw * ch);
+            WSG_CHECK(wsg_mesh_download(h, valid_before.data(), nullptr, nullptr));
+        }
         WSG_CHECK(wsg_mesh_biggest_component(h, zgap, &nleft));
+        if (dbg_images) {
+            valid_after.resize(valid_before.size());
+            WSG_CHECK(wsg_mesh_download(h, valid_after.data(), nullptr, nullptr));
+            save_components_jpg(env, valid_before, valid_after, cw, ch);
+        }
         LOGI << "biggest component size: " << nleft << " (px)";
         env.timer.mark("Outlier removal");
         std::cout << "[P|80|100]" << std::endl;
@@ -674,8 +781,12 @@ static int run_batch(int argc, char* argv[])
                     grp.push_back(b);
             std::vector<const uint8_t*> lc, rc;
             for (size_t b : grp) { g_logfile = logs[b]; log_dense_begin(envs[b], dp); lc.push_back(envs[b].left_crop.px.data()); rc.push_back(envs[b].right_crop.px.data()); }
+            const bool dbg_images = cfg.getb("SAVE_DEBUG_IMAGES");
+            std::vector<std::vector<float>> droi(dbg_images ? grp.size() : 0);
+            std::vector<float*> dptr;
+            for (auto& v : droi) { v.resize((size_t)envs[a0].right_crop.rows * envs[a0].right_crop.cols); dptr.push_back(v.data()); }
             const int rcode = wsg_dense_stereo_batch(h, (int)grp.size(), lc.data(), rc.data(), envs[a0].right_crop.rows, envs[a0].right_crop.cols,
-                                                     envs[a0].right_crop.cols, &dp, nullptr);
+                                                     envs[a0].right_crop.cols, &dp, dbg_images ? dptr.data() : nullptr);
             for (size_t k = 0; k < grp.size(); ++k) {
                 const size_t b = grp[k];
                 done[b] = 1;
@@ -685,7 +796,8 @@ static int run_batch(int argc, char* argv[])
                 // the per-frame seed of a single-frame run: RANDOM_SEED (or the clock) at process start, then one rand() stream
                 // per process.  One process per SEQUENCE would couple the frames' draws, so every frame re-seeds.
                 if (cfg.geti("RANDOM_SEED") == -1) srand((unsigned)time(0) + (unsigned)mine[g0 + b]); else srand(cfg.geti("RANDOM_SEED"));
-                if (wsg_dense_select(h, (int)k) != WSG_OK || stage_after_dense(envs[b], cfg, h, dp, &planes[(g0 + b) * 4]) != 0) state[b] = -1;
+                if (wsg_dense_select(h, (int)k) != WSG_OK ||
+                    stage_after_dense(envs[b], cfg, h, dp, &planes[(g0 + b) * 4], dbg_images ? droi[k].data() : nullptr) != 0) state[b] = -1;
             }
         }
         for (size_t b = 0; b < g1 - g0; ++b) {
@@ -786,14 +898,16 @@ int main(int argc, char* argv[])
     // ---- dense stereo (wass_stereo.cpp:764-1020)
     const wsg_dense_params dp = make_dense_params(cfg);
     log_dense_begin(env, dp);
+    std::vector<float> disp_roi;
+    if (cfg.getb("SAVE_DEBUG_IMAGES")) disp_roi.resize((size_t)env.right_crop.rows * env.right_crop.cols);
     if (wsg_dense_stereo(h, env.left_crop.px.data(), env.right_crop.px.data(), env.right_crop.rows, env.right_crop.cols,
-                         env.right_crop.cols, &dp, nullptr, nullptr) != WSG_OK) {
+                         env.right_crop.cols, &dp, disp_roi.empty() ? nullptr : disp_roi.data(), nullptr) != WSG_OK) {
         LOGE << "wsg_dense_stereo: " << wsg_last_error(h);
         return -1;
     }
     log_dense_end(env, h);
     double plane[4];
-    if (stage_after_dense(env, cfg, h, dp, plane) != 0) return -1;
+    if (stage_after_dense(env, cfg, h, dp, plane, disp_roi.empty() ? nullptr : disp_roi.data()) != 0) return -1;
     wsg_destroy(h);
     return 0;
 }

@@ -74,6 +74,14 @@ template <int K, int R, int NS, int MODE> struct SweepCfg {
     static_assert(STAGGER >= 0 && STAGGER <= NS - 4 + 0 || NS < 4, "stagger beyond the ring's slack");
 };
 
+// TMA prefetch: one thread asks the copy engine to pull `bytes` (a multiple of 16) of global memory into L2.  A row warp
+// issues one per stream and four pixels, eight pixels ahead of its register loads, which then hit L2 instead of HBM.
+__device__ __forceinline__ void bulk_prefetch_l2(const void* gptr, unsigned bytes)
+{
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gptr), "r"(bytes) : "memory");
+}
+static constexpr int SW_PF_AHEAD = 8;       // pixels between the L2 prefetch and the register load of the same pixel
+
 struct SweepArgs {
     int H, W1, W, D;
     int Dp8;                 // 16-byte vectors per pixel (= 32*K)
@@ -224,6 +232,8 @@ __device__ __forceinline__ void wta_flush(unsigned key, unsigned nb, int xl, boo
 template <int K> struct RowState {
     const uint4* cpf; const uint4* spf; uint4* scur;      // C / S prefetch cursors, S store cursor
     long long dstep;
+    const char* pfC; const char* pfS;                     // L2 prefetch cursors: lowest address of the next group of four pixels
+    long long pfstep;
     const uint4* ring_in; uint4* ring_out;
     uint16_t* scratch;                                    // final S of the previous pixel, natural disparity order
     volatile int* prog_in; volatile int* prog_me; volatile int* prog_next;
@@ -264,6 +274,13 @@ __device__ __forceinline__ void sweep_step(RowState<K>& st, const SweepArgs& a, 
     unsigned (&vsp)[NR] = st.Vs[U & 1];             // S(x-1)
     unsigned (&vsn)[NR] = st.Vs[(U + 1) & 1];       // S(x), made here
     unsigned v[3][NR], Nd[3][NR];
+    if (U == 0) {                                   // pixels x+3+AHEAD .. x+6+AHEAD into L2, one TMA prefetch per stream
+        if (l == 0) {
+            bulk_prefetch_l2(st.pfC, 4u * K * 512u);
+            if (MODE != 0) bulk_prefetch_l2(st.pfS, 4u * K * 512u);
+        }
+        st.pfC += st.pfstep; st.pfS += st.pfstep;
+    }
     load_set<K>(st.Cs[(U + 3) & 3], st.cpf);        // C(x+3) into the set C(x-1) has left (past the row end: unused data)
     st.cpf += st.dstep;
     if (MODE == 0) {
@@ -360,6 +377,13 @@ __device__ __forceinline__ void sweep_row(const uint4* __restrict__ C, uint4* __
     st.l = l; st.one = a.one; st.P1p = a.P1p; st.P2mP1p = a.P2mP1p;
     st.dstep = a.flip ? -(long long)a.Dp8 : (long long)a.Dp8;
     st.cpf = C + first; st.spf = S + first; st.scur = S + first;
+    {   // the group of four pixels x+3+AHEAD .. x+6+AHEAD (logical) starts, in memory, at its first pixel (flip: at its last)
+        const long long px0 = 3 + SW_PF_AHEAD + (a.flip ? 3 : 0);
+        const long long off = ((long long)yp * W1 + (a.flip ? W1 - 1 - px0 : px0)) * a.Dp8;
+        st.pfC = reinterpret_cast<const char*>(C + off);
+        st.pfS = reinterpret_cast<const char*>(S + off);
+        st.pfstep = (a.flip ? -4ll : 4ll) * a.Dp8 * 16;
+    }
     st.ring_in = smem + (size_t)r * Cfg::RING_V + l;
     st.ring_out = smem + (size_t)(r + 1) * Cfg::RING_V + l;
     st.scratch = reinterpret_cast<uint16_t*>(smem + Cfg::RINGS_V + (size_t)r * Cfg::PIX_V);
@@ -623,7 +647,7 @@ size_t sweep_boundary_bytes(const SgbmPlan& p, int rows)
     return (size_t)std::max(nbands - 1, 1) * p.W1 * 3 * p.K * 32 * 16;
 }
 
-size_t sweep_volume_pad_bytes() { return 8192; }     // >= 4 pixels of 1 KB: the unguarded prefetch at the row ends
+size_t sweep_volume_pad_bytes() { return 32768; }    // the unguarded prefetches at the row ends reach 3 + 8 + 4 pixels of up to 1 KB beyond
 
 bool sweep_supported(const SgbmPlan& p) { return p.NL == 32 && (p.K == 1 || p.K == 2); }
 
