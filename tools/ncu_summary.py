@@ -2,7 +2,7 @@
 """Summarise ncu outputs brought back in gpurun_out/ into small text files under profiles/.
     python tools/ncu_summary.py launches <launches.csv> <out.txt>
     python tools/ncu_summary.py rep <file.ncu-rep> <out.txt>
-    python tools/ncu_summary.py traffic <file.ncu-rep> <out.json> "<note>"
+    python tools/ncu_summary.py traffic <file.ncu-rep> <out.json> "<note>" [frames per launch]
 """
 import collections
 import csv
@@ -55,7 +55,7 @@ def rep(path, out):
     print(open(out).read())
 
 
-def traffic(rep, out_json, source_note):
+def traffic(rep, out_json, source_note, frames_per_launch=1):
     """profiles/traffic.json: DRAM bytes per launch (read+write, averaged over the captured launches) per kernel family."""
     import json
     txt = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv", "--metrics",
@@ -73,7 +73,7 @@ def traffic(rep, out_json, source_note):
         rd = float(r[ri].replace(",", "")) * scale(units[ri]); wr = float(r[wi].replace(",", "")) * scale(units[wi])
         t = float(r[ti].replace(",", "")) * scale(units[ti])
         fam.setdefault(name, []).append((rd, wr, t))
-    out = {"source": source_note}
+    out = {"source": source_note, "frames_per_launch": frames_per_launch}
     for n, v in fam.items():
         out[n] = {"launches_captured": len(v), "dram_read_bytes_per_launch": sum(x[0] for x in v) / len(v),
                   "dram_write_bytes_per_launch": sum(x[1] for x in v) / len(v),
@@ -85,6 +85,6 @@ def traffic(rep, out_json, source_note):
 
 if __name__ == "__main__":
     if sys.argv[1] == "traffic":
-        traffic(sys.argv[2], sys.argv[3], sys.argv[4] if len(sys.argv) > 4 else "")
+        traffic(sys.argv[2], sys.argv[3], sys.argv[4] if len(sys.argv) > 4 else "", int(sys.argv[5]) if len(sys.argv) > 5 else 1)
     else:
         {"launches": launches, "rep": rep}[sys.argv[1]](sys.argv[2], sys.argv[3])
