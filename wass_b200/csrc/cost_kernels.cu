@@ -4,11 +4,11 @@
 // Three stages run CONCURRENTLY on different warps of the CTA, one image row apart, with one barrier per row:
 //   T   (2 warps)  unpack the prefilter records of row r+2 into broadcast records (img1 side) and a reversed table
 //                  (img2 side, two copies one element apart) in shared memory; the records of row r+3 are in flight meanwhile
-//   P1  (3 warps)  Birchfield-Tomasi pixel cost of row r+1 for 64+2*SW2 columns x 32 disparities, two disparities per
-//                  32-bit register (VIADD.16x2 / VIADDMNMX.S16x2.RELU / VIMNMX.S16x2).  One thread = FOUR adjacent columns x
-//                  8 disparities: columns c and c+2 see the img2 table two entries apart, so ten table words per table serve
-//                  all four columns (5 from each parity copy) instead of sixteen, and the sums of the column pairs
-//                  (c,c+1), (c+2,c+3) that stage P2 reads are thread-local
+//   P1  (5 warps)  Birchfield-Tomasi pixel cost of row r+1 for 64+2*SW2 columns x 32 disparities, two disparities per
+//                  32-bit register (VIADD.16x2 / VIADDMNMX.S16x2.RELU / VIMNMX.S16x2).  One thread = columns c and c+2 x
+//                  8 disparities: the two see the img2 table two entries (one word) apart, so five table words per table
+//                  serve both instead of eight; the neighbouring lane owns c+1 and c+3 (the other parity copy of the
+//                  table), and the sums of the column pairs (c,c+1), (c+2,c+3) that stage P2 reads take one exchange
 //   P2  (4 warps)  row r: horizontal box sum (SW2 column pairs + one column, then sliding to the next column), a ring of
 //                  2*SH2+1 row sums in shared memory for the vertical sliding sum, 16-byte stores of C
 // The kernel is bound by the shared-memory pipe (wavefronts) and by instruction issue together, so (a) every layout is
@@ -32,12 +32,12 @@ static constexpr int WNCOL = WXT + 2 * WMAXSW;     // columns of pixel costs per
 static constexpr int WQN = 26;             // 16-byte slots between the per-column sub-arrays of the img1 records (= 2 mod 8)
 static constexpr int WVT = WNCOL + WDT;            // entries of the reversed img2 tables (largest index used: ncol + 30)
 static constexpr int WNTAB = 6;            // img2 tables: V, Vlo, -Vhi for the two channels (-V is made in the ALU)
-static constexpr int WBOFF = WNTAB * WVT + 8;      // s16 offset of copy B (entry i at i-1: odd-index pairs word-aligned)
+static constexpr int WBOFF = WNTAB * WVT + 10;     // s16 offset of copy B (entry i at i-1: odd-index pairs word-aligned); an ODD number of words
 static constexpr int WRV = WBOFF + WNTAB * WVT;    // s16 per table set
 static constexpr int WUSZ = 2 * 4 * WQN * 4;       // u32 per img1 record set: [half][column & 3][column >> 2][4]
-static constexpr int WP1T = 96, WTT = 64, WP2T = 128;
+static constexpr int WP1T = 160, WTT = 64, WP2T = 128;
 static constexpr int WCT = WP1T + WTT + WP2T;
-static_assert(WNCOL / 4 <= WQN && WQN % 8 == 2 && WBOFF % 2 == 0 && WNCOL / 4 * 4 <= WP1T && 3 * WTT >= WNCOL + WVT, "cost tile");
+static_assert(WNCOL / 4 <= WQN && WQN % 8 == 2 && WBOFF % 4 == 2 && WNCOL / 4 * 8 <= WP1T && 3 * WTT >= WNCOL + WVT, "cost tile");
 
 // Physical column of logical column c in the pd / ring arrays, and of column pair j in pp.  A quarter-warp of a 16-byte
 // access covers two columns (P1: 4q+j and 4q+4+j; P2: c and c+4, see its lane mapping) or two pairs (two apart):
@@ -128,56 +128,56 @@ __global__ void __launch_bounds__(WCT, 2) cost_wide_kernel(const uint2* __restri
 
     if (tid < WP1T) {
         // ================= P1: pixel cost of row-step s-1 from tables[(s-1)&1] into pd[(s-1)&1], pp[(s-1)&1]
-        // lane = g + 4 * (q & 7): a warp covers 8 column quads x 4 groups of 8 disparities.  One table LDS then reads words
-        // W - 2q + 4g: 27 consecutive banks at most, no conflict; the img1 records of one column residue sit in 8
-        // consecutive 16-byte slots (one wavefront, the four groups broadcast).
-        const int q = tid >> 2, g = tid & 3, cb = 4 * q;
+        // thread = (quad q of columns, e, g): columns 4q+e ("H") and 4q+e+2 ("L"), disparities 8g..8g+7; lane = e + 2g + 8(q&3).
+        // One table LDS reads words W - 2q + 4g from one parity copy for the even lanes and from the other for the odd
+        // lanes; the copies sit an odd number of words apart, so even word offsets of the two never share a bank.
+        const int e = tid & 1, g = (tid >> 1) & 3, q = tid >> 3, cb = 4 * q;
         const int xu = x0 - p.SW2 + cb;                        // W1-space column of the quad's first column, unclamped
         const bool on = cb < ncol, real = d0 + 8 * g < p.D;
-        // regular quad: no column clamped to the image -> table index of column cb+j = I - j
+        // regular quad: no column clamped to the image -> table index of column cb+j = I0 - j
         const bool regular = xu >= 0 && xu + 3 <= p.W1 - 1 && cb + 3 < ncol;
-        const int I = xb - (p.minX1 + xu) + 8 * g;
-        const int rvA = rv_off(max(I - 2, 0)) >> 1, rvB = rv_off(max(I - 3, 0)) >> 1;     // word offsets of the two 5-word spans
-        int pdo[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) pdo[j] = pd_off(cb + j, g);
-        const int ppo0 = ppcol(2 * q) * WDT + g * 8, ppo1 = ppcol(2 * q + 1) * WDT + g * 8;
+        const int I = xb - (p.minX1 + xu) - e + 8 * g;         // table index of column H (regular quads)
+        const int rvw = rv_off(max(I - 2, 0)) >> 1;            // word offset of entries I-2 .. I+7: H = words 1..4, L = words 0..3
+        const int pdH = pd_off(cb + e, g), pdL = pd_off(cb + e + 2, g);
+        const int ppo = ppcol(2 * q + e) * WDT + g * 8;        // pair (4q, 4q+1) for e = 0, (4q+2, 4q+3) for e = 1
+        const int uH = (e * WQN + q) * 4, uL = ((e + 2) * WQN + q) * 4;
         for (int s = 0; s < nsteps + 2; ++s) {
             const int rs = s - 1;
-            if (on && rs >= 0 && rs < nsteps) {
+            if (rs >= 0 && rs < nsteps) {
                 const int b = rs & 1;
-                uint4 out[4];
-#pragma unroll
-                for (int j = 0; j < 4; ++j) out[j] = make_uint4(0, 0, 0, 0);
-                if (real) {
+                uint4 oH = make_uint4(0, 0, 0, 0), oL = make_uint4(0, 0, 0, 0);
+                if (on && real) {
                     const unsigned* tw = reinterpret_cast<const unsigned*>(rv + b * WRV);
-                    const unsigned* ur = uu + b * WUSZ + q * 4;
+                    const unsigned* ur = uu + b * WUSZ;
                     unsigned T[WNTAB][5];
                     if (regular) {
-                        load_tables<5>(tw + rvA, T);               // entries I-2 .. I+7: columns cb (words 1..4), cb+2 (0..3)
-                        out[0] = bt_cost4<1>(ur + 0 * WQN * 4, T);
-                        out[2] = bt_cost4<0>(ur + 2 * WQN * 4, T);
-                        load_tables<5>(tw + rvB, T);               // entries I-3 .. I+6: columns cb+1 (words 1..4), cb+3 (0..3)
-                        out[1] = bt_cost4<1>(ur + 1 * WQN * 4, T);
-                        out[3] = bt_cost4<0>(ur + 3 * WQN * 4, T);
+                        load_tables<5>(tw + rvw, T);
+                        oH = bt_cost4<1>(ur + uH, T);
+                        oL = bt_cost4<0>(ur + uL, T);
                     } else {
                         // image border (columns replicate the first / last one) or the partial last quad: column by column
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            if (cb + j < ncol) {
-                                const int i0 = xb - (p.minX1 + min(max(xu + j, 0), p.W1 - 1)) + 8 * g;
-                                load_tables<4>(tw + (rv_off(i0) >> 1), T);
-                                out[j] = bt_cost4<0>(ur + j * WQN * 4, T);
-                            }
+                        if (cb + e < ncol) {
+                            const int i0 = xb - (p.minX1 + min(max(xu + e, 0), p.W1 - 1)) + 8 * g;
+                            load_tables<4>(tw + (rv_off(i0) >> 1), T);
+                            oH = bt_cost4<0>(ur + uH, T);
+                        }
+                        if (cb + e + 2 < ncol) {
+                            const int i0 = xb - (p.minX1 + min(max(xu + e + 2, 0), p.W1 - 1)) + 8 * g;
+                            load_tables<4>(tw + (rv_off(i0) >> 1), T);
+                            oL = bt_cost4<0>(ur + uL, T);
                         }
                     }
                 }
                 uint16_t* prow = pd + b * WNCOL * WDTP;
-#pragma unroll
-                for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(prow + pdo[j]) = out[j];
-                uint16_t* qrow = pp + b * (WNCOL / 2) * WDT;
-                *reinterpret_cast<uint4*>(qrow + ppo0) = vadd2x4(out[0], out[1]);
-                *reinterpret_cast<uint4*>(qrow + ppo1) = vadd2x4(out[2], out[3]);
+                if (on) {
+                    *reinterpret_cast<uint4*>(prow + pdH) = oH;
+                    *reinterpret_cast<uint4*>(prow + pdL) = oL;
+                }
+                // sums of the column pairs (4q, 4q+1), (4q+2, 4q+3): the partner lane (e ^ 1) holds the other column of each
+                const uint4 snd = e ? oH : oL, mine = e ? oL : oH;
+                const uint4 rcv = make_uint4(__shfl_xor_sync(FULL, snd.x, 1), __shfl_xor_sync(FULL, snd.y, 1),
+                                             __shfl_xor_sync(FULL, snd.z, 1), __shfl_xor_sync(FULL, snd.w, 1));
+                if (on) *reinterpret_cast<uint4*>(pp + b * (WNCOL / 2) * WDT + ppo) = vadd2x4(mine, rcv);
             }
             __syncthreads();
         }
