@@ -80,6 +80,12 @@ __device__ __forceinline__ void bulk_prefetch_l2(const void* gptr, unsigned byte
 {
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gptr), "r"(bytes) : "memory");
 }
+#ifndef WSG_SW_CA
+#define WSG_SW_CA 2          // pixels the register load of C runs ahead of its use (2..3; the horizontal path uses C(x+1))
+#endif
+#ifndef WSG_SW_SA
+#define WSG_SW_SA 2          // the same for S (1..2)
+#endif
 static constexpr int SW_PF_AHEAD = 8;       // pixels between the L2 prefetch and the register load of the same pixel
 
 struct SweepArgs {
@@ -281,7 +287,7 @@ __device__ __forceinline__ void sweep_step(RowState<K>& st, const SweepArgs& a, 
         }
         st.pfC += st.pfstep; st.pfS += st.pfstep;
     }
-    load_set<K>(st.Cs[(U + 3) & 3], st.cpf);        // C(x+3) into the set C(x-1) has left (past the row end: unused data)
+    load_set<K>(st.Cs[(U + WSG_SW_CA) & 3], st.cpf);   // C(x+CA) into a set that is free (past the row end: unused data)
     st.cpf += st.dstep;
     if (MODE == 0) {
 #pragma unroll
@@ -289,7 +295,7 @@ __device__ __forceinline__ void sweep_step(RowState<K>& st, const SweepArgs& a, 
     } else {
 #pragma unroll
         for (int j = 0; j < NR; ++j) vsn[j] = __viaddmin_u16x2(st.Ss[U & 1][j], Lh[j], SAT2);
-        load_set<K>(st.Ss[U & 1], st.spf);          // S(x+2)
+        load_set<K>(st.Ss[(U + WSG_SW_SA) & 1], st.spf);          // S(x+SA)
         st.spf += st.dstep;
     }
     if (NDIR == 4) {
@@ -398,10 +404,10 @@ __device__ __forceinline__ void sweep_row(const uint4* __restrict__ C, uint4* __
     // C(0), C(1), C(2) and S(0), S(1) up front; every step then issues C(x+3) and S(x+2).  The loads are not guarded at the
     // row end: the volumes are readable a few pixels beyond either end.
 #pragma unroll
-    for (int i = 0; i < 3; ++i) { load_set<K>(st.Cs[i], st.cpf); st.cpf += st.dstep; }
+    for (int i = 0; i < WSG_SW_CA; ++i) { load_set<K>(st.Cs[i], st.cpf); st.cpf += st.dstep; }
     if (MODE != 0) {
 #pragma unroll
-        for (int i = 0; i < 2; ++i) { load_set<K>(st.Ss[i], st.spf); st.spf += st.dstep; }
+        for (int i = 0; i < WSG_SW_SA; ++i) { load_set<K>(st.Ss[i], st.spf); st.spf += st.dstep; }
     }
 #pragma unroll
     for (int j = 0; j < NR; ++j) { st.Vs[0][j] = 0; st.Vs[1][j] = 0; st.Nh[j] = 0; }
