@@ -94,8 +94,9 @@ def test_full_workdir_run(tmp_path):
     import cv2
     rh, rw = cv2.imread(str(wd / "disparity_stereo_ouput.jpg"), cv2.IMREAD_UNCHANGED).shape        # the common ROI
     assert H - 4 <= rh <= H and W - 4 <= rw <= W
-    shapes = {"stereo.jpg": (H, 2 * W, 3), "stereo_input.jpg": (2 * rh, rw + D, 1), "disparity_final_scaled.jpg": (H, W, 1), "disparity_coverage.jpg": (H // 2, W // 2, 3),
-              "graph_components.jpg": (H // 2, W // 2, 3)}
+    shapes = {"stereo.jpg": (H, 2 * W, 3), "stereo_input.jpg": (2 * rh, rw + D, 1), "disparity_final_scaled.jpg": (H, W, 1),
+              "disparity_coverage.jpg": (H // 2, W // 2, 3),
+              "graph_components.jpg": (int(np.rint(rh * 0.5)), int(np.rint(rw * 0.5)), 3)}      # cv::resize: cvRound(n * 0.5)
     for f, shp in shapes.items():
         im = cv2.imread(str(wd / f), cv2.IMREAD_UNCHANGED)
         assert im is not None, f
@@ -106,7 +107,7 @@ def test_full_workdir_run(tmp_path):
     gc = cv2.imread(str(wd / "graph_components.jpg"))
     assert (gc[..., 1] > 128).mean() > 0.5                                                  # the kept component, in green
     dj = cv2.imread(str(wd / "disparity_final_scaled.jpg"), cv2.IMREAD_GRAYSCALE)
-    assert dj[H // 2, W // 2 - 50:W // 2 + 50].mean() > 20 and dj[:, :4].max() < 16            # disparities inside, nothing at the border
+    assert dj[H // 2, W // 2 - 50:W // 2 + 50].mean() > 20 and dj.min() < 8                    # disparities inside, holes rendered dark
     P1 = workdir.load_matrix_txt(str(wd / "P1cam.txt"))
     assert np.allclose(P1, c["K1"] @ np.hstack([c["R"], c["T"].reshape(3, 1)]))
     assert (wd / "P0cam.txt").read_text().count("\n") == 2 and "e+" in (wd / "P0cam.txt").read_text()

@@ -51,13 +51,26 @@ struct BitWriter {
     void flush() { if (n) put(0x7F, 8 - n); }
 };
 
-void fdct8x8(const float* in, float* out, const float (*cs)[8])
+// 8-point forward DCT after Arai, Agui and Nakajima (5 multiplications; the outputs carry the factors AAN[k], which go into
+// the quantisation divisors), rows then columns, in place.
+const float AAN[8] = {1.0f, 1.387039845f, 1.306562965f, 1.175875602f, 1.0f, 0.785694958f, 0.541196100f, 0.275899379f};
+inline void fdct8(float* d, int st)
 {
-    float tmp[64];
-    for (int y = 0; y < 8; ++y)
-        for (int u = 0; u < 8; ++u) { float s = 0; for (int x = 0; x < 8; ++x) s += in[y * 8 + x] * cs[u][x]; tmp[y * 8 + u] = s; }
-    for (int v = 0; v < 8; ++v)
-        for (int u = 0; u < 8; ++u) { float s = 0; for (int y = 0; y < 8; ++y) s += tmp[y * 8 + u] * cs[v][y]; out[v * 8 + u] = s; }
+    const float t0 = d[0] + d[7 * st], t7 = d[0] - d[7 * st], t1 = d[st] + d[6 * st], t6 = d[st] - d[6 * st];
+    const float t2 = d[2 * st] + d[5 * st], t5 = d[2 * st] - d[5 * st], t3 = d[3 * st] + d[4 * st], t4 = d[3 * st] - d[4 * st];
+    const float e0 = t0 + t3, e3 = t0 - t3, e1 = t1 + t2, e2 = t1 - t2;
+    d[0] = e0 + e1; d[4 * st] = e0 - e1;
+    const float z1 = (e2 + e3) * 0.707106781f;
+    d[2 * st] = e3 + z1; d[6 * st] = e3 - z1;
+    const float o0 = t4 + t5, o1 = t5 + t6, o2 = t6 + t7;
+    const float z5 = (o0 - o2) * 0.382683433f, z2 = 0.541196100f * o0 + z5, z4 = 1.306562965f * o2 + z5, z3 = o1 * 0.707106781f;
+    const float z11 = t7 + z3, z13 = t7 - z3;
+    d[5 * st] = z13 + z2; d[3 * st] = z13 - z2; d[st] = z11 + z4; d[7 * st] = z11 - z4;
+}
+inline void fdct8x8(float* b)
+{
+    for (int y = 0; y < 8; ++y) fdct8(b + 8 * y, 1);
+    for (int x = 0; x < 8; ++x) fdct8(b + x, 8);
 }
 
 void put16(std::vector<unsigned char>& o, int v) { o.push_back((unsigned char)(v >> 8)); o.push_back((unsigned char)v); }
@@ -73,9 +86,9 @@ bool write_jpeg(const std::string& path, const unsigned char* px, int rows, int 
     unsigned char q[2][64];
     for (int t = 0; t < 2; ++t)
         for (int i = 0; i < 64; ++i) { int v = ((t ? QCHR[i] : QLUM[i]) * scale + 50) / 100; q[t][i] = (unsigned char)(v < 1 ? 1 : (v > 255 ? 255 : v)); }
-    float cs[8][8];
-    for (int u = 0; u < 8; ++u)
-        for (int x = 0; x < 8; ++x) cs[u][x] = (u == 0 ? 0.35355339f : 0.5f) * cosf((2 * x + 1) * u * 3.14159265358979f / 16.f);
+    float rq[2][64];                          // 1 / (quantiser * AAN scale of the coefficient), in zig-zag order
+    for (int t = 0; t < 2; ++t)
+        for (int i = 0; i < 64; ++i) { const int n = ZIGZAG[i]; rq[t][i] = 1.f / ((float)q[t][n] * AAN[n >> 3] * AAN[n & 7] * 8.f); }
     Huff dc, ac;
     build(DC_BITS, DC_VALS, dc);
     build(AC_BITS, AC_VALS, ac);
@@ -96,9 +109,15 @@ bool write_jpeg(const std::string& path, const unsigned char* px, int rows, int 
     o.push_back(0); o.push_back(63); o.push_back(0);
     BitWriter bw(o);
     int pred[3] = {0, 0, 0};
-    float blk[3][64], coef[64];
+    float blk[3][64];
     for (int by = 0; by < rows; by += 8)
         for (int bx = 0; bx < cols; bx += 8) {
+            if (channels == 1 && by + 8 <= rows && bx + 8 <= cols) {
+                for (int y = 0; y < 8; ++y) {
+                    const unsigned char* p = px + (size_t)(by + y) * cols + bx;
+                    for (int x = 0; x < 8; ++x) blk[0][y * 8 + x] = (float)p[x] - 128.f;
+                }
+            } else
             for (int y = 0; y < 8; ++y)
                 for (int x = 0; x < 8; ++x) {
                     const int yy = by + y < rows ? by + y : rows - 1, xx = bx + x < cols ? bx + x : cols - 1;
@@ -113,10 +132,10 @@ bool write_jpeg(const std::string& path, const unsigned char* px, int rows, int 
                     }
                 }
             for (int c = 0; c < channels; ++c) {
-                fdct8x8(blk[c], coef, cs);
+                fdct8x8(blk[c]);
                 int zz[64];
-                const unsigned char* qt = q[c ? 1 : 0];
-                for (int i = 0; i < 64; ++i) zz[i] = (int)lrintf(coef[ZIGZAG[i]] / (float)qt[ZIGZAG[i]]);
+                const float* r = rq[c ? 1 : 0];
+                for (int i = 0; i < 64; ++i) { const float v = blk[c][ZIGZAG[i]] * r[i]; zz[i] = (int)(v + (v < 0 ? -0.5f : 0.5f)); }
                 int diff = zz[0] - pred[c];
                 pred[c] = zz[0];
                 int a = diff < 0 ? -diff : diff, nb = 0;

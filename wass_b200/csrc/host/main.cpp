@@ -344,6 +344,17 @@ void show_time_stats(const Timer& t)   // src/wass_stereo/render.hpp:175-191
 
 // ---- diagnostic images (the reference writes them unconditionally through cv::imwrite; content is informative only) ------
 struct Rgb { int rows = 0, cols = 0; std::vector<uint8_t> px; };
+// The encoder runs beside the device work, one thread per image; jpeg_wait() before a workdir is reported as done.
+struct JpegJobs {
+    std::vector<std::thread> jobs;
+    void add(std::string fn, std::vector<uint8_t> px, int rows, int cols, int channels)
+    {
+        jobs.emplace_back([fn = std::move(fn), px = std::move(px), rows, cols, channels] { write_jpeg(fn, px.data(), rows, cols, channels); });
+    }
+    void wait() { for (auto& t : jobs) if (t.joinable()) t.join(); jobs.clear(); }
+    ~JpegJobs() { wait(); }
+} g_jpeg;
+bool g_batch_mode = false;
 Rgb gray2rgb(const Image8& g)
 {
     Rgb o; o.rows = g.rows; o.cols = g.cols; o.px.resize((size_t)g.rows * g.cols * 3);
@@ -363,12 +374,16 @@ void rect_red(Rgb& im, int x0, int y0, int w, int h, int xoff = 0, int t = 3)   
 }
 Rgb half_size(const Rgb& s)      // cv::resize(.., 0.5, 0.5, INTER_LINEAR) up to rounding
 {
-    Rgb o; o.rows = s.rows / 2; o.cols = s.cols / 2; o.px.resize((size_t)o.rows * o.cols * 3);
+    auto half_len = [](int n) { const int k = n / 2; return (n & 1) ? k + (k & 1) : k; };    // cvRound(n * 0.5): halves go to the even neighbour
+    Rgb o; o.rows = std::max(half_len(s.rows), 1); o.cols = std::max(half_len(s.cols), 1); o.px.resize((size_t)o.rows * o.cols * 3);
     for (int y = 0; y < o.rows; ++y)
         for (int x = 0; x < o.cols; ++x)
             for (int c = 0; c < 3; ++c) {
-                const size_t a = ((size_t)(2 * y) * s.cols + 2 * x) * 3 + c, b = a + (size_t)s.cols * 3;
-                o.px[((size_t)y * o.cols + x) * 3 + c] = (uint8_t)((s.px[a] + s.px[a + 3] + s.px[b] + s.px[b + 3] + 2) >> 2);
+                const int y0 = std::min(2 * y, s.rows - 1), y1 = std::min(2 * y + 1, s.rows - 1);
+                const int x0 = std::min(2 * x, s.cols - 1), x1 = std::min(2 * x + 1, s.cols - 1);
+                const size_t r0 = (size_t)y0 * s.cols, r1 = (size_t)y1 * s.cols;
+                o.px[((size_t)y * o.cols + x) * 3 + c] = (uint8_t)((s.px[(r0 + x0) * 3 + c] + s.px[(r0 + x1) * 3 + c] +
+                                                                    s.px[(r1 + x0) * 3 + c] + s.px[(r1 + x1) * 3 + c] + 2) >> 2);
             }
     return o;
 }
@@ -385,7 +400,7 @@ void save_stereo_jpg(const Env& env)           // wass_stereo.cpp:1911-1926
     rect_red(o, env.roi_right[0], env.roi_right[1], env.roi_right[2], env.roi_right[3], W);
     for (int y = 0; y < H; y += 20)
         for (int x = 0; x < 2 * W; ++x) { uint8_t* p = &o.px[((size_t)y * 2 * W + x) * 3]; p[0] = 255; p[1] = 0; p[2] = 0; }
-    write_jpeg(path(env, "stereo.jpg"), o.px.data(), o.rows, o.cols, 3);
+    g_jpeg.add(path(env, "stereo.jpg"), std::move(o.px), o.rows, o.cols, 3);
 }
 void save_disparity_float_jpg(const std::string& fn, const float* d, int rows, int cols)   // render.hpp:97-136
 {
@@ -394,7 +409,7 @@ void save_disparity_float_jpg(const std::string& fn, const float* d, int rows, i
     std::vector<uint8_t> g((size_t)rows * cols);
     const float sc = mx > mn ? 255.f / (mx - mn) : 0.f;
     for (size_t i = 0; i < g.size(); ++i) g[i] = (uint8_t)((d[i] - mn) * sc);
-    write_jpeg(fn, g.data(), rows, cols, 1);
+    g_jpeg.add(fn, std::move(g), rows, cols, 1);
 }
 // stereo_input.jpg, disparity_stereo_ouput.jpg, disparity_final_scaled.jpg, disparity_coverage.jpg (wass_stereo.cpp:833, 854,
 // 1001-1017) from the final float disparity of the ROI.  (The reference renders disparity_stereo_ouput.jpg before its
@@ -409,7 +424,7 @@ void save_dense_jpgs(const Env& env, const wsg_dense_params& dp, const float* di
             memcpy(&g[(size_t)y * wp + N + off - comp], &env.left_crop.px[(size_t)y * rw], rw);
             memcpy(&g[(size_t)(rh + y) * wp + N], &env.right_crop.px[(size_t)y * rw], rw);
         }
-        write_jpeg(path(env, "stereo_input.jpg"), g.data(), 2 * rh, wp, 1);
+        g_jpeg.add(path(env, "stereo_input.jpg"), std::move(g), 2 * rh, wp, 1);
     }
     save_disparity_float_jpg(path(env, "disparity_stereo_ouput.jpg"), disp_roi, rh, rw);
     const int H = env.right_rect.rows, W = env.right_rect.cols;
@@ -419,8 +434,8 @@ void save_dense_jpgs(const Env& env, const wsg_dense_params& dp, const float* di
     Rgb cov = gray2rgb(env.right_rect);
     for (size_t i = 0; i < full.size(); ++i) if (full[i] > 1.f) cov.px[3 * i + 1] = 100;
     rect_red(cov, env.roi_right[0], env.roi_right[1], env.roi_right[2], env.roi_right[3]);
-    const Rgb h2 = half_size(cov);
-    write_jpeg(path(env, "disparity_coverage.jpg"), h2.px.data(), h2.rows, h2.cols, 3);
+    Rgb h2 = half_size(cov);
+    g_jpeg.add(path(env, "disparity_coverage.jpg"), std::move(h2.px), h2.rows, h2.cols, 3);
 }
 // graph_components.jpg (PovMesh.cpp:222-252, 982-984): the biggest component in green, at half size.  The reference gives
 // every other component its own palette colour; the component labels stay on the device here, so all of them are drawn red.
@@ -429,8 +444,8 @@ void save_components_jpg(const Env& env, const std::vector<uint8_t>& before, con
     Rgb im; im.rows = h; im.cols = w; im.px.assign((size_t)w * h * 3, 0);
     for (size_t i = 0; i < before.size(); ++i)
         if (after[i]) im.px[3 * i + 1] = 255; else if (before[i]) im.px[3 * i] = 255;
-    const Rgb h2 = half_size(im);
-    write_jpeg(path(env, "graph_components.jpg"), h2.px.data(), h2.rows, h2.cols, 3);
+    Rgb h2 = half_size(im);
+    g_jpeg.add(path(env, "graph_components.jpg"), std::move(h2.px), h2.rows, h2.cols, 3);
 }
 
 #define WSG_CHECK(call) do { if ((call) != WSG_OK) throw std::runtime_error(std::string(#call) + ": " + wsg_last_error(h)); } while (0)
@@ -667,6 +682,7 @@ static int stage_after_dense(Env& env, const Config& cfg, wsg_handle* h, const w
         }
         if (ok) for (int i = 0; i < 4; ++i) plane_out[i] = plane[i];
         LOG_SCOPE("wass_stereo");
+        if (!g_batch_mode) g_jpeg.wait();          // (batch mode: joined once per batch, the encoders run beside the next frames)
         env.timer.stop();
         std::cout << "[P|100|100]" << std::endl;
         show_time_stats(env.timer);
@@ -696,6 +712,7 @@ struct Prefetched { Image8 img0, img1; bool ok0 = false, ok1 = false; };
 
 static int run_batch(int argc, char* argv[])
 {
+    g_batch_mode = true;
     int B = 8, ranks = 1, rank = 0;
     std::string planes_out, id_file, cfg_file, list_file;
     std::vector<std::string> all;
@@ -805,6 +822,7 @@ static int run_batch(int argc, char* argv[])
             if (logs[b]) { logs[b]->close(); delete logs[b]; }
         }
         g_logfile = nullptr;
+        g_jpeg.wait();
         if (loader.joinable()) loader.join();
         cur.swap(nxt);
     }
