@@ -272,6 +272,12 @@ typedef struct wsg_refine_params {
 } wsg_refine_params;
 void wsg_refine_params_default(wsg_refine_params* p);
 int wsg_mesh_refine_plane(wsg_handle* h, const wsg_refine_params* p, double plane[4], unsigned long long* n_inliers);
+/* The points main() dumps to plane_refinement_inliers.xyz before the refinement (wass_stereo.cpp:2077-2085): every
+ * `every`-th (10 there) point that passes refine_plane's inlier test (PovMesh.cpp:596-618), in grid scan order, x y z as
+ * doubles.  Selected on the device (flags + scan + scatter): ~1 MB comes back instead of the whole 120 MB mesh.
+ * n_points = points written; n_inliers (optional) = all inliers. */
+int wsg_mesh_refine_inliers(wsg_handle* h, const wsg_refine_params* p, int every, double* xyz, size_t capacity_points,
+                            unsigned long long* n_points, unsigned long long* n_inliers);
 /* PovMesh::RT_from_plane, PovMesh.cpp:1044-1074 (host arithmetic) */
 void wsg_rt_from_plane(const double plane[4], double R[9], double T[3], double Rinv[9], double Tinv[3]);
 /* PovMesh::save_as_xyz_compressed, PovMesh.cpp:377-460: the exact bytes of mesh_cam.xyzC into dst. */

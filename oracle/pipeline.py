@@ -708,6 +708,22 @@ def refine_plane(valid, p3d, xmin=-9999.0, xmax=9999.0, ymin=-9999.0, ymax=9999.
     return np.array([n[0], n[1], n[2], d]), int(m.sum())
 
 
+def refinement_inlier_samples(valid, p3d, every=10, xmin=-9999.0, xmax=9999.0, ymin=-9999.0, ymax=9999.0, max_distance=70.0,
+                              central_third=False):
+    """The points main() writes to plane_refinement_inliers.xyz (wass_stereo.cpp:2077-2085): every `every`-th point passing
+    refine_plane's inlier test (PovMesh.cpp:596-618), in grid scan order.  Returns (points[n][3], n_inliers)."""
+    H, W = valid.shape
+    umin, umax = (W // 4, W * 3 // 4) if central_third else (0, W - 1)
+    vmin, vmax = (H // 4, H * 2 // 3) if central_third else (0, H - 1)
+    sel = np.zeros_like(valid)
+    sel[vmin:vmax + 1, umin:umax + 1] = True
+    P = p3d
+    dist = np.sqrt(P[..., 0] * P[..., 0] + P[..., 1] * P[..., 1] + P[..., 2] * P[..., 2])
+    m = valid & sel & (P[..., 0] > xmin) & (P[..., 0] < xmax) & (P[..., 1] > ymin) & (P[..., 1] < ymax) & (dist < max_distance)
+    pts = P[m]                       # boolean indexing walks the grid in scan order
+    return pts[::every].copy(), int(m.sum())
+
+
 def rt_from_plane(a, b, c, d):
     """PovMesh.cpp:1044-1074"""
     q = (1 - c) / (a * a + b * b)

@@ -144,6 +144,12 @@ def test_mesh_ops_match_oracle(handle):
     ref_v2 = op.crop_plane(ref_v, p3d, rplane, 0.05)
     v2, _, _ = handle.mesh_download()
     assert nl == ref_v2.sum() and np.array_equal(v2, ref_v2)
+    # the sample main() dumps to plane_refinement_inliers.xyz, selected on the device
+    for every, ct in ((10, False), (1, False), (7, True)):
+        rp = capi.refine_params(PLANE_USE_CENTRAL_THIRD_ONLY=int(ct))
+        smp, nin0 = handle.mesh_refine_inliers(rp, every)
+        rsmp, rnin0 = op.refinement_inlier_samples(ref_v2, p3d, every, central_third=ct)
+        assert nin0 == rnin0 and smp.shape == rsmp.shape and np.array_equal(smp, rsmp)
     plane2, nin = handle.mesh_refine_plane()
     rplane2, rnin = op.refine_plane(ref_v2, p3d)
     assert nin == rnin and np.allclose(plane2, rplane2, rtol=1e-6, atol=1e-9)

@@ -157,6 +157,7 @@ def load():
     lib.wsg_ransac_draw.argtypes = [ci, ci, ci, vp]
     lib.wsg_mesh_crop_plane.argtypes = [vp, dp, ctypes.c_double, u64p]
     lib.wsg_mesh_refine_plane.argtypes = [vp, ctypes.POINTER(RefineParams), dp, u64p]
+    lib.wsg_mesh_refine_inliers.argtypes = [vp, ctypes.POINTER(RefineParams), ci, vp, sz, u64p, u64p]
     lib.wsg_rt_from_plane.argtypes = [dp, dp, dp, dp, dp]
     lib.wsg_rt_from_plane.restype = None
     lib.wsg_mesh_export_xyzc.argtypes = [vp, dp, vp, sz, ctypes.POINTER(sz)]
@@ -562,6 +563,15 @@ class Handle:
         n = ctypes.c_ulonglong()
         self._ck(self.lib.wsg_mesh_refine_plane(self.h, ctypes.byref(p), plane, ctypes.byref(n)))
         return np.array(list(plane)), n.value
+
+    def mesh_refine_inliers(self, params=None, every=10):
+        """Every `every`-th refinement inlier in grid scan order (plane_refinement_inliers.xyz): (points[n][3], n_inliers)."""
+        p = params or refine_params()
+        W, H, _ = self.mesh_size()
+        out = np.empty(((W * H + every - 1) // every, 3), np.float64)
+        n, nin = ctypes.c_ulonglong(), ctypes.c_ulonglong()
+        self._ck(self.lib.wsg_mesh_refine_inliers(self.h, ctypes.byref(p), every, out.ctypes.data, out.shape[0], ctypes.byref(n), ctypes.byref(nin)))
+        return out[:n.value].copy(), nin.value
 
     def mesh_export_xyzc(self, plane, out=None):
         """Bytes of mesh_cam.xyzC.  `out`: optional reusable uint8 destination of at least 148 + 6*W*H bytes (e.g. a numpy

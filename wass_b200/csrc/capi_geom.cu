@@ -615,17 +615,50 @@ int wsg_mesh_crop_plane(wsg_handle* h, const double plane[4], double threshold, 
     return WSG_OK;
 }
 
+static RefineArgs refine_args(const wsg_refine_params* p, int W, int H)
+{
+    RefineArgs a;
+    a.xmin = p->PLANE_REFINE_XMIN; a.xmax = p->PLANE_REFINE_XMAX; a.ymin = p->PLANE_REFINE_YMIN; a.ymax = p->PLANE_REFINE_YMAX;
+    a.maxdist = p->PLANE_REFINEMENT_MAX_DISTANCE; a.weight_by_distance = p->PLANE_WEIGHT_PROPORTIONAL_TO_DISTANCE;
+    const bool ct = p->PLANE_USE_CENTRAL_THIRD_ONLY != 0;
+    a.umin = ct ? W / 4 : 0; a.umax = ct ? W * 3 / 4 : W - 1; a.vmin = ct ? H / 4 : 0; a.vmax = ct ? H * 2 / 3 : H - 1;
+    return a;
+}
+
+int wsg_mesh_refine_inliers(wsg_handle* h, const wsg_refine_params* p, int every, double* xyz, size_t capacity_points, unsigned long long* n_points,
+                            unsigned long long* n_inliers)
+{
+    int rc = need_mesh(h);
+    if (rc) return rc;
+    if (!p || !xyz || !n_points || every < 1) return WSG_ERR_INVALID_ARG;
+    const int n = h->mesh_w * h->mesh_h;
+    const size_t cub_bytes = compact_cub_bytes(n), nmax = ((size_t)n + every - 1) / every;
+    if ((rc = ensure(h, h->m_scratch, (size_t)n * 8 + cub_bytes + 512))) return rc;
+    if ((rc = ensure(h, h->m_out, nmax * 24 + 16))) return rc;
+    char* base = (char*)h->m_scratch.p;
+    unsigned long long nin = 0;
+    StageTimer t(h, WSG_STAGE_MESH, 3);
+    if (mesh_refine_sample(mesh_view(h), refine_args(p, h->mesh_w, h->mesh_h), (unsigned)every, (double*)h->m_out.p, (unsigned*)(base + 256),
+                           base + 256 + (size_t)n * 8, cub_bytes, &nin, h->stream)) {
+        h->err = "inlier sampling failed"; return WSG_ERR_CUDA;
+    }
+    const size_t np = (size_t)((nin + every - 1) / every);
+    *n_points = np;
+    if (n_inliers) *n_inliers = nin;
+    if (capacity_points < np) { h->err = "destination too small"; return WSG_ERR_INVALID_ARG; }
+    CK(h, cudaMemcpyAsync(xyz, h->m_out.p, np * 24, cudaMemcpyDeviceToHost, h->stream));
+    CK(h, cudaStreamSynchronize(h->stream));
+    CK(h, cudaGetLastError());
+    return WSG_OK;
+}
+
 int wsg_mesh_refine_plane(wsg_handle* h, const wsg_refine_params* p, double plane[4], unsigned long long* n_inliers)
 {
     int rc = need_mesh(h);
     if (rc) return rc;
     if (!p || !plane) return WSG_ERR_INVALID_ARG;
     const int W = h->mesh_w, H = h->mesh_h;
-    RefineArgs a;
-    a.xmin = p->PLANE_REFINE_XMIN; a.xmax = p->PLANE_REFINE_XMAX; a.ymin = p->PLANE_REFINE_YMIN; a.ymax = p->PLANE_REFINE_YMAX;
-    a.maxdist = p->PLANE_REFINEMENT_MAX_DISTANCE; a.weight_by_distance = p->PLANE_WEIGHT_PROPORTIONAL_TO_DISTANCE;
-    const bool ct = p->PLANE_USE_CENTRAL_THIRD_ONLY != 0;
-    a.umin = ct ? W / 4 : 0; a.umax = ct ? W * 3 / 4 : W - 1; a.vmin = ct ? H / 4 : 0; a.vmax = ct ? H * 2 / 3 : H - 1;
+    const RefineArgs a = refine_args(p, W, H);
     MeshView m = mesh_view(h);
     const int nb = refine_blocks(m);
     if ((rc = ensure(h, h->m_scratch, (size_t)nb * 6 * 8))) return rc;

@@ -65,6 +65,8 @@ void launch_plane_minmax(const MeshView& m, const double* R9, const double* T3, 
 int mesh_compact_quantise(const MeshView& m, const double* R9, const double* T3, const double* min3, const double* scale3,
                           uint16_t* out, unsigned* scan_tmp, void* cub_tmp, size_t cub_bytes, unsigned long long* n_host, cudaStream_t st);
 size_t compact_cub_bytes(int n);
+int mesh_refine_sample(const MeshView& m, const RefineArgs& a, unsigned every, double* out /*ceil(n/every) x 3*/, unsigned* scan_tmp, void* cub_tmp,
+                       size_t cub_bytes, unsigned long long* n_inliers, cudaStream_t st);
 int mesh_compact_xyz(const MeshView& m, float* out /*n x 3*/, unsigned* scan_tmp, void* cub_tmp, size_t cub_bytes,
                      unsigned long long* n_host, cudaStream_t st);
 void launch_count_valid(const MeshView& m, unsigned long long* counter, cudaStream_t st);

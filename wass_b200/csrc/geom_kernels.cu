@@ -756,6 +756,42 @@ int mesh_compact_quantise(const MeshView& m, const double* RT, const double* /*T
     quantise_scatter_kernel<<<296, 256, 0, st>>>(m, RT, min3, scale3, scan_tmp + (size_t)m.w * m.h, out);
     return 0;
 }
+// every `every`-th refinement inlier (refine_inlier above) in grid scan order, as doubles: what main() writes to
+// plane_refinement_inliers.xyz (wass_stereo.cpp:2077-2085), selected on the device instead of downloading the mesh
+__global__ void refine_flags_kernel(MeshView m, RefineArgs a, unsigned* flags)
+{
+    const size_t n = (size_t)m.w * m.h;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        double x, y, z, w;
+        flags[i] = refine_inlier(m, a, i, x, y, z, w) ? 1u : 0u;
+    }
+}
+__global__ void refine_sample_scatter_kernel(MeshView m, const unsigned* __restrict__ flags, const unsigned* __restrict__ pos, unsigned every,
+                                             double* __restrict__ out)
+{
+    const size_t n = (size_t)m.w * m.h;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        if (!flags[i] || pos[i] % every) continue;
+        double* o = out + (size_t)(pos[i] / every) * 3;
+        o[0] = m.X[i]; o[1] = m.Y[i]; o[2] = m.Z[i];
+    }
+}
+int mesh_refine_sample(const MeshView& m, const RefineArgs& a, unsigned every, double* out, unsigned* scan_tmp, void* cub_tmp, size_t cub_bytes,
+                       unsigned long long* n_inliers, cudaStream_t st)
+{
+    const int n = m.w * m.h;
+    unsigned* flags = scan_tmp;
+    unsigned* pos = scan_tmp + n;
+    refine_flags_kernel<<<296, 256, 0, st>>>(m, a, flags);
+    cub::DeviceScan::ExclusiveSum(cub_tmp, cub_bytes, flags, pos, n, st);
+    unsigned lastp = 0, lastf = 0;
+    cudaMemcpyAsync(&lastp, pos + n - 1, 4, cudaMemcpyDeviceToHost, st);
+    cudaMemcpyAsync(&lastf, flags + n - 1, 4, cudaMemcpyDeviceToHost, st);
+    refine_sample_scatter_kernel<<<296, 256, 0, st>>>(m, flags, pos, every, out);
+    if (cudaStreamSynchronize(st) != cudaSuccess) return -1;
+    *n_inliers = (unsigned long long)lastp + lastf;
+    return 0;
+}
 int mesh_compact_xyz(const MeshView& m, float* out, unsigned* scan_tmp, void* cub_tmp, size_t cub_bytes,
                      unsigned long long* n_host, cudaStream_t st)
 {

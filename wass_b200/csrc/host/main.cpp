@@ -344,13 +344,15 @@ void show_time_stats(const Timer& t)   // src/wass_stereo/render.hpp:175-191
 
 // ---- diagnostic images (the reference writes them unconditionally through cv::imwrite; content is informative only) ------
 struct Rgb { int rows = 0, cols = 0; std::vector<uint8_t> px; };
-// The encoder runs beside the device work, one thread per image; jpeg_wait() before a workdir is reported as done.
+// Background file writers: the JPEG encoder (one thread per image) and the inlier dump run beside the device work;
+// wait() before a workdir is reported as done.
 struct JpegJobs {
     std::vector<std::thread> jobs;
     void add(std::string fn, std::vector<uint8_t> px, int rows, int cols, int channels)
     {
         jobs.emplace_back([fn = std::move(fn), px = std::move(px), rows, cols, channels] { write_jpeg(fn, px.data(), rows, cols, channels); });
     }
+    template <class F> void run(F&& f) { jobs.emplace_back(std::forward<F>(f)); }       // any other background file writer
     void wait() { for (auto& t : jobs) if (t.joinable()) t.join(); jobs.clear(); }
     ~JpegJobs() { wait(); }
 } g_jpeg;
@@ -617,31 +619,22 @@ static int stage_after_dense(Env& env, const Config& cfg, wsg_handle* h, const w
             rp.PLANE_REFINEMENT_MAX_DISTANCE = cfg.getd("PLANE_REFINEMENT_MAX_DISTANCE");
             rp.PLANE_WEIGHT_PROPORTIONAL_TO_DISTANCE = cfg.getb("PLANE_WEIGHT_PROPORTIONAL_TO_DISTANCE");
             rp.PLANE_USE_CENTRAL_THIRD_ONLY = cfg.getb("PLANE_USE_CENTRAL_THIRD_ONLY");
-            {   // plane_refinement_inliers.xyz: every 10th refinement inlier, in grid scan order (wass_stereo.cpp:2077-2085)
-                const size_t np = (size_t)mw * mh;
-                std::vector<uint8_t> valid(np);
-                std::vector<double> xyz(np * 3);
-                WSG_CHECK(wsg_mesh_download(h, valid.data(), xyz.data(), nullptr));
-                const bool ct = rp.PLANE_USE_CENTRAL_THIRD_ONLY != 0;
-                const int umin = ct ? mw / 4 : 0, umax = ct ? mw * 3 / 4 : mw - 1, vmin = ct ? mh / 4 : 0, vmax = ct ? mh * 2 / 3 : mh - 1;
-                // (same bytes as `ofs << x << " " << y << " " << z << std::endl` -- %g is the stream's default format --
-                // without one flush per line: ~460 000 lines at the benchmark size)
-                std::string txt;
-                txt.reserve(np / 8);
-                char line[128];
-                size_t idx = 0;
-                for (int v = vmin; v <= vmax; ++v)
-                    for (int u = umin; u <= umax; ++u) {
-                        const size_t i = (size_t)v * mw + u;
-                        if (!valid[i]) continue;
-                        const double x = xyz[3 * i], y = xyz[3 * i + 1], z = xyz[3 * i + 2];
-                        if (x > rp.PLANE_REFINE_XMIN && x < rp.PLANE_REFINE_XMAX && y > rp.PLANE_REFINE_YMIN && y < rp.PLANE_REFINE_YMAX &&
-                            sqrt(x * x + y * y + z * z) < rp.PLANE_REFINEMENT_MAX_DISTANCE) {
-                            if (idx % 10 == 0) txt.append(line, (size_t)snprintf(line, sizeof line, "%g %g %g\n", x, y, z));
-                            ++idx;
-                        }
-                    }
-                write_file(path(env, "plane_refinement_inliers.xyz"), txt.data(), txt.size());
+            {   // plane_refinement_inliers.xyz: every 10th refinement inlier, in grid scan order (wass_stereo.cpp:2077-2085),
+                // picked on the device.  Same bytes as `ofs << x << " " << y << " " << z << std::endl` (%g is the stream's
+                // default format) without one flush per line: ~46 000 lines at the benchmark size.
+                std::vector<double> pts(((size_t)mw * mh + 9) / 10 * 3);
+                unsigned long long npts = 0;
+                WSG_CHECK(wsg_mesh_refine_inliers(h, &rp, 10, pts.data(), pts.size() / 3, &npts, nullptr));
+                // (glibc spends ~0.7 us per %g: 0.1 s per frame, more than the whole device side -- formatted and written on
+                // a worker thread, joined with the JPEG encoders before the workdir is reported done)
+                g_jpeg.run([fn = path(env, "plane_refinement_inliers.xyz"), pts = std::move(pts), npts] {
+                    std::string txt;
+                    txt.reserve((size_t)npts * 40);
+                    char line[128];
+                    for (size_t i = 0; i < (size_t)npts; ++i)
+                        txt.append(line, (size_t)snprintf(line, sizeof line, "%g %g %g\n", pts[3 * i], pts[3 * i + 1], pts[3 * i + 2]));
+                    write_file(fn, txt.data(), txt.size());
+                });
             }
             unsigned long long nin = 0;
             WSG_CHECK(wsg_mesh_refine_plane(h, &rp, plane, &nin));
