@@ -3,7 +3,7 @@
 
 Metric (BASELINE.json): Mdisparities/s (output disparity pixels W*H per second) on
 2448x2048 pairs with 256 disparities, full 8-path SGM (cv::StereoSGBM MODE_HH arithmetic),
-WASS default matcher parameters.  One "step" = one BATCH of rectified stereo pairs (--batch, default 8 per GPU) through the dense matcher
+WASS default matcher parameters.  One "step" = one BATCH of rectified stereo pairs (--batch, default 16 per GPU) through the dense matcher
 (prefilter -> cost volume -> 8-path aggregation -> WTA/LR/sub-pixel -> 3x3 median): one wsg_sgbm_compute_batch call.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
@@ -14,6 +14,9 @@ rank with no data-path collective (weak scaling).  Prints ONE JSON line on rank 
 import argparse
 import json
 import os
+
+# rank 0 prints ONE JSON line on stdout: NCCL's own "NCCL version ..." banner (NCCL_DEBUG=VERSION on some boxes) goes to stderr
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
 import subprocess
 import sys
 import threading

@@ -11,6 +11,8 @@ calibrated frames are cycled.  Prints one JSON line on rank 0.  A secondary figu
 import argparse
 import json
 import os
+
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")     # keep stdout to the one JSON line
 import sys
 import time
 import numpy as np

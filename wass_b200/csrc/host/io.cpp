@@ -94,6 +94,16 @@ bool save_matrix_txt(const std::string& path, const Mat& m)
 // ---- PNG ------------------------------------------------------------------------------------------
 static uint32_t be32(const unsigned char* p) { return ((uint32_t)p[0] << 24) | ((uint32_t)p[1] << 16) | ((uint32_t)p[2] << 8) | p[3]; }
 
+// RGB -> grey as cv::imread(IMREAD_GRAYSCALE) gets it for PNG files: not cv::cvtColor but libpng's own
+// png_set_rgb_to_gray(1, 0.299, 0.587) (modules/imgcodecs/src/grfmt_png.cpp): 15-bit coefficients 9797 / 19234 / 3737,
+// applied to the samples at their own bit depth (pinned against cv2 in tests/test_host_io.py).
+// libpng truncates the 8-bit result ("the historical approach") and rounds the 16-bit one.
+static inline int png_rgb_to_gray(int r, int g, int b, unsigned round = 0)
+{
+    if (r == g && g == b) return r;
+    return (int)(((unsigned)r * 9797u + (unsigned)g * 19234u + (unsigned)b * 3737u + round) >> 15);
+}
+
 bool read_png_gray(const std::string& path, Image8& out, std::string* err)
 {
     std::string s;
@@ -115,14 +125,15 @@ bool read_png_gray(const std::string& path, Image8& out, std::string* err)
         else if (type == "IEND") break;
         pos += 12 + len;
     }
-    if (w <= 0 || h <= 0 || interlace != 0 || (depth != 8 && depth != 16) ) {
-        if (err) *err = path + ": unsupported PNG (need non-interlaced 8/16-bit)";
+    const bool sub_byte = depth == 1 || depth == 2 || depth == 4;       // legal for grey and palette images only
+    if (w <= 0 || h <= 0 || interlace != 0 || (depth != 8 && depth != 16 && !(sub_byte && (ctype == 0 || ctype == 3)))) {
+        if (err) *err = path + ": unsupported PNG (need non-interlaced, 1/2/4/8/16 bits per sample)";
         return false;
     }
     int ch = ctype == 0 ? 1 : ctype == 2 ? 3 : ctype == 3 ? 1 : ctype == 4 ? 2 : ctype == 6 ? 4 : 0;
-    if (!ch || (ctype == 3 && depth != 8)) { if (err) *err = path + ": unsupported PNG colour type"; return false; }
-    const int bpp = ch * depth / 8;
-    const size_t stride = (size_t)w * bpp;
+    if (!ch || (ctype == 3 && depth == 16)) { if (err) *err = path + ": unsupported PNG colour type"; return false; }
+    const int bpp = sub_byte ? 1 : ch * depth / 8;                       // filter distance in bytes
+    const size_t stride = sub_byte ? ((size_t)w * depth + 7) / 8 : (size_t)w * bpp;
     std::vector<unsigned char> raw((stride + 1) * h);
     uLongf rawlen = raw.size();
     if (uncompress(raw.data(), &rawlen, idat.data(), idat.size()) != Z_OK || rawlen != raw.size()) {
@@ -149,18 +160,35 @@ bool read_png_gray(const std::string& path, Image8& out, std::string* err)
         }
     }
     out.rows = h; out.cols = w; out.px.resize((size_t)w * h);
-    const int step = depth / 8;     // 16-bit: keep the high byte (cv::imread 8-bit conversion scales by 1/256)
+    if (sub_byte) {
+        // samples are packed MSB first, rows start on a byte; grey levels are scaled to 8 bits by bit replication
+        // (libpng's expansion, which cv::imread relies on), palette indices go through PLTE
+        const int per = 8 / depth, mask = (1 << depth) - 1, mul = 255 / mask;
+        for (int y = 0; y < h; ++y)
+            for (int x = 0; x < w; ++x) {
+                const int v = (img[stride * y + x / per] >> ((per - 1 - x % per) * depth)) & mask;
+                if (ctype == 0) out.px[(size_t)y * w + x] = (uint8_t)(v * mul);
+                else {
+                    const int k = v * 3;
+                    const int r = k + 2 < (int)plte.size() ? plte[k] : 0, g = k + 2 < (int)plte.size() ? plte[k + 1] : 0, b = k + 2 < (int)plte.size() ? plte[k + 2] : 0;
+                    out.px[(size_t)y * w + x] = (uint8_t)png_rgb_to_gray(r, g, b);
+                }
+            }
+        return true;
+    }
+    const int step = depth / 8;     // 16-bit samples are big-endian; the 8-bit result keeps the high byte (libpng's strip_16)
     for (size_t i = 0; i < (size_t)w * h; ++i) {
         const unsigned char* p = img.data() + i * bpp;
         if (ctype == 0 || ctype == 4) out.px[i] = p[0];
         else if (ctype == 3) {
             const int k = p[0] * 3;
             const int r = k + 2 < (int)plte.size() ? plte[k] : 0, g = k + 2 < (int)plte.size() ? plte[k + 1] : 0, b = k + 2 < (int)plte.size() ? plte[k + 2] : 0;
-            out.px[i] = (uint8_t)((r * 4899 + g * 9617 + b * 1868 + 8192) >> 14);
+            out.px[i] = (uint8_t)png_rgb_to_gray(r, g, b);
+        } else if (depth == 8) {
+            out.px[i] = (uint8_t)png_rgb_to_gray(p[0], p[1], p[2]);
         } else {
-            // OpenCV BGR2GRAY fixed point: (R*4899 + G*9617 + B*1868 + 2^13) >> 14
-            const int r = p[0], g = p[step], b = p[2 * step];
-            out.px[i] = (uint8_t)((r * 4899 + g * 9617 + b * 1868 + 8192) >> 14);
+            const int r = p[0] << 8 | p[1], g = p[2] << 8 | p[3], b = p[4] << 8 | p[5];
+            out.px[i] = (uint8_t)(png_rgb_to_gray(r, g, b, 16384u) >> 8);
         }
     }
     return true;
