@@ -15,8 +15,16 @@ import argparse
 import json
 import os
 
-# rank 0 prints ONE JSON line on stdout: NCCL's own "NCCL version ..." banner (NCCL_DEBUG=VERSION on some boxes) goes to stderr
-os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+# rank 0 prints ONE JSON line on stdout.  Libraries print there too (NCCL's "NCCL version ..." banner comes through C stdio
+# whatever NCCL_DEBUG_FILE says), so file descriptor 1 is pointed at stderr for the whole run and the JSON line is written to
+# the real stdout at the end (emit()).
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit(line):
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
 import subprocess
 import sys
 import threading
@@ -176,7 +184,7 @@ def run_reference(args, rank):
             "cpu_baseline": {"value": value, "unit": "Mdisp/s", "cores": P, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "Mdisp/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # --------------------------------------------------------------------------------------------------
@@ -414,7 +422,7 @@ def run_ours(args, rank, world):
             assert line["plane_reduction"]["max_abs_err_vs_numpy_nanmean"] < 1e-12 and plane_info["frames"] == int(np.isfinite(allp[:, 0]).sum())
         if cpu is not None:
             line["cpu_baseline"] = cpu
-        print(json.dumps(line), flush=True)
+        emit(line)
         if mism or not same:
             raise SystemExit("PARITY FAILURE: %d of %d pixels differ from cv2 (device==host path: %s)" % (mism, checked, same))
     h.close()

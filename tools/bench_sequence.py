@@ -12,7 +12,8 @@ import argparse
 import json
 import os
 
-os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")     # keep stdout to the one JSON line
+_REAL_STDOUT = os.dup(1)     # keep stdout to the one JSON line: libraries (NCCL banner) print to fd 1 too
+os.dup2(2, 1)
 import sys
 import time
 import numpy as np
@@ -96,7 +97,7 @@ def main():
                 "ms_per_frame_per_gpu": float(dt[0]) * 1e3 / (a.frames / world),
                 "stage_ms_host_clock": stages, "points_per_frame": int(np.mean([r.n_points for r in res])),
                 "planes_valid": int(np.sum(~np.isnan(planes[:, 0]))), "mean_plane": [float(v) for v in mean]}
-        print(json.dumps(line), flush=True)
+        os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
     for x in h:
         x.close()
     if comm is not None:
