@@ -51,6 +51,9 @@ static constexpr int PROG_INF = 0x3fffffff;
 #ifndef WSG_SW_NS2
 #define WSG_SW_NS2 6
 #endif
+#ifndef WSG_SW_TMA
+#define WSG_SW_TMA 0         // 1: C and S staged through shared memory by TMA bulk copies (two pixels per copy, mbarrier completion)
+#endif                       //    instead of register loads -- measured, not faster; needs -DWSG_SW_NS1=6 to fit
 #ifndef WSG_SW_STAGGER
 #define WSG_SW_STAGGER -1  // extra columns a row lets the row above get ahead before it starts; -1: half the ring's slack
 #endif
@@ -63,7 +66,12 @@ template <int K, int R, int NS, int MODE> struct SweepCfg {
     static constexpr int RING_V = NS * SLOT_V;
     static constexpr int RINGS_V = (R + 1) * RING_V;          // ring r: states of the row above row r; ring R: out of the band
     static constexpr int SCR_V = MODE == 2 ? R * PIX_V : 0;   // per-row WTA scratch
-    static constexpr int SMEM = (RINGS_V + SCR_V) * 16 + 64;  // (+64: the scratch of the last row is read one element beyond)
+    // TMA staging (WSG_SW_TMA): per row and stream two buffers of two pixels; per row two mbarriers (one per buffer)
+    static constexpr int STREAMS = MODE == 0 ? 1 : 2;
+    static constexpr int STG_V = WSG_SW_TMA ? STREAMS * 4 * PIX_V : 0;
+    static constexpr int STGS_V = R * STG_V;
+    static constexpr int MBAR_V = WSG_SW_TMA ? R : 0;         // 16 bytes per row
+    static constexpr int SMEM = (RINGS_V + SCR_V + STGS_V + MBAR_V) * 16 + 64;  // (+64: the scratch of the last row is read one element beyond)
     static constexpr int THREADS = (R + 1) * 32;
     static constexpr int HD = NS - 2 < 4 ? NS - 2 : 4;        // boundary columns the helper polls per round trip
     // A row may run lag = 2 .. NS-2 columns behind the row above (2: it needs column x+1; NS-2: the ring is full).  Rows
@@ -80,6 +88,30 @@ __device__ __forceinline__ void bulk_prefetch_l2(const void* gptr, unsigned byte
 {
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gptr), "r"(bytes) : "memory");
 }
+// TMA bulk copy global -> shared with mbarrier completion, and the mbarrier operations it needs (WSG_SW_TMA)
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(unsigned long long* bar, unsigned parity)
+{
+    unsigned ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void bulk_copy_g2s(void* dst_smem, const void* src, unsigned bytes, unsigned long long* bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst_smem)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
 #ifndef WSG_SW_CA
 #define WSG_SW_CA 2          // pixels the register load of C runs ahead of its use (2..3; the horizontal path uses C(x+1))
 #endif
@@ -255,7 +287,47 @@ template <int K> struct RowState {
     unsigned long long* keys_row; int16_t* d1_row;
     unsigned one, P1p, P2mP1p;
     int l;
+    // WSG_SW_TMA: staging buffers of this row, their mbarriers, the global cursor of the next chunk to fetch
+    uint4* stg; unsigned long long* mbar;
+    const char* tmaC; const char* tmaS; long long tma_step;
+    int off_even, off_odd;                                // uint4 offset inside a chunk of its first / second logical pixel
+    int next_chunk, last_chunk;                           // next chunk to issue; last chunk of the row (W1 / 2)
+    unsigned ph;                                          // phase parity of the waits of this group of four pixels
 };
+
+// (WSG_SW_TMA) lane 0 fetches chunk st.next_chunk -- logical pixels 2c, 2c+1 of both streams -- into buffer c & 1
+template <int K, int MODE> __device__ __forceinline__ void tma_issue(RowState<K>& st)
+{
+    constexpr int PIX_V = K * 32;
+    if (st.next_chunk <= st.last_chunk) {
+        __syncwarp();                                     // every lane is done reading the buffer that is overwritten
+        if (st.l == 0) {
+            const int b = st.next_chunk & 1;
+            constexpr unsigned bytes = 2u * PIX_V * 16u;
+            fence_proxy_async();
+            mbar_expect_tx(st.mbar + b, MODE == 0 ? bytes : 2u * bytes);
+            bulk_copy_g2s(st.stg + b * 2 * PIX_V, st.tmaC, bytes, st.mbar + b);
+            if (MODE != 0) bulk_copy_g2s(st.stg + (4 + b * 2) * PIX_V, st.tmaS, bytes, st.mbar + b);
+        }
+    }
+    st.tmaC += st.tma_step; st.tmaS += st.tma_step;
+    ++st.next_chunk;
+}
+__device__ __forceinline__ void tma_wait(unsigned long long* bar, unsigned parity, int* err)
+{
+    int spins = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        if (++spins > (1 << 22)) { *err = 1; break; }
+    }
+}
+template <int K> __device__ __forceinline__ void lds_set(unsigned (&dst)[4 * K], const uint4* p, int l)
+{
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        const uint4 c = p[k * 32 + l];
+        dst[4 * k] = c.x; dst[4 * k + 1] = c.y; dst[4 * k + 2] = c.z; dst[4 * k + 3] = c.w;
+    }
+}
 
 template <int K> __device__ __forceinline__ void load_set(unsigned (&dst)[4 * K], const uint4* p)
 {
@@ -280,6 +352,26 @@ __device__ __forceinline__ void sweep_step(RowState<K>& st, const SweepArgs& a, 
     unsigned (&vsp)[NR] = st.Vs[U & 1];             // S(x-1)
     unsigned (&vsn)[NR] = st.Vs[(U + 1) & 1];       // S(x), made here
     unsigned v[3][NR], Nd[3][NR];
+#if WSG_SW_TMA
+    {
+        constexpr int PIX_V = K * 32;
+        // C(x+1) sits in chunk (x+1)/2, buffer ((U+1)/2) & 1; an odd U opens a new chunk: wait for its copy
+        if (U & 1) tma_wait(st.mbar + (((U + 1) >> 1) & 1), U == 1 ? st.ph : st.ph ^ 1u, a.err);
+        lds_set<K>(st.Cs[(U + 1) & 3], st.stg + (((U + 1) >> 1) & 1) * 2 * PIX_V + (((U + 1) & 1) ? st.off_odd : st.off_even), l);
+        if (MODE == 0) {
+#pragma unroll
+            for (int j = 0; j < NR; ++j) vsn[j] = Lh[j];
+            if (U & 1) tma_issue<K, MODE>(st);             // MODE 0: the chunk of C(x-1), C(x) is free (both are in registers)
+        } else {
+            unsigned sx[NR];
+            lds_set<K>(sx, st.stg + (4 + ((U >> 1) & 1) * 2) * PIX_V + ((U & 1) ? st.off_odd : st.off_even), l);
+#pragma unroll
+            for (int j = 0; j < NR; ++j) vsn[j] = __viaddmin_u16x2(sx[j], Lh[j], SAT2);
+            if (U & 1) tma_issue<K, MODE>(st);             // S(x) was the last read of chunk x/2: refill its buffer with chunk x/2 + 2
+        }
+        if (U == 3) st.ph ^= 1u;
+    }
+#else
     if (U == 0) {                                   // pixels x+3+AHEAD .. x+6+AHEAD into L2, one TMA prefetch per stream
         if (l == 0) {
             bulk_prefetch_l2(st.pfC, 4u * K * 512u);
@@ -298,6 +390,7 @@ __device__ __forceinline__ void sweep_step(RowState<K>& st, const SweepArgs& a, 
         load_set<K>(st.Ss[(U + WSG_SW_SA) & 1], st.spf);          // S(x+SA)
         st.spf += st.dstep;
     }
+#endif
     if (NDIR == 4) {
         // ---- states of the three directions that come from the row above: columns x-1, x, x+1 of ring r.  Columns -1
         // and W1 exist in the ring as zeros (zero-initialised slot NS-1, and one extra column written by the
@@ -401,6 +494,29 @@ __device__ __forceinline__ void sweep_row(const uint4* __restrict__ C, uint4* __
 #pragma unroll
     for (int k = 0; k < K; ++k) st.padm[k] = ((l * K + k) * 8 >= a.D) ? SAT2 : 0u;
 
+#if WSG_SW_TMA
+    {   // chunk c = logical pixels 2c, 2c+1 of both streams, fetched by one bulk copy per stream into buffer c & 1; chunks 0
+        // and 1 up front, chunk c+2 as soon as chunk c has been read.  A chunk may reach one pixel beyond the row end
+        // (the volumes are readable there).  With flip the pair sits in memory in reverse order.
+        st.stg = smem + Cfg::RINGS_V + Cfg::SCR_V + (size_t)r * Cfg::STG_V;
+        st.mbar = reinterpret_cast<unsigned long long*>(smem + Cfg::RINGS_V + Cfg::SCR_V + Cfg::STGS_V + r);
+        st.off_even = a.flip ? Cfg::PIX_V : 0; st.off_odd = a.flip ? 0 : Cfg::PIX_V;
+        st.last_chunk = W1 / 2; st.next_chunk = 0; st.ph = 0;
+        const long long off0 = ((long long)yp * W1 + (a.flip ? W1 - 2 : 0)) * a.Dp8;
+        st.tmaC = reinterpret_cast<const char*>(C + off0);
+        st.tmaS = reinterpret_cast<const char*>(S + off0);
+        st.tma_step = (a.flip ? -2ll : 2ll) * a.Dp8 * 16;
+        if (l == 0) {
+            mbar_init(st.mbar, 1); mbar_init(st.mbar + 1, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncwarp();
+        tma_issue<K, MODE>(st);
+        tma_issue<K, MODE>(st);
+        tma_wait(st.mbar, 0, a.err);
+        lds_set<K>(st.Cs[0], st.stg + st.off_even, l);
+    }
+#else
     // C(0), C(1), C(2) and S(0), S(1) up front; every step then issues C(x+3) and S(x+2).  The loads are not guarded at the
     // row end: the volumes are readable a few pixels beyond either end.
 #pragma unroll
@@ -409,6 +525,7 @@ __device__ __forceinline__ void sweep_row(const uint4* __restrict__ C, uint4* __
 #pragma unroll
         for (int i = 0; i < WSG_SW_SA; ++i) { load_set<K>(st.Ss[i], st.spf); st.spf += st.dstep; }
     }
+#endif
 #pragma unroll
     for (int j = 0; j < NR; ++j) { st.Vs[0][j] = 0; st.Vs[1][j] = 0; st.Nh[j] = 0; }
     // The horizontal direction runs ONE PIXEL AHEAD of the three directions that come from the row above: its step for
@@ -447,6 +564,13 @@ __device__ __forceinline__ void sweep_row(const uint4* __restrict__ C, uint4* __
         asm volatile("" ::: "memory");
         if (l == 0) *st.prog_me = W1 + 1;
     }
+#if WSG_SW_TMA
+    __syncwarp();
+    if (l == 0) {        // every issued chunk has been waited for: the barriers can be re-initialised by the next ticket
+        asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(smem_u32(st.mbar)) : "memory");
+        asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(smem_u32(st.mbar + 1)) : "memory");
+    }
+#endif
 }
 
 // The helper warp of a band.  PULL: polls the states the previous band's last row published (global memory, L2: a window
