@@ -396,21 +396,53 @@ __device__ __forceinline__ void uf_union(int* L, int a, int b)
 // the reference's tie rule for free and paid for it with one 32-byte sector per label access).  The tie rule -- among
 // components of equal size the reference keeps the one its column-major seed scan meets first, i.e. the one owning the
 // smallest column-major index -- is restored by a tie-break pass that only does work when two roots share the maximum.
-__global__ void ccl_init_kernel(MeshView m, int* L)
+// Two levels: (1) every CCL_TW x CCL_TH tile is labelled on its own in shared memory (union-find on local indices; the root
+// of a tile component is its smallest local index, i.e. its smallest row-major global index, which is what the global
+// labels hold); (2) only the edges that cross tile borders go through the global union-find.  The first version ran every
+// edge of the 5 M point mesh through global atomics (0.97 ms) although nearly all points end up in one component.
+static constexpr int CCL_TW = 64, CCL_TH = 16;
+__global__ void __launch_bounds__(256) ccl_local_kernel(MeshView m, int* L, double zgap)
 {
-    const size_t o = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
-    if (o >= (size_t)m.w * m.h) return;
-    L[o] = m.valid[o] ? (int)o : INT_MAX;
+    __shared__ int sl[CCL_TW * CCL_TH];
+    __shared__ double sz[CCL_TW * CCL_TH];
+    const int u0 = blockIdx.x * CCL_TW, v0 = blockIdx.y * CCL_TH;
+    for (int i = threadIdx.x; i < CCL_TW * CCL_TH; i += blockDim.x) {
+        const int u = u0 + i % CCL_TW, v = v0 + i / CCL_TW;
+        const bool in = u < m.w && v < m.h && m.valid[(size_t)v * m.w + u];
+        sl[i] = in ? i : INT_MAX;
+        sz[i] = in ? m.Z[(size_t)v * m.w + u] : 0.0;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < CCL_TW * CCL_TH; i += blockDim.x) {
+        if (sl[i] == INT_MAX) continue;               // (a valid element's label never becomes INT_MAX)
+        const int x = i % CCL_TW, y = i / CCL_TW;
+        const double z = sz[i];
+        if (x + 1 < CCL_TW && sl[i + 1] != INT_MAX && fabs(z - sz[i + 1]) < zgap) uf_union(sl, i, i + 1);
+        if (y + 1 < CCL_TH && sl[i + CCL_TW] != INT_MAX && fabs(z - sz[i + CCL_TW]) < zgap) uf_union(sl, i, i + CCL_TW);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < CCL_TW * CCL_TH; i += blockDim.x) {
+        const int u = u0 + i % CCL_TW, v = v0 + i / CCL_TW;
+        if (u >= m.w || v >= m.h) continue;
+        int lab = INT_MAX;
+        if (sl[i] != INT_MAX) {
+            const int r = uf_find(sl, i);
+            lab = (v0 + r / CCL_TW) * m.w + u0 + r % CCL_TW;
+        }
+        L[(size_t)v * m.w + u] = lab;
+    }
 }
-__global__ void ccl_merge_kernel(MeshView m, int* L, double zgap)
+__global__ void ccl_merge_kernel(MeshView m, int* L, double zgap)      // the edges between tiles
 {
     const int u = blockIdx.x * blockDim.x + threadIdx.x, v = blockIdx.y;
     if (u >= m.w) return;
+    const bool right = u % CCL_TW == CCL_TW - 1 && u + 1 < m.w, down = v % CCL_TH == CCL_TH - 1 && v + 1 < m.h;
+    if (!right && !down) return;
     const size_t o = (size_t)v * m.w + u;
     if (!m.valid[o]) return;
     const double z = m.Z[o];
-    if (u + 1 < m.w && m.valid[o + 1] && fabs(z - m.Z[o + 1]) < zgap) uf_union(L, (int)o, (int)o + 1);
-    if (v + 1 < m.h && m.valid[o + m.w] && fabs(z - m.Z[o + m.w]) < zgap) uf_union(L, (int)o, (int)o + m.w);
+    if (right && m.valid[o + 1] && fabs(z - m.Z[o + 1]) < zgap) uf_union(L, (int)o, (int)o + 1);
+    if (down && m.valid[o + m.w] && fabs(z - m.Z[o + m.w]) < zgap) uf_union(L, (int)o, (int)o + m.w);
 }
 __global__ void ccl_flatten_count_kernel(MeshView m, int* L, unsigned* cnt)
 {
@@ -465,7 +497,7 @@ int mesh_biggest_component(MeshView m, double zgap, int* labels, unsigned long l
     cudaMemsetAsync(scratch + 2, 0xff, 16, st);        // the two minima start at the maximum
     dim3 b(128), g((m.w + 127) / 128, m.h);
     const int nb = (n + 255) / 256;
-    ccl_init_kernel<<<nb, 256, 0, st>>>(m, labels);
+    ccl_local_kernel<<<dim3((m.w + CCL_TW - 1) / CCL_TW, (m.h + CCL_TH - 1) / CCL_TH), 256, 0, st>>>(m, labels, zgap);
     ccl_merge_kernel<<<g, b, 0, st>>>(m, labels, zgap);
     ccl_flatten_count_kernel<<<nb, 256, 0, st>>>(m, labels, cnt);
     ccl_max_kernel<<<nb, 256, 0, st>>>(cnt, n, best);
@@ -505,48 +537,77 @@ void launch_ransac_planes(const MeshView& m, const int* triples, int n, double* 
     ransac_planes_kernel<<<(n + 127) / 128, 128, 0, st>>>(m, triples, n, planes, ok);
 }
 
-static constexpr int RH = 16;   // hypotheses scored per pass over the points: their planes and counters live in registers
+static constexpr int RHMAX = 768;    // hypotheses per pass over the points: planes as double4 + float4 and counters in shared memory (39 KB)
+static constexpr int RPTS = 4;       // points a thread keeps in registers while it walks the planes
 // Inlier counts of all hypotheses (PovMesh.cpp:735-752: |n.p + d| < thr over ALL slots, fp64, in the reference's operation
-// order).  A thread keeps two points in registers and walks the RH planes of a pass (broadcast shared-memory loads), counting
-// in RH registers; the counters meet in a warp shuffle reduction and one shared atomic per warp and hypothesis at the end of
-// the pass (the first version balloted and issued a shared atomic per warp, point and hypothesis: 1.8 ms at 5 M points x 400).
+// order; the file is compiled without FMA contraction).  Scoring 400 planes against 5 M points in fp64 is bound by the FP64
+// pipe (seven operations per point and plane: 1.5 ms), so the verdict is SCREENED in fp32 first: |dist32 - dist64| is bounded
+// by eps = 2^-20 (|x| + |y| + |z| + max|d| + thr + 1) (four roundings and four conversions of at most 2^-24 relative each, on terms bounded
+// by that sum since |n| = 1 -- a 4x margin), so dist32 < thr - eps is an inlier and dist32 > thr + eps is not, exactly as
+// in fp64; only the points inside the band (a few in 10^4) and NaNs take the fp64 expression.  A thread holds RPTS points
+// in registers and walks ALL planes (broadcast shared-memory loads); the four verdicts are added, one REDUX.SUM folds the
+// warp and lane 0 issues one shared atomic per warp and plane.  The points are read once.
 __global__ void __launch_bounds__(256) ransac_count_kernel(MeshView m, const double* __restrict__ planes, const int* __restrict__ ok,
                                                            int n, double thr, unsigned long long* counts)
 {
-    __shared__ __align__(16) double sp[RH * 4];
-    __shared__ unsigned sc[RH];
+    __shared__ __align__(16) double sp[RHMAX * 4];
+    __shared__ __align__(16) float sf[RHMAX * 4];       // a, b, c, d in fp32
+    __shared__ unsigned sc[RHMAX];
+    __shared__ int s_dmax;                              // max |d| of the pass (float bits)
     const size_t npts = (size_t)m.w * m.h;
     const size_t stride = (size_t)gridDim.x * blockDim.x;
-    for (int h0 = 0; h0 < n; h0 += RH) {
-        const int nh = min(RH, n - h0);
+    const int lane = threadIdx.x & 31;
+    const float EPSK = 9.5367431640625e-7f;             // 2^-20
+    const float thr32 = (float)thr;
+    for (int h0 = 0; h0 < n; h0 += RHMAX) {
+        const int nh = min(RHMAX, n - h0);
         __syncthreads();
-        // missing hypotheses of the last pass: a plane no point can be close to
-        for (int i = threadIdx.x; i < RH * 4; i += blockDim.x) sp[i] = i < nh * 4 ? planes[4 * h0 + i] : ((i & 3) == 3 ? 1e300 : 0.0);
-        for (int i = threadIdx.x; i < RH; i += blockDim.x) sc[i] = 0;
+        if (threadIdx.x == 0) s_dmax = 0;
         __syncthreads();
-        unsigned cnt[RH];
-#pragma unroll
-        for (int hh = 0; hh < RH; ++hh) cnt[hh] = 0;
-        for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < npts; i += 2 * stride) {
-            const size_t j = i + stride;
-            const bool v0 = m.valid[i], v1 = j < npts && m.valid[j];
-            if (!v0 && !v1) continue;
-            // an invalid slot becomes a point far from every plane (|d| >= 1e300 is never < thr; NaN planes compare false too)
-            const double x0 = v0 ? m.X[i] : 0, y0 = v0 ? m.Y[i] : 0, z0 = v0 ? m.Z[i] : 0;
-            const double x1 = v1 ? m.X[j] : 0, y1 = v1 ? m.Y[j] : 0, z1 = v1 ? m.Z[j] : 0;
-#pragma unroll
-            for (int hh = 0; hh < RH; ++hh) {
-                const double2 ab = *reinterpret_cast<const double2*>(sp + 4 * hh), cd = *reinterpret_cast<const double2*>(sp + 4 * hh + 2);
-                const double d0 = fabs(ab.x * x0 + ab.y * y0 + cd.x * z0 + cd.y);
-                const double d1 = fabs(ab.x * x1 + ab.y * y1 + cd.x * z1 + cd.y);
-                cnt[hh] += (unsigned)(v0 && d0 < thr) + (unsigned)(v1 && d1 < thr);
-            }
+        for (int i = threadIdx.x; i < nh * 4; i += blockDim.x) { sp[i] = planes[4 * h0 + i]; sf[i] = (float)planes[4 * h0 + i]; }
+        for (int i = threadIdx.x; i < nh; i += blockDim.x) {
+            sc[i] = 0;
+            const float ad = fabsf((float)planes[4 * (h0 + i) + 3]);
+            if (ad == ad && ad < 3e38f) atomicMax(&s_dmax, __float_as_int(ad));      // (NaN / Inf planes go the fp64 way by themselves)
         }
+        __syncthreads();
+        const float eh = EPSK * (__int_as_float(s_dmax) + thr32 + 1.0f);
+        // (the loop bounds are the same for all lanes of a warp: warp-wide reductions inside)
+        for (size_t base = blockIdx.x * (size_t)blockDim.x + (threadIdx.x & ~31); base < npts; base += RPTS * stride) {
+            double x[RPTS], y[RPTS], z[RPTS];
+            float xf[RPTS], yf[RPTS], zf[RPTS], lo[RPTS], hi[RPTS];
+            bool any = false;
 #pragma unroll
-        for (int hh = 0; hh < RH; ++hh) {
-            unsigned c = cnt[hh];
-            for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
-            if ((threadIdx.x & 31) == 0 && c) atomicAdd(&sc[hh], c);
+            for (int k = 0; k < RPTS; ++k) {
+                const size_t j = base + lane + k * stride;
+                const bool v = j < npts && m.valid[j];
+                x[k] = v ? m.X[j] : 0; y[k] = v ? m.Y[j] : 0; z[k] = v ? m.Z[j] : 0;
+                xf[k] = (float)x[k]; yf[k] = (float)y[k]; zf[k] = (float)z[k];
+                const float eps = EPSK * (fabsf(xf[k]) + fabsf(yf[k]) + fabsf(zf[k])) + eh;
+                // |dist32| < lo: inlier for certain; >= hi: certainly not; an invalid slot is neither, whatever the plane
+                lo[k] = v ? thr32 - eps : -1.0f;
+                hi[k] = v ? thr32 + eps : -1.0f;
+                any |= v;
+            }
+            if (!__any_sync(0xffffffffu, any)) continue;
+            for (int hh = 0; hh < nh; ++hh) {
+                const float4 pf = *reinterpret_cast<const float4*>(sf + 4 * hh);
+                unsigned c = 0, ch = 0;
+#pragma unroll
+                for (int k = 0; k < RPTS; ++k) {
+                    const float d32 = fabsf(fmaf(pf.x, xf[k], fmaf(pf.y, yf[k], fmaf(pf.z, zf[k], pf.w))));
+                    c += (unsigned)(d32 < lo[k]);
+                    ch += (unsigned)!(d32 >= hi[k]);          // (NaN counts here: it takes the fp64 way)
+                }
+                if (c != ch) {                          // a point inside the band (or a NaN): the reference's own expression decides
+                    const double2 ab = *reinterpret_cast<const double2*>(sp + 4 * hh), cd = *reinterpret_cast<const double2*>(sp + 4 * hh + 2);
+                    c = 0;
+#pragma unroll
+                    for (int k = 0; k < RPTS; ++k) c += (unsigned)(hi[k] > 0.0f && fabs(ab.x * x[k] + ab.y * y[k] + cd.x * z[k] + cd.y) < thr);
+                }
+                c = __reduce_add_sync(0xffffffffu, c);
+                if (lane == 0 && c) atomicAdd(&sc[hh], c);
+            }
         }
         __syncthreads();
         for (int i = threadIdx.x; i < nh; i += blockDim.x)
