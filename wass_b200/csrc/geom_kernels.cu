@@ -521,7 +521,11 @@ __global__ void ransac_planes_kernel(MeshView m, const int* __restrict__ triples
     if (r >= n) return;
     const int* t = triples + 6 * r;
     const size_t i1 = (size_t)t[1] * m.w + t[0], i2 = (size_t)t[3] * m.w + t[2], i3 = (size_t)t[5] * m.w + t[4];
-    if (!m.valid[i1] || !m.valid[i2] || !m.valid[i3]) { ok[r] = 0; return; }
+    if (!m.valid[i1] || !m.valid[i2] || !m.valid[i3]) {      // (a plane no point is close to: the scorer never looks at ok[])
+        ok[r] = 0;
+        planes[4 * r] = 0; planes[4 * r + 1] = 0; planes[4 * r + 2] = 0; planes[4 * r + 3] = (double)INFINITY;
+        return;
+    }
     const double ax = m.X[i2] - m.X[i1], ay = m.Y[i2] - m.Y[i1], az = m.Z[i2] - m.Z[i1];
     const double bx = m.X[i3] - m.X[i1], by = m.Y[i3] - m.Y[i1], bz = m.Z[i3] - m.Z[i1];
     double nx = ay * bz - az * by, ny = az * bx - ax * bz, nz = ax * by - ay * bx;
@@ -537,16 +541,35 @@ void launch_ransac_planes(const MeshView& m, const int* triples, int n, double* 
     ransac_planes_kernel<<<(n + 127) / 128, 128, 0, st>>>(m, triples, n, planes, ok);
 }
 
-static constexpr int RHMAX = 768;    // hypotheses per pass over the points: planes as double4 + float4 and counters in shared memory (39 KB)
-static constexpr int RPTS = 4;       // points a thread keeps in registers while it walks the planes
+static constexpr int RHMAX = 768;    // hypotheses per pass over the points: planes as double4 + float4 and counters in shared memory (40 KB)
+static constexpr int RPTS = 8;       // points a thread keeps in registers (as floats) while it walks the planes
 // Inlier counts of all hypotheses (PovMesh.cpp:735-752: |n.p + d| < thr over ALL slots, fp64, in the reference's operation
 // order; the file is compiled without FMA contraction).  Scoring 400 planes against 5 M points in fp64 is bound by the FP64
 // pipe (seven operations per point and plane: 1.5 ms), so the verdict is SCREENED in fp32 first: |dist32 - dist64| is bounded
-// by eps = 2^-20 (|x| + |y| + |z| + max|d| + thr + 1) (four roundings and four conversions of at most 2^-24 relative each, on terms bounded
-// by that sum since |n| = 1 -- a 4x margin), so dist32 < thr - eps is an inlier and dist32 > thr + eps is not, exactly as
-// in fp64; only the points inside the band (a few in 10^4) and NaNs take the fp64 expression.  A thread holds RPTS points
-// in registers and walks ALL planes (broadcast shared-memory loads); the four verdicts are added, one REDUX.SUM folds the
-// warp and lane 0 issues one shared atomic per warp and plane.  The points are read once.
+// by eps = 2^-20 (|x| + |y| + |z| + max|d| + thr + 1) (four roundings and four conversions of at most 2^-24 relative each, on
+// terms bounded by that sum since |n| = 1 -- a 3x margin), so dist32 < thr - eps is an inlier and dist32 >= thr + eps is
+// not, exactly as in fp64; only the points inside the band (a few in 10^4) and NaNs take the fp64 expression, on values
+// re-read from memory.  A thread holds RPTS points in registers and walks ALL planes, four per iteration (broadcast
+// shared-memory loads); the counts of two planes share a register (16 bits each: a warp's sum is at most 256), so one
+// REDUX.SUM folds the warp for two planes, and lane 0 issues the shared atomics.  The points are read once.
+__device__ __forceinline__ unsigned ransac_exact4(const MeshView& m, const double* sp4, size_t base, int lane, size_t stride, size_t npts,
+                                                  const float (&hi)[RPTS], double thr)
+{
+    // exact counts of the RPTS points of this thread for FOUR consecutive planes, one byte each
+    unsigned out = 0;
+    for (int q = 0; q < 4; ++q) {
+        const double2 ab = *reinterpret_cast<const double2*>(sp4 + 4 * q), cd = *reinterpret_cast<const double2*>(sp4 + 4 * q + 2);
+        unsigned c = 0;
+#pragma unroll
+        for (int k = 0; k < RPTS; ++k) {
+            if (!(hi[k] > 0.0f)) continue;                // invalid slot
+            const size_t j = base + lane + k * stride;
+            c += (unsigned)(fabs(ab.x * m.X[j] + ab.y * m.Y[j] + cd.x * m.Z[j] + cd.y) < thr);
+        }
+        out |= c << (8 * q);
+    }
+    return out;
+}
 __global__ void __launch_bounds__(256) ransac_count_kernel(MeshView m, const double* __restrict__ planes, const int* __restrict__ ok,
                                                            int n, double thr, unsigned long long* counts)
 {
@@ -560,13 +583,17 @@ __global__ void __launch_bounds__(256) ransac_count_kernel(MeshView m, const dou
     const float EPSK = 9.5367431640625e-7f;             // 2^-20
     const float thr32 = (float)thr;
     for (int h0 = 0; h0 < n; h0 += RHMAX) {
-        const int nh = min(RHMAX, n - h0);
+        const int nh = min(RHMAX, n - h0), nh4 = (nh + 3) & ~3;
         __syncthreads();
         if (threadIdx.x == 0) s_dmax = 0;
         __syncthreads();
-        for (int i = threadIdx.x; i < nh * 4; i += blockDim.x) { sp[i] = planes[4 * h0 + i]; sf[i] = (float)planes[4 * h0 + i]; }
+        // (planes beyond nh in the last group of four: d = +inf, no point is ever close to them)
+        for (int i = threadIdx.x; i < nh4 * 4; i += blockDim.x) {
+            const double v = i < nh * 4 ? planes[4 * h0 + i] : ((i & 3) == 3 ? (double)INFINITY : 0.0);
+            sp[i] = v; sf[i] = (float)v;
+        }
+        for (int i = threadIdx.x; i < nh4; i += blockDim.x) sc[i] = 0;
         for (int i = threadIdx.x; i < nh; i += blockDim.x) {
-            sc[i] = 0;
             const float ad = fabsf((float)planes[4 * (h0 + i) + 3]);
             if (ad == ad && ad < 3e38f) atomicMax(&s_dmax, __float_as_int(ad));      // (NaN / Inf planes go the fp64 way by themselves)
         }
@@ -574,15 +601,13 @@ __global__ void __launch_bounds__(256) ransac_count_kernel(MeshView m, const dou
         const float eh = EPSK * (__int_as_float(s_dmax) + thr32 + 1.0f);
         // (the loop bounds are the same for all lanes of a warp: warp-wide reductions inside)
         for (size_t base = blockIdx.x * (size_t)blockDim.x + (threadIdx.x & ~31); base < npts; base += RPTS * stride) {
-            double x[RPTS], y[RPTS], z[RPTS];
             float xf[RPTS], yf[RPTS], zf[RPTS], lo[RPTS], hi[RPTS];
             bool any = false;
 #pragma unroll
             for (int k = 0; k < RPTS; ++k) {
                 const size_t j = base + lane + k * stride;
                 const bool v = j < npts && m.valid[j];
-                x[k] = v ? m.X[j] : 0; y[k] = v ? m.Y[j] : 0; z[k] = v ? m.Z[j] : 0;
-                xf[k] = (float)x[k]; yf[k] = (float)y[k]; zf[k] = (float)z[k];
+                xf[k] = v ? (float)m.X[j] : 0.f; yf[k] = v ? (float)m.Y[j] : 0.f; zf[k] = v ? (float)m.Z[j] : 0.f;
                 const float eps = EPSK * (fabsf(xf[k]) + fabsf(yf[k]) + fabsf(zf[k])) + eh;
                 // |dist32| < lo: inlier for certain; >= hi: certainly not; an invalid slot is neither, whatever the plane
                 lo[k] = v ? thr32 - eps : -1.0f;
@@ -590,23 +615,34 @@ __global__ void __launch_bounds__(256) ransac_count_kernel(MeshView m, const dou
                 any |= v;
             }
             if (!__any_sync(0xffffffffu, any)) continue;
-            for (int hh = 0; hh < nh; ++hh) {
-                const float4 pf = *reinterpret_cast<const float4*>(sf + 4 * hh);
-                unsigned c = 0, ch = 0;
+            for (int hh = 0; hh < nh4; hh += 4) {
+                unsigned c01 = 0, c23 = 0, h01 = 0, h23 = 0;      // counts below lo / below hi, planes (hh, hh+1) and (hh+2, hh+3)
 #pragma unroll
-                for (int k = 0; k < RPTS; ++k) {
-                    const float d32 = fabsf(fmaf(pf.x, xf[k], fmaf(pf.y, yf[k], fmaf(pf.z, zf[k], pf.w))));
-                    c += (unsigned)(d32 < lo[k]);
-                    ch += (unsigned)!(d32 >= hi[k]);          // (NaN counts here: it takes the fp64 way)
-                }
-                if (c != ch) {                          // a point inside the band (or a NaN): the reference's own expression decides
-                    const double2 ab = *reinterpret_cast<const double2*>(sp + 4 * hh), cd = *reinterpret_cast<const double2*>(sp + 4 * hh + 2);
-                    c = 0;
+                for (int q = 0; q < 4; ++q) {
+                    const float4 pf = *reinterpret_cast<const float4*>(sf + 4 * (hh + q));
+                    const unsigned one = (q & 1) ? 0x10000u : 1u;
+                    unsigned cl = 0, ch = 0;
 #pragma unroll
-                    for (int k = 0; k < RPTS; ++k) c += (unsigned)(hi[k] > 0.0f && fabs(ab.x * x[k] + ab.y * y[k] + cd.x * z[k] + cd.y) < thr);
+                    for (int k = 0; k < RPTS; ++k) {
+                        const float d32 = fabsf(fmaf(pf.x, xf[k], fmaf(pf.y, yf[k], fmaf(pf.z, zf[k], pf.w))));
+                        cl += (d32 < lo[k]) ? one : 0u;
+                        ch += !(d32 >= hi[k]) ? one : 0u;         // (NaN counts here: it takes the fp64 way)
+                    }
+                    if (q < 2) { c01 += cl; h01 += ch; } else { c23 += cl; h23 += ch; }
                 }
-                c = __reduce_add_sync(0xffffffffu, c);
-                if (lane == 0 && c) atomicAdd(&sc[hh], c);
+                if (c01 != h01 || c23 != h23) {          // a point inside the band (or a NaN): the reference's own expression decides
+                    const unsigned e = ransac_exact4(m, sp + 4 * hh, base, lane, stride, npts, hi, thr);
+                    c01 = (e & 0xFFu) | ((e & 0xFF00u) << 8);
+                    c23 = ((e >> 16) & 0xFFu) | ((e >> 24) << 16);
+                }
+                c01 = __reduce_add_sync(0xffffffffu, c01);
+                c23 = __reduce_add_sync(0xffffffffu, c23);
+                if (lane == 0 && (c01 | c23)) {
+                    if (c01 & 0xFFFFu) atomicAdd(&sc[hh], c01 & 0xFFFFu);
+                    if (c01 >> 16) atomicAdd(&sc[hh + 1], c01 >> 16);
+                    if (c23 & 0xFFFFu) atomicAdd(&sc[hh + 2], c23 & 0xFFFFu);
+                    if (c23 >> 16) atomicAdd(&sc[hh + 3], c23 >> 16);
+                }
             }
         }
         __syncthreads();
