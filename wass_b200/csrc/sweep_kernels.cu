@@ -760,6 +760,10 @@ int sweep_rows_per_band(const SgbmPlan& p, int nframes, int workers)
     static int forced = -1;
     if (forced < 0) { const char* e = getenv("WSG_SWEEP_ROWS"); forced = e ? atoi(e) : 0; }
     if (forced > 0) return std::min(std::max(forced, 1), rmax);
+    // One or two frames are a tight wavefront: every row waits for the row above, so a sweep lasts
+    // (2 H + bands x hand-off + W1) columns of one warp's LATENCY per column, which grows with the warps that share an SM.
+    // Measured at 2448x2048x256 (profiles/probe_r2_rows_small_batches.txt): 8 rows beat 15 by 7 % (n = 1) and 5 % (n = 2).
+    if (nframes <= 2 && p.K == 1) return std::min(rmax, 8);
     int best = rmax;
     double best_t = 1e300;
     for (int r = rmax; r >= std::max(rmax - 2, 1); --r) {
