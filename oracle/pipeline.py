@@ -482,6 +482,12 @@ def unrectify(uv, Kold, Rrect, Pnew):
     return np.array([v0 * Kold[0, 0] + Kold[0, 2], v1 * Kold[1, 1] + Kold[1, 2]])
 
 
+def unrectify_homography(uv, Hinv):
+    """wass_stereo.cpp:301-305: (HLi | HRi) * (u, v, 1), cv::Matx product (row sums from the left), then the division."""
+    r = [(Hinv[i, 0] * uv[0] + Hinv[i, 1] * uv[1]) + Hinv[i, 2] * 1.0 for i in range(3)]
+    return np.array([r[0] / r[2], r[1] / r[2]])
+
+
 def triangulate(disparity, calib, left, right, left_mask=None, right_mask=None, min_angle=20.0,
                 bbox=None, discard_burned=True, disparity_compensation=0, dense_scale=1.0, cam_distance=1.0):
     """wass_stereo.cpp:1039-1386.  disparity: float32, full rectified size.  calib: dict with
@@ -518,8 +524,12 @@ def triangulate(disparity, calib, left, right, left_mask=None, right_mask=None, 
             yl = F32(yr)
             if xl < 0 or xl >= rect_cols:
                 continue
-            pi = unrectify((np.float64(xl), np.float64(yl)), K0, R1, P1)
-            qi = unrectify((np.float64(xr), np.float64(yr)), K1, R2, P2)
+            if "HLi" in calib:      # USE_CUSTOM_STEREORECTIFY: through the inverse homographies (wass_stereo.cpp:301-305)
+                pi = unrectify_homography((np.float64(xl), np.float64(yl)), calib["HLi"])
+                qi = unrectify_homography((np.float64(xr), np.float64(yr)), calib["HRi"])
+            else:
+                pi = unrectify((np.float64(xl), np.float64(yl)), K0, R1, P1)
+                qi = unrectify((np.float64(xr), np.float64(yr)), K1, R2, P2)
             skip = False
             if (pi[0] < 1 or pi[0] >= Wl - 1 or pi[1] < 1 or pi[1] >= Hl - 1 or
                     qi[0] < 1 or qi[0] >= Wr - 1 or qi[1] < 1 or qi[1] >= Hr - 1):

@@ -19,6 +19,7 @@
 #pragma once
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
 #include <cstring>
 #include <iostream>
 #include <string>
@@ -28,6 +29,7 @@
 #define CV_8UC1 0
 #define CV_8UC3 16
 #define CV_32FC1 5
+#define CV_16SC1 3
 #define CV_64FC1 6
 #define CV_64F 6
 
@@ -57,6 +59,8 @@ template <typename T, int N> struct Vec : Matx<T, N, 1> {
     Vec(A... a) { T tmp[] = {T(a)...}; for (int i = 0; i < N; ++i) this->val[i] = tmp[i]; }
     T& operator[](int i) { return this->val[i]; }
     const T& operator[](int i) const { return this->val[i]; }
+    template <typename U, typename = typename std::enable_if<!std::is_same<U, T>::value>::type>
+    operator Vec<U, N>() const { Vec<U, N> r; for (int i = 0; i < N; ++i) r[i] = (U)this->val[i]; return r; }
     Vec cross(const Vec& o) const
     {
         static_assert(N == 3, "cross");
@@ -106,7 +110,10 @@ template <typename T> double determinant(const Matx<T, 3, 3>& m)
 }
 
 typedef Vec<double, 2> Vec2d;
+typedef Vec<float, 2> Vec2f;
 typedef Vec<double, 3> Vec3d;
+typedef Vec<double, 4> Vec4d;
+typedef Matx<double, 4, 1> Matx41d;
 typedef Vec<int, 2> Vec2i;
 typedef Vec<unsigned char, 3> Vec3b;
 typedef Matx<double, 3, 3> Matx33d;
@@ -125,7 +132,7 @@ template <typename T, int N> std::ostream& operator<<(std::ostream& o, const Vec
 }
 
 // ---------------------------------------------------------------------------------------------- Mat
-inline int shim_elem_size(int type) { return type == CV_64FC1 ? 8 : type == CV_32FC1 ? 4 : type == CV_8UC3 ? 3 : 1; }
+inline int shim_elem_size(int type) { return type == CV_64FC1 ? 8 : type == CV_32FC1 ? 4 : type == CV_8UC3 ? 3 : type == CV_16SC1 ? 2 : 1; }
 
 class Mat {
 public:
@@ -157,6 +164,21 @@ public:
         data = own.data();
     }
     static Mat zeros(int r, int c, int type) { return Mat(r, c, type); }
+    Mat clone() const { Mat o(rows, cols, mtype); if (data) memcpy(o.data, data, o.own.size()); return o; }
+    Mat t() const { Mat o(cols, rows, CV_64FC1); for (int i = 0; i < rows; ++i) for (int j = 0; j < cols; ++j) o.at<double>(j, i) = at<double>(i, j); return o; }
+    Mat mul(const Mat& b) const      // element-wise product of 8-bit images, saturated like cv::Mat::mul
+    {
+        Mat o(rows, cols, mtype);
+        for (size_t i = 0; i < (size_t)rows * cols; ++i) { const int v = (int)data[i] * (int)b.data[i]; o.data[i] = (unsigned char)(v > 255 ? 255 : v); }
+        return o;
+    }
+    template <typename T, int M, int N, typename = typename std::enable_if<(N > 1)>::type> operator Matx<T, M, N>() const
+    {
+        Matx<T, M, N> r;
+        for (int i = 0; i < M; ++i) for (int j = 0; j < N; ++j) r(i, j) = (T)at<double>(i, j);
+        return r;
+    }
+    template <typename T, int N> operator Vec<T, N>() const { Vec<T, N> r; for (int i = 0; i < N; ++i) r[i] = (T)((const double*)data)[i]; return r; }
     bool empty() const { return data == nullptr || rows * cols == 0; }
     int type() const { return mtype; }
     template <typename T> T& at(int i, int j) { return *(T*)(data + ((size_t)i * cols + j) * sizeof(T)); }
@@ -325,6 +347,50 @@ public:
         return *this;
     }
 };
+
+// ---------------------------------------------------------------------------------------------- Mat arithmetic the
+// triangulation stage of wass_stereo.cpp uses: 3x3 / 3x4 double products, and 8-bit mask images built as
+// `img.clone()*0 + 1`, `mask.mul(1 - aux)`, cv::threshold(..., THRESH_BINARY)
+inline unsigned char shim_sat8(double v) { v = std::nearbyint(v); return (unsigned char)(v < 0 ? 0 : (v > 255 ? 255 : v)); }
+inline Mat operator*(const Mat& A, const Mat& B)
+{
+    Mat r(A.rows, B.cols, CV_64FC1);
+    for (int i = 0; i < A.rows; ++i) for (int j = 0; j < B.cols; ++j) { double s = 0; for (int k = 0; k < A.cols; ++k) s += A.at<double>(i, k) * B.at<double>(k, j); r.at<double>(i, j) = s; }
+    return r;
+}
+inline Mat operator-(const Mat& A) { Mat r = A.clone(); for (size_t i = 0; i < (size_t)A.rows * A.cols; ++i) ((double*)r.data)[i] = -((const double*)A.data)[i]; return r; }
+inline Mat operator*(const Mat& A, double s)
+{
+    Mat r = A.clone();
+    if (A.mtype == CV_64FC1) for (size_t i = 0; i < (size_t)A.rows * A.cols; ++i) ((double*)r.data)[i] *= s;
+    else for (size_t i = 0; i < r.own.size(); ++i) r.data[i] = shim_sat8(A.data[i] * s);
+    return r;
+}
+inline Mat operator+(const Mat& A, double s) { Mat r = A.clone(); for (size_t i = 0; i < r.own.size(); ++i) r.data[i] = shim_sat8(A.data[i] + s); return r; }
+inline Mat operator-(double s, const Mat& A) { Mat r = A.clone(); for (size_t i = 0; i < r.own.size(); ++i) r.data[i] = shim_sat8(s - A.data[i]); return r; }
+enum { THRESH_BINARY = 0, IMREAD_GRAYSCALE = 0 };
+inline double threshold(const Mat& src, Mat& dst, double thresh, double maxval, int)
+{
+    Mat r(src.rows, src.cols, CV_8UC1);
+    for (size_t i = 0; i < (size_t)src.rows * src.cols; ++i) r.data[i] = src.data[i] > thresh ? shim_sat8(maxval) : 0;
+    dst = r;
+    return thresh;
+}
+struct Rect { int x = 0, y = 0, width = 0, height = 0; Rect() {} Rect(int a, int b, int c, int d) : x(a), y(b), width(c), height(d) {} };
+// cv::imread(..., IMREAD_GRAYSCALE) for binary PGM (P5, maxval 255) only: all the checker's mask images need
+inline Mat imread(const std::string& fn, int)
+{
+    FILE* f = fopen(fn.c_str(), "rb");
+    if (!f) return Mat();
+    int w = 0, h = 0, mx = 0;
+    Mat r;
+    if (fscanf(f, "P5 %d %d %d", &w, &h, &mx) == 3 && mx == 255 && fgetc(f) != EOF) {
+        r.create(h, w, CV_8UC1);
+        if (fread(r.data, 1, (size_t)w * h, f) != (size_t)w * h) r = Mat();
+    }
+    fclose(f);
+    return r;
+}
 
 // ---------------------------------------------------------------------------------------------- image IO: not needed by the checker
 inline bool imwrite(const std::string&, const Mat&) { return true; }

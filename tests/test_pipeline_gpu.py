@@ -2,6 +2,7 @@
 float32 disparity: bit-exact.  fp64 points: |rel diff| <= 1e-9 (tolerance stated by SURVEY.md §8d; the
 arithmetic is ordered like the reference, so most points are in fact identical).  .xyzC: +-1 LSB."""
 import ctypes
+import os
 import numpy as np
 import pytest
 
@@ -100,6 +101,40 @@ def test_triangulation_gates(handle):
         assert n == ref["n"] and np.array_equal(valid, ref["valid"])
         if n:
             assert np.abs(p3d - ref["p3d"])[valid].max() <= P3D_RTOL * np.abs(ref["p3d"][valid]).max()
+
+
+_TRI = np.load(os.path.join(os.path.dirname(__file__), "golden", "triang_golden.npz"))
+
+
+@pytest.mark.parametrize("name", [str(n) for n in _TRI["names"]])
+def test_gpu_triangulation_matches_the_reference_itself(handle, name):
+    """The CUDA triangulation against the output of the REFERENCE'S OWN triangulate( StereoMatchEnv& ) on the same inputs
+    (tests/golden/triang_golden.npz, made by oracle/_ref/triang_ref: tests/golden/make_triang_golden.py): every gate, both
+    un-rectification branches, masks, burned areas, DENSE_SCALE / disparity compensation."""
+    from wass_b200 import capi
+    g = lambda k: _TRI[name + "/" + k]
+    kv = {}
+    for line in bytes(g("config")).decode().splitlines():
+        if "=" in line:
+            k, v = line.split("=", 1)
+            kv[k.strip()] = v.strip().strip('"')
+    calib = dict(K0=g("K0"), K1=g("K1"), R=g("R"), T=g("T"), R1=g("R1"), R2=g("R2"), P1=g("P1"), P2=g("P2"),
+                 roi_left=tuple(int(v) for v in g("roiL")), roi_right=tuple(int(v) for v in g("roiR")))
+    if kv.get("USE_CUSTOM_STEREORECTIFY") == "true":
+        calib["HLi"], calib["HRi"] = g("HLi"), g("HRi")
+    comp, camdist = g("scal")
+    tp = capi.tri_params(TRIANG_MIN_ANGLE=float(kv.get("TRIANG_MIN_ANGLE", 20.0)),
+                         DISCARD_BURNED_AREAS=int(kv.get("DISCARD_BURNED_AREAS", "true") == "true"),
+                         disparity_compensation=int(comp), DENSE_SCALE=float(kv.get("DENSE_SCALE", 1.0)), cam_distance=float(camdist),
+                         **{k: float(kv[k]) for k in ("TRIANG_BBOX_TOP", "TRIANG_BBOX_LEFT", "TRIANG_BBOX_RIGHT", "TRIANG_BBOX_BOTTOM") if k in kv})
+    n = handle.triangulate(g("disp"), g("left"), g("right"), calib, tp,
+                           left_mask=g("lmask") if "LEFT_MASK_IMAGE" in kv else None,
+                           right_mask=g("rmask") if "RIGHT_MASK_IMAGE" in kv else None)
+    valid, p3d, grey = handle.mesh_download()
+    ref_valid = g("valid").astype(bool)
+    assert n == int(g("n")[0]) and np.array_equal(valid.astype(bool), ref_valid)
+    assert np.abs(p3d - g("xyz"))[ref_valid].max() <= P3D_RTOL * np.abs(g("xyz")[ref_valid]).max()
+    assert np.array_equal(grey[ref_valid], g("grey")[ref_valid])
 
 
 def _plane_mesh(H, W, seed, holes=0.1):
