@@ -25,11 +25,11 @@ def _chunk(t, d):
     return struct.pack(">I", len(d)) + t + d + struct.pack(">I", zlib.crc32(t + d) & 0xFFFFFFFF)
 
 
-def _png(w, h, depth, ctype, rows, plte=None, filt=0):
-    """rows: list of packed scanline bytes (already at the bit depth); filt: PNG filter type applied as type byte with
-    'None' filtering semantics only when 0 -- other types are produced by cv2.imwrite in the tests below."""
+def _png(w, h, depth, ctype, rows, plte=None, filt=0, interlace=0):
+    """rows: list of packed scanline bytes (already at the bit depth; for interlace=1 the scanlines of the seven Adam7
+    passes in order); filt: PNG filter type byte, only 0 ("None") here -- real filters come from cv2.imwrite below."""
     raw = b"".join(bytes([filt]) + r for r in rows)
-    out = b"\x89PNG\r\n\x1a\n" + _chunk(b"IHDR", struct.pack(">IIBBBBB", w, h, depth, ctype, 0, 0, 0))
+    out = b"\x89PNG\r\n\x1a\n" + _chunk(b"IHDR", struct.pack(">IIBBBBB", w, h, depth, ctype, 0, 0, interlace))
     if plte is not None:
         out += _chunk(b"PLTE", bytes(plte))
     return out + _chunk(b"IDAT", zlib.compress(raw)) + _chunk(b"IEND", b"")
@@ -59,6 +59,36 @@ def test_png_sub_byte_depths_match_cv2(probe, tmp_path, depth, ctype):
     plte = rng.integers(0, 256, 3 << depth).tolist() if ctype == 3 else None
     p = str(tmp_path / "a.png")
     open(p, "wb").write(_png(w, h, depth, ctype, [_pack(r, depth) for r in vals], plte))
+    ref = cv2.imread(p, cv2.IMREAD_GRAYSCALE)
+    assert ref is not None and ref.shape == (h, w)
+    assert np.array_equal(_read(probe, p, tmp_path), ref)
+
+
+ADAM7 = [(0, 0, 8, 8), (4, 0, 8, 8), (0, 4, 4, 8), (2, 0, 4, 4), (0, 2, 2, 4), (1, 0, 2, 2), (0, 1, 1, 2)]
+
+
+@pytest.mark.parametrize("depth,ctype", [(8, 0), (1, 0), (4, 3), (8, 2), (16, 0)])
+@pytest.mark.parametrize("shape", [(11, 37), (3, 2), (1, 1), (20, 9)])
+def test_png_adam7_interlaced_matches_cv2(probe, tmp_path, depth, ctype, shape):
+    rng = np.random.default_rng(depth * 100 + ctype * 10 + shape[0])
+    h, w = shape
+    ch = 3 if ctype == 2 else 1
+    vals = rng.integers(0, 1 << min(depth, 8), (h, w, ch))
+    plte = rng.integers(0, 256, 3 << depth).tolist() if ctype == 3 else None
+    rows = []
+    for x0, y0, dx, dy in ADAM7:
+        sub = vals[y0::dy, x0::dx]
+        if sub.shape[0] == 0 or sub.shape[1] == 0:
+            continue
+        for r in sub:
+            if depth < 8:
+                rows.append(_pack(r[:, 0], depth))
+            elif depth == 8:
+                rows.append(bytes(r.reshape(-1).tolist()))
+            else:
+                rows.append(b"".join(struct.pack(">H", int(v) * 257) for v in r[:, 0]))
+    p = str(tmp_path / "i.png")
+    open(p, "wb").write(_png(w, h, depth, ctype, rows, plte, interlace=1))
     ref = cv2.imread(p, cv2.IMREAD_GRAYSCALE)
     assert ref is not None and ref.shape == (h, w)
     assert np.array_equal(_read(probe, p, tmp_path), ref)

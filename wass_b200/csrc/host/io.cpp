@@ -126,69 +126,79 @@ bool read_png_gray(const std::string& path, Image8& out, std::string* err)
         pos += 12 + len;
     }
     const bool sub_byte = depth == 1 || depth == 2 || depth == 4;       // legal for grey and palette images only
-    if (w <= 0 || h <= 0 || interlace != 0 || (depth != 8 && depth != 16 && !(sub_byte && (ctype == 0 || ctype == 3)))) {
-        if (err) *err = path + ": unsupported PNG (need non-interlaced, 1/2/4/8/16 bits per sample)";
+    if (w <= 0 || h <= 0 || interlace > 1 || (depth != 8 && depth != 16 && !(sub_byte && (ctype == 0 || ctype == 3)))) {
+        if (err) *err = path + ": unsupported PNG (need 1/2/4/8/16 bits per sample, no or Adam7 interlace)";
         return false;
     }
-    int ch = ctype == 0 ? 1 : ctype == 2 ? 3 : ctype == 3 ? 1 : ctype == 4 ? 2 : ctype == 6 ? 4 : 0;
+    const int ch = ctype == 0 ? 1 : ctype == 2 ? 3 : ctype == 3 ? 1 : ctype == 4 ? 2 : ctype == 6 ? 4 : 0;
     if (!ch || (ctype == 3 && depth == 16)) { if (err) *err = path + ": unsupported PNG colour type"; return false; }
     const int bpp = sub_byte ? 1 : ch * depth / 8;                       // filter distance in bytes
-    const size_t stride = sub_byte ? ((size_t)w * depth + 7) / 8 : (size_t)w * bpp;
-    std::vector<unsigned char> raw((stride + 1) * h);
+    auto row_bytes = [&](int pw) { return sub_byte ? ((size_t)pw * depth + 7) / 8 : (size_t)pw * bpp; };
+    // the image is one pass, or the seven passes of Adam7: reduced images on the grids (x0 + i dx, y0 + j dy), each with its
+    // own scanlines and filter history
+    struct Pass { int x0, y0, dx, dy; };
+    static const Pass adam7[7] = {{0, 0, 8, 8}, {4, 0, 8, 8}, {0, 4, 4, 8}, {2, 0, 4, 4}, {0, 2, 2, 4}, {1, 0, 2, 2}, {0, 1, 1, 2}};
+    static const Pass whole[1] = {{0, 0, 1, 1}};
+    const Pass* passes = interlace ? adam7 : whole;
+    const int npass = interlace ? 7 : 1;
+    size_t total = 0;
+    for (int k = 0; k < npass; ++k) {
+        const int pw = (w - passes[k].x0 + passes[k].dx - 1) / passes[k].dx, ph = (h - passes[k].y0 + passes[k].dy - 1) / passes[k].dy;
+        if (pw > 0 && ph > 0) total += (row_bytes(pw) + 1) * ph;
+    }
+    std::vector<unsigned char> raw(total);
     uLongf rawlen = raw.size();
     if (uncompress(raw.data(), &rawlen, idat.data(), idat.size()) != Z_OK || rawlen != raw.size()) {
         if (err) *err = path + ": zlib inflate failed";
         return false;
     }
-    std::vector<unsigned char> img(stride * h);
-    for (int y = 0; y < h; ++y) {
-        const unsigned char* in = raw.data() + (stride + 1) * y;
-        unsigned char* cur = img.data() + stride * y;
-        const unsigned char* up = y ? cur - stride : nullptr;
-        const int ft = in[0];
-        for (size_t x = 0; x < stride; ++x) {
-            const int a = x >= (size_t)bpp ? cur[x - bpp] : 0, b = up ? up[x] : 0, c = (up && x >= (size_t)bpp) ? up[x - bpp] : 0;
-            int v = in[1 + x];
-            switch (ft) {
-                case 1: v += a; break;
-                case 2: v += b; break;
-                case 3: v += (a + b) / 2; break;
-                case 4: { const int p = a + b - c, pa = abs(p - a), pb = abs(p - b), pc = abs(p - c); v += (pa <= pb && pa <= pc) ? a : (pb <= pc ? b : c); break; }
-                default: break;
-            }
-            cur[x] = (unsigned char)v;
+    // 8-bit grey of pixel x of an unfiltered scanline.  Sub-byte samples are packed MSB first; grey levels are scaled to
+    // 8 bits by bit replication (libpng's expansion, which cv::imread relies on), palette indices go through PLTE;
+    // 16-bit samples are big-endian and the 8-bit result keeps the high byte (libpng's strip_16).
+    auto pal = [&](int v) {
+        const int k = v * 3;
+        if (k + 2 >= (int)plte.size()) return 0;
+        return png_rgb_to_gray(plte[k], plte[k + 1], plte[k + 2]);
+    };
+    auto grey_at = [&](const unsigned char* row, int x) -> int {
+        if (sub_byte) {
+            const int per = 8 / depth, mask = (1 << depth) - 1;
+            const int v = (row[x / per] >> ((per - 1 - x % per) * depth)) & mask;
+            return ctype == 0 ? v * (255 / mask) : pal(v);
         }
-    }
-    out.rows = h; out.cols = w; out.px.resize((size_t)w * h);
-    if (sub_byte) {
-        // samples are packed MSB first, rows start on a byte; grey levels are scaled to 8 bits by bit replication
-        // (libpng's expansion, which cv::imread relies on), palette indices go through PLTE
-        const int per = 8 / depth, mask = (1 << depth) - 1, mul = 255 / mask;
-        for (int y = 0; y < h; ++y)
-            for (int x = 0; x < w; ++x) {
-                const int v = (img[stride * y + x / per] >> ((per - 1 - x % per) * depth)) & mask;
-                if (ctype == 0) out.px[(size_t)y * w + x] = (uint8_t)(v * mul);
-                else {
-                    const int k = v * 3;
-                    const int r = k + 2 < (int)plte.size() ? plte[k] : 0, g = k + 2 < (int)plte.size() ? plte[k + 1] : 0, b = k + 2 < (int)plte.size() ? plte[k + 2] : 0;
-                    out.px[(size_t)y * w + x] = (uint8_t)png_rgb_to_gray(r, g, b);
+        const unsigned char* p = row + (size_t)x * bpp;
+        if (ctype == 0 || ctype == 4) return p[0];
+        if (ctype == 3) return pal(p[0]);
+        if (depth == 8) return png_rgb_to_gray(p[0], p[1], p[2]);
+        return png_rgb_to_gray(p[0] << 8 | p[1], p[2] << 8 | p[3], p[4] << 8 | p[5], 16384u) >> 8;
+    };
+    out.rows = h; out.cols = w; out.px.assign((size_t)w * h, 0);
+    const unsigned char* in = raw.data();
+    std::vector<unsigned char> cur, up;
+    for (int k = 0; k < npass; ++k) {
+        const Pass& ps = passes[k];
+        const int pw = (w - ps.x0 + ps.dx - 1) / ps.dx, ph = (h - ps.y0 + ps.dy - 1) / ps.dy;
+        if (pw <= 0 || ph <= 0) continue;
+        const size_t stride = row_bytes(pw);
+        cur.assign(stride, 0); up.assign(stride, 0);
+        for (int y = 0; y < ph; ++y) {
+            const int ft = in[0];
+            for (size_t x = 0; x < stride; ++x) {
+                const int a = x >= (size_t)bpp ? cur[x - bpp] : 0, bb = up[x], c = x >= (size_t)bpp ? up[x - bpp] : 0;
+                int v = in[1 + x];
+                switch (ft) {
+                    case 1: v += a; break;
+                    case 2: v += bb; break;
+                    case 3: v += (a + bb) / 2; break;
+                    case 4: { const int q = a + bb - c, pa = abs(q - a), pb = abs(q - bb), pc = abs(q - c); v += (pa <= pb && pa <= pc) ? a : (pb <= pc ? bb : c); break; }
+                    default: break;
                 }
+                cur[x] = (unsigned char)v;
             }
-        return true;
-    }
-    const int step = depth / 8;     // 16-bit samples are big-endian; the 8-bit result keeps the high byte (libpng's strip_16)
-    for (size_t i = 0; i < (size_t)w * h; ++i) {
-        const unsigned char* p = img.data() + i * bpp;
-        if (ctype == 0 || ctype == 4) out.px[i] = p[0];
-        else if (ctype == 3) {
-            const int k = p[0] * 3;
-            const int r = k + 2 < (int)plte.size() ? plte[k] : 0, g = k + 2 < (int)plte.size() ? plte[k + 1] : 0, b = k + 2 < (int)plte.size() ? plte[k + 2] : 0;
-            out.px[i] = (uint8_t)png_rgb_to_gray(r, g, b);
-        } else if (depth == 8) {
-            out.px[i] = (uint8_t)png_rgb_to_gray(p[0], p[1], p[2]);
-        } else {
-            const int r = p[0] << 8 | p[1], g = p[2] << 8 | p[3], b = p[4] << 8 | p[5];
-            out.px[i] = (uint8_t)(png_rgb_to_gray(r, g, b, 16384u) >> 8);
+            uint8_t* orow = &out.px[(size_t)(ps.y0 + y * ps.dy) * w];
+            for (int x = 0; x < pw; ++x) orow[ps.x0 + x * ps.dx] = (uint8_t)grey_at(cur.data(), x);
+            in += stride + 1;
+            cur.swap(up);          // this row becomes the prior one (the first row of a pass sees zeros)
         }
     }
     return true;

@@ -25,7 +25,7 @@ struct Image8 {         // 8-bit grey
 bool load_matrix_xml(const std::string& path, Mat& out, std::string* err);
 // WASS::save_matrix_txt<double> (src/include/utils.hpp:69-92): "%.16e", one space, rows by '\n', no trailing newline
 bool save_matrix_txt(const std::string& path, const Mat& m);
-// cv::imread(..., IMREAD_GRAYSCALE) for PNG: 8/16-bit grey, grey+alpha, RGB(A), palette -> 8-bit grey
+// cv::imread(..., IMREAD_GRAYSCALE) for PNG: 1/2/4/8/16-bit grey, grey+alpha, RGB(A) 8/16-bit, palette, plain or Adam7-interlaced -> 8-bit grey
 bool read_png_gray(const std::string& path, Image8& out, std::string* err);
 bool write_png_gray(const std::string& path, const Image8& img);
 bool write_file(const std::string& path, const void* data, size_t n);
