@@ -13,9 +13,11 @@
 #include <cstdlib>
 #include <cstring>
 #include <ctime>
+#include <chrono>
 #include <fstream>
 #include <iomanip>
 #include <iostream>
+#include <map>
 #include <sstream>
 #include <stdexcept>
 #include <string>
@@ -146,6 +148,37 @@ Image8 resize_cubic(const Image8& src, int nw, int nh)
     return o;
 }
 
+// WASS_HOST_PROFILE=1: wall time of the host stages of the main thread, summed over the workdirs of the process, on stderr
+struct HostProf {
+    struct Acc { std::map<std::string, double> t; std::vector<std::string> order; bool on = getenv("WASS_HOST_PROFILE") != nullptr; };
+    static Acc& acc() { static Acc a; return a; }
+    const char* name; std::chrono::steady_clock::time_point t0;
+    explicit HostProf(const char* n) : name(n), t0(std::chrono::steady_clock::now()) {}
+    ~HostProf()
+    {
+        Acc& a = acc();
+        if (!a.on) return;
+        if (!a.t.count(name)) a.order.push_back(name);
+        a.t[name] += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    }
+    static void report()
+    {
+        Acc& a = acc();
+        if (!a.on) return;
+        for (const auto& n : a.order) std::cerr << "[host] " << std::setw(28) << std::left << n << a.t[n] << " s" << std::endl;
+    }
+};
+
+// Background file writers: the JPEG encoder (one thread per image) and the inlier dump run beside the device work;
+// wait() before a workdir is reported as done.
+struct JpegJobs {
+    std::vector<std::thread> jobs;
+    template <class F> void run(F&& f) { jobs.emplace_back(std::forward<F>(f)); }       // any other background file writer
+    void wait() { for (auto& t : jobs) if (t.joinable()) t.join(); jobs.clear(); }
+    ~JpegJobs() { wait(); }
+} g_jpeg;
+bool g_batch_mode = false;
+
 bool load_data(Env& env, const Config& cfg)   // wass_stereo.cpp:337-442
 {
     LOG_SCOPE("load_data");
@@ -183,9 +216,9 @@ bool load_data(Env& env, const Config& cfg)   // wass_stereo.cpp:337-442
         LOGI << "original size: " << env.left.cols << "x" << env.left.rows;
         LOGI << "  scaled size: " << nw << "x" << nh;
         LOGI << "        scale: " << scale;
-        if (nw > 0 && nh > 0) {
-            write_png_gray(path(env, "00000000_s.png"), resize_cubic(env.left, (int)nw, (int)nh));
-            write_png_gray(path(env, "00000001_s.png"), resize_cubic(env.right, (int)nw, (int)nh));
+        if (nw > 0 && nh > 0) {      // (resize + PNG deflate: ~20 ms per image, off the main thread)
+            g_jpeg.run([fn = path(env, "00000000_s.png"), img = env.left, nw, nh] { write_png_gray(fn, resize_cubic(img, (int)nw, (int)nh)); });
+            g_jpeg.run([fn = path(env, "00000001_s.png"), img = env.right, nw, nh] { write_png_gray(fn, resize_cubic(img, (int)nw, (int)nh)); });
         }
         Mat k0 = env.intr_left, k1 = env.intr_right;
         for (auto& x : k0.v) x *= scale;
@@ -343,20 +376,8 @@ void show_time_stats(const Timer& t)   // src/wass_stereo/render.hpp:175-191
 }
 
 // ---- diagnostic images (the reference writes them unconditionally through cv::imwrite; content is informative only) ------
+
 struct Rgb { int rows = 0, cols = 0; std::vector<uint8_t> px; };
-// Background file writers: the JPEG encoder (one thread per image) and the inlier dump run beside the device work;
-// wait() before a workdir is reported as done.
-struct JpegJobs {
-    std::vector<std::thread> jobs;
-    void add(std::string fn, std::vector<uint8_t> px, int rows, int cols, int channels)
-    {
-        jobs.emplace_back([fn = std::move(fn), px = std::move(px), rows, cols, channels] { write_jpeg(fn, px.data(), rows, cols, channels); });
-    }
-    template <class F> void run(F&& f) { jobs.emplace_back(std::forward<F>(f)); }       // any other background file writer
-    void wait() { for (auto& t : jobs) if (t.joinable()) t.join(); jobs.clear(); }
-    ~JpegJobs() { wait(); }
-} g_jpeg;
-bool g_batch_mode = false;
 Rgb gray2rgb(const Image8& g)
 {
     Rgb o; o.rows = g.rows; o.cols = g.cols; o.px.resize((size_t)g.rows * g.cols * 3);
@@ -402,7 +423,7 @@ void save_stereo_jpg(const Env& env)           // wass_stereo.cpp:1911-1926
     rect_red(o, env.roi_right[0], env.roi_right[1], env.roi_right[2], env.roi_right[3], W);
     for (int y = 0; y < H; y += 20)
         for (int x = 0; x < 2 * W; ++x) { uint8_t* p = &o.px[((size_t)y * 2 * W + x) * 3]; p[0] = 255; p[1] = 0; p[2] = 0; }
-    g_jpeg.add(path(env, "stereo.jpg"), std::move(o.px), o.rows, o.cols, 3);
+    write_jpeg(path(env, "stereo.jpg"), o.px.data(), o.rows, o.cols, 3);
 }
 void save_disparity_float_jpg(const std::string& fn, const float* d, int rows, int cols)   // render.hpp:97-136
 {
@@ -411,7 +432,7 @@ void save_disparity_float_jpg(const std::string& fn, const float* d, int rows, i
     std::vector<uint8_t> g((size_t)rows * cols);
     const float sc = mx > mn ? 255.f / (mx - mn) : 0.f;
     for (size_t i = 0; i < g.size(); ++i) g[i] = (uint8_t)((d[i] - mn) * sc);
-    g_jpeg.add(fn, std::move(g), rows, cols, 1);
+    write_jpeg(fn, g.data(), rows, cols, 1);
 }
 // stereo_input.jpg, disparity_stereo_ouput.jpg, disparity_final_scaled.jpg, disparity_coverage.jpg (wass_stereo.cpp:833, 854,
 // 1001-1017) from the final float disparity of the ROI.  (The reference renders disparity_stereo_ouput.jpg before its
@@ -426,7 +447,7 @@ void save_dense_jpgs(const Env& env, const wsg_dense_params& dp, const float* di
             memcpy(&g[(size_t)y * wp + N + off - comp], &env.left_crop.px[(size_t)y * rw], rw);
             memcpy(&g[(size_t)(rh + y) * wp + N], &env.right_crop.px[(size_t)y * rw], rw);
         }
-        g_jpeg.add(path(env, "stereo_input.jpg"), std::move(g), 2 * rh, wp, 1);
+        write_jpeg(path(env, "stereo_input.jpg"), g.data(), 2 * rh, wp, 1);
     }
     save_disparity_float_jpg(path(env, "disparity_stereo_ouput.jpg"), disp_roi, rh, rw);
     const int H = env.right_rect.rows, W = env.right_rect.cols;
@@ -437,7 +458,7 @@ void save_dense_jpgs(const Env& env, const wsg_dense_params& dp, const float* di
     for (size_t i = 0; i < full.size(); ++i) if (full[i] > 1.f) cov.px[3 * i + 1] = 100;
     rect_red(cov, env.roi_right[0], env.roi_right[1], env.roi_right[2], env.roi_right[3]);
     Rgb h2 = half_size(cov);
-    g_jpeg.add(path(env, "disparity_coverage.jpg"), std::move(h2.px), h2.rows, h2.cols, 3);
+    write_jpeg(path(env, "disparity_coverage.jpg"), h2.px.data(), h2.rows, h2.cols, 3);
 }
 // graph_components.jpg (PovMesh.cpp:222-252, 982-984): the biggest component in green, at half size.  The reference gives
 // every other component its own palette colour; the component labels stay on the device here, so all of them are drawn red.
@@ -447,7 +468,7 @@ void save_components_jpg(const Env& env, const std::vector<uint8_t>& before, con
     for (size_t i = 0; i < before.size(); ++i)
         if (after[i]) im.px[3 * i + 1] = 255; else if (before[i]) im.px[3 * i] = 255;
     Rgb h2 = half_size(im);
-    g_jpeg.add(path(env, "graph_components.jpg"), std::move(h2.px), h2.rows, h2.cols, 3);
+    write_jpeg(path(env, "graph_components.jpg"), h2.px.data(), h2.rows, h2.cols, 3);
 }
 
 #define WSG_CHECK(call) do { if ((call) != WSG_OK) throw std::runtime_error(std::string(#call) + ": " + wsg_last_error(h)); } while (0)
@@ -480,16 +501,16 @@ static int stage_load_rectify(Env& env, const Config& cfg, wsg_handle* h)
     LOGI << "Reconstructing \"" << env.workdir << "\"";
     env.timer.start();
     env.cam_distance = 1.0;
-    if (!load_data(env, cfg)) return -1;
+    { HostProf hp("load_data"); if (!load_data(env, cfg)) return -1; }
     env.timer.mark("Data load");
     std::cout << "[P|10|100]" << std::endl;
     save_poses(env);
-    if (!rectify(env, cfg, h)) return -1;   // the reference ignores this return value and runs on undefined state
+    { HostProf hp("rectify"); if (!rectify(env, cfg, h)) return -1; }   // the reference ignores this return value and runs on undefined state
     env.timer.mark("Rectification");
     std::cout << "[P|20|100]" << std::endl;
     LOG_SCOPE("wass_stereo");
     save_poses(env);
-    if (cfg.getb("SAVE_DEBUG_IMAGES")) save_stereo_jpg(env);
+    if (cfg.getb("SAVE_DEBUG_IMAGES")) g_jpeg.run([&env] { save_stereo_jpg(env); });      // (reads env: joined before env goes away)
     return 0;
 }
 
@@ -521,7 +542,11 @@ static int stage_after_dense(Env& env, const Config& cfg, wsg_handle* h, const w
 {
     for (int i = 0; i < 4; ++i) plane_out[i] = std::nan("");
     const bool dbg_images = cfg.getb("SAVE_DEBUG_IMAGES");
-    if (dbg_images && disp_roi) save_dense_jpgs(env, dp, disp_roi);
+    if (dbg_images && disp_roi) {
+        const size_t nroi = (size_t)env.right_crop.rows * env.right_crop.cols;
+        g_jpeg.run([&env, dp, d = std::vector<float>(disp_roi, disp_roi + nroi)] { save_dense_jpgs(env, dp, d.data()); });
+    }
+    HostProf hp_all("after dense (total)");
     try {
         // ---- triangulation (wass_stereo.cpp:1039-1386)
         LOG_SCOPE("triangulate");
@@ -557,7 +582,7 @@ static int stage_after_dense(Env& env, const Config& cfg, wsg_handle* h, const w
         const uint8_t* rmp = load_mask("RIGHT_MASK_IMAGE", env.right, rm);
         LOGI << "triangulating disparity map";
         unsigned long long n_pts = 0;
-        WSG_CHECK(wsg_triangulate_from_dense(h, env.left.px.data(), env.right.px.data(), lmp, rmp, &cal, &tp, &n_pts));
+        { HostProf hp("triangulate"); WSG_CHECK(wsg_triangulate_from_dense(h, env.left.px.data(), env.right.px.data(), lmp, rmp, &cal, &tp, &n_pts)); }
         LOGI << "... 100%";
         LOGI << n_pts << " valid points found";
         env.timer.mark("Triangulation");
@@ -567,7 +592,7 @@ static int stage_after_dense(Env& env, const Config& cfg, wsg_handle* h, const w
 
         // ---- outlier removal (wass_stereo.cpp:2046-2060)
         double zgap = 0;
-        WSG_CHECK(wsg_mesh_zgap_percentile(h, cfg.getd("ZGAP_PERCENTILE"), &zgap));
+        { HostProf hp("zgap"); WSG_CHECK(wsg_mesh_zgap_percentile(h, cfg.getd("ZGAP_PERCENTILE"), &zgap)); }
         env.timer.mark("Z-gap stats");
         unsigned long long nleft = 0;
         LOG_SCOPE("cluster");
@@ -579,11 +604,11 @@ static int stage_after_dense(Env& env, const Config& cfg, wsg_handle* h, const w
             valid_before.resize((size_t)cw * ch);
             WSG_CHECK(wsg_mesh_download(h, valid_before.data(), nullptr, nullptr));
         }
-        WSG_CHECK(wsg_mesh_biggest_component(h, zgap, &nleft));
+        { HostProf hp("component"); WSG_CHECK(wsg_mesh_biggest_component(h, zgap, &nleft)); }
         if (dbg_images) {
             valid_after.resize(valid_before.size());
             WSG_CHECK(wsg_mesh_download(h, valid_after.data(), nullptr, nullptr));
-            save_components_jpg(env, valid_before, valid_after, cw, ch);
+            g_jpeg.run([&env, b = std::move(valid_before), a2 = std::move(valid_after), cw, ch] { save_components_jpg(env, b, a2, cw, ch); });
         }
         LOGI << "biggest component size: " << nleft << " (px)";
         env.timer.mark("Outlier removal");
@@ -600,7 +625,7 @@ static int stage_after_dense(Env& env, const Config& cfg, wsg_handle* h, const w
         wsg_ransac_draw(mw, mh, rounds, triples.data());
         double plane[4] = {0, 0, 0, 0};
         int ok = 0; unsigned long long best = 0;
-        if (rounds > 0) WSG_CHECK(wsg_mesh_ransac_plane(h, triples.data(), rounds, cfg.getd("PLANE_RANSAC_THRESHOLD"), plane, &ok, &best));
+        { HostProf hp("ransac"); if (rounds > 0) WSG_CHECK(wsg_mesh_ransac_plane(h, triples.data(), rounds, cfg.getd("PLANE_RANSAC_THRESHOLD"), plane, &ok, &best)); }
         LOG_SCOPE("ransac_find_plane");
         LOGI << rounds << " ransac rounds, " << best << " best inliers";
         LOGI << "ransac plane coeffs: " << plane[0] << " " << plane[1] << " " << plane[2] << " " << plane[3];
@@ -624,7 +649,7 @@ static int stage_after_dense(Env& env, const Config& cfg, wsg_handle* h, const w
                 // default format) without one flush per line: ~46 000 lines at the benchmark size.
                 std::vector<double> pts(((size_t)mw * mh + 9) / 10 * 3);
                 unsigned long long npts = 0;
-                WSG_CHECK(wsg_mesh_refine_inliers(h, &rp, 10, pts.data(), pts.size() / 3, &npts, nullptr));
+                { HostProf hp("refine inliers"); WSG_CHECK(wsg_mesh_refine_inliers(h, &rp, 10, pts.data(), pts.size() / 3, &npts, nullptr)); }
                 // (glibc spends ~0.7 us per %g: 0.1 s per frame, more than the whole device side -- formatted and written on
                 // a worker thread, joined with the JPEG encoders before the workdir is reported done)
                 g_jpeg.run([fn = path(env, "plane_refinement_inliers.xyz"), pts = std::move(pts), npts] {
@@ -637,7 +662,7 @@ static int stage_after_dense(Env& env, const Config& cfg, wsg_handle* h, const w
                 });
             }
             unsigned long long nin = 0;
-            WSG_CHECK(wsg_mesh_refine_plane(h, &rp, plane, &nin));
+            { HostProf hp("refine"); WSG_CHECK(wsg_mesh_refine_plane(h, &rp, plane, &nin)); }
             LOG_SCOPE("refine_plane");
             LOGI << "refinement inliers (after cropping): " << nin;
             LOGI << "estimated plane coeffs: " << plane[0] << " " << plane[1] << " " << plane[2] << " " << plane[3];
@@ -660,13 +685,15 @@ static int stage_after_dense(Env& env, const Config& cfg, wsg_handle* h, const w
         {
             int w2 = 0, h2 = 0; unsigned long long nv = 0;
             WSG_CHECK(wsg_mesh_size(h, &w2, &h2, &nv));
-            std::vector<char> buf(256 + (size_t)nv * 12);
+            HostProf hp_exp("export (total)");
+            static std::vector<char> buf;            // reused across the workdirs of a batch (zero-filling 56 MB per frame was 20 ms)
+            if (buf.size() < 256 + (size_t)nv * 12) buf.resize(256 + (size_t)nv * 12);
             size_t nb = 0;
             if (cfg.getb("SAVE_COMPRESSED")) {
                 LOG_SCOPE("save_as_xyz_compressed");
                 LOGI << "saving mesh as compressed xyz file...";
-                WSG_CHECK(wsg_mesh_export_xyzc(h, plane, buf.data(), buf.size(), &nb));
-                if (!write_file(path(env, "mesh_cam.xyzC"), buf.data(), nb)) { LOGE << "unable to save mesh data"; return -1; }
+                { HostProf hp("export xyzC (device + copy)"); WSG_CHECK(wsg_mesh_export_xyzc(h, plane, buf.data(), buf.size(), &nb)); }
+                { HostProf hp("write mesh_cam.xyzC"); if (!write_file(path(env, "mesh_cam.xyzC"), buf.data(), nb)) { LOGE << "unable to save mesh data"; return -1; } }
                 LOGI << "total data size: " << (double)nb / 1e6 << " MB";
             } else {
                 WSG_CHECK(wsg_mesh_export_xyzbin(h, buf.data(), buf.size(), &nb));
@@ -766,6 +793,7 @@ static int run_batch(int argc, char* argv[])
         std::thread loader;
         if (g1 < mine.size()) loader = std::thread(prefetch, g1, &nxt);
         std::vector<Env> envs(g1 - g0);
+        struct JoinJobs { ~JoinJobs() { g_jpeg.wait(); } } join_before_envs_go;      // background jobs read the Envs
         std::vector<std::ofstream*> logs(g1 - g0, nullptr);
         std::vector<int> state(g1 - g0, 0);                      // 0 ready for the matcher, -1 failed
         for (size_t j = g0; j < g1; ++j) {
@@ -778,7 +806,7 @@ static int run_batch(int argc, char* argv[])
             LOGI << "Loading configuration file " << cfg_file;
             if (save_configuration(cfg, path(env, "stereo_config.txt")) != 0) LOGE << "Unable to save stereo configuration file";
             if (cur[j - g0].ok0 && cur[j - g0].ok1) { env.pre_left = &cur[j - g0].img0; env.pre_right = &cur[j - g0].img1; }
-            if (stage_load_rectify(env, cfg, h) != 0) state[j - g0] = -1;
+            { HostProf hp("load + rectify (total)"); if (stage_load_rectify(env, cfg, h) != 0) state[j - g0] = -1; }
             env.pre_left = env.pre_right = nullptr;
         }
         // frames whose crops have the same size go through the matcher together (one sequence = one size in practice)
@@ -795,8 +823,12 @@ static int run_batch(int argc, char* argv[])
             std::vector<std::vector<float>> droi(dbg_images ? grp.size() : 0);
             std::vector<float*> dptr;
             for (auto& v : droi) { v.resize((size_t)envs[a0].right_crop.rows * envs[a0].right_crop.cols); dptr.push_back(v.data()); }
-            const int rcode = wsg_dense_stereo_batch(h, (int)grp.size(), lc.data(), rc.data(), envs[a0].right_crop.rows, envs[a0].right_crop.cols,
-                                                     envs[a0].right_crop.cols, &dp, dbg_images ? dptr.data() : nullptr);
+            int rcode;
+            {
+                HostProf hp_dense("dense batch");
+                rcode = wsg_dense_stereo_batch(h, (int)grp.size(), lc.data(), rc.data(), envs[a0].right_crop.rows, envs[a0].right_crop.cols,
+                                               envs[a0].right_crop.cols, &dp, dbg_images ? dptr.data() : nullptr);
+            }
             for (size_t k = 0; k < grp.size(); ++k) {
                 const size_t b = grp[k];
                 done[b] = 1;
@@ -867,6 +899,7 @@ static int run_batch(int argc, char* argv[])
         }
     }
     wsg_destroy(h);
+    HostProf::report();
     return failed ? -1 : 0;
 }
 
@@ -885,6 +918,7 @@ int main(int argc, char* argv[])
     if (argc > 1 && std::string("--batch") == argv[1]) return run_batch(argc, argv);
     if (argc != 3 && argc != 4) { std::cerr << "Invalid arguments" << std::endl; return -1; }
     Env env;
+    struct JoinJobs { ~JoinJobs() { g_jpeg.wait(); } } join_before_env_goes;          // background jobs read env
     env.workdir = argv[2];
     if (!exists(env.workdir)) { std::cerr << "\"" << env.workdir << "\" does not exists, aborting." << std::endl; return -1; }
     g_logfile = new std::ofstream(path(env, "wass_stereo_log.txt").c_str());
