@@ -17,6 +17,7 @@ mkdir -p "$HERE/_ref"
 awk '/^#ifdef WASS_ENABLE_OPTFLOW/ {skip=1} /^#endif/ {if (skip) {skip=0; next}} !skip && /^INCFG_REQUIRE/' \
     "$REF/src/wass_stereo/wass_stereo.cpp" "$REF/src/wass_stereo/PovMesh.cpp" > "$HERE/_ref/keys.inc"
 g++ -O1 -std=c++14 -I"$REF/ext/incfg" -I"$HERE/_ref" "$HERE/incfg_ref_driver.cpp" "$REF/ext/incfg/incfg.cpp" -o "$HERE/_ref/incfg_ref"
+rm -f "$HERE/_ref/keys.inc"         # (cut reference text exists only for the duration of the compile)
 echo "$HERE/_ref/incfg_ref"
 
 # oracle/_ref/povmesh_ref: the reference's OWN mesh stage -- src/wass_stereo/PovMesh.cpp (z-gap percentile, biggest
